@@ -1,0 +1,737 @@
+"""Dreamer-V3 update step as an explicit kernel schedule (no autograd, no torch math).
+
+`DV3Engine.train_step` is the B200 implementation of the reference's
+`sheeprl/algos/dreamer_v3/dreamer_v3.py:48-357` (`train`).  Every arithmetic operation is a call into
+the C-ABI CUDA library (`include/b200rl.h`, loaded by `sheeprl_b200.lib.CudaOps`): forward, the
+hand-derived backward (SURVEY.md Appendix E is the gradient-flow map it follows), global-norm clip,
+Adam.  PyTorch is used only to own device memory and the CUDA stream.  Because nothing on this path
+allocates, synchronises or branches on device data, the whole step is CUDA-graph capturable
+(`sheeprl_b200.graph`).
+
+Layouts (all fp32, row-major):
+  * replay rows are flattened time-major: row n = t*B + b  (matches `posteriors.reshape(1,-1,Z)` in
+    dreamer_v3.py:203-204), N = T*B;
+  * images are channel-last `[N,H,W,C]` inside the engine (LayerNorm over C is contiguous and the
+    implicit-GEMM K slices are contiguous); the CHW flatten order the reference's weights expect
+    (`nn.Flatten(-3,-1)`, agent.py:90 / `Unflatten(1,(-1,4,4))`, agent.py:201) is restored by a
+    batched transpose at the encoder output / decoder input;
+  * latent states `[z (S*D) | h (R)]` live directly in `traj[0]` so imagination starts in place;
+  * conv weights keep the reference layout: Conv2d `[Cout,Cin,4,4]`, ConvTranspose2d `[Cin,Cout,4,4]`
+    — both are `[C_small_image, C_big_image, ky, kx]` for the three stride-2 kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from sheeprl_b200.params import FlatGroup
+
+ACT_NONE, ACT_SILU = 0, 1
+TWOHOT_LOW, TWOHOT_HIGH = -20.0, 20.0
+
+
+def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int):
+    """Shapes keyed by the reference's state-dict names (built in agent.py:935-1180)."""
+    a, w = cfg.algo, cfg.algo.world_model
+    S, D = w.stochastic_size, w.discrete_size
+    Z, R = S * D, w.recurrent_model.recurrent_state_size
+    L = Z + R
+    du, nh = a.dense_units, a.mlp_layers
+    mult = w.encoder.cnn_channels_multiplier
+    stages = int(round(math.log2(cfg.env.screen_size) - 2))
+    A = int(sum(actions_dim))
+    wm, actor, critic = {}, {}, {}
+
+    def mlp(d, prefix, i, hidden, n_hidden, o):
+        for k in range(n_hidden):
+            d[f"{prefix}{3 * k}.weight"] = (hidden, i if k == 0 else hidden)
+            d[f"{prefix}{3 * k + 1}.weight"] = (hidden,)
+            d[f"{prefix}{3 * k + 1}.bias"] = (hidden,)
+        if o is not None:
+            d[f"{prefix}{3 * n_hidden}.weight"] = (o, hidden)
+            d[f"{prefix}{3 * n_hidden}.bias"] = (o,)
+
+    chans = [in_channels] + [mult * 2 ** i for i in range(stages)]
+    for i in range(stages):
+        p = f"encoder.cnn_encoder.model.0._model.{3 * i}"
+        wm[p + ".weight"] = (chans[i + 1], chans[i], 4, 4)
+        wm[f"encoder.cnn_encoder.model.0._model.{3 * i + 1}.weight"] = (chans[i + 1],)
+        wm[f"encoder.cnn_encoder.model.0._model.{3 * i + 1}.bias"] = (chans[i + 1],)
+    E = chans[-1] * 16
+    dx = w.recurrent_model.dense_units
+    wm["rssm.initial_recurrent_state"] = (R,)
+    wm["rssm.recurrent_model.mlp._model.0.weight"] = (dx, Z + A)
+    wm["rssm.recurrent_model.mlp._model.1.weight"] = (dx,)
+    wm["rssm.recurrent_model.mlp._model.1.bias"] = (dx,)
+    wm["rssm.recurrent_model.rnn.linear.weight"] = (3 * R, R + dx)
+    wm["rssm.recurrent_model.rnn.layer_norm.weight"] = (3 * R,)
+    wm["rssm.recurrent_model.rnn.layer_norm.bias"] = (3 * R,)
+    mlp(wm, "rssm.representation_model._model.", R + E, w.representation_model.hidden_size, 1, Z)
+    mlp(wm, "rssm.transition_model._model.", R, w.transition_model.hidden_size, 1, Z)
+    wm["observation_model.cnn_decoder.model.0.weight"] = (E, L)
+    wm["observation_model.cnn_decoder.model.0.bias"] = (E,)
+    dch = [chans[-1]] + [mult * 2 ** i for i in reversed(range(stages - 1))] + [in_channels]
+    for i in range(stages):
+        p = f"observation_model.cnn_decoder.model.2._model.{3 * i}"
+        wm[p + ".weight"] = (dch[i], dch[i + 1], 4, 4)
+        if i == stages - 1:
+            wm[p + ".bias"] = (dch[i + 1],)
+        else:
+            wm[f"observation_model.cnn_decoder.model.2._model.{3 * i + 1}.weight"] = (dch[i + 1],)
+            wm[f"observation_model.cnn_decoder.model.2._model.{3 * i + 1}.bias"] = (dch[i + 1],)
+    mlp(wm, "reward_model._model.", L, du, nh, w.reward_model.bins)
+    mlp(wm, "continue_model._model.", L, du, nh, 1)
+    mlp(actor, "model._model.", L, du, nh, None)
+    for i, ad in enumerate(actions_dim):
+        actor[f"mlp_heads.{i}.weight"] = (ad, du)
+        actor[f"mlp_heads.{i}.bias"] = (ad,)
+    mlp(critic, "_model.", L, du, nh, a.critic.bins)
+    return wm, actor, critic, dict(chans=chans, dch=dch, E=E, stages=stages)
+
+
+class _MLP:
+    """n_hidden x [Linear(no bias) -> LN -> SiLU] (+ output Linear with bias): forward with saved
+    pre-activations, hand-written backward.  (reference: sheeprl/models/models.py:16-119)"""
+
+    def __init__(self, eng, group: FlatGroup, prefix: str, in_dim: int, hidden: int, n_hidden: int,
+                 out_dim: Optional[int], rows: int, eps: float, tag: str, train: bool):
+        self.eng, self.g, self.prefix = eng, group, prefix
+        self.in_dim, self.hidden, self.n_hidden, self.out_dim, self.eps = in_dim, hidden, n_hidden, out_dim, eps
+        self.rows = rows
+        new = eng._buf
+        self.pre = [new(f"{tag}.pre{i}", rows, hidden) for i in range(n_hidden)]
+        self.act = [new(f"{tag}.act{i}", rows, hidden) for i in range(n_hidden)]
+        self.out = new(f"{tag}.out", rows, out_dim) if out_dim is not None else None
+        if train:
+            self.dact = new(f"{tag}.dact", rows, hidden)
+            self.dpre = new(f"{tag}.dpre", rows, hidden)
+
+    def W(self, i):
+        return self.g.views[f"{self.prefix}{3 * i}.weight"]
+
+    def forward(self, x: torch.Tensor, group: Optional[FlatGroup] = None, M: Optional[int] = None):
+        """x [M,in_dim] view; returns output logits (or last activation)."""
+        ops = self.eng.ops
+        g = group or self.g
+        M = x.shape[0] if M is None else M
+        cur = x
+        for i in range(self.n_hidden):
+            ops.gemm(cur, g.views[f"{self.prefix}{3 * i}.weight"], self.pre[i][:M], False, True)
+            ops.ln_act_fwd(self.pre[i][:M], g.views[f"{self.prefix}{3 * i + 1}.weight"],
+                           g.views[f"{self.prefix}{3 * i + 1}.bias"], self.eps, ACT_SILU, self.act[i][:M])
+            cur = self.act[i][:M]
+        if self.out_dim is None:
+            return cur
+        j = 3 * self.n_hidden
+        ops.gemm(cur, g.views[f"{self.prefix}{j}.weight"], self.out[:M], False, True,
+                 bias=g.views[f"{self.prefix}{j}.bias"])
+        return self.out[:M]
+
+    def backward(self, x: torch.Tensor, dout: torch.Tensor, dx: Optional[torch.Tensor], accumulate_dx: bool,
+                 M: Optional[int] = None):
+        """dout: grad wrt output logits (or wrt last activation when out_dim is None).  Parameter grads
+        are written (not accumulated) into the group's grad views; dx (+)= grad wrt x."""
+        ops, g = self.eng.ops, self.g
+        M = x.shape[0] if M is None else M
+        if self.out_dim is not None:
+            j = 3 * self.n_hidden
+            last = self.act[-1][:M]
+            ops.gemm(dout, last, g.gviews[f"{self.prefix}{j}.weight"], True, False)
+            ops.col_sum(dout, g.gviews[f"{self.prefix}{j}.bias"])
+            ops.gemm(dout, g.views[f"{self.prefix}{j}.weight"], self.dact[:M], False, False)
+            d = self.dact[:M]
+        else:
+            d = dout
+        for i in reversed(range(self.n_hidden)):
+            ops.ln_act_bwd(self.pre[i][:M], g.views[f"{self.prefix}{3 * i + 1}.weight"],
+                           g.views[f"{self.prefix}{3 * i + 1}.bias"], self.eps, ACT_SILU, d, self.dpre[:M],
+                           g.gviews[f"{self.prefix}{3 * i + 1}.weight"], g.gviews[f"{self.prefix}{3 * i + 1}.bias"])
+            inp = x if i == 0 else self.act[i - 1][:M]
+            ops.gemm(self.dpre[:M], inp, g.gviews[f"{self.prefix}{3 * i}.weight"], True, False)
+            if i > 0:
+                ops.gemm(self.dpre[:M], g.views[f"{self.prefix}{3 * i}.weight"], self.dact[:M], False, False)
+                d = self.dact[:M]
+            elif dx is not None:
+                ops.gemm(self.dpre[:M], g.views[f"{self.prefix}0.weight"], dx, False, False, accumulate=accumulate_dx)
+
+
+class DV3Engine:
+    def __init__(self, cfg, actions_dim: Sequence[int], in_channels: int = 3, device="cuda", ops=None):
+        a, w = cfg.algo, cfg.algo.world_model
+        if a.mlp_keys.encoder:
+            raise NotImplementedError("vector (mlp_keys) observations are not implemented in the B200 engine yet")
+        if w.decoupled_rssm:
+            raise NotImplementedError("decoupled_rssm is not implemented in the B200 engine yet")
+        if len(a.cnn_keys.encoder) != 1:
+            raise NotImplementedError("exactly one image key is supported")
+        if ops is None:
+            from sheeprl_b200.lib import CudaOps  # raises loudly if the extension / a GPU is missing
+
+            ops = CudaOps(device)
+        self.ops = ops
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.actions_dim = tuple(int(x) for x in actions_dim)
+        self.Cin = in_channels
+        self.T, self.B = a.per_rank_sequence_length, a.per_rank_batch_size
+        self.N = self.T * self.B
+        self.H = a.horizon
+        self.S, self.D = w.stochastic_size, w.discrete_size
+        self.Z, self.R = self.S * self.D, w.recurrent_model.recurrent_state_size
+        self.L = self.Z + self.R
+        self.A = int(sum(self.actions_dim))
+        self.du, self.nh = a.dense_units, a.mlp_layers
+        self.Dx = w.recurrent_model.dense_units
+        self.Dt, self.Dr = w.transition_model.hidden_size, w.representation_model.hidden_size
+        self.eps = float(a.mlp_layer_norm.kw.eps)
+        self.ceps = float(a.cnn_layer_norm.kw.eps)
+        self.unimix = float(a.unimix)
+        self.img = cfg.env.screen_size
+        self.key = a.cnn_keys.encoder[0]
+        self.bins_r, self.bins_c = w.reward_model.bins, a.critic.bins
+        wm_s, ac_s, cr_s, meta = dv3_param_shapes(cfg, self.actions_dim, in_channels)
+        self.chans, self.dch, self.E, self.stages = meta["chans"], meta["dch"], meta["E"], meta["stages"]
+        self.wm = FlatGroup(wm_s, device)
+        self.actor = FlatGroup(ac_s, device)
+        self.critic = FlatGroup(cr_s, device)
+        self.target = FlatGroup(cr_s, device, with_optimizer=False)
+        self.moments_state = torch.zeros(2, dtype=torch.float32, device=device)  # (low, high)
+        self.world_size = 1
+        self.allreduce = None          # set by the data-parallel wrapper: fn(flat_grad_tensor)
+        self.allgather = None          # fn(tensor) -> gathered tensor (Moments)
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._alloc()
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name: str, *shape, dtype=torch.float32) -> torch.Tensor:
+        assert name not in self._bufs, name
+        t = torch.zeros(*shape, dtype=dtype, device=self.device)
+        self._bufs[name] = t
+        return t
+
+    def _alloc(self):
+        N, T, B, H, Z, R, L, A, E = self.N, self.T, self.B, self.H, self.Z, self.R, self.L, self.A, self.E
+        b = self._buf
+        img = self.img
+        self.x0 = b("x0", N, img, img, self.Cin)
+        self.enc_y, self.enc_a = [], []
+        s = img
+        for i in range(self.stages):
+            s //= 2
+            self.enc_y.append(b(f"enc_y{i}", N, s, s, self.chans[i + 1]))
+            self.enc_a.append(b(f"enc_a{i}", N, s, s, self.chans[i + 1]))
+        self.emb = b("emb", N, E)
+        self.pe = b("pe", N, self.Dr)
+        self.traj = b("traj", H + 1, N, L)
+        self.latent = self.traj[0]
+        # scan saves
+        self.z_in, self.h_in, self.a_in = b("z_in", N, Z), b("h_in", N, R), b("a_in", N, A)
+        self.x_pre, self.x_act = b("x_pre", N, self.Dx), b("x_act", N, self.Dx)
+        self.g_pre, self.g_ln = b("g_pre", N, 3 * R), b("g_ln", N, 3 * R)
+        self.tr_pre, self.tr_act = b("tr_pre", N, self.Dt), b("tr_act", N, self.Dt)
+        self.rp_pre, self.rp_act = b("rp_pre", N, self.Dr), b("rp_act", N, self.Dr)
+        self.post_raw, self.prior_raw = b("post_raw", N, Z), b("prior_raw", N, Z)
+        self.post_mix, self.prior_mix = b("post_mix", N, Z), b("prior_mix", N, Z)
+        self.h0, self.z0 = b("h0", 1, R), b("z0", 1, Z)
+        self.init_tr_pre, self.init_tr_act = b("init_tr_pre", 1, self.Dt), b("init_tr_act", 1, self.Dt)
+        self.init_raw = b("init_raw", 1, Z)
+        self.zero_h, self.zero_z = b("zero_h", B, R), b("zero_z", B, Z)
+        self.shift_actions = b("shift_actions", N, A)
+        # scan grads
+        self.d_latent = b("d_latent", N, L)
+        self.d_post_mix, self.d_prior_mix = b("d_post_mix", N, Z), b("d_prior_mix", N, Z)
+        self.d_post_raw, self.d_prior_raw = b("d_post_raw", N, Z), b("d_prior_raw", N, Z)
+        self.d_rp_act, self.d_rp_pre = b("d_rp_act", N, self.Dr), b("d_rp_pre", N, self.Dr)
+        self.d_tr_act, self.d_tr_pre = b("d_tr_act", N, self.Dt), b("d_tr_pre", N, self.Dt)
+        self.d_g_ln, self.d_g_pre = b("d_g_ln", N, 3 * R), b("d_g_pre", N, 3 * R)
+        self.d_x_act, self.d_x_pre = b("d_x_act", N, self.Dx), b("d_x_pre", N, self.Dx)
+        self.dz_carry, self.dh_carry = b("dz_carry", B, Z), b("dh_carry", B, R)
+        self.dz_tot, self.dh_tot = b("dz_tot", B, Z), b("dh_tot", B, R)
+        self.dh_in, self.dz_in = b("dh_in", B, R), b("dz_in", B, Z)
+        self.d_h0 = b("d_h0", R)
+        self.d_emb = b("d_emb", N, E)
+        self.kl_rows = b("kl_rows", N, 4)
+        # decoder
+        self.dec_lin = b("dec_lin", N, E)
+        C0 = self.dch[0]
+        self.dec_in = b("dec_in", N, 4, 4, C0)
+        self.dec_y, self.dec_a = [], []
+        s = 4
+        for i in range(self.stages - 1):
+            s *= 2
+            self.dec_y.append(b(f"dec_y{i}", N, s, s, self.dch[i + 1]))
+            self.dec_a.append(b(f"dec_a{i}", N, s, s, self.dch[i + 1]))
+        self.recon = b("recon", N, img, img, self.Cin)
+        self.d_dec_in = b("d_dec_in", N, 4, 4, C0)
+        self.d_dec_lin = b("d_dec_lin", N, E)
+        self.d_dec_a = [b(f"d_dec_a{i}", *self.dec_a[i].shape) for i in range(self.stages - 1)]
+        self.d_enc_a = [b(f"d_enc_a{i}", *self.enc_a[i].shape) for i in range(self.stages)]
+        # losses
+        self.obs_rows, self.rew_rows, self.cont_rows = b("obs_rows", N), b("rew_rows", N), b("cont_rows", N)
+        self.metrics = b("metrics", 16)
+        self.normsq = {k: self._buf(f"normsq_{k}", (), dtype=torch.float64) for k in ("wm", "actor", "critic")}
+        self.norms = b("norms", 3)
+        # heads on the replay batch (world-model phase)
+        self.reward_wm = _MLP(self, self.wm, "reward_model._model.", L, self.du, self.nh, self.bins_r, N, self.eps,
+                              "rew", True)
+        self.cont_wm = _MLP(self, self.wm, "continue_model._model.", L, self.du, self.nh, 1, N, self.eps, "cont", True)
+        self.d_rew_logits, self.d_cont_logit = b("d_rew_logits", N, self.bins_r), b("d_cont_logit", N, 1)
+        # behaviour phase
+        M1 = (H + 1) * N
+        self.actions = b("img_actions", H + 1, N, A)
+        self.actor_mlp = _MLP(self, self.actor, "model._model.", L, self.du, self.nh, None, M1, self.eps, "actor", True)
+        self.actor_raw = b("actor_raw", M1, A)
+        self.d_actor_raw = b("d_actor_raw", H * N, A)
+        self.d_actor_hidden = b("d_actor_hidden", H * N, self.du)
+        self.critic_mlp = _MLP(self, self.critic, "_model.", L, self.du, self.nh, self.bins_c, M1, self.eps,
+                               "critic", True)
+        self.target_mlp = _MLP(self, self.target, "_model.", L, self.du, self.nh, self.bins_c, H * N, self.eps,
+                               "target", False)
+        self.rew_img = _MLP(self, self.wm, "reward_model._model.", L, self.du, self.nh, self.bins_r, M1, self.eps,
+                            "rew_img", False)
+        self.cont_img = _MLP(self, self.wm, "continue_model._model.", L, self.du, self.nh, 1, M1, self.eps,
+                             "cont_img", False)
+        self.values, self.rew_pred = b("values", H + 1, N), b("rew_pred", H + 1, N)
+        self.target_values = b("target_values", H * N)
+        self.true_cont = b("true_cont", N)
+        self.lam, self.discount = b("lam", H, N), b("discount", H + 1, N)
+        self.moments_out = b("moments_out", 2)
+        self.policy_rows = b("policy_rows", H * N)
+        self.value_rows = b("value_rows", H * N)
+        self.d_critic_logits = b("d_critic_logits", H * N, self.bins_c)
+        # imagination step scratch (N rows)
+        self.i_x_pre, self.i_x_act = b("i_x_pre", N, self.Dx), b("i_x_act", N, self.Dx)
+        self.i_g_pre, self.i_g_ln = b("i_g_pre", N, 3 * R), b("i_g_ln", N, 3 * R)
+        self.i_tr_pre, self.i_tr_act = b("i_tr_pre", N, self.Dt), b("i_tr_act", N, self.Dt)
+        self.i_raw = b("i_raw", N, Z)
+        # default noise buffers (production: filled by the Philox kernel each step)
+        self.noise_post = b("noise_post", T, B, Z)
+        self.noise_img_state = b("noise_img_state", H, N, Z)
+        self.noise_img_action = b("noise_img_action", H + 1, N, A)
+        self.rng_seed, self.rng_calls = 0, 0
+
+    def bytes_allocated(self) -> int:
+        tot = sum(t.numel() * t.element_size() for t in self._bufs.values())
+        for g in (self.wm, self.actor, self.critic):
+            tot += 4 * g.numel * 4
+        return tot + self.target.numel * 4
+
+    # ------------------------------------------------------------------ parameter name helpers
+    def _w(self, name):
+        return self.wm.views[name]
+
+    def _gw(self, name):
+        return self.wm.gviews[name]
+
+    # ------------------------------------------------------------------ the step
+    def train_step(self, data: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None):
+        """data: the reference's batch dict ([T,B,...]; image key uint8 or float 0..255).
+        noise: optional injected Exp(1) noise {"post":[T,B,S,D], "img_state":[H,N,S,D],
+        "img_action":[list per head of [H+1,N,A_h]]} (parity mode); None -> on-device Philox."""
+        ops = self.ops
+        T, B, N, H, Z, R, L, A = self.T, self.B, self.N, self.H, self.Z, self.R, self.L, self.A
+        a, w = self.cfg.algo, self.cfg.algo.world_model
+        if noise is None:
+            self.rng_calls += 1
+            ops.fill_exponential(self.noise_post.view(-1), self.rng_seed, 3 * self.rng_calls)
+            ops.fill_exponential(self.noise_img_state.view(-1), self.rng_seed, 3 * self.rng_calls + 1)
+            ops.fill_exponential(self.noise_img_action.view(-1), self.rng_seed, 3 * self.rng_calls + 2)
+        else:
+            self.noise_post.copy_(noise["post"].reshape(T, B, Z))
+            self.noise_img_state.copy_(noise["img_state"].reshape(H, N, Z))
+            self.noise_img_action.copy_(torch.cat([x for x in noise["img_action"]], -1))
+
+        # ---- inputs (dreamer_v3.py:98-104): normalise pixels, force is_first[0]=1, shift actions
+        ops.obs_prep(data[self.key].reshape(N, self.Cin, self.img, self.img), self.x0)
+        data["is_first"][0].fill_(1.0)                      # same in-place mutation as the reference (:100)
+        first = data["is_first"].reshape(N)
+        ops.zero(self.shift_actions[:B])
+        ops.copy(data["actions"].reshape(N, A)[: N - B], self.shift_actions[B:])
+        rewards = data["rewards"].reshape(N)
+        ops.affine(data["terminated"].reshape(N), self.true_cont, -1.0, 1.0)   # 1 - terminated
+
+        self._encoder_forward()
+        # embed part of the representation model's first layer, for all T at once (no recurrence in it)
+        Wr1 = self._w("rssm.representation_model._model.0.weight")
+        ops.gemm(self.emb, Wr1[:, R:], self.pe, False, True)
+        self._scan_forward(first)
+        self._decoder_forward()
+        rew_logits = self.reward_wm.forward(self.latent)
+        cont_logit = self.cont_wm.forward(self.latent)
+
+        # ---- losses + seed gradients (loss.py:9-88); mean over T*B
+        inv = 1.0 / N
+        P = self.img * self.img * self.Cin
+        ops.mse_loss_grad(self.recon.view(N, P), self.x0.view(N, P), inv, self.obs_rows, self.recon.view(N, P))
+        ops.twohot_loss_grad(rew_logits, rewards, None, inv, TWOHOT_LOW, TWOHOT_HIGH, self.rew_rows, self.d_rew_logits)
+        ops.bce_loss_grad(cont_logit, self.true_cont, float(w.continue_scale_factor), inv, self.cont_rows,
+                          self.d_cont_logit)
+        ops.kl_loss_grad(self.post_mix, self.prior_mix, self.S, self.D, float(w.kl_dynamic),
+                         float(w.kl_representation), float(w.kl_free_nats), float(w.kl_regularizer), inv,
+                         self.d_post_mix, self.d_prior_mix, self.kl_rows)
+        # metrics 0..7: wm_loss, obs, reward, state, continue, kl, post_ent, prior_ent
+        ops.sum_rows(self.obs_rows.view(N, 1), self.metrics[1:2], inv)
+        ops.sum_rows(self.rew_rows.view(N, 1), self.metrics[2:3], inv)
+        ops.sum_rows(self.cont_rows.view(N, 1), self.metrics[4:5], inv)
+        ops.sum_rows(self.kl_rows[:, 1:2], self.metrics[3:4], inv)
+        ops.sum_rows(self.kl_rows[:, 0:1], self.metrics[5:6], inv)
+        ops.sum_rows(self.kl_rows[:, 2:4], self.metrics[6:8], inv)
+        ops.zero(self.metrics[0:1])
+        ops.axpy(self.metrics[1:2], self.metrics[0:1])
+        ops.axpy(self.metrics[2:3], self.metrics[0:1])
+        ops.axpy(self.metrics[3:4], self.metrics[0:1], float(w.kl_regularizer))
+        ops.axpy(self.metrics[4:5], self.metrics[0:1])
+
+        # ---- world-model backward
+        ops.zero(self.wm.grad)
+        self._decoder_backward()                                       # writes d_latent
+        self.reward_wm.backward(self.latent, self.d_rew_logits, self.d_latent, True)
+        self.cont_wm.backward(self.latent, self.d_cont_logit, self.d_latent, True)
+        self._scan_backward(first)
+        self._encoder_backward()
+        self._optimizer_step("wm", self.wm, float(w.clip_gradients or 0.0), w.optimizer, 0)
+
+        # ---- behaviour learning with the updated world model
+        self._imagine()
+        self._behaviour_losses()
+        return self.metrics
+
+    # ------------------------------------------------------------------ encoder / decoder
+    def _enc_names(self, i):
+        p = "encoder.cnn_encoder.model.0._model."
+        return f"{p}{3 * i}.weight", f"{p}{3 * i + 1}.weight", f"{p}{3 * i + 1}.bias"
+
+    def _dec_names(self, i):
+        p = "observation_model.cnn_decoder.model.2._model."
+        return f"{p}{3 * i}.weight", f"{p}{3 * i + 1}.weight", f"{p}{3 * i + 1}.bias"
+
+    def _encoder_forward(self):
+        ops = self.ops
+        cur = self.x0
+        for i in range(self.stages):
+            wn, gn, bn = self._enc_names(i)
+            ops.conv_down(cur, self._w(wn), self.enc_y[i])
+            C = self.chans[i + 1]
+            ops.ln_act_fwd(self.enc_y[i].view(-1, C), self._w(gn), self._w(bn), self.ceps, ACT_SILU,
+                           self.enc_a[i].view(-1, C))
+            cur = self.enc_a[i]
+        C = self.chans[-1]
+        ops.transpose_batched(cur.view(self.N, 16, C), self.emb.view(self.N, C, 16))
+
+    def _encoder_backward(self):
+        """d_emb [N,E] (CHW order) -> conv weight / LN grads."""
+        ops = self.ops
+        C = self.chans[-1]
+        ops.transpose_batched(self.d_emb.view(self.N, C, 16), self.d_enc_a[-1].view(self.N, 16, C))
+        for i in reversed(range(self.stages)):
+            wn, gn, bn = self._enc_names(i)
+            C = self.chans[i + 1]
+            d = self.d_enc_a[i].view(-1, C)
+            ops.ln_act_bwd(self.enc_y[i].view(-1, C), self._w(gn), self._w(bn), self.ceps, ACT_SILU, d, d,
+                           self._gw(gn), self._gw(bn))
+            inp = self.x0 if i == 0 else self.enc_a[i - 1]
+            ops.conv_wgrad(self.d_enc_a[i], inp, self._gw(wn))
+            if i > 0:
+                ops.conv_up(self.d_enc_a[i], self._w(wn), self.d_enc_a[i - 1])
+
+    def _decoder_forward(self):
+        ops = self.ops
+        p = "observation_model.cnn_decoder.model."
+        ops.gemm(self.latent, self._w(p + "0.weight"), self.dec_lin, False, True, bias=self._w(p + "0.bias"))
+        C0 = self.dch[0]
+        ops.transpose_batched(self.dec_lin.view(self.N, C0, 16), self.dec_in.view(self.N, 16, C0))
+        cur = self.dec_in
+        for i in range(self.stages - 1):
+            wn, gn, bn = self._dec_names(i)
+            C = self.dch[i + 1]
+            ops.conv_up(cur, self._w(wn), self.dec_y[i])
+            ops.ln_act_fwd(self.dec_y[i].view(-1, C), self._w(gn), self._w(bn), self.ceps, ACT_SILU,
+                           self.dec_a[i].view(-1, C))
+            cur = self.dec_a[i]
+        wn = self._dec_names(self.stages - 1)[0]
+        ops.conv_up(cur, self._w(wn), self.recon, bias=self._w(wn.replace(".weight", ".bias")))
+
+    def _decoder_backward(self):
+        """self.recon holds d(loss)/d(recon) (written in place by mse_loss_grad). Writes d_latent."""
+        ops = self.ops
+        st = self.stages
+        wn = self._dec_names(st - 1)[0]
+        d_big = self.recon
+        ops.col_sum(d_big.view(-1, self.Cin), self._gw(wn.replace(".weight", ".bias")))
+        for i in reversed(range(st)):
+            wn, gn, bn = self._dec_names(i)
+            inp = self.dec_in if i == 0 else self.dec_a[i - 1]
+            d_inp = self.d_dec_in if i == 0 else self.d_dec_a[i - 1]
+            ops.conv_wgrad(inp, d_big, self._gw(wn))
+            ops.conv_down(d_big, self._w(wn), d_inp)
+            if i > 0:
+                gn_p, bn_p = self._dec_names(i - 1)[1:]
+                C = self.dch[i]
+                d = d_inp.view(-1, C)
+                ops.ln_act_bwd(self.dec_y[i - 1].view(-1, C), self._w(gn_p), self._w(bn_p), self.ceps, ACT_SILU, d, d,
+                               self._gw(gn_p), self._gw(bn_p))
+            d_big = d_inp
+        C0 = self.dch[0]
+        ops.transpose_batched(self.d_dec_in.view(self.N, 16, C0), self.d_dec_lin.view(self.N, C0, 16))
+        p = "observation_model.cnn_decoder.model."
+        ops.gemm(self.d_dec_lin, self.latent, self._gw(p + "0.weight"), True, False)
+        ops.col_sum(self.d_dec_lin, self._gw(p + "0.bias"))
+        ops.gemm(self.d_dec_lin, self._w(p + "0.weight"), self.d_latent, False, False)
+
+    # ------------------------------------------------------------------ RSSM pieces
+    def _recurrent_forward(self, z, act, h_prev, x_pre, x_act, g_pre, g_ln, h_out):
+        """RecurrentModel + LayerNormGRUCell on M rows (agent.py:328-341, models.py:396-403)."""
+        ops, Z, R = self.ops, self.Z, self.R
+        p = "rssm.recurrent_model."
+        Win = self._w(p + "mlp._model.0.weight")
+        ops.gemm(z, Win[:, :Z], x_pre, False, True)
+        ops.gemm(act, Win[:, Z:], x_pre, False, True, accumulate=True)
+        ops.ln_act_fwd(x_pre, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"), self.eps,
+                       ACT_SILU, x_act)
+        Wg = self._w(p + "rnn.linear.weight")
+        ops.gemm(h_prev, Wg[:, :R], g_pre, False, True)
+        ops.gemm(x_act, Wg[:, R:], g_pre, False, True, accumulate=True)
+        ops.ln_act_fwd(g_pre, self._w(p + "rnn.layer_norm.weight"), self._w(p + "rnn.layer_norm.bias"), self.eps,
+                       ACT_NONE, g_ln)
+        ops.gru_gate_fwd(g_ln, h_prev, h_out)
+
+    def _transition_forward(self, h, tr_pre, tr_act, raw):
+        ops = self.ops
+        p = "rssm.transition_model._model."
+        ops.gemm(h, self._w(p + "0.weight"), tr_pre, False, True)
+        ops.ln_act_fwd(tr_pre, self._w(p + "1.weight"), self._w(p + "1.bias"), self.eps, ACT_SILU, tr_act)
+        ops.gemm(tr_act, self._w(p + "3.weight"), raw, False, True, bias=self._w(p + "3.bias"))
+
+    def _scan_forward(self, first: torch.Tensor):
+        """64-step RSSM scan (dreamer_v3.py:131-145, agent.py:396-435)."""
+        ops, B, Z, R = self.ops, self.B, self.Z, self.R
+        # learned initial state, identical for every row and step (agent.py:391-394)
+        ops.tanh_fwd(self._w("rssm.initial_recurrent_state").view(1, R), self.h0)
+        self._transition_forward(self.h0, self.init_tr_pre, self.init_tr_act, self.init_raw)
+        ops.cat_sample(self.init_raw, None, self.unimix, self.S, self.D, self.z0)
+        pr = "rssm.representation_model._model."
+        Wr1 = self._w(pr + "0.weight")
+        for t in range(self.T):
+            s = slice(t * B, (t + 1) * B)
+            f = first[s]
+            if t == 0:
+                zp, hp = self.zero_z, self.zero_h
+            else:
+                sp = slice((t - 1) * B, t * B)
+                zp, hp = self.latent[sp, :Z], self.latent[sp, Z:]
+            ops.mask_rows(self.shift_actions[s], f, self.a_in[s])
+            ops.mask_mix(hp, self.h0, f, self.h_in[s])
+            ops.mask_mix(zp, self.z0, f, self.z_in[s])
+            h = self.latent[s, Z:]
+            self._recurrent_forward(self.z_in[s], self.a_in[s], self.h_in[s], self.x_pre[s], self.x_act[s],
+                                    self.g_pre[s], self.g_ln[s], h)
+            self._transition_forward(h, self.tr_pre[s], self.tr_act[s], self.prior_raw[s])
+            # prior: only its unimix log-probs are needed (the prior sample is discarded, dreamer_v3.py:135)
+            ops.cat_sample(self.prior_raw[s], None, self.unimix, self.S, self.D, None, self.prior_mix[s])
+            ops.copy(self.pe[s], self.rp_pre[s])
+            ops.gemm(h, Wr1[:, :R], self.rp_pre[s], False, True, accumulate=True)
+            ops.ln_act_fwd(self.rp_pre[s], self._w(pr + "1.weight"), self._w(pr + "1.bias"), self.eps, ACT_SILU,
+                           self.rp_act[s])
+            ops.gemm(self.rp_act[s], self._w(pr + "3.weight"), self.post_raw[s], False, True,
+                     bias=self._w(pr + "3.bias"))
+            ops.cat_sample(self.post_raw[s], self.noise_post[t], self.unimix, self.S, self.D, self.latent[s, :Z],
+                           self.post_mix[s])
+
+    def _scan_backward(self, first: torch.Tensor):
+        """BPTT over the scan.  Per-step only the data-gradient GEMMs run; the weight
+        gradients are single big GEMMs over all T*B rows afterwards."""
+        ops, B, Z, R = self.ops, self.B, self.Z, self.R
+        p = "rssm.recurrent_model."
+        pt, pr = "rssm.transition_model._model.", "rssm.representation_model._model."
+        Win, Wg = self._w(p + "mlp._model.0.weight"), self._w(p + "rnn.linear.weight")
+        Wr1 = self._w(pr + "0.weight")
+        ops.zero(self.dz_carry)
+        ops.zero(self.dh_carry)
+        ops.zero(self.d_h0)
+        for t in reversed(range(self.T)):
+            s = slice(t * B, (t + 1) * B)
+            f = first[s]
+            ops.copy(self.d_latent[s, :Z], self.dz_tot)
+            ops.axpy(self.dz_carry, self.dz_tot)
+            ops.copy(self.d_latent[s, Z:], self.dh_tot)
+            ops.axpy(self.dh_carry, self.dh_tot)
+            # posterior: straight-through sample + KL -> raw logits -> representation model
+            ops.cat_sample_bwd(self.post_raw[s], self.dz_tot, self.d_post_mix[s], self.unimix, self.S, self.D,
+                               self.d_post_raw[s])
+            ops.gemm(self.d_post_raw[s], self._w(pr + "3.weight"), self.d_rp_act[s], False, False)
+            ops.ln_act_bwd(self.rp_pre[s], self._w(pr + "1.weight"), self._w(pr + "1.bias"), self.eps, ACT_SILU,
+                           self.d_rp_act[s], self.d_rp_pre[s], None, None)
+            ops.gemm(self.d_rp_pre[s], Wr1[:, :R], self.dh_tot, False, False, accumulate=True)
+            # prior: KL only
+            ops.cat_sample_bwd(self.prior_raw[s], None, self.d_prior_mix[s], self.unimix, self.S, self.D,
+                               self.d_prior_raw[s])
+            ops.gemm(self.d_prior_raw[s], self._w(pt + "3.weight"), self.d_tr_act[s], False, False)
+            ops.ln_act_bwd(self.tr_pre[s], self._w(pt + "1.weight"), self._w(pt + "1.bias"), self.eps, ACT_SILU,
+                           self.d_tr_act[s], self.d_tr_pre[s], None, None)
+            ops.gemm(self.d_tr_pre[s], self._w(pt + "0.weight"), self.dh_tot, False, False, accumulate=True)
+            # GRU
+            ops.gru_gate_bwd(self.g_ln[s], self.h_in[s], self.dh_tot, self.d_g_ln[s], self.dh_in)
+            ops.ln_act_bwd(self.g_pre[s], self._w(p + "rnn.layer_norm.weight"), self._w(p + "rnn.layer_norm.bias"),
+                           self.eps, ACT_NONE, self.d_g_ln[s], self.d_g_pre[s], None, None)
+            ops.gemm(self.d_g_pre[s], Wg[:, :R], self.dh_in, False, False, accumulate=True)
+            ops.gemm(self.d_g_pre[s], Wg[:, R:], self.d_x_act[s], False, False)
+            ops.ln_act_bwd(self.x_pre[s], self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"),
+                           self.eps, ACT_SILU, self.d_x_act[s], self.d_x_pre[s], None, None)
+            ops.gemm(self.d_x_pre[s], Win[:, :Z], self.dz_in, False, False)
+            ops.mask_bwd(self.dz_in, f, self.dz_carry, None)
+            ops.mask_bwd(self.dh_in, f, self.dh_carry, self.d_h0)
+        # ---- deferred parameter gradients over all N rows
+        N = self.N
+        h_all = self.latent[:, Z:]
+        gW = self._gw
+        # representation model
+        ops.gemm(self.d_post_raw, self.rp_act, gW(pr + "3.weight"), True, False)
+        ops.col_sum(self.d_post_raw, gW(pr + "3.bias"))
+        ops.ln_act_bwd(self.rp_pre, self._w(pr + "1.weight"), self._w(pr + "1.bias"), self.eps, ACT_SILU,
+                       self.d_rp_act, self.d_rp_act, gW(pr + "1.weight"), gW(pr + "1.bias"))
+        gWr1 = gW(pr + "0.weight")
+        ops.gemm(self.d_rp_pre, h_all, gWr1[:, :R], True, False)
+        ops.gemm(self.d_rp_pre, self.emb, gWr1[:, R:], True, False)
+        ops.gemm(self.d_rp_pre, Wr1[:, R:], self.d_emb, False, False)
+        # transition model
+        ops.gemm(self.d_prior_raw, self.tr_act, gW(pt + "3.weight"), True, False)
+        ops.col_sum(self.d_prior_raw, gW(pt + "3.bias"))
+        ops.ln_act_bwd(self.tr_pre, self._w(pt + "1.weight"), self._w(pt + "1.bias"), self.eps, ACT_SILU,
+                       self.d_tr_act, self.d_tr_act, gW(pt + "1.weight"), gW(pt + "1.bias"))
+        ops.gemm(self.d_tr_pre, h_all, gW(pt + "0.weight"), True, False)
+        # recurrent model
+        ops.ln_act_bwd(self.g_pre, self._w(p + "rnn.layer_norm.weight"), self._w(p + "rnn.layer_norm.bias"),
+                       self.eps, ACT_NONE, self.d_g_ln, self.d_g_ln, gW(p + "rnn.layer_norm.weight"),
+                       gW(p + "rnn.layer_norm.bias"))
+        gWg = gW(p + "rnn.linear.weight")
+        ops.gemm(self.d_g_pre, self.h_in, gWg[:, :R], True, False)
+        ops.gemm(self.d_g_pre, self.x_act, gWg[:, R:], True, False)
+        ops.ln_act_bwd(self.x_pre, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"), self.eps,
+                       ACT_SILU, self.d_x_act, self.d_x_act, gW(p + "mlp._model.1.weight"),
+                       gW(p + "mlp._model.1.bias"))
+        gWin = gW(p + "mlp._model.0.weight")
+        ops.gemm(self.d_x_pre, self.z_in, gWin[:, :Z], True, False)
+        ops.gemm(self.d_x_pre, self.a_in, gWin[:, Z:], True, False)
+        # learned initial recurrent state: h0 = tanh(param)
+        ops.tanh_bwd(self.h0.view(R), self.d_h0, gW("rssm.initial_recurrent_state"))
+
+    # ------------------------------------------------------------------ optimiser
+    def _optimizer_step(self, name: str, g: FlatGroup, max_norm: float, ocfg, slot: int):
+        ops = self.ops
+        if self.allreduce is not None:
+            self.allreduce(g.grad, name)
+        ops.sumsq(g.grad, self.normsq[name])
+        g.step += 1
+        ops.increment(g.step_t)
+        b1, b2 = ocfg.betas
+        ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, self.normsq[name], max_norm, float(ocfg.lr),
+                      float(b1), float(b2), float(ocfg.eps), g.step_t, self.norms[slot: slot + 1])
+
+    # ------------------------------------------------------------------ behaviour learning
+    def _actor_heads(self, hidden: torch.Tensor, raw_out: torch.Tensor):
+        off = 0
+        for i, ad in enumerate(self.actions_dim):
+            self.ops.gemm(hidden, self.actor.views[f"mlp_heads.{i}.weight"], raw_out[:, off:off + ad], False, True,
+                          bias=self.actor.views[f"mlp_heads.{i}.bias"])
+            off += ad
+
+    def _imagine(self):
+        """H-step rollout from every posterior state (dreamer_v3.py:203-241), forward only: with discrete
+        actions the policy gradient does not flow through the rollout."""
+        ops, N, Z, R, H = self.ops, self.N, self.Z, self.R, self.H
+        am = self.actor_mlp
+        for i in range(H + 1):
+            rows = slice(i * N, (i + 1) * N)
+            if i > 0:
+                prev, cur = self.traj[i - 1], self.traj[i]
+                self._recurrent_forward(prev[:, :Z], self.actions[i - 1], prev[:, Z:], self.i_x_pre, self.i_x_act,
+                                        self.i_g_pre, self.i_g_ln, cur[:, Z:])
+                self._transition_forward(cur[:, Z:], self.i_tr_pre, self.i_tr_act, self.i_raw)
+                ops.cat_sample(self.i_raw, self.noise_img_state[i - 1], self.unimix, self.S, self.D, cur[:, :Z])
+            # actor on traj[i]; activations are kept for the policy-gradient backward (the reference's second
+            # actor evaluation at dreamer_v3.py:273 recomputes exactly these numbers)
+            x = self.traj[i]
+            cur_in = x
+            for l in range(am.n_hidden):
+                ops.gemm(cur_in, am.W(l), am.pre[l][rows], False, True)
+                ops.ln_act_fwd(am.pre[l][rows], self.actor.views[f"model._model.{3 * l + 1}.weight"],
+                               self.actor.views[f"model._model.{3 * l + 1}.bias"], self.eps, ACT_SILU, am.act[l][rows])
+                cur_in = am.act[l][rows]
+            self._actor_heads(cur_in, self.actor_raw[rows])
+            off = 0
+            for k, ad in enumerate(self.actions_dim):
+                ops.cat_sample(self.actor_raw[rows, off:off + ad], self.noise_img_action[i, :, off:off + ad],
+                               self.unimix, 1, ad, self.actions[i, :, off:off + ad])
+                off += ad
+
+    def _behaviour_losses(self):
+        ops, N, H, L = self.ops, self.N, self.H, self.L
+        a = self.cfg.algo
+        M1, M0 = (H + 1) * N, H * N
+        traj2 = self.traj.view(M1, L)
+        # ---- values / rewards / continues on the trajectories (dreamer_v3.py:244-248)
+        v_logits = self.critic_mlp.forward(traj2)
+        ops.twohot_mean(v_logits, TWOHOT_LOW, TWOHOT_HIGH, self.values.view(-1))
+        r_logits = self.rew_img.forward(traj2)
+        ops.twohot_mean(r_logits, TWOHOT_LOW, TWOHOT_HIGH, self.rew_pred.view(-1))
+        c_logit = self.cont_img.forward(traj2)
+        ops.lambda_returns(self.rew_pred, self.values, c_logit.view(H + 1, N), self.true_cont, float(a.gamma),
+                           float(a.lmbda), self.lam, self.discount)
+        # ---- Moments (dreamer_v3/utils.py:56-63)
+        mo = a.actor.moments
+        lam_all = self.lam if self.allgather is None else self.allgather(self.lam)
+        ops.moments_update(lam_all.view(-1), self.moments_state, float(mo.decay), float(mo.max),
+                           float(mo.percentile.low), float(mo.percentile.high), self.moments_out)
+        # ---- actor (dreamer_v3.py:272-304)
+        ops.actor_loss_grad(self.actor_raw[:M0], self.actions.view(M1, self.A)[:M0], self.lam.view(-1),
+                            self.values.view(-1)[:M0], self.discount.view(-1)[:M0], self.moments_out,
+                            self.actions_dim, self.unimix, float(a.actor.ent_coef), 1.0 / M0, self.policy_rows,
+                            self.d_actor_raw)
+        ops.sum_rows(self.policy_rows.view(M0, 1), self.metrics[8:9], -1.0 / M0)
+        ops.zero(self.actor.grad)
+        am = self.actor_mlp
+        last = am.act[-1][:M0]
+        ops.zero(self.d_actor_hidden)
+        off = 0
+        for i, ad in enumerate(self.actions_dim):
+            d = self.d_actor_raw[:, off:off + ad]
+            ops.gemm(d, last, self.actor.gviews[f"mlp_heads.{i}.weight"], True, False)
+            ops.col_sum(d, self.actor.gviews[f"mlp_heads.{i}.bias"])
+            ops.gemm(d, self.actor.views[f"mlp_heads.{i}.weight"], self.d_actor_hidden, False, False, accumulate=True)
+            off += ad
+        am.backward(traj2[:M0], self.d_actor_hidden, None, False, M=M0)
+        self._optimizer_step("actor", self.actor, float(a.actor.clip_gradients or 0.0), a.actor.optimizer, 1)
+        # ---- critic (dreamer_v3.py:307-327): qv logits are the first H*N rows of v_logits (same weights,
+        # same inputs as the reference's second critic evaluation)
+        t_logits = self.target_mlp.forward(traj2[:M0])
+        ops.twohot_mean(t_logits, TWOHOT_LOW, TWOHOT_HIGH, self.target_values)
+        disc = self.discount.view(-1)[:M0]
+        ops.twohot_loss_grad(v_logits[:M0], self.lam.view(-1), disc, 1.0 / M0, TWOHOT_LOW, TWOHOT_HIGH,
+                             self.value_rows, self.d_critic_logits)
+        ops.twohot_loss_grad(v_logits[:M0], self.target_values, disc, 1.0 / M0, TWOHOT_LOW, TWOHOT_HIGH,
+                             self.value_rows, self.d_critic_logits, accumulate=True)
+        ops.weighted_mean(self.value_rows, disc, 1.0 / M0, self.metrics[9:10])
+        ops.zero(self.critic.grad)
+        self.critic_mlp.backward(traj2[:M0], self.d_critic_logits, None, False, M=M0)
+        self._optimizer_step("critic", self.critic, float(a.critic.clip_gradients or 0.0), a.critic.optimizer, 2)
+
+    # ------------------------------------------------------------------ misc
+    METRIC_NAMES = (
+        "Loss/world_model_loss", "Loss/observation_loss", "Loss/reward_loss", "Loss/state_loss",
+        "Loss/continue_loss", "State/kl", "State/post_entropy", "State/prior_entropy", "Loss/policy_loss",
+        "Loss/value_loss",
+    )
+
+    def metrics_dict(self) -> Dict[str, torch.Tensor]:
+        d = {n: self.metrics[i] for i, n in enumerate(self.METRIC_NAMES)}
+        d["Grads/world_model"], d["Grads/actor"], d["Grads/critic"] = self.norms[0], self.norms[1], self.norms[2]
+        return d
+
+    def update_target(self, tau: float):
+        """Target-critic EMA (reference: dreamer_v3.py:674-680, done by `main` before each train call)."""
+        if tau >= 1.0:
+            self.ops.copy(self.critic.flat, self.target.flat)
+        else:
+            self.ops.ema(self.target.flat, self.critic.flat, float(tau))
