@@ -1,0 +1,138 @@
+/* b200rl — C-ABI of the B200 (sm_100a) kernels behind SheepRL's Dreamer-V3 / PPO / SAC update paths.
+ *
+ * The reference (Eclectic-Sheep/sheeprl) is pure Python and has NO native interface for this path
+ * (SURVEY.md §0 F1, §2.2); these entry points are what a reference-side binding (ctypes / a
+ * torch.utils.cpp_extension shim) calls from `sheeprl.algos.<algo>.train()`.
+ * Each declaration cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer owned by the caller (borrowed);
+ *     nothing is allocated or freed by the library; no host synchronisation; all work is enqueued on
+ *     `stream` (pass the caller's current stream) — hence CUDA-graph capturable;
+ *   - fp32, row-major; `ld*` = row stride in elements of a 2-D view whose inner stride is 1;
+ *   - return 0 on success; non-zero => b200rl_last_error() (thread-local message);
+ *   - built for sm_100a only (b200rl_device_check refuses other devices). There is no CPU fallback.
+ */
+#ifndef B200RL_H_
+#define B200RL_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* b200rl_last_error(void);
+int b200rl_abi_version(void);
+const char* b200rl_build_arch(void);
+int b200rl_device_check(void);
+
+/* ---- dense layers ------------------------------------------------------------------------------
+ * nn.Linear forward/backward everywhere in sheeprl/models/models.py:16-119 (MLP), agent.py:281-341
+ * (RecurrentModel), agent.py:1021-1051 (representation / transition).  C[M,N] = op(A) op(B) (+bias) (+C).
+ * A is [M,K] (lda) or [K,M] if transA; B is [K,N] (ldb) or [N,K] if transB (nn.Linear weight layout). */
+int b200rl_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                    int ldc, int transA, int transB, int accumulate, cudaStream_t stream);
+/* nn.LayerNorm(eps) (+ nn.SiLU): miniblock sheeprl/utils/model.py:34-88; LayerNormChannelLast
+ * sheeprl/models/models.py:507-518 (channel-last is native here).  act: 0 none, 1 SiLU. */
+int b200rl_ln_act_fwd(const float* X, const float* gamma, const float* beta, float* Y, long long M, int C,
+                      long long ldx, long long ldy, float eps, int act, cudaStream_t stream);
+int b200rl_ln_act_bwd(const float* X, const float* gamma, const float* beta, const float* dY, float* dX, float* dgamma,
+                      float* dbeta, long long M, int C, long long ldx, long long lddy, long long lddx, float eps,
+                      int act, int accumulate, cudaStream_t stream);
+int b200rl_col_sum(const float* X, float* out, long long M, int C, long long ldx, int accumulate, cudaStream_t stream);
+
+/* ---- image encoder / decoder ---------------------------------------------------------------------
+ * CNNEncoder agent.py:42-97 (Conv2d k4 s2 p1), CNNDecoder agent.py:154-226 (ConvTranspose2d k4 s2 p1),
+ * observation normalisation dreamer_v3.py:98.  Images are NHWC; W is [C_small, C_big, 4, 4] (the
+ * reference layouts of both layer kinds).  (h, w) = SMALL image size; big image is (2h, 2w). */
+int b200rl_obs_prep(const void* obs_nchw, int is_uint8, float* out_nhwc, long long NB, int C, int HW,
+                    cudaStream_t stream);
+int b200rl_transpose_batched(const float* X, float* Y, int NB, int a, int b, cudaStream_t stream);
+int b200rl_conv_down(const float* big, const float* W, float* small_, int NB, int h, int w, int Cs, int Cb,
+                     cudaStream_t stream);
+int b200rl_conv_up(const float* small_, const float* W, float* big, const float* bias, int NB, int h, int w, int Cs,
+                   int Cb, cudaStream_t stream);
+int b200rl_conv_wgrad(const float* small_, const float* big, float* dW, int NB, int h, int w, int Cs, int Cb,
+                      int accumulate, cudaStream_t stream);
+
+/* ---- RSSM ------------------------------------------------------------------------------------------
+ * LayerNormGRUCell gates models.py:399-403; is_first masking agent.py:425-430; unimix agent.py:437-449;
+ * straight-through categorical sampling dreamer_v2/utils.py:44-61 (noise q ~ Exp(1): sample =
+ * argmax(probs / q), noise == NULL -> mode); KL balancing + free nats loss.py:61-75. */
+int b200rl_gru_gate_fwd(const float* G, const float* Hin, float* Hout, long long M, int R, long long ldg,
+                        long long ldhi, long long ldho, cudaStream_t stream);
+int b200rl_gru_gate_bwd(const float* G, const float* Hin, const float* dH, float* dG, float* dHin, long long M, int R,
+                        long long ldg, long long ldhi, long long lddh, long long lddg, long long lddhi,
+                        cudaStream_t stream);
+int b200rl_mask_mix(const float* prev, const float* init_row, const float* first, float* out, long long M, int C,
+                    long long ldp, long long ldo, cudaStream_t stream);
+int b200rl_mask_bwd(const float* dIn, const float* first, float* dPrev, float* dInit, int M, int C, long long ldi,
+                    long long ldp, cudaStream_t stream);
+int b200rl_cat_sample(const float* raw, const float* noise, float* onehot, float* mix_out, long long M, int groups,
+                      int classes, long long ldr, long long ldn, long long ldo, long long ldm, float unimix,
+                      cudaStream_t stream);
+int b200rl_cat_sample_bwd(const float* raw, const float* dz, const float* dmix, float* draw, long long M, int groups,
+                          int classes, long long ldr, long long lddz, long long lddm, long long lddr, float unimix,
+                          cudaStream_t stream);
+int b200rl_kl_loss_grad(const float* post_mix, const float* prior_mix, float* d_post, float* d_prior, float* rows,
+                        long long M, int groups, int classes, long long ldp, long long ldq, long long lddp,
+                        long long lddq, float kl_dyn, float kl_rep, float free_nats, float regularizer, float scale,
+                        cudaStream_t stream);
+/* ---- losses (value + seed gradient) -----------------------------------------------------------------
+ * distribution.py:212-276 (MSE, two-hot on symlog), Bernoulli continue head loss.py:77, lambda returns
+ * dreamer_v3/utils.py:66-77 + dreamer_v3.py:244-260, Moments dreamer_v3/utils.py:40-63, discrete policy
+ * loss dreamer_v3.py:272-297. */
+int b200rl_mse_loss_grad(const float* pred, const float* target, float* loss_row, float* grad, long long M, int P,
+                         float scale, cudaStream_t stream);
+int b200rl_twohot_loss_grad(const float* logits, const float* x, const float* weight, float* loss_row, float* dlogits,
+                            long long M, int nbins, long long ldl, long long ldd, float low, float high, float scale,
+                            int accumulate, cudaStream_t stream);
+int b200rl_bce_loss_grad(const float* logit, const float* target, float* loss_row, float* dlogit, long long M,
+                         float loss_scale, float scale, cudaStream_t stream);
+int b200rl_twohot_mean(const float* logits, float* out, long long M, int nbins, long long ldl, float low, float high,
+                       cudaStream_t stream);
+int b200rl_lambda_returns(const float* rew, const float* val, const float* cont_logit, const float* true_cont,
+                          float* lam, float* discount, int H, int N, float gamma, float lmbda, cudaStream_t stream);
+int b200rl_moments_update(const float* x, long long n, float* state_low_high, float* out_offset_invscale, float decay,
+                          float max_, float p_low, float p_high, cudaStream_t stream);
+int b200rl_actor_loss_grad(const float* raw, const float* actions, const float* lam, const float* val,
+                           const float* discount, const float* moments, float* rows, float* draw, long long M,
+                           const int* head_dims_host, int n_heads, float unimix, float ent_coef, float scale,
+                           cudaStream_t stream);
+int b200rl_sum_rows(const float* X, float* out, long long M, int C, long long ldx, float scale, cudaStream_t stream);
+int b200rl_weighted_mean(const float* x, const float* w, float* out, long long n, float scale, cudaStream_t stream);
+
+/* ---- optimiser -----------------------------------------------------------------------------------------
+ * clip_grad_norm_ + torch.optim.Adam.step fused (dreamer_v3.py:191-200,298-304,318-327); target-critic
+ * EMA dreamer_v3.py:674-680; Exp(1) noise for categorical sampling (torch.multinomial). */
+int b200rl_sumsq(const float* x, long long n, double* out, cudaStream_t stream);
+int b200rl_adam_step(float* p, const float* g, float* m, float* v, const double* normsq, const int* step_dev,
+                     float* norm_out, long long n, float max_norm, float lr, float b1, float b2, float eps,
+                     cudaStream_t stream);
+int b200rl_ema(float* target, const float* src, long long n, float tau, cudaStream_t stream);
+int b200rl_fill_exponential(float* out, long long n, unsigned long long seed, unsigned int stream_id,
+                            const int* counter_dev, cudaStream_t stream);
+int b200rl_zero(float* x, long long n, cudaStream_t stream);
+int b200rl_copy2d(const float* src, float* dst, long long M, int C, long long lds, long long ldd, cudaStream_t stream);
+int b200rl_axpy(const float* x, float* y, long long n, float alpha, cudaStream_t stream);
+int b200rl_affine(const float* x, float* y, long long n, float alpha, float beta, cudaStream_t stream);
+int b200rl_tanh_fwd(const float* x, float* y, long long n, cudaStream_t stream);
+int b200rl_tanh_bwd(const float* y, const float* dy, float* dx, long long n, int accumulate, cudaStream_t stream);
+int b200rl_increment(int* p, cudaStream_t stream);
+
+/* ---- replay storage / PPO -------------------------------------------------------------------------------
+ * SequentialReplayBuffer._get_samples buffers.py:467-526 (+ get_tensor :1158-1180), ReplayBuffer.add
+ * buffers.py:145-221, gae utils/utils.py:63-100.  idx: int64 flat row indices in (sample, batch, time)
+ * order exactly as the reference computes them on the host; out rows in (sample, time, batch) order. */
+int b200rl_replay_gather(const void* storage, const long long* idx, void* out, int n_samples, int batch, int seq_len,
+                         long long row_bytes, cudaStream_t stream);
+int b200rl_replay_scatter(const void* src, const long long* dst_rows, void* storage, long long n_rows,
+                          long long row_bytes, cudaStream_t stream);
+int b200rl_gae(const float* rewards, const float* values, const float* dones, const float* next_value, float* returns,
+               float* advantages, int T, int E, float gamma, float lmbda, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H_ */

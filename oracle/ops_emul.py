@@ -354,8 +354,9 @@ class EmulOps:
     def ema(self, target: Tensor, src: Tensor, tau: float):
         target.mul_(1 - tau).add_(src, alpha=tau)
 
-    def fill_exponential(self, out: Tensor, seed: int, offset: int):
-        g = torch.Generator().manual_seed(seed * 1000003 + offset)
+    def fill_exponential(self, out: Tensor, seed: int, stream_id: int, counter: Optional[Tensor] = None):
+        c = int(counter.item()) if counter is not None else 0
+        g = torch.Generator().manual_seed(seed * 1000003 + stream_id * 7919 + c)
         out.exponential_(1.0, generator=g)
 
     def increment(self, step_t: Tensor):

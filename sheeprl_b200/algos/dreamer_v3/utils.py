@@ -1,0 +1,34 @@
+"""Dreamer-V3 side objects the reference keeps in `sheeprl/algos/dreamer_v3/utils.py`.
+
+`Moments` here is a thin state holder: the percentile / EMA arithmetic runs in the
+`b200rl_moments_update` kernel inside `DV3Engine` (reference: dreamer_v3/utils.py:40-63)."""
+from __future__ import annotations
+
+import torch
+
+AGGREGATOR_KEYS = {
+    "Rewards/rew_avg", "Game/ep_len_avg", "Loss/world_model_loss", "Loss/value_loss", "Loss/policy_loss",
+    "Loss/observation_loss", "Loss/reward_loss", "Loss/state_loss", "Loss/continue_loss", "State/kl",
+    "State/post_entropy", "State/prior_entropy", "Grads/world_model", "Grads/actor", "Grads/critic",
+}
+MODELS_TO_REGISTER = {"world_model", "actor", "critic", "target_critic", "moments"}
+
+
+class Moments(torch.nn.Module):
+    """Buffers `low` / `high` (checkpoint-compatible with the reference's Moments.state_dict())."""
+
+    def __init__(self, decay: float = 0.99, max_: float = 1e8, percentile_low: float = 0.05,
+                 percentile_high: float = 0.95) -> None:
+        super().__init__()
+        self._decay, self._max = decay, max_
+        self._percentile_low, self._percentile_high = percentile_low, percentile_high
+        self.register_buffer("low", torch.zeros((), dtype=torch.float32))
+        self.register_buffer("high", torch.zeros((), dtype=torch.float32))
+
+    def bind(self, state: torch.Tensor) -> None:
+        """Alias the buffers onto the engine's 2-float device state so the kernel updates them in place."""
+        with torch.no_grad():
+            state[0] = self.low.to(state.device)
+            state[1] = self.high.to(state.device)
+        self.low = state[0]
+        self.high = state[1]

@@ -1,0 +1,214 @@
+// LayerNorm(+SiLU) forward / backward and column sums (HBM-bound row kernels).
+//
+// Replaces: nn.LayerNorm(eps=1e-3) + nn.SiLU blocks built by `miniblock` (sheeprl/utils/model.py:34-88),
+// `LayerNormChannelLast` (sheeprl/models/models.py:507-518; channel-last is the native layout here so no
+// permute copies are needed) and their autograd backward; bias gradients (column sums).
+// One warp per row: lanes stride over the C contiguous channels, statistics via warp shuffles.
+#include "common.cuh"
+
+namespace {
+
+constexpr int ACT_NONE = 0, ACT_SILU = 1;
+
+__global__ void __launch_bounds__(256)
+ln_act_fwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float* __restrict__ Y, long long M, int C, long long ldx, long long ldy, float eps, int act) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float invC = 1.f / (float)C;
+  for (long long r = warp; r < M; r += nwarps) {
+    const float* x = X + r * ldx;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[c];
+    const float mu = warp_sum(s) * invC;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = x[c] - mu; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(warp_sum(v) * invC + eps);
+    float* y = Y + r * ldy;
+    for (int c = lane; c < C; c += 32) {
+      float o = (x[c] - mu) * rstd * gamma[c] + beta[c];
+      if (act == ACT_SILU) o = siluf_(o);
+      y[c] = o;
+    }
+  }
+}
+
+// CPL = channels per lane held in registers for the dgamma/dbeta partial sums (C <= 32*CPL).
+template <int CPL>
+__global__ void __launch_bounds__(256)
+ln_act_bwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* dY, float* dX, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                  long long M, int C, long long ldx, long long lddy, long long lddx, float eps, int act) {
+  extern __shared__ float sacc[];  // CPL == 0: [2*C] shared accumulators
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float invC = 1.f / (float)C;
+  constexpr int NACC = CPL > 0 ? CPL : 1;
+  float ag[NACC], ab[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+  const bool want_param = dgamma != nullptr;
+  if (CPL == 0 && want_param) {
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sacc[c] = 0.f;
+    __syncthreads();
+  }
+  for (long long r = warp; r < M; r += nwarps) {
+    const float* x = X + r * ldx;
+    const float* dy = dY + r * lddy;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[c];
+    const float mu = warp_sum(s) * invC;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = x[c] - mu; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(warp_sum(v) * invC + eps);
+    float s1 = 0.f, s2 = 0.f;
+    auto body = [&](int c, float& accg, float& accb) {
+      const float xh = (x[c] - mu) * rstd;
+      float dln = dy[c];
+      if (act == ACT_SILU) {
+        const float ln = xh * gamma[c] + beta[c];
+        const float sg = sigmoidf_(ln);
+        dln *= sg * (1.f + ln * (1.f - sg));
+      }
+      const float dxh = dln * gamma[c];
+      s1 += dxh;
+      s2 = fmaf(dxh, xh, s2);
+      accg = dln * xh;
+      accb = dln;
+    };
+    if constexpr (CPL > 0) {
+#pragma unroll
+      for (int j = 0; j < NACC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          float g_, b_;
+          body(c, g_, b_);
+          ag[j] += g_;
+          ab[j] += b_;
+        }
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        float g_, b_;
+        body(c, g_, b_);
+        if (want_param) { atomicAdd(&sacc[c], g_); atomicAdd(&sacc[C + c], b_); }
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+    float* dx = dX + r * lddx;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (x[c] - mu) * rstd;
+      float dln = dy[c];
+      if (act == ACT_SILU) {
+        const float ln = xh * gamma[c] + beta[c];
+        const float sg = sigmoidf_(ln);
+        dln *= sg * (1.f + ln * (1.f - sg));
+      }
+      dx[c] = rstd * (dln * gamma[c] - s1 - xh * s2);  // dX may alias dY: element c is read before it is written
+    }
+  }
+  if (want_param) {
+    if (CPL > 0) {
+#pragma unroll
+      for (int j = 0; j < NACC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) { atomicAdd(&dgamma[c], ag[j]); atomicAdd(&dbeta[c], ab[j]); }
+      }
+    } else {
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&dgamma[c], sacc[c]);
+        atomicAdd(&dbeta[c], sacc[C + c]);
+      }
+    }
+  }
+}
+
+// out[c] (+)= sum_m X[m,c]; blockDim = (32, 8); out pre-zeroed by the host wrapper unless accumulating.
+__global__ void col_sum_kernel(const float* __restrict__ X, float* __restrict__ out, long long M, int C,
+                               long long ldx, long long rows_per_block) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += X[r * ldx + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(&out[c], t);
+  }
+}
+
+int grid_for_rows(long long M) {
+  long long blocks = (M + 7) / 8;  // 8 warps (rows) per 256-thread block
+  const long long cap = (long long)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int b200rl_ln_act_fwd(const float* X, const float* gamma, const float* beta, float* Y, long long M, int C,
+                                 long long ldx, long long ldy, float eps, int act, cudaStream_t st) {
+  RL_CHECK_ARG(X && gamma && beta && Y, "null pointer");
+  RL_CHECK_ARG(C > 0 && ldx >= C && ldy >= C, "bad C / ld");
+  if (M <= 0) return B200RL_OK;
+  ln_act_fwd_kernel<<<grid_for_rows(M), 256, 0, st>>>(X, gamma, beta, Y, M, C, ldx, ldy, eps, act);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_ln_act_bwd(const float* X, const float* gamma, const float* beta, const float* dY, float* dX,
+                                 float* dgamma, float* dbeta, long long M, int C, long long ldx, long long lddy,
+                                 long long lddx, float eps, int act, int accumulate, cudaStream_t st) {
+  RL_CHECK_ARG(X && gamma && beta && dY && dX, "null pointer");
+  RL_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "dgamma/dbeta must both be given or both be null");
+  RL_CHECK_ARG(C > 0 && ldx >= C && lddy >= C && lddx >= C, "bad C / ld");
+  if (dgamma && !accumulate) {
+    RL_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st));
+    RL_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st));
+  }
+  if (M <= 0) return B200RL_OK;
+  int grid = grid_for_rows(M);
+  if (dgamma && grid > 2 * kNumSMs) grid = 2 * kNumSMs;  // fewer, longer-lived warps -> fewer flush atomics
+#define LN_BWD(CPL_, SMEM_)                                                                                    \
+  ln_act_bwd_kernel<CPL_><<<grid, 256, SMEM_, st>>>(X, gamma, beta, dY, dX, dgamma, dbeta, M, C, ldx, lddy, lddx, \
+                                                    eps, act)
+  if (C <= 32) LN_BWD(1, 0);
+  else if (C <= 64) LN_BWD(2, 0);
+  else if (C <= 128) LN_BWD(4, 0);
+  else if (C <= 256) LN_BWD(8, 0);
+  else if (C <= 512) LN_BWD(16, 0);
+  else {
+    RL_CHECK_ARG(C <= 5632, "C too large for the shared accumulator path");
+    LN_BWD(0, sizeof(float) * 2 * C);
+  }
+#undef LN_BWD
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_col_sum(const float* X, float* out, long long M, int C, long long ldx, int accumulate,
+                              cudaStream_t st) {
+  RL_CHECK_ARG(X && out, "null pointer");
+  RL_CHECK_ARG(C > 0 && ldx >= C, "bad C / ld");
+  if (!accumulate) RL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+  if (M <= 0) return B200RL_OK;
+  const int cb = ceil_div(C, 32);
+  long long rb = (2LL * kNumSMs + cb - 1) / cb;
+  long long rows_per_block = (M + rb - 1) / rb;
+  if (rows_per_block < 64) rows_per_block = 64;
+  rb = (M + rows_per_block - 1) / rows_per_block;
+  col_sum_kernel<<<dim3(cb, (unsigned)rb), dim3(32, 8), 0, st>>>(X, out, M, C, ldx, rows_per_block);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}

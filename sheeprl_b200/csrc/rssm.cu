@@ -1,0 +1,362 @@
+// RSSM element-wise / small-reduction kernels: GRU gate, is_first masking, unimix + categorical
+// straight-through sampling, categorical KL with free nats.  32-way class groups map onto the 32 lanes
+// of a warp, so softmax / log-sum-exp / KL / arg-max reductions are pure warp shuffles.
+//
+// Replaces (reference): LayerNormGRUCell gate math (sheeprl/models/models.py:399-403), RSSM.dynamic masking
+// (agent.py:425-430), RSSM._uniform_mix (agent.py:437-449), compute_stochastic_state
+// (dreamer_v2/utils.py:44-61) incl. torch's OneHotCategoricalStraightThrough / Categorical semantics,
+// the KL-balancing part of reconstruction_loss (dreamer_v3/loss.py:61-75), and their backward.
+#include "common.cuh"
+
+namespace {
+
+__global__ void gru_gate_fwd_kernel(const float* __restrict__ G, const float* __restrict__ Hin, float* __restrict__ Hout,
+                                    long long M, int R, long long ldg, long long ldhi, long long ldho) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * R) return;
+  const long long m = idx / R;
+  const int j = (int)(idx - m * R);
+  const float* g = G + m * ldg;
+  const float r = sigmoidf_(g[j]);
+  const float c = tanhf(r * g[R + j]);
+  const float u = sigmoidf_(g[2 * R + j] - 1.f);
+  const float h = Hin[m * ldhi + j];
+  Hout[m * ldho + j] = u * c + (1.f - u) * h;
+}
+
+__global__ void gru_gate_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Hin,
+                                    const float* __restrict__ dH, float* __restrict__ dG, float* __restrict__ dHin,
+                                    long long M, int R, long long ldg, long long ldhi, long long lddh,
+                                    long long lddg, long long lddhi) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * R) return;
+  const long long m = idx / R;
+  const int j = (int)(idx - m * R);
+  const float* g = G + m * ldg;
+  const float gc = g[R + j];
+  const float r = sigmoidf_(g[j]);
+  const float c = tanhf(r * gc);
+  const float u = sigmoidf_(g[2 * R + j] - 1.f);
+  const float h = Hin[m * ldhi + j];
+  const float dh = dH[m * lddh + j];
+  const float du = dh * (c - h);
+  const float drc = dh * u * (1.f - c * c);
+  float* dg = dG + m * lddg;
+  dg[j] = drc * gc * r * (1.f - r);
+  dg[R + j] = drc * r;
+  dg[2 * R + j] = du * u * (1.f - u);
+  dHin[m * lddhi + j] = dh * (1.f - u);
+}
+
+// out[m,c] = (1-f[m]) * prev[m,c] + f[m] * init[c]   (init == nullptr: plain row masking)
+__global__ void mask_mix_kernel(const float* __restrict__ prev, const float* __restrict__ init,
+                                const float* __restrict__ first, float* __restrict__ out, long long M, int C,
+                                long long ldp, long long ldo) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * C) return;
+  const long long m = idx / C;
+  const int c = (int)(idx - m * C);
+  const float f = first[m];
+  float v = (1.f - f) * prev[m * ldp + c];
+  if (init) v += f * init[c];
+  out[m * ldo + c] = v;
+}
+
+// dPrev[m,c] = (1-f[m]) * dIn[m,c];  dInit[c] += sum_m f[m]*dIn[m,c]   (one thread per column, M small)
+__global__ void mask_bwd_kernel(const float* __restrict__ dIn, const float* __restrict__ first,
+                                float* __restrict__ dPrev, float* __restrict__ dInit, int M, int C, long long ldi,
+                                long long ldp) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const float f = first[m];
+    const float d = dIn[m * ldi + c];
+    dPrev[m * ldp + c] = (1.f - f) * d;
+    s = fmaf(f, d, s);
+  }
+  if (dInit) dInit[c] += s;
+}
+
+struct GroupStats {
+  float raw_max, raw_sum;  // softmax of raw logits: s = exp(x-raw_max)/raw_sum
+  float lse;               // logsumexp of the unimix log-probs (torch Categorical normalisation)
+};
+
+__device__ __forceinline__ float unimix_logprob(float s, float unimix, float invK, float& pm) {
+  pm = (1.f - unimix) * s + unimix * invK;
+  return logf(fminf(fmaxf(pm, kFp32Eps), 1.f - kFp32Eps));
+}
+
+// One warp per (row, group).  Computes everything the forward/backward need about one categorical.
+__device__ __forceinline__ GroupStats group_stats(const float* x, int K, float unimix, int lane) {
+  GroupStats st;
+  float mx = -INFINITY;
+  for (int c = lane; c < K; c += 32) mx = fmaxf(mx, x[c]);
+  mx = warp_max(mx);
+  float sm = 0.f;
+  for (int c = lane; c < K; c += 32) sm += expf(x[c] - mx);
+  sm = warp_sum(sm);
+  st.raw_max = mx;
+  st.raw_sum = sm;
+  const float invK = 1.f / (float)K;
+  // logsumexp over l_c (max-shifted like torch.logsumexp)
+  float lmx = -INFINITY;
+  for (int c = lane; c < K; c += 32) {
+    float l = x[c];
+    if (unimix > 0.f) { float pm; l = unimix_logprob(expf(x[c] - mx) / sm, unimix, invK, pm); }
+    lmx = fmaxf(lmx, l);
+  }
+  lmx = warp_max(lmx);
+  float ls = 0.f;
+  for (int c = lane; c < K; c += 32) {
+    float l = x[c];
+    if (unimix > 0.f) { float pm; l = unimix_logprob(expf(x[c] - mx) / sm, unimix, invK, pm); }
+    ls += expf(l - lmx);
+  }
+  ls = warp_sum(ls);
+  st.lse = lmx + logf(ls);
+  return st;
+}
+
+__global__ void __launch_bounds__(256)
+cat_sample_kernel(const float* __restrict__ raw, const float* __restrict__ noise, float* __restrict__ onehot,
+                  float* __restrict__ mix_out, long long M, int groups, int K, long long ldr, long long ldn,
+                  long long ldo, long long ldm, float unimix) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= M * groups) return;
+  const long long m = warp / groups;
+  const int g = (int)(warp - m * groups);
+  const float* x = raw + m * ldr + (long long)g * K;
+  const GroupStats st = group_stats(x, K, unimix, lane);
+  const float invK = 1.f / (float)K;
+  // normalised log-probs lg = l - lse; probs = softmax(lg) (max-shifted); ratio = probs / q
+  float lgmax = -INFINITY;
+  for (int c = lane; c < K; c += 32) {
+    float l = x[c];
+    if (unimix > 0.f) { float pm; l = unimix_logprob(expf(x[c] - st.raw_max) / st.raw_sum, unimix, invK, pm); }
+    if (mix_out) mix_out[m * ldm + (long long)g * K + c] = l;
+    lgmax = fmaxf(lgmax, l - st.lse);
+  }
+  lgmax = warp_max(lgmax);
+  float psum = 0.f;
+  for (int c = lane; c < K; c += 32) {
+    float l = x[c];
+    if (unimix > 0.f) { float pm; l = unimix_logprob(expf(x[c] - st.raw_max) / st.raw_sum, unimix, invK, pm); }
+    psum += expf(l - st.lse - lgmax);
+  }
+  psum = warp_sum(psum);
+  if (!onehot) return;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int c = lane; c < K; c += 32) {
+    float l = x[c];
+    if (unimix > 0.f) { float pm; l = unimix_logprob(expf(x[c] - st.raw_max) / st.raw_sum, unimix, invK, pm); }
+    float p = expf(l - st.lse - lgmax) / psum;
+    if (noise) p = p / noise[m * ldn + (long long)g * K + c];
+    if (p > best) { best = p; besti = c; }  // strict > keeps the first maximum within a lane
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  for (int c = lane; c < K; c += 32) onehot[m * ldo + (long long)g * K + c] = (c == besti) ? 1.f : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+cat_sample_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ dz, const float* __restrict__ dmix,
+                      float* __restrict__ draw, long long M, int groups, int K, long long ldr, long long lddz,
+                      long long lddm, long long lddr, float unimix) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= M * groups) return;
+  const long long m = warp / groups;
+  const int g = (int)(warp - m * groups);
+  const long long go = (long long)g * K;
+  const float* x = raw + m * ldr + go;
+  const GroupStats st = group_stats(x, K, unimix, lane);
+  const float invK = 1.f / (float)K;
+  // pass 1: sum_c p_c * dz_c  (p = exp(l - lse): softmax of the normalised log-probs)
+  float pdz = 0.f;
+  if (dz) {
+    for (int c = lane; c < K; c += 32) {
+      float l = x[c];
+      if (unimix > 0.f) { float pm; l = unimix_logprob(expf(x[c] - st.raw_max) / st.raw_sum, unimix, invK, pm); }
+      pdz = fmaf(expf(l - st.lse), dz[m * lddz + go + c], pdz);
+    }
+    pdz = warp_sum(pdz);
+  }
+  // pass 2: g_c = dmix_c + p_c (dz_c - pdz); ds_c = g_c (1-u)/pm_c; sds = sum s_c ds_c
+  float sds = 0.f;
+  for (int c = lane; c < K; c += 32) {
+    const float s = expf(x[c] - st.raw_max) / st.raw_sum;
+    float pm = 0.f, l = x[c];
+    if (unimix > 0.f) l = unimix_logprob(s, unimix, invK, pm);
+    float gg = dmix ? dmix[m * lddm + go + c] : 0.f;
+    if (dz) gg += expf(l - st.lse) * (dz[m * lddz + go + c] - pdz);
+    if (unimix > 0.f) {
+      const bool inside = pm >= kFp32Eps && pm <= 1.f - kFp32Eps;
+      const float ds = inside ? gg * (1.f - unimix) / pm : 0.f;
+      sds = fmaf(s, ds, sds);
+    }
+  }
+  sds = warp_sum(sds);
+  for (int c = lane; c < K; c += 32) {
+    const float s = expf(x[c] - st.raw_max) / st.raw_sum;
+    float pm = 0.f, l = x[c];
+    if (unimix > 0.f) l = unimix_logprob(s, unimix, invK, pm);
+    float gg = dmix ? dmix[m * lddm + go + c] : 0.f;
+    if (dz) gg += expf(l - st.lse) * (dz[m * lddz + go + c] - pdz);
+    if (unimix > 0.f) {
+      const bool inside = pm >= kFp32Eps && pm <= 1.f - kFp32Eps;
+      const float ds = inside ? gg * (1.f - unimix) / pm : 0.f;
+      gg = s * (ds - sds);
+    }
+    draw[m * lddr + go + c] = gg;
+  }
+}
+
+// One block (8 warps) per row; warps loop over the groups.  Inputs are unimix log-probs.
+__global__ void __launch_bounds__(256)
+kl_loss_grad_kernel(const float* __restrict__ post, const float* __restrict__ prior, float* __restrict__ d_post,
+                    float* __restrict__ d_prior, float* __restrict__ rows, int groups, int K, long long ldp,
+                    long long ldq, long long lddp, long long lddq, float kl_dyn, float kl_rep, float free_nats,
+                    float coef /* scale * regularizer */) {
+  __shared__ float red[32];
+  const long long m = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* lp0 = post + m * ldp;
+  const float* lq0 = prior + m * ldq;
+  float kl = 0.f, hp = 0.f, hq = 0.f;
+  for (int g = wid; g < groups; g += nw) {
+    const float* a = lp0 + (long long)g * K;
+    const float* b = lq0 + (long long)g * K;
+    float ma = -INFINITY, mb = -INFINITY;
+    for (int c = lane; c < K; c += 32) { ma = fmaxf(ma, a[c]); mb = fmaxf(mb, b[c]); }
+    ma = warp_max(ma); mb = warp_max(mb);
+    float sa = 0.f, sb = 0.f;
+    for (int c = lane; c < K; c += 32) { sa += expf(a[c] - ma); sb += expf(b[c] - mb); }
+    const float lsea = ma + logf(warp_sum(sa)), lseb = mb + logf(warp_sum(sb));
+    float t = 0.f, ea = 0.f, eb = 0.f;
+    for (int c = lane; c < K; c += 32) {
+      const float lpa = a[c] - lsea, lqb = b[c] - lseb;
+      const float pa = expf(lpa), pb = expf(lqb);
+      t = fmaf(pa, lpa - lqb, t);
+      ea = fmaf(-pa, lpa, ea);
+      eb = fmaf(-pb, lqb, eb);
+    }
+    kl += t; hp += ea; hq += eb;  // per-lane partials; reduced below
+  }
+  kl = block_sum(kl, red);
+  hp = block_sum(hp, red);
+  hq = block_sum(hq, red);
+  if (threadIdx.x == 0) {
+    rows[m * 4 + 0] = kl;
+    rows[m * 4 + 1] = (kl_dyn + kl_rep) * fmaxf(kl, free_nats);
+    rows[m * 4 + 2] = hp;
+    rows[m * 4 + 3] = hq;
+  }
+  const float live = (kl > free_nats) ? coef : 0.f;
+  for (int g = wid; g < groups; g += nw) {
+    const float* a = lp0 + (long long)g * K;
+    const float* b = lq0 + (long long)g * K;
+    float ma = -INFINITY, mb = -INFINITY;
+    for (int c = lane; c < K; c += 32) { ma = fmaxf(ma, a[c]); mb = fmaxf(mb, b[c]); }
+    ma = warp_max(ma); mb = warp_max(mb);
+    float sa = 0.f, sb = 0.f;
+    for (int c = lane; c < K; c += 32) { sa += expf(a[c] - ma); sb += expf(b[c] - mb); }
+    const float lsea = ma + logf(warp_sum(sa)), lseb = mb + logf(warp_sum(sb));
+    float t = 0.f;
+    for (int c = lane; c < K; c += 32) {
+      const float lpa = a[c] - lsea, lqb = b[c] - lseb;
+      t = fmaf(expf(lpa), lpa - lqb, t);
+    }
+    const float klg = warp_sum(t);
+    for (int c = lane; c < K; c += 32) {
+      const float lpa = a[c] - lsea, lqb = b[c] - lseb;
+      const float pa = expf(lpa), pb = expf(lqb);
+      d_prior[m * lddq + (long long)g * K + c] = kl_dyn * live * (pb - pa);
+      d_post[m * lddp + (long long)g * K + c] = kl_rep * live * pa * ((lpa - lqb) - klg);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int b200rl_gru_gate_fwd(const float* G, const float* Hin, float* Hout, long long M, int R, long long ldg,
+                                   long long ldhi, long long ldho, cudaStream_t st) {
+  RL_CHECK_ARG(G && Hin && Hout, "null pointer");
+  if (M * R <= 0) return B200RL_OK;
+  gru_gate_fwd_kernel<<<ceil_div(M * R, 256), 256, 0, st>>>(G, Hin, Hout, M, R, ldg, ldhi, ldho);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_gru_gate_bwd(const float* G, const float* Hin, const float* dH, float* dG, float* dHin,
+                                   long long M, int R, long long ldg, long long ldhi, long long lddh, long long lddg,
+                                   long long lddhi, cudaStream_t st) {
+  RL_CHECK_ARG(G && Hin && dH && dG && dHin, "null pointer");
+  if (M * R <= 0) return B200RL_OK;
+  gru_gate_bwd_kernel<<<ceil_div(M * R, 256), 256, 0, st>>>(G, Hin, dH, dG, dHin, M, R, ldg, ldhi, lddh, lddg, lddhi);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_mask_mix(const float* prev, const float* init, const float* first, float* out, long long M,
+                               int C, long long ldp, long long ldo, cudaStream_t st) {
+  RL_CHECK_ARG(prev && first && out, "null pointer");
+  if (M * C <= 0) return B200RL_OK;
+  mask_mix_kernel<<<ceil_div(M * C, 256), 256, 0, st>>>(prev, init, first, out, M, C, ldp, ldo);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_mask_bwd(const float* dIn, const float* first, float* dPrev, float* dInit, int M, int C,
+                               long long ldi, long long ldp, cudaStream_t st) {
+  RL_CHECK_ARG(dIn && first && dPrev, "null pointer");
+  if (M <= 0 || C <= 0) return B200RL_OK;
+  mask_bwd_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dIn, first, dPrev, dInit, M, C, ldi, ldp);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_cat_sample(const float* raw, const float* noise, float* onehot, float* mix_out, long long M,
+                                 int groups, int K, long long ldr, long long ldn, long long ldo, long long ldm,
+                                 float unimix, cudaStream_t st) {
+  RL_CHECK_ARG(raw, "null pointer");
+  RL_CHECK_ARG(groups > 0 && K > 0, "bad groups / classes");
+  if (M <= 0) return B200RL_OK;
+  const long long warps = M * groups;
+  cat_sample_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(raw, noise, onehot, mix_out, M, groups, K, ldr, ldn, ldo, ldm,
+                                                        unimix);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_cat_sample_bwd(const float* raw, const float* dz, const float* dmix, float* draw, long long M,
+                                     int groups, int K, long long ldr, long long lddz, long long lddm,
+                                     long long lddr, float unimix, cudaStream_t st) {
+  RL_CHECK_ARG(raw && draw, "null pointer");
+  RL_CHECK_ARG(groups > 0 && K > 0, "bad groups / classes");
+  if (M <= 0) return B200RL_OK;
+  const long long warps = M * groups;
+  cat_sample_bwd_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(raw, dz, dmix, draw, M, groups, K, ldr, lddz, lddm, lddr,
+                                                            unimix);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_kl_loss_grad(const float* post_mix, const float* prior_mix, float* d_post, float* d_prior,
+                                   float* rows, long long M, int groups, int K, long long ldp, long long ldq,
+                                   long long lddp, long long lddq, float kl_dyn, float kl_rep, float free_nats,
+                                   float regularizer, float scale, cudaStream_t st) {
+  RL_CHECK_ARG(post_mix && prior_mix && d_post && d_prior && rows, "null pointer");
+  if (M <= 0) return B200RL_OK;
+  kl_loss_grad_kernel<<<(unsigned)M, 256, 0, st>>>(post_mix, prior_mix, d_post, d_prior, rows, groups, K, ldp, ldq,
+                                                   lddp, lddq, kl_dyn, kl_rep, free_nats, scale * regularizer);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}

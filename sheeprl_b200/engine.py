@@ -310,7 +310,8 @@ class DV3Engine:
         self.noise_post = b("noise_post", T, B, Z)
         self.noise_img_state = b("noise_img_state", H, N, Z)
         self.noise_img_action = b("noise_img_action", H + 1, N, A)
-        self.rng_seed, self.rng_calls = 0, 0
+        self.rng_seed = 0
+        self.rng_t = torch.zeros(1, dtype=torch.int32, device=self.device)   # device-side step counter for Philox
 
     def bytes_allocated(self) -> int:
         tot = sum(t.numel() * t.element_size() for t in self._bufs.values())
@@ -334,10 +335,10 @@ class DV3Engine:
         T, B, N, H, Z, R, L, A = self.T, self.B, self.N, self.H, self.Z, self.R, self.L, self.A
         a, w = self.cfg.algo, self.cfg.algo.world_model
         if noise is None:
-            self.rng_calls += 1
-            ops.fill_exponential(self.noise_post.view(-1), self.rng_seed, 3 * self.rng_calls)
-            ops.fill_exponential(self.noise_img_state.view(-1), self.rng_seed, 3 * self.rng_calls + 1)
-            ops.fill_exponential(self.noise_img_action.view(-1), self.rng_seed, 3 * self.rng_calls + 2)
+            ops.increment(self.rng_t)
+            ops.fill_exponential(self.noise_post.view(-1), self.rng_seed, 0, self.rng_t)
+            ops.fill_exponential(self.noise_img_state.view(-1), self.rng_seed, 1, self.rng_t)
+            ops.fill_exponential(self.noise_img_action.view(-1), self.rng_seed, 2, self.rng_t)
         else:
             self.noise_post.copy_(noise["post"].reshape(T, B, Z))
             self.noise_img_state.copy_(noise["img_state"].reshape(H, N, Z))

@@ -1,0 +1,354 @@
+"""ctypes binding of the C-ABI in `include/b200rl.h` (library: `sheeprl_b200/libb200rl.so`).
+
+`CudaOps` exposes one method per entry point, taking torch tensors purely as (device pointer, shape,
+leading dimension) carriers; all work is enqueued on torch's current CUDA stream.  There is NO
+fallback: constructing `CudaOps` without the built library or without an sm_100 GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200rl.so")
+
+c_int, c_ll, c_float, c_void_p = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+
+_lib = None
+
+
+class B200RLError(RuntimeError):
+    pass
+
+
+def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
+    """Loads the shared library (no GPU needed to load; kernels need one to run)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(path):
+            raise B200RLError(
+                f"{path} not found: build it with `python -m sheeprl_b200.build` (nvcc, sm_100a). "
+                "The B200 engine has no CPU / PyTorch fallback.")
+        _lib = ctypes.CDLL(path)
+        _lib.b200rl_last_error.restype = ctypes.c_char_p
+        _lib.b200rl_build_arch.restype = ctypes.c_char_p
+    return _lib
+
+
+def declared_symbols(header: Optional[str] = None) -> Sequence[str]:
+    """Names of every function declared in include/b200rl.h."""
+    import re
+
+    header = header or os.path.join(os.path.dirname(_HERE), "include", "b200rl.h")
+    src = open(header).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200rl_[a-z0-9_]+)\s*\(", src)))
+
+
+def _p(t: Optional[torch.Tensor]):
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Row stride of a 2-D view with unit inner stride (1-D tensors are single rows)."""
+    if t.dim() == 1:
+        assert t.numel() <= 1 or t.stride(0) == 1, "1-D views must be contiguous"
+        return max(t.numel(), 1)
+    assert t.dim() == 2, f"expected a 2-D view, got {tuple(t.shape)}"
+    assert t.shape[1] == 1 or t.stride(1) == 1, f"inner stride must be 1, got {t.stride()}"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _f32(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_cuda, (t.dtype, t.device)
+
+
+class CudaOps:
+    name = "cuda"
+
+    def __init__(self, device="cuda"):
+        if not torch.cuda.is_available():
+            raise B200RLError("no CUDA device visible: the B200 engine has no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.index is not None:
+            torch.cuda.set_device(self.device)
+        if self.lib.b200rl_device_check() != 0:
+            raise B200RLError(self.lib.b200rl_last_error().decode())
+        self.launches = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _st(self):
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _ck(self, rc: int):
+        self.launches += 1
+        if rc != 0:
+            raise B200RLError(self.lib.b200rl_last_error().decode())
+
+    # ------------------------------------------------------------------ GEMM family
+    def gemm(self, A, B, C, transA: bool, transB: bool, bias=None, accumulate: bool = False):
+        _f32(A, B, C, bias)
+        M, N = C.shape
+        K = A.shape[0] if transA else A.shape[1]
+        assert (A.shape[1] if transA else A.shape[0]) == M, (A.shape, C.shape, transA)
+        assert (B.shape[0] if transB else B.shape[1]) == N and (B.shape[1] if transB else B.shape[0]) == K, \
+            (A.shape, B.shape, C.shape, transA, transB)
+        self._ck(self.lib.b200rl_gemm_f32(_p(A), _p(B), _p(C), _p(bias), c_int(M), c_int(N), c_int(K), c_int(_ld(A)),
+                                          c_int(_ld(B)), c_int(_ld(C)), c_int(int(transA)), c_int(int(transB)),
+                                          c_int(int(accumulate)), self._st()))
+
+    def col_sum(self, X, out, accumulate: bool = False):
+        _f32(X, out)
+        self._ck(self.lib.b200rl_col_sum(_p(X), _p(out), c_ll(X.shape[0]), c_int(X.shape[1]), c_ll(_ld(X)),
+                                         c_int(int(accumulate)), self._st()))
+
+    def ln_act_fwd(self, X, gamma, beta, eps: float, act: int, Y):
+        _f32(X, gamma, beta, Y)
+        self._ck(self.lib.b200rl_ln_act_fwd(_p(X), _p(gamma), _p(beta), _p(Y), c_ll(X.shape[0]), c_int(X.shape[1]),
+                                            c_ll(_ld(X)), c_ll(_ld(Y)), c_float(eps), c_int(act), self._st()))
+
+    def ln_act_bwd(self, X, gamma, beta, eps: float, act: int, dY, dX, dgamma, dbeta, accumulate: bool = False):
+        _f32(X, gamma, beta, dY, dX, dgamma, dbeta)
+        self._ck(self.lib.b200rl_ln_act_bwd(_p(X), _p(gamma), _p(beta), _p(dY), _p(dX), _p(dgamma), _p(dbeta),
+                                            c_ll(X.shape[0]), c_int(X.shape[1]), c_ll(_ld(X)), c_ll(_ld(dY)),
+                                            c_ll(_ld(dX)), c_float(eps), c_int(act), c_int(int(accumulate)), self._st()))
+
+    # ------------------------------------------------------------------ convolutions
+    def obs_prep(self, obs, out):
+        assert obs.is_cuda and obs.is_contiguous() and out.is_contiguous()
+        assert obs.dtype in (torch.uint8, torch.float32), obs.dtype
+        NB, C, H, W = obs.shape
+        self._ck(self.lib.b200rl_obs_prep(_p(obs), c_int(int(obs.dtype == torch.uint8)), _p(out), c_ll(NB), c_int(C),
+                                          c_int(H * W), self._st()))
+
+    def transpose_batched(self, X, Y):
+        _f32(X, Y)
+        assert X.is_contiguous() and Y.is_contiguous()
+        NB, a, b = X.shape
+        self._ck(self.lib.b200rl_transpose_batched(_p(X), _p(Y), c_int(NB), c_int(a), c_int(b), self._st()))
+
+    def conv_down(self, big, W, small):
+        _f32(big, W, small)
+        assert big.is_contiguous() and small.is_contiguous() and W.is_contiguous()
+        NB, h, w, Cs = small.shape
+        Cb = big.shape[-1]
+        assert tuple(big.shape) == (NB, 2 * h, 2 * w, Cb) and tuple(W.shape) == (Cs, Cb, 4, 4)
+        self._ck(self.lib.b200rl_conv_down(_p(big), _p(W), _p(small), c_int(NB), c_int(h), c_int(w), c_int(Cs),
+                                           c_int(Cb), self._st()))
+
+    def conv_up(self, small, W, big, bias=None):
+        _f32(big, W, small, bias)
+        assert big.is_contiguous() and small.is_contiguous() and W.is_contiguous()
+        NB, h, w, Cs = small.shape
+        Cb = big.shape[-1]
+        assert tuple(big.shape) == (NB, 2 * h, 2 * w, Cb) and tuple(W.shape) == (Cs, Cb, 4, 4)
+        self._ck(self.lib.b200rl_conv_up(_p(small), _p(W), _p(big), _p(bias), c_int(NB), c_int(h), c_int(w), c_int(Cs),
+                                         c_int(Cb), self._st()))
+
+    def conv_wgrad(self, small, big, dW, accumulate: bool = False):
+        _f32(big, dW, small)
+        assert big.is_contiguous() and small.is_contiguous() and dW.is_contiguous()
+        NB, h, w, Cs = small.shape
+        Cb = big.shape[-1]
+        assert tuple(big.shape) == (NB, 2 * h, 2 * w, Cb) and tuple(dW.shape) == (Cs, Cb, 4, 4)
+        self._ck(self.lib.b200rl_conv_wgrad(_p(small), _p(big), _p(dW), c_int(NB), c_int(h), c_int(w), c_int(Cs),
+                                            c_int(Cb), c_int(int(accumulate)), self._st()))
+
+    # ------------------------------------------------------------------ RSSM pieces
+    def gru_gate_fwd(self, G, Hin, Hout):
+        _f32(G, Hin, Hout)
+        M, R = Hin.shape
+        self._ck(self.lib.b200rl_gru_gate_fwd(_p(G), _p(Hin), _p(Hout), c_ll(M), c_int(R), c_ll(_ld(G)), c_ll(_ld(Hin)),
+                                              c_ll(_ld(Hout)), self._st()))
+
+    def gru_gate_bwd(self, G, Hin, dH, dG, dHin):
+        _f32(G, Hin, dH, dG, dHin)
+        M, R = Hin.shape
+        self._ck(self.lib.b200rl_gru_gate_bwd(_p(G), _p(Hin), _p(dH), _p(dG), _p(dHin), c_ll(M), c_int(R), c_ll(_ld(G)),
+                                              c_ll(_ld(Hin)), c_ll(_ld(dH)), c_ll(_ld(dG)), c_ll(_ld(dHin)), self._st()))
+
+    def mask_mix(self, prev, init, first, out):
+        _f32(prev, init, first, out)
+        M, C = out.shape
+        self._ck(self.lib.b200rl_mask_mix(_p(prev), _p(init), _p(first), _p(out), c_ll(M), c_int(C), c_ll(_ld(prev)),
+                                          c_ll(_ld(out)), self._st()))
+
+    def mask_rows(self, X, first, out):
+        self.mask_mix(X, None, first, out)
+
+    def mask_bwd(self, dIn, first, dPrev, dInit):
+        _f32(dIn, first, dPrev, dInit)
+        M, C = dIn.shape
+        self._ck(self.lib.b200rl_mask_bwd(_p(dIn), _p(first), _p(dPrev), _p(dInit), c_int(M), c_int(C), c_ll(_ld(dIn)),
+                                          c_ll(_ld(dPrev)), self._st()))
+
+    def cat_sample(self, raw, noise, unimix: float, groups: int, classes: int, onehot, mix_out=None):
+        _f32(raw, noise, onehot, mix_out)
+        M = raw.shape[0]
+        if noise is not None and noise.dim() != 2:
+            noise = noise.reshape(M, -1)
+        self._ck(self.lib.b200rl_cat_sample(
+            _p(raw), _p(noise), _p(onehot), _p(mix_out), c_ll(M), c_int(groups), c_int(classes), c_ll(_ld(raw)),
+            c_ll(_ld(noise) if noise is not None else 0), c_ll(_ld(onehot) if onehot is not None else 0),
+            c_ll(_ld(mix_out) if mix_out is not None else 0), c_float(unimix), self._st()))
+
+    def cat_sample_bwd(self, raw, dz, dmix, unimix: float, groups: int, classes: int, draw):
+        _f32(raw, dz, dmix, draw)
+        M = raw.shape[0]
+        self._ck(self.lib.b200rl_cat_sample_bwd(
+            _p(raw), _p(dz), _p(dmix), _p(draw), c_ll(M), c_int(groups), c_int(classes), c_ll(_ld(raw)),
+            c_ll(_ld(dz) if dz is not None else 0), c_ll(_ld(dmix) if dmix is not None else 0), c_ll(_ld(draw)),
+            c_float(unimix), self._st()))
+
+    def kl_loss_grad(self, post_mix, prior_mix, groups, classes, kl_dyn, kl_rep, free_nats, regularizer, scale,
+                     d_post, d_prior, rows):
+        _f32(post_mix, prior_mix, d_post, d_prior, rows)
+        assert rows.is_contiguous() and rows.shape[1] == 4
+        self._ck(self.lib.b200rl_kl_loss_grad(
+            _p(post_mix), _p(prior_mix), _p(d_post), _p(d_prior), _p(rows), c_ll(post_mix.shape[0]), c_int(groups),
+            c_int(classes), c_ll(_ld(post_mix)), c_ll(_ld(prior_mix)), c_ll(_ld(d_post)), c_ll(_ld(d_prior)),
+            c_float(kl_dyn), c_float(kl_rep), c_float(free_nats), c_float(regularizer), c_float(scale), self._st()))
+
+    # ------------------------------------------------------------------ losses
+    def mse_loss_grad(self, pred, target, scale: float, loss_row, grad):
+        _f32(pred, target, loss_row, grad)
+        assert pred.is_contiguous() and target.is_contiguous() and grad.is_contiguous()
+        M, P = pred.shape
+        self._ck(self.lib.b200rl_mse_loss_grad(_p(pred), _p(target), _p(loss_row), _p(grad), c_ll(M), c_int(P),
+                                               c_float(scale), self._st()))
+
+    def twohot_loss_grad(self, logits, x, weight, scale, low, high, loss_row, dlogits, accumulate: bool = False):
+        _f32(logits, x, weight, loss_row, dlogits)
+        M, nb = logits.shape
+        assert x.numel() == M and x.is_contiguous()
+        self._ck(self.lib.b200rl_twohot_loss_grad(
+            _p(logits), _p(x), _p(weight), _p(loss_row), _p(dlogits), c_ll(M), c_int(nb), c_ll(_ld(logits)),
+            c_ll(_ld(dlogits)), c_float(low), c_float(high), c_float(scale), c_int(int(accumulate)), self._st()))
+
+    def bce_loss_grad(self, logit, target, loss_scale, scale, loss_row, dlogit):
+        _f32(logit, target, loss_row, dlogit)
+        assert logit.is_contiguous() and target.is_contiguous() and dlogit.is_contiguous()
+        self._ck(self.lib.b200rl_bce_loss_grad(_p(logit), _p(target), _p(loss_row), _p(dlogit), c_ll(logit.numel()),
+                                               c_float(loss_scale), c_float(scale), self._st()))
+
+    def twohot_mean(self, logits, low, high, out):
+        _f32(logits, out)
+        self._ck(self.lib.b200rl_twohot_mean(_p(logits), _p(out), c_ll(logits.shape[0]), c_int(logits.shape[1]),
+                                             c_ll(_ld(logits)), c_float(low), c_float(high), self._st()))
+
+    def lambda_returns(self, rew, val, cont_logit, true_cont, gamma, lmbda, lam, discount):
+        _f32(rew, val, cont_logit, true_cont, lam, discount)
+        for t in (rew, val, cont_logit, lam, discount):
+            assert t.is_contiguous()
+        H, N = lam.shape
+        self._ck(self.lib.b200rl_lambda_returns(_p(rew), _p(val), _p(cont_logit), _p(true_cont), _p(lam), _p(discount),
+                                                c_int(H), c_int(N), c_float(gamma), c_float(lmbda), self._st()))
+
+    def moments_update(self, x, state, decay, max_, p_low, p_high, out):
+        _f32(x, state, out)
+        assert x.is_contiguous()
+        self._ck(self.lib.b200rl_moments_update(_p(x), c_ll(x.numel()), _p(state), _p(out), c_float(decay),
+                                                c_float(max_), c_float(p_low), c_float(p_high), self._st()))
+
+    def actor_loss_grad(self, raw, actions, lam, val, discount, moments, head_dims, unimix, ent_coef, scale, rows,
+                        draw):
+        _f32(raw, actions, lam, val, discount, moments, rows, draw)
+        for t in (raw, actions, draw):
+            assert t.is_contiguous()
+        hd = (c_int * len(head_dims))(*[int(x) for x in head_dims])
+        self._ck(self.lib.b200rl_actor_loss_grad(_p(raw), _p(actions), _p(lam), _p(val), _p(discount), _p(moments),
+                                                 _p(rows), _p(draw), c_ll(raw.shape[0]), hd, c_int(len(head_dims)),
+                                                 c_float(unimix), c_float(ent_coef), c_float(scale), self._st()))
+
+    def sum_rows(self, X, out, scale: float):
+        _f32(X, out)
+        self._ck(self.lib.b200rl_sum_rows(_p(X), _p(out), c_ll(X.shape[0]), c_int(X.shape[1]), c_ll(_ld(X)),
+                                          c_float(scale), self._st()))
+
+    def weighted_mean(self, x, w, scale: float, out):
+        _f32(x, w, out)
+        self._ck(self.lib.b200rl_weighted_mean(_p(x), _p(w), _p(out), c_ll(x.numel()), c_float(scale), self._st()))
+
+    # ------------------------------------------------------------------ optimiser / utilities
+    def sumsq(self, x, out):
+        assert out.dtype == torch.float64 and x.is_contiguous()
+        self._ck(self.lib.b200rl_sumsq(_p(x), c_ll(x.numel()), _p(out), self._st()))
+
+    def adam_step(self, p, g, m, v, normsq, max_norm, lr, b1, b2, eps, step_t, norm_out):
+        _f32(p, g, m, v, norm_out)
+        assert step_t.dtype == torch.int32 and normsq.dtype == torch.float64
+        self._ck(self.lib.b200rl_adam_step(_p(p), _p(g), _p(m), _p(v), _p(normsq), _p(step_t), _p(norm_out),
+                                           c_ll(p.numel()), c_float(max_norm), c_float(lr), c_float(b1), c_float(b2),
+                                           c_float(eps), self._st()))
+
+    def ema(self, target, src, tau: float):
+        _f32(target, src)
+        self._ck(self.lib.b200rl_ema(_p(target), _p(src), c_ll(target.numel()), c_float(tau), self._st()))
+
+    def fill_exponential(self, out, seed: int, stream_id: int, counter=None):
+        """Exp(1) noise from Philox4x32-10 keyed by (seed, stream_id, *counter); `counter` is a device int32
+        incremented once per train step so that graph replays draw fresh noise."""
+        _f32(out)
+        assert out.is_contiguous()
+        self._ck(self.lib.b200rl_fill_exponential(_p(out), c_ll(out.numel()), ctypes.c_ulonglong(seed & (2 ** 64 - 1)),
+                                                  ctypes.c_uint(stream_id & 0xFFFFFFFF), _p(counter), self._st()))
+
+    def increment(self, step_t):
+        self._ck(self.lib.b200rl_increment(_p(step_t), self._st()))
+
+    def zero(self, x):
+        assert x.is_contiguous()
+        if x.dtype == torch.float32:
+            self._ck(self.lib.b200rl_zero(_p(x), c_ll(x.numel()), self._st()))
+        else:
+            x.zero_()
+
+    def copy(self, src, dst):
+        _f32(src, dst)
+        if src.dim() == 1:
+            src, dst = src.view(1, -1), dst.view(1, -1)
+        M, C = src.shape
+        self._ck(self.lib.b200rl_copy2d(_p(src), _p(dst), c_ll(M), c_int(C), c_ll(_ld(src)), c_ll(_ld(dst)), self._st()))
+
+    def axpy(self, x, y, alpha: float = 1.0):
+        _f32(x, y)
+        assert x.is_contiguous() and y.is_contiguous()
+        self._ck(self.lib.b200rl_axpy(_p(x), _p(y), c_ll(x.numel()), c_float(alpha), self._st()))
+
+    def affine(self, x, out, alpha: float, beta: float):
+        _f32(x, out)
+        assert x.is_contiguous() and out.is_contiguous()
+        self._ck(self.lib.b200rl_affine(_p(x), _p(out), c_ll(x.numel()), c_float(alpha), c_float(beta), self._st()))
+
+    def tanh_fwd(self, x, y):
+        _f32(x, y)
+        self._ck(self.lib.b200rl_tanh_fwd(_p(x), _p(y), c_ll(x.numel()), self._st()))
+
+    def tanh_bwd(self, y, dy, dx, accumulate: bool = False):
+        _f32(y, dy, dx)
+        self._ck(self.lib.b200rl_tanh_bwd(_p(y), _p(dy), _p(dx), c_ll(y.numel()), c_int(int(accumulate)), self._st()))
+
+    # ------------------------------------------------------------------ replay / PPO
+    def replay_gather(self, storage, idx, out, n_samples: int, batch: int, seq_len: int):
+        assert storage.is_contiguous() and out.is_contiguous() and idx.dtype == torch.int64 and idx.is_contiguous()
+        row_bytes = storage[0].numel() * storage.element_size()
+        self._ck(self.lib.b200rl_replay_gather(_p(storage), _p(idx), _p(out), c_int(n_samples), c_int(batch),
+                                               c_int(seq_len), c_ll(row_bytes), self._st()))
+
+    def replay_scatter(self, src, dst_rows, storage):
+        assert storage.is_contiguous() and src.is_contiguous() and dst_rows.dtype == torch.int64
+        row_bytes = storage[0].numel() * storage.element_size()
+        self._ck(self.lib.b200rl_replay_scatter(_p(src), _p(dst_rows), _p(storage), c_ll(dst_rows.numel()),
+                                                c_ll(row_bytes), self._st()))
+
+    def gae(self, rewards, values, dones, next_value, gamma, lmbda, returns, advantages):
+        _f32(rewards, values, dones, next_value, returns, advantages)
+        T, E = rewards.shape[0], rewards[0].numel()
+        self._ck(self.lib.b200rl_gae(_p(rewards), _p(values), _p(dones), _p(next_value), _p(returns), _p(advantages),
+                                     c_int(T), c_int(E), c_float(gamma), c_float(lmbda), self._st()))

@@ -1,0 +1,131 @@
+"""End-to-end parity of the CUDA engine (every op through the C-ABI) on a B200:
+  * against the committed reference fixtures (tests/golden, produced by the unmodified reference train());
+  * against the oracle on the BASELINE config (S, B=16, T=64, H=15), incl. gradients;
+  * size-independent properties at full size (finite, deterministic replay, sample one-hotness)."""
+import pytest
+import torch
+
+from tests.helpers import assert_params_close, load_fixture, oracle_run
+
+pytestmark = pytest.mark.gpu
+
+
+def to_cuda(d):
+    return {k: (v.cuda() if torch.is_tensor(v) else [x.cuda() for x in v]) for k, v in d.items()}
+
+
+def make_engine(cfg, adim, init):
+    from sheeprl_b200.engine import DV3Engine
+
+    eng = DV3Engine(cfg, adim, in_channels=3, device="cuda")
+    eng.wm.load(init["wm"]), eng.actor.load(init["actor"]), eng.critic.load(init["critic"])
+    eng.target.load(init["target"])
+    return eng
+
+
+def check_grads(eng_grads, o_out, cfg, rtol):
+    for grp, max_norm, nm in (("wm", cfg.algo.world_model.clip_gradients, "world_model"),
+                              ("actor", cfg.algo.actor.clip_gradients, "actor"),
+                              ("critic", cfg.algo.critic.clip_gradients, "critic")):
+        og = o_out[f"grads/{grp}"]
+        coef = min(1.0, max_norm / (float(o_out["Grads/" + nm]) + 1e-6))
+        gmax = max(float(v.abs().max()) for v in og.values())
+        for k, v in og.items():
+            d = float((eng_grads[grp][k].cpu() * coef - v).abs().max())
+            assert d <= rtol * max(gmax, 1e-12) + 1e-9, (grp, k, d, gmax)
+
+
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b"])
+def test_engine_cuda_matches_reference_fixture(name):
+    fx, cfg = load_fixture(name)
+    adim = fx["actions_dim"]
+    steps = len(fx["data"])
+    st, o_outs, ms, _ = oracle_run(cfg, adim, fx["init"], fx["data"], fx["noise"], steps, keep=True)
+    eng = make_engine(cfg, adim, fx["init"])
+    for s in range(steps):
+        batch = {k: v.clone().float().cuda() for k, v in fx["data"][s].items()}
+        eng.train_step(batch, to_cuda(fx["noise"][s]))
+        if s == 0:
+            grads = {g: {k: v.clone() for k, v in getattr(eng, g).gviews.items()} for g in ("wm", "actor", "critic")}
+            check_grads(grads, o_outs[0], cfg, 3e-5)
+        got = {k: float(v) for k, v in eng.metrics_dict().items()}
+        for k, v in fx["metrics"][s].items():
+            assert got[k] == pytest.approx(v, rel=1e-4, abs=1e-6), (s, k)
+    lrs = {"wm": 1e-4, "actor": 8e-5, "critic": 8e-5}
+    for n, g in (("wm", eng.wm), ("actor", eng.actor), ("critic", eng.critic)):
+        assert_params_close({k: v.cpu() for k, v in g.views.items()}, fx["after"][n], lrs[n], steps, tol=3e-6, label=n)
+    assert float(eng.moments_state[0]) == pytest.approx(float(fx["moments"]["low"]), rel=1e-4, abs=1e-7)
+    assert float(eng.moments_state[1]) == pytest.approx(float(fx["moments"]["high"]), rel=1e-4, abs=1e-7)
+
+
+def test_engine_cuda_baseline_config_vs_oracle_and_reference_digest():
+    """BASELINE.json configs[1]: Dreamer-V3 S, 64x64x3, bs16 seq64 horizon15.  Tolerance 1e-4 (north_star)."""
+    from oracle import dv3_oracle as O
+    from oracle.make_golden import perturbed_oracle_init, subsample
+
+    fx, cfg = load_fixture("dv3_S_digest")
+    adim = fx["actions_dim"]
+    a, w = cfg.algo, cfg.algo.world_model
+    init = perturbed_oracle_init(cfg, adim, fx["init_seed"], fx["perturb"])
+    data = [O.make_batch(cfg, adim, seed=fx["data_seed"])]
+    noise = [O.draw_noise(a.per_rank_sequence_length, a.per_rank_batch_size, a.horizon, w.stochastic_size,
+                          w.discrete_size, adim, seed=fx["noise_seed"])]
+    st, o_outs, ms, _ = oracle_run(cfg, adim, init, data, noise, 1, condition_margin=1e-3, keep=True)
+    eng = make_engine(cfg, adim, init)
+    batch = {k: v.clone().cuda() for k, v in data[0].items()}
+    batch["rgb"] = batch["rgb"].to(torch.uint8)          # uint8 fast path (values are integral)
+    eng.train_step(batch, to_cuda(noise[0]))
+    torch.cuda.synchronize()
+    # intermediates named in SURVEY.md §8a
+    N = eng.N
+    assert torch.equal(eng.latent[:, : eng.Z].cpu().reshape(o_outs[0]["latent"][..., : eng.Z].shape),
+                       o_outs[0]["latent"][..., : eng.Z].round()), "posterior samples differ"
+    for nm, got, want in (("h", eng.latent[:, eng.Z:], o_outs[0]["latent"][..., eng.Z:].reshape(N, -1)),
+                          ("post_logits", eng.post_mix, o_outs[0]["post_logits"].reshape(N, -1)),
+                          ("prior_logits", eng.prior_mix, o_outs[0]["prior_logits"].reshape(N, -1)),
+                          ("emb", eng.emb, o_outs[0]["emb"].reshape(N, -1)),
+                          ("lambda", eng.lam, o_outs[0]["lambda_values"].squeeze(-1)),
+                          ("values", eng.values, o_outs[0]["values"].squeeze(-1)),
+                          ("discount", eng.discount, o_outs[0]["discount"].squeeze(-1))):
+        err = float((got.cpu() - want).abs().max())
+        assert err <= 1e-4 * max(1.0, float(want.abs().max())), (nm, err)
+    assert torch.equal(eng.actions.cpu(), o_outs[0]["imagined_actions"].round()), "imagined actions differ"
+    assert torch.equal(eng.traj[:, :, : eng.Z].cpu(), o_outs[0]["traj"][:, :, : eng.Z].round()), "imagined states differ"
+    grads = {g: {k: v.clone() for k, v in getattr(eng, g).gviews.items()} for g in ("wm", "actor", "critic")}
+    check_grads(grads, o_outs[0], cfg, 1e-4)
+    got = {k: float(v) for k, v in eng.metrics_dict().items()}
+    for k, v in fx["metrics"][0].items():                 # numbers produced by the REAL reference
+        assert got[k] == pytest.approx(v, rel=1e-4, abs=1e-6), k
+    for n, g in (("wm", eng.wm), ("actor", eng.actor), ("critic", eng.critic)):
+        sub = {k: subsample(v.cpu()) for k, v in g.views.items()}
+        assert_params_close(sub, fx["after_sub"][n], 1e-4, 1, tol=3e-6, frac=5e-3, label=n)
+        assert_params_close({k: v.cpu() for k, v in g.views.items()}, st[n], 1e-4, 1, tol=3e-6, frac=2e-3, label=n)
+
+
+def test_engine_cuda_full_size_properties():
+    """Size-independent properties at the BASELINE config with on-device Philox noise."""
+    from oracle import dv3_oracle as O
+    from sheeprl_b200.configs import make_dv3_cfg
+
+    cfg = make_dv3_cfg("S")
+    adim = (2,)
+    wm, actor, critic, target = O.init_params(cfg, adim, seed=0)
+    init = {"wm": wm, "actor": actor, "critic": critic, "target": target}
+    data = O.make_batch(cfg, adim, seed=3, as_uint8=True)
+    runs = []
+    for rep in range(2):
+        eng = make_engine(cfg, adim, init)
+        eng.rng_seed = 99
+        for s in range(2):
+            eng.train_step({k: v.clone().cuda() for k, v in data.items()}, None)
+        torch.cuda.synchronize()
+        runs.append((eng.metrics.clone().cpu(), eng.traj[:, :, : eng.Z].clone().cpu(), eng.wm.flat.clone().cpu()))
+        z = eng.traj[:, :, : eng.Z].reshape(-1, eng.S, eng.D)
+        assert torch.all(z.sum(-1) == 1) and torch.all((z == 0) | (z == 1)), "states are not one-hot per group"
+        assert torch.isfinite(eng.metrics).all() and torch.isfinite(eng.wm.flat).all()
+        assert torch.isfinite(eng.actor.flat).all() and torch.isfinite(eng.critic.flat).all()
+        d = eng.discount
+        assert torch.all(d[1:] <= d[:-1] + 1e-6), "discount must be non-increasing along the horizon"
+    # same seed -> same samples; metrics agree to fp32-atomics noise
+    assert torch.equal(runs[0][1], runs[1][1])
+    assert float((runs[0][0] - runs[1][0]).abs().max()) <= 1e-4 * float(runs[0][0].abs().max())

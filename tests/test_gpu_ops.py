@@ -1,0 +1,390 @@
+"""Per-kernel parity: every C-ABI op (called through ctypes) against its executable specification
+(oracle/ops_emul.py, fp32 torch on CPU) on seeded inputs.  Tolerances are fp32 round-off scaled by the
+reduction length; integer / index outputs (samples, gathers) must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.ops_emul import EmulOps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from sheeprl_b200.lib import CudaOps
+
+    return CudaOps("cuda"), EmulOps()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def close(got, want, rtol=1e-5, atol=1e-6, what=""):
+    got = got.detach().float().cpu()
+    want = want.detach().float().cpu()
+    err = (got - want).abs()
+    bound = atol + rtol * want.abs().max()
+    assert float(err.max()) <= float(bound), (what, float(err.max()), float(bound))
+
+
+def run_both(ops, name, tensors, *scalars, outputs, **kw):
+    """tensors: dict name -> CPU tensor (None allowed). Runs op `name` on both backends with the tensors
+    passed positionally in dict order, returns {out_name: (cuda_result, cpu_result)}."""
+    cu, em = ops
+    cpu = {k: (v.clone() if v is not None else None) for k, v in tensors.items()}
+    gpu = {k: (v.clone().cuda() if v is not None else None) for k, v in tensors.items()}
+    return cu, em, cpu, gpu
+
+
+GEMM_SHAPES = [
+    (16, 512, 1026, False, True), (16, 1536, 1024, False, True), (16, 1024, 512, False, False),
+    (1024, 512, 1536, False, True), (1024, 1536, 255, False, False), (255, 512, 1024, True, False),
+    (300, 70, 33, False, True), (7, 3, 5, False, True), (5, 1, 129, False, True), (1000, 2, 512, False, True),
+    (2, 512, 1000, True, False), (130, 130, 70, True, True), (64, 4096, 200, False, True),
+]
+
+
+@pytest.mark.parametrize("M,N,K,tA,tB", GEMM_SHAPES)
+@pytest.mark.parametrize("mode", ["plain", "bias", "acc", "strided"])
+def test_gemm(ops, M, N, K, tA, tB, mode):
+    cu, em = ops
+    A = rnd(*((K, M) if tA else (M, K)), seed=1)
+    B = rnd(*((N, K) if tB else (K, N)), seed=2)
+    C0 = rnd(M, N, seed=3)
+    bias = rnd(N, seed=4) if mode == "bias" else None
+    acc = mode == "acc"
+    if mode == "strided":
+        # operands are column slices of wider buffers (leading dimension > width)
+        Aw = rnd(A.shape[0], A.shape[1] + 5, seed=5)
+        Bw = rnd(B.shape[0], B.shape[1] + 3, seed=6)
+        Cw = rnd(M, N + 7, seed=7)
+        Ac, Bc, Cc = Aw[:, 2:2 + A.shape[1]], Bw[:, 1:1 + B.shape[1]], Cw.clone()[:, 4:4 + N]
+        Awg, Bwg, Cwg = Aw.cuda(), Bw.cuda(), Cw.cuda()
+        Ag, Bg, Cg = Awg[:, 2:2 + A.shape[1]], Bwg[:, 1:1 + B.shape[1]], Cwg[:, 4:4 + N]
+        em.gemm(Ac, Bc, Cc, tA, tB)
+        cu.gemm(Ag, Bg, Cg, tA, tB)
+        close(Cg, Cc, rtol=2e-6 * max(K, 8) ** 0.5, what="gemm strided")
+        assert torch.equal(Cwg[:, :4].cpu(), Cw[:, :4]) and torch.equal(Cwg[:, 4 + N:].cpu(), Cw[:, 4 + N:])
+        return
+    Cc, Cg = C0.clone(), C0.clone().cuda()
+    em.gemm(A, B, Cc, tA, tB, bias=bias, accumulate=acc)
+    cu.gemm(A.cuda(), B.cuda(), Cg, tA, tB, bias=None if bias is None else bias.cuda(), accumulate=acc)
+    close(Cg, Cc, rtol=2e-6 * max(K, 8) ** 0.5, what="gemm")
+
+
+@pytest.mark.parametrize("M,C", [(1024, 512), (1000, 32), (16, 1536), (37, 72), (5, 4), (4096, 255), (64, 3)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_ln_act(ops, M, C, act):
+    cu, em = ops
+    X, gam, bet, dY = rnd(M, C, seed=1, scale=2.0), rnd(C, seed=2) + 1.0, rnd(C, seed=3), rnd(M, C, seed=4)
+    Yc = torch.empty(M, C)
+    Yg = torch.empty(M, C, device="cuda")
+    em.ln_act_fwd(X, gam, bet, 1e-3, act, Yc)
+    cu.ln_act_fwd(X.cuda(), gam.cuda(), bet.cuda(), 1e-3, act, Yg)
+    close(Yg, Yc, what="ln fwd")
+    dXc, dgc, dbc = torch.empty(M, C), torch.empty(C), torch.empty(C)
+    dXg, dgg, dbg = torch.empty(M, C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    em.ln_act_bwd(X, gam, bet, 1e-3, act, dY, dXc, dgc, dbc)
+    cu.ln_act_bwd(X.cuda(), gam.cuda(), bet.cuda(), 1e-3, act, dY.cuda(), dXg, dgg, dbg)
+    close(dXg, dXc, rtol=2e-5, what="ln dX")
+    close(dgg, dgc, rtol=2e-5 * max(M, 16) ** 0.5 / 4, what="ln dgamma")
+    close(dbg, dbc, rtol=2e-5 * max(M, 16) ** 0.5 / 4, what="ln dbeta")
+    # in-place (dX aliases dY), no parameter grads
+    dYg = dY.cuda()
+    cu.ln_act_bwd(X.cuda(), gam.cuda(), bet.cuda(), 1e-3, act, dYg, dYg, None, None)
+    close(dYg, dXc, rtol=2e-5, what="ln dX in place")
+
+
+@pytest.mark.parametrize("M,C", [(1024, 255), (1048576 // 64, 3), (17, 4096), (3, 1)])
+def test_col_sum(ops, M, C):
+    cu, em = ops
+    X = rnd(M, C, seed=1)
+    oc, og = torch.zeros(C), torch.full((C,), 5.0, device="cuda")
+    em.col_sum(X, oc)
+    cu.col_sum(X.cuda(), og)
+    close(og, oc, rtol=1e-5 * max(M, 16) ** 0.5, what="col_sum")
+
+
+CONV_SHAPES = [(3, 8, 8, 16, 8), (2, 4, 4, 32, 16), (5, 16, 16, 4, 3), (2, 32, 32, 32, 3), (3, 2, 2, 40, 24),
+               (2, 4, 4, 130, 72), (1, 8, 8, 8, 2)]
+
+
+@pytest.mark.parametrize("NB,h,w,Cs,Cb", CONV_SHAPES)
+def test_conv_down_up_wgrad(ops, NB, h, w, Cs, Cb):
+    cu, em = ops
+    big, small = rnd(NB, 2 * h, 2 * w, Cb, seed=1), rnd(NB, h, w, Cs, seed=2)
+    W, bias = rnd(Cs, Cb, 4, 4, seed=3, scale=0.2), rnd(Cb, seed=4)
+    oc, og = torch.empty_like(small), torch.empty_like(small).cuda()
+    em.conv_down(big, W, oc)
+    cu.conv_down(big.cuda(), W.cuda(), og)
+    close(og, oc, rtol=3e-6 * (16 * Cb) ** 0.5, what="conv_down")
+    for b in (None, bias):
+        oc, og = torch.empty_like(big), torch.empty_like(big).cuda()
+        em.conv_up(small, W, oc, b)
+        cu.conv_up(small.cuda(), W.cuda(), og, None if b is None else b.cuda())
+        close(og, oc, rtol=3e-6 * (4 * Cs) ** 0.5, what="conv_up")
+    oc, og = torch.empty_like(W), torch.full_like(W, 3.0).cuda()
+    em.conv_wgrad(small, big, oc)
+    cu.conv_wgrad(small.cuda(), big.cuda(), og)
+    close(og, oc, rtol=3e-6 * (NB * h * w) ** 0.5, what="conv_wgrad")
+
+
+def test_obs_prep_and_transpose(ops):
+    cu, em = ops
+    g = torch.Generator().manual_seed(0)
+    obs = torch.randint(0, 256, (6, 3, 16, 16), generator=g, dtype=torch.uint8)
+    for o in (obs, obs.float()):
+        oc, og = torch.empty(6, 16, 16, 3), torch.empty(6, 16, 16, 3, device="cuda")
+        em.obs_prep(o, oc)
+        cu.obs_prep(o.cuda(), og)
+        assert torch.equal(og.cpu(), oc)
+    X = rnd(7, 16, 40, seed=1)
+    Yc, Yg = torch.empty(7, 40, 16), torch.empty(7, 40, 16, device="cuda")
+    em.transpose_batched(X, Yc)
+    cu.transpose_batched(X.cuda(), Yg)
+    assert torch.equal(Yg.cpu(), Yc)
+
+
+@pytest.mark.parametrize("M,R", [(16, 512), (1024, 24), (3, 7)])
+def test_gru_gate(ops, M, R):
+    cu, em = ops
+    G, Hin, dH = rnd(M, 3 * R, seed=1), rnd(M, R, seed=2), rnd(M, R, seed=3)
+    oc, og = torch.empty(M, R), torch.empty(M, R, device="cuda")
+    em.gru_gate_fwd(G, Hin, oc)
+    cu.gru_gate_fwd(G.cuda(), Hin.cuda(), og)
+    close(og, oc, what="gru fwd")
+    dGc, dHc = torch.empty(M, 3 * R), torch.empty(M, R)
+    dGg, dHg = torch.empty(M, 3 * R, device="cuda"), torch.empty(M, R, device="cuda")
+    em.gru_gate_bwd(G, Hin, dH, dGc, dHc)
+    cu.gru_gate_bwd(G.cuda(), Hin.cuda(), dH.cuda(), dGg, dHg)
+    close(dGg, dGc, what="gru dG")
+    close(dHg, dHc, what="gru dHin")
+
+
+def test_masks(ops):
+    cu, em = ops
+    M, C = 16, 100
+    prev, init, dIn = rnd(M, C, seed=1), rnd(1, C, seed=2), rnd(M, C, seed=3)
+    first = (torch.rand(M, generator=torch.Generator().manual_seed(4)) < 0.3).float()
+    oc, og = torch.empty(M, C), torch.empty(M, C, device="cuda")
+    em.mask_mix(prev, init, first, oc)
+    cu.mask_mix(prev.cuda(), init.cuda(), first.cuda(), og)
+    close(og, oc, what="mask_mix")
+    em.mask_rows(prev, first, oc)
+    cu.mask_rows(prev.cuda(), first.cuda(), og)
+    close(og, oc, what="mask_rows")
+    dpc, dic = torch.empty(M, C), torch.ones(C)
+    dpg, dig = torch.empty(M, C, device="cuda"), torch.ones(C, device="cuda")
+    em.mask_bwd(dIn, first, dpc, dic)
+    cu.mask_bwd(dIn.cuda(), first.cuda(), dpg, dig)
+    close(dpg, dpc, what="mask_bwd prev")
+    close(dig, dic, what="mask_bwd init")
+
+
+@pytest.mark.parametrize("M,S,D", [(16, 32, 32), (1024, 32, 32), (9, 6, 5), (33, 1, 2), (12, 1, 18), (5, 4, 40)])
+@pytest.mark.parametrize("unimix", [0.01, 0.0])
+def test_cat_sample_fwd_bwd(ops, M, S, D, unimix):
+    cu, em = ops
+    raw = rnd(M, S * D, seed=1, scale=2.0)
+    q = torch.empty(M, S * D).exponential_(1.0, generator=torch.Generator().manual_seed(2))
+    for noise in (q, None):
+        hc, mc = torch.empty(M, S * D), torch.empty(M, S * D)
+        hg, mg = torch.empty(M, S * D, device="cuda"), torch.empty(M, S * D, device="cuda")
+        em.cat_sample(raw, noise, unimix, S, D, hc, mc)
+        cu.cat_sample(raw.cuda(), None if noise is None else noise.cuda(), unimix, S, D, hg, mg)
+        close(mg, mc, rtol=2e-6, atol=2e-6, what="unimix logits")
+        mism = (hg.cpu() != hc).reshape(M * S, D).any(-1).float().mean()
+        assert float(mism) <= 1e-3, float(mism)  # only exact near-ties of p/q may differ
+    dz, dmix = rnd(M, S * D, seed=3), rnd(M, S * D, seed=4)
+    for a, b in ((dz, dmix), (dz, None), (None, dmix)):
+        oc, og = torch.empty(M, S * D), torch.empty(M, S * D, device="cuda")
+        em.cat_sample_bwd(raw, a, b, unimix, S, D, oc)
+        cu.cat_sample_bwd(raw.cuda(), None if a is None else a.cuda(), None if b is None else b.cuda(), unimix, S, D, og)
+        close(og, oc, rtol=1e-5, what="cat_sample_bwd")
+
+
+@pytest.mark.parametrize("M,S,D,free", [(1024, 32, 32, 1.0), (64, 6, 5, 0.05), (16, 4, 8, 100.0)])
+def test_kl_loss_grad(ops, M, S, D, free):
+    cu, em = ops
+    post = torch.log_softmax(rnd(M, S, D, seed=1), -1).reshape(M, -1) + 0.01
+    prior = torch.log_softmax(rnd(M, S, D, seed=2), -1).reshape(M, -1)
+    outs_c = [torch.empty(M, S * D), torch.empty(M, S * D), torch.empty(M, 4)]
+    outs_g = [t.cuda() for t in outs_c]
+    em.kl_loss_grad(post, prior, S, D, 0.5, 0.1, free, 1.0, 1.0 / M, *outs_c)
+    cu.kl_loss_grad(post.cuda(), prior.cuda(), S, D, 0.5, 0.1, free, 1.0, 1.0 / M, *outs_g)
+    for g, c, n in zip(outs_g, outs_c, ("d_post", "d_prior", "rows")):
+        close(g, c, rtol=2e-5, what=n)
+
+
+def test_losses(ops):
+    cu, em = ops
+    M, P, nb = 96, 12288, 255
+    pred, tgt = rnd(M, P, seed=1), rnd(M, P, seed=2)
+    lc, gc = torch.empty(M), torch.empty(M, P)
+    lg, pg = torch.empty(M, device="cuda"), pred.cuda()
+    em.mse_loss_grad(pred, tgt, 1.0 / M, lc, gc)
+    cu.mse_loss_grad(pg, tgt.cuda(), 1.0 / M, lg, pg)  # in place
+    close(lg, lc, rtol=1e-5, what="mse loss")
+    close(pg, gc, what="mse grad")
+    logits = rnd(M, nb, seed=3, scale=2.0)
+    x = torch.cat((rnd(M - 6, seed=4, scale=30.0), torch.tensor([0.0, 1e9, -1e9, 20.0, -20.0, 0.157])))
+    w = torch.rand(M, generator=torch.Generator().manual_seed(5))
+    for weight in (None, w):
+        lc, dc = torch.zeros(M), torch.zeros(M, nb)
+        lg, dg = torch.zeros(M, device="cuda"), torch.zeros(M, nb, device="cuda")
+        for accumulate in (False, True):
+            em.twohot_loss_grad(logits, x, weight, 1.0 / M, -20.0, 20.0, lc, dc, accumulate)
+            cu.twohot_loss_grad(logits.cuda(), x.cuda(), None if weight is None else weight.cuda(), 1.0 / M, -20.0,
+                                20.0, lg, dg, accumulate)
+        close(lg, lc, rtol=1e-5, what="twohot loss")
+        close(dg, dc, rtol=1e-5, what="twohot grad")
+    oc, og = torch.empty(M), torch.empty(M, device="cuda")
+    em.twohot_mean(logits, -20.0, 20.0, oc)
+    cu.twohot_mean(logits.cuda(), -20.0, 20.0, og)
+    close(og, oc, rtol=2e-5, what="twohot mean")
+    lo, y = rnd(M, seed=6, scale=3.0), (torch.rand(M, generator=torch.Generator().manual_seed(7)) < 0.9).float()
+    lc, dc, lg, dg = torch.empty(M), torch.empty(M), torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    em.bce_loss_grad(lo, y, 1.0, 1.0 / M, lc, dc)
+    cu.bce_loss_grad(lo.cuda(), y.cuda(), 1.0, 1.0 / M, lg, dg)
+    close(lg, lc, what="bce loss")
+    close(dg, dc, what="bce grad")
+
+
+def test_lambda_returns_and_moments(ops):
+    cu, em = ops
+    H, N = 15, 1024
+    rew, val, cl = rnd(H + 1, N, seed=1), rnd(H + 1, N, seed=2), rnd(H + 1, N, seed=3, scale=2.0)
+    tc = (torch.rand(N, generator=torch.Generator().manual_seed(4)) < 0.95).float()
+    lc, dc = torch.empty(H, N), torch.empty(H + 1, N)
+    lg, dg = torch.empty(H, N, device="cuda"), torch.empty(H + 1, N, device="cuda")
+    em.lambda_returns(rew, val, cl, tc, 0.997, 0.95, lc, dc)
+    cu.lambda_returns(rew.cuda(), val.cuda(), cl.cuda(), tc.cuda(), 0.997, 0.95, lg, dg)
+    close(lg, lc, rtol=1e-5, what="lambda")
+    close(dg, dc, rtol=1e-5, what="discount")
+    for n in (15360, 7, 1, 122880):
+        x = rnd(n, seed=5)
+        sc, oc = torch.tensor([0.1, 0.7]), torch.empty(2)
+        sg, og = sc.clone().cuda(), torch.empty(2, device="cuda")
+        em.moments_update(x, sc, 0.99, 1.0, 0.05, 0.95, oc)
+        cu.moments_update(x.cuda(), sg, 0.99, 1.0, 0.05, 0.95, og)
+        close(sg, sc, rtol=1e-6, what="moments state")
+        close(og, oc, rtol=1e-6, what="moments out")
+    # exact order statistics (quantile with weight 0): compare against sort
+    x = rnd(1001, seed=6)
+    sg, og = torch.zeros(2, device="cuda"), torch.empty(2, device="cuda")
+    cu.moments_update(x.cuda(), sg, 0.0, 1e8, 0.25, 0.75, og)
+    srt = x.sort().values
+    assert float(sg[0]) == float(srt[250]) and float(sg[1]) == float(srt[750])
+
+
+@pytest.mark.parametrize("heads", [(2,), (3, 2), (18,), (4, 4, 4)])
+def test_actor_loss_grad(ops, heads):
+    cu, em = ops
+    M, A = 960, sum(heads)
+    raw = rnd(M, A, seed=1, scale=1.5)
+    g = torch.Generator().manual_seed(2)
+    acts = torch.cat([torch.nn.functional.one_hot(torch.randint(0, h, (M,), generator=g), h).float() for h in heads], -1)
+    lam, val, disc = rnd(M, seed=3), rnd(M, seed=4), torch.rand(M, generator=g)
+    mom = torch.tensor([0.05, 1.3])
+    rc, dc = torch.empty(M), torch.empty(M, A)
+    rg, dg = torch.empty(M, device="cuda"), torch.empty(M, A, device="cuda")
+    em.actor_loss_grad(raw, acts, lam, val, disc, mom, heads, 0.01, 3e-4, 1.0 / M, rc, dc)
+    cu.actor_loss_grad(raw.cuda(), acts.cuda(), lam.cuda(), val.cuda(), disc.cuda(), mom.cuda(), heads, 0.01, 3e-4,
+                       1.0 / M, rg, dg)
+    close(rg, rc, rtol=1e-5, what="actor rows")
+    close(dg, dc, rtol=1e-5, what="actor draw")
+
+
+def test_optimizer_and_utils(ops):
+    cu, em = ops
+    n = 100003 // 4 * 4 + 64
+    p, g = rnd(n, seed=1), rnd(n, seed=2, scale=3.0)
+    m, v = rnd(n, seed=3, scale=0.1), rnd(n, seed=4).abs() * 0.01
+    nc, ng = torch.zeros((), dtype=torch.float64), torch.zeros((), dtype=torch.float64, device="cuda")
+    em.sumsq(g, nc)
+    cu.sumsq(g.cuda(), ng)
+    assert abs(float(ng) - float(nc)) <= 1e-9 * float(nc)
+    for max_norm in (1000.0, 10.0, 0.0):
+        pc, mc, vc, oc = p.clone(), m.clone(), v.clone(), torch.zeros(1)
+        pg, mg, vg, og = p.cuda(), m.cuda(), v.cuda(), torch.zeros(1, device="cuda")
+        st_c, st_g = torch.tensor([3], dtype=torch.int32), torch.tensor([3], dtype=torch.int32, device="cuda")
+        em.adam_step(pc, g, mc, vc, nc, max_norm, 1e-4, 0.9, 0.999, 1e-8, st_c, oc)
+        cu.adam_step(pg, g.cuda(), mg, vg, ng, max_norm, 1e-4, 0.9, 0.999, 1e-8, st_g, og)
+        close(pg, pc, rtol=0, atol=5e-7, what="adam p")  # 1-2 ulp at |p| ~ 1
+        close(mg, mc, rtol=1e-6, what="adam m")
+        close(vg, vc, rtol=1e-6, what="adam v")
+        close(og, oc, rtol=1e-6, what="norm")
+    tc, tg = p.clone(), p.cuda()
+    em.ema(tc, g, 0.02)
+    cu.ema(tg, g.cuda(), 0.02)
+    close(tg, tc, what="ema")
+    e = torch.empty(1 << 20, device="cuda")
+    cu.fill_exponential(e, 1234, 7)
+    assert float(e.min()) > 0 and abs(float(e.mean()) - 1.0) < 0.01 and abs(float(e.var()) - 1.0) < 0.03
+    e2 = torch.empty(1 << 20, device="cuda")
+    cu.fill_exponential(e2, 1234, 8)
+    assert not torch.equal(e, e2)
+    ctr = torch.ones(1, dtype=torch.int32, device="cuda")
+    cu.fill_exponential(e2, 1234, 7, ctr)
+    assert not torch.equal(e, e2)
+    ctr.zero_()
+    cu.fill_exponential(e2, 1234, 7, ctr)
+    assert torch.equal(e, e2)
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    cu.increment(st), cu.increment(st)
+    assert int(st) == 2
+    x = rnd(33, 20, seed=5)
+    big = torch.zeros(33, 50, device="cuda")
+    cu.copy(x.cuda(), big[:, 7:27])
+    assert torch.equal(big[:, 7:27].cpu(), x) and float(big[:, :7].abs().sum()) == 0
+    y = rnd(100, seed=6).cuda()
+    y0 = y.clone()
+    cu.axpy(y0, y, 0.5)
+    close(y, y0.cpu() * 1.5, what="axpy")
+    cu.affine(y0, y, -1.0, 1.0)
+    close(y, 1 - y0.cpu(), what="affine")
+    cu.tanh_fwd(y0, y)
+    close(y, torch.tanh(y0.cpu()), what="tanh")
+    d = torch.zeros(100, device="cuda")
+    cu.tanh_bwd(y, y0, d)
+    close(d, y0.cpu() * (1 - torch.tanh(y0.cpu()) ** 2), what="tanh bwd")
+    o = torch.empty(2, device="cuda")
+    X = rnd(500, 4, seed=7)
+    cu.sum_rows(X.cuda()[:, 1:3], o, 0.5)
+    close(o, 0.5 * X[:, 1:3].sum(0), rtol=1e-5, what="sum_rows")
+    cu.weighted_mean(X.cuda()[:, 0].contiguous(), X.cuda()[:, 1].contiguous(), 0.1, o[:1])
+    close(o[:1], 0.1 * (X[:, 0] * X[:, 1]).sum().reshape(1), rtol=1e-5, what="weighted_mean")
+
+
+def test_replay_gather_scatter_and_gae(ops):
+    cu, em = ops
+    rng = np.random.default_rng(0)
+    size, row = 500, (3, 8, 8)
+    storage = torch.from_numpy(rng.integers(0, 256, size=(size, *row), dtype=np.uint8)).cuda()
+    S, B, T = 2, 4, 16
+    idx = torch.from_numpy(rng.integers(0, size, size=(S * B * T,))).cuda()
+    out = torch.empty(S, T, B, *row, dtype=torch.uint8, device="cuda")
+    cu.replay_gather(storage, idx, out, S, B, T)
+    want = storage.cpu()[idx.cpu()].reshape(S, B, T, *row).swapaxes(1, 2)
+    assert torch.equal(out.cpu(), want)
+    fs = torch.from_numpy(rng.standard_normal((size, 5)).astype(np.float32)).cuda()  # 20-byte rows (unaligned path)
+    outf = torch.empty(S, T, B, 5, device="cuda")
+    cu.replay_gather(fs, idx, outf, S, B, T)
+    assert torch.equal(outf.cpu(), fs.cpu()[idx.cpu()].reshape(S, B, T, 5).swapaxes(1, 2))
+    rows = torch.tensor([3, 499, 0], device="cuda")
+    src = torch.from_numpy(rng.integers(0, 256, size=(3, *row), dtype=np.uint8)).cuda()
+    cu.replay_scatter(src, rows, storage)
+    assert torch.equal(storage[rows].cpu(), src.cpu())
+    Tn, E = 128, 16
+    r, v, nv = rnd(Tn, E, 1, seed=1), rnd(Tn, E, 1, seed=2), rnd(E, 1, seed=3)
+    d = (torch.rand(Tn, E, 1, generator=torch.Generator().manual_seed(4)) < 0.05).float()
+    ret, adv = torch.empty(Tn, E, 1, device="cuda"), torch.empty(Tn, E, 1, device="cuda")
+    cu.gae(r.cuda(), v.cuda(), d.cuda(), nv.cuda(), 0.99, 0.95, ret, adv)
+    from oracle.ppo_oracle import gae_oracle
+
+    ret_c, adv_c = gae_oracle(r, v, d, nv, Tn, 0.99, 0.95)
+    close(adv, adv_c, rtol=1e-5, what="gae adv")
+    close(ret, ret_c, rtol=1e-5, what="gae ret")
