@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Benchmark: Dreamer-V3 train-steps/sec (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host cores (oracle port)
+
+One "step" = one call of the Dreamer-V3 update (`train()`, reference dreamer_v3.py:48-357) on one per-rank
+replay batch of the BASELINE config: size S, B=16, T=64, 64x64x3 uint8 observations, horizon 15, discrete A=2.
+Prints ONE JSON line (see the task contract): `value` = device-resident throughput (CUDA-graph replay of the
+step, inputs in HBM), `e2e` = the same metric through the public `train()` call with pinned-host inputs
+(H2D copy + metric D2H inside the timed region), `roofline` for the dominant kernel family measured live with
+CUDA events, `cpu_baseline` = the oracle port of the reference on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Dreamer-V3 train-steps/sec (S, bs16 seq64 horizon15, 64x64x3 obs)"
+UNIT = "train-steps/s"
+WORKLOAD = "dreamer_v3_S bs16 seq64 h15 64x64x3 discreteA2 (BASELINE.json configs[1])"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+
+        self.thr = threading.Thread(target=pump, daemon=True)
+        self.thr.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thr.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_batch(cfg, adim, seed, device=None, pinned=False):
+    """SURVEY.md §8d synthetic replay batch (uint8 pixels, one-hot actions, N(0,1) rewards...)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    T, B, sz = cfg.algo.per_rank_sequence_length, cfg.algo.per_rank_batch_size, cfg.env.screen_size
+    d = {
+        "rgb": torch.randint(0, 256, (T, B, 3, sz, sz), generator=g, dtype=torch.uint8),
+        "actions": torch.nn.functional.one_hot(torch.randint(0, adim[0], (T, B), generator=g), adim[0]).float(),
+        "rewards": torch.randn(T, B, 1, generator=g),
+        "terminated": (torch.rand(T, B, 1, generator=g) < 0.01).float(),
+        "truncated": torch.zeros(T, B, 1),
+        "is_first": (torch.rand(T, B, 1, generator=g) < 0.02).float(),
+    }
+    if pinned:
+        d = {k: v.pin_memory() for k, v in d.items()}
+    if device is not None:
+        d = {k: v.to(device) for k, v in d.items()}
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------------
+# per-op instrumentation (roofline): CUDA events around every C-ABI call of one eager step
+# ---------------------------------------------------------------------------------------------------------
+class ProfilingOps:
+    """Wraps CudaOps; brackets every op with CUDA events on the launching stream and accounts its
+    algorithmic FLOPs / bytes (DESIGN.md lists the per-op formulas)."""
+
+    def __init__(self, inner):
+        import torch
+
+        self._inner, self._torch = inner, torch
+        self.records = []
+
+    def __getattr__(self, name):
+        fn = getattr(self._inner, name)
+        if not callable(fn):
+            return fn
+        torch = self._torch
+
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            self.records.append((name, e0, e1, self._work(name, a, k)))
+            return r
+
+        return wrapped
+
+    @staticmethod
+    def _nbytes(*ts):
+        return sum(t.numel() * t.element_size() for t in ts if t is not None and hasattr(t, "numel"))
+
+    def _work(self, name, a, k):
+        """(flops, bytes) algorithmic work of one call."""
+        if name == "gemm":
+            A, B, C, tA, tB = a[:5]
+            M, N = C.shape
+            K = A.shape[0] if tA else A.shape[1]
+            return 2.0 * M * N * K, 4.0 * (M * K + K * N + M * N)
+        if name in ("conv_down", "conv_up"):
+            big, small = (a[0], a[2]) if name == "conv_down" else (a[2], a[0])
+            NB, h, w, Cs = small.shape
+            Cb = big.shape[-1]
+            return 2.0 * NB * h * w * Cs * Cb * 16, 4.0 * (big.numel() + small.numel() + Cs * Cb * 16)
+        if name == "conv_wgrad":
+            small, big = a[0], a[1]
+            NB, h, w, Cs = small.shape
+            return 2.0 * NB * h * w * Cs * big.shape[-1] * 16, 4.0 * (big.numel() + small.numel())
+        return 0.0, float(self._nbytes(*[x for x in a if hasattr(x, "numel")]))
+
+    def summary(self):
+        self._torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, (fl, by) in self.records:
+            t = e0.elapsed_time(e1)
+            s = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+            s[0] += t
+            s[1] += fl
+            s[2] += by
+            s[3] += 1
+        return agg
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from sheeprl_b200.algos.dreamer_v3.agent import build_agent
+    from sheeprl_b200.algos.dreamer_v3.dreamer_v3 import make_optimizers, train
+    from sheeprl_b200.algos.dreamer_v3.utils import Moments
+    from sheeprl_b200.configs import make_dv3_cfg
+    from sheeprl_b200.parallel import attach_data_parallel, init_process_group_from_env
+
+    rank, local, world = init_process_group_from_env("nccl")
+    assert world == args.gpus, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = make_dv3_cfg("S")
+    cfg.seed = 5
+    adim = (2,)
+
+    class Fab:  # the three attributes train()/build_agent() read from Fabric
+        device, world_size, global_rank = dev, world, rank
+
+    class Space:
+        shape = (3, 64, 64)
+
+    wm, actor, critic, target, _ = build_agent(Fab, adim, False, cfg, {"rgb": Space})
+    eng = wm._b200_engine
+    attach_data_parallel(eng)
+    eng.rng_seed = 1234 + rank
+    opts = make_optimizers(eng, cfg)
+    mo = cfg.algo.actor.moments
+    moments = Moments(mo.decay, mo.max, mo.percentile.low, mo.percentile.high)
+
+    class Agg:
+        disabled = False
+
+        def __init__(self):
+            self.v = {}
+
+        def update(self, k, v):
+            self.v[k] = v
+
+    agg = Agg()
+    host = synthetic_batch(cfg, adim, seed=100 + rank, pinned=True)
+    static = {k: v.to(dev) for k, v in host.items()}            # device-resident inputs for `value`
+    in_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_public(data):
+        eng.update_target(cfg.algo.critic.tau)                  # main() does this before each train() (:674-680)
+        train(Fab, wm, actor, critic, target, *opts, data, agg, cfg, False, adim, moments)
+
+    # ---- warm-up (eager): loads modules, first-touch, W >= 3
+    launches0 = eng.ops.launches
+    step_public(static)
+    launches_per_step = eng.ops.launches - launches0
+    for _ in range(max(args.warmup, 3) - 1):
+        step_public(static)
+    barrier()
+
+    # ---- per-op breakdown of ONE eager step (roofline evidence), rank 0 only
+    breakdown = None
+    if rank == 0:
+        prof = ProfilingOps(eng.ops)
+        eng.ops = prof
+        for m in (eng.reward_wm, eng.cont_wm, eng.actor_mlp, eng.critic_mlp, eng.target_mlp, eng.rew_img, eng.cont_img):
+            m.eng = eng
+        step_public(static)
+        breakdown = prof.summary()
+        eng.ops = prof._inner
+    barrier()
+
+    # ---- CUDA graph of the whole update (single GPU; multi-GPU keeps eager launches around NCCL)
+    graph = None
+    if not args.no_graph and world == 1:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step_public(static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_public(static)
+        for _ in range(2):
+            graph.replay()
+    barrier()
+
+    # ---- timed region 1: `value` (inputs resident in HBM)
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        if graph is not None:
+            graph.replay()
+        else:
+            step_public(static)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- timed region 2: `e2e` through the public train() with pinned-host inputs + metric read-back
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    out_host = torch.empty(13, dtype=torch.float32).pin_memory()
+    barrier()
+    e2.record()
+    for _ in range(args.steps):
+        tgt = static if graph is not None else dev_in
+        for k, v in host.items():
+            tgt[k].copy_(v, non_blocking=True)                  # H2D of this step's replay batch (pinned source)
+        if graph is not None:
+            graph.replay()
+        else:
+            step_public(dev_in)
+        out_host[:10].copy_(eng.metrics[:10], non_blocking=True)
+        out_host[10:].copy_(eng.norms, non_blocking=True)
+        torch.cuda.current_stream().synchronize()               # D2H read of the step's losses
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clk = clocks.stop()
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    assert all(torch.isfinite(eng.metrics).tolist()), "non-finite metrics"
+    value = world * args.steps / (ms / 1e3)
+    e2e_v = world * args.steps / (ms_e2e / 1e3)
+    hbm, tf, src = measured_peaks()
+    # dominant kernel family by device time in the eager breakdown
+    tot_ms = sum(v[0] for v in breakdown.values())
+    dom = max(breakdown.items(), key=lambda kv: kv[1][0])
+    name, (t_ms, fl, by, cnt) = dom
+    fp32_simt_peak = 148 * 128 * 2 * (clk["sm_max_mhz"] or 1965.0) * 1e6 / 1e12   # TFLOP/s at max clock
+    if fl > 0:
+        roof = {"kernel": f"b200rl_{name}* (fp32 SIMT implicit/explicit GEMM)", "bound": "tensor",
+                "achieved": fl / (t_ms * 1e-3) / 1e12, "peak": tf, "unit": "TFLOP/s",
+                "frac": fl / (t_ms * 1e-3) / 1e12 / tf, "traffic": None, "peak_source": f"{src} bf16 cuBLAS",
+                "note": f"exact-fp32 FFMA path; fp32 SIMT ceiling is {fp32_simt_peak:.1f} TFLOP/s "
+                        f"(frac of that: {fl / (t_ms * 1e-3) / 1e12 / fp32_simt_peak:.3f}); share of step {t_ms / tot_ms:.2f}",
+                "launches": cnt, "ms_per_step": t_ms}
+    else:
+        roof = {"kernel": f"b200rl_{name}", "bound": "hbm", "achieved": by / (t_ms * 1e-3) / 1e9, "peak": hbm,
+                "unit": "GB/s", "frac": by / (t_ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": src,
+                "launches": cnt, "ms_per_step": t_ms}
+    cpu = cpu_baseline(steps=1, warmup=1) if args.cpu_baseline else None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_rank_batch": 16, "seq_len": 64, "horizon": 15,
+                   "parallelism": f"dp{world}", "cuda_graph": graph is not None,
+                   "l2": "per-step working set (~1.6 GB of activations + 0.5 GB optimiser state) >> 126 MB L2"},
+        "clocks": clk,
+        "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 13 * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][0])[:12]},
+    }
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port, oracle/dv3_oracle.py) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_baseline(steps: int, warmup: int):
+    import torch
+
+    from oracle import dv3_oracle as O          # checker / baseline only — never on the product path
+    from sheeprl_b200.configs import make_dv3_cfg
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = make_dv3_cfg("S")
+    adim = (2,)
+    wm, actor, critic, target = O.init_params(cfg, adim, seed=0)
+    a, w = cfg.algo, cfg.algo.world_model
+    opts = [O.AdamState(wm, w.optimizer.lr, w.optimizer.eps), O.AdamState(actor, a.actor.optimizer.lr, a.actor.optimizer.eps),
+            O.AdamState(critic, a.critic.optimizer.lr, a.critic.optimizer.eps)]
+    ms = {"low": torch.zeros(()), "high": torch.zeros(())}
+    data = O.make_batch(cfg, adim, seed=1)
+    times = []
+    for s in range(warmup + steps):
+        noise = O.draw_noise(a.per_rank_sequence_length, a.per_rank_batch_size, a.horizon, w.stochastic_size,
+                             w.discrete_size, adim, seed=10 + s)
+        t0 = time.perf_counter()
+        O.dv3_train_step(cfg, wm, actor, critic, target, *opts, data, noise, ms, adim)
+        times.append(time.perf_counter() - t0)
+    tt = times[warmup:]
+    return {"value": len(tt) / sum(tt), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(tt)} full train() step(s) of the same workload after {warmup} warm-up, torch fp32 CPU, "
+                      f"{cores} threads; s/step={sum(tt) / len(tt):.2f}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 30))
+    warm = max(1, min(args.warmup, 3))
+    cb = cpu_baseline(steps=steps, warmup=warm)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_rank_batch": 16, "seq_len": 64, "horizon": 15,
+                   "parallelism": "host cpu threads"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
