@@ -79,6 +79,28 @@ int b200rl_kl_loss_grad(const float* post_mix, const float* prior_mix, float* d_
                         long long M, int groups, int classes, long long ldp, long long ldq, long long lddp,
                         long long lddq, float kl_dyn, float kl_rep, float free_nats, float regularizer, float scale,
                         cudaStream_t stream);
+/* Persistent fused scan: all T steps of RSSM.dynamic (dreamer_v3.py:131-145 -> agent.py:396-435) in ONE
+ * cooperative kernel; weight slices resident in shared memory, state rows staged in shared memory, grid
+ * barriers between the 4 dependent stages of a step (rssm_scan.cu).  Writes the same saved activations as the
+ * per-step ops above so either backward can consume them.  Requires B <= 16, classes <= 32 and the per-CTA
+ * weight slices to fit in 227 KB (returns non-zero otherwise; the caller then uses the per-step ops). */
+typedef struct b200rl_rssm_scan_args {
+  int T, B, S, D, R, A, Dx, Dt, Dr, ld_lat, ld_wr1;
+  float eps, unimix;
+  const float *W_in, *lnx_g, *lnx_b, *W_g, *lng_g, *lng_b, *W_t1, *lnt_g, *lnt_b, *W_t2, *b_t2;
+  const float *W_r1, *lnr_g, *lnr_b, *W_r2, *b_r2;
+  const float *h0, *z0;                       /* [R] tanh(initial_recurrent_state); [S*D] one-hot initial posterior */
+  const float *pe, *actions, *first, *noise;  /* [T,B,Dr] embed projection; [T,B,A] shifted; [T,B]; [T,B,S*D] Exp(1) */
+  float* latent;                              /* [T*B, ld_lat]: z (S*D) | h (R) */
+  float *z_in, *h_in, *a_in, *x_pre, *x_act, *g_pre, *g_ln, *tr_pre, *tr_act, *rp_pre, *rp_act;
+  float *post_raw, *prior_raw, *post_mix, *prior_mix;
+  void* workspace;
+  long long workspace_bytes;
+} b200rl_rssm_scan_args;
+long long b200rl_rssm_scan_workspace_bytes(int T, int B, int S);
+int b200rl_rssm_scan_fwd(const b200rl_rssm_scan_args* args, cudaStream_t stream);
+int b200rl_rssm_scan_error(const void* workspace, cudaStream_t stream);
+
 /* ---- losses (value + seed gradient) -----------------------------------------------------------------
  * distribution.py:212-276 (MSE, two-hot on symlog), Bernoulli continue head loss.py:77, lambda returns
  * dreamer_v3/utils.py:66-77 + dreamer_v3.py:244-260, Moments dreamer_v3/utils.py:40-63, discrete policy

@@ -312,6 +312,9 @@ class DV3Engine:
         self.noise_img_action = b("noise_img_action", H + 1, N, A)
         self.rng_seed = 0
         self.rng_t = torch.zeros(1, dtype=torch.int32, device=self.device)   # device-side step counter for Philox
+        # persistent fused RSSM scan (csrc/rssm_scan.cu) when the ops backend provides it and the shape qualifies
+        self.fused_scan = bool(hasattr(self.ops, "rssm_scan_fwd") and self.B <= 16 and self.D <= 32 and self.S <= 64)
+        self._scan_ws = None
 
     def bytes_allocated(self) -> int:
         tot = sum(t.numel() * t.element_size() for t in self._bufs.values())
@@ -514,6 +517,8 @@ class DV3Engine:
         ops.cat_sample(self.init_raw, None, self.unimix, self.S, self.D, self.z0)
         pr = "rssm.representation_model._model."
         Wr1 = self._w(pr + "0.weight")
+        if self.fused_scan and self._scan_forward_fused(first):
+            return
         for t in range(self.T):
             s = slice(t * B, (t + 1) * B)
             f = first[s]
@@ -539,6 +544,36 @@ class DV3Engine:
                      bias=self._w(pr + "3.bias"))
             ops.cat_sample(self.post_raw[s], self.noise_post[t], self.unimix, self.S, self.D, self.latent[s, :Z],
                            self.post_mix[s])
+
+    def _scan_forward_fused(self, first: torch.Tensor) -> bool:
+        """The whole scan as ONE persistent cooperative kernel (csrc/rssm_scan.cu).  Produces exactly the saved
+        activations of the per-step path above.  Returns False (and disables itself) if the model does not fit
+        the kernel's shared-memory budget."""
+        p = "rssm.recurrent_model."
+        pt, pr = "rssm.transition_model._model.", "rssm.representation_model._model."
+        w = self._w
+        if self._scan_ws is None:
+            self._scan_ws = self.ops.rssm_scan_workspace(self.T, self.B, self.S)
+        tensors = dict(
+            W_in=w(p + "mlp._model.0.weight"), lnx_g=w(p + "mlp._model.1.weight"), lnx_b=w(p + "mlp._model.1.bias"),
+            W_g=w(p + "rnn.linear.weight"), lng_g=w(p + "rnn.layer_norm.weight"), lng_b=w(p + "rnn.layer_norm.bias"),
+            W_t1=w(pt + "0.weight"), lnt_g=w(pt + "1.weight"), lnt_b=w(pt + "1.bias"), W_t2=w(pt + "3.weight"),
+            b_t2=w(pt + "3.bias"), W_r1=w(pr + "0.weight"), lnr_g=w(pr + "1.weight"), lnr_b=w(pr + "1.bias"),
+            W_r2=w(pr + "3.weight"), b_r2=w(pr + "3.bias"), h0=self.h0, z0=self.z0, pe=self.pe,
+            actions=self.shift_actions, first=first, noise=self.noise_post, latent=self.latent, z_in=self.z_in,
+            h_in=self.h_in, a_in=self.a_in, x_pre=self.x_pre, x_act=self.x_act, g_pre=self.g_pre, g_ln=self.g_ln,
+            tr_pre=self.tr_pre, tr_act=self.tr_act, rp_pre=self.rp_pre, rp_act=self.rp_act, post_raw=self.post_raw,
+            prior_raw=self.prior_raw, post_mix=self.post_mix, prior_mix=self.prior_mix)
+        dims = dict(T=self.T, B=self.B, S=self.S, D=self.D, R=self.R, A=self.A, Dx=self.Dx, Dt=self.Dt, Dr=self.Dr,
+                    ld_lat=self.L, ld_wr1=self.R + self.E)
+        try:
+            self.ops.rssm_scan_fwd(dims, self.eps, self.unimix, tensors, self._scan_ws)
+        except Exception as e:  # shape outside the kernel's envelope: keep the per-step kernels
+            if "shared memory" in str(e) or "supports" in str(e):
+                self.fused_scan = False
+                return False
+            raise
+        return True
 
     def _scan_backward(self, first: torch.Tensor):
         """BPTT over the scan.  Per-step only the data-gradient GEMMs run; the weight

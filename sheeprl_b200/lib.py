@@ -68,6 +68,18 @@ def _f32(*ts):
             assert t.dtype == torch.float32 and t.is_cuda, (t.dtype, t.device)
 
 
+class RssmScanArgs(ctypes.Structure):
+    """Mirror of `b200rl_rssm_scan_args` (include/b200rl.h) — field order must match the C struct."""
+    POINTERS = ("W_in", "lnx_g", "lnx_b", "W_g", "lng_g", "lng_b", "W_t1", "lnt_g", "lnt_b", "W_t2", "b_t2",
+                "W_r1", "lnr_g", "lnr_b", "W_r2", "b_r2", "h0", "z0", "pe", "actions", "first", "noise", "latent",
+                "z_in", "h_in", "a_in", "x_pre", "x_act", "g_pre", "g_ln", "tr_pre", "tr_act", "rp_pre", "rp_act",
+                "post_raw", "prior_raw", "post_mix", "prior_mix")
+    _fields_ = ([(n, c_int) for n in ("T", "B", "S", "D", "R", "A", "Dx", "Dt", "Dr", "ld_lat", "ld_wr1")]
+                + [("eps", c_float), ("unimix", c_float)]
+                + [(n, c_void_p) for n in POINTERS]
+                + [("workspace", c_void_p), ("workspace_bytes", c_ll)])
+
+
 class CudaOps:
     name = "cuda"
 
@@ -333,6 +345,30 @@ class CudaOps:
     def tanh_bwd(self, y, dy, dx, accumulate: bool = False):
         _f32(y, dy, dx)
         self._ck(self.lib.b200rl_tanh_bwd(_p(y), _p(dy), _p(dx), c_ll(y.numel()), c_int(int(accumulate)), self._st()))
+
+    # ------------------------------------------------------------------ persistent RSSM scan
+    def rssm_scan_workspace(self, T: int, B: int, S: int) -> torch.Tensor:
+        self.lib.b200rl_rssm_scan_workspace_bytes.restype = c_ll
+        n = int(self.lib.b200rl_rssm_scan_workspace_bytes(c_int(T), c_int(B), c_int(S)))
+        return torch.zeros((n + 3) // 4, dtype=torch.int32, device=self.device)
+
+    def rssm_scan_fwd(self, dims: dict, eps: float, unimix: float, tensors: dict, workspace: torch.Tensor):
+        """dims: T,B,S,D,R,A,Dx,Dt,Dr,ld_lat,ld_wr1; tensors: name -> device tensor for every pointer field of
+        `b200rl_rssm_scan_args` (include/b200rl.h)."""
+        a = RssmScanArgs()
+        for k in ("T", "B", "S", "D", "R", "A", "Dx", "Dt", "Dr", "ld_lat", "ld_wr1"):
+            setattr(a, k, int(dims[k]))
+        a.eps, a.unimix = float(eps), float(unimix)
+        for name in RssmScanArgs.POINTERS:
+            t = tensors[name]
+            assert t.is_cuda and t.dtype == torch.float32, name
+            setattr(a, name, t.data_ptr())
+        a.workspace = workspace.data_ptr()
+        a.workspace_bytes = workspace.numel() * workspace.element_size()
+        self._ck(self.lib.b200rl_rssm_scan_fwd(ctypes.byref(a), self._st()))
+
+    def rssm_scan_error(self, workspace: torch.Tensor) -> int:
+        return int(self.lib.b200rl_rssm_scan_error(_p(workspace), self._st()))
 
     # ------------------------------------------------------------------ replay / PPO
     def replay_gather(self, storage, idx, out, n_samples: int, batch: int, seq_len: int):
