@@ -97,8 +97,19 @@ typedef struct b200rl_rssm_scan_args {
   void* workspace;
   long long workspace_bytes;
 } b200rl_rssm_scan_args;
-long long b200rl_rssm_scan_workspace_bytes(int T, int B, int S);
+/* Gradient buffers of the persistent BPTT kernel (same meaning as the per-step path's buffers):
+ * inputs d_latent [T*B, ld_lat] (grad wrt z|h from decoder + heads), d_post_mix / d_prior_mix (KL seed grads);
+ * outputs: per-step pre-activation gradients consumed by the deferred weight-gradient GEMMs, and d_h0 [R]. */
+typedef struct b200rl_rssm_scan_grads {
+  const float *d_latent, *d_post_mix, *d_prior_mix;
+  float *d_post_raw, *d_prior_raw, *d_rp_act, *d_rp_pre, *d_tr_act, *d_tr_pre, *d_g_ln, *d_g_pre, *d_x_act, *d_x_pre;
+  float* d_h0;
+} b200rl_rssm_scan_grads;
+long long b200rl_rssm_scan_workspace_bytes(int T, int B, int S, int D);
 int b200rl_rssm_scan_fwd(const b200rl_rssm_scan_args* args, cudaStream_t stream);
+/* BPTT over the same scan (autograd replay inside fabric.backward, dreamer_v3.py:191); must follow
+ * b200rl_rssm_scan_fwd on the same workspace (uses its saved LayerNorm statistics). */
+int b200rl_rssm_scan_bwd(const b200rl_rssm_scan_args* args, const b200rl_rssm_scan_grads* grads, cudaStream_t stream);
 int b200rl_rssm_scan_error(const void* workspace, cudaStream_t stream);
 
 /* ---- losses (value + seed gradient) -----------------------------------------------------------------

@@ -315,6 +315,8 @@ class DV3Engine:
         # persistent fused RSSM scan (csrc/rssm_scan.cu) when the ops backend provides it and the shape qualifies
         self.fused_scan = bool(hasattr(self.ops, "rssm_scan_fwd") and self.B <= 16 and self.D <= 32 and self.S <= 64)
         self._scan_ws = None
+        self.fused_scan_bwd = hasattr(self.ops, "rssm_scan_bwd")
+        self._fused_fwd_done = False
 
     def bytes_allocated(self) -> int:
         tot = sum(t.numel() * t.element_size() for t in self._bufs.values())
@@ -553,8 +555,28 @@ class DV3Engine:
         pt, pr = "rssm.transition_model._model.", "rssm.representation_model._model."
         w = self._w
         if self._scan_ws is None:
-            self._scan_ws = self.ops.rssm_scan_workspace(self.T, self.B, self.S)
-        tensors = dict(
+            self._scan_ws = self.ops.rssm_scan_workspace(self.T, self.B, self.S, self.D)
+        tensors = self._scan_tensors(first)
+        dims = self._scan_dims()
+        try:
+            self.ops.rssm_scan_fwd(dims, self.eps, self.unimix, tensors, self._scan_ws)
+        except Exception as e:  # shape outside the kernel's envelope: keep the per-step kernels
+            if "shared memory" in str(e) or "supports" in str(e):
+                self.fused_scan = False
+                return False
+            raise
+        self._fused_fwd_done = True
+        return True
+
+    def _scan_dims(self):
+        return dict(T=self.T, B=self.B, S=self.S, D=self.D, R=self.R, A=self.A, Dx=self.Dx, Dt=self.Dt, Dr=self.Dr,
+                    ld_lat=self.L, ld_wr1=self.R + self.E)
+
+    def _scan_tensors(self, first: torch.Tensor):
+        p = "rssm.recurrent_model."
+        pt, pr = "rssm.transition_model._model.", "rssm.representation_model._model."
+        w = self._w
+        return dict(
             W_in=w(p + "mlp._model.0.weight"), lnx_g=w(p + "mlp._model.1.weight"), lnx_b=w(p + "mlp._model.1.bias"),
             W_g=w(p + "rnn.linear.weight"), lng_g=w(p + "rnn.layer_norm.weight"), lng_b=w(p + "rnn.layer_norm.bias"),
             W_t1=w(pt + "0.weight"), lnt_g=w(pt + "1.weight"), lnt_b=w(pt + "1.bias"), W_t2=w(pt + "3.weight"),
@@ -564,13 +586,20 @@ class DV3Engine:
             h_in=self.h_in, a_in=self.a_in, x_pre=self.x_pre, x_act=self.x_act, g_pre=self.g_pre, g_ln=self.g_ln,
             tr_pre=self.tr_pre, tr_act=self.tr_act, rp_pre=self.rp_pre, rp_act=self.rp_act, post_raw=self.post_raw,
             prior_raw=self.prior_raw, post_mix=self.post_mix, prior_mix=self.prior_mix)
-        dims = dict(T=self.T, B=self.B, S=self.S, D=self.D, R=self.R, A=self.A, Dx=self.Dx, Dt=self.Dt, Dr=self.Dr,
-                    ld_lat=self.L, ld_wr1=self.R + self.E)
+
+    def _scan_backward_fused(self, first: torch.Tensor) -> bool:
+        """BPTT of the scan as ONE persistent cooperative kernel; fills the same per-step gradient buffers the
+        deferred weight-gradient GEMMs read."""
+        grads = dict(d_latent=self.d_latent, d_post_mix=self.d_post_mix, d_prior_mix=self.d_prior_mix,
+                     d_post_raw=self.d_post_raw, d_prior_raw=self.d_prior_raw, d_rp_act=self.d_rp_act,
+                     d_rp_pre=self.d_rp_pre, d_tr_act=self.d_tr_act, d_tr_pre=self.d_tr_pre, d_g_ln=self.d_g_ln,
+                     d_g_pre=self.d_g_pre, d_x_act=self.d_x_act, d_x_pre=self.d_x_pre, d_h0=self.d_h0)
         try:
-            self.ops.rssm_scan_fwd(dims, self.eps, self.unimix, tensors, self._scan_ws)
-        except Exception as e:  # shape outside the kernel's envelope: keep the per-step kernels
+            self.ops.rssm_scan_bwd(self._scan_dims(), self.eps, self.unimix, self._scan_tensors(first), grads,
+                                   self._scan_ws)
+        except Exception as e:
             if "shared memory" in str(e) or "supports" in str(e):
-                self.fused_scan = False
+                self.fused_scan_bwd = False
                 return False
             raise
         return True
@@ -586,7 +615,9 @@ class DV3Engine:
         ops.zero(self.dz_carry)
         ops.zero(self.dh_carry)
         ops.zero(self.d_h0)
-        for t in reversed(range(self.T)):
+        fused = self.fused_scan and self.fused_scan_bwd and self._fused_fwd_done and self._scan_backward_fused(first)
+        self._fused_fwd_done = False
+        for t in (() if fused else reversed(range(self.T))):
             s = slice(t * B, (t + 1) * B)
             f = first[s]
             ops.copy(self.d_latent[s, :Z], self.dz_tot)

@@ -80,6 +80,13 @@ class RssmScanArgs(ctypes.Structure):
                 + [("workspace", c_void_p), ("workspace_bytes", c_ll)])
 
 
+class RssmScanGrads(ctypes.Structure):
+    """Mirror of `b200rl_rssm_scan_grads`."""
+    POINTERS = ("d_latent", "d_post_mix", "d_prior_mix", "d_post_raw", "d_prior_raw", "d_rp_act", "d_rp_pre",
+                "d_tr_act", "d_tr_pre", "d_g_ln", "d_g_pre", "d_x_act", "d_x_pre", "d_h0")
+    _fields_ = [(n, c_void_p) for n in POINTERS]
+
+
 class CudaOps:
     name = "cuda"
 
@@ -347,14 +354,12 @@ class CudaOps:
         self._ck(self.lib.b200rl_tanh_bwd(_p(y), _p(dy), _p(dx), c_ll(y.numel()), c_int(int(accumulate)), self._st()))
 
     # ------------------------------------------------------------------ persistent RSSM scan
-    def rssm_scan_workspace(self, T: int, B: int, S: int) -> torch.Tensor:
+    def rssm_scan_workspace(self, T: int, B: int, S: int, D: int) -> torch.Tensor:
         self.lib.b200rl_rssm_scan_workspace_bytes.restype = c_ll
-        n = int(self.lib.b200rl_rssm_scan_workspace_bytes(c_int(T), c_int(B), c_int(S)))
+        n = int(self.lib.b200rl_rssm_scan_workspace_bytes(c_int(T), c_int(B), c_int(S), c_int(D)))
         return torch.zeros((n + 3) // 4, dtype=torch.int32, device=self.device)
 
-    def rssm_scan_fwd(self, dims: dict, eps: float, unimix: float, tensors: dict, workspace: torch.Tensor):
-        """dims: T,B,S,D,R,A,Dx,Dt,Dr,ld_lat,ld_wr1; tensors: name -> device tensor for every pointer field of
-        `b200rl_rssm_scan_args` (include/b200rl.h)."""
+    def _scan_args(self, dims: dict, eps: float, unimix: float, tensors: dict, workspace: torch.Tensor):
         a = RssmScanArgs()
         for k in ("T", "B", "S", "D", "R", "A", "Dx", "Dt", "Dr", "ld_lat", "ld_wr1"):
             setattr(a, k, int(dims[k]))
@@ -365,7 +370,23 @@ class CudaOps:
             setattr(a, name, t.data_ptr())
         a.workspace = workspace.data_ptr()
         a.workspace_bytes = workspace.numel() * workspace.element_size()
+        return a
+
+    def rssm_scan_fwd(self, dims: dict, eps: float, unimix: float, tensors: dict, workspace: torch.Tensor):
+        """dims: T,B,S,D,R,A,Dx,Dt,Dr,ld_lat,ld_wr1; tensors: name -> device tensor for every pointer field of
+        `b200rl_rssm_scan_args` (include/b200rl.h)."""
+        a = self._scan_args(dims, eps, unimix, tensors, workspace)
         self._ck(self.lib.b200rl_rssm_scan_fwd(ctypes.byref(a), self._st()))
+
+    def rssm_scan_bwd(self, dims: dict, eps: float, unimix: float, tensors: dict, grads: dict,
+                      workspace: torch.Tensor):
+        a = self._scan_args(dims, eps, unimix, tensors, workspace)
+        q = RssmScanGrads()
+        for name in RssmScanGrads.POINTERS:
+            t = grads[name]
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), name
+            setattr(q, name, t.data_ptr())
+        self._ck(self.lib.b200rl_rssm_scan_bwd(ctypes.byref(a), ctypes.byref(q), self._st()))
 
     def rssm_scan_error(self, workspace: torch.Tensor) -> int:
         return int(self.lib.b200rl_rssm_scan_error(_p(workspace), self._st()))

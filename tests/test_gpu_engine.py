@@ -138,7 +138,8 @@ def test_engine_cuda_full_size_properties():
 
 @pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "S"])
 def test_fused_scan_equals_per_step_scan(name):
-    """Persistent cooperative RSSM kernel (csrc/rssm_scan.cu) vs the per-step kernels: same saved activations."""
+    """Persistent cooperative RSSM kernels (csrc/rssm_scan.cu, forward + BPTT) vs the per-step kernels:
+    same saved activations, same world-model gradients."""
     from oracle import dv3_oracle as O
     from sheeprl_b200.configs import make_dv3_cfg
 
@@ -153,6 +154,7 @@ def test_fused_scan_equals_per_step_scan(name):
         a, w = cfg.algo, cfg.algo.world_model
         noise = O.draw_noise(a.per_rank_sequence_length, a.per_rank_batch_size, a.horizon, w.stochastic_size,
                              w.discrete_size, adim, seed=5)
+        oracle_run(cfg, adim, init, [data], [noise], 1, condition_margin=1e-3)   # removes near-tie draws in place
     else:
         fx, cfg = load_fixture(name)
         adim, init, data, noise = fx["actions_dim"], fx["init"], fx["data"][0], fx["noise"][0]
@@ -163,14 +165,16 @@ def test_fused_scan_equals_per_step_scan(name):
         eng.train_step({k: v.clone().float().cuda() for k, v in data.items()}, to_cuda(noise))
         torch.cuda.synchronize()
         if fused:
-            assert eng.fused_scan, "fused scan was disabled"
+            assert eng.fused_scan and eng.fused_scan_bwd, "fused scan was disabled"
             assert eng.ops.rssm_scan_error(eng._scan_ws) == 0, "grid barrier timed out"
         outs.append({k: getattr(eng, k).clone() for k in (
             "latent", "z_in", "h_in", "a_in", "x_pre", "x_act", "g_pre", "g_ln", "tr_pre", "tr_act", "rp_pre", "rp_act",
-            "post_raw", "prior_raw", "post_mix", "prior_mix")} | {"wm": eng.wm.flat.clone(), "metrics": eng.metrics.clone()})
+            "post_raw", "prior_raw", "post_mix", "prior_mix", "d_post_raw", "d_prior_raw", "d_rp_pre", "d_tr_pre",
+            "d_g_pre", "d_x_pre", "d_rp_act", "d_tr_act", "d_g_ln", "d_x_act", "d_h0")}
+            | {"wm_grad": eng.wm.grad.clone(), "metrics": eng.metrics.clone()})
     ref, got = outs
     Z = ref["z_in"].shape[1]
     assert torch.equal(ref["latent"][:, :Z], got["latent"][:, :Z]), "sampled posteriors differ"
     for k in ref:
         err = float((ref[k] - got[k]).abs().max())
-        assert err <= 2e-5 * max(1.0, float(ref[k].abs().max())), (k, err)
+        assert err <= 5e-5 * max(1e-3, float(ref[k].abs().max())), (k, err, float(ref[k].abs().max()))

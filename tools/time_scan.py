@@ -25,3 +25,18 @@ for fused in (False, True):
         eng._scan_forward(first)
     e1.record(); torch.cuda.synchronize()
     print("fused" if fused else "per-step", "scan fwd ms:", e0.elapsed_time(e1) / 5, "err flag", eng.ops.rssm_scan_error(eng._scan_ws) if eng._scan_ws is not None else None)
+
+# backward scan timing (needs a fused forward right before each fused backward)
+for fused in (False, True):
+    eng.fused_scan = fused
+    tot = 0.0
+    for it in range(4):
+        eng._scan_forward(first)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng._scan_backward(first)
+        e1.record(); torch.cuda.synchronize()
+        if it > 0:
+            tot += e0.elapsed_time(e1)
+    print("fused" if fused else "per-step", "scan bwd (+deferred wgrad GEMMs) ms:", tot / 3, "err flag", eng.ops.rssm_scan_error(eng._scan_ws))
