@@ -33,6 +33,13 @@ int b200rl_device_check(void);
  * A is [M,K] (lda) or [K,M] if transA; B is [K,N] (ldb) or [N,K] if transB (nn.Linear weight layout). */
 int b200rl_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
                     int ldc, int transA, int transB, int accumulate, cudaStream_t stream);
+/* Tensor-core path used by b200rl_gemm_f32 for large NT products (transA = 0, transB = 1, 16-byte aligned
+ * operands): 3xTF32 split-precision on tcgen05.mma with TMA-fed 128B-swizzled tiles and TMEM accumulators
+ * (gemm_tc.cu).  Same contract as b200rl_gemm_f32; `_supported` tells whether a shape is eligible. */
+int b200rl_gemm_tc_supported(const float* A, const float* B, int M, int N, int K, int lda, int ldb, int transA,
+                             int transB);
+int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                   int ldc, int transA, int transB, int accumulate, cudaStream_t stream);
 /* nn.LayerNorm(eps) (+ nn.SiLU): miniblock sheeprl/utils/model.py:34-88; LayerNormChannelLast
  * sheeprl/models/models.py:507-518 (channel-last is native here).  act: 0 none, 1 SiLU. */
 int b200rl_ln_act_fwd(const float* X, const float* gamma, const float* beta, float* Y, long long M, int C,

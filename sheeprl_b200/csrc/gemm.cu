@@ -7,6 +7,8 @@
 //
 // Reference ops replaced: nn.Linear forward / its autograd backward as used throughout
 // sheeprl/algos/dreamer_v3/agent.py (MLP, RecurrentModel, representation/transition models).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -172,7 +174,22 @@ int launch_cfg(const float* A, const float* B, float* C, const float* bias, int 
 
 }  // namespace
 
-// include/b200rl.h: b200rl_gemm_f32
+extern "C" int b200rl_gemm_tc_supported(const float* A, const float* B, int M, int N, int K, int lda, int ldb,
+                                        int transA, int transB);
+extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                              int ldb, int ldc, int transA, int transB, int accumulate, cudaStream_t st);
+
+static bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200RL_DISABLE_TC");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// include/b200rl.h: b200rl_gemm_f32.  Large NT products go to the tcgen05 3xTF32 kernel (gemm_tc.cu); everything
+// else (skinny, transposed, unaligned) runs on the exact-fp32 FFMA kernels below.
 extern "C" int b200rl_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K,
                                int lda, int ldb, int ldc, int transA, int transB, int accumulate,
                                cudaStream_t st) {
@@ -187,6 +204,8 @@ extern "C" int b200rl_gemm_f32(const float* A, const float* B, float* C, const f
     }
     return B200RL_OK;
   }
+  if (tc_enabled() && b200rl_gemm_tc_supported(A, B, M, N, K, lda, ldb, transA, transB))
+    return b200rl_gemm_tc(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, accumulate, st);
   if (M <= 32) return launch_cfg<16, 64, 32, 1, 8>(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, accumulate, st);
   if (N <= 32) return launch_cfg<128, 32, 16, 8, 2>(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, accumulate, st);
   if (M <= 64 || N <= 64)

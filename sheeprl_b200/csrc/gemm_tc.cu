@@ -1,0 +1,379 @@
+// Tensor-core GEMM for sm_100a: C[M,N] = A[M,K] * B[N,K]^T (+bias) (+C), fp32 in / fp32 out, computed as
+// 3xTF32 on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged
+// in shared memory by TMA with the 128-byte swizzle).
+//
+// Why 3xTF32: the parity bar for this path is 1e-4 against an fp32 CPU oracle through chains of ~100 dependent
+// layers.  Each fp32 operand x is split in-kernel into hi = x with the 13 low mantissa bits
+// cleared (exactly what the TF32 datapath keeps) and lo = x - hi (exact in fp32); the product is accumulated
+// as hi*hi + hi*lo + lo*hi in fp32 (the dropped lo*lo term is ~2^-22 relative).  Effective rate is 1/3 of the
+// TF32 peak, ~10x the FFMA path.
+//
+// Pipeline (per 128x128 output tile, K step 32 = one 128-byte swizzle atom):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor loads of the raw fp32 A / B tiles, mbarrier complete_tx
+//   warps 4-7: splitters      -- rewrite each landed tile in place as `hi`, write `lo` to a twin buffer (same
+//                                swizzled offsets, so the split is layout-agnostic), fence.proxy.async, arrive
+//   warp 1   : MMA issuer     -- one elected lane issues 4 k-steps x 3 tcgen05.mma per stage, tcgen05.commit
+//                                releases the stage back to the producer
+//   warps 8-15: accumulators  -- every 4 k-blocks tcgen05.ld the finished TMEM chunk and add it into fp32
+//                                registers with RN adds (the tensor core accumulates with truncation), double
+//                                buffered TMEM; finally +bias / +C and store
+//   warp 2   : TMEM allocator
+// Replaces: every large nn.Linear forward / input-gradient product of the Dreamer-V3 step
+// (sheeprl/models/models.py MLP; agent.py heads, RSSM imagination, actor, critic).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int NTHREADS = 512;                       // 16 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 split, 8-15 accumulate
+constexpr int SPLIT_WARP0 = 4, NSPLIT_THREADS = 128;
+constexpr int ACC_WARP0 = 8, NACC_WARPS = 8;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel (trap -> launch failure), never hang the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile [rows][32 fp32] with 128B swizzle: 8-row groups are 1024 B apart (SBO), one atom along K.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                            // leading byte offset (unused: single atom along K)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+struct Smem {
+  // every operand buffer is a whole number of 1024-byte swizzle groups
+  float a_hi[STAGES][BM * BK];
+  float a_lo[STAGES][BM * BK];
+  float b_hi[STAGES][BN * BK];
+  float b_lo[STAGES][BN * BK];
+  uint64_t full[STAGES], split[STAGES], empty[STAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+// Two-level accumulation.  The tensor core adds each k-step into the fp32 TMEM accumulator with truncation
+// (round-toward-zero), a bias of ~2^-24 |acc| per add that grows linearly with K (measured 1.3e-5 at K=1536).
+// So TMEM only ever holds a CHUNK of CH k-blocks (CH*4 k-steps); each finished chunk is drained by the
+// accumulator warps into fp32 REGISTERS with round-to-nearest FADDs while the tensor core fills the other
+// TMEM buffer.
+constexpr int CH = 4;
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C,
+               const float* __restrict__ bias, int M, int N, int K, int ldc, int accumulate) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Smem<BN>& s = *reinterpret_cast<Smem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = (K + BK - 1) / BK;
+  const int nchunks = (nkb + CH - 1) / CH;
+  constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers; power of two >= 32 (BN in {64,128})
+  constexpr int ACC_COLS = BN / 2;         // columns per accumulator warp (two warps share a TMEM lane quarter)
+  // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.split[i], NSPLIT_THREADS / 32);
+      mbar_init(&s.empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.tfull[i], 1);
+      mbar_init(&s.tempty[i], NACC_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(&s.tmem_base, TMEM_COLS);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % STAGES;
+        if (kb >= STAGES) mbar_wait(&s.empty[st], ((kb / STAGES) - 1) & 1);
+        mbar_expect_tx(&s.full[st], (uint32_t)((BM + BN) * BK * sizeof(float)));
+        tma_load_2d(s.a_hi[st], &mapA, &s.full[st], kb * BK, m0);
+        tma_load_2d(s.b_hi[st], &mapB, &s.full[st], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single elected lane)
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % STAGES;
+        const int c = kb / CH, buf = c & 1;
+        const bool chunk_start = (kb % CH) == 0;
+        if (chunk_start && c >= 2) {           // the accumulator warps must have drained this TMEM buffer
+          mbar_wait(&s.tempty[buf], ((c >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        mbar_wait(&s.split[st], (kb / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem + (uint32_t)(buf * BN);
+        const uint32_t ah = smem_u32(s.a_hi[st]), al = smem_u32(s.a_lo[st]);
+        const uint32_t bh = smem_u32(s.b_hi[st]), bl = smem_u32(s.b_lo[st]);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 8; ++k4) {
+          const uint32_t off = k4 * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
+          // small cross terms first, then the leading term
+          umma_tf32(acc, make_desc(ah + off), make_desc(bl + off), IDESC, !(chunk_start && k4 == 0));
+          umma_tf32(acc, make_desc(al + off), make_desc(bh + off), IDESC, 1);
+          umma_tf32(acc, make_desc(ah + off), make_desc(bh + off), IDESC, 1);
+        }
+        umma_commit(&s.empty[st]);   // stage reusable once these MMAs have read it
+        if ((kb % CH) == CH - 1 || kb == nkb - 1) umma_commit(&s.tfull[buf]);   // chunk complete
+      }
+    }
+  } else if (warp >= SPLIT_WARP0 && warp < ACC_WARP0) {
+    // ===== splitters: hi/lo decomposition of each landed stage (layout-agnostic, in place)
+    const int t = threadIdx.x - SPLIT_WARP0 * 32;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb % STAGES;
+      mbar_wait(&s.full[st], (kb / STAGES) & 1);
+      float4* ah = reinterpret_cast<float4*>(s.a_hi[st]);
+      float4* al = reinterpret_cast<float4*>(s.a_lo[st]);
+#pragma unroll
+      for (int i = 0; i < BM * BK / 4 / NSPLIT_THREADS; ++i) {
+        const int idx = t + i * NSPLIT_THREADS;
+        const float4 v = ah[idx];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+        ah[idx] = h;
+        al[idx] = l;
+      }
+      float4* bh = reinterpret_cast<float4*>(s.b_hi[st]);
+      float4* bl = reinterpret_cast<float4*>(s.b_lo[st]);
+#pragma unroll
+      for (int i = 0; i < BN * BK / 4 / NSPLIT_THREADS; ++i) {
+        const int idx = t + i * NSPLIT_THREADS;
+        const float4 v = bh[idx];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+        bh[idx] = h;
+        bl[idx] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.split[st]);
+    }
+  } else if (warp >= ACC_WARP0) {
+    // ===== accumulators + epilogue.  Warp (q, half): TMEM lanes [32q, 32q+32), columns [half*BN/2, +BN/2).
+    const int q = warp & 3, half = (warp - ACC_WARP0) >> 2;
+    float acc[ACC_COLS];
+#pragma unroll
+    for (int j = 0; j < ACC_COLS; ++j) acc[j] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&s.tfull[buf], (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < ACC_COLS; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * ACC_COLS + c0), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tempty[buf]);
+    }
+    const int row = m0 + q * 32 + lane;
+    if (row < M) {
+      const int cb = n0 + half * ACC_COLS;
+      float* crow = C + (size_t)row * ldc + cb;
+      const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (cb + ACC_COLS <= N);
+      if (vec) {
+#pragma unroll
+        for (int j = 0; j < ACC_COLS; j += 4) {
+          float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          if (bias) { o.x += bias[cb + j]; o.y += bias[cb + j + 1]; o.z += bias[cb + j + 2]; o.w += bias[cb + j + 3]; }
+          if (accumulate) { const float4 p = *reinterpret_cast<const float4*>(crow + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+          *reinterpret_cast<float4*>(crow + j) = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < ACC_COLS; ++j) {
+          if (cb + j < N) {
+            float o = acc[j];
+            if (bias) o += bias[cb + j];
+            if (accumulate) o += crow[j];
+            crow[j] = o;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side: tensor-map cache
+struct MapKey {
+  const void* ptr; int rows, cols, ld, box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<long long>()(((long long)k.rows << 32) ^ k.cols) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    h ^= std::hash<long long>()(((long long)k.ld << 8) ^ k.box_rows) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapHash> g_maps;
+std::mutex g_maps_mu;
+
+// [rows][cols] fp32, row stride ld; box = [box_rows][32], 128-byte swizzle, zero fill out of bounds
+int get_map(const float* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  MapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return B200RL_OK; }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b200rl_set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d", (int)r, rows, cols, ld);
+    return B200RL_ERR_CUDA;
+  }
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return B200RL_OK;
+}
+
+}  // namespace
+
+// Shapes the tensor-core path accepts: NT product, 16-byte aligned operands with row strides that are
+// multiples of 16 bytes, and enough work to fill a tile.
+extern "C" int b200rl_gemm_tc_supported(const float* A, const float* B, int M, int N, int K, int lda, int ldb,
+                                        int transA, int transB) {
+  if (transA || !transB) return 0;
+  if (M < 256 || N < 48 || K < 32) return 0;
+  if ((lda & 3) || (ldb & 3)) return 0;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return 0;
+  return 1;
+}
+
+extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                              int ldb, int ldc, int transA, int transB, int accumulate, cudaStream_t st) {
+  RL_CHECK_ARG(A && B && C, "null pointer");
+  RL_CHECK_ARG(b200rl_gemm_tc_supported(A, B, M, N, K, lda, ldb, transA, transB), "shape not eligible for the tensor-core path");
+  const int BN = (N <= 64) ? 64 : 128;
+  CUtensorMap ma, mb;
+  if (int rc = get_map(A, M, K, lda, BM, &ma)) return rc;
+  if (int rc = get_map(B, N, K, ldb, BN, &mb)) return rc;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if (BN == 64) {
+    const size_t smem = sizeof(Smem<64>) + 1024;
+    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate);
+  } else {
+    const size_t smem = sizeof(Smem<128>) + 1024;
+    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate);
+  }
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}

@@ -44,7 +44,32 @@ GEMM_SHAPES = [
     (1024, 512, 1536, False, True), (1024, 1536, 255, False, False), (255, 512, 1024, True, False),
     (300, 70, 33, False, True), (7, 3, 5, False, True), (5, 1, 129, False, True), (1000, 2, 512, False, True),
     (2, 512, 1000, True, False), (130, 130, 70, True, True), (64, 4096, 200, False, True),
+    # tensor-core (tcgen05 3xTF32) eligible: NT, M >= 256, N >= 48, 16-byte aligned rows
+    (16384, 512, 1536, False, True), (1024, 255, 512, False, True), (15360, 512, 512, False, True),
+    (1000, 72, 40, False, True), (257, 129, 36, False, True), (1024, 4096, 1536, False, True),
 ]
+
+
+def test_gemm_tensor_core_path_is_taken_and_exact_enough(ops):
+    """The tcgen05 path must (a) be selected for the big NT products, (b) keep fp32-level accuracy (3xTF32)."""
+    import ctypes
+
+    cu, em = ops
+    M, N, K = 2048, 512, 1536
+    A, B = rnd(M, K, seed=11), rnd(N, K, seed=12)
+    Ag, Bg = A.cuda(), B.cuda()
+    assert cu.lib.b200rl_gemm_tc_supported(ctypes.c_void_p(Ag.data_ptr()), ctypes.c_void_p(Bg.data_ptr()), M, N, K, K, K, 0, 1) == 1
+    Cg = torch.empty(M, N, device="cuda")
+    cu.gemm(Ag, Bg, Cg, False, True)
+    ref = (A.double() @ B.double().t())
+    err = float((Cg.cpu().double() - ref).abs().max() / ref.abs().max())
+    assert err < 3e-6, err          # plain TF32 would give ~1e-3 here
+    # view with a 16-byte aligned column offset and a wider leading dimension
+    Aw, Bw, Cw = rnd(M, K + 8, seed=13).cuda(), rnd(N, K + 8, seed=14).cuda(), torch.zeros(M, N + 8, device="cuda")
+    cu.gemm(Aw[:, 4:4 + K], Bw[:, 4:4 + K], Cw[:, 4:4 + N], False, True)
+    ref = Aw[:, 4:4 + K].cpu().double() @ Bw[:, 4:4 + K].cpu().double().t()
+    assert float((Cw[:, 4:4 + N].cpu().double() - ref).abs().max() / ref.abs().max()) < 3e-6
+    assert float(Cw[:, :4].abs().sum()) == 0 and float(Cw[:, 4 + N:].abs().sum()) == 0
 
 
 @pytest.mark.parametrize("M,N,K,tA,tB", GEMM_SHAPES)
