@@ -56,12 +56,30 @@ int b200rl_col_sum(const float* X, float* out, long long M, int C, long long ldx
 int b200rl_obs_prep(const void* obs_nchw, int is_uint8, float* out_nhwc, long long NB, int C, int HW,
                     cudaStream_t stream);
 int b200rl_transpose_batched(const float* X, float* Y, int NB, int a, int b, cudaStream_t stream);
+/* Y[j][i] = X[i][j] for a strided [rows][cols] view (used to present K-major operands to the tensor-core GEMM:
+ * W^T for input gradients, dY^T / X^T for weight gradients). */
+int b200rl_transpose2d(const float* X, float* Y, int rows, int cols, long long ldx, long long ldy, cudaStream_t stream);
 int b200rl_conv_down(const float* big, const float* W, float* small_, int NB, int h, int w, int Cs, int Cb,
                      cudaStream_t stream);
 int b200rl_conv_up(const float* small_, const float* W, float* big, const float* bias, int NB, int h, int w, int Cs,
                    int Cb, cudaStream_t stream);
 int b200rl_conv_wgrad(const float* small_, const float* big, float* dW, int NB, int h, int w, int Cs, int Cb,
                       int accumulate, cudaStream_t stream);
+/* Tensor-core implicit-GEMM versions of conv_down / conv_up (gemm_tc.cu: 4-D TMA boxes gather the taps, no
+ * im2col buffer, 3xTF32 tcgen05).  `Wpacked` is a caller-owned 16*Cs*Cb-float workspace filled by
+ * b200rl_conv_pack (down: [Cs][tap][Cb]; up: [parity][Cb][tap][Cs]) after every weight update.  Eligible when the
+ * gathered image has a multiple of 32 channels and the small grid tiles by 128 pixels (`_supported`). */
+/* Weight gradient as one tensor-core GEMM over all pixels: small^T [Cs][P] times the transposed im2col of `big`
+ * [16*Cb][P] (both K-major, split-K).  `workspace`: b200rl_conv_wgrad_tc_workspace(...) floats, caller-owned. */
+long long b200rl_conv_wgrad_tc_workspace(int NB, int h, int w, int Cs, int Cb);
+int b200rl_conv_wgrad_tc(const float* small_, const float* big, float* dW, float* workspace, int NB, int h, int w,
+                         int Cs, int Cb, int accumulate, cudaStream_t stream);
+int b200rl_conv_tc_supported(int mode_up, int NB, int h, int w, int Cs, int Cb);
+int b200rl_conv_pack(const float* W, float* Wpacked, int mode_up, int Cs, int Cb, cudaStream_t stream);
+int b200rl_conv_down_tc(const float* big, const float* Wpacked, float* small_, int NB, int h, int w, int Cs, int Cb,
+                        cudaStream_t stream);
+int b200rl_conv_up_tc(const float* small_, const float* Wpacked, float* big, const float* bias, int NB, int h, int w,
+                      int Cs, int Cb, cudaStream_t stream);
 
 /* ---- RSSM ------------------------------------------------------------------------------------------
  * LayerNormGRUCell gates models.py:399-403; is_first masking agent.py:425-430; unimix agent.py:437-449;

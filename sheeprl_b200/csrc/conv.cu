@@ -358,7 +358,112 @@ __global__ void transpose_batched_kernel(const float* __restrict__ X, float* __r
   }
 }
 
+// Y[j*ldy + i] = X[i*ldx + j]; X [rows][cols] with row stride ldx; 32x32 smem tiles
+__global__ void transpose2d_kernel(const float* __restrict__ X, float* __restrict__ Y, int rows, int cols,
+                                   long long ldx, long long ldy) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + threadIdx.x;
+    if (i < rows && j < cols) tile[r][threadIdx.x] = X[(long long)i * ldx + j];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + threadIdx.x;
+    if (i < rows && j < cols) Y[(long long)j * ldy + i] = tile[threadIdx.x][r];
+  }
+}
+
+// Transposed im2col for the weight-gradient GEMM: out[(tap*Cb + cb)][pix] = big[n, 2y-1+ky, 2x-1+kx, cb] (0 outside).
+// One block = 32 pixels x 32 channels of one tap: coalesced channel reads, smem transpose, coalesced pixel writes.
+__global__ void im2col_t_kernel(const float* __restrict__ Big, float* __restrict__ out, int NB, int h, int w, int Cb,
+                                long long ldo) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z, ky = tap >> 2, kx = tap & 3;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const long long P = (long long)NB * h * w;
+  const int Hb = 2 * h, Wb = 2 * w;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const long long p = p0 + r;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < P && c < Cb) {
+      const int x = (int)(p % w);
+      const long long t = p / w;
+      const int y = (int)(t % h);
+      const long long n = t / h;
+      const int yy = 2 * y - 1 + ky, xx = 2 * x - 1 + kx;
+      if (yy >= 0 && yy < Hb && xx >= 0 && xx < Wb) v = Big[((n * Hb + yy) * Wb + xx) * (long long)Cb + c];
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = c0 + r;
+    const long long p = p0 + threadIdx.x;
+    if (c < Cb && p < P) out[((long long)tap * Cb + c) * ldo + p] = tile[threadIdx.x][r];
+  }
+}
+
+// dW[cs][cb][tap] = G[tap*Cb + cb][cs]
+__global__ void wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ dW, int Cs, int Cb, int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Cs * Cb * 16) return;
+  const int tap = (int)(idx % 16);
+  const int cb = (int)((idx / 16) % Cb);
+  const int cs = (int)(idx / (16LL * Cb));
+  const float v = G[((long long)tap * Cb + cb) * Cs + cs];
+  dW[idx] = accumulate ? dW[idx] + v : v;
+}
+
 }  // namespace
+
+extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                              int ldb, int ldc, int transA, int transB, int accumulate, cudaStream_t st);
+
+// Weight gradient on the tensor cores: dW = small^T (x) im2col(big) as ONE K-major GEMM with K = all pixels.
+// workspace: (Cs + 16*Cb) * Ppad + 16*Cs*Cb floats, Ppad = pixels rounded up to 4.
+extern "C" long long b200rl_conv_wgrad_tc_workspace(int NB, int h, int w, int Cs, int Cb) {
+  const long long P = ((long long)NB * h * w + 3) / 4 * 4;
+  return (Cs + 16LL * Cb) * P + 16LL * Cs * Cb;
+}
+extern "C" int b200rl_conv_wgrad_tc(const float* small_, const float* big, float* dW, float* workspace, int NB, int h,
+                                    int w, int Cs, int Cb, int accumulate, cudaStream_t st) {
+  RL_CHECK_ARG(small_ && big && dW && workspace, "null pointer");
+  const long long P = (long long)NB * h * w, Pp = (P + 3) / 4 * 4;
+  RL_CHECK_ARG(P >= 1024 && Cs >= 48 && Cb >= 8 && P <= 2000000000LL, "shape not eligible for the tensor-core wgrad path");
+  float* St = workspace;                       // [Cs][Pp]
+  float* Bt = workspace + (long long)Cs * Pp;  // [16*Cb][Pp]
+  float* G = Bt + 16LL * Cb * Pp;              // [16*Cb][Cs]
+  RL_CHECK_ARG(ceil_div(P, 32) <= 2147483647LL && ceil_div(Cb, 32) <= 65535, "grid too large");
+  // small [P][Cs] -> St [Cs][Pp]
+  {
+    const long long rows = P;
+    for (long long r0 = 0; r0 < rows; r0 += 32LL * 65535) {   // transpose2d launches are limited to 65535 row tiles
+      const int nr = (int)min((long long)32 * 65535, rows - r0);
+      transpose2d_kernel<<<dim3(ceil_div(Cs, 32), ceil_div(nr, 32)), dim3(32, 8), 0, st>>>(small_ + r0 * Cs, St + r0, nr, Cs, Cs, Pp);
+    }
+  }
+  im2col_t_kernel<<<dim3((unsigned)ceil_div(P, 32), ceil_div(Cb, 32), 16), dim3(32, 8), 0, st>>>(big, Bt, NB, h, w, Cb, Pp);
+  RL_CHECK_LAUNCH();
+  // rows = (tap, cb) (>= 128), columns = cs: G = im2col^T . small
+  if (int rc = b200rl_gemm_tc(Bt, St, G, nullptr, 16 * Cb, Cs, (int)P, (int)Pp, (int)Pp, Cs, 0, 1, 0, st)) return rc;
+  wgrad_unpack_kernel<<<ceil_div(16LL * Cs * Cb, 256), 256, 0, st>>>(G, dW, Cs, Cb, accumulate);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_transpose2d(const float* X, float* Y, int rows, int cols, long long ldx, long long ldy,
+                                  cudaStream_t st) {
+  RL_CHECK_ARG(X && Y, "null pointer");
+  if (rows <= 0 || cols <= 0) return B200RL_OK;
+  RL_CHECK_ARG(ldx >= cols && ldy >= rows, "leading dimension too small");
+  RL_CHECK_ARG(ceil_div(rows, 32) <= 65535, "too many rows for one launch");
+  transpose2d_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, st>>>(X, Y, rows, cols, ldx, ldy);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
 
 extern "C" int b200rl_conv_down(const float* big, const float* W, float* small, int NB, int h, int w, int Cs, int Cb,
                                 cudaStream_t st) {

@@ -20,7 +20,15 @@
 //   warp 2   : TMEM allocator
 // Replaces: every large nn.Linear forward / input-gradient product of the Dreamer-V3 step
 // (sheeprl/models/models.py MLP; agent.py heads, RSSM imagination, actor, critic).
+//
+// The same pipeline runs the stride-2 k4 p1 convolutions as IMPLICIT GEMMs (no im2col buffer): the A tile of a
+// k-block (one filter tap x 32 input channels) is a 4-D TMA box over the channel-last image
+// [N][H][W][C] -- box {32 ch, bw, bh, bn} with element strides {1,2,2,1} for the strided gather of Conv2d
+// forward ("down"), {1,1,1,1} for the 2x2 sub-pixel taps of ConvTranspose2d forward ("up") -- and TMA's
+// out-of-bounds zero fill supplies the padding.  Replaces CNNEncoder / CNNDecoder convolutions
+// (sheeprl/algos/dreamer_v3/agent.py:78-91, :199-222) and their input-gradient passes.
 #include <cuda.h>
+#include <cudaTypedefs.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -72,6 +80,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           smem_u32(smem_dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -139,16 +155,42 @@ struct Smem {
 // TMEM buffer.
 constexpr int CH = 4;
 
+constexpr int MODE_GEMM = 0, MODE_DOWN = 1, MODE_UP = 2;
+struct TileGeo {
+  int mode;
+  int h, w, NB;            // small-image grid (conv modes)
+  int bw, bh, bn;          // output tile = bn images x bh rows x bw cols of the small grid (bw*bh*bn == 128)
+  int tiles_x, tiles_y;    // tiles per image
+  int chunks;              // input channels / 32
+  int Cout;                // output channels
+  int ksplits;             // GEMM mode: number of K splits (gridDim.z); > 1 => atomic accumulation into C
+};
+
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C,
-               const float* __restrict__ bias, int M, int N, int K, int ldc, int accumulate) {
+               const float* __restrict__ bias, int M, int N, int K, int ldc, int accumulate, const TileGeo geo) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem<BN>& s = *reinterpret_cast<Smem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb = (K + BK - 1) / BK;
+  // split-K (GEMM mode): blockIdx.z owns k-blocks [kb_base, kb_base + nkb); partial sums are atomically added
+  int kb_base = 0, nkb = (K + BK - 1) / BK;
+  if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
+    const int per = (nkb + geo.ksplits - 1) / geo.ksplits;
+    kb_base = (int)blockIdx.z * per;
+    nkb = min(per, nkb - kb_base);
+  }
   const int nchunks = (nkb + CH - 1) / CH;
+  // conv modes: this CTA's tile origin on the small-image grid; blockIdx.z = output parity class (up)
+  int tn0 = 0, ty0 = 0, tx0 = 0;
+  const int py = (int)blockIdx.z >> 1, px = (int)blockIdx.z & 1;
+  if (geo.mode != MODE_GEMM) {
+    const int id = blockIdx.y;
+    tx0 = (id % geo.tiles_x) * geo.bw;
+    ty0 = ((id / geo.tiles_x) % geo.tiles_y) * geo.bh;
+    tn0 = (id / (geo.tiles_x * geo.tiles_y)) * geo.bn;
+  }
   constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers; power of two >= 32 (BN in {64,128})
   constexpr int ACC_COLS = BN / 2;         // columns per accumulator warp (two warps share a TMEM lane quarter)
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -179,8 +221,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int st = kb % STAGES;
         if (kb >= STAGES) mbar_wait(&s.empty[st], ((kb / STAGES) - 1) & 1);
         mbar_expect_tx(&s.full[st], (uint32_t)((BM + BN) * BK * sizeof(float)));
-        tma_load_2d(s.a_hi[st], &mapA, &s.full[st], kb * BK, m0);
-        tma_load_2d(s.b_hi[st], &mapB, &s.full[st], kb * BK, n0);
+        if (geo.mode == MODE_GEMM) {
+          tma_load_2d(s.a_hi[st], &mapA, &s.full[st], (kb_base + kb) * BK, m0);
+          tma_load_2d(s.b_hi[st], &mapB, &s.full[st], (kb_base + kb) * BK, n0);
+        } else {
+          const int tap = kb / geo.chunks, ch = (kb - tap * geo.chunks) * BK;
+          int x, y;
+          if (geo.mode == MODE_DOWN) { x = 2 * tx0 - 1 + (tap & 3); y = 2 * ty0 - 1 + (tap >> 2); }
+          else                       { x = tx0 + px - (tap & 1);    y = ty0 + py - (tap >> 1); }
+          tma_load_4d(s.a_hi[st], &mapA, &s.full[st], ch, x, y, tn0);
+          tma_load_2d(s.b_hi[st], &mapB, &s.full[st], kb * BK, n0 + (geo.mode == MODE_UP ? (int)blockIdx.z * geo.Cout : 0));
+        }
       }
     }
   } else if (warp == 1) {
@@ -271,11 +322,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (lane == 0) mbar_arrive(&s.tempty[buf]);
     }
     const int row = m0 + q * 32 + lane;
-    if (row < M) {
+    bool row_ok = row < M;
+    size_t row_off = (size_t)row * ldc;
+    if (geo.mode != MODE_GEMM) {
+      const int r = q * 32 + lane;
+      const int wi = r % geo.bw, hi = (r / geo.bw) % geo.bh, ni = r / (geo.bw * geo.bh);
+      const int n = tn0 + ni, y = ty0 + hi, x = tx0 + wi;
+      row_ok = n < geo.NB;
+      if (geo.mode == MODE_DOWN) row_off = (((size_t)n * geo.h + y) * geo.w + x) * (size_t)ldc;
+      else row_off = (((size_t)n * (2 * geo.h) + (2 * y + py)) * (2 * geo.w) + (2 * x + px)) * (size_t)ldc;
+    }
+    if (row_ok) {
       const int cb = n0 + half * ACC_COLS;
-      float* crow = C + (size_t)row * ldc + cb;
+      float* crow = C + row_off + cb;
       const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (cb + ACC_COLS <= N);
-      if (vec) {
+      if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
+#pragma unroll
+        for (int j = 0; j < ACC_COLS; ++j)
+          if (cb + j < N) atomicAdd(crow + j, acc[j]);   // C was initialised by init_c_kernel (bias / zero / kept)
+      } else if (vec) {
 #pragma unroll
         for (int j = 0; j < ACC_COLS; j += 4) {
           float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -319,6 +384,23 @@ struct MapHash {
 std::unordered_map<MapKey, CUtensorMap, MapHash> g_maps;
 std::mutex g_maps_mu;
 
+// cuTensorMapEncodeTiled is a driver-API symbol: resolve it through the runtime at first use so that the library
+// has no link-time dependency on libcuda.so (it must load on a GPU-less build host).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 // [rows][cols] fp32, row stride ld; box = [box_rows][32], 128-byte swizzle, zero fill out of bounds
 int get_map(const float* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
   MapKey key{ptr, rows, cols, ld, box_rows};
@@ -330,7 +412,9 @@ int get_map(const float* ptr, int rows, int cols, int ld, int box_rows, CUtensor
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) { b200rl_set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200RL_ERR_CUDA; }
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -343,14 +427,158 @@ int get_map(const float* ptr, int rows, int cols, int ld, int box_rows, CUtensor
   return B200RL_OK;
 }
 
+struct Map4Key {
+  const void* ptr; int C, W, H, N, bw, bh, bn, es;
+  bool operator==(const Map4Key& o) const {
+    return ptr == o.ptr && C == o.C && W == o.W && H == o.H && N == o.N && bw == o.bw && bh == o.bh && bn == o.bn && es == o.es;
+  }
+};
+struct Map4Hash {
+  size_t operator()(const Map4Key& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    const long long v[4] = {((long long)k.C << 32) ^ k.W, ((long long)k.H << 32) ^ k.N, ((long long)k.bw << 32) ^ k.bh,
+                            ((long long)k.bn << 32) ^ k.es};
+    for (long long x : v) h ^= std::hash<long long>()(x) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+std::unordered_map<Map4Key, CUtensorMap, Map4Hash> g_maps4;
+
+// channel-last image [N][H][W][C]; box = {32 ch, bw px, bh px, bn images} sampled with element stride es in W and H
+int get_map4(const float* ptr, int C, int W, int H, int N, int bw, int bh, int bn, int es, CUtensorMap* out) {
+  Map4Key key{ptr, C, W, H, N, bw, bh, bn, es};
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  auto it = g_maps4.find(key);
+  if (it != g_maps4.end()) { *out = it->second; return B200RL_OK; }
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)C * W * 4, (cuuint64_t)C * W * H * 4};
+  // with an element stride e the box spans (count-1)*e+1 source elements and loads `count` of them
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)((bw - 1) * es + 1), (cuuint32_t)((bh - 1) * es + 1), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) { b200rl_set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200RL_ERR_CUDA; }
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b200rl_set_error("cuTensorMapEncodeTiled(4D) failed (%d) for image [%d,%d,%d,%d]", (int)r, N, H, W, C);
+    return B200RL_ERR_CUDA;
+  }
+  if (g_maps4.size() > 1024) g_maps4.clear();
+  g_maps4.emplace(key, m);
+  *out = m;
+  return B200RL_OK;
+}
+
+// tile shape on the small grid: as wide as possible, 128 pixels in total
+bool conv_tile(int h, int w, int NB, int* bw, int* bh, int* bn) {
+  if (w <= 0 || h <= 0 || (w & (w - 1)) || (h & (h - 1))) return false;
+  *bw = w < 128 ? w : 128;
+  int rest = 128 / *bw;
+  *bh = h < rest ? h : rest;
+  *bn = rest / *bh;
+  return (w % *bw == 0) && (h % *bh == 0) && (*bw * *bh * *bn == 128) && (NB % *bn == 0);
+}
+
+__global__ void conv_pack_down_kernel(const float* __restrict__ W, float* __restrict__ P, int Cs, int Cb) {
+  // P[cs][tap][cb] = W[cs][cb][tap]
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Cs * Cb * 16) return;
+  const int cb = (int)(idx % Cb);
+  const int tap = (int)((idx / Cb) % 16);
+  const int cs = (int)(idx / ((long long)Cb * 16));
+  P[idx] = W[((long long)cs * Cb + cb) * 16 + tap];
+}
+__global__ void conv_pack_up_kernel(const float* __restrict__ W, float* __restrict__ P, int Cs, int Cb) {
+  // P[parity][cb][t][cs] = W[cs][cb][ky][kx], ky = (1-py)+2j, kx = (1-px)+2i, t = 2j+i
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Cs * Cb * 16) return;
+  const int cs = (int)(idx % Cs);
+  const int t = (int)((idx / Cs) % 4);
+  const int cb = (int)((idx / ((long long)Cs * 4)) % Cb);
+  const int par = (int)(idx / ((long long)Cs * 4 * Cb));
+  const int py = par >> 1, px = par & 1;
+  const int ky = (1 - py) + 2 * (t >> 1), kx = (1 - px) + 2 * (t & 1);
+  P[idx] = W[((long long)cs * Cb + cb) * 16 + ky * 4 + kx];
+}
+
+__global__ void init_c_kernel(float* __restrict__ C, const float* __restrict__ bias, int M, int N, int ldc, int keep) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * N) return;
+  const int m = (int)(idx / N), n = (int)(idx % N);
+  float v = keep ? C[(size_t)m * ldc + n] : 0.f;
+  if (bias) v += bias[n];
+  C[(size_t)m * ldc + n] = v;
+}
+
+int launch_conv(int mode, const float* img, const float* Wp, float* out, const float* bias, int NB, int h, int w, int Cin,
+                int Cout, cudaStream_t st) {
+  TileGeo g;
+  g.mode = mode; g.h = h; g.w = w; g.NB = NB; g.chunks = Cin / BK; g.Cout = Cout; g.ksplits = 1;
+  RL_CHECK_ARG(conv_tile(h, w, NB, &g.bw, &g.bh, &g.bn), "image grid not tileable by 128 pixels");
+  g.tiles_x = w / g.bw; g.tiles_y = h / g.bh;
+  const int taps = mode == MODE_DOWN ? 16 : 4;
+  const int K = taps * Cin;
+  CUtensorMap ma, mb;
+  if (mode == MODE_DOWN) { if (int rc = get_map4(img, Cin, 2 * w, 2 * h, NB, g.bw, g.bh, g.bn, 2, &ma)) return rc; }
+  else                   { if (int rc = get_map4(img, Cin, w, h, NB, g.bw, g.bh, g.bn, 1, &ma)) return rc; }
+  const int BN = (Cout <= 64) ? 64 : 128;
+  const int brows = mode == MODE_UP ? 4 * Cout : Cout;
+  if (int rc = get_map(Wp, brows, K, K, BN, &mb)) return rc;
+  const int mtiles = g.tiles_x * g.tiles_y * (NB / g.bn);
+  dim3 grid((Cout + BN - 1) / BN, mtiles, mode == MODE_UP ? 4 : 1);
+  const int M = NB * h * w;  // unused by conv addressing; row validity comes from geo
+  if (BN == 64) {
+    const size_t smem = sizeof(Smem<64>) + 1024;
+    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma, mb, out, bias, M, Cout, K, Cout, 0, g);
+  } else {
+    const size_t smem = sizeof(Smem<128>) + 1024;
+    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, out, bias, M, Cout, K, Cout, 0, g);
+  }
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
 }  // namespace
+
+// ---- convolution entry points (tensor-core implicit GEMM).  Wpacked: 16*Cs*Cb floats of caller workspace.
+extern "C" int b200rl_conv_tc_supported(int mode_up, int NB, int h, int w, int Cs, int Cb) {
+  int bw, bh, bn;
+  if (!conv_tile(h, w, NB, &bw, &bh, &bn)) return 0;
+  const int Cin = mode_up ? Cs : Cb, Cout = mode_up ? Cb : Cs;
+  if (Cin % BK != 0 || Cout < 16 || Cout % 4 != 0) return 0;
+  return 1;
+}
+extern "C" int b200rl_conv_pack(const float* W, float* Wpacked, int mode_up, int Cs, int Cb, cudaStream_t st) {
+  RL_CHECK_ARG(W && Wpacked, "null pointer");
+  const long long n = (long long)Cs * Cb * 16;
+  if (mode_up) conv_pack_up_kernel<<<ceil_div(n, 256), 256, 0, st>>>(W, Wpacked, Cs, Cb);
+  else conv_pack_down_kernel<<<ceil_div(n, 256), 256, 0, st>>>(W, Wpacked, Cs, Cb);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+extern "C" int b200rl_conv_down_tc(const float* big, const float* Wpacked, float* small_, int NB, int h, int w, int Cs,
+                                   int Cb, cudaStream_t st) {
+  RL_CHECK_ARG(big && Wpacked && small_, "null pointer");
+  RL_CHECK_ARG(b200rl_conv_tc_supported(0, NB, h, w, Cs, Cb), "shape not eligible for the tensor-core conv path");
+  return launch_conv(MODE_DOWN, big, Wpacked, small_, nullptr, NB, h, w, Cb, Cs, st);
+}
+extern "C" int b200rl_conv_up_tc(const float* small_, const float* Wpacked, float* big, const float* bias, int NB, int h,
+                                 int w, int Cs, int Cb, cudaStream_t st) {
+  RL_CHECK_ARG(big && Wpacked && small_, "null pointer");
+  RL_CHECK_ARG(b200rl_conv_tc_supported(1, NB, h, w, Cs, Cb), "shape not eligible for the tensor-core conv path");
+  return launch_conv(MODE_UP, small_, Wpacked, big, bias, NB, h, w, Cs, Cb, st);
+}
 
 // Shapes the tensor-core path accepts: NT product, 16-byte aligned operands with row strides that are
 // multiples of 16 bytes, and enough work to fill a tile.
 extern "C" int b200rl_gemm_tc_supported(const float* A, const float* B, int M, int N, int K, int lda, int ldb,
                                         int transA, int transB) {
   if (transA || !transB) return 0;
-  if (M < 256 || N < 48 || K < 32) return 0;
+  if (M < 128 || N < 48 || K < 32) return 0;
   if ((lda & 3) || (ldb & 3)) return 0;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return 0;
   return 1;
@@ -365,14 +593,31 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
   if (int rc = get_map(A, M, K, lda, BM, &ma)) return rc;
   if (int rc = get_map(B, N, K, ldb, BN, &mb)) return rc;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  TileGeo g = {};
+  g.mode = MODE_GEMM;
+  g.ksplits = 1;
+  const int tiles = grid.x * grid.y, nkb = (K + BK - 1) / BK;
+  if (tiles < 120 && nkb >= 16) {
+    int sp = (2 * kNumSMs + tiles - 1) / tiles;
+    if (sp > nkb / 8) sp = nkb / 8;
+    if (sp < 1) sp = 1;
+    const int per = (nkb + sp - 1) / sp;
+    g.ksplits = (nkb + per - 1) / per;   // every split owns at least one k-block
+  }
+  if (g.ksplits > 1) {
+    grid.z = g.ksplits;
+    if (!accumulate || bias) {
+      init_c_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(C, bias, M, N, ldc, accumulate);
+    }
+  }
   if (BN == 64) {
     const size_t smem = sizeof(Smem<64>) + 1024;
     RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate);
+    gemm_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate, g);
   } else {
     const size_t smem = sizeof(Smem<128>) + 1024;
     RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate);
+    gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate, g);
   }
   RL_CHECK_LAUNCH();
   return B200RL_OK;

@@ -100,6 +100,9 @@ class CudaOps:
         if self.lib.b200rl_device_check() != 0:
             raise B200RLError(self.lib.b200rl_last_error().decode())
         self.launches = 0
+        self.use_tc = os.environ.get("B200RL_DISABLE_TC", "0") != "1"   # tensor-core (tcgen05) paths
+        self._pack_bufs = {}
+        self._scratch_bufs = {}
 
     # ------------------------------------------------------------------ plumbing
     def _st(self):
@@ -118,9 +121,45 @@ class CudaOps:
         assert (A.shape[1] if transA else A.shape[0]) == M, (A.shape, C.shape, transA)
         assert (B.shape[0] if transB else B.shape[1]) == N and (B.shape[1] if transB else B.shape[0]) == K, \
             (A.shape, B.shape, C.shape, transA, transB)
+        if self.use_tc and (transA or not transB) and M >= 128 and N >= 48 and K >= 256 and \
+                2.0 * M * N * K >= 2e8 and self._gemm_via_transposes(A, B, C, M, N, K, transA, transB, bias, accumulate):
+            return
         self._ck(self.lib.b200rl_gemm_f32(_p(A), _p(B), _p(C), _p(bias), c_int(M), c_int(N), c_int(K), c_int(_ld(A)),
                                           c_int(_ld(B)), c_int(_ld(C)), c_int(int(transA)), c_int(int(transB)),
                                           c_int(int(accumulate)), self._st()))
+
+    def _scratch(self, slot: str, numel: int) -> torch.Tensor:
+        buf = self._scratch_bufs.get(slot)
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(numel, dtype=torch.float32, device=self.device)
+            self._scratch_bufs[slot] = buf
+        return buf
+
+    def _gemm_via_transposes(self, A, B, C, M, N, K, transA, transB, bias, accumulate) -> bool:
+        """Input-gradient (A @ W) and weight-gradient (dY^T @ X) products on the tensor cores: the operand(s) whose
+        reduction index is not contiguous are transposed into scratch (K-major), then the NT tcgen05 kernel runs
+        (split-K over the long reduction of weight gradients)."""
+        Kp = (K + 3) // 4 * 4
+        if transA:   # A is [K, M]
+            At = self._scratch("At", M * Kp)
+            self._ck(self.lib.b200rl_transpose2d(_p(A), _p(At), c_int(K), c_int(M), c_ll(_ld(A)), c_ll(Kp), self._st()))
+            a_ptr, lda = At.data_ptr(), Kp
+        else:
+            if _ld(A) % 4 or A.data_ptr() % 16:
+                return False
+            a_ptr, lda = A.data_ptr(), _ld(A)
+        if not transB:   # B is [K, N]
+            Bt = self._scratch("Bt", N * Kp)
+            self._ck(self.lib.b200rl_transpose2d(_p(B), _p(Bt), c_int(K), c_int(N), c_ll(_ld(B)), c_ll(Kp), self._st()))
+            b_ptr, ldb = Bt.data_ptr(), Kp
+        else:
+            if _ld(B) % 4 or B.data_ptr() % 16:
+                return False
+            b_ptr, ldb = B.data_ptr(), _ld(B)
+        self._ck(self.lib.b200rl_gemm_tc(c_void_p(a_ptr), c_void_p(b_ptr), _p(C), _p(bias), c_int(M), c_int(N), c_int(K),
+                                         c_int(lda), c_int(ldb), c_int(_ld(C)), c_int(0), c_int(1),
+                                         c_int(int(accumulate)), self._st()))
+        return True
 
     def col_sum(self, X, out, accumulate: bool = False):
         _f32(X, out)
@@ -158,8 +197,24 @@ class CudaOps:
         NB, h, w, Cs = small.shape
         Cb = big.shape[-1]
         assert tuple(big.shape) == (NB, 2 * h, 2 * w, Cb) and tuple(W.shape) == (Cs, Cb, 4, 4)
+        if self.use_tc and self.lib.b200rl_conv_tc_supported(0, NB, h, w, Cs, Cb):
+            Wp = self._packed(W, 0, Cs, Cb)
+            self._ck(self.lib.b200rl_conv_down_tc(_p(big), _p(Wp), _p(small), c_int(NB), c_int(h), c_int(w), c_int(Cs),
+                                                  c_int(Cb), self._st()))
+            return
         self._ck(self.lib.b200rl_conv_down(_p(big), _p(W), _p(small), c_int(NB), c_int(h), c_int(w), c_int(Cs),
                                            c_int(Cb), self._st()))
+
+    def _packed(self, W, mode_up: int, Cs: int, Cb: int):
+        """Tap-major copy of a conv weight for the tensor-core kernels (caller-owned workspace, refreshed on every
+        use because the optimiser rewrites W each step; 16*Cs*Cb floats, a few microseconds)."""
+        key = (W.data_ptr(), mode_up)
+        buf = self._pack_bufs.get(key)
+        if buf is None or buf.numel() != W.numel():
+            buf = torch.empty(W.numel(), dtype=torch.float32, device=W.device)
+            self._pack_bufs[key] = buf
+        self._ck(self.lib.b200rl_conv_pack(_p(W), _p(buf), c_int(mode_up), c_int(Cs), c_int(Cb), self._st()))
+        return buf
 
     def conv_up(self, small, W, big, bias=None):
         _f32(big, W, small, bias)
@@ -167,6 +222,11 @@ class CudaOps:
         NB, h, w, Cs = small.shape
         Cb = big.shape[-1]
         assert tuple(big.shape) == (NB, 2 * h, 2 * w, Cb) and tuple(W.shape) == (Cs, Cb, 4, 4)
+        if self.use_tc and self.lib.b200rl_conv_tc_supported(1, NB, h, w, Cs, Cb):
+            Wp = self._packed(W, 1, Cs, Cb)
+            self._ck(self.lib.b200rl_conv_up_tc(_p(small), _p(Wp), _p(big), _p(bias), c_int(NB), c_int(h), c_int(w),
+                                                c_int(Cs), c_int(Cb), self._st()))
+            return
         self._ck(self.lib.b200rl_conv_up(_p(small), _p(W), _p(big), _p(bias), c_int(NB), c_int(h), c_int(w), c_int(Cs),
                                          c_int(Cb), self._st()))
 
@@ -176,6 +236,13 @@ class CudaOps:
         NB, h, w, Cs = small.shape
         Cb = big.shape[-1]
         assert tuple(big.shape) == (NB, 2 * h, 2 * w, Cb) and tuple(dW.shape) == (Cs, Cb, 4, 4)
+        if self.use_tc and NB * h * w >= 4096 and Cs >= 48 and Cb >= 8:
+            self.lib.b200rl_conv_wgrad_tc_workspace.restype = c_ll
+            n = int(self.lib.b200rl_conv_wgrad_tc_workspace(c_int(NB), c_int(h), c_int(w), c_int(Cs), c_int(Cb)))
+            ws = self._scratch("wgrad", n)
+            self._ck(self.lib.b200rl_conv_wgrad_tc(_p(small), _p(big), _p(dW), _p(ws), c_int(NB), c_int(h), c_int(w),
+                                                   c_int(Cs), c_int(Cb), c_int(int(accumulate)), self._st()))
+            return
         self._ck(self.lib.b200rl_conv_wgrad(_p(small), _p(big), _p(dW), c_int(NB), c_int(h), c_int(w), c_int(Cs),
                                             c_int(Cb), c_int(int(accumulate)), self._st()))
 
