@@ -147,6 +147,173 @@ __global__ void col_sum_kernel(const float* __restrict__ X, float* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Vectorised row kernels: a row of C = 4*LPR*NV floats is held in registers by LPR lanes (NV float4 each), so X
+// (and dY) are read exactly once with 128-bit accesses, 32/LPR rows are processed per warp at a time and the
+// statistics are sub-warp shuffles.  These are the HBM-bound kernels of the conv stacks (C = 32..256, 1M rows).
+// ---------------------------------------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256)
+ln_act_fwd_vec_kernel(const float* __restrict__ X, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float* __restrict__ Y, long long M, long long ldx, long long ldy, float eps, int act) {
+  constexpr int RPW = 32 / LPR, C = 4 * LPR * NV;
+  const int lane = threadIdx.x & 31, lr = lane % LPR, sub = lane / LPR;
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float4 g[NV], b[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i] = reinterpret_cast<const float4*>(gamma)[lr + i * LPR];
+    b[i] = reinterpret_cast<const float4*>(beta)[lr + i * LPR];
+  }
+  const float invC = 1.f / (float)C;
+  for (long long r0 = gwarp * RPW; r0 < M; r0 += nwarps * RPW) {
+    const long long r = r0 + sub;
+    const bool ok = r < M;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      v[i] = ok ? reinterpret_cast<const float4*>(X + r * ldx)[lr + i * LPR] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mu = group_sum<LPR>(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(group_sum<LPR>(q) * invC + eps);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 o;
+        o.x = (v[i].x - mu) * rstd * g[i].x + b[i].x;
+        o.y = (v[i].y - mu) * rstd * g[i].y + b[i].y;
+        o.z = (v[i].z - mu) * rstd * g[i].z + b[i].z;
+        o.w = (v[i].w - mu) * rstd * g[i].w + b[i].w;
+        if (act == ACT_SILU) { o.x = siluf_(o.x); o.y = siluf_(o.y); o.z = siluf_(o.z); o.w = siluf_(o.w); }
+        reinterpret_cast<float4*>(Y + r * ldy)[lr + i * LPR] = o;
+      }
+    }
+  }
+}
+
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256)
+ln_act_bwd_vec_kernel(const float* __restrict__ X, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* dY, float* dX, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M,
+                      long long ldx, long long lddy, long long lddx, float eps, int act) {
+  constexpr int RPW = 32 / LPR, C = 4 * LPR * NV;
+  __shared__ float sacc[2 * C];
+  const int lane = threadIdx.x & 31, lr = lane % LPR, sub = lane / LPR;
+  const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool want_param = dgamma != nullptr;
+  if (want_param) {
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sacc[c] = 0.f;
+    __syncthreads();
+  }
+  float4 g[NV], b[NV], ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i] = reinterpret_cast<const float4*>(gamma)[lr + i * LPR];
+    b[i] = reinterpret_cast<const float4*>(beta)[lr + i * LPR];
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invC = 1.f / (float)C;
+  auto dact = [&](float ln, float dy) -> float {
+    if (act != ACT_SILU) return dy;
+    const float sg = sigmoidf_(ln);
+    return dy * sg * (1.f + ln * (1.f - sg));
+  };
+  for (long long r0 = gwarp * RPW; r0 < M; r0 += nwarps * RPW) {
+    const long long r = r0 + sub;
+    const bool ok = r < M;
+    float4 v[NV], d[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = ok ? reinterpret_cast<const float4*>(X + r * ldx)[lr + i * LPR] : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[i] = ok ? reinterpret_cast<const float4*>(dY + r * lddy)[lr + i * LPR] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mu = group_sum<LPR>(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(group_sum<LPR>(q) * invC + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      // v <- xh, d <- dxh ; accumulate parameter gradients
+      float4 xh, dl;
+      xh.x = (v[i].x - mu) * rstd; xh.y = (v[i].y - mu) * rstd; xh.z = (v[i].z - mu) * rstd; xh.w = (v[i].w - mu) * rstd;
+      dl.x = dact(xh.x * g[i].x + b[i].x, d[i].x); dl.y = dact(xh.y * g[i].y + b[i].y, d[i].y);
+      dl.z = dact(xh.z * g[i].z + b[i].z, d[i].z); dl.w = dact(xh.w * g[i].w + b[i].w, d[i].w);
+      ag[i].x += dl.x * xh.x; ag[i].y += dl.y * xh.y; ag[i].z += dl.z * xh.z; ag[i].w += dl.w * xh.w;
+      ab[i].x += dl.x; ab[i].y += dl.y; ab[i].z += dl.z; ab[i].w += dl.w;
+      d[i].x = dl.x * g[i].x; d[i].y = dl.y * g[i].y; d[i].z = dl.z * g[i].z; d[i].w = dl.w * g[i].w;
+      v[i] = xh;
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * xh.x + d[i].y * xh.y) + (d[i].z * xh.z + d[i].w * xh.w);
+    }
+    s1 = group_sum<LPR>(s1) * invC;
+    s2 = group_sum<LPR>(s2) * invC;
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 o;
+        o.x = rstd * (d[i].x - s1 - v[i].x * s2); o.y = rstd * (d[i].y - s1 - v[i].y * s2);
+        o.z = rstd * (d[i].z - s1 - v[i].z * s2); o.w = rstd * (d[i].w - s1 - v[i].w * s2);
+        reinterpret_cast<float4*>(dX + r * lddx)[lr + i * LPR] = o;
+      }
+    }
+  }
+  if (want_param) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * (lr + i * LPR);
+      atomicAdd(&sacc[c + 0], ag[i].x); atomicAdd(&sacc[c + 1], ag[i].y); atomicAdd(&sacc[c + 2], ag[i].z); atomicAdd(&sacc[c + 3], ag[i].w);
+      atomicAdd(&sacc[C + c + 0], ab[i].x); atomicAdd(&sacc[C + c + 1], ab[i].y); atomicAdd(&sacc[C + c + 2], ab[i].z); atomicAdd(&sacc[C + c + 3], ab[i].w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      atomicAdd(&dgamma[c], sacc[c]);
+      atomicAdd(&dbeta[c], sacc[C + c]);
+    }
+  }
+}
+
+int vec_grid(long long M, int rows_per_warp) {
+  long long warps = (M + rows_per_warp - 1) / rows_per_warp;
+  long long blocks = (warps + 7) / 8;
+  const long long cap = (long long)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+bool vec_ok(int C, long long ld0, long long ld1, long long ld2, const void* p0, const void* p1, const void* p2, const void* g,
+            const void* b) {
+  if (C != 32 && C != 64 && C != 128 && C != 256 && C != 512 && C != 1024 && C != 1536) return false;
+  if ((ld0 | ld1 | ld2) & 3) return false;
+  return ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) |
+           reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
 int grid_for_rows(long long M) {
   long long blocks = (M + 7) / 8;  // 8 warps (rows) per 256-thread block
   const long long cap = (long long)kNumSMs * 8;
@@ -162,6 +329,22 @@ extern "C" int b200rl_ln_act_fwd(const float* X, const float* gamma, const float
   RL_CHECK_ARG(X && gamma && beta && Y, "null pointer");
   RL_CHECK_ARG(C > 0 && ldx >= C && ldy >= C, "bad C / ld");
   if (M <= 0) return B200RL_OK;
+  if (vec_ok(C, ldx, ldy, 0, X, Y, nullptr, gamma, beta)) {
+#define LN_FWD_VEC(LPR_, NV_) \
+  ln_act_fwd_vec_kernel<LPR_, NV_><<<vec_grid(M, 32 / LPR_), 256, 0, st>>>(X, gamma, beta, Y, M, ldx, ldy, eps, act)
+    switch (C) {
+      case 32: LN_FWD_VEC(8, 1); break;
+      case 64: LN_FWD_VEC(16, 1); break;
+      case 128: LN_FWD_VEC(32, 1); break;
+      case 256: LN_FWD_VEC(32, 2); break;
+      case 512: LN_FWD_VEC(32, 4); break;
+      case 1024: LN_FWD_VEC(32, 8); break;
+      default: LN_FWD_VEC(32, 12); break;
+    }
+#undef LN_FWD_VEC
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
   ln_act_fwd_kernel<<<grid_for_rows(M), 256, 0, st>>>(X, gamma, beta, Y, M, C, ldx, ldy, eps, act);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
@@ -178,6 +361,23 @@ extern "C" int b200rl_ln_act_bwd(const float* X, const float* gamma, const float
     RL_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st));
   }
   if (M <= 0) return B200RL_OK;
+  if (vec_ok(C, ldx, lddy, lddx, X, dY, dX, gamma, beta)) {
+#define LN_BWD_VEC(LPR_, NV_)                                                                                      \
+  ln_act_bwd_vec_kernel<LPR_, NV_><<<vec_grid(M, 32 / LPR_), 256, 0, st>>>(X, gamma, beta, dY, dX, dgamma, dbeta, M, \
+                                                                         ldx, lddy, lddx, eps, act)
+    switch (C) {
+      case 32: LN_BWD_VEC(8, 1); break;
+      case 64: LN_BWD_VEC(16, 1); break;
+      case 128: LN_BWD_VEC(32, 1); break;
+      case 256: LN_BWD_VEC(32, 2); break;
+      case 512: LN_BWD_VEC(32, 4); break;
+      case 1024: LN_BWD_VEC(32, 8); break;
+      default: LN_BWD_VEC(32, 12); break;
+    }
+#undef LN_BWD_VEC
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
   int grid = grid_for_rows(M);
   if (dgamma && grid > 2 * kNumSMs) grid = 2 * kNumSMs;  // fewer, longer-lived warps -> fewer flush atomics
 #define LN_BWD(CPL_, SMEM_)                                                                                    \
