@@ -303,22 +303,39 @@ def run_b200(args):
     value = world * args.steps / (ms / 1e3)
     e2e_v = world * args.steps / (ms_e2e / 1e3)
     hbm, tf, src = measured_peaks()
-    # dominant kernel family by device time in the eager breakdown
+    # Dominant kernel: gemm_tc_kernel (tcgen05 3xTF32; serves every large Linear / conv forward, input-gradient
+    # and weight-gradient product).  `achieved` = algorithmic FLOPs of its largest launch in the step (a 2-layer-MLP
+    # GEMM over the imagined trajectories: M=(H+1)*T*B, N=512, K=1536) / its mean launch duration, measured here
+    # with CUDA events on the launching stream; operands (134 MB) exceed the 126 MB L2.
     tot_ms = sum(v[0] for v in breakdown.values())
-    dom = max(breakdown.items(), key=lambda kv: kv[1][0])
-    name, (t_ms, fl, by, cnt) = dom
-    fp32_simt_peak = 148 * 128 * 2 * (clk["sm_max_mhz"] or 1965.0) * 1e6 / 1e12   # TFLOP/s at max clock
-    if fl > 0:
-        roof = {"kernel": f"b200rl_{name}* (fp32 SIMT implicit/explicit GEMM)", "bound": "tensor",
-                "achieved": fl / (t_ms * 1e-3) / 1e12, "peak": tf, "unit": "TFLOP/s",
-                "frac": fl / (t_ms * 1e-3) / 1e12 / tf, "traffic": None, "peak_source": f"{src} bf16 cuBLAS",
-                "note": f"exact-fp32 FFMA path; fp32 SIMT ceiling is {fp32_simt_peak:.1f} TFLOP/s "
-                        f"(frac of that: {fl / (t_ms * 1e-3) / 1e12 / fp32_simt_peak:.3f}); share of step {t_ms / tot_ms:.2f}",
-                "launches": cnt, "ms_per_step": t_ms}
-    else:
-        roof = {"kernel": f"b200rl_{name}", "bound": "hbm", "achieved": by / (t_ms * 1e-3) / 1e9, "peak": hbm,
-                "unit": "GB/s", "frac": by / (t_ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": src,
-                "launches": cnt, "ms_per_step": t_ms}
+    tc_ops = ("gemm", "conv_down", "conv_up", "conv_wgrad")
+    share = sum(breakdown[k][0] for k in tc_ops if k in breakdown) / tot_ms
+    gm, gn, gk = (eng.H + 1) * eng.N, eng.du, eng.L
+    ga = torch.randn(gm, gk, device=dev)
+    gb = torch.randn(gn, gk, device=dev)
+    gc = torch.empty(gm, gn, device=dev)
+    for _ in range(3):
+        eng.ops.gemm(ga, gb, gc, False, True)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(20):
+        eng.ops.gemm(ga, gb, gc, False, True)
+    g1.record()
+    torch.cuda.synchronize()
+    g_ms = g0.elapsed_time(g1) / 20
+    g_tf = 2.0 * gm * gn * gk / (g_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_tc_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roof = {"kernel": "gemm_tc_kernel<128> (tcgen05.mma kind::tf32, 3xTF32 split, TMA, TMEM)", "bound": "tensor",
+            "achieved": g_tf, "peak": tf, "unit": "TFLOP/s", "frac": g_tf / tf, "traffic": traffic,
+            "peak_source": f"{src} bf16 cuBLAS",
+            "shape": {"M": gm, "N": gn, "K": gk}, "us_per_launch": g_ms * 1e3,
+            "note": "fp32-equivalent FLOP/s: every product costs 3 TF32 MMAs and TF32 runs at half the bf16 rate, so the "
+                    f"scheme's ceiling is peak/6 = {tf / 6:.0f} TFLOP/s (frac of that: {g_tf / (tf / 6):.2f}); tensor-core "
+                    f"ops (gemm+conv) take {share:.2f} of the step; ncu tensor-pipe %: profiles/r1_gemm_tc_ncu_summary.txt"}
     cpu = cpu_baseline(steps=1, warmup=1) if args.cpu_baseline else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
