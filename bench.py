@@ -229,16 +229,15 @@ def run_b200(args):
         step_public(static)
     barrier()
 
-    # ---- per-op breakdown of ONE eager step (roofline evidence), rank 0 only
-    breakdown = None
-    if rank == 0:
-        prof = ProfilingOps(eng.ops)
-        eng.ops = prof
-        for m in (eng.reward_wm, eng.cont_wm, eng.actor_mlp, eng.critic_mlp, eng.target_mlp, eng.rew_img, eng.cont_img):
-            m.eng = eng
-        step_public(static)
-        breakdown = prof.summary()
-        eng.ops = prof._inner
+    # ---- per-op breakdown of ONE eager step (roofline evidence).  Every rank runs it: the step contains the
+    # data-parallel collectives, so a rank-0-only step would leave the other ranks' NCCL queues one step short.
+    prof = ProfilingOps(eng.ops)
+    eng.ops = prof
+    for m in (eng.reward_wm, eng.cont_wm, eng.actor_mlp, eng.critic_mlp, eng.target_mlp, eng.rew_img, eng.cont_img):
+        m.eng = eng
+    step_public(static)
+    breakdown = prof.summary()
+    eng.ops = prof._inner
     barrier()
 
     # ---- CUDA graph of the whole update (single GPU; multi-GPU keeps eager launches around NCCL)
@@ -336,7 +335,7 @@ def run_b200(args):
             "note": "fp32-equivalent FLOP/s: every product costs 3 TF32 MMAs and TF32 runs at half the bf16 rate, so the "
                     f"scheme's ceiling is peak/6 = {tf / 6:.0f} TFLOP/s (frac of that: {g_tf / (tf / 6):.2f}); tensor-core "
                     f"ops (gemm+conv) take {share:.2f} of the step; ncu tensor-pipe %: profiles/r1_gemm_tc_ncu_summary.txt"}
-    cpu = cpu_baseline(steps=1, warmup=1) if args.cpu_baseline else None
+    cpu = cpu_baseline(steps=1, warmup=1) if (args.cpu_baseline and world == 1) else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -440,7 +439,13 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_b200(args)
+        try:
+            run_b200(args)
+        finally:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":
