@@ -380,3 +380,11 @@ class EmulOps:
     def tanh_bwd(self, y: Tensor, dy: Tensor, dx: Tensor, accumulate: bool = False):
         r = dy * (1 - y * y)
         dx.add_(r) if accumulate else dx.copy_(r)
+
+    # ---- replay storage (csrc/replay.cu)
+    def replay_gather(self, storage: Tensor, idx: Tensor, out: Tensor, n_samples: int, batch: int, seq_len: int):
+        rows = storage[idx.long()].reshape(n_samples, batch, seq_len, *storage.shape[1:])
+        out.view(n_samples, seq_len, batch, *storage.shape[1:]).copy_(rows.transpose(1, 2))
+
+    def replay_scatter(self, src: Tensor, dst_rows: Tensor, storage: Tensor):
+        storage[dst_rows.long()] = src
