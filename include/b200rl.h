@@ -190,6 +190,42 @@ int b200rl_replay_scatter(const void* src, const long long* dst_rows, void* stor
 int b200rl_gae(const float* rewards, const float* values, const float* dones, const float* next_value, float* returns,
                float* advantages, int T, int E, float gamma, float lmbda, cudaStream_t stream);
 
+/* ---- SAC / PPO dense layers and SAC element-wise stages ---------------------------------------------------
+ * b200rl_bgemm: `nets` independent products C[n] = epi(A[n] * B[n] + bias[n]) in one launch; A(m,k) = A[m*sam+k*sak],
+ * B(k,n) = B[k*sbk+n*sbn] (covers NN/NT/TN), C row-major with ldc.  epilogue: 0 none, 1 ReLU, 2 Tanh, 3 multiply by
+ * ReLU'(aux), 4 multiply by Tanh'(aux) = 1-aux^2 (aux = the layer's saved activation output).  rsum (optional):
+ * rsum[m] = sum_k A(m,k), i.e. the bias gradient when A = dY^T.  Replaces nn.Linear + activation forward/backward
+ * of models/models.py:16-119 as used by sac/agent.py:19-108 and ppo/agent.py:84-177. */
+int b200rl_bgemm(const float* A, long long sam, long long sak, long long strideA, const float* B, long long sbk,
+                 long long sbn, long long strideB, float* C, long long ldc, long long strideC, const float* bias,
+                 long long strideBias, const float* aux, long long ldaux, long long strideAux, float* rsum,
+                 long long strideRsum, int M, int N, int K, int nets, int epilogue, int accumulate, cudaStream_t stream);
+/* SACActor._get_actions_and_log_probs sac/agent.py:110-142: head = [mean | log_std] (B x 2A), eps ~ N(0,1);
+ * writes the rescaled tanh action into `action` (row stride ld_action: straight into the critics' input buffer),
+ * logp[B], and tanh(x_t) for the backward. */
+int b200rl_sac_sample_fwd(const float* head, const float* eps, const float* scale, const float* abias, float* action,
+                          long long ld_action, float* logp, float* tanh_out, int B, int A, cudaStream_t stream);
+/* autograd of the above for the policy loss (loss.py:9-11): d(action) = sum over `nets` critics' input gradients,
+ * d(logp) = exp(log_alpha)/B. */
+int b200rl_sac_sample_bwd(const float* head, const float* eps, const float* tanh_y, const float* scale,
+                          const float* dact, long long stride_net, int nets, const float* log_alpha, float* dhead, int B,
+                          int A, cudaStream_t stream);
+/* SACAgent.get_next_target_q_values sac/agent.py:254-262 (alpha read from the device log_alpha) */
+int b200rl_sac_target(const float* q_target, long long stride_net, int nets, const float* logp, const float* rewards,
+                      const float* terminated, const float* log_alpha, float gamma, float* y, int B, cudaStream_t stream);
+/* critic_loss sac/loss.py:14-20 + its gradient w.r.t. q */
+int b200rl_sac_critic_loss(const float* q, long long stride_net, int nets, const float* y, float* dq, float* loss_out,
+                           int B, cudaStream_t stream);
+/* policy_loss + entropy_loss sac/loss.py:9-11,23-26 with torch.min over critics (sac.py:62-63): gradients w.r.t. q
+ * and log_alpha */
+int b200rl_sac_actor_loss(const float* q, long long stride_net, int nets, const float* logp, const float* log_alpha,
+                          float target_entropy, float* dq, float* actor_loss, float* alpha_loss, float* dlog_alpha, int B,
+                          cudaStream_t stream);
+/* N(0,1) noise (Philox4x32-10 + Box-Muller), same counter scheme as b200rl_fill_exponential; replaces
+ * Normal.rsample's torch.normal draw (sac/agent.py:126) */
+int b200rl_fill_normal(float* out, long long n, unsigned long long seed, unsigned int stream_id, const int* counter_dev,
+                       cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

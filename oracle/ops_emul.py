@@ -388,3 +388,70 @@ class EmulOps:
 
     def replay_scatter(self, src: Tensor, dst_rows: Tensor, storage: Tensor):
         storage[dst_rows.long()] = src
+
+    # ---- SAC / PPO dense layers (csrc/mlp.cu)
+    def bgemm(self, A: Tensor, B: Tensor, C: Tensor, bias=None, aux=None, rsum=None, epi: str = "none",
+              accumulate: bool = False):
+        v = torch.matmul(A, B)
+        if bias is not None:
+            v = v + bias.unsqueeze(1)
+        if epi == "relu":
+            v = torch.relu(v)
+        elif epi == "tanh":
+            v = torch.tanh(v)
+        elif epi == "drelu":
+            v = v * (aux > 0)
+        elif epi == "dtanh":
+            v = v * (1 - aux * aux)
+        C.add_(v) if accumulate else C.copy_(v)
+        if rsum is not None:
+            r = A.sum(-1).expand(C.shape[0], -1)
+            rsum.add_(r) if accumulate else rsum.copy_(r)
+
+    # ---- SAC element-wise stages (csrc/sac.cu)
+    def sac_sample_fwd(self, head, eps, scale, abias, action, logp, tanh_out=None):
+        A = eps.shape[1]
+        mean, ls = head[:, :A], head[:, A:].clamp(-5.0, 2.0)
+        std = ls.exp()
+        xt = mean + std * eps
+        y = torch.tanh(xt)
+        action.copy_(y * scale + abias)
+        lp = -((xt - mean) ** 2) / (2 * std * std) - std.log() - math.log(math.sqrt(2 * math.pi))
+        lp = lp - torch.log(scale * (1 - y * y) + 1e-6)
+        logp.copy_(lp.sum(-1))
+        if tanh_out is not None:
+            tanh_out.copy_(y)
+
+    def sac_sample_bwd(self, head, eps, tanh_y, scale, dact, log_alpha, dhead):
+        B, A = eps.shape
+        raw = head[:, A:]
+        std = raw.clamp(-5.0, 2.0).exp()
+        dlogp = log_alpha.exp() / B
+        om = 1 - tanh_y * tanh_y
+        dxt = dact.sum(0) * scale * om + dlogp * (2 * scale * tanh_y * om) / (scale * om + 1e-6)
+        dstd = dxt * eps - dlogp / std
+        dhead[:, :A] = dxt
+        dhead[:, A:] = torch.where((raw >= -5.0) & (raw <= 2.0), dstd * std, torch.zeros_like(std))
+
+    def sac_target(self, q_target, logp, rewards, terminated, log_alpha, gamma, y):
+        y.copy_(rewards + (1 - terminated) * gamma * (q_target.min(0)[0] - log_alpha.exp() * logp))
+
+    def sac_critic_loss(self, q, y, dq, loss_out):
+        d = q - y.unsqueeze(0)
+        loss_out.copy_((d * d).mean(1).sum().reshape(1))
+        dq.copy_(2 * d / q.shape[1])
+
+    def sac_actor_loss(self, q, logp, log_alpha, target_entropy, dq, actor_loss, alpha_loss, dlog_alpha):
+        B = q.shape[1]
+        m, arg = q.min(0)
+        dq.zero_()
+        dq.scatter_(0, arg.unsqueeze(0), -1.0 / B)
+        actor_loss.copy_((log_alpha.exp() * logp - m).mean().reshape(1))
+        s = (logp + target_entropy).mean()
+        alpha_loss.copy_((-log_alpha * s).reshape(1))
+        dlog_alpha.copy_((-s).reshape(1))
+
+    def fill_normal(self, out: Tensor, seed: int, stream_id: int, counter: Optional[Tensor] = None):
+        c = int(counter.item()) if counter is not None else 0
+        g = torch.Generator().manual_seed(seed * 1000003 + stream_id * 7919 + c)
+        out.normal_(generator=g)

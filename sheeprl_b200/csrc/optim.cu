@@ -103,6 +103,34 @@ __global__ void fill_exponential_kernel(float* __restrict__ out, long long n, ui
   }
 }
 
+__global__ void fill_normal_kernel(float* __restrict__ out, long long n, uint32_t seed_lo, uint32_t seed_hi,
+                                   uint32_t stream, const int* __restrict__ counter) {
+  const uint32_t ctr = counter ? (uint32_t)(*counter) : 0u;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = (n + 3) >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), stream, ctr};
+    uint32_t k0 = seed_lo, k1 = seed_hi;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {                                         // Box-Muller on two uniforms
+      const float u1 = ((float)(c[j] >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+      const float u2 = (float)(c[j + 1] >> 8) * (1.0f / 16777216.0f);        // [0, 1)
+      const float r = sqrtf(-2.f * logf(u1));
+      float sn, cs;
+      sincospif(2.f * u2, &sn, &cs);
+      const long long idx = i * 4 + j;
+      if (idx < n) out[idx] = r * cs;
+      if (idx + 1 < n) out[idx + 1] = r * sn;
+    }
+  }
+}
+
 __global__ void copy2d_kernel(const float* __restrict__ src, float* __restrict__ dst, long long M, int C,
                               long long lds, long long ldd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,6 +204,16 @@ extern "C" int b200rl_fill_exponential(float* out, long long n, unsigned long lo
   if (n <= 0) return B200RL_OK;
   fill_exponential_kernel<<<stream_grid((n + 3) / 4), 256, 0, st>>>(out, n, (uint32_t)seed, (uint32_t)(seed >> 32),
                                                                    stream_id, counter_dev);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_fill_normal(float* out, long long n, unsigned long long seed, unsigned int stream_id,
+                                  const int* counter_dev, cudaStream_t st) {
+  RL_CHECK_ARG(out, "null pointer");
+  if (n <= 0) return B200RL_OK;
+  fill_normal_kernel<<<stream_grid((n + 3) / 4), 256, 0, st>>>(out, n, (uint32_t)seed, (uint32_t)(seed >> 32), stream_id,
+                                                              counter_dev);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }

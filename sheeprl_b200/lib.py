@@ -476,3 +476,76 @@ class CudaOps:
         T, E = rewards.shape[0], rewards[0].numel()
         self._ck(self.lib.b200rl_gae(_p(rewards), _p(values), _p(dones), _p(next_value), _p(returns), _p(advantages),
                                      c_int(T), c_int(E), c_float(gamma), c_float(lmbda), self._st()))
+
+    # ------------------------------------------------------------------ SAC / PPO dense layers (csrc/mlp.cu)
+    EPI = {"none": 0, "relu": 1, "tanh": 2, "drelu": 3, "dtanh": 4}
+
+    def bgemm(self, A, B, C, bias=None, aux=None, rsum=None, epi: str = "none", accumulate: bool = False):
+        """C[n] = epi(A[n] @ B[n] + bias[n]) for 3-D *views* A [n|1, M, K], B [n|1, K, N] (any strides: pass
+        `.transpose(-1, -2)` views for the NT / TN products), C [n, M, N] (unit inner stride).  A leading dim of
+        1 broadcasts the operand over the `n` networks.  rsum [n, M] (optional) receives the row sums of A."""
+        _f32(A, B, C, bias, aux, rsum)
+        nets, M, N = C.shape
+        K = A.shape[2]
+        assert A.shape[1:] == (M, K) and B.shape[1:] == (K, N) and C.stride(2) == 1, (A.shape, B.shape, C.shape)
+
+        def ns(t):  # stride between networks (0 = shared)
+            return 0 if t.shape[0] == 1 else t.stride(0)
+
+        if aux is not None:
+            assert aux.shape == C.shape and aux.stride(2) == 1
+        if bias is not None:
+            assert bias.shape[1] == N and (N == 1 or bias.stride(1) == 1)
+        if rsum is not None:
+            assert rsum.shape == (nets, M) and (M == 1 or rsum.stride(1) == 1)
+        self._ck(self.lib.b200rl_bgemm(
+            _p(A), c_ll(A.stride(1)), c_ll(A.stride(2)), c_ll(ns(A)), _p(B), c_ll(B.stride(1)), c_ll(B.stride(2)),
+            c_ll(ns(B)), _p(C), c_ll(C.stride(1)), c_ll(ns(C)), _p(bias), c_ll(0 if bias is None else ns(bias)),
+            _p(aux), c_ll(0 if aux is None else aux.stride(1)), c_ll(0 if aux is None else ns(aux)), _p(rsum),
+            c_ll(0 if rsum is None else ns(rsum)), c_int(M), c_int(N), c_int(K), c_int(nets), c_int(self.EPI[epi]),
+            c_int(int(accumulate)), self._st()))
+
+    # ------------------------------------------------------------------ SAC element-wise stages (csrc/sac.cu)
+    def sac_sample_fwd(self, head, eps, scale, abias, action, logp, tanh_out=None):
+        """action: a [B, A] view (unit inner stride, any row stride) — e.g. the action columns of the critics' input."""
+        _f32(head, eps, scale, abias, action, logp, tanh_out)
+        B, A = eps.shape
+        assert head.shape == (B, 2 * A) and head.is_contiguous() and eps.is_contiguous() and action.stride(1) == 1
+        self._ck(self.lib.b200rl_sac_sample_fwd(_p(head), _p(eps), _p(scale), _p(abias), _p(action),
+                                                c_ll(action.stride(0)), _p(logp), _p(tanh_out), c_int(B), c_int(A),
+                                                self._st()))
+
+    def sac_sample_bwd(self, head, eps, tanh_y, scale, dact, log_alpha, dhead):
+        """dact: [nets, B, A] contiguous input gradients of the critics' action columns."""
+        _f32(head, eps, tanh_y, scale, dact, log_alpha, dhead)
+        nets, B, A = dact.shape
+        assert dact.is_contiguous() and dhead.is_contiguous() and head.is_contiguous()
+        self._ck(self.lib.b200rl_sac_sample_bwd(_p(head), _p(eps), _p(tanh_y), _p(scale), _p(dact), c_ll(B * A),
+                                                c_int(nets), _p(log_alpha), _p(dhead), c_int(B), c_int(A), self._st()))
+
+    def sac_target(self, q_target, logp, rewards, terminated, log_alpha, gamma: float, y):
+        _f32(q_target, logp, rewards, terminated, log_alpha, y)
+        nets, B = q_target.shape
+        assert q_target.is_contiguous()
+        self._ck(self.lib.b200rl_sac_target(_p(q_target), c_ll(B), c_int(nets), _p(logp), _p(rewards), _p(terminated),
+                                            _p(log_alpha), c_float(gamma), _p(y), c_int(B), self._st()))
+
+    def sac_critic_loss(self, q, y, dq, loss_out):
+        _f32(q, y, dq, loss_out)
+        nets, B = q.shape
+        assert q.is_contiguous() and dq.is_contiguous()
+        self._ck(self.lib.b200rl_sac_critic_loss(_p(q), c_ll(B), c_int(nets), _p(y), _p(dq), _p(loss_out), c_int(B),
+                                                 self._st()))
+
+    def sac_actor_loss(self, q, logp, log_alpha, target_entropy: float, dq, actor_loss, alpha_loss, dlog_alpha):
+        _f32(q, logp, log_alpha, dq, actor_loss, alpha_loss, dlog_alpha)
+        nets, B = q.shape
+        assert q.is_contiguous() and dq.is_contiguous()
+        self._ck(self.lib.b200rl_sac_actor_loss(_p(q), c_ll(B), c_int(nets), _p(logp), _p(log_alpha),
+                                                c_float(target_entropy), _p(dq), _p(actor_loss), _p(alpha_loss),
+                                                _p(dlog_alpha), c_int(B), self._st()))
+
+    def fill_normal(self, out, seed: int, stream_id: int, counter=None):
+        _f32(out)
+        self._ck(self.lib.b200rl_fill_normal(_p(out), c_ll(out.numel()), ctypes.c_ulonglong(seed),
+                                             ctypes.c_uint(stream_id), _p(counter), self._st()))

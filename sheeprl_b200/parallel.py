@@ -42,7 +42,9 @@ def attach_data_parallel(engine, group=None) -> None:
         engine.allgather = None
         return
     use_avg = dist.get_backend(group) == "nccl"
-    gather_buf = torch.empty(world * engine.lam.numel(), dtype=torch.float32, device=engine.device)
+    # Dreamer-V3 gathers its lambda-values for Moments (dreamer_v3/utils.py:58); SAC / PPO engines have no gather
+    gather_buf = (torch.empty(world * engine.lam.numel(), dtype=torch.float32, device=engine.device)
+                  if hasattr(engine, "lam") else None)
 
     def allreduce(flat_grad: torch.Tensor, name: str):
         if use_avg:
