@@ -226,6 +226,22 @@ int b200rl_sac_actor_loss(const float* q, long long stride_net, int nets, const 
 int b200rl_fill_normal(float* out, long long n, unsigned long long seed, unsigned int stream_id, const int* counter_dev,
                        cudaStream_t stream);
 
+/* ---- PPO --------------------------------------------------------------------------------------------------
+ * Channel-last patch gather / scatter for NatureCNN's unpadded convolutions (models/models.py:288-328):
+ * col[(b,oy,ox),(ky,kx,c)] = x[b,oy*s+ky,ox*s+kx,c]; col2im is its transpose (sum over overlapping patches), optionally
+ * masked by ReLU'(act) of the activation that fed the convolution. */
+int b200rl_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, cudaStream_t stream);
+int b200rl_col2im(const float* dcol, const float* act, float* dx, int B, int H, int W, int C, int k, int stride,
+                  cudaStream_t stream);
+/* PPO objective on one minibatch: log-prob + entropy of the taken actions from the actor head (OneHotCategorical per
+ * head / Independent Normal, ppo/agent.py:179-239), optional advantage normalisation (utils/utils.py:121-130),
+ * policy / value / entropy losses (ppo/loss.py:6-75, reduction mean) and the gradients of
+ * policy + vf_coef*value + ent_coef*entropy w.r.t. the head outputs and the values.  losses[3]. */
+int b200rl_ppo_loss(const float* head, const float* actions, const float* old_logp, const float* adv,
+                    const float* values, const float* old_values, const float* returns, float* dhead, float* dvalues,
+                    float* losses, int B, const int* head_dims, int n_heads, int is_continuous, int clip_vloss,
+                    int normalize_adv, float clip_coef, float vf_coef, float ent_coef, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

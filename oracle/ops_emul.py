@@ -455,3 +455,48 @@ class EmulOps:
         c = int(counter.item()) if counter is not None else 0
         g = torch.Generator().manual_seed(seed * 1000003 + stream_id * 7919 + c)
         out.normal_(generator=g)
+
+    # ---- PPO (csrc/ppo.cu)
+    def im2col(self, x: Tensor, col: Tensor, k: int, stride: int):
+        B, H, W, C = x.shape
+        p = x.unfold(1, k, stride).unfold(2, k, stride)          # [B, Ho, Wo, C, ky, kx]
+        col.copy_(p.permute(0, 1, 2, 4, 5, 3).reshape(col.shape))
+
+    def col2im(self, dcol: Tensor, act, dx: Tensor, k: int, stride: int):
+        B, H, W, C = dx.shape
+        Ho, Wo = (H - k) // stride + 1, (W - k) // stride + 1
+        d = dcol.reshape(B, Ho * Wo, k, k, C).permute(0, 4, 2, 3, 1).reshape(B, C * k * k, Ho * Wo)
+        out = F.fold(d, (H, W), kernel_size=k, stride=stride).permute(0, 2, 3, 1)
+        dx.copy_(out * (act > 0) if act is not None else out)
+
+    def ppo_loss(self, head, actions, old_logp, adv, values, old_values, returns, dhead, dvalues, losses, head_dims,
+                 is_continuous, clip_vloss, normalize_adv, clip_coef, vf_coef, ent_coef):
+        h = head.detach().clone().requires_grad_(True)
+        v = values.detach().clone().requires_grad_(True)
+        if is_continuous:
+            mean, ls = h.chunk(2, -1)
+            sd = ls.exp()
+            lp = (-((actions - mean) ** 2) / (2 * sd * sd) - ls - math.log(math.sqrt(2 * math.pi))).sum(-1)
+            ent = (0.5 + 0.5 * math.log(2 * math.pi) + ls).sum(-1)
+        else:
+            lp, ent, off = 0.0, 0.0, 0
+            for n in head_dims:
+                logp = torch.log_softmax(h[:, off:off + n], -1)
+                lp = lp + (logp * actions[:, off:off + n]).sum(-1)
+                ent = ent - (logp.exp() * logp).sum(-1)
+                off += n
+        a = adv
+        if normalize_adv:
+            a = (a - a.mean()) / (a.std() + 1e-8)
+        ratio = (lp - old_logp).exp()
+        pg = -torch.min(a * ratio, a * ratio.clamp(1 - clip_coef, 1 + clip_coef)).mean()
+        if clip_vloss:
+            vc = old_values + (v - old_values).clamp(-clip_coef, clip_coef)
+            vl = 0.5 * torch.max((v - returns) ** 2, (vc - returns) ** 2).mean()
+        else:
+            vl = ((v - returns) ** 2).mean()
+        el = (-ent).mean()
+        gh, gv = torch.autograd.grad(pg + vf_coef * vl + ent_coef * el, [h, v], allow_unused=True)
+        dhead.copy_(gh)
+        dvalues.copy_(gv)
+        losses.copy_(torch.stack([pg, vl, el]).detach())

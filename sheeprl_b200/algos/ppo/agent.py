@@ -1,0 +1,116 @@
+"""`build_agent` for the B200 PPO engine — same signature / return tuple as the reference
+(`sheeprl/algos/ppo/agent.py:325-369`).  `PPOAgent` is a parameter container whose `state_dict()` has the
+reference's keys and shapes (conv weights [Cout,Cin,k,k], one Linear per action head); the arithmetic of `train()`
+runs in `PPOEngine` kernels.  Acting (`PPOPlayer`) is SURVEY §8f."""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import torch
+
+from sheeprl_b200.algos.ppo.engine import PPOEngine
+
+
+def spec_from_cfg(cfg, actions_dim: Sequence[int], is_continuous: bool, obs_space) -> dict:
+    a = cfg.algo
+    cnn_keys, mlp_keys = list(a.cnn_keys.encoder or []), list(a.mlp_keys.encoder or [])
+    if len(cnn_keys) > 1 or len(mlp_keys) > 1:
+        raise NotImplementedError("the B200 PPO engine takes at most one image key and one vector key")
+    dist = str(cfg.distribution.get("type", "auto")).lower()
+    if dist == "tanh_normal":
+        raise NotImplementedError("distribution.type=tanh_normal is not built yet (auto / discrete / normal are)")
+    if a.encoder.layer_norm or a.actor.layer_norm or a.critic.layer_norm:
+        raise NotImplementedError("layer_norm=True MLPs are not built for PPO yet")
+    acts = {str(a.encoder.dense_act), str(a.actor.dense_act), str(a.critic.dense_act)}
+    if len(acts) != 1 or acts.pop().rsplit(".", 1)[-1] not in ("Tanh", "ReLU"):
+        raise NotImplementedError("dense_act must be torch.nn.Tanh or torch.nn.ReLU, the same for encoder/actor/critic")
+    if not (a.encoder.dense_units == a.actor.dense_units == a.critic.dense_units
+            and a.encoder.mlp_layers == a.actor.mlp_layers == a.critic.mlp_layers):
+        raise NotImplementedError("encoder / actor / critic must share dense_units and mlp_layers")
+    return dict(
+        cnn_channels=int(math.prod(obs_space[cnn_keys[0]].shape[:-2])) if cnn_keys else 0,
+        screen=int(cfg.env.screen_size) if cnn_keys else 0, cnn_key=cnn_keys[0] if cnn_keys else None,
+        mlp_dim=int(obs_space[mlp_keys[0]].shape[0]) if mlp_keys else 0, mlp_key=mlp_keys[0] if mlp_keys else None,
+        dense=int(a.actor.dense_units), layers=int(a.actor.mlp_layers), cnn_features=int(a.encoder.cnn_features_dim),
+        mlp_features=int(a.encoder.mlp_features_dim), actions_dim=tuple(int(x) for x in actions_dim),
+        is_continuous=bool(is_continuous), act="tanh" if str(a.actor.dense_act).endswith("Tanh") else "relu")
+
+
+def hp_from_cfg(cfg) -> dict:
+    a = cfg.algo
+    if str(a.loss_reduction).lower() != "mean":
+        raise NotImplementedError("loss_reduction must be 'mean'")
+    return dict(clip_coef=float(a.clip_coef), vf_coef=float(a.vf_coef), ent_coef=float(a.ent_coef),
+                clip_vloss=bool(a.clip_vloss), normalize_advantages=bool(a.normalize_advantages),
+                max_grad_norm=float(a.max_grad_norm))
+
+
+def default_init(shapes, generator: torch.Generator, ortho_linear_prefix: Optional[str] = None) -> Dict[str, torch.Tensor]:
+    """torch's default reset_parameters for Conv2d / Linear: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias
+    (the reference builds its PPO modules without a custom init unless encoder.ortho_init, ppo/agent.py:140-144)."""
+    out, bound = {}, None
+    for name, shp in shapes.items():
+        if name.endswith(".weight"):
+            bound = 1.0 / math.sqrt(math.prod(shp[1:]))
+            if ortho_linear_prefix and name.startswith(ortho_linear_prefix) and len(shp) == 2:
+                w = torch.empty(*shp)
+                torch.nn.init.orthogonal_(w, 1.0, generator=generator)
+                out[name], bound = w, 0.0
+                continue
+        out[name] = (torch.rand(*shp, generator=generator) * 2 - 1) * bound
+    return out
+
+
+class PPOAgent:
+    """Reference surface used by `ppo.main` / checkpoints (ppo/agent.py:84-239)."""
+
+    def __init__(self, engine: PPOEngine):
+        self._b200_engine = engine
+        self.actions_dim = list(engine.spec["actions_dim"])
+        self.is_continuous = engine.spec["is_continuous"]
+
+    def state_dict(self):
+        return self._b200_engine.export_reference_state()
+
+    def load_state_dict(self, state: Dict[str, torch.Tensor]) -> None:
+        self._b200_engine.load_reference_state(state)
+
+    def parameters(self):
+        return iter(self._b200_engine.group.views.values())
+
+    def forward(self, *a, **k):
+        raise RuntimeError("the B200 PPOAgent has no forward(): the update runs in PPOEngine kernels")
+
+    __call__ = forward
+
+
+class PPOPlayer:
+    """Acting path placeholder."""
+
+    def __init__(self, engine: PPOEngine):
+        self.engine = engine
+
+    def get_actions(self, obs, greedy: bool = False):
+        raise NotImplementedError("PPOPlayer acting path is scheduled after the train() hot path (SURVEY §8f)")
+
+    get_values = __call__ = get_actions
+
+
+def build_agent(fabric, actions_dim: Sequence[int], is_continuous: bool, cfg: Dict[str, Any], obs_space,
+                agent_state: Optional[Dict[str, torch.Tensor]] = None, ops=None) -> Tuple[PPOAgent, PPOPlayer]:
+    if ops is None:
+        from sheeprl_b200.lib import CudaOps
+
+        ops = CudaOps()
+    spec = spec_from_cfg(cfg, actions_dim, is_continuous, obs_space)
+    o = cfg.algo.optimizer
+    opt = {"lr": float(o.lr), "eps": float(o.eps), "betas": tuple(o.get("betas", (0.9, 0.999)))}
+    eng = PPOEngine(spec, hp_from_cfg(cfg), opt, fabric.device, ops, seed=int(cfg.get("seed", 0) or 0))
+    g = torch.Generator().manual_seed(int(cfg.get("seed", 0) or 0))
+    ortho = "feature_extractor." if cfg.algo.encoder.ortho_init else None
+    eng.load_reference_state(default_init(eng.reference_shapes(), g, ortho))
+    agent = PPOAgent(eng)
+    if agent_state:
+        agent.load_state_dict(agent_state)
+    return agent, PPOPlayer(eng)

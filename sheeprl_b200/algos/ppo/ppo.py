@@ -1,0 +1,71 @@
+"""`train()` of PPO on the B200 engine — the reference's signature and side effects
+(sheeprl/algos/ppo/ppo.py:30-102): `update_epochs` passes over the rollout in minibatches drawn by the same
+torch samplers (RandomSampler / DistributedSampler + BatchSampler — host-side index plumbing, identical streams
+under the same seed), parameters and Adam state updated in place, three `aggregator.update` calls per minibatch.
+Each minibatch is one `PPOEngine.minibatch_step` (csrc/ppo.cu + csrc/mlp.cu + replay gather)."""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Sequence
+
+import torch
+from torch.utils.data import BatchSampler, DistributedSampler, RandomSampler
+
+from sheeprl_b200.algos.dreamer_v3.dreamer_v3 import B200Adam
+from sheeprl_b200.utils.registry import register_algorithm
+
+METRIC_ORDER = ("Loss/policy_loss", "Loss/value_loss", "Loss/entropy_loss")
+
+
+def make_optimizer(agent, cfg=None) -> B200Adam:
+    e = agent._b200_engine
+    return B200Adam(e.group, list(e.group.shapes), e.opt["lr"], e.opt["eps"], e.opt["betas"])
+
+
+def minibatch_indices(n_rows: int, fabric, cfg):
+    """The reference's sampler stack (ppo.py:39-56), yielding one list of row indices per minibatch."""
+    indexes = list(range(n_rows))
+    if cfg.buffer.share_data:
+        sampler = DistributedSampler(indexes, num_replicas=fabric.world_size, rank=fabric.global_rank, shuffle=True,
+                                     seed=cfg.seed)
+    else:
+        sampler = RandomSampler(indexes)
+    batches = BatchSampler(sampler, batch_size=cfg.algo.per_rank_batch_size, drop_last=False)
+    for epoch in range(cfg.algo.update_epochs):
+        if cfg.buffer.share_data:
+            batches.sampler.set_epoch(epoch)
+        yield from batches
+
+
+def train(fabric, agent, optimizer, data: Dict[str, torch.Tensor], aggregator, cfg: Dict[str, Any],
+          index_batches: Optional[Sequence[Sequence[int]]] = None) -> None:
+    """data: flat `[N, ...]` tensors on `fabric.device` with the keys the reference passes (ppo.py:399-407): the
+    observation keys (image raw 0..255, float32 or uint8), actions, logprobs, values, returns, advantages.
+    `index_batches` (extra, optional): explicit minibatch index lists for parity tests."""
+    eng = getattr(agent, "_b200_engine", None)
+    if eng is None:
+        raise TypeError("train() needs the agent returned by sheeprl_b200.algos.ppo.agent.build_agent")
+    s = eng.spec
+    d = {k: data[k] for k in ("actions", "logprobs", "values", "returns", "advantages")}
+    d = {k: (v if v.dtype == torch.float32 else v.float()).contiguous() for k, v in d.items()}
+    if s["cnn_channels"]:
+        v = data[s.get("cnn_key") or "rgb"]
+        d["rgb"] = (v if v.dtype in (torch.uint8, torch.float32) else v.float()).contiguous()
+    if s["mlp_dim"]:
+        d["state"] = data[s.get("mlp_key") or "state"].float().contiguous()
+    n_rows = d["actions"].shape[0]
+    it = index_batches if index_batches is not None else minibatch_indices(n_rows, fabric, cfg)
+    log = aggregator is not None and not aggregator.disabled
+
+    def on_minibatch(losses):
+        if log:
+            for i, k in enumerate(METRIC_ORDER):
+                aggregator.update(k, losses[i])
+
+    eng.train(d, it, on_minibatch)
+
+
+@register_algorithm()
+def main(fabric, cfg: Dict[str, Any]):
+    raise NotImplementedError(
+        "the environment-interaction loop (sheeprl/algos/ppo/ppo.py:105-430) is outside this round's hot path "
+        "(SURVEY.md §8); call build_agent()/train() from the reference's main().")

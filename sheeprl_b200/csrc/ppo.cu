@@ -1,0 +1,241 @@
+// PPO update: the pieces around the dense products (csrc/mlp.cu) — patch gather / scatter for the NatureCNN
+// convolutions and the fused PPO objective.
+//
+// Replaces (reference): NatureCNN's Conv2d(k8,s4) / (k4,s2) / (k3,s1) forward + backward
+// (sheeprl/models/models.py:288-328, cnn_forward utils/model.py:165-223), PPOAgent.forward's distribution glue
+// (OneHotCategorical / Independent(Normal) log_prob + entropy, sheeprl/algos/ppo/agent.py:179-239),
+// normalize_tensor (utils/utils.py:121-130) and policy_loss / value_loss / entropy_loss (ppo/loss.py:6-75) with
+// their autograd backward.
+//
+// Convolutions are channel-last: rows of the patch matrix are output pixels (b, oy, ox), columns are (ky, kx, c), so
+// a conv is patch-gather -> product with the [Cout, k, k, Cin] weight (stored in that layout in the flat parameter
+// group) -> [B*Ho*Wo, Cout], which is already the next layer's channel-last input.  A PPO minibatch is 64..256
+// images: ~6 GFLOP per update, i.e. launch-latency territory, hence the emphasis on few, fused launches.
+#include "common.cuh"
+
+namespace {
+
+// col[(b,oy,ox), (ky,kx,c)] = x[b, oy*s+ky, ox*s+kx, c]      (no padding: NatureCNN uses none)
+__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int k,
+                              int s, int Ho, int Wo) {
+  const long long total = (long long)B * Ho * Wo * k * k * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int kkc = k * k * C, kc = k * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int col_j = (int)(i % kkc);
+    const long long row = i / kkc;
+    const int ky = col_j / kc, r = col_j - ky * kc;        // r = kx*C + c : contiguous run in x
+    const int ox = (int)(row % Wo);
+    const long long t = row / Wo;
+    const int oy = (int)(t % Ho);
+    const long long b = t / Ho;
+    col[i] = __ldg(x + ((b * H + (long long)oy * s + ky) * W + (long long)ox * s) * C + r);
+  }
+}
+
+// dx[b,y,x,c] = mask * sum over (ky,kx) with (y-ky) % s == 0, (x-kx) % s == 0 of dcol[(b,(y-ky)/s,(x-kx)/s), (ky,kx,c)]
+// mask = (act[b,y,x,c] > 0) when `act` (the ReLU output that fed this conv) is given.
+__global__ void col2im_kernel(const float* __restrict__ dcol, const float* __restrict__ act, float* __restrict__ dx,
+                              int B, int H, int W, int C, int k, int s, int Ho, int Wo) {
+  const long long total = (long long)B * H * W * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int kkc = k * k * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int xx = (int)(t % W);
+    t /= W;
+    const int yy = (int)(t % H);
+    const long long b = t / H;
+    float acc = 0.f;
+    if (!act || act[i] > 0.f) {
+      for (int ky = yy % s; ky < k; ky += s) {
+        const int oy = (yy - ky) / s;
+        if (yy - ky < 0) break;
+        if (oy >= Ho) continue;
+        for (int kx = xx % s; kx < k; kx += s) {
+          const int ox = (xx - kx) / s;
+          if (xx - kx < 0) break;
+          if (ox >= Wo) continue;
+          acc += __ldg(dcol + ((b * Ho + oy) * Wo + ox) * kkc + (ky * k + kx) * C + c);
+        }
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+struct PpoLossArgs {
+  const float* head;        // discrete: logits [B, sumA]; continuous: [mean | log_std] [B, 2A]
+  const float* actions;     // discrete: one-hot [B, sumA]; continuous: [B, A]
+  const float* old_logp; const float* adv; const float* values; const float* old_values; const float* returns;
+  float* dhead; float* dvalues; float* losses;   // losses[3] = policy, value, entropy
+  int B, n_heads; int head_dims[8];
+  int is_continuous, clip_vloss, normalize_adv;
+  float clip_coef, vf_coef, ent_coef;
+};
+
+// One CTA: B is a minibatch (<= a few thousand rows).
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const PpoLossArgs a) {
+  __shared__ float red[32];
+  const int B = a.B;
+  const float invB = 1.f / (float)B;
+  // ---- advantage normalisation (utils/utils.py:121-130): (x - mean) / (std_unbiased + 1e-8)
+  float mean = 0.f, inv_std = 1.f;
+  if (a.normalize_adv) {
+    float s = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) s += a.adv[b];
+    mean = block_sum(s, red) * invB;
+    float v = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) { const float d = a.adv[b] - mean; v += d * d; }
+    v = block_sum(v, red) / (float)(B - 1);
+    inv_std = 1.f / (sqrtf(v) + 1e-8f);
+  }
+  int width = 0;
+  for (int h = 0; h < a.n_heads; ++h) width += a.head_dims[h];
+  if (a.is_continuous) width *= 2;
+  float s_pg = 0.f, s_v = 0.f, s_e = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* hd = a.head + (long long)b * width;
+    float* dh = a.dhead + (long long)b * width;
+    float lp = 0.f, ent = 0.f;
+    // ---- pass 1: log-prob of the taken action and entropy (ppo/agent.py:179-239)
+    if (a.is_continuous) {
+      const int A = width / 2;
+      for (int j = 0; j < A; ++j) {
+        const float mu = hd[j], ls = hd[A + j], sd = expf(ls), d = a.actions[(long long)b * A + j] - mu;
+        lp += -(d * d) / (2.f * sd * sd) - ls - 0.9189385332046727f;
+        ent += 0.5f + 0.9189385332046727f + ls;
+      }
+    } else {
+      int off = 0;
+      for (int h = 0; h < a.n_heads; ++h) {
+        const int n = a.head_dims[h];
+        float m = -INFINITY;
+        for (int j = 0; j < n; ++j) m = fmaxf(m, hd[off + j]);
+        float z = 0.f;
+        for (int j = 0; j < n; ++j) z += expf(hd[off + j] - m);
+        const float lse = m + logf(z);
+        float hh = 0.f;
+        for (int j = 0; j < n; ++j) {
+          const float lpj = hd[off + j] - lse;
+          lp += lpj * a.actions[(long long)b * width + off + j];
+          hh -= expf(lpj) * lpj;
+        }
+        ent += hh;
+        off += n;
+      }
+    }
+    // ---- objective (ppo/loss.py) and d/dlp, d/dent, d/dvalue
+    const float adv = (a.adv[b] - mean) * inv_std;
+    const float ratio = expf(lp - a.old_logp[b]);
+    const float pg1 = adv * ratio;
+    const float pg2 = adv * fminf(fmaxf(ratio, 1.f - a.clip_coef), 1.f + a.clip_coef);
+    s_pg += -fminf(pg1, pg2);
+    const float dlp = (pg1 <= pg2) ? -pg1 * invB : 0.f;             // d(-min)/dlp = -adv*ratio on the unclipped branch
+    const float val = a.values[b], ret = a.returns[b];
+    float dval;
+    if (a.clip_vloss) {
+      const float old = a.old_values[b];
+      const float dv = val - old;
+      const float vc = old + fminf(fmaxf(dv, -a.clip_coef), a.clip_coef);
+      const float u = (val - ret) * (val - ret), c = (vc - ret) * (vc - ret);
+      s_v += 0.5f * fmaxf(u, c);
+      const float inside = (dv >= -a.clip_coef && dv <= a.clip_coef) ? 1.f : 0.f;
+      const float gu = (val - ret), gc = (vc - ret) * inside;
+      dval = (u > c) ? gu : ((u < c) ? gc : 0.5f * (gu + gc));        // torch.max splits ties evenly
+    } else {
+      s_v += (val - ret) * (val - ret);
+      dval = 2.f * (val - ret);
+    }
+    a.dvalues[b] = a.vf_coef * dval * invB;
+    s_e += -ent;
+    const float dent = -a.ent_coef * invB;
+    // ---- pass 2: gradient w.r.t. the head outputs
+    if (a.is_continuous) {
+      const int A = width / 2;
+      for (int j = 0; j < A; ++j) {
+        const float mu = hd[j], ls = hd[A + j], sd = expf(ls), d = a.actions[(long long)b * A + j] - mu;
+        dh[j] = dlp * d / (sd * sd);
+        dh[A + j] = dlp * (d * d / (sd * sd) - 1.f) + dent;
+      }
+    } else {
+      int off = 0;
+      for (int h = 0; h < a.n_heads; ++h) {
+        const int n = a.head_dims[h];
+        float m = -INFINITY;
+        for (int j = 0; j < n; ++j) m = fmaxf(m, hd[off + j]);
+        float z = 0.f;
+        for (int j = 0; j < n; ++j) z += expf(hd[off + j] - m);
+        const float lse = m + logf(z);
+        float hh = 0.f, asum = 0.f;
+        for (int j = 0; j < n; ++j) {
+          const float lpj = hd[off + j] - lse;
+          hh -= expf(lpj) * lpj;
+          asum += a.actions[(long long)b * width + off + j];
+        }
+        for (int j = 0; j < n; ++j) {
+          const float lpj = hd[off + j] - lse, pj = expf(lpj);
+          dh[off + j] = dlp * (a.actions[(long long)b * width + off + j] - pj * asum) - dent * pj * (lpj + hh);
+        }
+        off += n;
+      }
+    }
+  }
+  s_pg = block_sum(s_pg, red);
+  s_v = block_sum(s_v, red);
+  s_e = block_sum(s_e, red);
+  if (threadIdx.x == 0) {
+    a.losses[0] = s_pg * invB;
+    a.losses[1] = s_v * invB;
+    a.losses[2] = s_e * invB;
+  }
+}
+
+}  // namespace
+
+extern "C" int b200rl_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, cudaStream_t st) {
+  RL_CHECK_ARG(x && col, "null pointer");
+  RL_CHECK_ARG(B > 0 && H >= k && W >= k && C > 0 && k > 0 && stride > 0, "bad dims");
+  const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
+  const long long total = (long long)B * Ho * Wo * k * k * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  im2col_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, col, B, H, W, C, k, stride, Ho, Wo);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_col2im(const float* dcol, const float* act, float* dx, int B, int H, int W, int C, int k, int stride,
+                             cudaStream_t st) {
+  RL_CHECK_ARG(dcol && dx, "null pointer");
+  RL_CHECK_ARG(B > 0 && H >= k && W >= k && C > 0 && k > 0 && stride > 0, "bad dims");
+  const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
+  const long long total = (long long)B * H * W * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  col2im_kernel<<<(unsigned)blocks, 256, 0, st>>>(dcol, act, dx, B, H, W, C, k, stride, Ho, Wo);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_ppo_loss(const float* head, const float* actions, const float* old_logp, const float* adv,
+                               const float* values, const float* old_values, const float* returns, float* dhead,
+                               float* dvalues, float* losses, int B, const int* head_dims, int n_heads, int is_continuous,
+                               int clip_vloss, int normalize_adv, float clip_coef, float vf_coef, float ent_coef,
+                               cudaStream_t st) {
+  RL_CHECK_ARG(head && actions && old_logp && adv && values && old_values && returns && dhead && dvalues && losses,
+               "null pointer");
+  RL_CHECK_ARG(B > 0 && n_heads > 0 && n_heads <= 8 && head_dims, "bad dims (at most 8 action heads)");
+  RL_CHECK_ARG(!normalize_adv || B > 1, "advantage normalisation needs at least two rows");
+  PpoLossArgs a{};
+  a.head = head; a.actions = actions; a.old_logp = old_logp; a.adv = adv; a.values = values;
+  a.old_values = old_values; a.returns = returns; a.dhead = dhead; a.dvalues = dvalues; a.losses = losses;
+  a.B = B; a.n_heads = n_heads;
+  for (int i = 0; i < n_heads; ++i) a.head_dims[i] = head_dims[i];
+  a.is_continuous = is_continuous; a.clip_vloss = clip_vloss; a.normalize_adv = normalize_adv;
+  a.clip_coef = clip_coef; a.vf_coef = vf_coef; a.ent_coef = ent_coef;
+  ppo_loss_kernel<<<1, 256, 0, st>>>(a);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}

@@ -549,3 +549,33 @@ class CudaOps:
         _f32(out)
         self._ck(self.lib.b200rl_fill_normal(_p(out), c_ll(out.numel()), ctypes.c_ulonglong(seed),
                                              ctypes.c_uint(stream_id), _p(counter), self._st()))
+
+    # ------------------------------------------------------------------ PPO (csrc/ppo.cu)
+    def im2col(self, x, col, k: int, stride: int):
+        """x [B,H,W,C] channel-last -> col [B*Ho*Wo, k*k*C]"""
+        _f32(x, col)
+        B, H, W, C = x.shape
+        assert x.is_contiguous() and col.is_contiguous()
+        self._ck(self.lib.b200rl_im2col(_p(x), _p(col), c_int(B), c_int(H), c_int(W), c_int(C), c_int(k), c_int(stride),
+                                        self._st()))
+
+    def col2im(self, dcol, act, dx, k: int, stride: int):
+        """dx [B,H,W,C] = scatter-sum of dcol, masked by (act > 0) when act is given"""
+        _f32(dcol, act, dx)
+        B, H, W, C = dx.shape
+        assert dx.is_contiguous() and dcol.is_contiguous() and (act is None or act.is_contiguous())
+        self._ck(self.lib.b200rl_col2im(_p(dcol), _p(act), _p(dx), c_int(B), c_int(H), c_int(W), c_int(C), c_int(k),
+                                        c_int(stride), self._st()))
+
+    def ppo_loss(self, head, actions, old_logp, adv, values, old_values, returns, dhead, dvalues, losses, head_dims,
+                 is_continuous: bool, clip_vloss: bool, normalize_adv: bool, clip_coef: float, vf_coef: float,
+                 ent_coef: float):
+        _f32(head, actions, old_logp, adv, values, old_values, returns, dhead, dvalues, losses)
+        for t in (head, actions, dhead):
+            assert t.is_contiguous()
+        dims = (c_int * len(head_dims))(*head_dims)
+        self._ck(self.lib.b200rl_ppo_loss(_p(head), _p(actions), _p(old_logp), _p(adv), _p(values), _p(old_values),
+                                          _p(returns), _p(dhead), _p(dvalues), _p(losses), c_int(head.shape[0]), dims,
+                                          c_int(len(head_dims)), c_int(int(is_continuous)), c_int(int(clip_vloss)),
+                                          c_int(int(normalize_adv)), c_float(clip_coef), c_float(vf_coef),
+                                          c_float(ent_coef), self._st()))
