@@ -26,17 +26,22 @@ struct BG {
   int M, N, K, epi, accumulate;
 };
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
-bgemm_kernel(const BG g) {
-  constexpr int BK = 16;
+// Tile kernel: BMxBN outputs per CTA, TMxTN per thread, 256 threads, BK-deep k-steps, double-buffered shared
+// tiles with register prefetch of the next k-step (these products are latency- not throughput-bound: without the
+// prefetch every k-step pays a full L2 round trip).  blockIdx.z = net * ksplit + split; with ksplit > 1 each CTA
+// reduces a K-slice and adds its partial tile with fp32 atomics (weight gradients: long K, tiny output).
+template <int BM, int BN, int TM, int TN, int BK>
+__global__ void __launch_bounds__(256) bgemm_kernel(const BG g, const int ksplit, const int kper) {
   constexpr int NT = (BM / TM) * (BN / TN);
-  __shared__ float As[BK][BM + 1];
-  __shared__ float Bs[BK][BN + 1];
-  const int net = blockIdx.z;
+  static_assert(NT == 256, "256 threads");
+  constexpr int EA = BM * BK / NT, EB = BN * BK / NT;
+  __shared__ float As[2][BK][BM + 1];
+  __shared__ float Bs[2][BK][BN + 1];
+  const int net = blockIdx.z / ksplit, ks = blockIdx.z - net * ksplit;
   const float* __restrict__ A = g.A + net * g.strideA;
   const float* __restrict__ B = g.B + net * g.strideB;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = ks * kper, kend = min(g.K, kbeg + kper);
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   float acc[TM][TN];
@@ -47,38 +52,69 @@ bgemm_kernel(const BG g) {
   float rs = 0.f;                                    // row sum of A for row m0 + tid (tid < BM)
   const bool want_rsum = g.rsum != nullptr && blockIdx.x == 0;
   const bool a_kfast = g.sak == 1, b_nfast = g.sbn == 1;
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
-    // stage A tile (BM x BK): consecutive threads walk the unit-stride dimension
-    for (int e = tid; e < BM * BK; e += NT) {
-      const int m = a_kfast ? e / BK : e % BM;
-      const int k = a_kfast ? e % BK : e / BM;
+  float ra[EA], rb[EB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int e = 0; e < EA; ++e) {                   // consecutive threads walk the unit-stride dimension
+      const int idx = tid + e * NT;
+      const int m = a_kfast ? idx / BK : idx % BM;
+      const int k = a_kfast ? idx % BK : idx / BM;
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < g.M && gk < g.K) ? __ldg(A + gm * g.sam + gk * g.sak) : 0.f;
+      ra[e] = (gm < g.M && gk < kend) ? __ldg(A + gm * g.sam + gk * g.sak) : 0.f;
     }
-    for (int e = tid; e < BN * BK; e += NT) {
-      const int n = b_nfast ? e % BN : e / BK;
-      const int k = b_nfast ? e / BN : e % BK;
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      const int idx = tid + e * NT;
+      const int n = b_nfast ? idx % BN : idx / BK;
+      const int k = b_nfast ? idx / BN : idx % BK;
       const int gn = n0 + n, gk = k0 + k;
-      Bs[k][n] = (gn < g.N && gk < g.K) ? __ldg(B + gk * g.sbk + gn * g.sbn) : 0.f;
+      rb[e] = (gn < g.N && gk < kend) ? __ldg(B + gk * g.sbk + gn * g.sbn) : 0.f;
     }
-    __syncthreads();
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < EA; ++e) {
+      const int idx = tid + e * NT;
+      const int m = a_kfast ? idx / BK : idx % BM;
+      const int k = a_kfast ? idx % BK : idx / BM;
+      As[buf][k][m] = ra[e];
+    }
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      const int idx = tid + e * NT;
+      const int n = b_nfast ? idx % BN : idx / BK;
+      const int k = b_nfast ? idx / BN : idx % BK;
+      Bs[buf][k][n] = rb[e];
+    }
+  };
+  int cur = 0;
+  if (kbeg < kend) {
+    fetch(kbeg);
+    stash(0);
+  }
+  __syncthreads();
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = k0 + BK < kend;
+    if (more) fetch(k0 + BK);
     if (want_rsum && tid < BM) {
 #pragma unroll
-      for (int k = 0; k < BK; ++k) rs += As[k][tid];
+      for (int k = 0; k < BK; ++k) rs += As[cur][k][tid];
     }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN];
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+      for (int i = 0; i < TM; ++i) a[i] = As[cur][k][ty * TM + i];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+      for (int j = 0; j < TN; ++j) b[j] = Bs[cur][k][tx * TN + j];
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    if (more) stash(cur ^ 1);
     __syncthreads();
+    cur ^= 1;
   }
   float* __restrict__ C = g.C + net * g.strideC;
   const float* __restrict__ bias = g.bias ? g.bias + net * g.strideBias : nullptr;
@@ -92,19 +128,35 @@ bgemm_kernel(const BG g) {
       const int n = n0 + tx * TN + j;
       if (n >= g.N) continue;
       float v = acc[i][j];
+      float* c = C + m * g.ldc + n;
+      if (ksplit > 1) {                              // partial tile (epilogue is EPI_NONE, no bias: checked by host)
+        atomicAdd(c, v);
+        continue;
+      }
       if (bias) v += bias[n];
       if (g.epi == EPI_RELU) v = fmaxf(v, 0.f);
       else if (g.epi == EPI_TANH) v = tanhf(v);
       else if (g.epi == EPI_DRELU) v = (aux[m * g.ldaux + n] > 0.f) ? v : 0.f;
       else if (g.epi == EPI_DTANH) { const float y = aux[m * g.ldaux + n]; v *= (1.f - y * y); }
-      float* c = C + m * g.ldc + n;
       *c = g.accumulate ? *c + v : v;
     }
   }
   if (want_rsum && tid < BM && m0 + tid < g.M) {
     float* r = g.rsum + net * g.strideRsum + m0 + tid;
-    *r = g.accumulate ? *r + rs : rs;
+    if (ksplit > 1) atomicAdd(r, rs);
+    else *r = g.accumulate ? *r + rs : rs;
   }
+}
+
+// zero C (and rsum) ahead of a split-K launch that does not accumulate
+__global__ void bgemm_zero_kernel(const BG g) {
+  const int net = blockIdx.z;
+  float* C = g.C + net * g.strideC;
+  const long long total = (long long)g.M * g.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    C[(i / g.N) * g.ldc + (i % g.N)] = 0.f;
+  if (g.rsum && blockIdx.x == 0)
+    for (int m = threadIdx.x; m < g.M; m += blockDim.x) g.rsum[net * g.strideRsum + m] = 0.f;
 }
 
 }  // namespace
@@ -120,14 +172,35 @@ extern "C" int b200rl_bgemm(const float* A, long long sam, long long sak, long l
   RL_CHECK_ARG(epilogue < EPI_DRELU || aux, "derivative epilogue needs the saved activation");
   BG g{A, sam, sak, strideA, B, sbk, sbn, strideB, C, ldc, strideC, bias, strideBias, aux, ldaux, strideAux,
        rsum, strideRsum, M, N, K, epilogue, accumulate};
+  // tile shape: wide tiles once they fill the machine, narrow N for thin outputs (conv1: N = 32), else 32x32
   const long long tiles64 = (long long)((M + 63) / 64) * ((N + 63) / 64) * nets;
-  if (tiles64 >= 2 * kNumSMs) {
-    dim3 grid((N + 63) / 64, (M + 63) / 64, nets);
-    bgemm_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(g);
-  } else {
-    dim3 grid((N + 31) / 32, (M + 31) / 32, nets);
-    bgemm_kernel<32, 32, 2, 2><<<grid, 256, 0, st>>>(g);
+  int BMv = 32, BNv = 32;
+  if (N <= 32 && (long long)((M + 63) / 64) * nets >= kNumSMs) { BMv = 64; BNv = 32; }
+  else if (tiles64 >= kNumSMs) { BMv = 64; BNv = 64; }
+  constexpr int BK = 32;
+  const int tx = (N + BNv - 1) / BNv, ty = (M + BMv - 1) / BMv;
+  const long long tiles = (long long)tx * ty * nets;
+  // split-K: only for plain products (weight gradients) whose output tiles cannot fill the SMs
+  int ksplit = 1;
+  if (epilogue == EPI_NONE && !bias && tiles < kNumSMs && K >= 8 * BK) {
+    ksplit = (int)((4LL * kNumSMs + tiles - 1) / tiles);
+    if (ksplit > K / (2 * BK)) ksplit = K / (2 * BK);
+    if (ksplit > 128) ksplit = 128;
+    if (ksplit < 1) ksplit = 1;
   }
+  int kper = ((K + ksplit - 1) / ksplit + BK - 1) / BK * BK;
+  ksplit = (K + kper - 1) / kper;
+  RL_CHECK_ARG((long long)nets * ksplit <= 65535, "too many networks x K-splits for grid.z");
+  if (ksplit > 1 && !accumulate) {
+    const long long total = (long long)M * N;
+    int zb = (int)((total + 255) / 256);
+    if (zb > 64) zb = 64;
+    bgemm_zero_kernel<<<dim3(zb, 1, nets), 256, 0, st>>>(g);
+  }
+  dim3 grid(tx, ty, nets * ksplit);
+  if (BMv == 64 && BNv == 64) bgemm_kernel<64, 64, 4, 4, BK><<<grid, 256, 0, st>>>(g, ksplit, kper);
+  else if (BMv == 64) bgemm_kernel<64, 32, 4, 2, BK><<<grid, 256, 0, st>>>(g, ksplit, kper);
+  else bgemm_kernel<32, 32, 2, 2, BK><<<grid, 256, 0, st>>>(g, ksplit, kper);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }
