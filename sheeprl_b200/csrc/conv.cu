@@ -375,18 +375,21 @@ __global__ void transpose2d_kernel(const float* __restrict__ X, float* __restric
 }
 
 // Transposed im2col for the weight-gradient GEMM: out[(tap*Cb + cb)][pix] = big[n, 2y-1+ky, 2x-1+kx, cb] (0 outside).
-// One block = 32 pixels x 32 channels of one tap: coalesced channel reads, smem transpose, coalesced pixel writes.
-__global__ void im2col_t_kernel(const float* __restrict__ Big, float* __restrict__ out, int NB, int h, int w, int Cb,
-                                long long ldo) {
-  __shared__ float tile[32][33];
+// One block = 128 pixels x 32 channels of one tap: 128-byte channel reads, smem transpose, 512-byte pixel runs written
+// as float4 (the matrix is 4x the activation it is gathered from, so the write side is what has to be wide).
+__global__ void __launch_bounds__(256)
+im2col_t_kernel(const float* __restrict__ Big, float* __restrict__ out, int NB, int h, int w, int Cb, long long ldo) {
+  constexpr int PT = 128;
+  __shared__ __align__(16) float tile[32][PT + 4];
   const int tap = blockIdx.z, ky = tap >> 2, kx = tap & 3;
-  const long long p0 = (long long)blockIdx.x * 32;
+  const long long p0 = (long long)blockIdx.x * PT;
   const int c0 = blockIdx.y * 32;
   const long long P = (long long)NB * h * w;
   const int Hb = 2 * h, Wb = 2 * w;
-  for (int r = threadIdx.y; r < 32; r += 8) {
+  const int c = c0 + threadIdx.x;
+#pragma unroll 4
+  for (int r = threadIdx.y; r < PT; r += 8) {
     const long long p = p0 + r;
-    const int c = c0 + threadIdx.x;
     float v = 0.f;
     if (p < P && c < Cb) {
       const int x = (int)(p % w);
@@ -394,15 +397,24 @@ __global__ void im2col_t_kernel(const float* __restrict__ Big, float* __restrict
       const int y = (int)(t % h);
       const long long n = t / h;
       const int yy = 2 * y - 1 + ky, xx = 2 * x - 1 + kx;
-      if (yy >= 0 && yy < Hb && xx >= 0 && xx < Wb) v = Big[((n * Hb + yy) * Wb + xx) * (long long)Cb + c];
+      if (yy >= 0 && yy < Hb && xx >= 0 && xx < Wb) v = __ldg(Big + ((n * Hb + yy) * Wb + xx) * (long long)Cb + c);
     }
-    tile[r][threadIdx.x] = v;
+    tile[threadIdx.x][r] = v;
   }
   __syncthreads();
+  // 32 channel rows x 32 float4 per row: warp ty writes rows ty, ty+8, ...
   for (int r = threadIdx.y; r < 32; r += 8) {
-    const int c = c0 + r;
-    const long long p = p0 + threadIdx.x;
-    if (c < Cb && p < P) out[((long long)tap * Cb + c) * ldo + p] = tile[threadIdx.x][r];
+    const int cc = c0 + r;
+    const long long p = p0 + 4 * threadIdx.x;
+    if (cc >= Cb || p >= P) continue;
+    float* dst = out + ((long long)tap * Cb + cc) * ldo + p;
+    const float4 v = *reinterpret_cast<const float4*>(&tile[r][4 * threadIdx.x]);
+    if (p + 3 < P) *reinterpret_cast<float4*>(dst) = v;
+    else {
+      dst[0] = v.x;
+      if (p + 1 < P) dst[1] = v.y;
+      if (p + 2 < P) dst[2] = v.z;
+    }
   }
 }
 
@@ -445,7 +457,7 @@ extern "C" int b200rl_conv_wgrad_tc(const float* small_, const float* big, float
       transpose2d_kernel<<<dim3(ceil_div(Cs, 32), ceil_div(nr, 32)), dim3(32, 8), 0, st>>>(small_ + r0 * Cs, St + r0, nr, Cs, Cs, Pp);
     }
   }
-  im2col_t_kernel<<<dim3((unsigned)ceil_div(P, 32), ceil_div(Cb, 32), 16), dim3(32, 8), 0, st>>>(big, Bt, NB, h, w, Cb, Pp);
+  im2col_t_kernel<<<dim3((unsigned)ceil_div(P, 128), ceil_div(Cb, 32), 16), dim3(32, 8), 0, st>>>(big, Bt, NB, h, w, Cb, Pp);
   RL_CHECK_LAUNCH();
   // rows = (tap, cb) (>= 128), columns = cs: G = im2col^T . small
   if (int rc = b200rl_gemm_tc(Bt, St, G, nullptr, 16 * Cb, Cs, (int)P, (int)Pp, (int)Pp, Cs, 0, 1, 0, st)) return rc;
@@ -464,6 +476,14 @@ extern "C" int b200rl_transpose2d(const float* X, float* Y, int rows, int cols, 
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }
+
+// thin-channel specialisations (conv_thin.cu)
+bool b200rl_thin_up_supported(int Cs, int Cb);
+bool b200rl_thin_wgrad_supported(int Cs, int Cb);
+int b200rl_conv_up_thin(const float* small, const float* W, float* big, const float* bias, int NB, int h, int w, int Cs,
+                        int Cb, cudaStream_t st);
+int b200rl_conv_wgrad_thin(const float* small, const float* big, float* dW, int NB, int h, int w, int Cs, int Cb,
+                           cudaStream_t st);
 
 extern "C" int b200rl_conv_down(const float* big, const float* W, float* small, int NB, int h, int w, int Cs, int Cb,
                                 cudaStream_t st) {
@@ -485,6 +505,7 @@ extern "C" int b200rl_conv_up(const float* small, const float* W, float* big, co
                               int Cs, int Cb, cudaStream_t st) {
   RL_CHECK_ARG(big && W && small, "null pointer");
   RL_CHECK_ARG(NB > 0 && h > 0 && w > 0 && Cs > 0 && Cb > 0, "bad dims");
+  if (b200rl_thin_up_supported(Cs, Cb)) return b200rl_conv_up_thin(small, W, big, bias, NB, h, w, Cs, Cb, st);
   const long long Mtot = (long long)NB * h * w;
   const int gm = ceil_div(Mtot, 128);
   if (Cb <= 32)
@@ -502,6 +523,7 @@ extern "C" int b200rl_conv_wgrad(const float* small, const float* big, float* dW
   RL_CHECK_ARG(big && dW && small, "null pointer");
   RL_CHECK_ARG(NB > 0 && h > 0 && w > 0 && Cs > 0 && Cb > 0, "bad dims");
   if (!accumulate) RL_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)Cs * Cb * 16, st));
+  if (b200rl_thin_wgrad_supported(Cs, Cb)) return b200rl_conv_wgrad_thin(small, big, dW, NB, h, w, Cs, Cb, st);
   const long long Mtot = (long long)NB * h * w;
   if (Cb <= 4 && Cs * 16 * Cb <= 24 * 256) {
     long long blocks = min((long long)4 * kNumSMs, (Mtot + 31) / 32);

@@ -138,6 +138,8 @@ def test_col_sum(ops, M, C):
 
 CONV_SHAPES = [(3, 8, 8, 16, 8), (2, 4, 4, 32, 16), (5, 16, 16, 4, 3), (2, 32, 32, 32, 3), (3, 2, 2, 40, 24),
                (2, 4, 4, 130, 72), (1, 8, 8, 8, 2),
+               # thin big-image side (conv_thin.cu): partial / multiple 32-pixel row tiles, every channel-group count
+               (3, 16, 16, 64, 3), (2, 40, 40, 96, 3), (1, 32, 32, 48, 3), (2, 8, 8, 32, 1), (2, 8, 8, 64, 4),
                # tensor-core implicit-GEMM eligible (gathered image has a multiple of 32 channels, grid tiles by 128 px)
                (8, 4, 4, 64, 32), (2, 32, 32, 32, 64), (4, 16, 16, 128, 64), (16, 8, 8, 256, 128), (24, 4, 4, 96, 32)]
 
