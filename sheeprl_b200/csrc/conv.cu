@@ -381,25 +381,33 @@ __global__ void __launch_bounds__(256)
 im2col_t_kernel(const float* __restrict__ Big, float* __restrict__ out, int NB, int h, int w, int Cb, long long ldo) {
   constexpr int PT = 128;
   __shared__ __align__(16) float tile[32][PT + 4];
+  __shared__ long long src[PT];                     // source pixel offset (in pixels) or -1 outside the image
   const int tap = blockIdx.z, ky = tap >> 2, kx = tap & 3;
   const long long p0 = (long long)blockIdx.x * PT;
   const int c0 = blockIdx.y * 32;
   const long long P = (long long)NB * h * w;
   const int Hb = 2 * h, Wb = 2 * w;
   const int c = c0 + threadIdx.x;
-#pragma unroll 4
-  for (int r = threadIdx.y; r < PT; r += 8) {
-    const long long p = p0 + r;
-    float v = 0.f;
-    if (p < P && c < Cb) {
+  // the (n, y, x) decomposition costs two 64-bit divisions: do it once per pixel, not once per element
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < PT) {
+    const long long p = p0 + tid;
+    long long off = -1;
+    if (p < P) {
       const int x = (int)(p % w);
       const long long t = p / w;
       const int y = (int)(t % h);
       const long long n = t / h;
       const int yy = 2 * y - 1 + ky, xx = 2 * x - 1 + kx;
-      if (yy >= 0 && yy < Hb && xx >= 0 && xx < Wb) v = __ldg(Big + ((n * Hb + yy) * Wb + xx) * (long long)Cb + c);
+      if (yy >= 0 && yy < Hb && xx >= 0 && xx < Wb) off = (n * Hb + yy) * Wb + xx;
     }
-    tile[threadIdx.x][r] = v;
+    src[tid] = off;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int r = threadIdx.y; r < PT; r += 8) {
+    const long long off = src[r];
+    tile[threadIdx.x][r] = (off >= 0 && c < Cb) ? __ldg(Big + off * Cb + c) : 0.f;
   }
   __syncthreads();
   // 32 channel rows x 32 float4 per row: warp ty writes rows ty, ty+8, ...

@@ -218,7 +218,8 @@ int b200rl_conv_wgrad_thin(const float* small, const float* big, float* dW, int 
                            cudaStream_t st) {
   const int tiles_per_row = (w + 31) / 32;
   const long long ntiles = (long long)NB * h * tiles_per_row;
-  long long blocks = ntiles < 2LL * kNumSMs ? ntiles : 2LL * kNumSMs;
+  // ~13 KB of smem and 80 registers per thread: 6 CTAs per SM hide the stage -> compute latency of a 32-pixel tile
+  long long blocks = ntiles < 6LL * kNumSMs ? ntiles : 6LL * kNumSMs;
   const size_t smem = sizeof(float) * (4 * (2 * 32 + 2) * Cb + 32 * 32 + 16 * Cb * Cs);
   switch (Cb) {
     case 1: conv_wgrad_thin_kernel<1><<<(unsigned)blocks, 256, smem, st>>>(small, big, dW, NB, h, w, Cs, tiles_per_row); break;

@@ -389,8 +389,12 @@ extern "C" int b200rl_ln_act_bwd(const float* X, const float* gamma, const float
   else if (C <= 256) LN_BWD(8, 0);
   else if (C <= 512) LN_BWD(16, 0);
   else {
-    RL_CHECK_ARG(C <= 5632, "C too large for the shared accumulator path");
-    LN_BWD(0, sizeof(float) * 2 * C);
+    // wide rows (XL: the GRU's joint LayerNorm spans 3*4096 channels): per-CTA gamma/beta partials in opted-in smem
+    RL_CHECK_ARG(C <= 28000, "C too large for the shared accumulator path");
+    const size_t smem = sizeof(float) * 2 * (size_t)C;
+    if (smem > 48 * 1024)
+      RL_CUDA(cudaFuncSetAttribute(ln_act_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LN_BWD(0, smem);
   }
 #undef LN_BWD
   RL_CHECK_LAUNCH();

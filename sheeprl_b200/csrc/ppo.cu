@@ -18,18 +18,16 @@ namespace {
 // col[(b,oy,ox), (ky,kx,c)] = x[b, oy*s+ky, ox*s+kx, c]      (no padding: NatureCNN uses none)
 __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int k,
                               int s, int Ho, int Wo) {
-  const long long total = (long long)B * Ho * Wo * k * k * C;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const int kkc = k * k * C, kc = k * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int col_j = (int)(i % kkc);
-    const long long row = i / kkc;
-    const int ky = col_j / kc, r = col_j - ky * kc;        // r = kx*C + c : contiguous run in x
-    const int ox = (int)(row % Wo);
-    const long long t = row / Wo;
-    const int oy = (int)(t % Ho);
-    const long long b = t / Ho;
-    col[i] = __ldg(x + ((b * H + (long long)oy * s + ky) * W + (long long)ox * s) * C + r);
+  // 32-bit index arithmetic (host guarantees < 2^31 elements): 64-bit div/mod would dominate this copy kernel
+  const unsigned total = (unsigned)B * Ho * Wo * k * k * C;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned kkc = k * k * C, kc = k * C;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned row = i / kkc, col_j = i - row * kkc;
+    const unsigned ky = col_j / kc, r = col_j - ky * kc;        // r = kx*C + c : contiguous run in x
+    const unsigned t = row / Wo, ox = row - t * Wo;
+    const unsigned b = t / Ho, oy = t - b * Ho;
+    col[i] = __ldg(x + (((size_t)b * H + oy * s + ky) * W + ox * s) * C + r);
   }
 }
 
@@ -37,27 +35,25 @@ __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ c
 // mask = (act[b,y,x,c] > 0) when `act` (the ReLU output that fed this conv) is given.
 __global__ void col2im_kernel(const float* __restrict__ dcol, const float* __restrict__ act, float* __restrict__ dx,
                               int B, int H, int W, int C, int k, int s, int Ho, int Wo) {
-  const long long total = (long long)B * H * W * C;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const int kkc = k * k * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int c = (int)(i % C);
-    long long t = i / C;
-    const int xx = (int)(t % W);
-    t /= W;
-    const int yy = (int)(t % H);
-    const long long b = t / H;
+  const unsigned total = (unsigned)B * H * W * C;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned kkc = k * k * C;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    unsigned t = i / C;
+    const int c = (int)(i - t * C);
+    const unsigned t2 = t / W;
+    const int xx = (int)(t - t2 * W);
+    const unsigned b = t2 / H;
+    const int yy = (int)(t2 - b * H);
     float acc = 0.f;
     if (!act || act[i] > 0.f) {
-      for (int ky = yy % s; ky < k; ky += s) {
+      for (int ky = yy % s; ky < k && ky <= yy; ky += s) {
         const int oy = (yy - ky) / s;
-        if (yy - ky < 0) break;
         if (oy >= Ho) continue;
-        for (int kx = xx % s; kx < k; kx += s) {
+        for (int kx = xx % s; kx < k && kx <= xx; kx += s) {
           const int ox = (xx - kx) / s;
-          if (xx - kx < 0) break;
           if (ox >= Wo) continue;
-          acc += __ldg(dcol + ((b * Ho + oy) * Wo + ox) * kkc + (ky * k + kx) * C + c);
+          acc += __ldg(dcol + ((size_t)(b * Ho + oy) * Wo + ox) * kkc + (ky * k + kx) * C + c);
         }
       }
     }
@@ -199,6 +195,7 @@ extern "C" int b200rl_im2col(const float* x, float* col, int B, int H, int W, in
   RL_CHECK_ARG(B > 0 && H >= k && W >= k && C > 0 && k > 0 && stride > 0, "bad dims");
   const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
   const long long total = (long long)B * Ho * Wo * k * k * C;
+  RL_CHECK_ARG(total < 2147483647LL, "patch matrix too large for 32-bit indexing: split the minibatch");
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
   im2col_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, col, B, H, W, C, k, stride, Ho, Wo);
@@ -212,6 +209,7 @@ extern "C" int b200rl_col2im(const float* dcol, const float* act, float* dx, int
   RL_CHECK_ARG(B > 0 && H >= k && W >= k && C > 0 && k > 0 && stride > 0, "bad dims");
   const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
   const long long total = (long long)B * H * W * C;
+  RL_CHECK_ARG(total < 2147483647LL && (long long)B * Ho * Wo * k * k * C < 2147483647LL, "image too large for 32-bit indexing");
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
   col2im_kernel<<<(unsigned)blocks, 256, 0, st>>>(dcol, act, dx, B, H, W, C, k, stride, Ho, Wo);

@@ -178,3 +178,38 @@ def test_fused_scan_equals_per_step_scan(name):
     for k in ref:
         err = float((ref[k] - got[k]).abs().max())
         assert err <= 5e-5 * max(1e-3, float(ref[k].abs().max())), (k, err, float(ref[k].abs().max()))
+
+
+def test_engine_cuda_xl_widths_vs_oracle():
+    """BASELINE.json configs[4] model (Dreamer-V3 XL: 5 MLP layers, dense 1024, R=4096, conv 96/192/384/768) on a
+    short batch (B=2, T=4, H=3): the per-step scan path (weights exceed the persistent kernel's shared memory), the
+    tensor-core GEMM / conv paths at XL widths and every gradient against the oracle, 1e-4."""
+    from oracle import dv3_oracle as O
+    from oracle.make_golden import perturbed_oracle_init
+    from sheeprl_b200.configs import make_dv3_cfg
+
+    cfg = make_dv3_cfg("XL", per_rank_batch_size=2, per_rank_sequence_length=4, horizon=3)
+    adim = (3,)
+    a, w = cfg.algo, cfg.algo.world_model
+    init = perturbed_oracle_init(cfg, adim, 21, 0.02)
+    data = [O.make_batch(cfg, adim, seed=22)]
+    noise = [O.draw_noise(a.per_rank_sequence_length, a.per_rank_batch_size, a.horizon, w.stochastic_size,
+                          w.discrete_size, adim, seed=23)]
+    st, o_outs, ms, _ = oracle_run(cfg, adim, init, data, noise, 1, condition_margin=1e-3, keep=True)
+    eng = make_engine(cfg, adim, init)
+    batch = {k: v.clone().cuda() for k, v in data[0].items()}
+    eng.train_step(batch, to_cuda(noise[0]))
+    torch.cuda.synchronize()
+    assert not eng.fused_scan                               # XL falls back to the per-step kernels
+    N = eng.N
+    assert torch.equal(eng.latent[:, : eng.Z].cpu().reshape(o_outs[0]["latent"][..., : eng.Z].shape),
+                       o_outs[0]["latent"][..., : eng.Z].round()), "posterior samples differ"
+    for nm, got, want in (("h", eng.latent[:, eng.Z:], o_outs[0]["latent"][..., eng.Z:].reshape(N, -1)),
+                          ("lambda", eng.lam, o_outs[0]["lambda_values"].squeeze(-1))):
+        err = float((got.cpu() - want).abs().max())
+        assert err <= 1e-4 * max(1.0, float(want.abs().max())), (nm, err)
+    grads = {g: {k: v.clone() for k, v in getattr(eng, g).gviews.items()} for g in ("wm", "actor", "critic")}
+    check_grads(grads, o_outs[0], cfg, 1e-4)
+    got = {k: float(v) for k, v in eng.metrics_dict().items()}
+    for k in got:
+        assert got[k] == pytest.approx(float(o_outs[0][k]), rel=1e-4, abs=1e-6), k
