@@ -212,4 +212,8 @@ def test_engine_cuda_xl_widths_vs_oracle():
     check_grads(grads, o_outs[0], cfg, 1e-4)
     got = {k: float(v) for k, v in eng.metrics_dict().items()}
     for k in got:
-        assert got[k] == pytest.approx(float(o_outs[0][k]), rel=1e-4, abs=1e-6), k
+        # Grads/*: torch's fp32 CPU norm over 1e8-element tensors is itself only good to ~6e-4 here (the double-
+        # precision norm of the ORACLE's own gradients equals the kernel's 7844.57, torch reports 7839.71), so the
+        # logged norms are compared at 1e-3; every gradient tensor was compared at 1e-4 above.
+        tol = 1e-3 if k.startswith("Grads/") else 1e-4
+        assert got[k] == pytest.approx(float(o_outs[0][k]), rel=tol, abs=1e-6), k
