@@ -242,6 +242,12 @@ int b200rl_ppo_loss(const float* head, const float* actions, const float* old_lo
                     float* losses, int B, const int* head_dims, int n_heads, int is_continuous, int clip_vloss,
                     int normalize_adv, float clip_coef, float vf_coef, float ent_coef, cudaStream_t stream);
 
+/* Linear([z, a]) for a one-hot z (S groups of K classes, straight-through categorical sample) as a gather-sum over the
+ * transposed weight WT [S*K + A, N]: RecurrentModel.mlp's first Linear (agent.py:328-341) inside the imagination
+ * rollout.  z: [M, S*K] (row stride ldz), act: [M, A], out: [M, N]. */
+int b200rl_onehot_linear(const float* z, const float* act, const float* WT, float* out, long long M, int S, int K, int A,
+                         int N, long long ldz, long long lda, long long ldo, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -500,3 +500,11 @@ class EmulOps:
         dhead.copy_(gh)
         dvalues.copy_(gv)
         losses.copy_(torch.stack([pg, vl, el]).detach())
+
+    # ---- imagination: Linear([one-hot z, a]) as a gather-sum (csrc/rssm.cu)
+    def transpose2d(self, X: Tensor, Y: Tensor):
+        Y.copy_(X.t())
+
+    def onehot_linear(self, z: Tensor, act: Tensor, WT: Tensor, out: Tensor, groups: int, classes: int):
+        Z = groups * classes
+        out.copy_(z @ WT[:Z] + act @ WT[Z:])

@@ -166,6 +166,48 @@ cat_sample_kernel(const float* __restrict__ raw, const float* __restrict__ noise
   for (int c = lane; c < K; c += 32) onehot[m * ldo + (long long)g * K + c] = (c == besti) ? 1.f : 0.f;
 }
 
+// K <= 32: one class per lane, every quantity computed once and kept in a register.  Same expressions and the same
+// butterfly reductions as cat_sample_kernel, so samples and log-probs are bit-identical to the general path.
+__global__ void __launch_bounds__(256)
+cat_sample_small_kernel(const float* __restrict__ raw, const float* __restrict__ noise, float* __restrict__ onehot,
+                        float* __restrict__ mix_out, long long M, int groups, int K, long long ldr, long long ldn,
+                        long long ldo, long long ldm, float unimix) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= M * groups) return;
+  const long long m = warp / groups;
+  const int g = (int)(warp - m * groups);
+  const bool on = lane < K;
+  const float xv = on ? raw[m * ldr + (long long)g * K + lane] : -INFINITY;
+  const float mx = warp_max(xv);
+  const float sm = warp_sum(on ? expf(xv - mx) : 0.f);
+  const float invK = 1.f / (float)K;
+  float l = xv;
+  if (unimix > 0.f && on) { float pm; l = unimix_logprob(expf(xv - mx) / sm, unimix, invK, pm); }
+  const float lmx = warp_max(on ? l : -INFINITY);
+  const float ls = warp_sum(on ? expf(l - lmx) : 0.f);
+  const float lse = lmx + logf(ls);
+  if (mix_out && on) mix_out[m * ldm + (long long)g * K + lane] = l;
+  const float lgmax = warp_max(on ? l - lse : -INFINITY);
+  const float e = on ? expf(l - lse - lgmax) : 0.f;
+  const float psum = warp_sum(e);
+  if (!onehot) return;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  if (on) {
+    float p = e / psum;
+    if (noise) p = p / noise[m * ldn + (long long)g * K + lane];
+    if (p > best) { best = p; besti = lane; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (on) onehot[m * ldo + (long long)g * K + lane] = (lane == besti) ? 1.f : 0.f;
+}
+
 __global__ void __launch_bounds__(256)
 cat_sample_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ dz, const float* __restrict__ dmix,
                       float* __restrict__ draw, long long M, int groups, int K, long long ldr, long long lddz,
@@ -284,6 +326,38 @@ kl_loss_grad_kernel(const float* __restrict__ post, const float* __restrict__ pr
   }
 }
 
+
+// out[m, :] = sum_g WT[g*K + idx(m,g), :] + sum_a act[m,a] * WT[S*K + a, :]   with idx = the hot class of group g.
+// z is a concatenation of S one-hot groups (a straight-through categorical sample), so Linear([z, a]) is a gather-sum
+// of S+A rows of the transposed weight instead of a K = S*K + A product (agent.py:328-341 RecurrentModel.mlp input).
+// One CTA per row; WT [S*K + A, N] row-major (transposed copy of the Linear weight, L2 resident).
+__global__ void __launch_bounds__(256)
+onehot_linear_kernel(const float* __restrict__ z, const float* __restrict__ act, const float* __restrict__ WT,
+                     float* __restrict__ out, int S, int K, int A, int N, long long ldz, long long lda, long long ldo) {
+  __shared__ int idx[64];
+  __shared__ float av[32];
+  const long long m = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int g = warp; g < S; g += 8) {                       // hot index of each group by ballot
+    int found = 0;
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      const int c = c0 + lane;
+      const unsigned b = __ballot_sync(0xffffffffu, c < K && z[m * ldz + (long long)g * K + c] != 0.f);
+      if (b) { found = c0 + __ffs(b) - 1; break; }
+    }
+    if (lane == 0) idx[g] = found;
+  }
+  if (threadIdx.x < A) av[threadIdx.x] = act[m * lda + threadIdx.x];
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int g = 0; g < S; ++g) acc += __ldg(WT + ((long long)g * K + idx[g]) * N + n);   // independent L2 loads in flight
+    for (int a = 0; a < A; ++a) acc = fmaf(av[a], __ldg(WT + ((long long)S * K + a) * N + n), acc);
+    out[m * ldo + n] = acc;
+  }
+}
+
 }  // namespace
 
 extern "C" int b200rl_gru_gate_fwd(const float* G, const float* Hin, float* Hout, long long M, int R, long long ldg,
@@ -330,8 +404,12 @@ extern "C" int b200rl_cat_sample(const float* raw, const float* noise, float* on
   RL_CHECK_ARG(groups > 0 && K > 0, "bad groups / classes");
   if (M <= 0) return B200RL_OK;
   const long long warps = M * groups;
-  cat_sample_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(raw, noise, onehot, mix_out, M, groups, K, ldr, ldn, ldo, ldm,
-                                                        unimix);
+  if (K <= 32)
+    cat_sample_small_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(raw, noise, onehot, mix_out, M, groups, K, ldr, ldn, ldo,
+                                                                ldm, unimix);
+  else
+    cat_sample_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(raw, noise, onehot, mix_out, M, groups, K, ldr, ldn, ldo, ldm,
+                                                          unimix);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }
@@ -357,6 +435,16 @@ extern "C" int b200rl_kl_loss_grad(const float* post_mix, const float* prior_mix
   if (M <= 0) return B200RL_OK;
   kl_loss_grad_kernel<<<(unsigned)M, 256, 0, st>>>(post_mix, prior_mix, d_post, d_prior, rows, groups, K, ldp, ldq,
                                                    lddp, lddq, kl_dyn, kl_rep, free_nats, scale * regularizer);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_onehot_linear(const float* z, const float* act, const float* WT, float* out, long long M, int S,
+                                    int K, int A, int N, long long ldz, long long lda, long long ldo, cudaStream_t st) {
+  RL_CHECK_ARG(z && act && WT && out, "null pointer");
+  RL_CHECK_ARG(S > 0 && S <= 64 && K > 0 && A >= 0 && A <= 32 && N > 0, "bad dims (S <= 64 groups, A <= 32)");
+  if (M <= 0) return B200RL_OK;
+  onehot_linear_kernel<<<(unsigned)M, 256, 0, st>>>(z, act, WT, out, S, K, A, N, ldz, lda, ldo);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }

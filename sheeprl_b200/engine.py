@@ -487,13 +487,17 @@ class DV3Engine:
         ops.gemm(self.d_dec_lin, self._w(p + "0.weight"), self.d_latent, False, False)
 
     # ------------------------------------------------------------------ RSSM pieces
-    def _recurrent_forward(self, z, act, h_prev, x_pre, x_act, g_pre, g_ln, h_out):
-        """RecurrentModel + LayerNormGRUCell on M rows (agent.py:328-341, models.py:396-403)."""
+    def _recurrent_forward(self, z, act, h_prev, x_pre, x_act, g_pre, g_ln, h_out, win_t=None):
+        """RecurrentModel + LayerNormGRUCell on M rows (agent.py:328-341, models.py:396-403).  `win_t`: transposed
+        first-layer weight; given only when z is an exact one-hot sample (imagination), the product becomes a gather."""
         ops, Z, R = self.ops, self.Z, self.R
         p = "rssm.recurrent_model."
         Win = self._w(p + "mlp._model.0.weight")
-        ops.gemm(z, Win[:, :Z], x_pre, False, True)
-        ops.gemm(act, Win[:, Z:], x_pre, False, True, accumulate=True)
+        if win_t is not None:
+            ops.onehot_linear(z, act, win_t, x_pre, self.S, self.D)
+        else:
+            ops.gemm(z, Win[:, :Z], x_pre, False, True)
+            ops.gemm(act, Win[:, Z:], x_pre, False, True, accumulate=True)
         ops.ln_act_fwd(x_pre, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"), self.eps,
                        ACT_SILU, x_act)
         Wg = self._w(p + "rnn.linear.weight")
@@ -709,12 +713,20 @@ class DV3Engine:
         actions the policy gradient does not flow through the rollout."""
         ops, N, Z, R, H = self.ops, self.N, self.Z, self.R, self.H
         am = self.actor_mlp
+        # imagined z is an exact one-hot sample: its Linear is a gather over the transposed weight (refreshed here,
+        # after the world-model update)
+        gather = hasattr(ops, "onehot_linear") and self.S <= 64 and self.A <= 32
+        if gather:
+            Win = self._w("rssm.recurrent_model.mlp._model.0.weight")
+            if getattr(self, "_win_t", None) is None:
+                self._win_t = torch.empty(Win.shape[1], Win.shape[0], dtype=torch.float32, device=self.device)
+            ops.transpose2d(Win, self._win_t)
         for i in range(H + 1):
             rows = slice(i * N, (i + 1) * N)
             if i > 0:
                 prev, cur = self.traj[i - 1], self.traj[i]
                 self._recurrent_forward(prev[:, :Z], self.actions[i - 1], prev[:, Z:], self.i_x_pre, self.i_x_act,
-                                        self.i_g_pre, self.i_g_ln, cur[:, Z:])
+                                        self.i_g_pre, self.i_g_ln, cur[:, Z:], win_t=self._win_t if gather else None)
                 self._transition_forward(cur[:, Z:], self.i_tr_pre, self.i_tr_act, self.i_raw)
                 ops.cat_sample(self.i_raw, self.noise_img_state[i - 1], self.unimix, self.S, self.D, cur[:, :Z])
             # actor on traj[i]; activations are kept for the policy-gradient backward (the reference's second

@@ -579,3 +579,17 @@ class CudaOps:
                                           c_int(len(head_dims)), c_int(int(is_continuous)), c_int(int(clip_vloss)),
                                           c_int(int(normalize_adv)), c_float(clip_coef), c_float(vf_coef),
                                           c_float(ent_coef), self._st()))
+
+    # ------------------------------------------------------------------ imagination: Linear([one-hot z, a]) as a gather
+    def transpose2d(self, X, Y):
+        """Y [cols, rows] = X [rows, cols]^T (2-D views with unit inner stride)"""
+        _f32(X, Y)
+        rows, cols = X.shape
+        self._ck(self.lib.b200rl_transpose2d(_p(X), _p(Y), c_int(rows), c_int(cols), c_ll(_ld(X)), c_ll(_ld(Y)), self._st()))
+
+    def onehot_linear(self, z, act, WT, out, groups: int, classes: int):
+        _f32(z, act, WT, out)
+        M, A, N = z.shape[0], act.shape[1], WT.shape[1]
+        assert WT.is_contiguous() and WT.shape[0] == groups * classes + A and out.shape == (M, N)
+        self._ck(self.lib.b200rl_onehot_linear(_p(z), _p(act), _p(WT), _p(out), c_ll(M), c_int(groups), c_int(classes),
+                                               c_int(A), c_int(N), c_ll(_ld(z)), c_ll(_ld(act)), c_ll(_ld(out)), self._st()))

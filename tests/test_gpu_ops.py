@@ -420,3 +420,21 @@ def test_replay_gather_scatter_and_gae(ops):
     ret_c, adv_c = gae_oracle(r, v, d, nv, Tn, 0.99, 0.95)
     close(adv, adv_c, rtol=1e-5, what="gae adv")
     close(ret, ret_c, rtol=1e-5, what="gae ret")
+
+
+@pytest.mark.parametrize("M,S,D,A,N", [(1024, 32, 32, 2, 512), (7, 6, 5, 5, 24), (33, 4, 40, 1, 130)])
+def test_onehot_linear_and_transpose2d(ops, M, S, D, A, N):
+    cu, em = ops
+    g = torch.Generator().manual_seed(3)
+    z = torch.nn.functional.one_hot(torch.randint(0, D, (M, S), generator=g), D).float().reshape(M, S * D)
+    buf = torch.zeros(M, S * D + 7)                          # z lives inside a wider row, as in traj[:, :Z]
+    buf[:, : S * D] = z
+    act, W = rnd(M, A, seed=1), rnd(N, S * D + A, seed=2, scale=0.1)
+    WTc, WTg = torch.empty(S * D + A, N), torch.empty(S * D + A, N, device="cuda")
+    em.transpose2d(W, WTc)
+    cu.transpose2d(W.cuda(), WTg)
+    assert torch.equal(WTg.cpu(), WTc)
+    oc, og = torch.empty(M, N), torch.empty(M, N, device="cuda")
+    em.onehot_linear(buf[:, : S * D], act, WTc, oc, S, D)
+    cu.onehot_linear(buf.cuda()[:, : S * D], act.cuda(), WTg, og, S, D)
+    close(og, oc, rtol=1e-5, what="onehot_linear")
