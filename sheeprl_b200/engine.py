@@ -302,7 +302,10 @@ class DV3Engine:
         self.value_rows = b("value_rows", H * N)
         self.d_critic_logits = b("d_critic_logits", H * N, self.bins_c)
         # imagination step scratch (N rows)
-        self.i_x_pre, self.i_x_act = b("i_x_pre", N, self.Dx), b("i_x_act", N, self.Dx)
+        self.i_x_pre = b("i_x_pre", N, self.Dx)
+        # imagination keeps the GRU input [h | x] contiguous so that its Linear is ONE product (weights are [h, x] ordered)
+        self.i_hx = b("i_hx", N, self.R + self.Dx)
+        self.i_x_act = self.i_hx[:, self.R:]
         self.i_g_pre, self.i_g_ln = b("i_g_pre", N, 3 * R), b("i_g_ln", N, 3 * R)
         self.i_tr_pre, self.i_tr_act = b("i_tr_pre", N, self.Dt), b("i_tr_act", N, self.Dt)
         self.i_raw = b("i_raw", N, Z)
@@ -487,7 +490,7 @@ class DV3Engine:
         ops.gemm(self.d_dec_lin, self._w(p + "0.weight"), self.d_latent, False, False)
 
     # ------------------------------------------------------------------ RSSM pieces
-    def _recurrent_forward(self, z, act, h_prev, x_pre, x_act, g_pre, g_ln, h_out, win_t=None):
+    def _recurrent_forward(self, z, act, h_prev, x_pre, x_act, g_pre, g_ln, h_out, win_t=None, hx=None):
         """RecurrentModel + LayerNormGRUCell on M rows (agent.py:328-341, models.py:396-403).  `win_t`: transposed
         first-layer weight; given only when z is an exact one-hot sample (imagination), the product becomes a gather."""
         ops, Z, R = self.ops, self.Z, self.R
@@ -501,8 +504,11 @@ class DV3Engine:
         ops.ln_act_fwd(x_pre, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"), self.eps,
                        ACT_SILU, x_act)
         Wg = self._w(p + "rnn.linear.weight")
-        ops.gemm(h_prev, Wg[:, :R], g_pre, False, True)
-        ops.gemm(x_act, Wg[:, R:], g_pre, False, True, accumulate=True)
+        if hx is not None:                                   # [h | x] contiguous (x_act is its right half)
+            ops.gemm(hx, Wg, g_pre, False, True)
+        else:
+            ops.gemm(h_prev, Wg[:, :R], g_pre, False, True)
+            ops.gemm(x_act, Wg[:, R:], g_pre, False, True, accumulate=True)
         ops.ln_act_fwd(g_pre, self._w(p + "rnn.layer_norm.weight"), self._w(p + "rnn.layer_norm.bias"), self.eps,
                        ACT_NONE, g_ln)
         ops.gru_gate_fwd(g_ln, h_prev, h_out)
@@ -725,8 +731,10 @@ class DV3Engine:
             rows = slice(i * N, (i + 1) * N)
             if i > 0:
                 prev, cur = self.traj[i - 1], self.traj[i]
+                ops.copy(prev[:, Z:], self.i_hx[:, :R])
                 self._recurrent_forward(prev[:, :Z], self.actions[i - 1], prev[:, Z:], self.i_x_pre, self.i_x_act,
-                                        self.i_g_pre, self.i_g_ln, cur[:, Z:], win_t=self._win_t if gather else None)
+                                        self.i_g_pre, self.i_g_ln, cur[:, Z:], win_t=self._win_t if gather else None,
+                                        hx=self.i_hx)
                 self._transition_forward(cur[:, Z:], self.i_tr_pre, self.i_tr_act, self.i_raw)
                 ops.cat_sample(self.i_raw, self.noise_img_state[i - 1], self.unimix, self.S, self.D, cur[:, :Z])
             # actor on traj[i]; activations are kept for the policy-gradient backward (the reference's second
