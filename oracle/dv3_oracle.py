@@ -255,7 +255,10 @@ class AdamState:
 # --------------------------------------------------------------------------------------------------
 # the update step
 # --------------------------------------------------------------------------------------------------
-def draw_noise(T: int, B: int, H: int, S: int, D: int, actions_dim: Sequence[int], seed: int) -> Dict[str, Tensor]:
+def draw_noise(T: int, B: int, H: int, S: int, D: int, actions_dim: Sequence[int], seed: int,
+               is_continuous: bool = False) -> Dict[str, Tensor]:
+    """Exp(1) noise for every categorical draw; continuous actions: one N(0,1) tensor [H+1, N, sum(A)] consumed by
+    Normal.rsample (agent.py:817)."""
     g = torch.Generator().manual_seed(seed)
     N = T * B
 
@@ -266,8 +269,28 @@ def draw_noise(T: int, B: int, H: int, S: int, D: int, actions_dim: Sequence[int
         "prior": exp1(T, B, S, D),       # consumed by the reference, discarded by training (agent.py:433)
         "post": exp1(T, B, S, D),
         "img_state": exp1(H, N, S, D),
-        "img_action": [exp1(H + 1, N, ad) for ad in actions_dim],
+        "img_action": ([torch.randn(H + 1, N, int(sum(actions_dim)), generator=g)] if is_continuous
+                       else [exp1(H + 1, N, ad) for ad in actions_dim]),
     }
+
+
+def continuous_action(head: Tensor, eps_n: Tensor, acfg):
+    """Actor.forward, continuous `scaled_normal` branch (agent.py:803-825): returns (clipped action, entropy)."""
+    mean, std = torch.chunk(head, 2, -1)
+    std = (acfg.max_std - acfg.min_std) * torch.sigmoid(std + acfg.init_std) + acfg.min_std
+    act = torch.tanh(mean) + std * eps_n
+    if acfg.action_clip > 0.0:
+        clip = torch.full_like(act, acfg.action_clip)
+        act = act * (clip / torch.maximum(clip, act.abs())).detach()
+    ent = (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(std)).sum(-1)
+    return act, ent
+
+
+def reference_normal_order(noise: Dict[str, Tensor], H: int) -> List[Tensor]:
+    """N(0,1) tensors in the order the reference calls Normal.rsample with continuous actions: one per imagination
+    step (dreamer_v3.py:219,240) and one (discarded) for the re-evaluation on the whole trajectory (:273)."""
+    e = noise["img_action"][0]
+    return [e[i] for i in range(H + 1)] + [torch.zeros_like(e)]
 
 
 def reference_noise_order(noise: Dict[str, Tensor], T: int, H: int, n_heads: int) -> List[Tensor]:
@@ -303,8 +326,10 @@ def dv3_train_step(
     actions_dim: Sequence[int],
     condition_margin: float = 0.0,
     keep: bool = False,
+    is_continuous: bool = False,
 ) -> Dict[str, Tensor]:
-    """One Dreamer-V3 update (discrete actions).  Mutates the parameter dicts, optimiser states and
+    """One Dreamer-V3 update (discrete actions, or continuous `scaled_normal` actions with is_continuous=True: the
+    policy gradient then flows through the imagined rollout, dreamer_v3.py:283-284).  Mutates the parameter dicts, optimiser states and
     `moments_state` ("low","high") in place like the reference mutates its modules; returns the 13
     metrics of dreamer_v3.py:330-352 plus (keep=True) the intermediates named in SURVEY.md §8a."""
     a = cfg.algo
@@ -390,21 +415,32 @@ def dv3_train_step(
 
     # ---- imagination with the UPDATED world model (dreamer_v3.py:203-241); discrete actions: the policy
     # loss does not back-propagate through the rollout, so it runs without grad.
-    with torch.no_grad():
+    with torch.set_grad_enabled(is_continuous):
+        # world model / critic act as constants here (their gradients from the policy loss are discarded by the reference)
+        wm_c = {k: v.detach() for k, v in wm.items()}
+        critic_c = {k: v.detach() for k, v in critic.items()}
         zi = zs.detach().reshape(N, Z)
         hi = hs.detach().reshape(N, R)
         traj = [torch.cat((zi, hi), -1)]
         acts = []
 
+        ents = []
+
         def act_sample(state, i):
+            if is_continuous:      # the actor always sees a detached state (dreamer_v3.py:219,240)
+                hdn = dense_stack(actor, "model._model.", state.detach(), n_hid, eps, False)
+                head = F.linear(hdn, actor["mlp_heads.0.weight"], actor["mlp_heads.0.bias"])
+                act, ent = continuous_action(head, noise["img_action"][0][i], a.actor)
+                ents.append(ent)
+                return act
             ls = actor_logits(actor, state, n_hid, actions_dim, um, eps)
             return torch.cat([st_sample(l, 1, ad, noise["img_action"][k][i], condition_margin)
                               for k, (l, ad) in enumerate(zip(ls, actions_dim))], -1)
 
         acts.append(act_sample(traj[0], 0))
         for i in range(1, H + 1):
-            hi = recurrent_step(wm, zi, acts[-1], hi, eps)
-            zi = st_sample(transition_logits(wm, hi, S, D, um, eps), S, D, noise["img_state"][i - 1],
+            hi = recurrent_step(wm_c, zi, acts[-1], hi, eps)
+            zi = st_sample(transition_logits(wm_c, hi, S, D, um, eps), S, D, noise["img_state"][i - 1],
                            condition_margin)
             traj.append(torch.cat((zi, hi), -1))
             acts.append(act_sample(traj[-1], i))
@@ -412,9 +448,9 @@ def dv3_train_step(
         acts = torch.stack(acts)          # [H+1, N, sum(A)]
 
         # ---- dreamer_v3.py:244-260
-        values = twohot_mean(dense_stack(critic, "_model.", traj, n_hid, eps, True))
-        rew = twohot_mean(dense_stack(wm, "reward_model._model.", traj, n_hid, eps, True))
-        cont = (torch.sigmoid(dense_stack(wm, "continue_model._model.", traj, n_hid, eps, True)) > 0.5).float()
+        values = twohot_mean(dense_stack(critic_c, "_model.", traj, n_hid, eps, True))
+        rew = twohot_mean(dense_stack(wm_c, "reward_model._model.", traj, n_hid, eps, True))
+        cont = (torch.sigmoid(dense_stack(wm_c, "continue_model._model.", traj, n_hid, eps, True)) > 0.5).float()
         cont = torch.cat((cont_target.reshape(1, N, 1), cont[1:]), 0)
         # compute_lambda_values (dreamer_v3/utils.py:66-77)
         c = cont[1:] * a.gamma
@@ -429,8 +465,8 @@ def dv3_train_step(
 
         # ---- Moments (dreamer_v3/utils.py:56-63)
         mo = a.actor.moments
-        lo = torch.quantile(lam.flatten(), mo.percentile.low)
-        hi_q = torch.quantile(lam.flatten(), mo.percentile.high)
+        lo = torch.quantile(lam.detach().flatten(), mo.percentile.low)
+        hi_q = torch.quantile(lam.detach().flatten(), mo.percentile.high)
         moments_state["low"] = mo.decay * moments_state["low"] + (1 - mo.decay) * lo
         moments_state["high"] = mo.decay * moments_state["high"] + (1 - mo.decay) * hi_q
         invscale = torch.maximum(torch.tensor(1.0 / mo.max), moments_state["high"] - moments_state["low"])
@@ -438,16 +474,22 @@ def dv3_train_step(
         advantage = (lam - offset) / invscale - (values[:-1] - offset) / invscale
 
     # ---- actor loss (dreamer_v3.py:272-304)
-    ls = actor_logits(actor, traj, n_hid, actions_dim, um, eps)
-    logp = 0.0
-    ent = 0.0
-    for l, av in zip(ls, torch.split(acts, list(actions_dim), -1)):
-        lg, pr = categorical_normalise(l)
-        logp = logp + lg.gather(-1, av.argmax(-1, keepdim=True))     # [H+1,N,1]
-        ent = ent + (-(torch.clamp(lg, min=torch.finfo(lg.dtype).min) * pr).sum(-1))
-    objective = logp[:-1] * advantage
+    if is_continuous:
+        # objective = advantage, differentiated through lambda-values AND the baseline into the rollout; the entropy
+        # comes from the reference's second actor evaluation on the detached trajectory, numerically the same heads
+        objective = advantage
+        ent = torch.stack(ents)                                          # [H+1, N]
+    else:
+        ls = actor_logits(actor, traj, n_hid, actions_dim, um, eps)
+        logp = 0.0
+        ent = 0.0
+        for l, av in zip(ls, torch.split(acts, list(actions_dim), -1)):
+            lg, pr = categorical_normalise(l)
+            logp = logp + lg.gather(-1, av.argmax(-1, keepdim=True))     # [H+1,N,1]
+            ent = ent + (-(torch.clamp(lg, min=torch.finfo(lg.dtype).min) * pr).sum(-1))
+        objective = logp[:-1] * advantage
     entropy = a.actor.ent_coef * ent
-    policy_loss = -torch.mean(discount[:-1] * (objective + entropy.unsqueeze(-1)[:-1]))
+    policy_loss = -torch.mean(discount[:-1].detach() * (objective + entropy.unsqueeze(-1)[:-1]))
     policy_loss.backward()
     with torch.no_grad():
         actor_norm = clip_grad_norm([v.grad for v in actor.values()], a.actor.clip_gradients)
@@ -456,6 +498,8 @@ def dv3_train_step(
         opt_actor.step(actor, {k: v.grad for k, v in actor.items()})
 
     # ---- critic loss (dreamer_v3.py:307-327)
+    traj, lam, acts = traj.detach(), lam.detach(), acts.detach()
+    values, rew, discount, advantage = values.detach(), rew.detach(), discount.detach(), advantage.detach()
     qv_logits = dense_stack(critic, "_model.", traj[:-1], n_hid, eps, True)
     with torch.no_grad():
         tgt_vals = twohot_mean(dense_stack(target_critic, "_model.", traj[:-1], n_hid, eps, True))
@@ -499,7 +543,7 @@ def _uniform(shape, fan_in, fan_out, scale, g):
     return (torch.rand(*shape, generator=g) * 2 - 1) * lim
 
 
-def init_params(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int = 0):
+def init_params(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int = 0, is_continuous: bool = False):
     """Parameter dicts with the reference's state-dict keys/shapes and the reference's
     initialisation distributions (dreamer_v3/utils.py:143-186, agent.py:1170-1180)."""
     g = torch.Generator().manual_seed(seed)
@@ -557,8 +601,11 @@ def init_params(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int
     mlp(wm, "continue_model._model.", L, du, nh, 1, 1.0)
     actor: Dict[str, Tensor] = {}
     mlp(actor, "model._model.", L, du, nh, None, None)
-    for i, ad in enumerate(actions_dim):
-        lin(actor, f"mlp_heads.{i}", ad, du, True, 1.0)
+    if is_continuous:
+        lin(actor, "mlp_heads.0", 2 * A, du, True, 1.0)
+    else:
+        for i, ad in enumerate(actions_dim):
+            lin(actor, f"mlp_heads.{i}", ad, du, True, 1.0)
     critic: Dict[str, Tensor] = {}
     mlp(critic, "_model.", L, du, nh, a.critic.bins, 0.0)
     target = {k: v.clone() for k, v in critic.items()}
@@ -566,7 +613,7 @@ def init_params(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int
 
 
 def make_batch(cfg, actions_dim: Sequence[int], seed: int = 1, in_channels: int = 3,
-               as_uint8: bool = False) -> Dict[str, Tensor]:
+               as_uint8: bool = False, is_continuous: bool = False) -> Dict[str, Tensor]:
     """Synthetic replay batch of SURVEY.md §8d: uniform uint8 pixels, one-hot actions, N(0,1) rewards,
     Bernoulli(0.01) terminated, Bernoulli(0.02) is_first."""
     g = torch.Generator().manual_seed(seed)
@@ -575,8 +622,11 @@ def make_batch(cfg, actions_dim: Sequence[int], seed: int = 1, in_channels: int 
     rgb = torch.randint(0, 256, (T, B, in_channels, sz, sz), generator=g, dtype=torch.uint8)
     acts = []
     for ad in actions_dim:
-        idx = torch.randint(0, ad, (T, B), generator=g)
-        acts.append(F.one_hot(idx, ad).float())
+        if is_continuous:
+            acts.append(torch.rand(T, B, ad, generator=g) * 2 - 1)
+        else:
+            idx = torch.randint(0, ad, (T, B), generator=g)
+            acts.append(F.one_hot(idx, ad).float())
     return {
         cfg.algo.cnn_keys.encoder[0]: rgb if as_uint8 else rgb.float(),
         "actions": torch.cat(acts, -1),

@@ -35,6 +35,12 @@ FIXTURES = {
                  mlp_layers=1, cnn_channels_multiplier=2, recurrent_state_size=40, hidden_size=24,
                  stochastic_size=4, discrete_size=8, bins=255),
         actions_dim=(4,), perturb=0.02, steps=2),
+    # continuous actions (scaled_normal): the policy gradient flows through the imagined rollout
+    "dv3_tiny_c": dict(
+        cfg=dict(size="S", per_rank_batch_size=3, per_rank_sequence_length=4, horizon=4, dense_units=32,
+                 mlp_layers=2, cnn_channels_multiplier=4, recurrent_state_size=24, hidden_size=32,
+                 stochastic_size=6, discrete_size=5, bins=31),
+        actions_dim=(3,), perturb=0.05, steps=2, is_continuous=True),
 }
 
 
@@ -57,10 +63,11 @@ def perturbed_oracle_init(cfg, adim, seed, perturb):
 def build_case(spec, seed=0):
     cfg = make_dv3_cfg(**spec["cfg"])
     adim = tuple(spec["actions_dim"])
+    cont = bool(spec.get("is_continuous", False))
     if spec.get("oracle_init"):
         sd = perturbed_oracle_init(cfg, adim, seed, spec["perturb"])
     else:
-        _, _, wm, actor, critic, target, _ = ref_run.build_reference_agent(cfg, adim, seed=seed)
+        _, _, wm, actor, critic, target, _ = ref_run.build_reference_agent(cfg, adim, seed=seed, is_continuous=cont)
         sd = ref_run.reference_state_dicts(wm, actor, critic, target)
         g = torch.Generator().manual_seed(5)
         if spec["perturb"] > 0:
@@ -71,16 +78,18 @@ def build_case(spec, seed=0):
     a, w = cfg.algo, cfg.algo.world_model
     T, B, H = a.per_rank_sequence_length, a.per_rank_batch_size, a.horizon
     steps = spec["steps"]
-    data = [O.make_batch(cfg, adim, seed=1 + s) for s in range(steps)]
-    noise = [O.draw_noise(T, B, H, w.stochastic_size, w.discrete_size, adim, seed=10 + s) for s in range(steps)]
+    data = [O.make_batch(cfg, adim, seed=1 + s, is_continuous=cont) for s in range(steps)]
+    noise = [O.draw_noise(T, B, H, w.stochastic_size, w.discrete_size, adim, seed=10 + s, is_continuous=cont)
+             for s in range(steps)]
     # condition the noise with the oracle (in place), then run the reference on the conditioned noise
     cp = [{k: v.clone() for k, v in sd[n].items()} for n in ("wm", "actor", "critic", "target")]
     opts = [O.AdamState(cp[0], w.optimizer.lr, w.optimizer.eps), O.AdamState(cp[1], a.actor.optimizer.lr, a.actor.optimizer.eps),
             O.AdamState(cp[2], a.critic.optimizer.lr, a.critic.optimizer.eps)]
     ms = {"low": torch.zeros(()), "high": torch.zeros(())}
     for s in range(steps):
-        O.dv3_train_step(cfg, *cp, *opts, data[s], noise[s], ms, adim, condition_margin=1e-3)
-    after, metrics, moments = ref_run.run_reference_train(cfg, adim, data, noise, n_steps=steps, state=sd, seed=seed)
+        O.dv3_train_step(cfg, *cp, *opts, data[s], noise[s], ms, adim, condition_margin=1e-3, is_continuous=cont)
+    after, metrics, moments = ref_run.run_reference_train(cfg, adim, data, noise, n_steps=steps, state=sd, seed=seed,
+                                                          is_continuous=cont)
     return cfg, adim, sd, data, noise, after, metrics, moments, (cp, ms)
 
 
@@ -90,7 +99,8 @@ def main():
         cfg, adim, sd, data, noise, after, metrics, moments, _ = build_case(spec)
         for d in data:
             d["rgb"] = d["rgb"].to(torch.uint8)
-        torch.save({"cfg_kwargs": spec["cfg"], "actions_dim": adim, "init": sd, "data": data, "noise": noise,
+        torch.save({"cfg_kwargs": spec["cfg"], "actions_dim": adim, "is_continuous": bool(spec.get("is_continuous", False)),
+                    "init": sd, "data": data, "noise": noise,
                     "after": after, "metrics": metrics, "moments": moments}, os.path.join(GOLDEN, name + ".pt"))
         print("wrote", name, {k: round(v, 5) for k, v in metrics[-1].items()})
     # BASELINE config digest (weights are regenerated from seeds by the consumer through the oracle's

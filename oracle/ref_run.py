@@ -10,7 +10,7 @@ from typing import Dict, Sequence
 import torch
 
 from oracle import ref_harness
-from oracle.dv3_oracle import reference_noise_order
+from oracle.dv3_oracle import reference_noise_order, reference_normal_order
 
 
 def to_ref_cfg(cfg):
@@ -20,7 +20,8 @@ def to_ref_cfg(cfg):
     return ref_dotdict(copy.deepcopy(cfg.as_dict()))
 
 
-def build_reference_agent(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int = 0):
+def build_reference_agent(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int = 0,
+                          is_continuous: bool = False):
     ref_harness.install()
     from sheeprl.algos.dreamer_v3.agent import build_agent
 
@@ -29,7 +30,7 @@ def build_reference_agent(cfg, actions_dim: Sequence[int], in_channels: int = 3,
     sz = cfg.env.screen_size
     obs_space = {k: ref_harness.Shape((in_channels, sz, sz)) for k in cfg.algo.cnn_keys.encoder}
     torch.manual_seed(seed)
-    wm, actor, critic, target, player = build_agent(fab, tuple(actions_dim), False, rcfg, obs_space)
+    wm, actor, critic, target, player = build_agent(fab, tuple(actions_dim), is_continuous, rcfg, obs_space)
     return fab, rcfg, wm, actor, critic, target, player
 
 
@@ -41,14 +42,14 @@ def reference_state_dicts(wm, actor, critic, target) -> Dict[str, Dict[str, torc
 
 
 def run_reference_train(cfg, actions_dim, data, noise, n_steps: int = 1, in_channels: int = 3, seed: int = 0,
-                        state=None, moments_state=None):
+                        state=None, moments_state=None, is_continuous: bool = False):
     """Returns (state_dicts_after, metrics list, moments(low,high)).  `state`: optional dict of state
     dicts to load before stepping."""
     ref_harness.install()
     from sheeprl.algos.dreamer_v3 import dreamer_v3 as D
     from sheeprl.algos.dreamer_v3.utils import Moments
 
-    fab, rcfg, wm, actor, critic, target, _ = build_reference_agent(cfg, actions_dim, in_channels, seed)
+    fab, rcfg, wm, actor, critic, target, _ = build_reference_agent(cfg, actions_dim, in_channels, seed, is_continuous)
     if state is not None:
         for mod, name in ((wm, "wm"), (actor, "actor"), (critic, "critic"), (target, "target")):
             _load(mod, state[name])
@@ -70,8 +71,26 @@ def run_reference_train(cfg, actions_dim, data, noise, n_steps: int = 1, in_chan
     for s in range(n_steps):
         agg = ref_harness.RecordingAggregator()
         batch = {k: v.clone().float() for k, v in data[s].items()}
-        with ref_harness.NoiseQueue(reference_noise_order(noise[s], T, H, len(actions_dim))):
-            D.train(fab, wm, actor, critic, target, wo, ao, co, batch, agg, rcfg, False, tuple(actions_dim), moments)
+        if is_continuous:
+            # categorical draws: prior/post per step + the imagined states; Normal.rsample: the actions
+            import torch.distributions.normal as TN
+
+            cat = []
+            for t in range(T):
+                cat += [noise[s]["prior"][t], noise[s]["post"][t]]
+            cat += [noise[s]["img_state"][i] for i in range(H)]
+            normal = reference_normal_order(noise[s], H)
+            orig = TN._standard_normal
+            TN._standard_normal = lambda shape, dtype, device: normal.pop(0).reshape(shape)
+            try:
+                with ref_harness.NoiseQueue(cat):
+                    D.train(fab, wm, actor, critic, target, wo, ao, co, batch, agg, rcfg, True, tuple(actions_dim), moments)
+            finally:
+                TN._standard_normal = orig
+            assert not normal, "the reference drew fewer Normal samples than expected"
+        else:
+            with ref_harness.NoiseQueue(reference_noise_order(noise[s], T, H, len(actions_dim))):
+                D.train(fab, wm, actor, critic, target, wo, ao, co, batch, agg, rcfg, False, tuple(actions_dim), moments)
         metrics.append(agg.values)
     return (reference_state_dicts(wm, actor, critic, target), metrics,
             {"low": moments.low.detach().clone(), "high": moments.high.detach().clone()})

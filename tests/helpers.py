@@ -19,7 +19,7 @@ def clone_state(sd):
     return {n: {k: v.clone() for k, v in d.items()} for n, d in sd.items()}
 
 
-def oracle_run(cfg, adim, init, data, noise, steps, condition_margin=0.0, keep=False):
+def oracle_run(cfg, adim, init, data, noise, steps, condition_margin=0.0, keep=False, is_continuous=False):
     st = clone_state(init)
     a, w = cfg.algo, cfg.algo.world_model
     opts = [O.AdamState(st["wm"], w.optimizer.lr, w.optimizer.eps),
@@ -29,7 +29,8 @@ def oracle_run(cfg, adim, init, data, noise, steps, condition_margin=0.0, keep=F
     outs = []
     for s in range(steps):
         outs.append(O.dv3_train_step(cfg, st["wm"], st["actor"], st["critic"], st["target"], *opts, data[s], noise[s],
-                                     ms, adim, condition_margin=condition_margin, keep=keep))
+                                     ms, adim, condition_margin=condition_margin, keep=keep,
+                                     is_continuous=is_continuous))
     return st, outs, ms, opts
 
 

@@ -8,11 +8,12 @@ from tests.helpers import assert_params_close, load_fixture, oracle_run
 METRICS_RTOL = 2e-5
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c"])
 def test_oracle_matches_reference_fixture(name):
     fx, cfg = load_fixture(name)
     steps = len(fx["data"])
-    st, outs, ms, _ = oracle_run(cfg, fx["actions_dim"], fx["init"], fx["data"], fx["noise"], steps)
+    st, outs, ms, _ = oracle_run(cfg, fx["actions_dim"], fx["init"], [{k: v.float() for k, v in d.items()} for d in fx["data"]],
+                                 fx["noise"], steps, is_continuous=fx.get("is_continuous", False))
     for s in range(steps):
         for k, v in fx["metrics"][s].items():
             assert float(outs[s][k]) == pytest.approx(v, rel=METRICS_RTOL, abs=1e-6), (s, k)
