@@ -248,6 +248,24 @@ int b200rl_ppo_loss(const float* head, const float* actions, const float* old_lo
 int b200rl_onehot_linear(const float* z, const float* act, const float* WT, float* out, long long M, int S, int K, int A,
                          int N, long long ldz, long long lda, long long ldo, cudaStream_t stream);
 
+/* ---- Dreamer-V3 continuous actions (policy gradient through the imagined rollout) -------------------------
+ * Actor.forward `scaled_normal` branch agent.py:803-825: head = [mean | std_raw] (M x 2A), eps ~ N(0,1);
+ * action (row stride lda) = clip-rescaled tanh(mean) + std*eps, ent[M] = Independent(Normal).entropy(). */
+int b200rl_cont_action_fwd(const float* head, const float* eps, float* action, long long lda, float* ent, long long M,
+                           int A, float min_std, float max_std, float init_std, float clip, cudaStream_t stream);
+/* its backward: d_action (row stride ldd) and the entropy bonus d_ent[m] = ent_scale * discount[m] -> dhead */
+int b200rl_cont_action_bwd(const float* head, const float* eps, const float* d_action, long long ldd,
+                           const float* discount, float* dhead, long long M, int A, float min_std, float max_std,
+                           float init_std, float clip, float ent_scale, cudaStream_t stream);
+/* continuous objective dreamer_v3.py:276-296 + backward of compute_lambda_values (dreamer_v3/utils.py:66-77):
+ * rows[H,N] = discount*(advantage + ent_coef*entropy); d_val / d_rew [H+1,N] = d(policy_loss)/d(values, rewards) */
+int b200rl_lambda_returns_bwd(const float* cont_logit, const float* discount, const float* moments, const float* lam,
+                              const float* val, const float* ent, float* d_val, float* d_rew, float* rows, int H, int N,
+                              float gamma, float lmbda, float ent_coef, float scale, cudaStream_t stream);
+/* backward of TwoHotEncodingDistribution.mean (distribution.py:245-247): d_logits = d_mean * dsymexp * softmax' */
+int b200rl_twohot_mean_bwd(const float* logits, const float* d_mean, float* d_logits, long long M, int nb, long long ldl,
+                           long long ldd, float low, float high, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -508,3 +508,50 @@ class EmulOps:
     def onehot_linear(self, z: Tensor, act: Tensor, WT: Tensor, out: Tensor, groups: int, classes: int):
         Z = groups * classes
         out.copy_(z @ WT[:Z] + act @ WT[Z:])
+
+    # ---- Dreamer-V3 continuous actions (csrc/dv3_cont.cu)
+    def cont_action_fwd(self, head, eps, action, ent, min_std, max_std, init_std, clip):
+        A = eps.shape[1]
+        std = (max_std - min_std) * torch.sigmoid(head[:, A:] + init_std) + min_std
+        a = torch.tanh(head[:, :A]) + std * eps
+        if clip > 0:
+            a = a * (clip / torch.clamp(a.abs(), min=clip))
+        action.copy_(a)
+        if ent is not None:
+            ent.copy_((0.5 + 0.5 * math.log(2 * math.pi) + std.log()).sum(-1))
+
+    def cont_action_bwd(self, head, eps, d_action, discount, dhead, min_std, max_std, init_std, clip, ent_scale):
+        M, A = eps.shape
+        sg = torch.sigmoid(head[:, A:] + init_std)
+        std = (max_std - min_std) * sg + min_std
+        th = torch.tanh(head[:, :A])
+        a_raw = th + std * eps
+        f = clip / torch.clamp(a_raw.abs(), min=clip) if clip > 0 else torch.ones_like(a_raw)
+        da = d_action * f
+        dstd = da * eps + (ent_scale * discount.reshape(-1)[:M]).unsqueeze(-1) / std
+        dhead[:, :A] = da * (1 - th * th)
+        dhead[:, A:] = dstd * (max_std - min_std) * sg * (1 - sg)
+
+    def lambda_returns_bwd(self, cont_logit, discount, moments, lam, val, ent, gamma, lmbda, ent_coef, scale, d_val,
+                           d_rew, rows):
+        H, N = lam.shape
+        inv = 1.0 / moments[1]
+        c = (torch.sigmoid(cont_logit.reshape(H + 1, N)) > 0.5).float() * gamma
+        D, v, e = discount.reshape(H + 1, N), val.reshape(H + 1, N), ent.reshape(-1)[: H * N].reshape(H, N)
+        rows.reshape(H, N).copy_(D[:H] * ((lam - v[:H]) * inv + ent_coef * e))
+        dv, dr = d_val.reshape(H + 1, N), d_rew.reshape(H + 1, N)
+        dv.zero_(), dr.zero_()
+        G = torch.zeros(N)
+        for t in range(H):
+            G = -scale * D[t] * inv + (c[t] * lmbda * G if t > 0 else 0.0)
+            dr[t + 1] = G
+            dv[t] += scale * D[t] * inv
+            dv[t + 1] += G * c[t + 1] * (1 - lmbda)
+        dv[H] += c[H] * lmbda * G
+
+    def twohot_mean_bwd(self, logits, d_mean, low, high, d_logits):
+        nb = logits.shape[-1]
+        bins = torch.linspace(low, high, nb)
+        p = torch.softmax(logits, -1)
+        m = (p * bins).sum(-1, keepdim=True)
+        d_logits.copy_(d_mean.reshape(-1, 1) * torch.exp(m.abs()) * p * (bins - m))

@@ -109,11 +109,9 @@ def build_agent(
     critic_state: Optional[Dict[str, torch.Tensor]] = None,
     target_critic_state: Optional[Dict[str, torch.Tensor]] = None,
 ) -> Tuple[WorldModel, ParamTree, ParamTree, ParamTree, PlayerDV3]:
-    if is_continuous:
-        raise NotImplementedError("continuous actions need the imagination backward (SURVEY App. E); not built yet")
     key = cfg.algo.cnn_keys.encoder[0]
     in_channels = int(math.prod(obs_space[key].shape[:-2]))
-    eng = DV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device)
+    eng = DV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, is_continuous=is_continuous)
     g = torch.Generator().manual_seed(int(cfg.get("seed", 0) or 0))
     nh = cfg.algo.mlp_layers
     haf = bool(cfg.algo.hafner_initialization)
@@ -126,7 +124,8 @@ def build_agent(
         # last ConvTranspose2d (agent.py:1180) it is a no-op, so that layer keeps its truncated-normal init.
         assert last_dec in wm_init
     eng.wm.load(wm_init if world_model_state is None else world_model_state)
-    ac_scale = {f"mlp_heads.{i}.weight": 1.0 for i in range(len(actions_dim))} if haf else {}
+    n_heads = 1 if is_continuous else len(actions_dim)
+    ac_scale = {f"mlp_heads.{i}.weight": 1.0 for i in range(n_heads)} if haf else {}
     eng.actor.load(initial_state(eng.actor, ac_scale, g) if actor_state is None else actor_state)
     cr_scale = {f"_model.{3 * nh}.weight": 0.0} if haf else {}
     eng.critic.load(initial_state(eng.critic, cr_scale, g) if critic_state is None else critic_state)

@@ -98,9 +98,9 @@ def train(
     """One Dreamer-V3 update.  `data`: dict of `[T, B, ...]` tensors on `fabric.device` (float32 as the
     reference passes them; the image key may also be uint8).  `noise` (extra, optional): injected Exp(1)
     sampling noise for parity tests; None -> on-device Philox."""
-    if is_continuous:
-        raise NotImplementedError("continuous actions are not supported by the B200 engine yet")
     eng = _engine_of(world_model)
+    if bool(is_continuous) != eng.is_continuous:
+        raise ValueError("is_continuous differs from the value build_agent() was called with")
     if moments is not None and getattr(moments, "low", None) is not None and moments.low.data_ptr() != eng.moments_state.data_ptr():
         moments.bind(eng.moments_state)
     eng.train_step(data, noise)

@@ -32,7 +32,7 @@ ACT_NONE, ACT_SILU = 0, 1
 TWOHOT_LOW, TWOHOT_HIGH = -20.0, 20.0
 
 
-def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int):
+def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int, is_continuous: bool = False):
     """Shapes keyed by the reference's state-dict names (built in agent.py:935-1180)."""
     a, w = cfg.algo, cfg.algo.world_model
     S, D = w.stochastic_size, w.discrete_size
@@ -84,9 +84,13 @@ def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int):
     mlp(wm, "reward_model._model.", L, du, nh, w.reward_model.bins)
     mlp(wm, "continue_model._model.", L, du, nh, 1)
     mlp(actor, "model._model.", L, du, nh, None)
-    for i, ad in enumerate(actions_dim):
-        actor[f"mlp_heads.{i}.weight"] = (ad, du)
-        actor[f"mlp_heads.{i}.bias"] = (ad,)
+    if is_continuous:      # one head: [mean | std] of every action dimension (agent.py:772)
+        actor["mlp_heads.0.weight"] = (2 * A, du)
+        actor["mlp_heads.0.bias"] = (2 * A,)
+    else:
+        for i, ad in enumerate(actions_dim):
+            actor[f"mlp_heads.{i}.weight"] = (ad, du)
+            actor[f"mlp_heads.{i}.bias"] = (ad,)
     mlp(critic, "_model.", L, du, nh, a.critic.bins)
     return wm, actor, critic, dict(chans=chans, dch=dch, E=E, stages=stages)
 
@@ -130,16 +134,17 @@ class _MLP:
         return self.out[:M]
 
     def backward(self, x: torch.Tensor, dout: torch.Tensor, dx: Optional[torch.Tensor], accumulate_dx: bool,
-                 M: Optional[int] = None):
+                 M: Optional[int] = None, data_only: bool = False, group: Optional[FlatGroup] = None):
         """dout: grad wrt output logits (or wrt last activation when out_dim is None).  Parameter grads
         are written (not accumulated) into the group's grad views; dx (+)= grad wrt x."""
-        ops, g = self.eng.ops, self.g
+        ops, g = self.eng.ops, group or self.g
         M = x.shape[0] if M is None else M
         if self.out_dim is not None:
             j = 3 * self.n_hidden
             last = self.act[-1][:M]
-            ops.gemm(dout, last, g.gviews[f"{self.prefix}{j}.weight"], True, False)
-            ops.col_sum(dout, g.gviews[f"{self.prefix}{j}.bias"])
+            if not data_only:
+                ops.gemm(dout, last, g.gviews[f"{self.prefix}{j}.weight"], True, False)
+                ops.col_sum(dout, g.gviews[f"{self.prefix}{j}.bias"])
             ops.gemm(dout, g.views[f"{self.prefix}{j}.weight"], self.dact[:M], False, False)
             d = self.dact[:M]
         else:
@@ -147,9 +152,11 @@ class _MLP:
         for i in reversed(range(self.n_hidden)):
             ops.ln_act_bwd(self.pre[i][:M], g.views[f"{self.prefix}{3 * i + 1}.weight"],
                            g.views[f"{self.prefix}{3 * i + 1}.bias"], self.eps, ACT_SILU, d, self.dpre[:M],
-                           g.gviews[f"{self.prefix}{3 * i + 1}.weight"], g.gviews[f"{self.prefix}{3 * i + 1}.bias"])
+                           None if data_only else g.gviews[f"{self.prefix}{3 * i + 1}.weight"],
+                           None if data_only else g.gviews[f"{self.prefix}{3 * i + 1}.bias"])
             inp = x if i == 0 else self.act[i - 1][:M]
-            ops.gemm(self.dpre[:M], inp, g.gviews[f"{self.prefix}{3 * i}.weight"], True, False)
+            if not data_only:
+                ops.gemm(self.dpre[:M], inp, g.gviews[f"{self.prefix}{3 * i}.weight"], True, False)
             if i > 0:
                 ops.gemm(self.dpre[:M], g.views[f"{self.prefix}{3 * i}.weight"], self.dact[:M], False, False)
                 d = self.dact[:M]
@@ -158,8 +165,12 @@ class _MLP:
 
 
 class DV3Engine:
-    def __init__(self, cfg, actions_dim: Sequence[int], in_channels: int = 3, device="cuda", ops=None):
+    def __init__(self, cfg, actions_dim: Sequence[int], in_channels: int = 3, device="cuda", ops=None,
+                 is_continuous: bool = False):
         a, w = cfg.algo, cfg.algo.world_model
+        self.is_continuous = bool(is_continuous)
+        if self.is_continuous and str(cfg.distribution.get("type", "auto")).lower() not in ("auto", "scaled_normal"):
+            raise NotImplementedError("continuous actions: only distribution.type = auto / scaled_normal is built")
         if a.mlp_keys.encoder:
             raise NotImplementedError("vector (mlp_keys) observations are not implemented in the B200 engine yet")
         if w.decoupled_rssm:
@@ -191,7 +202,8 @@ class DV3Engine:
         self.img = cfg.env.screen_size
         self.key = a.cnn_keys.encoder[0]
         self.bins_r, self.bins_c = w.reward_model.bins, a.critic.bins
-        wm_s, ac_s, cr_s, meta = dv3_param_shapes(cfg, self.actions_dim, in_channels)
+        wm_s, ac_s, cr_s, meta = dv3_param_shapes(cfg, self.actions_dim, in_channels, self.is_continuous)
+        self.AW = 2 * self.A if self.is_continuous else self.A          # width of the actor head output
         self.chans, self.dch, self.E, self.stages = meta["chans"], meta["dch"], meta["E"], meta["stages"]
         self.wm = FlatGroup(wm_s, device)
         self.actor = FlatGroup(ac_s, device)
@@ -282,15 +294,15 @@ class DV3Engine:
         M1 = (H + 1) * N
         self.actions = b("img_actions", H + 1, N, A)
         self.actor_mlp = _MLP(self, self.actor, "model._model.", L, self.du, self.nh, None, M1, self.eps, "actor", True)
-        self.actor_raw = b("actor_raw", M1, A)
-        self.d_actor_raw = b("d_actor_raw", H * N, A)
+        self.actor_raw = b("actor_raw", M1, self.AW)
+        self.d_actor_raw = b("d_actor_raw", H * N, self.AW)
         self.d_actor_hidden = b("d_actor_hidden", H * N, self.du)
         self.critic_mlp = _MLP(self, self.critic, "_model.", L, self.du, self.nh, self.bins_c, M1, self.eps,
                                "critic", True)
         self.target_mlp = _MLP(self, self.target, "_model.", L, self.du, self.nh, self.bins_c, H * N, self.eps,
                                "target", False)
         self.rew_img = _MLP(self, self.wm, "reward_model._model.", L, self.du, self.nh, self.bins_r, M1, self.eps,
-                            "rew_img", False)
+                            "rew_img", self.is_continuous)     # continuous actions back-propagate through this head
         self.cont_img = _MLP(self, self.wm, "continue_model._model.", L, self.du, self.nh, 1, M1, self.eps,
                              "cont_img", False)
         self.values, self.rew_pred = b("values", H + 1, N), b("rew_pred", H + 1, N)
@@ -309,6 +321,24 @@ class DV3Engine:
         self.i_g_pre, self.i_g_ln = b("i_g_pre", N, 3 * R), b("i_g_ln", N, 3 * R)
         self.i_tr_pre, self.i_tr_act = b("i_tr_pre", N, self.Dt), b("i_tr_act", N, self.Dt)
         self.i_raw = b("i_raw", N, Z)
+        if self.is_continuous:
+            # the policy gradient flows back through the rollout (dreamer_v3.py:283-284): every step's activations
+            # are kept, plus the gradient buffers of the data-only BPTT
+            self.c_x_pre, self.c_hx = b("c_x_pre", H, N, self.Dx), b("c_hx", H, N, self.R + self.Dx)
+            self.c_g_pre, self.c_g_ln = b("c_g_pre", H, N, 3 * R), b("c_g_ln", H, N, 3 * R)
+            self.c_tr_pre, self.c_tr_act = b("c_tr_pre", H, N, self.Dt), b("c_tr_act", H, N, self.Dt)
+            self.c_raw = b("c_raw", H, N, Z)
+            self.act_ent = b("act_ent", M1)
+            self.d_values, self.d_rew = b("d_values", H + 1, N), b("d_rew", H + 1, N)
+            self.d_v_logits, self.d_r_logits = b("d_v_logits", M1, self.bins_c), b("d_r_logits", M1, self.bins_r)
+            self.d_traj = b("d_traj", H + 1, N, L)
+            self.cd_raw = b("cd_raw", N, Z)
+            self.cd_tr_act, self.cd_tr_pre = b("cd_tr_act", N, self.Dt), b("cd_tr_pre", N, self.Dt)
+            self.cd_g_ln, self.cd_g_pre = b("cd_g_ln", N, 3 * R), b("cd_g_pre", N, 3 * R)
+            self.cd_x_act, self.cd_x_pre = b("cd_x_act", N, self.Dx), b("cd_x_pre", N, self.Dx)
+            self.cd_dz, self.cd_dh = b("cd_dz", N, Z), b("cd_dh", N, R)
+            self.cd_dz_carry, self.cd_dh_carry = b("cd_dz_carry", N, Z), b("cd_dh_carry", N, R)
+            self.cd_a = b("cd_a", N, A)
         # default noise buffers (production: filled by the Philox kernel each step)
         self.noise_post = b("noise_post", T, B, Z)
         self.noise_img_state = b("noise_img_state", H, N, Z)
@@ -346,7 +376,10 @@ class DV3Engine:
             ops.increment(self.rng_t)
             ops.fill_exponential(self.noise_post.view(-1), self.rng_seed, 0, self.rng_t)
             ops.fill_exponential(self.noise_img_state.view(-1), self.rng_seed, 1, self.rng_t)
-            ops.fill_exponential(self.noise_img_action.view(-1), self.rng_seed, 2, self.rng_t)
+            if self.is_continuous:
+                ops.fill_normal(self.noise_img_action.view(-1), self.rng_seed, 2, self.rng_t)
+            else:
+                ops.fill_exponential(self.noise_img_action.view(-1), self.rng_seed, 2, self.rng_t)
         else:
             self.noise_post.copy_(noise["post"].reshape(T, B, Z))
             self.noise_img_state.copy_(noise["img_state"].reshape(H, N, Z))
@@ -708,6 +741,10 @@ class DV3Engine:
 
     # ------------------------------------------------------------------ behaviour learning
     def _actor_heads(self, hidden: torch.Tensor, raw_out: torch.Tensor):
+        if self.is_continuous:
+            self.ops.gemm(hidden, self.actor.views["mlp_heads.0.weight"], raw_out, False, True,
+                          bias=self.actor.views["mlp_heads.0.bias"])
+            return
         off = 0
         for i, ad in enumerate(self.actions_dim):
             self.ops.gemm(hidden, self.actor.views[f"mlp_heads.{i}.weight"], raw_out[:, off:off + ad], False, True,
@@ -731,12 +768,18 @@ class DV3Engine:
             rows = slice(i * N, (i + 1) * N)
             if i > 0:
                 prev, cur = self.traj[i - 1], self.traj[i]
-                ops.copy(prev[:, Z:], self.i_hx[:, :R])
-                self._recurrent_forward(prev[:, :Z], self.actions[i - 1], prev[:, Z:], self.i_x_pre, self.i_x_act,
-                                        self.i_g_pre, self.i_g_ln, cur[:, Z:], win_t=self._win_t if gather else None,
-                                        hx=self.i_hx)
-                self._transition_forward(cur[:, Z:], self.i_tr_pre, self.i_tr_act, self.i_raw)
-                ops.cat_sample(self.i_raw, self.noise_img_state[i - 1], self.unimix, self.S, self.D, cur[:, :Z])
+                if self.is_continuous:       # keep every step's activations for the backward through the rollout
+                    j = i - 1
+                    x_pre, hx, g_pre, g_ln = self.c_x_pre[j], self.c_hx[j], self.c_g_pre[j], self.c_g_ln[j]
+                    tr_pre, tr_act, raw = self.c_tr_pre[j], self.c_tr_act[j], self.c_raw[j]
+                else:
+                    x_pre, hx, g_pre, g_ln = self.i_x_pre, self.i_hx, self.i_g_pre, self.i_g_ln
+                    tr_pre, tr_act, raw = self.i_tr_pre, self.i_tr_act, self.i_raw
+                ops.copy(prev[:, Z:], hx[:, :R])
+                self._recurrent_forward(prev[:, :Z], self.actions[i - 1], prev[:, Z:], x_pre, hx[:, R:], g_pre, g_ln,
+                                        cur[:, Z:], win_t=self._win_t if gather else None, hx=hx)
+                self._transition_forward(cur[:, Z:], tr_pre, tr_act, raw)
+                ops.cat_sample(raw, self.noise_img_state[i - 1], self.unimix, self.S, self.D, cur[:, :Z])
             # actor on traj[i]; activations are kept for the policy-gradient backward (the reference's second
             # actor evaluation at dreamer_v3.py:273 recomputes exactly these numbers)
             x = self.traj[i]
@@ -747,11 +790,69 @@ class DV3Engine:
                                self.actor.views[f"model._model.{3 * l + 1}.bias"], self.eps, ACT_SILU, am.act[l][rows])
                 cur_in = am.act[l][rows]
             self._actor_heads(cur_in, self.actor_raw[rows])
+            if self.is_continuous:
+                ac = self.cfg.algo.actor
+                ops.cont_action_fwd(self.actor_raw[rows], self.noise_img_action[i], self.actions[i], self.act_ent[rows],
+                                    float(ac.min_std), float(ac.max_std), float(ac.init_std), float(ac.action_clip))
+                continue
             off = 0
             for k, ad in enumerate(self.actions_dim):
                 ops.cat_sample(self.actor_raw[rows, off:off + ad], self.noise_img_action[i, :, off:off + ad],
                                self.unimix, 1, ad, self.actions[i, :, off:off + ad])
                 off += ad
+
+
+    def _continuous_policy_gradient(self, v_logits, r_logits, c_logit):
+        """Continuous actions: objective = advantage (dreamer_v3.py:283-284), so d(policy_loss) flows from the
+        lambda-values and the baseline through the critic / reward heads into the imagined states, back through the
+        15 dynamics steps (straight-through prior samples, transition MLP, GRU, Linear([z, a])) into each step's
+        action and from there into the actor head.  World-model / critic weights are constants here (the reference
+        discards their gradients from this loss): every product is a data-gradient product."""
+        ops, N, H, Z, R, L, A = self.ops, self.N, self.H, self.Z, self.R, self.L, self.A
+        a = self.cfg.algo
+        ac = a.actor
+        M1, M0 = (H + 1) * N, H * N
+        p = "rssm.recurrent_model."
+        pt = "rssm.transition_model._model."
+        ops.lambda_returns_bwd(c_logit.view(H + 1, N), self.discount, self.moments_out, self.lam, self.values,
+                               self.act_ent, float(a.gamma), float(a.lmbda), float(ac.ent_coef), 1.0 / M0,
+                               self.d_values, self.d_rew, self.policy_rows.view(H, N))
+        ops.twohot_mean_bwd(v_logits, self.d_values.view(-1), TWOHOT_LOW, TWOHOT_HIGH, self.d_v_logits)
+        ops.twohot_mean_bwd(r_logits, self.d_rew.view(-1), TWOHOT_LOW, TWOHOT_HIGH, self.d_r_logits)
+        traj2, d_traj2 = self.traj.view(M1, L), self.d_traj.view(M1, L)
+        self.critic_mlp.backward(traj2, self.d_v_logits, d_traj2, False, data_only=True)
+        self.rew_img.backward(traj2, self.d_r_logits, d_traj2, True, data_only=True)
+        Win, Wg = self._w(p + "mlp._model.0.weight"), self._w(p + "rnn.linear.weight")
+        args = (float(ac.min_std), float(ac.max_std), float(ac.init_std), float(ac.action_clip))
+        ops.zero(self.cd_dz_carry)
+        ops.zero(self.cd_dh_carry)
+        for i in range(H, 0, -1):
+            j = i - 1
+            # total gradient of state i = heads (critic / reward on traj[i]) + what step i+1 sent back
+            ops.copy(self.d_traj[i][:, :Z], self.cd_dz)
+            ops.axpy(self.cd_dz_carry, self.cd_dz)
+            ops.copy(self.d_traj[i][:, Z:], self.cd_dh)
+            ops.axpy(self.cd_dh_carry, self.cd_dh)
+            # z_i = straight-through sample of prior(h_i) -> transition MLP -> h_i
+            ops.cat_sample_bwd(self.c_raw[j], self.cd_dz, None, self.unimix, self.S, self.D, self.cd_raw)
+            ops.gemm(self.cd_raw, self._w(pt + "3.weight"), self.cd_tr_act, False, False)
+            ops.ln_act_bwd(self.c_tr_pre[j], self._w(pt + "1.weight"), self._w(pt + "1.bias"), self.eps, ACT_SILU,
+                           self.cd_tr_act, self.cd_tr_pre, None, None)
+            ops.gemm(self.cd_tr_pre, self._w(pt + "0.weight"), self.cd_dh, False, False, accumulate=True)
+            # h_i = GRU(h_{i-1}, x_i), x_i = SiLU(LN(W_in [z_{i-1}, a_{i-1}]))
+            ops.gru_gate_bwd(self.c_g_ln[j], self.c_hx[j][:, :R], self.cd_dh, self.cd_g_ln, self.cd_dh_carry)
+            ops.ln_act_bwd(self.c_g_pre[j], self._w(p + "rnn.layer_norm.weight"), self._w(p + "rnn.layer_norm.bias"),
+                           self.eps, ACT_NONE, self.cd_g_ln, self.cd_g_pre, None, None)
+            ops.gemm(self.cd_g_pre, Wg[:, :R], self.cd_dh_carry, False, False, accumulate=True)
+            ops.gemm(self.cd_g_pre, Wg[:, R:], self.cd_x_act, False, False)
+            ops.ln_act_bwd(self.c_x_pre[j], self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"),
+                           self.eps, ACT_SILU, self.cd_x_act, self.cd_x_pre, None, None)
+            ops.gemm(self.cd_x_pre, Win[:, :Z], self.cd_dz_carry, False, False)
+            ops.gemm(self.cd_x_pre, Win[:, Z:], self.cd_a, False, False)
+            # a_{i-1}: through the clipped rsample into the actor head; entropy bonus of step i-1
+            rows = slice(j * N, (j + 1) * N)
+            ops.cont_action_bwd(self.actor_raw[rows], self.noise_img_action[j], self.cd_a, self.discount[j],
+                                self.d_actor_raw[rows], *args, -float(ac.ent_coef) / M0)
 
     def _behaviour_losses(self):
         ops, N, H, L = self.ops, self.N, self.H, self.L
@@ -772,17 +873,20 @@ class DV3Engine:
         ops.moments_update(lam_all.view(-1), self.moments_state, float(mo.decay), float(mo.max),
                            float(mo.percentile.low), float(mo.percentile.high), self.moments_out)
         # ---- actor (dreamer_v3.py:272-304)
-        ops.actor_loss_grad(self.actor_raw[:M0], self.actions.view(M1, self.A)[:M0], self.lam.view(-1),
-                            self.values.view(-1)[:M0], self.discount.view(-1)[:M0], self.moments_out,
-                            self.actions_dim, self.unimix, float(a.actor.ent_coef), 1.0 / M0, self.policy_rows,
-                            self.d_actor_raw)
+        if self.is_continuous:
+            self._continuous_policy_gradient(v_logits, r_logits, c_logit)        # fills d_actor_raw, policy_rows
+        else:
+            ops.actor_loss_grad(self.actor_raw[:M0], self.actions.view(M1, self.A)[:M0], self.lam.view(-1),
+                                self.values.view(-1)[:M0], self.discount.view(-1)[:M0], self.moments_out,
+                                self.actions_dim, self.unimix, float(a.actor.ent_coef), 1.0 / M0, self.policy_rows,
+                                self.d_actor_raw)
         ops.sum_rows(self.policy_rows.view(M0, 1), self.metrics[8:9], -1.0 / M0)
         ops.zero(self.actor.grad)
         am = self.actor_mlp
         last = am.act[-1][:M0]
         ops.zero(self.d_actor_hidden)
         off = 0
-        for i, ad in enumerate(self.actions_dim):
+        for i, ad in enumerate((self.AW,) if self.is_continuous else self.actions_dim):
             d = self.d_actor_raw[:, off:off + ad]
             ops.gemm(d, last, self.actor.gviews[f"mlp_heads.{i}.weight"], True, False)
             ops.col_sum(d, self.actor.gviews[f"mlp_heads.{i}.bias"])

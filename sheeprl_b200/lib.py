@@ -593,3 +593,36 @@ class CudaOps:
         assert WT.is_contiguous() and WT.shape[0] == groups * classes + A and out.shape == (M, N)
         self._ck(self.lib.b200rl_onehot_linear(_p(z), _p(act), _p(WT), _p(out), c_ll(M), c_int(groups), c_int(classes),
                                                c_int(A), c_int(N), c_ll(_ld(z)), c_ll(_ld(act)), c_ll(_ld(out)), self._st()))
+
+    # ------------------------------------------------------------------ Dreamer-V3 continuous actions (csrc/dv3_cont.cu)
+    def cont_action_fwd(self, head, eps, action, ent, min_std: float, max_std: float, init_std: float, clip: float):
+        _f32(head, eps, action, ent)
+        M, A = eps.shape
+        assert head.shape == (M, 2 * A) and head.is_contiguous() and eps.is_contiguous()
+        self._ck(self.lib.b200rl_cont_action_fwd(_p(head), _p(eps), _p(action), c_ll(_ld(action)), _p(ent), c_ll(M),
+                                                 c_int(A), c_float(min_std), c_float(max_std), c_float(init_std),
+                                                 c_float(clip), self._st()))
+
+    def cont_action_bwd(self, head, eps, d_action, discount, dhead, min_std: float, max_std: float, init_std: float,
+                        clip: float, ent_scale: float):
+        _f32(head, eps, d_action, discount, dhead)
+        M, A = eps.shape
+        assert head.is_contiguous() and eps.is_contiguous() and dhead.is_contiguous() and discount.numel() >= M
+        self._ck(self.lib.b200rl_cont_action_bwd(_p(head), _p(eps), _p(d_action), c_ll(_ld(d_action)), _p(discount),
+                                                 _p(dhead), c_ll(M), c_int(A), c_float(min_std), c_float(max_std),
+                                                 c_float(init_std), c_float(clip), c_float(ent_scale), self._st()))
+
+    def lambda_returns_bwd(self, cont_logit, discount, moments, lam, val, ent, gamma, lmbda, ent_coef, scale, d_val,
+                           d_rew, rows):
+        _f32(cont_logit, discount, moments, lam, val, ent, d_val, d_rew, rows)
+        H, N = lam.shape
+        self._ck(self.lib.b200rl_lambda_returns_bwd(_p(cont_logit), _p(discount), _p(moments), _p(lam), _p(val), _p(ent),
+                                                    _p(d_val), _p(d_rew), _p(rows), c_int(H), c_int(N), c_float(gamma),
+                                                    c_float(lmbda), c_float(ent_coef), c_float(scale), self._st()))
+
+    def twohot_mean_bwd(self, logits, d_mean, low: float, high: float, d_logits):
+        _f32(logits, d_mean, d_logits)
+        M, nb = logits.shape
+        self._ck(self.lib.b200rl_twohot_mean_bwd(_p(logits), _p(d_mean), _p(d_logits), c_ll(M), c_int(nb),
+                                                 c_ll(_ld(logits)), c_ll(_ld(d_logits)), c_float(low), c_float(high),
+                                                 self._st()))

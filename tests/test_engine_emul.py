@@ -9,8 +9,8 @@ from sheeprl_b200.engine import DV3Engine
 from tests.helpers import assert_params_close, load_fixture, oracle_run
 
 
-def run_engine(cfg, adim, init, data, noise, steps):
-    eng = DV3Engine(cfg, adim, in_channels=3, device="cpu", ops=EmulOps())
+def run_engine(cfg, adim, init, data, noise, steps, is_continuous=False):
+    eng = DV3Engine(cfg, adim, in_channels=3, device="cpu", ops=EmulOps(), is_continuous=is_continuous)
     eng.wm.load(init["wm"]), eng.actor.load(init["actor"]), eng.critic.load(init["critic"])
     eng.target.load(init["target"])
     outs, grads = [], []
@@ -24,13 +24,15 @@ def run_engine(cfg, adim, init, data, noise, steps):
     return eng, outs, grads
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c"])
 def test_engine_matches_oracle_and_reference(name):
     fx, cfg = load_fixture(name)
     adim = fx["actions_dim"]
     steps = len(fx["data"])
-    st, o_outs, ms, _ = oracle_run(cfg, adim, fx["init"], fx["data"], fx["noise"], steps, keep=True)
-    eng, e_outs, e_grads = run_engine(cfg, adim, fx["init"], fx["data"], fx["noise"], steps)
+    cont = fx.get("is_continuous", False)
+    fdata = [{k: v.float() for k, v in d.items()} for d in fx["data"]]
+    st, o_outs, ms, _ = oracle_run(cfg, adim, fx["init"], fdata, fx["noise"], steps, keep=True, is_continuous=cont)
+    eng, e_outs, e_grads = run_engine(cfg, adim, fx["init"], fx["data"], fx["noise"], steps, is_continuous=cont)
     # gradients of the first step (pre-clip in the engine, post-clip in the oracle -> rescale)
     for grp, max_norm in (("wm", cfg.algo.world_model.clip_gradients), ("actor", cfg.algo.actor.clip_gradients),
                           ("critic", cfg.algo.critic.clip_gradients)):

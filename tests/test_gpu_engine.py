@@ -14,10 +14,10 @@ def to_cuda(d):
     return {k: (v.cuda() if torch.is_tensor(v) else [x.cuda() for x in v]) for k, v in d.items()}
 
 
-def make_engine(cfg, adim, init):
+def make_engine(cfg, adim, init, is_continuous=False):
     from sheeprl_b200.engine import DV3Engine
 
-    eng = DV3Engine(cfg, adim, in_channels=3, device="cuda")
+    eng = DV3Engine(cfg, adim, in_channels=3, device="cuda", is_continuous=is_continuous)
     eng.wm.load(init["wm"]), eng.actor.load(init["actor"]), eng.critic.load(init["critic"])
     eng.target.load(init["target"])
     return eng
@@ -35,13 +35,16 @@ def check_grads(eng_grads, o_out, cfg, rtol):
             assert d <= rtol * max(gmax, 1e-12) + 1e-9, (grp, k, d, gmax)
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c"])
 def test_engine_cuda_matches_reference_fixture(name):
+    """dv3_tiny_c: continuous actions, policy gradient through the imagined rollout"""
     fx, cfg = load_fixture(name)
     adim = fx["actions_dim"]
     steps = len(fx["data"])
-    st, o_outs, ms, _ = oracle_run(cfg, adim, fx["init"], fx["data"], fx["noise"], steps, keep=True)
-    eng = make_engine(cfg, adim, fx["init"])
+    cont = fx.get("is_continuous", False)
+    fdata = [{k: v.float() for k, v in d.items()} for d in fx["data"]]
+    st, o_outs, ms, _ = oracle_run(cfg, adim, fx["init"], fdata, fx["noise"], steps, keep=True, is_continuous=cont)
+    eng = make_engine(cfg, adim, fx["init"], cont)
     for s in range(steps):
         batch = {k: v.clone().float().cuda() for k, v in fx["data"][s].items()}
         eng.train_step(batch, to_cuda(fx["noise"][s]))

@@ -438,3 +438,42 @@ def test_onehot_linear_and_transpose2d(ops, M, S, D, A, N):
     em.onehot_linear(buf[:, : S * D], act, WTc, oc, S, D)
     cu.onehot_linear(buf.cuda()[:, : S * D], act.cuda(), WTg, og, S, D)
     close(og, oc, rtol=1e-5, what="onehot_linear")
+
+
+def test_continuous_action_kernels(ops):
+    """csrc/dv3_cont.cu against the torch test double: scaled_normal sampling fwd/bwd, lambda-return backward,
+    two-hot mean backward."""
+    cu, em = ops
+    M, A, H, N, nb = 300, 5, 4, 75, 31
+    head, eps = rnd(M, 2 * A, seed=1) * 2, rnd(M, A, seed=2) * 1.5           # some |a| > clip
+    args = (0.1, 1.0, 2.0, 1.0)
+    ac, ec = torch.zeros(M, A + 3)[:, 3:], torch.zeros(M)
+    ag, eg = torch.zeros(M, A + 3, device="cuda")[:, 3:], torch.zeros(M, device="cuda")
+    em.cont_action_fwd(head, eps, ac, ec, *args)
+    cu.cont_action_fwd(head.cuda(), eps.cuda(), ag, eg, *args)
+    close(ag, ac, rtol=1e-5, what="cont action"), close(eg, ec, rtol=1e-5, what="cont entropy")
+    dact, disc = rnd(M, A, seed=3), torch.rand(M)
+    dc, dg = torch.zeros(M, 2 * A), torch.zeros(M, 2 * A, device="cuda")
+    em.cont_action_bwd(head, eps, dact, disc, dc, *args, -0.01)
+    cu.cont_action_bwd(head.cuda(), eps.cuda(), dact.cuda(), disc.cuda(), dg, *args, -0.01)
+    close(dg, dc, rtol=1e-5, atol=1e-6, what="cont dhead")
+    cont_logit, D = rnd(H + 1, N, seed=4), torch.rand(H + 1, N)
+    mom, lam, val, ent = torch.tensor([0.2, 1.7]), rnd(H, N, seed=5), rnd(H + 1, N, seed=6), rnd((H + 1) * N, seed=7)
+    outs_c = [torch.zeros(H + 1, N), torch.zeros(H + 1, N), torch.zeros(H, N)]
+    outs_g = [t.cuda() for t in outs_c]
+    em.lambda_returns_bwd(cont_logit, D, mom, lam, val, ent, 0.997, 0.95, 3e-4, 1.0 / (H * N), *outs_c)
+    cu.lambda_returns_bwd(cont_logit.cuda(), D.cuda(), mom.cuda(), lam.cuda(), val.cuda(), ent.cuda(), 0.997, 0.95, 3e-4,
+                          1.0 / (H * N), *outs_g)
+    for g_, c_, nme in zip(outs_g, outs_c, ("d_val", "d_rew", "rows")):
+        close(g_, c_, rtol=1e-5, atol=1e-7, what=nme)
+    logits, dm = rnd(M, nb, seed=8) * 3, rnd(M, seed=9)
+    lc, lg = torch.zeros(M, nb), torch.zeros(M, nb, device="cuda")
+    em.twohot_mean_bwd(logits, dm, -20.0, 20.0, lc)
+    cu.twohot_mean_bwd(logits.cuda(), dm.cuda(), -20.0, 20.0, lg)
+    close(lg, lc, rtol=2e-5, atol=1e-6, what="twohot mean bwd")
+    # and the emulated backward really is the derivative of the forward (autograd check of the specification)
+    lt = logits.clone().requires_grad_(True)
+    bins = torch.linspace(-20, 20, nb)
+    m = (torch.softmax(lt, -1) * bins).sum(-1)
+    (torch.sign(m) * (torch.exp(m.abs()) - 1) * dm).sum().backward()
+    close(lc, lt.grad, rtol=1e-4, atol=1e-6, what="twohot mean bwd vs autograd")
