@@ -14,6 +14,7 @@ from typing import Any, Dict, Mapping, Optional, Sequence, Tuple
 import torch
 from torch import nn
 
+from sheeprl_b200.algos.dreamer_v3.player import PlayerDV3
 from sheeprl_b200.engine import DV3Engine
 from sheeprl_b200.params import FlatGroup
 
@@ -46,18 +47,6 @@ class _Node(nn.Module):
 
 class WorldModel(ParamTree):
     """Parameter container for the world model (reference: dreamer_v2/agent.py:707-732)."""
-
-
-class PlayerDV3:
-    """Acting path placeholder (not part of this round's hot path)."""
-
-    def __init__(self, engine: DV3Engine, num_envs: int):
-        self.engine, self.num_envs = engine, num_envs
-
-    def init_states(self, reset_envs=None):
-        raise NotImplementedError("PlayerDV3 acting path is scheduled after the train() hot path (SURVEY §8f)")
-
-    get_actions = init_states
 
 
 def _trunc_normal(shape, fan_in, fan_out, g, limit_in_std):

@@ -32,3 +32,18 @@ class Moments(torch.nn.Module):
             state[1] = self.high.to(state.device)
         self.low = state[0]
         self.high = state[1]
+
+
+def prepare_obs(fabric, obs, *, cnn_keys=(), num_envs: int = 1, **kwargs):
+    """numpy observations -> device tensors `[1, num_envs, ...]` (reference: dreamer_v3/utils.py:80-91).  Image keys stay
+    uint8: `PlayerDV3.get_actions` normalises them in the obs_prep kernel, so the host->device copy is 4x smaller than
+    the reference's float32 `/255 - 0.5` tensor."""
+    out = {}
+    for k, v in obs.items():
+        t = torch.from_numpy(v.copy()).to(fabric.device)
+        if k in cnn_keys:
+            t = t.view(1, num_envs, -1, *v.shape[-2:])
+            out[k] = t if t.dtype == torch.uint8 else t.float() / 255 - 0.5
+        else:
+            out[k] = t.float().view(1, num_envs, -1)
+    return out

@@ -84,15 +84,37 @@ class SACAgent:
 
 
 class SACPlayer:
-    """Acting path placeholder."""
+    """Acting path (reference: sac/agent.py:270-314): tanh-Normal sample (or tanh(mean) when greedy) from the trainer's
+    actor parameters — the engine's flat group is shared, so there is nothing to tie or copy."""
 
     def __init__(self, engine: SACEngine):
         self.engine = engine
+        self._bufs = {}
 
-    def get_actions(self, obs, greedy: bool = False):
-        raise NotImplementedError("SACPlayer acting path is scheduled after the train() hot path (SURVEY §8f)")
+    @torch.no_grad()
+    def get_actions(self, obs: torch.Tensor, greedy: bool = False) -> torch.Tensor:
+        e, o = self.engine, self.engine.ops
+        x = obs.reshape(-1, e.O).float().contiguous()
+        E = x.shape[0]
+        if E not in self._bufs:
+            f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=e.device)  # noqa: E731
+            self._bufs[E] = (f(1, E, e.Ha), f(1, E, e.Ha), f(1, E, 2 * e.A), f(E, e.A), f(E), f(E, e.A),
+                             torch.zeros(1, dtype=torch.int32, device=e.device))
+        a1, a2, head, eps, logp, act, ctr = self._bufs[E]
+        w = e._actor_views(e.actor.views)
+        t = lambda W: W.transpose(1, 2)  # noqa: E731
+        o.bgemm(x.unsqueeze(0), t(w["W0"]), a1, bias=w["b0"], epi="relu")
+        o.bgemm(a1, t(w["W1"]), a2, bias=w["b1"], epi="relu")
+        o.bgemm(a2, t(w["W2"]), head, bias=w["b2"])
+        if greedy:
+            eps.zero_()                                       # x_t = mean  ->  tanh(mean) * scale + bias
+        else:
+            o.increment(ctr)
+            o.fill_normal(eps.view(-1), e.rng_seed + 1, 7, ctr)
+        o.sac_sample_fwd(head[0], eps, e.scale, e.abias, act, logp)
+        return act.clone().reshape(*obs.shape[:-1], e.A)
 
-    __call__ = get_actions
+    __call__ = forward = get_actions
 
 
 def build_agent(fabric, cfg: Dict[str, Any], obs_space, action_space, agent_state: Optional[Dict[str, torch.Tensor]] = None,

@@ -166,7 +166,9 @@ class _MLP:
 
 class DV3Engine:
     def __init__(self, cfg, actions_dim: Sequence[int], in_channels: int = 3, device="cuda", ops=None,
-                 is_continuous: bool = False):
+                 is_continuous: bool = False, groups=None):
+        """groups: optional (wm, actor, critic, target) FlatGroups to adopt instead of allocating new ones — the acting
+        engine of PlayerDV3 shares the trainer's parameters this way (the reference ties `.data`, agent.py:1229-1235)."""
         a, w = cfg.algo, cfg.algo.world_model
         self.is_continuous = bool(is_continuous)
         if self.is_continuous and str(cfg.distribution.get("type", "auto")).lower() not in ("auto", "scaled_normal"):
@@ -205,10 +207,13 @@ class DV3Engine:
         wm_s, ac_s, cr_s, meta = dv3_param_shapes(cfg, self.actions_dim, in_channels, self.is_continuous)
         self.AW = 2 * self.A if self.is_continuous else self.A          # width of the actor head output
         self.chans, self.dch, self.E, self.stages = meta["chans"], meta["dch"], meta["E"], meta["stages"]
-        self.wm = FlatGroup(wm_s, device)
-        self.actor = FlatGroup(ac_s, device)
-        self.critic = FlatGroup(cr_s, device)
-        self.target = FlatGroup(cr_s, device, with_optimizer=False)
+        if groups is not None:
+            self.wm, self.actor, self.critic, self.target = groups
+        else:
+            self.wm = FlatGroup(wm_s, device)
+            self.actor = FlatGroup(ac_s, device)
+            self.critic = FlatGroup(cr_s, device)
+            self.target = FlatGroup(cr_s, device, with_optimizer=False)
         self.moments_state = torch.zeros(2, dtype=torch.float32, device=device)  # (low, high)
         self.world_size = 1
         self.allreduce = None          # set by the data-parallel wrapper: fn(flat_grad_tensor)

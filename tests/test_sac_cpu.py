@@ -141,3 +141,24 @@ def test_public_api_and_state_dict_roundtrip():
     for k, v in st["losses"].items():
         assert abs(agg.v[k] - v) <= 1e-4 * max(1.0, abs(v))
     assert opts[0].state_dict()["state"][0]["step"] == 1
+
+
+def test_player_greedy_and_sampled_actions():
+    """SACPlayer (sac/agent.py:270-314): greedy = tanh(mean)*scale+bias; sampled actions stay inside the bounds"""
+    from sheeprl_b200.algos.sac.agent import SACPlayer
+
+    fx = load("sac_tiny")
+    eng = make_engine(fx)
+    player = SACPlayer(eng)
+    obs = fx["steps"][0]["data"]["observations"]
+    P = fx["init"]["actor"]
+    x = torch.relu(obs @ P["model._model.0.weight"].t() + P["model._model.0.bias"])
+    x = torch.relu(x @ P["model._model.2.weight"].t() + P["model._model.2.bias"])
+    mean = x @ P["fc_mean.weight"].t() + P["fc_mean.bias"]
+    sp = fx["spec"]
+    scale, bias = (sp["high"] - sp["low"]) / 2.0, (sp["high"] + sp["low"]) / 2.0
+    got = player.get_actions(obs, greedy=True)
+    assert got.shape == (sp["B"], sp["act_dim"])
+    assert float((got - (torch.tanh(mean) * scale + bias)).abs().max()) < 1e-5
+    a1, a2 = player.get_actions(obs), player.get_actions(obs)
+    assert not torch.equal(a1, a2) and float(a1.min()) >= sp["low"] - 1e-6 and float(a1.max()) <= sp["high"] + 1e-6
