@@ -170,6 +170,12 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
+    # Native libraries write banners to fd 1 (NCCL prints "NCCL version ..." at communicator creation): keep stdout
+    # for the ONE JSON line of the contract and send everything else to stderr until the result is ready.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     from sheeprl_b200.algos.dreamer_v3.agent import build_agent
     from sheeprl_b200.algos.dreamer_v3.dreamer_v3 import make_optimizers, train
     from sheeprl_b200.algos.dreamer_v3.utils import Moments
@@ -351,7 +357,9 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][0])[:12]},
     }
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------
