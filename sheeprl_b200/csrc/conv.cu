@@ -444,15 +444,28 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
 
 // Weight gradient on the tensor cores: dW = small^T (x) im2col(big) as ONE K-major GEMM with K = all pixels.
 // workspace: (Cs + 16*Cb) * Ppad + 16*Cs*Cb floats, Ppad = pixels rounded up to 4.
+extern "C" int b200rl_conv_wgrad_mn_supported(int NB, int h, int w, int Cs, int Cb);
 extern "C" long long b200rl_conv_wgrad_tc_workspace(int NB, int h, int w, int Cs, int Cb) {
+  if (b200rl_conv_wgrad_mn_supported(NB, h, w, Cs, Cb)) return 16LL * Cs * Cb;   // only the [16*Cb][Cs] result
   const long long P = ((long long)NB * h * w + 3) / 4 * 4;
   return (Cs + 16LL * Cb) * P + 16LL * Cs * Cb;
 }
+extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float* G, int NB, int h, int w, int Cs, int Cb,
+                                    cudaStream_t st);
+
 extern "C" int b200rl_conv_wgrad_tc(const float* small_, const float* big, float* dW, float* workspace, int NB, int h,
                                     int w, int Cs, int Cb, int accumulate, cudaStream_t st) {
   RL_CHECK_ARG(small_ && big && dW && workspace, "null pointer");
   const long long P = (long long)NB * h * w, Pp = (P + 3) / 4 * 4;
   RL_CHECK_ARG(P >= 1024 && Cs >= 48 && Cb >= 8 && P <= 2000000000LL, "shape not eligible for the tensor-core wgrad path");
+  if (b200rl_conv_wgrad_mn_supported(NB, h, w, Cs, Cb)) {
+    // operands read in place: the gathered big image and the small image are both MN-major tcgen05 operands
+    float* G = workspace;                      // [16*Cb][Cs]
+    if (int rc = b200rl_conv_wgrad_mn(small_, big, G, NB, h, w, Cs, Cb, st)) return rc;
+    wgrad_unpack_kernel<<<ceil_div(16LL * Cs * Cb, 256), 256, 0, st>>>(G, dW, Cs, Cb, accumulate);
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
   float* St = workspace;                       // [Cs][Pp]
   float* Bt = workspace + (long long)Cs * Pp;  // [16*Cb][Pp]
   float* G = Bt + 16LL * Cb * Pp;              // [16*Cb][Cs]

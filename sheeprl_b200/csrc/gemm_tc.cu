@@ -140,6 +140,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile (the operand is stored [K][MN] in global memory: transposed products without transposes).
+// For 32-bit (tf32) operands the only MN-major shared-memory layout the tensor core accepts is the 128-byte swizzle
+// with a 32-byte base (CUTLASS: Layout_MN_SW128_32B_Atom, TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 4 k-rows x
+// 128 B (32 MN floats) in which the 32-byte chunk index is XOR-ed with the row index.  A TMA box {32 MN floats, 32
+// k-rows} lands as eight such atoms (4 KB); a 128-wide tile is four of those blocks.  Descriptor: LBO = distance
+// between 32-wide MN blocks (4096 B), SBO = distance between 4-row k atoms (512 B); one K=8 instruction reads two atoms.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;                  // leading byte offset: next 32-element MN block
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: next 4-row k atom
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                            // SWIZZLE_128B_BASE32B
+  return d;
+}
+
 template <int BN>
 struct Smem {
   // every operand buffer is a whole number of 1024-byte swizzle groups
@@ -167,6 +183,9 @@ struct TileGeo {
   int chunks;              // input channels / 32
   int Cout;                // output channels
   int ksplits;             // GEMM mode: number of K splits (gridDim.z); > 1 => atomic accumulation into C
+  int a_mn, b_mn;          // GEMM mode: operand stored [K][M] / [K][N] (MN-major) instead of [M][K] / [N][K]
+  int wg;                  // GEMM mode, conv weight gradient: A rows = (tap, big channel), K = small-grid pixels gathered
+                           // from the channel-last big image by 4-D TMA boxes of 32 pixels (Cout = big channels)
 };
 
 template <int BN>
@@ -225,8 +244,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (kb >= STAGES) mbar_wait(&s.empty[st], ((kb / STAGES) - 1) & 1);
         mbar_expect_tx(&s.full[st], (uint32_t)((BM + BN) * BK * sizeof(float)));
         if (geo.mode == MODE_GEMM) {
-          tma_load_2d(s.a_hi[st], &mapA, &s.full[st], (kb_base + kb) * BK, m0);
-          tma_load_2d(s.b_hi[st], &mapB, &s.full[st], (kb_base + kb) * BK, n0);
+          const int k0 = (kb_base + kb) * BK;
+          if (geo.wg) {
+            // k0 = first of 32 raster-consecutive small pixels (one box bw x bh x bn); block j of the tile = rows of one
+            // (tap, 32-channel chunk): the same strided gather as the forward conv, read MN-major
+            const int x0 = k0 % geo.w, y0 = (k0 / geo.w) % geo.h, i0 = k0 / (geo.w * geo.h);
+            for (int j = 0; j < BM / 32; ++j) {
+              const int r0 = m0 + 32 * j, tap = r0 / geo.Cout, ch = r0 - tap * geo.Cout;
+              tma_load_4d(s.a_hi[st] + j * 1024, &mapA, &s.full[st], ch, 2 * x0 - 1 + (tap & 3), 2 * y0 - 1 + (tap >> 2), i0);
+            }
+          } else if (!geo.a_mn) tma_load_2d(s.a_hi[st], &mapA, &s.full[st], k0, m0);
+          else
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(s.a_hi[st] + j * 1024, &mapA, &s.full[st], m0 + 32 * j, k0);
+          if (!geo.b_mn) tma_load_2d(s.b_hi[st], &mapB, &s.full[st], k0, n0);
+          else
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(s.b_hi[st] + j * 1024, &mapB, &s.full[st], n0 + 32 * j, k0);
         } else {
           const int tap = kb / geo.chunks, ch = (kb - tap * geo.chunks) * BK;
           int x, y;
@@ -240,6 +272,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer (single elected lane)
     if (lane == 0) {
+      const bool a_mn = geo.a_mn != 0, b_mn = geo.b_mn != 0;
+      const uint32_t idesc = IDESC | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+      const uint64_t a_step = (a_mn ? 1024 : 32) >> 4, b_step = (b_mn ? 1024 : 32) >> 4;
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % STAGES;
         const int c = kb / CH, buf = c & 1;
@@ -253,13 +288,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t acc = tmem + (uint32_t)(buf * BN);
         const uint32_t ah = smem_u32(s.a_hi[st]), al = smem_u32(s.a_lo[st]);
         const uint32_t bh = smem_u32(s.b_hi[st]), bl = smem_u32(s.b_lo[st]);
+        // descriptors of the stage once; a k-step only advances the 14-bit start-address field (16-byte units):
+        // K-major by 32 B inside the 128-byte swizzle row, MN-major by 1024 B (two 4-row k atoms)
+        const uint64_t dah0 = a_mn ? make_desc_mn(ah) : make_desc(ah), dal0 = a_mn ? make_desc_mn(al) : make_desc(al);
+        const uint64_t dbh0 = b_mn ? make_desc_mn(bh) : make_desc(bh), dbl0 = b_mn ? make_desc_mn(bl) : make_desc(bl);
 #pragma unroll
         for (int k4 = 0; k4 < BK / 8; ++k4) {
-          const uint32_t off = k4 * 32;  // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
+          const uint64_t oa = (uint64_t)k4 * a_step, ob = (uint64_t)k4 * b_step;
           // small cross terms first, then the leading term
-          umma_tf32(acc, make_desc(ah + off), make_desc(bl + off), IDESC, !(chunk_start && k4 == 0));
-          umma_tf32(acc, make_desc(al + off), make_desc(bh + off), IDESC, 1);
-          umma_tf32(acc, make_desc(ah + off), make_desc(bh + off), IDESC, 1);
+          umma_tf32(acc, dah0 + oa, dbl0 + ob, idesc, !(chunk_start && k4 == 0));
+          umma_tf32(acc, dal0 + oa, dbh0 + ob, idesc, 1);
+          umma_tf32(acc, dah0 + oa, dbh0 + ob, idesc, 1);
         }
         umma_commit(&s.empty[st]);   // stage reusable once these MMAs have read it
         if ((kb % CH) == CH - 1 || kb == nkb - 1) umma_commit(&s.tfull[buf]);   // chunk complete
@@ -404,8 +443,8 @@ EncodeTiledFn encode_tiled() {
 }
 
 // [rows][cols] fp32, row stride ld; box = [box_rows][32], 128-byte swizzle, zero fill out of bounds
-int get_map(const float* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
-  MapKey key{ptr, rows, cols, ld, box_rows};
+int get_map(const float* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out, bool atom32 = false) {
+  MapKey key{ptr, rows, cols, ld, box_rows | (atom32 ? 1 << 16 : 0)};
   std::lock_guard<std::mutex> lk(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return B200RL_OK; }
@@ -417,7 +456,8 @@ int get_map(const float* ptr, int rows, int cols, int ld, int box_rows, CUtensor
   EncodeTiledFn enc = encode_tiled();
   if (!enc) { b200rl_set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200RL_ERR_CUDA; }
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
-                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b200rl_set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d", (int)r, rows, cols, ld);
@@ -447,8 +487,9 @@ struct Map4Hash {
 std::unordered_map<Map4Key, CUtensorMap, Map4Hash> g_maps4;
 
 // channel-last image [N][H][W][C]; box = {32 ch, bw px, bh px, bn images} sampled with element stride es in W and H
-int get_map4(const float* ptr, int C, int W, int H, int N, int bw, int bh, int bn, int es, CUtensorMap* out) {
-  Map4Key key{ptr, C, W, H, N, bw, bh, bn, es};
+int get_map4(const float* ptr, int C, int W, int H, int N, int bw, int bh, int bn, int es, CUtensorMap* out,
+             bool atom32 = false) {
+  Map4Key key{ptr, C, W, H, N, bw, bh, bn, es | (atom32 ? 1 << 8 : 0)};
   std::lock_guard<std::mutex> lk(g_maps_mu);
   auto it = g_maps4.find(key);
   if (it != g_maps4.end()) { *out = it->second; return B200RL_OK; }
@@ -461,7 +502,8 @@ int get_map4(const float* ptr, int C, int W, int H, int N, int bw, int bh, int b
   EncodeTiledFn enc = encode_tiled();
   if (!enc) { b200rl_set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200RL_ERR_CUDA; }
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box,
-                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b200rl_set_error("cuTensorMapEncodeTiled(4D) failed (%d) for image [%d,%d,%d,%d]", (int)r, N, H, W, C);
@@ -579,7 +621,7 @@ extern "C" int b200rl_conv_up_tc(const float* small_, const float* Wpacked, floa
 // multiples of 16 bytes, and enough work to fill a tile.
 extern "C" int b200rl_gemm_tc_supported(const float* A, const float* B, int M, int N, int K, int lda, int ldb,
                                         int transA, int transB) {
-  if (transA || !transB) return 0;
+  (void)transA; (void)transB;      // all four layouts: a transposed operand is read MN-major, in place
   if (M < 128 || N < 48 || K < 32) return 0;
   if ((lda & 3) || (ldb & 3)) return 0;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return 0;
@@ -592,11 +634,16 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
   RL_CHECK_ARG(b200rl_gemm_tc_supported(A, B, M, N, K, lda, ldb, transA, transB), "shape not eligible for the tensor-core path");
   const int BN = (N <= 64) ? 64 : 128;
   CUtensorMap ma, mb;
-  if (int rc = get_map(A, M, K, lda, BM, &ma)) return rc;
-  if (int rc = get_map(B, N, K, ldb, BN, &mb)) return rc;
+  // A: [M][K] (K-major) or, transposed, [K][M] (MN-major: boxes of 32 k-rows x 32 m);  B: [N][K] or [K][N]
+  if (!transA) { if (int rc = get_map(A, M, K, lda, BM, &ma)) return rc; }
+  else         { if (int rc = get_map(A, K, M, lda, 32, &ma, true)) return rc; }
+  if (transB)  { if (int rc = get_map(B, N, K, ldb, BN, &mb)) return rc; }
+  else         { if (int rc = get_map(B, K, N, ldb, 32, &mb, true)) return rc; }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   TileGeo g = {};
   g.mode = MODE_GEMM;
+  g.a_mn = transA ? 1 : 0;
+  g.b_mn = transB ? 0 : 1;
   g.ksplits = 1;
   const int tiles = grid.x * grid.y, nkb = (K + BK - 1) / BK;
   if (tiles < 120 && nkb >= 16) {
@@ -620,6 +667,53 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
     const size_t smem = sizeof(Smem<128>) + 1024;
     RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate, g);
+  }
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+// ---- convolution weight gradient on the tensor cores, operands read in place (no im2col, no transposes):
+//   G[(tap, cb), cs] = sum over small pixels p of big[patch(p)][tap][cb] * small[p][cs]
+// A = gathered big image, MN-major (rows (tap, cb), K = pixels); B = small [P][Cs], MN-major; split-K over pixels.
+extern "C" int b200rl_conv_wgrad_mn_supported(int NB, int h, int w, int Cs, int Cb) {
+  if (w <= 0 || h <= 0 || (w & (w - 1)) || (h & (h - 1))) return 0;
+  const long long P = (long long)NB * h * w;
+  if (Cb % 32 || Cs < 48 || Cs % 4 || P % 32 || P < 1024 || P > 2000000000LL) return 0;
+  // the 32 pixels of a k-block must be one box: part of a row, whole rows of one image, or whole images
+  const int bw = w < 32 ? w : 32, bh = (32 / bw) < h ? (32 / bw) : h, bn = 32 / (bw * bh);
+  return (bw * bh * bn == 32) && (NB % bn == 0);
+}
+
+extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float* G, int NB, int h, int w, int Cs, int Cb,
+                                    cudaStream_t st) {
+  RL_CHECK_ARG(small_ && big && G, "null pointer");
+  RL_CHECK_ARG(b200rl_conv_wgrad_mn_supported(NB, h, w, Cs, Cb), "shape not eligible for the in-place wgrad path");
+  const int P = NB * h * w, M = 16 * Cb, N = Cs;
+  TileGeo g = {};
+  g.mode = MODE_GEMM; g.a_mn = 1; g.b_mn = 1; g.wg = 1;
+  g.h = h; g.w = w; g.NB = NB; g.Cout = Cb;
+  g.bw = w < 32 ? w : 32; g.bh = (32 / g.bw) < h ? (32 / g.bw) : h; g.bn = 32 / (g.bw * g.bh);
+  CUtensorMap ma, mb;
+  if (int rc = get_map4(big, Cb, 2 * w, 2 * h, NB, g.bw, g.bh, g.bn, 2, &ma, true)) return rc;
+  if (int rc = get_map(small_, P, Cs, Cs, 32, &mb, true)) return rc;
+  const int BN = (N <= 64) ? 64 : 128;
+  dim3 grid((N + BN - 1) / BN, M / BM);
+  const int tiles = grid.x * grid.y, nkb = P / BK;
+  int sp = (2 * kNumSMs + tiles - 1) / tiles;
+  if (sp > nkb / 8) sp = nkb / 8;
+  if (sp < 1) sp = 1;
+  const int per = (nkb + sp - 1) / sp;
+  g.ksplits = (nkb + per - 1) / per;
+  grid.z = g.ksplits;
+  if (g.ksplits > 1) init_c_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(G, nullptr, M, N, N, 0);
+  if (BN == 64) {
+    const size_t smem = sizeof(Smem<64>) + 1024;
+    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma, mb, G, nullptr, M, N, P, N, 0, g);
+  } else {
+    const size_t smem = sizeof(Smem<128>) + 1024;
+    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, G, nullptr, M, N, P, N, 0, g);
   }
   RL_CHECK_LAUNCH();
   return B200RL_OK;

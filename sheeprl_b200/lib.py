@@ -121,9 +121,7 @@ class CudaOps:
         assert (A.shape[1] if transA else A.shape[0]) == M, (A.shape, C.shape, transA)
         assert (B.shape[0] if transB else B.shape[1]) == N and (B.shape[1] if transB else B.shape[0]) == K, \
             (A.shape, B.shape, C.shape, transA, transB)
-        if self.use_tc and (transA or not transB) and M >= 128 and N >= 48 and K >= 256 and \
-                2.0 * M * N * K >= 2e8 and self._gemm_via_transposes(A, B, C, M, N, K, transA, transB, bias, accumulate):
-            return
+        # every layout goes to one entry point: transposed operands are read in place as MN-major tcgen05 operands
         self._ck(self.lib.b200rl_gemm_f32(_p(A), _p(B), _p(C), _p(bias), c_int(M), c_int(N), c_int(K), c_int(_ld(A)),
                                           c_int(_ld(B)), c_int(_ld(C)), c_int(int(transA)), c_int(int(transB)),
                                           c_int(int(accumulate)), self._st()))
@@ -134,32 +132,6 @@ class CudaOps:
             buf = torch.empty(numel, dtype=torch.float32, device=self.device)
             self._scratch_bufs[slot] = buf
         return buf
-
-    def _gemm_via_transposes(self, A, B, C, M, N, K, transA, transB, bias, accumulate) -> bool:
-        """Input-gradient (A @ W) and weight-gradient (dY^T @ X) products on the tensor cores: the operand(s) whose
-        reduction index is not contiguous are transposed into scratch (K-major), then the NT tcgen05 kernel runs
-        (split-K over the long reduction of weight gradients)."""
-        Kp = (K + 3) // 4 * 4
-        if transA:   # A is [K, M]
-            At = self._scratch("At", M * Kp)
-            self._ck(self.lib.b200rl_transpose2d(_p(A), _p(At), c_int(K), c_int(M), c_ll(_ld(A)), c_ll(Kp), self._st()))
-            a_ptr, lda = At.data_ptr(), Kp
-        else:
-            if _ld(A) % 4 or A.data_ptr() % 16:
-                return False
-            a_ptr, lda = A.data_ptr(), _ld(A)
-        if not transB:   # B is [K, N]
-            Bt = self._scratch("Bt", N * Kp)
-            self._ck(self.lib.b200rl_transpose2d(_p(B), _p(Bt), c_int(K), c_int(N), c_ll(_ld(B)), c_ll(Kp), self._st()))
-            b_ptr, ldb = Bt.data_ptr(), Kp
-        else:
-            if _ld(B) % 4 or B.data_ptr() % 16:
-                return False
-            b_ptr, ldb = B.data_ptr(), _ld(B)
-        self._ck(self.lib.b200rl_gemm_tc(c_void_p(a_ptr), c_void_p(b_ptr), _p(C), _p(bias), c_int(M), c_int(N), c_int(K),
-                                         c_int(lda), c_int(ldb), c_int(_ld(C)), c_int(0), c_int(1),
-                                         c_int(int(accumulate)), self._st()))
-        return True
 
     def col_sum(self, X, out, accumulate: bool = False):
         _f32(X, out)
@@ -236,7 +208,7 @@ class CudaOps:
         NB, h, w, Cs = small.shape
         Cb = big.shape[-1]
         assert tuple(big.shape) == (NB, 2 * h, 2 * w, Cb) and tuple(dW.shape) == (Cs, Cb, 4, 4)
-        if self.use_tc and NB * h * w >= 4096 and Cs >= 48 and Cb >= 8:
+        if self.use_tc and NB * h * w >= 1024 and Cs >= 48 and Cb >= 8:
             self.lib.b200rl_conv_wgrad_tc_workspace.restype = c_ll
             n = int(self.lib.b200rl_conv_wgrad_tc_workspace(c_int(NB), c_int(h), c_int(w), c_int(Cs), c_int(Cb)))
             ws = self._scratch("wgrad", n)

@@ -47,9 +47,11 @@ GEMM_SHAPES = [
     # tensor-core (tcgen05 3xTF32) eligible: NT, M >= 256, N >= 48, 16-byte aligned rows
     (16384, 512, 1536, False, True), (1024, 255, 512, False, True), (15360, 512, 512, False, True),
     (1000, 72, 40, False, True), (257, 129, 36, False, True), (1024, 4096, 1536, False, True),
-    # routed to the tensor cores through K-major transposes: input gradients (NN) and weight gradients (TN, split-K)
+    # transposed operands are read in place as MN-major tcgen05 operands: input gradients (NN), weight gradients (TN)
     (16384, 1536, 512, False, False), (1024, 512, 255, False, False), (512, 1536, 16384, True, False),
     (255, 512, 15360, True, False), (4096, 1536, 1024, True, False), (1024, 4608, 512, False, False),
+    # MN-major operands with ragged tiles in every dimension (TMA zero fill on both box axes)
+    (257, 129, 100, True, False), (300, 200, 68, False, False), (129, 52, 36, True, True), (1024, 1024, 1026, True, False),
 ]
 
 
@@ -141,7 +143,9 @@ CONV_SHAPES = [(3, 8, 8, 16, 8), (2, 4, 4, 32, 16), (5, 16, 16, 4, 3), (2, 32, 3
                # thin big-image side (conv_thin.cu): partial / multiple 32-pixel row tiles, every channel-group count
                (3, 16, 16, 64, 3), (2, 40, 40, 96, 3), (1, 32, 32, 48, 3), (2, 8, 8, 32, 1), (2, 8, 8, 64, 4),
                # tensor-core implicit-GEMM eligible (gathered image has a multiple of 32 channels, grid tiles by 128 px)
-               (8, 4, 4, 64, 32), (2, 32, 32, 32, 64), (4, 16, 16, 128, 64), (16, 8, 8, 256, 128), (24, 4, 4, 96, 32)]
+               (8, 4, 4, 64, 32), (2, 32, 32, 32, 64), (4, 16, 16, 128, 64), (16, 8, 8, 256, 128), (24, 4, 4, 96, 32),
+               # weight gradient with operands read in place (MN-major tcgen05): k-block = part of a row / rows / images
+               (64, 4, 4, 256, 128), (2, 32, 32, 64, 32), (1, 64, 64, 48, 32), (32, 8, 8, 128, 64)]
 
 
 @pytest.mark.parametrize("NB,h,w,Cs,Cb", CONV_SHAPES)
