@@ -184,6 +184,7 @@ struct TileGeo {
   int Cout;                // output channels
   int ksplits;             // GEMM mode: number of K splits (gridDim.z); > 1 => atomic accumulation into C
   int a_mn, b_mn;          // GEMM mode: operand stored [K][M] / [K][N] (MN-major) instead of [M][K] / [N][K]
+  int mtiles;              // number of M tiles; a CTA walks tiles blockIdx.y, blockIdx.y + gridDim.y, ... (persistent)
   int wg;                  // GEMM mode, conv weight gradient: A rows = (tap, big channel), K = small-grid pixels gathered
                            // from the channel-last big image by 4-D TMA boxes of 32 pixels (Cout = big channels)
 };
@@ -195,7 +196,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem<BN>& s = *reinterpret_cast<Smem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int n0 = blockIdx.x * BN;
+  const int mtiles = geo.mtiles, tstride = gridDim.y;
   // split-K (GEMM mode): blockIdx.z owns k-blocks [kb_base, kb_base + nkb); partial sums are atomically added
   int kb_base = 0, nkb = (K + BK - 1) / BK;
   if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
@@ -204,15 +206,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     nkb = min(per, nkb - kb_base);
   }
   const int nchunks = (nkb + CH - 1) / CH;
-  // conv modes: this CTA's tile origin on the small-image grid; blockIdx.z = output parity class (up)
-  int tn0 = 0, ty0 = 0, tx0 = 0;
+  // conv modes: a tile's origin on the small-image grid; blockIdx.z = output parity class (up)
   const int py = (int)blockIdx.z >> 1, px = (int)blockIdx.z & 1;
-  if (geo.mode != MODE_GEMM) {
-    const int id = blockIdx.y;
+  auto tile_origin = [&](int id, int& tx0, int& ty0, int& tn0) {
     tx0 = (id % geo.tiles_x) * geo.bw;
     ty0 = ((id / geo.tiles_x) % geo.tiles_y) * geo.bh;
     tn0 = (id / (geo.tiles_x * geo.tiles_y)) * geo.bn;
-  }
+  };
   constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers; power of two >= 32 (BN in {64,128})
   constexpr int ACC_COLS = BN / 2;         // columns per accumulator warp (two warps share a TMEM lane quarter)
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -239,9 +239,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(&s.empty[st], ((kb / STAGES) - 1) & 1);
+      int it = 0;                                  // k-blocks issued so far, across tiles: stage / phase bookkeeping
+      for (int tile = blockIdx.y; tile < mtiles; tile += tstride) {
+      const int m0 = tile * BM;
+      int tx0 = 0, ty0 = 0, tn0 = 0;
+      if (geo.mode != MODE_GEMM) tile_origin(tile, tx0, ty0, tn0);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int st = it % STAGES;
+        if (it >= STAGES) mbar_wait(&s.empty[st], ((it / STAGES) - 1) & 1);
         mbar_expect_tx(&s.full[st], (uint32_t)((BM + BN) * BK * sizeof(float)));
         if (geo.mode == MODE_GEMM) {
           const int k0 = (kb_base + kb) * BK;
@@ -268,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tma_load_2d(s.b_hi[st], &mapB, &s.full[st], kb * BK, n0 + (geo.mode == MODE_UP ? (int)blockIdx.z * geo.Cout : 0));
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single elected lane)
@@ -275,15 +281,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const bool a_mn = geo.a_mn != 0, b_mn = geo.b_mn != 0;
       const uint32_t idesc = IDESC | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
       const uint64_t a_step = (a_mn ? 1024 : 32) >> 4, b_step = (b_mn ? 1024 : 32) >> 4;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % STAGES;
-        const int c = kb / CH, buf = c & 1;
+      int it = 0, gc0 = 0;                         // k-blocks / TMEM chunks issued so far, across tiles
+      for (int tile = blockIdx.y; tile < mtiles; tile += tstride, gc0 += nchunks)
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int st = it % STAGES;
+        const int c = gc0 + kb / CH, buf = c & 1;
         const bool chunk_start = (kb % CH) == 0;
         if (chunk_start && c >= 2) {           // the accumulator warps must have drained this TMEM buffer
           mbar_wait(&s.tempty[buf], ((c >> 1) - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        mbar_wait(&s.split[st], (kb / STAGES) & 1);
+        mbar_wait(&s.split[st], (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem + (uint32_t)(buf * BN);
         const uint32_t ah = smem_u32(s.a_hi[st]), al = smem_u32(s.a_lo[st]);
@@ -307,7 +315,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp >= SPLIT_WARP0 && warp < ACC_WARP0) {
     // ===== splitters: hi/lo decomposition of each landed stage (layout-agnostic, in place)
     const int t = threadIdx.x - SPLIT_WARP0 * 32;
-    for (int kb = 0; kb < nkb; ++kb) {
+    int ntl = 0;
+    for (int tile = blockIdx.y; tile < mtiles; tile += tstride) ++ntl;
+    const int total_kb = ntl * nkb;
+    for (int kb = 0; kb < total_kb; ++kb) {
       const int st = kb % STAGES;
       mbar_wait(&s.full[st], (kb / STAGES) & 1);
       float4* ah = reinterpret_cast<float4*>(s.a_hi[st]);
@@ -344,11 +355,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp >= ACC_WARP0) {
     // ===== accumulators + epilogue.  Warp (q, half): TMEM lanes [32q, 32q+32), columns [half*BN/2, +BN/2).
     const int q = warp & 3, half = (warp - ACC_WARP0) >> 2;
+    int gc0 = 0;
+    for (int tile = blockIdx.y; tile < mtiles; tile += tstride, gc0 += nchunks) {
+    const int m0 = tile * BM;
+    int tx0 = 0, ty0 = 0, tn0 = 0;
+    if (geo.mode != MODE_GEMM) tile_origin(tile, tx0, ty0, tn0);
     float acc[ACC_COLS];
 #pragma unroll
     for (int j = 0; j < ACC_COLS; ++j) acc[j] = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const int buf = c & 1;
+    for (int cl = 0; cl < nchunks; ++cl) {
+      const int c = gc0 + cl, buf = c & 1;
       mbar_wait(&s.tfull[buf], (c >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -401,6 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
     }
+    }   // tile loop
   }
   __syncthreads();
   if (warp == 2) {
@@ -525,6 +542,18 @@ bool conv_tile(int h, int w, int NB, int* bw, int* bh, int* bn) {
   return (w % *bw == 0) && (h % *bh == 0) && (*bw * *bh * *bn == 128) && (NB % *bn == 0);
 }
 
+// Persistent scheduling: with one CTA per SM (the operand stages fill shared memory) a launch of many short tiles pays
+// TMEM allocation, barrier setup, pipeline fill and an un-overlapped epilogue per tile.  When there are more than two
+// waves of tiles, launch about one CTA per SM and let each walk its M tiles (the epilogue of a tile overlaps the main
+// loop of the next through the double-buffered TMEM accumulator).
+static unsigned persistent_grid_y(int mtiles, unsigned gx, unsigned gz) {
+  const long long total = (long long)mtiles * gx * gz;
+  if (total <= 2LL * kNumSMs) return (unsigned)mtiles;
+  unsigned gy = kNumSMs / (gx * gz);
+  if (gy < 1) gy = 1;
+  return gy < (unsigned)mtiles ? gy : (unsigned)mtiles;
+}
+
 __global__ void conv_pack_down_kernel(const float* __restrict__ W, float* __restrict__ P, int Cs, int Cb) {
   // P[cs][tap][cb] = W[cs][cb][tap]
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,7 +600,9 @@ int launch_conv(int mode, const float* img, const float* Wp, float* out, const f
   const int brows = mode == MODE_UP ? 4 * Cout : Cout;
   if (int rc = get_map(Wp, brows, K, K, BN, &mb)) return rc;
   const int mtiles = g.tiles_x * g.tiles_y * (NB / g.bn);
-  dim3 grid((Cout + BN - 1) / BN, mtiles, mode == MODE_UP ? 4 : 1);
+  g.mtiles = mtiles;
+  dim3 grid((Cout + BN - 1) / BN, 1, mode == MODE_UP ? 4 : 1);
+  grid.y = persistent_grid_y(mtiles, grid.x, grid.z);
   const int M = NB * h * w;  // unused by conv addressing; row validity comes from geo
   if (BN == 64) {
     const size_t smem = sizeof(Smem<64>) + 1024;
@@ -659,6 +690,8 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
       init_c_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(C, bias, M, N, ldc, accumulate);
     }
   }
+  g.mtiles = (int)grid.y;
+  grid.y = persistent_grid_y(g.mtiles, grid.x, grid.z);
   if (BN == 64) {
     const size_t smem = sizeof(Smem<64>) + 1024;
     RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -705,6 +738,7 @@ extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float
   const int per = (nkb + sp - 1) / sp;
   g.ksplits = (nkb + per - 1) / per;
   grid.z = g.ksplits;
+  g.mtiles = (int)grid.y;
   if (g.ksplits > 1) init_c_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(G, nullptr, M, N, N, 0);
   if (BN == 64) {
     const size_t smem = sizeof(Smem<64>) + 1024;
