@@ -246,9 +246,10 @@ def run_b200(args):
     eng.ops = prof._inner
     barrier()
 
-    # ---- CUDA graph of the whole update (single GPU; multi-GPU keeps eager launches around NCCL)
+    # ---- CUDA graph of the whole update; at N > 1 the NCCL all-reduces / all-gather are captured with it
+    # (B200RL_BENCH_EAGER_NCCL=1 keeps eager launches around NCCL)
     graph = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph and (world == 1 or os.environ.get("B200RL_BENCH_EAGER_NCCL", "0") != "1"):
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -442,6 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--graph-nccl", action="store_true", help="(default now) capture the step incl. the NCCL collectives in a CUDA graph at N > 1")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
