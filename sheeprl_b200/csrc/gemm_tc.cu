@@ -40,7 +40,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BK = 32, STAGES = 4;   // 4 x 48 KB operand stages; TMEM: 2 accumulators + 4 x (A hi | lo) = 512 columns
 constexpr int NTHREADS = 512;                       // 16 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 split, 8-15 accumulate
 constexpr int SPLIT_WARP0 = 4, NSPLIT_THREADS = 128;
 constexpr int ACC_WARP0 = 8, NACC_WARPS = 8;
@@ -111,6 +111,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = tile row, one 32-bit column per k element), B from a shared-memory descriptor
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -159,8 +182,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 template <int BN>
 struct Smem {
   // every operand buffer is a whole number of 1024-byte swizzle groups
-  float a_hi[STAGES][BM * BK];
-  float a_lo[STAGES][BM * BK];
+  float a_hi[STAGES][BM * BK];   // raw A tiles; their hi / lo halves go to TENSOR MEMORY (see kATmem below)
   float b_hi[STAGES][BN * BK];
   float b_lo[STAGES][BN * BK];
   uint64_t full[STAGES], split[STAGES], empty[STAGES], tfull[2], tempty[2];
@@ -213,7 +235,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     ty0 = ((id / geo.tiles_x) % geo.tiles_y) * geo.bh;
     tn0 = (id / (geo.tiles_x * geo.tiles_y)) * geo.bn;
   };
-  constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers; power of two >= 32 (BN in {64,128})
+  // Tensor memory: two accumulator buffers (2*BN columns) + per stage the A operand as hi | lo (2 x 32 columns): the
+  // A halves are read by the tensor core from TMEM instead of shared memory, which removes half of the operand traffic
+  // of a shared-memory-bandwidth-bound kernel (ncu: LSU + tensor-core wavefronts = 84 % of the smem pipe).
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t A_TMEM0 = 2 * BN;     // column of stage 0's A hi; stage st: + 64*st; lo: + 32
   constexpr int ACC_COLS = BN / 2;         // columns per accumulator warp (two warps share a TMEM lane quarter)
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -278,9 +304,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer (single elected lane)
     if (lane == 0) {
-      const bool a_mn = geo.a_mn != 0, b_mn = geo.b_mn != 0;
-      const uint32_t idesc = IDESC | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
-      const uint64_t a_step = (a_mn ? 1024 : 32) >> 4, b_step = (b_mn ? 1024 : 32) >> 4;
+      const bool b_mn = geo.b_mn != 0;
+      // A comes from tensor memory (always [row][k]): only B's major bit depends on the operand layout
+      const uint32_t idesc = IDESC | ((uint32_t)b_mn << 16);
+      const uint64_t b_step = (b_mn ? 1024 : 32) >> 4;
       int it = 0, gc0 = 0;                         // k-blocks / TMEM chunks issued so far, across tiles
       for (int tile = blockIdx.y; tile < mtiles; tile += tstride, gc0 += nchunks)
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -294,19 +321,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(&s.split[st], (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem + (uint32_t)(buf * BN);
-        const uint32_t ah = smem_u32(s.a_hi[st]), al = smem_u32(s.a_lo[st]);
         const uint32_t bh = smem_u32(s.b_hi[st]), bl = smem_u32(s.b_lo[st]);
-        // descriptors of the stage once; a k-step only advances the 14-bit start-address field (16-byte units):
-        // K-major by 32 B inside the 128-byte swizzle row, MN-major by 1024 B (two 4-row k atoms)
-        const uint64_t dah0 = a_mn ? make_desc_mn(ah) : make_desc(ah), dal0 = a_mn ? make_desc_mn(al) : make_desc(al);
+        // B descriptors of the stage once; a k-step only advances the 14-bit start-address field (16-byte units):
+        // K-major by 32 B inside the 128-byte swizzle row, MN-major by 1024 B (two 4-row k atoms).  A: 8 TMEM columns.
         const uint64_t dbh0 = b_mn ? make_desc_mn(bh) : make_desc(bh), dbl0 = b_mn ? make_desc_mn(bl) : make_desc(bl);
+        const uint32_t ta_hi = tmem + A_TMEM0 + 64u * (uint32_t)st, ta_lo = ta_hi + 32u;
 #pragma unroll
         for (int k4 = 0; k4 < BK / 8; ++k4) {
-          const uint64_t oa = (uint64_t)k4 * a_step, ob = (uint64_t)k4 * b_step;
+          const uint64_t ob = (uint64_t)k4 * b_step;
           // small cross terms first, then the leading term
-          umma_tf32(acc, dah0 + oa, dbl0 + ob, idesc, !(chunk_start && k4 == 0));
-          umma_tf32(acc, dal0 + oa, dbh0 + ob, idesc, 1);
-          umma_tf32(acc, dah0 + oa, dbh0 + ob, idesc, 1);
+          umma_tf32_ts(acc, ta_hi + 8u * k4, dbl0 + ob, idesc, !(chunk_start && k4 == 0));
+          umma_tf32_ts(acc, ta_lo + 8u * k4, dbh0 + ob, idesc, 1);
+          umma_tf32_ts(acc, ta_hi + 8u * k4, dbh0 + ob, idesc, 1);
         }
         umma_commit(&s.empty[st]);   // stage reusable once these MMAs have read it
         if ((kb % CH) == CH - 1 || kb == nkb - 1) umma_commit(&s.tfull[buf]);   // chunk complete
@@ -315,25 +341,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp >= SPLIT_WARP0 && warp < ACC_WARP0) {
     // ===== splitters: hi/lo decomposition of each landed stage (layout-agnostic, in place)
     const int t = threadIdx.x - SPLIT_WARP0 * 32;
+    const bool a_mn_tile = geo.a_mn != 0;          // GEMM with transposed A, or the conv weight gradient
     int ntl = 0;
     for (int tile = blockIdx.y; tile < mtiles; tile += tstride) ++ntl;
     const int total_kb = ntl * nkb;
     for (int kb = 0; kb < total_kb; ++kb) {
       const int st = kb % STAGES;
       mbar_wait(&s.full[st], (kb / STAGES) & 1);
-      float4* ah = reinterpret_cast<float4*>(s.a_hi[st]);
-      float4* al = reinterpret_cast<float4*>(s.a_lo[st]);
+      {
+        // A: thread t owns tile row t = TMEM lane t (splitter warp w reads/writes lanes [32w, 32w+32)).  It gathers the
+        // row's 32 k values from the swizzled tile, stores them (the raw bits are the hi operand: the datapath truncates)
+        // and lo = x - trunc(x) into this stage's TMEM columns.
+        const char* base = reinterpret_cast<const char*>(s.a_hi[st]);
+        uint32_t hi[32], lo[32];
+        if (!a_mn_tile) {
+          // K-major tile: row t = 128 B, 16-byte chunk c stored at position c ^ (t & 7)
+          const char* row = base + t * 128;
 #pragma unroll
-      for (int i = 0; i < BM * BK / 4 / NSPLIT_THREADS; ++i) {
-        const int idx = t + i * NSPLIT_THREADS;
-        const float4 v = ah[idx];
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-        // hi is NOT written back: the TF32 datapath ignores the 13 low mantissa bits, so the raw tile *is* the hi operand
-        al[idx] = l;
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ (t & 7)) << 4));
+            hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+            hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+          }
+        } else {
+          // MN-major tile: block t/32 (4 KB), k-row k = 128 B, element t%32 inside it with the 32-byte chunk index
+          // XOR-ed by k % 4 (SWIZZLE_128B_BASE32B)
+          const char* blk = base + (t >> 5) * 4096 + ((t & 7) << 2);
+          const int ch = (t & 31) >> 3;
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            hi[k] = *reinterpret_cast<const uint32_t*>(blk + k * 128 + ((ch ^ (k & 3)) << 5));
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float x = __uint_as_float(hi[k]);
+          lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
+        }
+        const uint32_t ta = tmem + (((uint32_t)(t & ~31)) << 16) + A_TMEM0 + 64u * (uint32_t)st;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       float4* bh = reinterpret_cast<float4*>(s.b_hi[st]);
       float4* bl = reinterpret_cast<float4*>(s.b_lo[st]);
@@ -349,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         bl[idx] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM stores ordered before the arrival
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.split[st]);
     }
