@@ -379,8 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         const uint32_t ta = tmem + (((uint32_t)(t & ~31)) << 16) + A_TMEM0 + 64u * (uint32_t)st;
         tmem_st32(ta, hi);
-        tmem_st32(ta + 32u, lo);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tmem_st32(ta + 32u, lo);      // completion is awaited after the B tile has been split (overlaps the two)
       }
       float4* bh = reinterpret_cast<float4*>(s.b_hi[st]);
       float4* bl = reinterpret_cast<float4*>(s.b_lo[st]);
@@ -395,6 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
         bl[idx] = l;
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // the A halves have landed in TMEM
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM stores ordered before the arrival
       __syncwarp();
