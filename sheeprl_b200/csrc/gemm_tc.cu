@@ -442,9 +442,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float* crow = C + row_off + cb;
       const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (cb + ACC_COLS <= N);
       if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
+        // C was initialised by init_c_kernel (bias / zero / kept); 16-byte vector reductions when the row allows
+        if (vec) {
 #pragma unroll
-        for (int j = 0; j < ACC_COLS; ++j)
-          if (cb + j < N) atomicAdd(crow + j, acc[j]);   // C was initialised by init_c_kernel (bias / zero / kept)
+          for (int j = 0; j < ACC_COLS; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < ACC_COLS; ++j)
+            if (cb + j < N) atomicAdd(crow + j, acc[j]);
+        }
       } else if (vec) {
 #pragma unroll
         for (int j = 0; j < ACC_COLS; j += 4) {
