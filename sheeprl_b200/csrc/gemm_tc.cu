@@ -732,12 +732,20 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
   g.b_mn = transB ? 0 : 1;
   g.ksplits = 1;
   const int tiles = grid.x * grid.y, nkb = (K + BK - 1) / BK;
-  if (tiles < 120 && nkb >= 16) {
-    int sp = (2 * kNumSMs + tiles - 1) / tiles;
-    if (sp > nkb / 8) sp = nkb / 8;
-    if (sp < 1) sp = 1;
-    const int per = (nkb + sp - 1) / sp;
-    g.ksplits = (nkb + per - 1) / per;   // every split owns at least one k-block
+  if (tiles < 2 * kNumSMs && nkb >= 8) {
+    // split-K for launches that cannot fill the SMs (the M = T*B = 1024 products of the imagination rollout, weight
+    // gradients): pick the split count that minimises  waves x (k-blocks per CTA x t_kb + fixed cost)  with
+    // t_kb ~ 0.8 us per 128x128x32 k-block, ~4 us of pipeline fill + epilogue per CTA, ~2 us for the vector reductions
+    int best = 1;
+    float best_t = 1e30f;
+    const int max_sp = nkb / 4 < 32 ? nkb / 4 : 32;
+    for (int sp = 1; sp <= (max_sp < 1 ? 1 : max_sp); ++sp) {
+      const int per = (nkb + sp - 1) / sp, real = (nkb + per - 1) / per;
+      const int waves = (tiles * real + kNumSMs - 1) / kNumSMs;
+      const float t = waves * (per * 0.8f + 4.0f + (real > 1 ? 2.0f : 0.0f));
+      if (t < best_t - 1e-3f) { best_t = t; best = real; }
+    }
+    g.ksplits = best;
   }
   if (g.ksplits > 1) {
     grid.z = g.ksplits;
