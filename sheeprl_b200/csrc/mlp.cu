@@ -119,6 +119,33 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BG g, const int ksplit
   float* __restrict__ C = g.C + net * g.strideC;
   const float* __restrict__ bias = g.bias ? g.bias + net * g.strideBias : nullptr;
   const float* __restrict__ aux = g.aux ? g.aux + net * g.strideAux : nullptr;
+  if (ksplit > 1) {
+    // partial tile of a split-K product (plain epilogue, checked by the host): vector reductions where the row allows
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = m0 + ty * TM + i;
+      if (m >= g.M) continue;
+      const int n = n0 + tx * TN;
+      float* c = C + m * g.ldc + n;
+      bool done = false;
+      if constexpr (TN == 4) {
+        if (n + 3 < g.N && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+          atomicAdd(reinterpret_cast<float4*>(c), make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+          done = true;
+        }
+      } else if constexpr (TN == 2) {
+        if (n + 1 < g.N && ((reinterpret_cast<uintptr_t>(c) & 7) == 0)) {
+          atomicAdd(reinterpret_cast<float2*>(c), make_float2(acc[i][0], acc[i][1]));
+          done = true;
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+          if (n + j < g.N) atomicAdd(c + j, acc[i][j]);
+      }
+    }
+  } else
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
@@ -129,10 +156,6 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BG g, const int ksplit
       if (n >= g.N) continue;
       float v = acc[i][j];
       float* c = C + m * g.ldc + n;
-      if (ksplit > 1) {                              // partial tile (epilogue is EPI_NONE, no bias: checked by host)
-        atomicAdd(c, v);
-        continue;
-      }
       if (bias) v += bias[n];
       if (g.epi == EPI_RELU) v = fmaxf(v, 0.f);
       else if (g.epi == EPI_TANH) v = tanhf(v);
