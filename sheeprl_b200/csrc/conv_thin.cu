@@ -123,7 +123,7 @@ conv_up_thin_kernel(const float* __restrict__ small, const float* __restrict__ W
 // feed 16*CB FMAs on register accumulators; one cross-warp + atomic reduction per CTA at the very end.
 // ---------------------------------------------------------------------------------------------------------
 template <int CB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv_wgrad_thin_kernel(const float* __restrict__ small, const float* __restrict__ big, float* __restrict__ dW, int NB,
                        int h, int w, int Cs, int tiles_per_row) {
   constexpr int TX = 32, ROWF = (2 * TX + 2) * CB;              // floats per staged big row (even)
@@ -142,27 +142,47 @@ conv_wgrad_thin_kernel(const float* __restrict__ small, const float* __restrict_
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4 * CB; ++b) acc[a][b] = 0.f;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // software pipeline: the next tile's global loads are issued into registers before the current tile is consumed
+    // (the kernel is otherwise stalled on their latency: 3 CTAs per SM cannot hide it)
+    constexpr int NBR = (4 * ROWF + 255) / 256, NSR = TX * 32 / 256;
+    float rb[NBR], rs[NSR];
+    auto fetch = [&](long long tile) {
       const int tx = (int)(tile % tiles_per_row);
       const long long r = tile / tiles_per_row;
       const int y = (int)(r % h);
       const long long n = r / h;
       const int x0 = tx * TX, npx = min(TX, w - x0);
-      __syncthreads();
-      // stage big rows 2y-1 .. 2y+2, columns 2*x0-1 .. 2*x0+2*TX  (zero outside the image)
-      for (int e = threadIdx.x; e < 4 * ROWF; e += blockDim.x) {
-        const int row = e / ROWF, f = e - row * ROWF;
-        const int col = f / CB, c = f - col * CB;
-        const int yy = 2 * y - 1 + row, xx = 2 * x0 - 1 + col;
+#pragma unroll
+      for (int u = 0; u < NBR; ++u) {
+        const int e = threadIdx.x + u * 256;
         float v = 0.f;
-        if (yy >= 0 && yy < Hb && xx >= 0 && xx < Wb) v = __ldg(big + ((n * Hb + yy) * Wb + xx) * (long long)CB + c);
-        Bt[e] = v;
+        if (e < 4 * ROWF) {
+          const int row = e / ROWF, f = e - row * ROWF;
+          const int col = f / CB, c = f - col * CB;
+          const int yy = 2 * y - 1 + row, xx = 2 * x0 - 1 + col;
+          if (yy >= 0 && yy < Hb && xx >= 0 && xx < Wb) v = __ldg(big + ((n * Hb + yy) * Wb + xx) * (long long)CB + c);
+        }
+        rb[u] = v;
       }
-      for (int e = threadIdx.x; e < TX * 32; e += blockDim.x) {
-        const int p = e >> 5, c = e & 31;
-        St[p * 32 + c] = (p < npx) ? __ldg(small + ((n * h + y) * (long long)w + x0 + p) * Cs + g * 32 + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < NSR; ++u) {
+        const int e = threadIdx.x + u * 256, p = e >> 5, c = e & 31;
+        rs[u] = (p < npx) ? __ldg(small + ((n * h + y) * (long long)w + x0 + p) * Cs + g * 32 + c) : 0.f;
       }
+    };
+    long long tile = blockIdx.x;
+    if (tile < ntiles) fetch(tile);
+    for (; tile < ntiles; tile += gridDim.x) {
+      __syncthreads();                                         // the previous tile has been consumed
+#pragma unroll
+      for (int u = 0; u < NBR; ++u) {
+        const int e = threadIdx.x + u * 256;
+        if (e < 4 * ROWF) Bt[e] = rb[u];
+      }
+#pragma unroll
+      for (int u = 0; u < NSR; ++u) St[threadIdx.x + u * 256] = rs[u];
       __syncthreads();
+      if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);  // in flight while this tile is multiplied
 #pragma unroll
       for (int q = 0; q < TX / 8; ++q) {
         const int p = warp + 8 * q;
