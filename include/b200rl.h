@@ -266,6 +266,14 @@ int b200rl_lambda_returns_bwd(const float* cont_logit, const float* discount, co
 int b200rl_twohot_mean_bwd(const float* logits, const float* d_mean, float* d_logits, long long M, int nb, long long ldl,
                            long long ldd, float low, float high, cudaStream_t stream);
 
+/* Convolution weight gradient with both operands read in place as MN-major tcgen05 operands (no im2col, no transposes):
+ * G[(tap, cb), cs] = sum over small pixels p of big[patch(p)][tap][cb] * small[p][cs]; big [NB,2h,2w,Cb] and small
+ * [NB,h,w,Cs] channel-last, G [16*Cb][Cs] (unpacked to the reference's [Cs][Cb][4][4] by b200rl_conv_wgrad_tc).
+ * Replaces the autograd weight-gradient of CNNEncoder / CNNDecoder convolutions (agent.py:78-91, :199-222). */
+int b200rl_conv_wgrad_mn_supported(int NB, int h, int w, int Cs, int Cb);
+int b200rl_conv_wgrad_mn(const float* small_, const float* big, float* G, int NB, int h, int w, int Cs, int Cb,
+                         cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,8 @@ GPU-less host pass the torch test double from ``oracle/ops_emul.py``).
 """
 from __future__ import annotations
 
+import json
+import os
 from typing import Dict, Optional, Sequence, Type
 
 import numpy as np
@@ -278,6 +280,39 @@ class ReplayBuffer:
         t = self.sample_tensors(batch_size, sample_next_obs=sample_next_obs, n_samples=n_samples, **kwargs)
         return {k: v.cpu().numpy() for k, v in t.items()}
 
+    # ------------------------------------------------------------------ disk spill / restore
+    def to_memmap(self, directory) -> None:
+        """Writes the ring to `<directory>/<key>.memmap` — raw `[buffer_size, n_envs, ...]` arrays in the stored dtype,
+        the very files the reference's `MemmapArray` keeps when `buffer.memmap=True` (sheeprl/utils/memmap.py:22-85,
+        buffers.py:203-210) — plus `meta.json` with the write head, so a device ring can be checkpointed / resumed or
+        handed to the reference's host buffers."""
+        os.makedirs(directory, exist_ok=True)
+        meta = {"buffer_size": self._buffer_size, "n_envs": self._n_envs, "pos": self._pos, "full": self._full, "keys": {}}
+        for k, v in self._buf.items():
+            a = v.detach().cpu().numpy()
+            mm = np.memmap(os.path.join(directory, f"{k}.memmap"), dtype=a.dtype, mode="w+", shape=a.shape)
+            mm[:] = a
+            mm.flush()
+            meta["keys"][k] = {"dtype": str(a.dtype), "shape": list(a.shape)}
+        with open(os.path.join(directory, "meta.json"), "w") as f:
+            json.dump(meta, f)
+
+    def load_memmap(self, directory) -> None:
+        """Inverse of :meth:`to_memmap` (also reads a directory written by the reference when given its key dtypes /
+        shapes through `meta.json`)."""
+        with open(os.path.join(directory, "meta.json")) as f:
+            meta = json.load(f)
+        if meta["buffer_size"] != self._buffer_size or meta["n_envs"] != self._n_envs:
+            raise ValueError("memmap directory was written by a buffer of a different size")
+        for k, info in meta["keys"].items():
+            a = np.memmap(os.path.join(directory, f"{k}.memmap"), dtype=np.dtype(info["dtype"]), mode="r",
+                          shape=tuple(info["shape"]))
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if k not in self._buf:
+                self._allocate(k, tuple(t.shape[2:]), t.dtype)
+            self._buf[k].copy_(t)
+        self._pos, self._full = int(meta["pos"]), bool(meta["full"])
+
     # ------------------------------------------------------------------ item access (reference: buffers.py:329-361)
     def __getitem__(self, key: str) -> torch.Tensor:
         if not isinstance(key, str):
@@ -455,6 +490,15 @@ class EnvIndependentReplayBuffer:
         self.ops  # bind the kernels to every ring
         for j, env_idx in enumerate(indices):
             self._buf[env_idx].add({k: v[:, j:j + 1] for k, v in data.items()}, validate_args=validate_args)
+
+    def to_memmap(self, directory) -> None:
+        """`<directory>/env_<i>/<key>.memmap`, the reference's layout (buffers.py:581)"""
+        for i, b in enumerate(self._buf):
+            b.to_memmap(os.path.join(directory, f"env_{i}"))
+
+    def load_memmap(self, directory) -> None:
+        for i, b in enumerate(self._buf):
+            b.load_memmap(os.path.join(directory, f"env_{i}"))
 
     def sample_tensors(self, batch_size: int, sample_next_obs: bool = False, clone: bool = False, n_samples: int = 1,
                        dtype=None, device=None, from_numpy: bool = False, **kwargs) -> Dict[str, torch.Tensor]:

@@ -131,3 +131,32 @@ def test_dtypes_and_item_access():
     t = rb.sample_tensors(4, dtype=torch.float32, n_samples=2)
     assert t["rewards"].dtype == torch.float32 and t["rewards"].shape == (2, 4, 1) and float(t["rewards"].min()) == 7.0
     assert len(rb) == 6 and not rb.full and not rb.empty and rb.n_envs == 2
+
+
+def test_memmap_spill_and_restore(tmp_path):
+    """§8f-2: a device ring written with to_memmap() is (a) readable as the reference's raw [size, n_envs, ...] memmap
+    files and (b) restored bit-for-bit, write head included, so sampling continues identically."""
+    from tests.buffer_scenarios import synth_rows
+
+    def make():
+        rb = RB.EnvIndependentReplayBuffer(16, 3, buffer_cls=RB.SequentialReplayBuffer, device="cpu", ops=EmulOps())
+        return rb
+
+    a = make()
+    a.add(synth_rows(11, 3, 1))
+    a.add(synth_rows(9, 2, 2), indices=[0, 2])                     # wraps two of the rings
+    a.to_memmap(tmp_path)
+    raw = np.memmap(tmp_path / "env_2" / "observations.memmap", dtype=np.uint8, mode="r", shape=(16, 1, 3, 4, 4))
+    assert np.array_equal(raw, a.buffer[2]["observations"].numpy())
+    b = make()
+    b.add(synth_rows(1, 3, 3))                                      # allocates storage; contents are overwritten
+    b.load_memmap(tmp_path)
+    assert [r._pos for r in b.buffer] == [r._pos for r in a.buffer] and b.full == a.full
+    for ra, rb_ in zip(a.buffer, b.buffer):
+        for k in ra.buffer:
+            assert torch.equal(ra[k], rb_[k]), k
+    from tests.buffer_scenarios import seed_rngs
+    seed_rngs(a, 5), seed_rngs(b, 5)
+    sa, sb = a.sample(8, sequence_length=4, n_samples=2), b.sample(8, sequence_length=4, n_samples=2)
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k])
