@@ -59,3 +59,62 @@ def test_two_rank_gloo_step_keeps_replicas_identical_and_averages_gradients():
         grads.append(eng.wm.grad.clone())
     want = 0.5 * (grads[0] + grads[1])
     assert float((a["wm_grad"] - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+def _worker_sac_ppo(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    from sheeprl_b200.parallel import attach_data_parallel, init_process_group_from_env
+    from tests.test_ppo_cpu import load as load_ppo, make_engine as make_ppo
+    from tests.test_sac_cpu import load as load_sac, make_engine as make_sac
+
+    init_process_group_from_env("gloo")
+    # SAC: each rank gets a different batch of the fixture (sac.py trains DDP-wrapped actor / critics, :68-73 reduces alpha)
+    fx = load_sac("sac_tiny")
+    eng = make_sac(fx)
+    attach_data_parallel(eng)
+    st = fx["steps"][rank]
+    eng.train_step(dict(st["data"]), True, {"eps_next": st["eps_next"], "eps_cur": st["eps_cur"]})
+    res = {"sac_actor": eng.actor.flat.clone(), "sac_qf": eng.qf.flat.clone(), "sac_alpha": eng.alpha.flat.clone(),
+           "sac_qf_grad": eng.qf.grad.clone()}
+    # PPO: ranks train on different minibatches of the rollout
+    fp = load_ppo("ppo_branches")
+    pe = make_ppo(fp)
+    attach_data_parallel(pe)
+    pe.train(fp["data"], [fp["index_batches"][rank]])
+    res["ppo"] = pe.group.flat.clone()
+    res["ppo_grad"] = pe.group.grad.clone()
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sac_and_ppo_average_gradients():
+    """SAC / PPO engines through the same data-parallel hook: replicas identical, gradient = mean over ranks"""
+    mp.set_start_method("spawn", force=True)
+    out = mp.Manager().dict()
+    port = 30100 + (os.getpid() % 500)
+    mp.spawn(_worker_sac_ppo, args=(2, port, out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    for k in a.keys():
+        assert torch.equal(a[k], b[k]), k
+    sys.path.insert(0, ROOT)
+    from tests.test_ppo_cpu import load as load_ppo, make_engine as make_ppo
+    from tests.test_sac_cpu import load as load_sac, make_engine as make_sac
+
+    fx, grads = load_sac("sac_tiny"), []
+    for r in range(2):
+        eng = make_sac(fx)
+        st = fx["steps"][r]
+        eng.train_step(dict(st["data"]), True, {"eps_next": st["eps_next"], "eps_cur": st["eps_cur"]})
+        grads.append(eng.qf.grad.clone())
+    # the critic gradient is computed before any parameter changes: the DP gradient is the mean of the two
+    want = 0.5 * (grads[0] + grads[1])
+    assert float((a["sac_qf_grad"] - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    fp, pg = load_ppo("ppo_branches"), []
+    for r in range(2):
+        pe = make_ppo(fp)
+        pe.train(fp["data"], [fp["index_batches"][r]])
+        pg.append(pe.group.grad.clone())
+    want = 0.5 * (pg[0] + pg[1])
+    assert float((a["ppo_grad"] - want).abs().max()) <= 1e-5 * float(want.abs().max())
