@@ -274,6 +274,12 @@ int b200rl_conv_wgrad_mn_supported(int NB, int h, int w, int Cs, int Cb);
 int b200rl_conv_wgrad_mn(const float* small_, const float* big, float* G, int NB, int h, int w, int Cs, int Cb,
                          cudaStream_t stream);
 
+/* PPOPlayer.forward / get_actions (ppo/agent.py:269-322): per-head categorical sample (Exp(1) noise; mode when greedy or
+ * noise == NULL) or Normal sample (N(0,1) noise; mean when greedy) from the actor head, its log-probability logp[B];
+ * actions: one-hot [B, sum(head_dims)] or [B, A]. */
+int b200rl_ppo_act(const float* head, const float* noise, float* actions, float* logp, int B, const int* head_dims,
+                   int n_heads, int is_continuous, int greedy, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

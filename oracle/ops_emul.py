@@ -555,3 +555,23 @@ class EmulOps:
         p = torch.softmax(logits, -1)
         m = (p * bins).sum(-1, keepdim=True)
         d_logits.copy_(d_mean.reshape(-1, 1) * torch.exp(m.abs()) * p * (bins - m))
+
+    def ppo_act(self, head, noise, actions, logp, head_dims, is_continuous, greedy):
+        if is_continuous:
+            A = sum(head_dims)
+            mean, ls = head[:, :A], head[:, A:]
+            a = mean if (greedy or noise is None) else mean + ls.exp() * noise
+            actions.copy_(a)
+            logp.copy_((-((a - mean) ** 2) / (2 * (ls.exp() ** 2)) - ls - math.log(math.sqrt(2 * math.pi))).sum(-1))
+            return
+        off, lp = 0, 0.0
+        for n in head_dims:
+            lg = torch.log_softmax(head[:, off:off + n], -1)
+            p = lg.exp()
+            if not greedy and noise is not None:
+                p = p / noise[:, off:off + n]
+            idx = p.argmax(-1)
+            actions[:, off:off + n] = F.one_hot(idx, n).float()
+            lp = lp + lg.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
+            off += n
+        logp.copy_(lp)

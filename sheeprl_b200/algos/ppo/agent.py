@@ -86,15 +86,78 @@ class PPOAgent:
 
 
 class PPOPlayer:
-    """Acting path placeholder."""
+    """Acting path (reference: ppo/agent.py:242-322): `forward(obs) -> (actions, logprobs, values)`, `get_values`,
+    `get_actions(obs, greedy)` on the trainer's flat parameter group (nothing to tie or copy).  obs: the dict the
+    rollout loop passes — image key `[E, C, H, W]` float already normalised (ppo.py:283-285) or raw uint8, vector key
+    `[E, D]`.  `noise` (extra, optional): injected Exp(1) / N(0,1) draws for parity tests."""
 
     def __init__(self, engine: PPOEngine):
         self.engine = engine
+        self._ctr = torch.zeros(1, dtype=torch.int32, device=engine.device)
+        self.rng_seed = 0x9E37
+        self._acts: Dict[int, tuple] = {}
 
-    def get_actions(self, obs, greedy: bool = False):
-        raise NotImplementedError("PPOPlayer acting path is scheduled after the train() hot path (SURVEY §8f)")
+    class _ActorInfo:
+        def __init__(self, spec):
+            self.is_continuous, self.distribution = spec["is_continuous"], "normal" if spec["is_continuous"] else "discrete"
 
-    get_values = __call__ = get_actions
+    @property
+    def actor(self):
+        return PPOPlayer._ActorInfo(self.engine.spec)
+
+    def _run(self, obs, actor: bool, critic: bool):
+        e, s = self.engine, self.engine.spec
+        rgb = x_state = None
+        E = None
+        normalized = False
+        if s["cnn_channels"]:
+            rgb = obs[s.get("cnn_key") or "rgb"].reshape(-1, s["cnn_channels"], s["screen"], s["screen"]).contiguous()
+            E, normalized = rgb.shape[0], rgb.dtype != torch.uint8
+        if s["mlp_dim"]:
+            x_state = obs[s.get("mlp_key") or "state"].reshape(-1, s["mlp_dim"]).float().contiguous().unsqueeze(0)
+            E = x_state.shape[1]
+        b = e._buffers(E)
+        e.forward(b, rgb, x_state, rgb_normalized=normalized, actor=actor, critic=critic)
+        return b, E
+
+    def _sample(self, b, E, greedy: bool, noise):
+        e = self.engine
+        A = sum(e.head_dims)
+        if E not in self._acts:
+            f = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=e.device)  # noqa: E731
+            self._acts[E] = (f(E, A), f(E), f(E, A))
+        acts, logp, nz = self._acts[E]
+        if noise is None and not greedy:
+            e.ops.increment(self._ctr)
+            (e.ops.fill_normal if e.spec["is_continuous"] else e.ops.fill_exponential)(nz.view(-1), self.rng_seed, 21, self._ctr)
+            noise = nz
+        e.ops.ppo_act(b["head"][0], None if greedy else noise.reshape(E, A).contiguous(), acts, logp, e.head_dims,
+                      e.spec["is_continuous"], greedy)
+        if e.spec["is_continuous"]:
+            return (acts.clone(),), logp.clone().unsqueeze(-1)
+        out, off = [], 0
+        for ad in e.head_dims:
+            out.append(acts[:, off:off + ad].clone())
+            off += ad
+        return tuple(out), logp.clone().unsqueeze(-1)
+
+    @torch.no_grad()
+    def forward(self, obs, noise=None):
+        b, E = self._run(obs, True, True)
+        actions, logp = self._sample(b, E, False, noise)
+        return actions, logp, b["values"][0].clone()
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def get_values(self, obs):
+        b, _ = self._run(obs, False, True)
+        return b["values"][0].clone()
+
+    @torch.no_grad()
+    def get_actions(self, obs, greedy: bool = False, noise=None):
+        b, E = self._run(obs, True, False)
+        return self._sample(b, E, greedy, noise)[0]
 
 
 def build_agent(fabric, actions_dim: Sequence[int], is_continuous: bool, cfg: Dict[str, Any], obs_space,

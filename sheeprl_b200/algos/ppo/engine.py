@@ -223,6 +223,32 @@ class PPOEngine:
             dpre = dhidden[i - 1]
         return dpre                                         # pre-activation gradient of layer 0
 
+    def forward(self, b: dict, rgb, x_state, rgb_normalized: bool = False, actor: bool = True, critic: bool = True):
+        """PPOAgent.forward up to the head / value outputs (ppo/agent.py:208-212) into the buffer set `b`.
+        rgb: [B,C,H,W] uint8 / float raw 0..255 (normalised here, ppo/utils.py:69-72) or, with rgb_normalized, float
+        already normalised (what the reference's rollout loop passes to the player); x_state: [1,B,mlp_dim]."""
+        o = self.ops
+        feat = b["feat"]
+        B = feat.shape[1]
+        if self.geo:
+            if rgb_normalized:
+                H, W, C = self.geo[0][:3]
+                o.transpose_batched(rgb.float().contiguous().view(B, C, H * W), b["x0"].view(B, H * W, C))
+            else:
+                o.obs_prep(rgb, b["x0"])                    # /255 - 0.5, NCHW -> channel-last
+            x = b["x0"]
+            for i, (H, W, C, k, st, Ho, Wo, Co) in enumerate(self.geo):
+                o.im2col(x, b["col"][i][0], k, st)
+                self._fwd(self.convs[i], b["col"][i], b["y"][i])
+                x = b["y"][i][0].view(B, Ho, Wo, Co)
+            self._fwd(self.fc, b["y"][-1].view(1, B, -1), feat[:, :, :self.F])
+        if self.spec["mlp_dim"]:
+            self._mlp_fwd(self.menc, x_state, b["mh"], feat[:, :, self.F:])
+        if critic:
+            self._mlp_fwd(self.critic, feat, b["ch"], b["values"])
+        if actor:
+            self._mlp_fwd(self.actor, feat, b["ah"], b["head"])
+
     # ------------------------------------------------------------------ one minibatch
     def minibatch_step(self, data: Dict[str, torch.Tensor], idx: torch.Tensor):
         """data: flat [N, ...] device tensors (rgb uint8 or float32 raw 0..255; everything else float32);
@@ -239,19 +265,8 @@ class PPOEngine:
 
         # ---- forward
         feat = b["feat"]
-        if self.geo:
-            o.obs_prep(rows("rgb"), b["x0"])                # /255 - 0.5 (ppo/utils.py:69-72), NCHW -> channel-last
-            x = b["x0"]
-            for i, (H, W, C, k, st, Ho, Wo, Co) in enumerate(self.geo):
-                o.im2col(x, b["col"][i][0], k, st)
-                self._fwd(self.convs[i], b["col"][i], b["y"][i])
-                x = b["y"][i][0].view(B, Ho, Wo, Co)
-            self._fwd(self.fc, b["y"][-1].view(1, B, -1), feat[:, :, :self.F])
-        if s["mlp_dim"]:
-            x_state = rows("state").unsqueeze(0)
-            self._mlp_fwd(self.menc, x_state, b["mh"], feat[:, :, self.F:])
-        self._mlp_fwd(self.critic, feat, b["ch"], b["values"])
-        self._mlp_fwd(self.actor, feat, b["ah"], b["head"])
+        x_state = rows("state").unsqueeze(0) if s["mlp_dim"] else None
+        self.forward(b, rows("rgb") if self.geo else None, x_state)
         # ---- objective + gradients w.r.t. head outputs and values
         o.ppo_loss(b["head"][0], rows("actions"), rows("logprobs").reshape(-1), rows("advantages").reshape(-1),
                    b["values"].reshape(-1), rows("values").reshape(-1), rows("returns").reshape(-1), b["dhead"][0],

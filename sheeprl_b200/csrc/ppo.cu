@@ -188,6 +188,52 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const PpoLossArgs a) {
   }
 }
 
+// PPOPlayer.forward (ppo/agent.py:269-293): sample an action per head (OneHotCategorical: arg-max of p / q with
+// q ~ Exp(1), identical to torch.multinomial; Normal: mean + std * eps) or take the mode / mean when greedy, and
+// its log-probability.  Thread per row.
+__global__ void ppo_act_kernel(const float* __restrict__ head, const float* __restrict__ noise, float* __restrict__ actions,
+                               float* __restrict__ logp, int B, int n_heads, PpoLossArgs dims, int is_continuous,
+                               int greedy) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int width = 0;
+  for (int h = 0; h < n_heads; ++h) width += dims.head_dims[h];
+  float lp = 0.f;
+  if (is_continuous) {
+    const int A = width;
+    const float* hd = head + (long long)b * 2 * A;
+    for (int j = 0; j < A; ++j) {
+      const float mu = hd[j], ls = hd[A + j], sd = expf(ls);
+      const float e = (greedy || !noise) ? 0.f : noise[(long long)b * A + j];
+      const float a = mu + sd * e, d = a - mu;
+      actions[(long long)b * A + j] = a;
+      lp += -(d * d) / (2.f * sd * sd) - ls - 0.9189385332046727f;
+    }
+  } else {
+    const float* hd = head + (long long)b * width;
+    int off = 0;
+    for (int h = 0; h < n_heads; ++h) {
+      const int n = dims.head_dims[h];
+      float m = -INFINITY;
+      for (int j = 0; j < n; ++j) m = fmaxf(m, hd[off + j]);
+      float z = 0.f;
+      for (int j = 0; j < n; ++j) z += expf(hd[off + j] - m);
+      const float lse = m + logf(z);
+      float best = -INFINITY;
+      int arg = 0;
+      for (int j = 0; j < n; ++j) {
+        float p = expf(hd[off + j] - lse);
+        if (!greedy && noise) p = p / noise[(long long)b * width + off + j];
+        if (p > best) { best = p; arg = j; }
+      }
+      for (int j = 0; j < n; ++j) actions[(long long)b * width + off + j] = (j == arg) ? 1.f : 0.f;
+      lp += hd[off + arg] - lse;
+      off += n;
+    }
+  }
+  logp[b] = lp;
+}
+
 }  // namespace
 
 extern "C" int b200rl_im2col(const float* x, float* col, int B, int H, int W, int C, int k, int stride, cudaStream_t st) {
@@ -234,6 +280,17 @@ extern "C" int b200rl_ppo_loss(const float* head, const float* actions, const fl
   a.is_continuous = is_continuous; a.clip_vloss = clip_vloss; a.normalize_adv = normalize_adv;
   a.clip_coef = clip_coef; a.vf_coef = vf_coef; a.ent_coef = ent_coef;
   ppo_loss_kernel<<<1, 256, 0, st>>>(a);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_ppo_act(const float* head, const float* noise, float* actions, float* logp, int B,
+                              const int* head_dims, int n_heads, int is_continuous, int greedy, cudaStream_t st) {
+  RL_CHECK_ARG(head && actions && logp && head_dims, "null pointer");
+  RL_CHECK_ARG(B > 0 && n_heads > 0 && n_heads <= 8, "bad dims (at most 8 action heads)");
+  PpoLossArgs d{};
+  for (int i = 0; i < n_heads; ++i) d.head_dims[i] = head_dims[i];
+  ppo_act_kernel<<<ceil_div(B, 128), 128, 0, st>>>(head, noise, actions, logp, B, n_heads, d, is_continuous, greedy);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }

@@ -598,3 +598,10 @@ class CudaOps:
         self._ck(self.lib.b200rl_twohot_mean_bwd(_p(logits), _p(d_mean), _p(d_logits), c_ll(M), c_int(nb),
                                                  c_ll(_ld(logits)), c_ll(_ld(d_logits)), c_float(low), c_float(high),
                                                  self._st()))
+
+    def ppo_act(self, head, noise, actions, logp, head_dims, is_continuous: bool, greedy: bool):
+        _f32(head, noise, actions, logp)
+        assert head.is_contiguous() and actions.is_contiguous() and (noise is None or noise.is_contiguous())
+        dims = (c_int * len(head_dims))(*head_dims)
+        self._ck(self.lib.b200rl_ppo_act(_p(head), _p(noise), _p(actions), _p(logp), c_int(head.shape[0]), dims,
+                                         c_int(len(head_dims)), c_int(int(is_continuous)), c_int(int(greedy)), self._st()))

@@ -98,3 +98,11 @@ def test_full_size_pixel_minibatch_against_oracle(cu):
         for i, k in enumerate(("Loss/policy_loss", "Loss/value_loss", "Loss/entropy_loss")):
             assert abs(float(got[i]) - w[k]) <= 1e-4 * max(1.0, abs(w[k])), (k, float(got[i]), w[k])
     assert_params_close(eng.export_reference_state(), p, "pixel64", steps=2)
+
+
+@pytest.mark.parametrize("name", ["ppo_branches", "ppo_continuous", "ppo_pixel"])
+@pytest.mark.parametrize("uint8_image", [False, True])
+def test_player_matches_reference(cu, name, uint8_image):
+    from tests.test_ppo_cpu import check_player
+
+    check_player(name, device="cuda", ops=cu, uint8_image=uint8_image)

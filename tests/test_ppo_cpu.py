@@ -112,3 +112,35 @@ def test_public_api_draws_the_reference_minibatches():
     assert abs(Agg.rows[-1][1] - fx["losses"][-1]["Loss/entropy_loss"]) < 1e-4
     assert_params_close(agent.state_dict(), fx["after"], "public", steps=len(fx["losses"]))
     assert opt.state_dict()["state"][0]["step"] == len(fx["losses"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PPOPlayer against the executed reference player (tests/golden/ppo_player.pt, oracle/make_golden_ppo_player.py)
+# ---------------------------------------------------------------------------------------------------------
+def check_player(name, device="cpu", ops=None, uint8_image=False):
+    from sheeprl_b200.algos.ppo.agent import PPOPlayer
+
+    pf = torch.load(os.path.join(GOLDEN, "ppo_player.pt"), weights_only=False)[name]
+    fx = load(name)
+    eng = make_engine(fx, device=device, ops=ops)
+    player = PPOPlayer(eng)
+    obs = {k: v.to(device) for k, v in pf["obs"].items()}
+    if uint8_image and "rgb" in obs:
+        obs["rgb"] = torch.round((obs["rgb"] + 0.5) * 255).to(torch.uint8)
+    actions, logp, values = player(obs, noise=pf["noise"].to(device))
+    cont = fx["spec"]["is_continuous"]
+    for got, want in zip(actions, pf["actions"]):
+        if cont:
+            assert float((got.cpu() - want).abs().max()) <= 1e-5
+        else:
+            assert torch.equal(got.cpu(), want)
+    assert float((logp.cpu() - pf["logp"]).abs().max()) <= 1e-4 * max(1.0, float(pf["logp"].abs().max()))
+    assert float((values.cpu() - pf["values"]).abs().max()) <= 1e-4 * max(1.0, float(pf["values"].abs().max()))
+    assert float((player.get_values(obs).cpu() - pf["values2"]).abs().max()) <= 1e-4 * max(1.0, float(pf["values2"].abs().max()))
+    for got, want in zip(player.get_actions(obs, greedy=True), pf["greedy"]):
+        assert float((got.cpu() - want).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["ppo_branches", "ppo_continuous", "ppo_pixel"])
+def test_player_matches_reference(name):
+    check_player(name)
