@@ -749,7 +749,9 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
   }
   if (g.ksplits > 1) {
     grid.z = g.ksplits;
-    if (!accumulate || bias) {
+    if (!accumulate && !bias && ldc == N) {
+      RL_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));      // contiguous C: a memset node is enough
+    } else if (!accumulate || bias) {
       init_c_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(C, bias, M, N, ldc, accumulate);
     }
   }
@@ -802,7 +804,7 @@ extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float
   g.ksplits = (nkb + per - 1) / per;
   grid.z = g.ksplits;
   g.mtiles = (int)grid.y;
-  if (g.ksplits > 1) init_c_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(G, nullptr, M, N, N, 0);
+  if (g.ksplits > 1) RL_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)M * N, st));
   if (BN == 64) {
     const size_t smem = sizeof(Smem<64>) + 1024;
     RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
