@@ -1,8 +1,9 @@
-"""Secondary measurements (not the headline bench.py line): SAC updates/s (BASELINE config 3 shapes: 17-dim obs, 6-dim
+"""(lives under tests/: it times the oracle as the CPU baseline, which only tests/, smoke() and bench.py may import)
+Secondary measurements (not the headline bench.py line): SAC updates/s (BASELINE config 3 shapes: 17-dim obs, 6-dim
 action, 256 hidden, batch 256) and PPO minibatches/s (config 2 shapes: 64 x 12x84x84 uint8, NatureCNN-512), each as a
 CUDA graph of the engine's launches, next to the oracle (torch CPU) on the host cores.
 
-    python tools/bench_algos.py [--steps 200] [--no-cpu]        -> one JSON line per algorithm
+    python tests/perf/bench_algos.py [--steps 200] [--no-cpu]        -> one JSON line per algorithm
 """
 from __future__ import annotations
 
@@ -14,7 +15,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -1,6 +1,6 @@
 """Dreamer-V3 S with CONTINUOUS actions (6-dim, BASELINE batch): finite-ness + step time (eager and CUDA graph)."""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import dv3_oracle as O
 from sheeprl_b200.configs import make_dv3_cfg
