@@ -341,7 +341,7 @@ def run_b200(args):
             "shape": {"M": gm, "N": gn, "K": gk}, "us_per_launch": g_ms * 1e3,
             "note": "fp32-equivalent FLOP/s: every product costs 3 TF32 MMAs and TF32 runs at half the bf16 rate, so the "
                     f"scheme's ceiling is peak/6 = {tf / 6:.0f} TFLOP/s (frac of that: {g_tf / (tf / 6):.2f}); tensor-core "
-                    f"ops (gemm+conv) take {share:.2f} of the step; ncu tensor-pipe %: profiles/r1_gemm_tc_ncu_summary.txt"}
+                    f"ops (gemm+conv) take {share:.2f} of the step; ncu --set full of this launch: profiles/r1_gemm_tc_traffic.json (r1d_gemm_tc.ncu-rep)"}
     cpu = cpu_baseline(steps=1, warmup=1) if (args.cpu_baseline and world == 1) else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -41,7 +41,8 @@ int b200rl_gemm_tc_supported(const float* A, const float* B, int M, int N, int K
 int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
                    int ldc, int transA, int transB, int accumulate, cudaStream_t stream);
 /* nn.LayerNorm(eps) (+ nn.SiLU): miniblock sheeprl/utils/model.py:34-88; LayerNormChannelLast
- * sheeprl/models/models.py:507-518 (channel-last is native here).  act: 0 none, 1 SiLU. */
+ * sheeprl/models/models.py:507-518 (channel-last is native here).  act: 0 none, 1 SiLU, 2 tanh, 3 ReLU (the last two:
+ * PPO MLPs with layer_norm=True, sheeprl/algos/ppo/agent.py:58-66,152-176). */
 int b200rl_ln_act_fwd(const float* X, const float* gamma, const float* beta, float* Y, long long M, int C,
                       long long ldx, long long ldy, float eps, int act, cudaStream_t stream);
 int b200rl_ln_act_bwd(const float* X, const float* gamma, const float* beta, const float* dY, float* dX, float* dgamma,
@@ -236,7 +237,8 @@ int b200rl_col2im(const float* dcol, const float* act, float* dx, int B, int H, 
 /* PPO objective on one minibatch: log-prob + entropy of the taken actions from the actor head (OneHotCategorical per
  * head / Independent Normal, ppo/agent.py:179-239), optional advantage normalisation (utils/utils.py:121-130),
  * policy / value / entropy losses (ppo/loss.py:6-75, reduction mean) and the gradients of
- * policy + vf_coef*value + ent_coef*entropy w.r.t. the head outputs and the values.  losses[3]. */
+ * policy + vf_coef*value + ent_coef*entropy w.r.t. the head outputs and the values.  losses[3].
+ * is_continuous: 0 discrete, 1 `normal`, 2 `tanh_normal` (stored actions are tanh-squashed, agent.py:194-206). */
 int b200rl_ppo_loss(const float* head, const float* actions, const float* old_logp, const float* adv,
                     const float* values, const float* old_values, const float* returns, float* dhead, float* dvalues,
                     float* losses, int B, const int* head_dims, int n_heads, int is_continuous, int clip_vloss,
@@ -276,7 +278,8 @@ int b200rl_conv_wgrad_mn(const float* small_, const float* big, float* G, int NB
 
 /* PPOPlayer.forward / get_actions (ppo/agent.py:269-322): per-head categorical sample (Exp(1) noise; mode when greedy or
  * noise == NULL) or Normal sample (N(0,1) noise; mean when greedy) from the actor head, its log-probability logp[B];
- * actions: one-hot [B, sum(head_dims)] or [B, A]. */
+ * actions: one-hot [B, sum(head_dims)] or [B, A].  is_continuous: 0 discrete, 1 `normal`, 2 `tanh_normal` as
+ * forward() returns it (safetanh + corrected log-prob, :257-268), 3 `tanh_normal` as get_actions() returns it (:306-311). */
 int b200rl_ppo_act(const float* head, const float* noise, float* actions, float* logp, int B, const int* head_dims,
                    int n_heads, int is_continuous, int greedy, cudaStream_t stream);
 

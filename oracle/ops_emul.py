@@ -19,7 +19,8 @@ import torch.nn.functional as F
 
 Tensor = torch.Tensor
 FP32_EPS = 1.1920928955078125e-07
-ACT_NONE, ACT_SILU = 0, 1
+ACT_NONE, ACT_SILU, ACT_TANH, ACT_RELU = 0, 1, 2, 3
+SAFE_LIM = 1.0 - 1e-6        # safetanh / safeatanh clamp (sheeprl/utils/utils.py:304-313)
 
 
 def _symlog(x):
@@ -57,6 +58,10 @@ class EmulOps:
         y = F.layer_norm(X, (X.shape[-1],), gamma, beta, eps)
         if act == ACT_SILU:
             y = F.silu(y)
+        elif act == ACT_TANH:
+            y = torch.tanh(y)
+        elif act == ACT_RELU:
+            y = torch.relu(y)
         Y.copy_(y)
 
     def ln_act_bwd(self, X: Tensor, gamma: Tensor, beta: Tensor, eps: float, act: int, dY: Tensor,
@@ -70,6 +75,10 @@ class EmulOps:
         if act == ACT_SILU:
             s = torch.sigmoid(ln)
             dln = dY * (s * (1 + ln * (1 - s)))
+        elif act == ACT_TANH:
+            dln = dY * (1 - torch.tanh(ln) ** 2)
+        elif act == ACT_RELU:
+            dln = dY * (ln > 0).to(dY.dtype)
         else:
             dln = dY.clone()
         if dgamma is not None:
@@ -476,7 +485,11 @@ class EmulOps:
         if is_continuous:
             mean, ls = h.chunk(2, -1)
             sd = ls.exp()
-            lp = (-((actions - mean) ** 2) / (2 * sd * sd) - ls - math.log(math.sqrt(2 * math.pi))).sum(-1)
+            corr = 0.0
+            if int(is_continuous) == 2:          # tanh_normal: stored actions are squashed (ppo/agent.py:194-206)
+                corr = 2.0 * (math.log(2.0) - actions - F.softplus(-2.0 * actions)).sum(-1)
+                actions = torch.atanh(actions.clamp(-SAFE_LIM, SAFE_LIM))
+            lp = (-((actions - mean) ** 2) / (2 * sd * sd) - ls - math.log(math.sqrt(2 * math.pi))).sum(-1) - corr
             ent = (0.5 + 0.5 * math.log(2 * math.pi) + ls).sum(-1)
         else:
             lp, ent, off = 0.0, 0.0, 0
@@ -561,8 +574,14 @@ class EmulOps:
             A = sum(head_dims)
             mean, ls = head[:, :A], head[:, A:]
             a = mean if (greedy or noise is None) else mean + ls.exp() * noise
+            lp = (-((a - mean) ** 2) / (2 * (ls.exp() ** 2)) - ls - math.log(math.sqrt(2 * math.pi))).sum(-1)
+            if int(is_continuous) == 2:          # PPOPlayer.forward with tanh_normal (ppo/agent.py:257-268)
+                a = torch.tanh(a).clamp(-SAFE_LIM, SAFE_LIM)
+                lp = lp - 2.0 * (math.log(2.0) - a - F.softplus(-2.0 * a)).sum(-1)
+            elif int(is_continuous) == 3:        # PPOPlayer.get_actions with tanh_normal (ppo/agent.py:306-311)
+                a = torch.atanh(a.clamp(-SAFE_LIM, SAFE_LIM))
             actions.copy_(a)
-            logp.copy_((-((a - mean) ** 2) / (2 * (ls.exp() ** 2)) - ls - math.log(math.sqrt(2 * math.pi))).sum(-1))
+            logp.copy_(lp)
             return
         off, lp = 0, 0.0
         for n in head_dims:

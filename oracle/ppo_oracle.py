@@ -40,9 +40,38 @@ from oracle.dv3_oracle import AdamState  # noqa: E402,F401
 CONVS = ((8, 4), (4, 2), (3, 1))          # NatureCNN (kernel, stride), channels 32/64/64 (models.py:301-309)
 
 
+def net_cfg(spec, which: str):
+    """(dense_units, mlp_layers, layer_norm) of `which` in {"encoder", "actor", "critic"}: the per-net overrides
+    spec["nets"][which] = (dense, layers) and spec["layer_norm"] (bool or per-net dict) over spec["dense"/"layers"]."""
+    dense, layers = (spec.get("nets") or {}).get(which, (spec["dense"], spec["layers"]))
+    ln = spec.get("layer_norm", False)
+    ln = bool(ln.get(which, False)) if isinstance(ln, dict) else bool(ln)
+    return int(dense), int(layers), ln
+
+
+def _stack_shapes(out, prefix, d, dense, layers, ln, last):
+    """keys of an `MLP` (models/models.py:17-126 over utils/model.py:34-88 miniblocks): per hidden layer
+    Linear [, LayerNorm], activation -> Sequential index stride 3 with norm, 2 without; then the output Linear."""
+    st = 3 if ln else 2
+    for i in range(layers):
+        out[f"{prefix}._model.{st * i}.weight"] = (dense, d)
+        out[f"{prefix}._model.{st * i}.bias"] = (dense,)
+        if ln:
+            out[f"{prefix}._model.{st * i + 1}.weight"] = (dense,)
+            out[f"{prefix}._model.{st * i + 1}.bias"] = (dense,)
+        d = dense
+    if last is not None:
+        out[f"{prefix}._model.{st * layers}.weight"] = (last, d)
+        out[f"{prefix}._model.{st * layers}.bias"] = (last,)
+        d = last
+    return d
+
+
 def ppo_param_shapes(spec) -> "Dict[str, tuple]":
-    """Reference state-dict keys/shapes of PPOAgent for `spec` = dict(cnn_channels (0 = no image), screen, mlp_dim
-    (0 = no vector obs), dense, layers, cnn_features, mlp_features, actions_dim, is_continuous)."""
+    """Reference state-dict keys/shapes of PPOAgent for `spec` = dict(cnn_channels (0 = no image; the sum over the
+    image keys, which the encoder concatenates on the channel axis, ppo/agent.py:34-36), screen, mlp_dim (0 = no vector
+    obs; sum over the vector keys), dense, layers, cnn_features, mlp_features, actions_dim, is_continuous
+    [, layer_norm, nets, dist])."""
     out = {}
     feat = 0
     if spec["cnn_channels"]:
@@ -55,36 +84,38 @@ def ppo_param_shapes(spec) -> "Dict[str, tuple]":
         out["feature_extractor.cnn_encoder.model.fc.bias"] = (spec["cnn_features"],)
         feat += spec["cnn_features"]
     if spec["mlp_dim"]:
-        d = spec["mlp_dim"]
-        for i in range(spec["layers"]):
-            out[f"feature_extractor.mlp_encoder.model._model.{2 * i}.weight"] = (spec["dense"], d)
-            out[f"feature_extractor.mlp_encoder.model._model.{2 * i}.bias"] = (spec["dense"],)
-            d = spec["dense"]
-        out[f"feature_extractor.mlp_encoder.model._model.{2 * spec['layers']}.weight"] = (spec["mlp_features"], d)
-        out[f"feature_extractor.mlp_encoder.model._model.{2 * spec['layers']}.bias"] = (spec["mlp_features"],)
-        feat += spec["mlp_features"]
-    for net in ("critic", "actor.actor_backbone"):
-        d = feat
-        for i in range(spec["layers"]):
-            out[f"{net}._model.{2 * i}.weight"] = (spec["dense"], d)
-            out[f"{net}._model.{2 * i}.bias"] = (spec["dense"],)
-            d = spec["dense"]
-        if net == "critic":
-            out[f"critic._model.{2 * spec['layers']}.weight"] = (1, d)
-            out[f"critic._model.{2 * spec['layers']}.bias"] = (1,)
+        dense, layers, ln = net_cfg(spec, "encoder")
+        feat += _stack_shapes(out, "feature_extractor.mlp_encoder.model", spec["mlp_dim"], dense, layers, ln, spec["mlp_features"])
+    dense, layers, ln = net_cfg(spec, "critic")
+    _stack_shapes(out, "critic", feat, dense, layers, ln, 1)
+    dense, layers, ln = net_cfg(spec, "actor")
+    _stack_shapes(out, "actor.actor_backbone", feat, dense, layers, ln, None)
     heads = [2 * sum(spec["actions_dim"])] if spec["is_continuous"] else list(spec["actions_dim"])
     for i, a in enumerate(heads):
-        out[f"actor.actor_heads.{i}.weight"] = (a, spec["dense"])
+        out[f"actor.actor_heads.{i}.weight"] = (a, dense)       # in_features = actor dense_units (ppo/agent.py:180-183)
         out[f"actor.actor_heads.{i}.bias"] = (a,)
     return out
 
 
-def _mlp(p, prefix, x, layers, act, last=True):
+def _mlp(p, prefix, x, cfg, act, last=True):
+    dense, layers, ln = cfg
+    st = 3 if ln else 2
     for i in range(layers):
-        x = act(F.linear(x, p[f"{prefix}._model.{2 * i}.weight"], p[f"{prefix}._model.{2 * i}.bias"]))
+        x = F.linear(x, p[f"{prefix}._model.{st * i}.weight"], p[f"{prefix}._model.{st * i}.bias"])
+        if ln:
+            x = F.layer_norm(x, (dense,), p[f"{prefix}._model.{st * i + 1}.weight"], p[f"{prefix}._model.{st * i + 1}.bias"], 1e-5)
+        x = act(x)
     if last:
-        x = F.linear(x, p[f"{prefix}._model.{2 * layers}.weight"], p[f"{prefix}._model.{2 * layers}.bias"])
+        x = F.linear(x, p[f"{prefix}._model.{st * layers}.weight"], p[f"{prefix}._model.{st * layers}.bias"])
     return x
+
+
+SAFE_LIM = 1.0 - 1e-6       # safetanh / safeatanh clamp, eps = finfo(float32).resolution (utils/utils.py:304-313)
+
+
+def tanh_correction(tanh_actions):
+    """the term the reference SUBTRACTS from Normal.log_prob for `tanh_normal` (ppo/agent.py:201-205, 264-268)"""
+    return 2.0 * (math.log(2.0) - tanh_actions - F.softplus(-2.0 * tanh_actions)).sum(-1, keepdim=True)
 
 
 def ppo_forward(p, spec, obs: Dict[str, torch.Tensor], actions: torch.Tensor):
@@ -101,17 +132,21 @@ def ppo_forward(p, spec, obs: Dict[str, torch.Tensor], actions: torch.Tensor):
         feats.append(torch.relu(F.linear(x, p["feature_extractor.cnn_encoder.model.fc.weight"],
                                          p["feature_extractor.cnn_encoder.model.fc.bias"])))
     if spec["mlp_dim"]:
-        feats.append(_mlp(p, "feature_extractor.mlp_encoder.model", obs["state"], spec["layers"], act))
+        feats.append(_mlp(p, "feature_extractor.mlp_encoder.model", obs["state"], net_cfg(spec, "encoder"), act))
     feat = torch.cat(feats, -1)
-    values = _mlp(p, "critic", feat, spec["layers"], act)
-    h = _mlp(p, "actor.actor_backbone", feat, spec["layers"], act, last=False)
+    values = _mlp(p, "critic", feat, net_cfg(spec, "critic"), act)
+    h = _mlp(p, "actor.actor_backbone", feat, net_cfg(spec, "actor"), act, last=False)
     if spec["is_continuous"]:
         out = F.linear(h, p["actor.actor_heads.0.weight"], p["actor.actor_heads.0.bias"])
         mean, log_std = out.chunk(2, -1)
         std = log_std.exp()
+        corr = 0.0
+        if spec.get("dist", "normal") == "tanh_normal":                 # stored actions are tanh-squashed (agent.py:194-206)
+            corr = tanh_correction(actions)
+            actions = torch.atanh(actions.clamp(-SAFE_LIM, SAFE_LIM))
         lp = (-((actions - mean) ** 2) / (2 * std ** 2) - log_std - math.log(math.sqrt(2 * math.pi))).sum(-1, keepdim=True)
         ent = (0.5 + 0.5 * math.log(2 * math.pi) + log_std).sum(-1, keepdim=True)
-        return lp, ent, values
+        return lp - corr, ent, values
     lps, ents, off = [], [], 0
     for i, a in enumerate(spec["actions_dim"]):
         logits = F.linear(h, p[f"actor.actor_heads.{i}.weight"], p[f"actor.actor_heads.{i}.bias"])
@@ -176,6 +211,8 @@ def make_rollout(spec, N: int, seed: int) -> Dict[str, torch.Tensor]:
         d["state"] = torch.randn(N, spec["mlp_dim"], generator=g)
     if spec["is_continuous"]:
         d["actions"] = torch.randn(N, sum(spec["actions_dim"]), generator=g)
+        if spec.get("dist", "normal") == "tanh_normal":
+            d["actions"] = torch.tanh(d["actions"]).clamp(-SAFE_LIM, SAFE_LIM)
     else:
         d["actions"] = torch.cat([F.one_hot(torch.randint(0, a, (N,), generator=g), a).float()
                                   for a in spec["actions_dim"]], -1)

@@ -13,28 +13,67 @@ from sheeprl_b200.algos.ppo.engine import PPOEngine
 
 
 def spec_from_cfg(cfg, actions_dim: Sequence[int], is_continuous: bool, obs_space) -> dict:
+    """engine spec from the reference's config tree (ppo/agent.py:99-184, configs/algo/ppo.yaml)"""
     a = cfg.algo
     cnn_keys, mlp_keys = list(a.cnn_keys.encoder or []), list(a.mlp_keys.encoder or [])
-    if len(cnn_keys) > 1 or len(mlp_keys) > 1:
-        raise NotImplementedError("the B200 PPO engine takes at most one image key and one vector key")
     dist = str(cfg.distribution.get("type", "auto")).lower()
-    if dist == "tanh_normal":
-        raise NotImplementedError("distribution.type=tanh_normal is not built yet (auto / discrete / normal are)")
-    if a.encoder.layer_norm or a.actor.layer_norm or a.critic.layer_norm:
-        raise NotImplementedError("layer_norm=True MLPs are not built for PPO yet")
+    if dist not in ("auto", "normal", "tanh_normal", "discrete"):
+        raise ValueError("The distribution must be on of: `auto`, `discrete`, `normal` and `tanh_normal`. "
+                         f"Found: {dist}")                                            # ppo/agent.py:109-113
+    if dist == "discrete" and is_continuous:
+        raise ValueError("You have choose a discrete distribution but `is_continuous` is true")
+    if dist not in ("discrete", "auto") and not is_continuous:
+        raise ValueError("You have choose a continuous distribution but `is_continuous` is false")
+    if dist == "auto":
+        dist = "normal" if is_continuous else "discrete"
     acts = {str(a.encoder.dense_act), str(a.actor.dense_act), str(a.critic.dense_act)}
     if len(acts) != 1 or acts.pop().rsplit(".", 1)[-1] not in ("Tanh", "ReLU"):
         raise NotImplementedError("dense_act must be torch.nn.Tanh or torch.nn.ReLU, the same for encoder/actor/critic")
-    if not (a.encoder.dense_units == a.actor.dense_units == a.critic.dense_units
-            and a.encoder.mlp_layers == a.actor.mlp_layers == a.critic.mlp_layers):
-        raise NotImplementedError("encoder / actor / critic must share dense_units and mlp_layers")
+    if mlp_keys and int(a.encoder.mlp_layers) == 0:
+        raise NotImplementedError("encoder.mlp_layers == 0 (identity vector encoder) is not built")
+    if mlp_keys and not a.encoder.mlp_features_dim:
+        raise NotImplementedError("encoder.mlp_features_dim must be set")
+    cnn = [(k, int(math.prod(obs_space[k].shape[:-2]))) for k in cnn_keys]
+    mlp = [(k, int(obs_space[k].shape[0])) for k in mlp_keys]
     return dict(
-        cnn_channels=int(math.prod(obs_space[cnn_keys[0]].shape[:-2])) if cnn_keys else 0,
-        screen=int(cfg.env.screen_size) if cnn_keys else 0, cnn_key=cnn_keys[0] if cnn_keys else None,
-        mlp_dim=int(obs_space[mlp_keys[0]].shape[0]) if mlp_keys else 0, mlp_key=mlp_keys[0] if mlp_keys else None,
-        dense=int(a.actor.dense_units), layers=int(a.actor.mlp_layers), cnn_features=int(a.encoder.cnn_features_dim),
-        mlp_features=int(a.encoder.mlp_features_dim), actions_dim=tuple(int(x) for x in actions_dim),
-        is_continuous=bool(is_continuous), act="tanh" if str(a.actor.dense_act).endswith("Tanh") else "relu")
+        cnn_channels=sum(c for _, c in cnn), screen=int(cfg.env.screen_size) if cnn_keys else 0, cnn_keys=cnn,
+        mlp_dim=sum(d for _, d in mlp), mlp_keys=mlp,
+        dense=int(a.actor.dense_units), layers=int(a.actor.mlp_layers),
+        nets={w: (int(a[w].dense_units), int(a[w].mlp_layers)) for w in ("encoder", "actor", "critic")},
+        layer_norm={w: bool(a[w].layer_norm) for w in ("encoder", "actor", "critic")},
+        cnn_features=int(a.encoder.cnn_features_dim), mlp_features=int(a.encoder.mlp_features_dim or 0),
+        actions_dim=tuple(int(x) for x in actions_dim), is_continuous=bool(is_continuous), dist=dist,
+        act="tanh" if str(a.actor.dense_act).endswith("Tanh") else "relu")
+
+
+def obs_key_names(spec: dict):
+    """([image keys], [vector keys]) in the order the encoders concatenate them (ppo/agent.py:34-36, 67-69)"""
+    cnn = [k for k, _ in spec.get("cnn_keys") or []] or ([spec.get("cnn_key") or "rgb"] if spec["cnn_channels"] else [])
+    mlp = [k for k, _ in spec.get("mlp_keys") or []] or ([spec.get("mlp_key") or "state"] if spec["mlp_dim"] else [])
+    return cnn, mlp
+
+
+def gather_obs(spec: dict, data, lead_dims: int = 1):
+    """(image tensor [N, C_total, H, W] or None, vector tensor [N, D_total] or None) from a dict of per-key tensors:
+    the concatenation the reference's encoders do on every forward, done once here.  A dict that already holds the
+    concatenated "rgb" / "state" tensors is accepted as is."""
+    cnn, mlp = obs_key_names(spec)
+    rgb = state = None
+    if cnn:
+        if all(k in data for k in cnn):
+            parts = [data[k].reshape(-1, *data[k].shape[-3:]) for k in cnn]
+        else:
+            parts = [data["rgb"].reshape(-1, *data["rgb"].shape[-3:])]
+        if any(p.dtype != parts[0].dtype for p in parts) or parts[0].dtype not in (torch.uint8, torch.float32):
+            parts = [p.float() for p in parts]
+        rgb = (parts[0] if len(parts) == 1 else torch.cat(parts, 1)).contiguous()
+    if mlp:
+        if all(k in data for k in mlp):
+            parts = [data[k].reshape(-1, data[k].shape[-1]).float() for k in mlp]
+        else:
+            parts = [data["state"].reshape(-1, data["state"].shape[-1]).float()]
+        state = (parts[0] if len(parts) == 1 else torch.cat(parts, 1)).contiguous()
+    return rgb, state
 
 
 def hp_from_cfg(cfg) -> dict:
@@ -98,30 +137,29 @@ class PPOPlayer:
         self._acts: Dict[int, tuple] = {}
 
     class _ActorInfo:
-        def __init__(self, spec):
-            self.is_continuous, self.distribution = spec["is_continuous"], "normal" if spec["is_continuous"] else "discrete"
+        def __init__(self, engine):
+            self.is_continuous, self.distribution = engine.spec["is_continuous"], engine.dist
 
     @property
     def actor(self):
-        return PPOPlayer._ActorInfo(self.engine.spec)
+        return PPOPlayer._ActorInfo(self.engine)
 
     def _run(self, obs, actor: bool, critic: bool):
         e, s = self.engine, self.engine.spec
-        rgb = x_state = None
-        E = None
+        rgb, x_state = gather_obs(s, obs)
         normalized = False
-        if s["cnn_channels"]:
-            rgb = obs[s.get("cnn_key") or "rgb"].reshape(-1, s["cnn_channels"], s["screen"], s["screen"]).contiguous()
+        if rgb is not None:
             E, normalized = rgb.shape[0], rgb.dtype != torch.uint8
-        if s["mlp_dim"]:
-            x_state = obs[s.get("mlp_key") or "state"].reshape(-1, s["mlp_dim"]).float().contiguous().unsqueeze(0)
+        if x_state is not None:
+            x_state = x_state.unsqueeze(0)
             E = x_state.shape[1]
         b = e._buffers(E)
         e.forward(b, rgb, x_state, rgb_normalized=normalized, actor=actor, critic=critic)
         return b, E
 
-    def _sample(self, b, E, greedy: bool, noise):
+    def _sample(self, b, E, greedy: bool, noise, get_actions: bool = False):
         e = self.engine
+        mode = e.dist_mode + (1 if (get_actions and e.dist == "tanh_normal") else 0)   # csrc/ppo.cu ppo_act modes
         A = sum(e.head_dims)
         if E not in self._acts:
             f = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=e.device)  # noqa: E731
@@ -132,7 +170,7 @@ class PPOPlayer:
             (e.ops.fill_normal if e.spec["is_continuous"] else e.ops.fill_exponential)(nz.view(-1), self.rng_seed, 21, self._ctr)
             noise = nz
         e.ops.ppo_act(b["head"][0], None if greedy else noise.reshape(E, A).contiguous(), acts, logp, e.head_dims,
-                      e.spec["is_continuous"], greedy)
+                      mode, greedy)
         if e.spec["is_continuous"]:
             return (acts.clone(),), logp.clone().unsqueeze(-1)
         out, off = [], 0
@@ -157,7 +195,7 @@ class PPOPlayer:
     @torch.no_grad()
     def get_actions(self, obs, greedy: bool = False, noise=None):
         b, E = self._run(obs, True, False)
-        return self._sample(b, E, greedy, noise)[0]
+        return self._sample(b, E, greedy, noise, get_actions=True)[0]
 
 
 def build_agent(fabric, actions_dim: Sequence[int], is_continuous: bool, cfg: Dict[str, Any], obs_space,

@@ -24,6 +24,18 @@ import torch
 from sheeprl_b200.params import FlatGroup
 
 CONVS = ((8, 4, 32), (4, 2, 64), (3, 1, 64))        # NatureCNN (kernel, stride, channels) models.py:301-309
+LN_EPS = 1e-5                                        # nn.LayerNorm default (ppo/agent.py:63-64 passes only the shape)
+ACT_CODE = {"none": 0, "tanh": 2, "relu": 3}         # b200rl_ln_act_* activation codes
+DIST_MODE = {"discrete": 0, "normal": 1, "tanh_normal": 2}
+
+
+def net_cfg(spec: dict, which: str):
+    """(dense_units, mlp_layers, layer_norm) of the "encoder" / "actor" / "critic" MLP: spec["nets"][which] = (dense,
+    layers) and spec["layer_norm"] (bool or per-net dict) override the shared spec["dense"] / spec["layers"]."""
+    dense, layers = (spec.get("nets") or {}).get(which, (spec["dense"], spec["layers"]))
+    ln = spec.get("layer_norm", False)
+    ln = bool(ln.get(which, False)) if isinstance(ln, dict) else bool(ln)
+    return int(dense), int(layers), ln
 
 
 class _Lin:
@@ -35,12 +47,38 @@ class _Lin:
         self.W, self.b = v[wkey].unsqueeze(0), v[bkey].unsqueeze(0)
         self.gW, self.gb = g[wkey].unsqueeze(0), g[bkey].unsqueeze(0)
         self.act = act
+        self.ln = None                                   # (gamma, beta, dgamma, dbeta) when a LayerNorm follows
+
+
+class _Stack:
+    """An `MLP` of the reference (models/models.py:17-126): `layers` hidden blocks Linear [-> LayerNorm] -> act, then an
+    output Linear without activation (absent for the actor backbone, whose output layer is the stacked action heads)."""
+
+    def __init__(self, eng, prefix: str, which: str, tag: str, last_key: Optional[str] = None):
+        dense, layers, ln = net_cfg(eng.spec, which)
+        st = 3 if ln else 2
+        v, g = eng.group.views, eng.group.gviews
+        self.tag, self.has_ln, self.dense = tag, ln, dense
+        self.lins: List[_Lin] = []
+        for i in range(layers):
+            lin = _Lin(eng, f"{prefix}._model.{st * i}.weight", eng.act)
+            if ln:
+                wk, bk = f"{prefix}._model.{st * i + 1}.weight", f"{prefix}._model.{st * i + 1}.bias"
+                lin.ln = (v[wk], v[bk], g[wk], g[bk])
+            self.lins.append(lin)
+        self.lins.append(_Lin(eng, last_key or f"{prefix}._model.{st * layers}.weight", "none"))
+
+    @property
+    def n_hidden(self):
+        return len(self.lins) - 1
 
 
 class PPOEngine:
     def __init__(self, spec: dict, hp: dict, opt: dict, device, ops, seed: int = 0):
         """spec: cnn_channels (0 = none), screen, mlp_dim (0 = none), dense, layers, cnn_features, mlp_features,
-        actions_dim, is_continuous, act ('tanh' | 'relu').  hp: clip_coef, vf_coef, ent_coef, clip_vloss,
+        actions_dim, is_continuous, act ('tanh' | 'relu') [, dist ('normal' | 'tanh_normal'), layer_norm (bool or
+        {"encoder"/"actor"/"critic": bool}), nets ({"encoder"/"actor"/"critic": (dense, layers)})].  cnn_channels /
+        mlp_dim are the sums over the image / vector keys (the encoders concatenate them, ppo/agent.py:34-36,67-69).  hp: clip_coef, vf_coef, ent_coef, clip_vloss,
         normalize_advantages, max_grad_norm.  opt: lr, eps, betas."""
         self.spec, self.hp, self.opt = dict(spec), dict(hp), dict(opt)
         self.device, self.ops = torch.device(device), ops
@@ -49,6 +87,10 @@ class PPOEngine:
         self.act = s.get("act", "tanh")
         self.head_dims = list(s["actions_dim"])
         self.head_width = 2 * sum(self.head_dims) if s["is_continuous"] else sum(self.head_dims)
+        self.dist = (s.get("dist") or "normal") if s["is_continuous"] else "discrete"
+        if self.dist not in DIST_MODE or (s["is_continuous"] and self.dist == "discrete"):
+            raise ValueError(f"distribution must be one of {sorted(DIST_MODE)}, got {self.dist!r}")
+        self.dist_mode = DIST_MODE[self.dist]
         self.F = s["cnn_features"] if s["cnn_channels"] else 0
         self.Mf = s["mlp_features"] if s["mlp_dim"] else 0
         self.feat_dim = self.F + self.Mf
@@ -77,40 +119,41 @@ class PPOEngine:
             _, _, _, _, _, Ho, Wo, Co = self.geo[-1]
             out[f"{pre}.fc.weight"] = (s["cnn_features"], Ho * Wo * Co)
             out[f"{pre}.fc.bias"] = (s["cnn_features"],)
-        L, D = s["layers"], s["dense"]
+        def stack(prefix, d, which, last):
+            dense, layers, ln = net_cfg(s, which)
+            st = 3 if ln else 2
+            for i in range(layers):
+                out[f"{prefix}._model.{st * i}.weight"] = (dense, d)
+                out[f"{prefix}._model.{st * i}.bias"] = (dense,)
+                if ln:
+                    out[f"{prefix}._model.{st * i + 1}.weight"] = (dense,)
+                    out[f"{prefix}._model.{st * i + 1}.bias"] = (dense,)
+                d = dense
+            if last is not None:
+                out[f"{prefix}._model.{st * layers}.weight"] = (last, d)
+                out[f"{prefix}._model.{st * layers}.bias"] = (last,)
+
         if s["mlp_dim"]:
-            d = s["mlp_dim"]
-            for i in range(L):
-                out[f"feature_extractor.mlp_encoder.model._model.{2 * i}.weight"] = (D, d)
-                out[f"feature_extractor.mlp_encoder.model._model.{2 * i}.bias"] = (D,)
-                d = D
-            out[f"feature_extractor.mlp_encoder.model._model.{2 * L}.weight"] = (s["mlp_features"], d)
-            out[f"feature_extractor.mlp_encoder.model._model.{2 * L}.bias"] = (s["mlp_features"],)
-        for net in ("critic", "actor.actor_backbone"):
-            d = self.feat_dim
-            for i in range(L):
-                out[f"{net}._model.{2 * i}.weight"] = (D, d)
-                out[f"{net}._model.{2 * i}.bias"] = (D,)
-                d = D
-            if net == "critic":
-                out[f"critic._model.{2 * L}.weight"] = (1, d)
-                out[f"critic._model.{2 * L}.bias"] = (1,)
-        out["actor.heads.weight"] = (self.head_width, D if L > 0 else self.feat_dim)
+            stack("feature_extractor.mlp_encoder.model", s["mlp_dim"], "encoder", s["mlp_features"])
+        stack("critic", self.feat_dim, "critic", 1)
+        stack("actor.actor_backbone", self.feat_dim, "actor", None)
+        # every head reads `actor.dense_units` inputs, also with an empty backbone (ppo/agent.py:180-183)
+        out["actor.heads.weight"] = (self.head_width, net_cfg(s, "actor")[0])
         out["actor.heads.bias"] = (self.head_width,)
         return out
 
     def _build_layers(self):
-        s, L = self.spec, self.spec["layers"]
+        s = self.spec
         pre = "feature_extractor.cnn_encoder.model"
         self.convs = [_Lin(self, f"{pre}._model.{2 * i}.weight", "relu") for i in range(len(self.geo))]
         for c in self.convs:                              # [1, Cout, k*k*Cin]
             c.W, c.gW = c.W.flatten(2), c.gW.flatten(2)
         self.fc = _Lin(self, f"{pre}.fc.weight", "relu") if self.geo else None
-        mp = "feature_extractor.mlp_encoder.model._model"
-        self.menc = ([_Lin(self, f"{mp}.{2 * i}.weight", self.act) for i in range(L)] + [_Lin(self, f"{mp}.{2 * L}.weight", "none")]
-                     if s["mlp_dim"] else [])
-        self.critic = [_Lin(self, f"critic._model.{2 * i}.weight", self.act) for i in range(L)] + [_Lin(self, f"critic._model.{2 * L}.weight", "none")]
-        self.actor = [_Lin(self, f"actor.actor_backbone._model.{2 * i}.weight", self.act) for i in range(L)] + [_Lin(self, "actor.heads.weight", "none")]
+        self.menc = _Stack(self, "feature_extractor.mlp_encoder.model", "encoder", "m") if s["mlp_dim"] else None
+        self.critic = _Stack(self, "critic", "critic", "c")
+        self.actor = _Stack(self, "actor.actor_backbone", "actor", "a", last_key="actor.heads.weight")
+        if self.actor.n_hidden == 0 and self.actor.dense != self.feat_dim:
+            raise ValueError("actor.mlp_layers == 0 needs actor.dense_units == feature dim (the heads read dense_units inputs)")
 
     def reference_shapes(self) -> "OrderedDict[str, tuple]":
         out = OrderedDict()
@@ -177,7 +220,7 @@ class PPOEngine:
         if B in self._bufs:
             return self._bufs[B]
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
-        s, D, L = self.spec, self.spec["dense"], self.spec["layers"]
+        s = self.spec
         b = {"idx": torch.zeros(B, dtype=torch.int64, device=self.device)}
         if self.geo:
             H, W, C = self.geo[0][:3]
@@ -187,10 +230,12 @@ class PPOEngine:
             b["dy"] = [f(1, B * Ho * Wo, Co) for (_, _, _, _, _, Ho, Wo, Co) in self.geo]
             b["dcol"] = [None] + [f(1, B * Ho * Wo, k * k * Ci) for (_, _, Ci, k, _, Ho, Wo, _) in self.geo[1:]]
         b["feat"], b["dfeat"] = f(1, B, self.feat_dim), f(1, B, self.feat_dim)
-        if s["mlp_dim"]:
-            b["mh"], b["dmh"] = [f(1, B, D) for _ in range(L)], [f(1, B, D) for _ in range(L)]
-        b["ch"], b["dch"] = [f(1, B, D) for _ in range(L)], [f(1, B, D) for _ in range(L)]
-        b["ah"], b["dah"] = [f(1, B, D) for _ in range(L)], [f(1, B, D) for _ in range(L)]
+        for st in (self.menc, self.critic, self.actor):
+            if st is None:
+                continue
+            n, D = st.n_hidden, st.dense
+            b[st.tag + "h"], b["d" + st.tag + "h"] = [f(1, B, D) for _ in range(n)], [f(1, B, D) for _ in range(n)]
+            b[st.tag + "pre"] = [f(1, B, D) for _ in range(n)] if st.has_ln else None     # pre-LayerNorm activations
         b["values"], b["dvalues"] = f(1, B, 1), f(1, B, 1)
         b["head"], b["dhead"] = f(1, B, self.head_width), f(1, B, self.head_width)
         self._bufs[B] = b
@@ -209,19 +254,33 @@ class PPOEngine:
             W = lin.W if Wcols is None else lin.W[:, :, Wcols[0]:Wcols[1]]
             o.bgemm(dpre, W, dx, aux=dx_aux, epi=dx_epi, accumulate=accumulate_dx)
 
-    def _mlp_fwd(self, layers: List[_Lin], x, hidden: list, out):
-        for i, lin in enumerate(layers):
-            y = hidden[i] if i < len(hidden) else out
-            self._fwd(lin, x, y)
+    def _mlp_fwd(self, st: _Stack, b: dict, x, out):
+        hidden, pre = b[st.tag + "h"], b[st.tag + "pre"]
+        for i, lin in enumerate(st.lins):
+            y = hidden[i] if i < st.n_hidden else out
+            if lin.ln is not None:                          # Linear -> LayerNorm -> act (utils/model.py:76-87)
+                self.ops.bgemm(x, lin.W.transpose(1, 2), pre[i], bias=lin.b)
+                self.ops.ln_act_fwd(pre[i][0], lin.ln[0], lin.ln[1], LN_EPS, ACT_CODE[lin.act], y[0])
+            else:
+                self._fwd(lin, x, y)
             x = y
 
-    def _mlp_bwd(self, layers: List[_Lin], x0, hidden: list, dhidden: list, dout):
-        """backward through a stack whose last layer has no activation; returns nothing (weight grads written)."""
+    def _mlp_bwd(self, st: _Stack, b: dict, dout):
+        """backward through the stack down to its first layer; weight / LayerNorm gradients of layers >= 1 are written,
+        the return value is the gradient w.r.t. layer 0's Linear output (the caller owns layer 0's products)."""
+        hidden, dhidden, pre = b[st.tag + "h"], b["d" + st.tag + "h"], b[st.tag + "pre"]
         dpre = dout
-        for i in range(len(layers) - 1, 0, -1):
-            self._bwd(layers[i], dpre, hidden[i - 1], dx=dhidden[i - 1], dx_epi="d" + layers[i - 1].act, dx_aux=hidden[i - 1])
+        for i in range(st.n_hidden, 0, -1):
+            below = st.lins[i - 1]
+            if below.ln is not None:
+                self._bwd(st.lins[i], dpre, hidden[i - 1], dx=dhidden[i - 1])
+                gam, bet, dgam, dbet = below.ln
+                self.ops.ln_act_bwd(pre[i - 1][0], gam, bet, LN_EPS, ACT_CODE[below.act], dhidden[i - 1][0], dhidden[i - 1][0],
+                                    dgam, dbet)
+            else:
+                self._bwd(st.lins[i], dpre, hidden[i - 1], dx=dhidden[i - 1], dx_epi="d" + below.act, dx_aux=hidden[i - 1])
             dpre = dhidden[i - 1]
-        return dpre                                         # pre-activation gradient of layer 0
+        return dpre
 
     def forward(self, b: dict, rgb, x_state, rgb_normalized: bool = False, actor: bool = True, critic: bool = True):
         """PPOAgent.forward up to the head / value outputs (ppo/agent.py:208-212) into the buffer set `b`.
@@ -242,12 +301,12 @@ class PPOEngine:
                 self._fwd(self.convs[i], b["col"][i], b["y"][i])
                 x = b["y"][i][0].view(B, Ho, Wo, Co)
             self._fwd(self.fc, b["y"][-1].view(1, B, -1), feat[:, :, :self.F])
-        if self.spec["mlp_dim"]:
-            self._mlp_fwd(self.menc, x_state, b["mh"], feat[:, :, self.F:])
+        if self.menc is not None:
+            self._mlp_fwd(self.menc, b, x_state, feat[:, :, self.F:])
         if critic:
-            self._mlp_fwd(self.critic, feat, b["ch"], b["values"])
+            self._mlp_fwd(self.critic, b, feat, b["values"])
         if actor:
-            self._mlp_fwd(self.actor, feat, b["ah"], b["head"])
+            self._mlp_fwd(self.actor, b, feat, b["head"])
 
     # ------------------------------------------------------------------ one minibatch
     def minibatch_step(self, data: Dict[str, torch.Tensor], idx: torch.Tensor):
@@ -270,21 +329,20 @@ class PPOEngine:
         # ---- objective + gradients w.r.t. head outputs and values
         o.ppo_loss(b["head"][0], rows("actions"), rows("logprobs").reshape(-1), rows("advantages").reshape(-1),
                    b["values"].reshape(-1), rows("values").reshape(-1), rows("returns").reshape(-1), b["dhead"][0],
-                   b["dvalues"].reshape(-1), self.losses, self.head_dims, s["is_continuous"], hp["clip_vloss"],
+                   b["dvalues"].reshape(-1), self.losses, self.head_dims, self.dist_mode, hp["clip_vloss"],
                    hp["normalize_advantages"], hp["clip_coef"], hp["vf_coef"], hp["ent_coef"])
         # ---- backward: actor, critic -> feature gradient (cnn columns masked by the fc ReLU)
         F_ = self.F
-        for j, (layers, hid, dhid, dout) in enumerate(((self.actor, b["ah"], b["dah"], b["dhead"]),
-                                                       (self.critic, b["ch"], b["dch"], b["dvalues"]))):
-            dpre0 = self._mlp_bwd(layers, feat, hid, dhid, dout)
-            o.bgemm(dpre0.transpose(1, 2), feat, layers[0].gW, rsum=layers[0].gb)
+        for j, (st, dout) in enumerate(((self.actor, b["dhead"]), (self.critic, b["dvalues"]))):
+            dpre0, l0 = self._mlp_bwd(st, b, dout), st.lins[0]
+            o.bgemm(dpre0.transpose(1, 2), feat, l0.gW, rsum=l0.gb)
             if F_:
-                o.bgemm(dpre0, layers[0].W[:, :, :F_], b["dfeat"][:, :, :F_], aux=feat[:, :, :F_], epi="drelu", accumulate=j > 0)
+                o.bgemm(dpre0, l0.W[:, :, :F_], b["dfeat"][:, :, :F_], aux=feat[:, :, :F_], epi="drelu", accumulate=j > 0)
             if self.Mf:
-                o.bgemm(dpre0, layers[0].W[:, :, F_:], b["dfeat"][:, :, F_:], accumulate=j > 0)
-        if s["mlp_dim"]:
-            dpre0 = self._mlp_bwd(self.menc, x_state, b["mh"], b["dmh"], b["dfeat"][:, :, F_:])
-            o.bgemm(dpre0.transpose(1, 2), x_state, self.menc[0].gW, rsum=self.menc[0].gb)
+                o.bgemm(dpre0, l0.W[:, :, F_:], b["dfeat"][:, :, F_:], accumulate=j > 0)
+        if self.menc is not None:
+            dpre0, l0 = self._mlp_bwd(self.menc, b, b["dfeat"][:, :, F_:]), self.menc.lins[0]
+            o.bgemm(dpre0.transpose(1, 2), x_state, l0.gW, rsum=l0.gb)
         if self.geo:
             n = len(self.geo)
             flat = b["y"][-1].view(1, B, -1)

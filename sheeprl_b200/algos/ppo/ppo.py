@@ -11,6 +11,7 @@ import torch
 from torch.utils.data import BatchSampler, DistributedSampler, RandomSampler
 
 from sheeprl_b200.algos.dreamer_v3.dreamer_v3 import B200Adam
+from sheeprl_b200.algos.ppo.agent import gather_obs
 from sheeprl_b200.utils.registry import register_algorithm
 
 METRIC_ORDER = ("Loss/policy_loss", "Loss/value_loss", "Loss/entropy_loss")
@@ -47,11 +48,11 @@ def train(fabric, agent, optimizer, data: Dict[str, torch.Tensor], aggregator, c
     s = eng.spec
     d = {k: data[k] for k in ("actions", "logprobs", "values", "returns", "advantages")}
     d = {k: (v if v.dtype == torch.float32 else v.float()).contiguous() for k, v in d.items()}
-    if s["cnn_channels"]:
-        v = data[s.get("cnn_key") or "rgb"]
-        d["rgb"] = (v if v.dtype in (torch.uint8, torch.float32) else v.float()).contiguous()
-    if s["mlp_dim"]:
-        d["state"] = data[s.get("mlp_key") or "state"].float().contiguous()
+    rgb, state = gather_obs(s, data)                      # per-key tensors -> the encoders' concatenated inputs
+    if rgb is not None:
+        d["rgb"] = rgb
+    if state is not None:
+        d["state"] = state
     n_rows = d["actions"].shape[0]
     it = index_batches if index_batches is not None else minibatch_indices(n_rows, fabric, cfg)
     log = aggregator is not None and not aggregator.disabled

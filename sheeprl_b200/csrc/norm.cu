@@ -8,7 +8,27 @@
 
 namespace {
 
-constexpr int ACT_NONE = 0, ACT_SILU = 1;
+constexpr int ACT_NONE = 0, ACT_SILU = 1, ACT_TANH = 2, ACT_RELU = 3;   // (2, 3: the PPO MLPs with layer_norm=True)
+
+__device__ __forceinline__ float act_fwd(int act, float o) {
+  if (act == ACT_SILU) return siluf_(o);
+  if (act == ACT_TANH) return tanhf(o);
+  if (act == ACT_RELU) return fmaxf(o, 0.f);
+  return o;
+}
+// dy * act'(ln)
+__device__ __forceinline__ float act_bwd(int act, float ln, float dy) {
+  if (act == ACT_SILU) {
+    const float sg = sigmoidf_(ln);
+    return dy * sg * (1.f + ln * (1.f - sg));
+  }
+  if (act == ACT_TANH) {
+    const float t = tanhf(ln);
+    return dy * (1.f - t * t);
+  }
+  if (act == ACT_RELU) return ln > 0.f ? dy : 0.f;
+  return dy;
+}
 
 __global__ void __launch_bounds__(256)
 ln_act_fwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -27,9 +47,7 @@ ln_act_fwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma, 
     const float rstd = rsqrtf(warp_sum(v) * invC + eps);
     float* y = Y + r * ldy;
     for (int c = lane; c < C; c += 32) {
-      float o = (x[c] - mu) * rstd * gamma[c] + beta[c];
-      if (act == ACT_SILU) o = siluf_(o);
-      y[c] = o;
+      y[c] = act_fwd(act, (x[c] - mu) * rstd * gamma[c] + beta[c]);
     }
   }
 }
@@ -66,12 +84,7 @@ ln_act_bwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma, 
     float s1 = 0.f, s2 = 0.f;
     auto body = [&](int c, float& accg, float& accb) {
       const float xh = (x[c] - mu) * rstd;
-      float dln = dy[c];
-      if (act == ACT_SILU) {
-        const float ln = xh * gamma[c] + beta[c];
-        const float sg = sigmoidf_(ln);
-        dln *= sg * (1.f + ln * (1.f - sg));
-      }
+      const float dln = (act == ACT_NONE) ? dy[c] : act_bwd(act, xh * gamma[c] + beta[c], dy[c]);
       const float dxh = dln * gamma[c];
       s1 += dxh;
       s2 = fmaf(dxh, xh, s2);
@@ -101,12 +114,7 @@ ln_act_bwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma, 
     float* dx = dX + r * lddx;
     for (int c = lane; c < C; c += 32) {
       const float xh = (x[c] - mu) * rstd;
-      float dln = dy[c];
-      if (act == ACT_SILU) {
-        const float ln = xh * gamma[c] + beta[c];
-        const float sg = sigmoidf_(ln);
-        dln *= sg * (1.f + ln * (1.f - sg));
-      }
+      const float dln = (act == ACT_NONE) ? dy[c] : act_bwd(act, xh * gamma[c] + beta[c], dy[c]);
       dx[c] = rstd * (dln * gamma[c] - s1 - xh * s2);  // dX may alias dY: element c is read before it is written
     }
   }
@@ -201,7 +209,7 @@ ln_act_fwd_vec_kernel(const float* __restrict__ X, const float* __restrict__ gam
         o.y = (v[i].y - mu) * rstd * g[i].y + b[i].y;
         o.z = (v[i].z - mu) * rstd * g[i].z + b[i].z;
         o.w = (v[i].w - mu) * rstd * g[i].w + b[i].w;
-        if (act == ACT_SILU) { o.x = siluf_(o.x); o.y = siluf_(o.y); o.z = siluf_(o.z); o.w = siluf_(o.w); }
+        if (act != ACT_NONE) { o.x = act_fwd(act, o.x); o.y = act_fwd(act, o.y); o.z = act_fwd(act, o.z); o.w = act_fwd(act, o.w); }
         reinterpret_cast<float4*>(Y + r * ldy)[lr + i * LPR] = o;
       }
     }
@@ -232,11 +240,7 @@ ln_act_bwd_vec_kernel(const float* __restrict__ X, const float* __restrict__ gam
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invC = 1.f / (float)C;
-  auto dact = [&](float ln, float dy) -> float {
-    if (act != ACT_SILU) return dy;
-    const float sg = sigmoidf_(ln);
-    return dy * sg * (1.f + ln * (1.f - sg));
-  };
+  auto dact = [&](float ln, float dy) -> float { return act_bwd(act, ln, dy); };
   for (long long r0 = gwarp * RPW; r0 < M; r0 += nwarps * RPW) {
     const long long r = r0 + sub;
     const bool ok = r < M;
@@ -328,6 +332,7 @@ extern "C" int b200rl_ln_act_fwd(const float* X, const float* gamma, const float
                                  long long ldx, long long ldy, float eps, int act, cudaStream_t st) {
   RL_CHECK_ARG(X && gamma && beta && Y, "null pointer");
   RL_CHECK_ARG(C > 0 && ldx >= C && ldy >= C, "bad C / ld");
+  RL_CHECK_ARG(act >= ACT_NONE && act <= ACT_RELU, "act must be 0 (none), 1 (SiLU), 2 (tanh) or 3 (ReLU)");
   if (M <= 0) return B200RL_OK;
   if (vec_ok(C, ldx, ldy, 0, X, Y, nullptr, gamma, beta)) {
 #define LN_FWD_VEC(LPR_, NV_) \
@@ -356,6 +361,7 @@ extern "C" int b200rl_ln_act_bwd(const float* X, const float* gamma, const float
   RL_CHECK_ARG(X && gamma && beta && dY && dX, "null pointer");
   RL_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "dgamma/dbeta must both be given or both be null");
   RL_CHECK_ARG(C > 0 && ldx >= C && lddy >= C && lddx >= C, "bad C / ld");
+  RL_CHECK_ARG(act >= ACT_NONE && act <= ACT_RELU, "act must be 0 (none), 1 (SiLU), 2 (tanh) or 3 (ReLU)");
   if (dgamma && !accumulate) {
     RL_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st));
     RL_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st));

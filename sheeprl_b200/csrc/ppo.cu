@@ -15,6 +15,16 @@
 
 namespace {
 
+// `tanh_normal` (ppo/agent.py:194-206, 257-268): stored actions are tanh-squashed; x = safeatanh(a) with the clamp
+// 1 - finfo(float32).resolution (utils/utils.py:304-313) and the reference's log-prob term 2*(log 2 - a - softplus(-2a)).
+constexpr float kSafeLim = 0.999999f;
+__device__ __forceinline__ float safe_atanh(float y) { return atanhf(fminf(fmaxf(y, -kSafeLim), kSafeLim)); }
+__device__ __forceinline__ float tanh_logp_term(float ta) {
+  const float v = -2.f * ta;
+  const float sp = v > 20.f ? v : log1pf(expf(v));          // torch softplus (threshold 20)
+  return 2.f * (0.6931471805599453f - ta - sp);
+}
+
 // col[(b,oy,ox), (ky,kx,c)] = x[b, oy*s+ky, ox*s+kx, c]      (no padding: NatureCNN uses none)
 __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int k,
                               int s, int Ho, int Wo) {
@@ -67,7 +77,7 @@ struct PpoLossArgs {
   const float* old_logp; const float* adv; const float* values; const float* old_values; const float* returns;
   float* dhead; float* dvalues; float* losses;   // losses[3] = policy, value, entropy
   int B, n_heads; int head_dims[8];
-  int is_continuous, clip_vloss, normalize_adv;
+  int is_continuous, clip_vloss, normalize_adv;   // is_continuous: 0 discrete, 1 Normal, 2 tanh-squashed Normal
   float clip_coef, vf_coef, ent_coef;
 };
 
@@ -98,11 +108,15 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const PpoLossArgs a) {
     // ---- pass 1: log-prob of the taken action and entropy (ppo/agent.py:179-239)
     if (a.is_continuous) {
       const int A = width / 2;
+      float corr = 0.f;
       for (int j = 0; j < A; ++j) {
-        const float mu = hd[j], ls = hd[A + j], sd = expf(ls), d = a.actions[(long long)b * A + j] - mu;
+        float x = a.actions[(long long)b * A + j];
+        if (a.is_continuous == 2) { corr += tanh_logp_term(x); x = safe_atanh(x); }
+        const float mu = hd[j], ls = hd[A + j], sd = expf(ls), d = x - mu;
         lp += -(d * d) / (2.f * sd * sd) - ls - 0.9189385332046727f;
         ent += 0.5f + 0.9189385332046727f + ls;
       }
+      lp -= corr;
     } else {
       int off = 0;
       for (int h = 0; h < a.n_heads; ++h) {
@@ -151,7 +165,9 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const PpoLossArgs a) {
     if (a.is_continuous) {
       const int A = width / 2;
       for (int j = 0; j < A; ++j) {
-        const float mu = hd[j], ls = hd[A + j], sd = expf(ls), d = a.actions[(long long)b * A + j] - mu;
+        float x = a.actions[(long long)b * A + j];
+        if (a.is_continuous == 2) x = safe_atanh(x);             // the squash term does not depend on the head
+        const float mu = hd[j], ls = hd[A + j], sd = expf(ls), d = x - mu;
         dh[j] = dlp * d / (sd * sd);
         dh[A + j] = dlp * (d * d / (sd * sd) - 1.f) + dent;
       }
@@ -202,12 +218,22 @@ __global__ void ppo_act_kernel(const float* __restrict__ head, const float* __re
   if (is_continuous) {
     const int A = width;
     const float* hd = head + (long long)b * 2 * A;
+    // is_continuous: 1 Normal; 2 tanh_normal as PPOPlayer.forward returns it (safetanh of the sample, corrected
+    // log-prob, agent.py:257-268); 3 tanh_normal as PPOPlayer.get_actions returns it (safeatanh of the sample / mean,
+    // agent.py:306-311 — the reference's behaviour, kept as is)
     for (int j = 0; j < A; ++j) {
       const float mu = hd[j], ls = hd[A + j], sd = expf(ls);
       const float e = (greedy || !noise) ? 0.f : noise[(long long)b * A + j];
-      const float a = mu + sd * e, d = a - mu;
-      actions[(long long)b * A + j] = a;
+      float a = mu + sd * e;
+      const float d = a - mu;
       lp += -(d * d) / (2.f * sd * sd) - ls - 0.9189385332046727f;
+      if (is_continuous == 2) {
+        a = fminf(fmaxf(tanhf(a), -kSafeLim), kSafeLim);
+        lp -= tanh_logp_term(a);
+      } else if (is_continuous == 3) {
+        a = safe_atanh(a);
+      }
+      actions[(long long)b * A + j] = a;
     }
   } else {
     const float* hd = head + (long long)b * width;
@@ -272,6 +298,7 @@ extern "C" int b200rl_ppo_loss(const float* head, const float* actions, const fl
                "null pointer");
   RL_CHECK_ARG(B > 0 && n_heads > 0 && n_heads <= 8 && head_dims, "bad dims (at most 8 action heads)");
   RL_CHECK_ARG(!normalize_adv || B > 1, "advantage normalisation needs at least two rows");
+  RL_CHECK_ARG(is_continuous >= 0 && is_continuous <= 2, "is_continuous: 0 discrete, 1 normal, 2 tanh_normal");
   PpoLossArgs a{};
   a.head = head; a.actions = actions; a.old_logp = old_logp; a.adv = adv; a.values = values;
   a.old_values = old_values; a.returns = returns; a.dhead = dhead; a.dvalues = dvalues; a.losses = losses;
@@ -288,6 +315,7 @@ extern "C" int b200rl_ppo_act(const float* head, const float* noise, float* acti
                               const int* head_dims, int n_heads, int is_continuous, int greedy, cudaStream_t st) {
   RL_CHECK_ARG(head && actions && logp && head_dims, "null pointer");
   RL_CHECK_ARG(B > 0 && n_heads > 0 && n_heads <= 8, "bad dims (at most 8 action heads)");
+  RL_CHECK_ARG(is_continuous >= 0 && is_continuous <= 3, "is_continuous: 0 discrete, 1 normal, 2 / 3 tanh_normal");
   PpoLossArgs d{};
   for (int i = 0; i < n_heads; ++i) d.head_dims[i] = head_dims[i];
   ppo_act_kernel<<<ceil_div(B, 128), 128, 0, st>>>(head, noise, actions, logp, B, n_heads, d, is_continuous, greedy);

@@ -172,7 +172,9 @@ class DV3Engine:
         a, w = cfg.algo, cfg.algo.world_model
         self.is_continuous = bool(is_continuous)
         if self.is_continuous and str(cfg.distribution.get("type", "auto")).lower() not in ("auto", "scaled_normal"):
-            raise NotImplementedError("continuous actions: only distribution.type = auto / scaled_normal is built")
+            raise NotImplementedError(
+                "continuous actions: distribution.type must be auto / scaled_normal — the reference's own train() fails "
+                "with tanh_normal (entropy fallback shape, dreamer_v3.py:294-297) and normal (negative scale)")
         if a.mlp_keys.encoder:
             raise NotImplementedError("vector (mlp_keys) observations are not implemented in the B200 engine yet")
         if w.decoupled_rssm:

@@ -128,6 +128,30 @@ def test_ln_act(ops, M, C, act):
     close(dYg, dXc, rtol=2e-5, what="ln dX in place")
 
 
+@pytest.mark.parametrize("M,C", [(1000, 32), (37, 72), (64, 64), (16, 1536), (256, 24)])
+@pytest.mark.parametrize("act", [2, 3])
+def test_ln_act_tanh_relu(ops, M, C, act):
+    """LayerNorm + tanh / ReLU (PPO MLPs with layer_norm=True, eps 1e-5).  ReLU'(0) is a jump: the inputs are re-drawn
+    until no LayerNorm output sits within 1e-5 of it, so a 1-ulp difference cannot flip a mask bit."""
+    cu, em = ops
+    for seed in range(1, 40):
+        X, gam, bet, dY = rnd(M, C, seed=seed, scale=2.0), rnd(C, seed=seed + 100) + 1.0, rnd(C, seed=seed + 200), rnd(M, C, seed=seed + 300)
+        ln = torch.nn.functional.layer_norm(X, (C,), gam, bet, 1e-5)
+        if act != 3 or float(ln.abs().min()) > 1e-5:
+            break
+    Yc, Yg = torch.empty(M, C), torch.empty(M, C, device="cuda")
+    em.ln_act_fwd(X, gam, bet, 1e-5, act, Yc)
+    cu.ln_act_fwd(X.cuda(), gam.cuda(), bet.cuda(), 1e-5, act, Yg)
+    close(Yg, Yc, what="ln fwd")
+    dXc, dgc, dbc = torch.empty(M, C), torch.empty(C), torch.empty(C)
+    dXg, dgg, dbg = torch.empty(M, C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    em.ln_act_bwd(X, gam, bet, 1e-5, act, dY, dXc, dgc, dbc)
+    cu.ln_act_bwd(X.cuda(), gam.cuda(), bet.cuda(), 1e-5, act, dY.cuda(), dXg, dgg, dbg)
+    close(dXg, dXc, rtol=2e-5, what="ln dX")
+    close(dgg, dgc, rtol=2e-5 * max(M, 16) ** 0.5 / 4, what="ln dgamma")
+    close(dbg, dbc, rtol=2e-5 * max(M, 16) ** 0.5 / 4, what="ln dbeta")
+
+
 @pytest.mark.parametrize("M,C", [(1024, 255), (1048576 // 64, 3), (17, 4096), (3, 1)])
 def test_col_sum(ops, M, C):
     cu, em = ops

@@ -45,14 +45,19 @@ def test_im2col_col2im(cu, B, H, C, k, s):
         close(dx_g, dx_w, what="col2im")
 
 
-@pytest.mark.parametrize("cont,clipv,norm", [(False, False, False), (False, True, True), (True, False, True), (True, True, False)])
+@pytest.mark.parametrize("cont,clipv,norm", [(False, False, False), (False, True, True), (True, False, True), (True, True, False),
+                                             (2, True, True), (2, False, False)])
 def test_ppo_loss_kernel(cu, cont, clipv, norm):
+    """cont: False discrete, True `normal`, 2 `tanh_normal` (stored actions tanh-squashed, some at the clamp)"""
     em = EmulOps()
     B, dims = 300, [4, 3]
     width = 2 * sum(dims) if cont else sum(dims)
     g = torch.Generator().manual_seed(5)
     head = rnd(B, width, seed=1)
-    if cont:
+    if cont == 2:
+        actions = torch.tanh(rnd(B, sum(dims), seed=2) * 1.5)
+        actions[:5] = torch.tensor([1.0, -1.0, 0.9999995, 0.0, -0.99999]).unsqueeze(-1)      # clamp region of safeatanh
+    elif cont:
         actions = rnd(B, sum(dims), seed=2)
     else:
         actions = torch.cat([torch.nn.functional.one_hot(torch.randint(0, n, (B,), generator=g), n).float() for n in dims], -1)
@@ -100,7 +105,24 @@ def test_full_size_pixel_minibatch_against_oracle(cu):
     assert_params_close(eng.export_reference_state(), p, "pixel64", steps=2)
 
 
-@pytest.mark.parametrize("name", ["ppo_branches", "ppo_continuous", "ppo_pixel"])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("greedy", [False, True])
+def test_ppo_act_continuous_modes(cu, mode, greedy):
+    """b200rl_ppo_act on a Normal head: 1 `normal`, 2 `tanh_normal` as forward() returns it, 3 as get_actions() does"""
+    em = EmulOps()
+    B, dims = 257, [3, 2]
+    A = sum(dims)
+    head, noise = rnd(B, 2 * A, seed=1), rnd(B, A, seed=2)
+    head[:4, :A] = torch.tensor([9.0, -9.0, 0.0, 20.0]).unsqueeze(-1)                        # saturating tanh / clamp
+    aw, lw = torch.zeros(B, A), torch.zeros(B)
+    ag, lg = torch.zeros(B, A, device="cuda"), torch.zeros(B, device="cuda")
+    em.ppo_act(head, noise, aw, lw, dims, mode, greedy)
+    cu.ppo_act(head.cuda(), noise.cuda(), ag, lg, dims, mode, greedy)
+    close(ag, aw, rtol=2e-5, atol=2e-6, what="actions")
+    close(lg, lw, rtol=1e-4, atol=1e-5, what="logp")
+
+
+@pytest.mark.parametrize("name", ["ppo_branches", "ppo_continuous", "ppo_pixel", "ppo_tanh_ln", "ppo_multikey"])
 @pytest.mark.parametrize("uint8_image", [False, True])
 def test_player_matches_reference(cu, name, uint8_image):
     from tests.test_ppo_cpu import check_player

@@ -9,7 +9,7 @@ from oracle import ppo_oracle as PO
 from oracle.dv3_oracle import AdamState
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-NAMES = ["ppo_vector", "ppo_branches", "ppo_continuous", "ppo_pixel"]
+NAMES = ["ppo_vector", "ppo_branches", "ppo_continuous", "ppo_pixel", "ppo_tanh_ln", "ppo_multikey"]
 
 
 def load(name):
@@ -76,25 +76,24 @@ def test_engine_schedule_matches_reference(name):
     check_engine(fx, make_engine(fx), name)
 
 
-def test_public_api_draws_the_reference_minibatches():
+@pytest.mark.parametrize("name", ["ppo_branches", "ppo_tanh_ln", "ppo_multikey"])
+def test_public_api_draws_the_reference_minibatches(name):
     """train() without explicit indices uses torch's RandomSampler/BatchSampler exactly as the reference: under the
-    fixture's sampler seed it visits the recorded minibatches and lands on the reference's parameters."""
-    from oracle.make_golden_ppo import ppo_cfg
+    fixture's sampler seed it visits the recorded minibatches and lands on the reference's parameters.  The config
+    tree is the one the reference was run with (layer_norm / distribution / per-network sizes / several obs keys) and
+    the rollout holds one tensor per observation key."""
+    from oracle.make_golden_ppo import obs_space, ppo_cfg, split_obs
     from oracle.ops_emul import EmulOps
     from sheeprl_b200.algos.ppo.agent import build_agent
     from sheeprl_b200.algos.ppo.ppo import make_optimizer, train
 
-    fx = load("ppo_branches")
+    fx = load(name)
 
     class Fab:
         device, world_size, global_rank = torch.device("cpu"), 1, 0
 
-    class Space:
-        def __init__(self, shape):
-            self.shape = shape
-
     cfg = ppo_cfg(fx["spec"], fx["hp"], fx["batch"], fx["epochs"])
-    agent, _ = build_agent(Fab, fx["spec"]["actions_dim"], False, cfg, {"state": Space((fx["spec"]["mlp_dim"],))},
+    agent, _ = build_agent(Fab, fx["spec"]["actions_dim"], fx["spec"]["is_continuous"], cfg, obs_space(fx["spec"]),
                            agent_state=fx["init"], ops=EmulOps())
     opt = make_optimizer(agent, cfg)
 
@@ -107,7 +106,7 @@ def test_public_api_draws_the_reference_minibatches():
 
     Agg = _Agg()
     torch.manual_seed(fx["sampler_seed"])
-    train(Fab, agent, opt, dict(fx["data"]), Agg, cfg)
+    train(Fab, agent, opt, split_obs(fx["spec"], fx["data"]), Agg, cfg)
     assert len(Agg.rows) == 3 * len(fx["losses"])
     assert abs(Agg.rows[-1][1] - fx["losses"][-1]["Loss/entropy_loss"]) < 1e-4
     assert_params_close(agent.state_dict(), fx["after"], "public", steps=len(fx["losses"]))
@@ -124,9 +123,13 @@ def check_player(name, device="cpu", ops=None, uint8_image=False):
     fx = load(name)
     eng = make_engine(fx, device=device, ops=ops)
     player = PPOPlayer(eng)
+    from oracle.make_golden_ppo import split_obs
+
     obs = {k: v.to(device) for k, v in pf["obs"].items()}
     if uint8_image and "rgb" in obs:
         obs["rgb"] = torch.round((obs["rgb"] + 0.5) * 255).to(torch.uint8)
+    obs = split_obs(fx["spec"], obs)                       # one tensor per observation key, as the rollout loop passes
+    assert player.actor.distribution == (fx["spec"].get("dist", "normal") if fx["spec"]["is_continuous"] else "discrete")
     actions, logp, values = player(obs, noise=pf["noise"].to(device))
     cont = fx["spec"]["is_continuous"]
     for got, want in zip(actions, pf["actions"]):
@@ -138,9 +141,15 @@ def check_player(name, device="cpu", ops=None, uint8_image=False):
     assert float((values.cpu() - pf["values"]).abs().max()) <= 1e-4 * max(1.0, float(pf["values"].abs().max()))
     assert float((player.get_values(obs).cpu() - pf["values2"]).abs().max()) <= 1e-4 * max(1.0, float(pf["values2"].abs().max()))
     for got, want in zip(player.get_actions(obs, greedy=True), pf["greedy"]):
-        assert float((got.cpu() - want).abs().max()) <= 1e-5
+        assert float((got.cpu() - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+    if pf.get("sampled") is not None:                      # get_actions(greedy=False) on the same injected noise
+        for got, want in zip(player.get_actions(obs, greedy=False, noise=pf["noise"].to(device)), pf["sampled"]):
+            assert float((got.cpu() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
 
 
-@pytest.mark.parametrize("name", ["ppo_branches", "ppo_continuous", "ppo_pixel"])
+PLAYER_NAMES = ["ppo_branches", "ppo_continuous", "ppo_pixel", "ppo_tanh_ln", "ppo_multikey"]
+
+
+@pytest.mark.parametrize("name", PLAYER_NAMES)
 def test_player_matches_reference(name):
     check_player(name)
