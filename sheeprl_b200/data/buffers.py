@@ -33,6 +33,21 @@ import torch
 _MEMMAP_MODES = ("r+", "w+", "c", "copyonwrite", "readwrite", "write")
 
 
+def _restore_device(name: str) -> torch.device:
+    """device of an unpickled buffer: where it was, or the host when that accelerator is absent (the kernels then
+    refuse to run, as everywhere else)"""
+    dev = torch.device(name)
+    if dev.type == "cuda" and not torch.cuda.is_available():
+        return torch.device("cpu")
+    return dev
+
+
+def _clone_rng(rng: np.random.Generator) -> np.random.Generator:
+    out = np.random.Generator(type(rng.bit_generator)())
+    out.bit_generator.state = rng.bit_generator.state
+    return out
+
+
 def _default_ops():
     from sheeprl_b200.lib import CudaOps  # raises B200RLError when the extension / a B200 is missing
 
@@ -313,6 +328,56 @@ class ReplayBuffer:
             self._buf[k].copy_(t)
         self._pos, self._full = int(meta["pos"]), bool(meta["full"])
 
+    # ------------------------------------------------------------------ checkpoints
+    # The reference checkpoints the buffer OBJECT (`state["rb"] = replay_buffer`, utils/callback.py:37-41), so the
+    # device ring pickles as host tensors + write head + Generator and comes back on its device.
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_ops"] = None
+        st["_device"] = str(self._device)
+        if self._owner is not None:                       # a ring of an EnvIndependentReplayBuffer: the owner holds the bytes
+            st["_owner"], st["_buf"] = None, {k: None for k in self._buf}
+        else:
+            st["_buf"] = {k: v.detach().cpu() for k, v in self._buf.items()}
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._device = _restore_device(st["_device"])
+        self._buf = {k: (v if v is None else v.to(self._device)) for k, v in st["_buf"].items()}
+
+    @classmethod
+    def from_reference(cls, ref, device="cuda", ops=None):
+        """Adopts a buffer object of the reference (`sheeprl.data.buffers.ReplayBuffer` / `SequentialReplayBuffer`, e.g.
+        `state["rb"]` of one of its checkpoints): storage (numpy or `MemmapArray`), write head, fullness, Generator."""
+        rb = cls(ref._buffer_size, ref._n_envs, obs_keys=tuple(ref._obs_keys), device=device, ops=ops)
+        rb._adopt(ref)
+        return rb
+
+    def _adopt(self, ref) -> None:
+        for k, v in ref._buf.items():
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(v)))
+            self._allocate(k, tuple(t.shape[2:]), t.dtype)
+            self._buf[k].copy_(t)
+        self._pos, self._full = int(ref._pos), bool(ref._full)
+        self._rng = _clone_rng(ref._rng)
+
+    def to_reference(self, memmap: bool = False, memmap_dir=None):
+        """The same buffer as an object of the reference's class of the same name (needs `sheeprl` importable), for a
+        checkpoint the reference can resume from (`dreamer_v3.py:486-520`)."""
+        import importlib
+
+        ref_cls = getattr(importlib.import_module("sheeprl.data.buffers"), type(self).__name__)
+        ref = ref_cls(self._buffer_size, self._n_envs, obs_keys=self._obs_keys, memmap=memmap, memmap_dir=memmap_dir)
+        self._export(ref)
+        return ref
+
+    def _export(self, ref) -> None:
+        if self._buf:
+            ref.add({k: v.detach().cpu().numpy() for k, v in self._buf.items()})     # allocates (memmap or numpy) + fills
+        ref._pos, ref._full = self._pos, self._full
+        ref._rng = _clone_rng(self._rng)
+
     # ------------------------------------------------------------------ item access (reference: buffers.py:329-361)
     def __getitem__(self, key: str) -> torch.Tensor:
         if not isinstance(key, str):
@@ -490,6 +555,44 @@ class EnvIndependentReplayBuffer:
         self.ops  # bind the kernels to every ring
         for j, env_idx in enumerate(indices):
             self._buf[env_idx].add({k: v[:, j:j + 1] for k, v in data.items()}, validate_args=validate_args)
+
+    # ------------------------------------------------------------------ checkpoints (see ReplayBuffer.__getstate__)
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_ops"] = None
+        st["_device"] = str(self._device)
+        st["_store"] = {k: v.detach().cpu() for k, v in self._store.items()}
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._device = _restore_device(st["_device"])
+        self._store = {k: v.to(self._device) for k, v in st["_store"].items()}
+        for i, b in enumerate(self._buf):
+            b._owner, b._slab, b._device = self, i, self._device
+            b._buf = {k: self._store[k][i] for k in b._buf}
+
+    @classmethod
+    def from_reference(cls, ref, device="cuda", ops=None):
+        """Adopts a `sheeprl.data.buffers.EnvIndependentReplayBuffer` (e.g. `state["rb"]` of a reference checkpoint)."""
+        sequential = ref._concat_along_axis == 2
+        rb = cls(ref._buffer_size, ref._n_envs, obs_keys=tuple(ref._buf[0]._obs_keys),
+                 buffer_cls=SequentialReplayBuffer if sequential else ReplayBuffer, device=device, ops=ops)
+        for mine, theirs in zip(rb._buf, ref._buf):
+            mine._adopt(theirs)
+        rb._rng = _clone_rng(ref._rng)
+        return rb
+
+    def to_reference(self, memmap: bool = False, memmap_dir=None):
+        import importlib
+
+        mod = importlib.import_module("sheeprl.data.buffers")
+        ref = mod.EnvIndependentReplayBuffer(self._buffer_size, self._n_envs, obs_keys=self._buf[0]._obs_keys, memmap=memmap,
+                                             memmap_dir=memmap_dir, buffer_cls=getattr(mod, type(self._buf[0]).__name__))
+        for mine, theirs in zip(self._buf, ref._buf):
+            mine._export(theirs)
+        ref._rng = _clone_rng(self._rng)
+        return ref
 
     def to_memmap(self, directory) -> None:
         """`<directory>/env_<i>/<key>.memmap`, the reference's layout (buffers.py:581)"""

@@ -86,3 +86,20 @@ def test_buffer_feeds_train(cu):
         batch = {k: (v[i] if v.dtype == torch.uint8 else v[i].float()) for k, v in local.items()}
         train(Fab, wm, actor, critic, target, *opts, batch, None, cfg, False, (3,), moments)
     assert torch.isfinite(eng.metrics).all()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "sequential", "env_independent"])
+def test_device_ring_pickles_and_returns_to_the_gpu(cu, kind, tmp_path):
+    """checkpoint round trip of an HBM-resident ring (host tensors in the file, storage back on cuda:0 afterwards) and
+    the checkpoint callback's truncated fix-up on device storage"""
+    from sheeprl_b200.utils.callback import CheckpointCallback, load_replay_buffer
+    from tests.test_buffer_checkpoint_cpu import _Fabric, _heads, _make, _same_samples
+
+    a, kw = _make(kind, device="cuda", ops=cu)
+    CheckpointCallback().on_checkpoint_coupled(_Fabric(), str(tmp_path / "c.ckpt"), {"iter_num": 1}, a)
+    b = load_replay_buffer(torch.load(tmp_path / "c.ckpt", weights_only=False)["rb"], ops=cu)
+    rings = b.buffer if kind == "env_independent" else [b]
+    assert all(t.is_cuda for r in rings for t in r.buffer.values()) and _heads(a) == _heads(b)
+    for r in rings:                                       # undo the checkpoint's truncation mark, then compare draws
+        r["truncated"][(r._pos - 1) % r.buffer_size] = 0
+    _same_samples(a, b, kw)
