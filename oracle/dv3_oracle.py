@@ -311,46 +311,22 @@ def reference_noise_order(noise: Dict[str, Tensor], T: int, H: int, n_heads: int
     return out
 
 
-def dv3_train_step(
-    cfg,
-    wm: Dict[str, Tensor],
-    actor: Dict[str, Tensor],
-    critic: Dict[str, Tensor],
-    target_critic: Dict[str, Tensor],
-    opt_wm: AdamState,
-    opt_actor: AdamState,
-    opt_critic: AdamState,
-    data: Dict[str, Tensor],
-    noise: Dict[str, Tensor],
-    moments_state: Dict[str, Tensor],
-    actions_dim: Sequence[int],
-    condition_margin: float = 0.0,
-    keep: bool = False,
-    is_continuous: bool = False,
-) -> Dict[str, Tensor]:
-    """One Dreamer-V3 update (discrete actions, or continuous `scaled_normal` actions with is_continuous=True: the
-    policy gradient then flows through the imagined rollout, dreamer_v3.py:283-284).  Mutates the parameter dicts, optimiser states and
-    `moments_state` ("low","high") in place like the reference mutates its modules; returns the 13
-    metrics of dreamer_v3.py:330-352 plus (keep=True) the intermediates named in SURVEY.md §8a."""
+def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dict[str, Tensor], noise: Dict[str, Tensor],
+                      condition_margin: float, keep: bool, out: Dict[str, Tensor]):
+    """Dynamic learning (dreamer_v3.py:98-200; identical in p2e_dv3_exploration.py:113-205): encoder, RSSM scan, heads,
+    reconstruction loss, backward, clip, Adam on `wm` (which must already require grad).  Fills the 9 world-model
+    metrics into `out`; returns (zs [T,B,Z], hs [T,B,R], cont_target [T,B,1])."""
     a = cfg.algo
     w = a.world_model
     T, B = a.per_rank_sequence_length, a.per_rank_batch_size
     S, D = w.stochastic_size, w.discrete_size
     Z, R = S * D, w.recurrent_model.recurrent_state_size
-    H = a.horizon
-    N = T * B
     eps = a.mlp_layer_norm.kw.eps
     ceps = a.cnn_layer_norm.kw.eps
     um = a.unimix
     stages = int(round(math.log2(cfg.env.screen_size) - 2))
     key = a.cnn_keys.encoder[0]
     n_hid = a.mlp_layers
-    out: Dict[str, Tensor] = {}
-
-    for d in (wm, actor, critic):
-        for v in d.values():
-            v.requires_grad_(True)
-            v.grad = None
 
     # ---- dreamer_v3.py:98-104
     obs = data[key].float() / 255.0 - 0.5
@@ -412,6 +388,52 @@ def dv3_train_step(
         out.update({"emb": emb.detach(), "latent": latent.detach(), "post_logits": post_l.detach(),
                     "prior_logits": prior_l.detach(), "recon": recon.detach(),
                     "reward_logits": rew_logits.detach(), "continue_logit": cont_logit.detach()})
+
+    return zs, hs, cont_target
+
+
+def dv3_train_step(
+    cfg,
+    wm: Dict[str, Tensor],
+    actor: Dict[str, Tensor],
+    critic: Dict[str, Tensor],
+    target_critic: Dict[str, Tensor],
+    opt_wm: AdamState,
+    opt_actor: AdamState,
+    opt_critic: AdamState,
+    data: Dict[str, Tensor],
+    noise: Dict[str, Tensor],
+    moments_state: Dict[str, Tensor],
+    actions_dim: Sequence[int],
+    condition_margin: float = 0.0,
+    keep: bool = False,
+    is_continuous: bool = False,
+) -> Dict[str, Tensor]:
+    """One Dreamer-V3 update (discrete actions, or continuous `scaled_normal` actions with is_continuous=True: the
+    policy gradient then flows through the imagined rollout, dreamer_v3.py:283-284).  Mutates the parameter dicts, optimiser states and
+    `moments_state` ("low","high") in place like the reference mutates its modules; returns the 13
+    metrics of dreamer_v3.py:330-352 plus (keep=True) the intermediates named in SURVEY.md §8a."""
+    a = cfg.algo
+    w = a.world_model
+    T, B = a.per_rank_sequence_length, a.per_rank_batch_size
+    S, D = w.stochastic_size, w.discrete_size
+    Z, R = S * D, w.recurrent_model.recurrent_state_size
+    H = a.horizon
+    N = T * B
+    eps = a.mlp_layer_norm.kw.eps
+    ceps = a.cnn_layer_norm.kw.eps
+    um = a.unimix
+    stages = int(round(math.log2(cfg.env.screen_size) - 2))
+    key = a.cnn_keys.encoder[0]
+    n_hid = a.mlp_layers
+    out: Dict[str, Tensor] = {}
+
+    for d in (wm, actor, critic):
+        for v in d.values():
+            v.requires_grad_(True)
+            v.grad = None
+
+    zs, hs, cont_target = world_model_phase(cfg, wm, opt_wm, data, noise, condition_margin, keep, out)
 
     # ---- imagination with the UPDATED world model (dreamer_v3.py:203-241); discrete actions: the policy
     # loss does not back-propagate through the rollout (SURVEY.md App. E), so it runs without grad.

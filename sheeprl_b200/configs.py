@@ -144,3 +144,20 @@ def make_dv3_cfg(
             node = node[p]
         node[parts[-1]] = v
     return cfg
+
+
+def make_p2e_dv3_cfg(size: str = "S", *, n_ensembles: int = 8, intrinsic_weight: float = 0.1, extrinsic_weight: float = 1.0,
+                     intrinsic_reward_multiplier: float = 1.0, **kw: Any) -> dotdict:
+    """`make_dv3_cfg` plus the Plan2Explore additions of `configs/algo/p2e_dv3.yaml` (ensembles, the exploration
+    critics and their mixing weights, the player's actor choice)."""
+    cfg = make_dv3_cfg(size, **kw)
+    a = cfg.algo
+    a["name"] = "p2e_dv3_exploration"
+    a["intrinsic_reward_multiplier"] = intrinsic_reward_multiplier
+    a["player"]["actor_type"] = "exploration"
+    a["critics_exploration"] = dotdict({"intrinsic": {"weight": intrinsic_weight, "reward_type": "intrinsic"},
+                                        "extrinsic": {"weight": extrinsic_weight, "reward_type": "task"}})
+    a["ensembles"] = dotdict({"n": n_ensembles, "dense_act": a.dense_act, "mlp_layers": a.mlp_layers,
+                              "dense_units": a.dense_units, "layer_norm": copy.deepcopy(a.mlp_layer_norm.as_dict()),
+                              "clip_gradients": 100.0, "optimizer": _adam(1e-4, 1e-5)})
+    return cfg

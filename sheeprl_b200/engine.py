@@ -376,9 +376,16 @@ class DV3Engine:
         """data: the reference's batch dict ([T,B,...]; image key uint8 or float 0..255).
         noise: optional injected Exp(1) noise {"post":[T,B,S,D], "img_state":[H,N,S,D],
         "img_action":[list per head of [H+1,N,A_h]]} (parity mode); None -> on-device Philox."""
+        self._draw_noise(noise)
+        self._world_model_phase(data)
+        # ---- behaviour learning with the updated world model
+        self._imagine()
+        self._behaviour_losses()
+        return self.metrics
+
+    def _draw_noise(self, noise: Optional[Dict[str, torch.Tensor]]):
         ops = self.ops
-        T, B, N, H, Z, R, L, A = self.T, self.B, self.N, self.H, self.Z, self.R, self.L, self.A
-        a, w = self.cfg.algo, self.cfg.algo.world_model
+        T, B, N, H, Z = self.T, self.B, self.N, self.H, self.Z
         if noise is None:
             ops.increment(self.rng_t)
             ops.fill_exponential(self.noise_post.view(-1), self.rng_seed, 0, self.rng_t)
@@ -392,6 +399,11 @@ class DV3Engine:
             self.noise_img_state.copy_(noise["img_state"].reshape(H, N, Z))
             self.noise_img_action.copy_(torch.cat([x for x in noise["img_action"]], -1))
 
+    def _world_model_phase(self, data: Dict[str, torch.Tensor]):
+        """Dynamic learning (dreamer_v3.py:98-200): forward, losses, backward, clip + Adam of the world model."""
+        ops = self.ops
+        T, B, N, H, Z, R, L, A = self.T, self.B, self.N, self.H, self.Z, self.R, self.L, self.A
+        a, w = self.cfg.algo, self.cfg.algo.world_model
         # ---- inputs (dreamer_v3.py:98-104): normalise pixels, force is_first[0]=1, shift actions
         ops.obs_prep(data[self.key].reshape(N, self.Cin, self.img, self.img), self.x0)
         data["is_first"][0].fill_(1.0)                      # same in-place mutation as the reference (:100)
@@ -441,11 +453,6 @@ class DV3Engine:
         self._scan_backward(first)
         self._encoder_backward()
         self._optimizer_step("wm", self.wm, float(w.clip_gradients or 0.0), w.optimizer, 0)
-
-        # ---- behaviour learning with the updated world model
-        self._imagine()
-        self._behaviour_losses()
-        return self.metrics
 
     # ------------------------------------------------------------------ encoder / decoder
     def _enc_names(self, i):
@@ -747,22 +754,25 @@ class DV3Engine:
                       float(b1), float(b2), float(ocfg.eps), g.step_t, self.norms[slot: slot + 1])
 
     # ------------------------------------------------------------------ behaviour learning
-    def _actor_heads(self, hidden: torch.Tensor, raw_out: torch.Tensor):
+    def _actor_heads(self, hidden: torch.Tensor, raw_out: torch.Tensor, actor: Optional[FlatGroup] = None):
+        actor = actor or self.actor
         if self.is_continuous:
-            self.ops.gemm(hidden, self.actor.views["mlp_heads.0.weight"], raw_out, False, True,
-                          bias=self.actor.views["mlp_heads.0.bias"])
+            self.ops.gemm(hidden, actor.views["mlp_heads.0.weight"], raw_out, False, True,
+                          bias=actor.views["mlp_heads.0.bias"])
             return
         off = 0
         for i, ad in enumerate(self.actions_dim):
-            self.ops.gemm(hidden, self.actor.views[f"mlp_heads.{i}.weight"], raw_out[:, off:off + ad], False, True,
-                          bias=self.actor.views[f"mlp_heads.{i}.bias"])
+            self.ops.gemm(hidden, actor.views[f"mlp_heads.{i}.weight"], raw_out[:, off:off + ad], False, True,
+                          bias=actor.views[f"mlp_heads.{i}.bias"])
             off += ad
 
-    def _imagine(self):
+    def _imagine(self, actor: Optional[FlatGroup] = None, actor_mlp: Optional["_MLP"] = None):
         """H-step rollout from every posterior state (dreamer_v3.py:203-241), forward only: with discrete
-        actions the policy gradient does not flow through the rollout."""
+        actions the policy gradient does not flow through the rollout.  `actor` / `actor_mlp`:
+        another policy over the same world model (Plan2Explore's exploration actor); default the task actor."""
         ops, N, Z, R, H = self.ops, self.N, self.Z, self.R, self.H
-        am = self.actor_mlp
+        actor = actor or self.actor
+        am = actor_mlp or self.actor_mlp
         # imagined z is an exact one-hot sample: its Linear is a gather over the transposed weight (refreshed here,
         # after the world-model update)
         gather = hasattr(ops, "onehot_linear") and self.S <= 64 and self.A <= 32
@@ -793,10 +803,10 @@ class DV3Engine:
             cur_in = x
             for l in range(am.n_hidden):
                 ops.gemm(cur_in, am.W(l), am.pre[l][rows], False, True)
-                ops.ln_act_fwd(am.pre[l][rows], self.actor.views[f"model._model.{3 * l + 1}.weight"],
-                               self.actor.views[f"model._model.{3 * l + 1}.bias"], self.eps, ACT_SILU, am.act[l][rows])
+                ops.ln_act_fwd(am.pre[l][rows], actor.views[f"model._model.{3 * l + 1}.weight"],
+                               actor.views[f"model._model.{3 * l + 1}.bias"], self.eps, ACT_SILU, am.act[l][rows])
                 cur_in = am.act[l][rows]
-            self._actor_heads(cur_in, self.actor_raw[rows])
+            self._actor_heads(cur_in, self.actor_raw[rows], actor)
             if self.is_continuous:
                 ac = self.cfg.algo.actor
                 ops.cont_action_fwd(self.actor_raw[rows], self.noise_img_action[i], self.actions[i], self.act_ent[rows],
