@@ -312,10 +312,11 @@ def reference_noise_order(noise: Dict[str, Tensor], T: int, H: int, n_heads: int
 
 
 def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dict[str, Tensor], noise: Dict[str, Tensor],
-                      condition_margin: float, keep: bool, out: Dict[str, Tensor]):
+                      condition_margin: float, keep: bool, out: Dict[str, Tensor], detach_heads: bool = False):
     """Dynamic learning (dreamer_v3.py:98-200; identical in p2e_dv3_exploration.py:113-205): encoder, RSSM scan, heads,
     reconstruction loss, backward, clip, Adam on `wm` (which must already require grad).  Fills the 9 world-model
-    metrics into `out`; returns (zs [T,B,Z], hs [T,B,R], cont_target [T,B,1])."""
+    metrics into `out`; returns (zs [T,B,Z], hs [T,B,R], cont_target [T,B,1]).  detach_heads: the reward / continue
+    heads read `latent.detach()` (p2e_dv3_exploration.py:157,160: their losses do not shape the latent state)."""
     a = cfg.algo
     w = a.world_model
     T, B = a.per_rank_sequence_length, a.per_rank_batch_size
@@ -360,9 +361,10 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
     # ---- heads + losses (dreamer_v3.py:149-190, loss.py:9-88)
     recon = decoder_forward(wm, latent, stages, ceps, obs.shape[-3:])
     obs_loss = ((recon - obs) ** 2).sum((-3, -2, -1))
-    rew_logits = dense_stack(wm, "reward_model._model.", latent, n_hid, eps, True)
+    head_in = latent.detach() if detach_heads else latent
+    rew_logits = dense_stack(wm, "reward_model._model.", head_in, n_hid, eps, True)
     reward_loss = -twohot_log_prob(rew_logits, rewards)
-    cont_logit = dense_stack(wm, "continue_model._model.", latent, n_hid, eps, True)
+    cont_logit = dense_stack(wm, "continue_model._model.", head_in, n_hid, eps, True)
     continue_loss = w.continue_scale_factor * F.binary_cross_entropy_with_logits(
         cont_logit, cont_target, reduction="none").sum(-1)
     kl = categorical_kl(post_l.detach(), prior_l, S, D)

@@ -26,7 +26,8 @@ from sheeprl_b200.configs import make_p2e_dv3_cfg  # noqa: E402
 
 CFG = dict(size="S", per_rank_batch_size=3, per_rank_sequence_length=5, horizon=4, dense_units=32, mlp_layers=2,
            cnn_channels_multiplier=4, recurrent_state_size=24, hidden_size=32, stochastic_size=6, discrete_size=5, bins=31,
-           n_ensembles=3, intrinsic_weight=0.4, extrinsic_weight=1.0, intrinsic_reward_multiplier=2.0)
+           n_ensembles=3, intrinsic_weight=0.4, extrinsic_weight=1.0, intrinsic_reward_multiplier=2.0,
+           algo__world_model__kl_free_nats=0.05)      # KL term active (the default 1.0 clamps it away at this tiny state size)
 ACTIONS_DIM = (3, 2)
 STEPS = 2
 

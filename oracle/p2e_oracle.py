@@ -2,7 +2,8 @@
 (`sheeprl/algos/p2e_dv3/p2e_dv3_exploration.py:41-520`, discrete actions), on top of the Dreamer-V3 oracle's pieces.
 
 Phases, in the reference's order:
-  1. dynamic learning              == dreamer_v3 (`world_model_phase`, :113-205)
+  1. dynamic learning              == dreamer_v3 (`world_model_phase`, :113-205) except that the reward / continue
+                                              heads read the DETACHED latent (:157,160)
   2. ensemble learning             :212-240   N MLPs predict the next posterior from [z_t, h_t, a_t]
   3. behaviour learning exploration :242-392  rollout with the exploration actor; one critic per entry of
                                               `critics_exploration` (intrinsic reward = ensemble disagreement, or the
@@ -153,7 +154,8 @@ def p2e_train_step(cfg, wm, ensembles, actor_task, critic_task, target_task, act
             v.grad = None
 
     # ---- 1. dynamic learning
-    zs, hs, cont_target = world_model_phase(cfg, wm, opts["wm"], data, noise, condition_margin, False, out)
+    zs, hs, cont_target = world_model_phase(cfg, wm, opts["wm"], data, noise, condition_margin, False, out,
+                                            detach_heads=True)
     zs, hs = zs.detach(), hs.detach()
 
     # ---- 2. ensemble learning (:212-240).  NB the clip covers the LAST member only (`module=ens` after the loop)

@@ -21,7 +21,9 @@ from sheeprl_b200.engine import ACT_SILU, DV3Engine
 
 
 class PlayerDV3:
-    def __init__(self, engine: DV3Engine, num_envs: int, actor_type: Optional[str] = None):
+    def __init__(self, engine: DV3Engine, num_envs: int, actor_type: Optional[str] = None, actor_group=None):
+        """actor_group: the flat group of the policy that acts (default the trainer's task actor; Plan2Explore passes
+        its exploration actor when `algo.player.actor_type == "exploration"`, p2e_dv3/agent.py:206-212)"""
         self.trainer = engine
         self.num_envs = int(num_envs)
         self.actor_type = actor_type
@@ -35,7 +37,7 @@ class PlayerDV3:
         cfg.algo.horizon = 1
         self.eng = DV3Engine(cfg, engine.actions_dim, in_channels=engine.Cin, device=engine.device, ops=engine.ops,
                              is_continuous=engine.is_continuous,
-                             groups=(engine.wm, engine.actor, engine.critic, engine.target))
+                             groups=(engine.wm, actor_group or engine.actor, engine.critic, engine.target))
         e, E = self.eng, self.num_envs
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
         # persistent acting state (reference attribute names; leading dim 1 as in the reference)

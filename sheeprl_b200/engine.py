@@ -399,8 +399,10 @@ class DV3Engine:
             self.noise_img_state.copy_(noise["img_state"].reshape(H, N, Z))
             self.noise_img_action.copy_(torch.cat([x for x in noise["img_action"]], -1))
 
-    def _world_model_phase(self, data: Dict[str, torch.Tensor]):
-        """Dynamic learning (dreamer_v3.py:98-200): forward, losses, backward, clip + Adam of the world model."""
+    def _world_model_phase(self, data: Dict[str, torch.Tensor], heads_detached: bool = False):
+        """Dynamic learning (dreamer_v3.py:98-200): forward, losses, backward, clip + Adam of the world model.
+        heads_detached: the reward / continue losses do not reach the latent state (Plan2Explore feeds those heads
+        `latent_states.detach()`, p2e_dv3_exploration.py:157,160)."""
         ops = self.ops
         T, B, N, H, Z, R, L, A = self.T, self.B, self.N, self.H, self.Z, self.R, self.L, self.A
         a, w = self.cfg.algo, self.cfg.algo.world_model
@@ -448,8 +450,8 @@ class DV3Engine:
         # ---- world-model backward
         ops.zero(self.wm.grad)
         self._decoder_backward()                                       # writes d_latent
-        self.reward_wm.backward(self.latent, self.d_rew_logits, self.d_latent, True)
-        self.cont_wm.backward(self.latent, self.d_cont_logit, self.d_latent, True)
+        self.reward_wm.backward(self.latent, self.d_rew_logits, None if heads_detached else self.d_latent, True)
+        self.cont_wm.backward(self.latent, self.d_cont_logit, None if heads_detached else self.d_latent, True)
         self._scan_backward(first)
         self._encoder_backward()
         self._optimizer_step("wm", self.wm, float(w.clip_gradients or 0.0), w.optimizer, 0)
@@ -898,32 +900,51 @@ class DV3Engine:
                                 self.actions_dim, self.unimix, float(a.actor.ent_coef), 1.0 / M0, self.policy_rows,
                                 self.d_actor_raw)
         ops.sum_rows(self.policy_rows.view(M0, 1), self.metrics[8:9], -1.0 / M0)
-        ops.zero(self.actor.grad)
-        am = self.actor_mlp
+        self._actor_update(self.actor, self.actor_mlp, "actor", 1)
+        # ---- critic (dreamer_v3.py:307-327): qv logits are the first H*N rows of v_logits (same weights,
+        # same inputs as the reference's second critic evaluation)
+        self._critic_update(self.critic, self.critic_mlp, self.target_mlp, v_logits, self.lam, self.metrics[9:10],
+                            "critic", 2)
+
+    def _actor_update(self, actor: FlatGroup, am: "_MLP", name: str, slot: int):
+        """backward of the policy loss from `d_actor_raw` (rows of the first H steps) through the heads and the actor
+        MLP whose activations the rollout kept, then all-reduce / clip / Adam (dreamer_v3.py:298-304)"""
+        ops, N, H, L = self.ops, self.N, self.H, self.L
+        a = self.cfg.algo
+        M1, M0 = (H + 1) * N, H * N
+        traj2 = self.traj.view(M1, L)
+        ops.zero(actor.grad)
         last = am.act[-1][:M0]
         ops.zero(self.d_actor_hidden)
         off = 0
         for i, ad in enumerate((self.AW,) if self.is_continuous else self.actions_dim):
             d = self.d_actor_raw[:, off:off + ad]
-            ops.gemm(d, last, self.actor.gviews[f"mlp_heads.{i}.weight"], True, False)
-            ops.col_sum(d, self.actor.gviews[f"mlp_heads.{i}.bias"])
-            ops.gemm(d, self.actor.views[f"mlp_heads.{i}.weight"], self.d_actor_hidden, False, False, accumulate=True)
+            ops.gemm(d, last, actor.gviews[f"mlp_heads.{i}.weight"], True, False)
+            ops.col_sum(d, actor.gviews[f"mlp_heads.{i}.bias"])
+            ops.gemm(d, actor.views[f"mlp_heads.{i}.weight"], self.d_actor_hidden, False, False, accumulate=True)
             off += ad
         am.backward(traj2[:M0], self.d_actor_hidden, None, False, M=M0)
-        self._optimizer_step("actor", self.actor, float(a.actor.clip_gradients or 0.0), a.actor.optimizer, 1)
-        # ---- critic (dreamer_v3.py:307-327): qv logits are the first H*N rows of v_logits (same weights,
-        # same inputs as the reference's second critic evaluation)
-        t_logits = self.target_mlp.forward(traj2[:M0])
+        self._optimizer_step(name, actor, float(a.actor.clip_gradients or 0.0), a.actor.optimizer, slot)
+
+    def _critic_update(self, critic: FlatGroup, cm: "_MLP", tm: "_MLP", v_logits: torch.Tensor, lam: torch.Tensor,
+                       metric: torch.Tensor, name: str, slot: int):
+        """two-hot regression of the critic on the lambda-values and on the target critic's values, discount-weighted
+        (dreamer_v3.py:307-327); `v_logits` are `cm`'s logits on the whole trajectory (its activations are live)"""
+        ops, N, H, L = self.ops, self.N, self.H, self.L
+        a = self.cfg.algo
+        M1, M0 = (H + 1) * N, H * N
+        traj2 = self.traj.view(M1, L)
+        t_logits = tm.forward(traj2[:M0])
         ops.twohot_mean(t_logits, TWOHOT_LOW, TWOHOT_HIGH, self.target_values)
         disc = self.discount.view(-1)[:M0]
-        ops.twohot_loss_grad(v_logits[:M0], self.lam.view(-1), disc, 1.0 / M0, TWOHOT_LOW, TWOHOT_HIGH,
+        ops.twohot_loss_grad(v_logits[:M0], lam.view(-1), disc, 1.0 / M0, TWOHOT_LOW, TWOHOT_HIGH,
                              self.value_rows, self.d_critic_logits)
         ops.twohot_loss_grad(v_logits[:M0], self.target_values, disc, 1.0 / M0, TWOHOT_LOW, TWOHOT_HIGH,
                              self.value_rows, self.d_critic_logits, accumulate=True)
-        ops.weighted_mean(self.value_rows, disc, 1.0 / M0, self.metrics[9:10])
-        ops.zero(self.critic.grad)
-        self.critic_mlp.backward(traj2[:M0], self.d_critic_logits, None, False, M=M0)
-        self._optimizer_step("critic", self.critic, float(a.critic.clip_gradients or 0.0), a.critic.optimizer, 2)
+        ops.weighted_mean(self.value_rows, disc, 1.0 / M0, metric)
+        ops.zero(critic.grad)
+        cm.backward(traj2[:M0], self.d_critic_logits, None, False, M=M0)
+        self._optimizer_step(name, critic, float(a.critic.clip_gradients or 0.0), a.critic.optimizer, slot)
 
     # ------------------------------------------------------------------ misc
     METRIC_NAMES = (
