@@ -109,7 +109,7 @@ def install():
 
     hu.get_class = get_class
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.append(REFERENCE_ROOT)       # at the END: the reference ships its own top-level `tests` package
     import sheeprl  # noqa: F401
     import sheeprl.algos.dreamer_v3.agent as agent_mod
 
