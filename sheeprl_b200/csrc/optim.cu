@@ -34,7 +34,7 @@ sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out)
 __global__ void __launch_bounds__(256)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  const double* __restrict__ normsq, const int* __restrict__ step_t, float* __restrict__ norm_out,
-                 long long n, float max_norm, float lr, float b1, float b2, float eps) {
+                 long long n, float max_norm, float lr, float b1, float b2, float eps, int vec) {
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const float total = (float)sqrt(*normsq);
@@ -52,22 +52,63 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const float omb1 = 1.f - b1, omb2 = 1.f - b2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float gi = g[i] * coef;
-    float mi = m[i], vi = v[i];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto update = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= coef;
     mi = mi + omb1 * (gi - mi);            // exp_avg.lerp_(grad, 1 - beta1)
     vi = vi * b2 + omb2 * gi * gi;         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+    pi = pi - step_size * (mi / denom);
+  };
+  long long done = 0;
+  if (vec) {   // 28 B / parameter of HBM traffic as 128-bit accesses (flat groups are 256-byte aligned)
+    const long long n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long i = tid; i < n4; i += stride) {
+      float4 pp = p4[i], mm = m4[i], vv = v4[i];
+      const float4 gg = g4[i];
+      update(pp.x, gg.x, mm.x, vv.x);
+      update(pp.y, gg.y, mm.y, vv.y);
+      update(pp.z, gg.z, mm.z, vv.z);
+      update(pp.w, gg.w, mm.w, vv.w);
+      p4[i] = pp;
+      m4[i] = mm;
+      v4[i] = vv;
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + tid; i < n; i += stride) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    update(pi, g[i], mi, vi);
+    p[i] = pi;
     m[i] = mi;
     v[i] = vi;
   }
 }
 
-__global__ void ema_kernel(float* __restrict__ tgt, const float* __restrict__ src, long long n, float tau) {
+__global__ void ema_kernel(float* __restrict__ tgt, const float* __restrict__ src, long long n, float tau, int vec) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    tgt[i] = tgt[i] * (1.f - tau) + tau * src[i];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long done = 0;
+  if (vec) {
+    const long long n4 = n >> 2;
+    float4* t4 = reinterpret_cast<float4*>(tgt);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (long long i = tid; i < n4; i += stride) {
+      float4 t = t4[i];
+      const float4 s = s4[i];
+      t.x = t.x * (1.f - tau) + tau * s.x;
+      t.y = t.y * (1.f - tau) + tau * s.y;
+      t.z = t.z * (1.f - tau) + tau * s.z;
+      t.w = t.w * (1.f - tau) + tau * s.w;
+      t4[i] = t;
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + tid; i < n; i += stride) tgt[i] = tgt[i] * (1.f - tau) + tau * src[i];
 }
 
 // Philox4x32-10
@@ -185,7 +226,10 @@ extern "C" int b200rl_adam_step(float* p, const float* g, float* m, float* v, co
                                 cudaStream_t st) {
   RL_CHECK_ARG(p && g && m && v && normsq && step_t && norm_out, "null pointer");
   if (n <= 0) return B200RL_OK;
-  adam_step_kernel<<<stream_grid(n), 256, 0, st>>>(p, g, m, v, normsq, step_t, norm_out, n, max_norm, lr, b1, b2, eps);
+  const int vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                    reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  adam_step_kernel<<<stream_grid(vec ? (n + 3) / 4 : n), 256, 0, st>>>(p, g, m, v, normsq, step_t, norm_out, n, max_norm, lr,
+                                                                      b1, b2, eps, vec);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }
@@ -193,7 +237,8 @@ extern "C" int b200rl_adam_step(float* p, const float* g, float* m, float* v, co
 extern "C" int b200rl_ema(float* target, const float* src, long long n, float tau, cudaStream_t st) {
   RL_CHECK_ARG(target && src, "null pointer");
   if (n <= 0) return B200RL_OK;
-  ema_kernel<<<stream_grid(n), 256, 0, st>>>(target, src, n, tau);
+  const int vec = ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+  ema_kernel<<<stream_grid(vec ? (n + 3) / 4 : n), 256, 0, st>>>(target, src, n, tau, vec);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }

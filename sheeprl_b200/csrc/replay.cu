@@ -64,19 +64,36 @@ __global__ void gae_kernel(const float* __restrict__ rewards, const float* __res
                            float lmbda) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
+  // The recurrence is a dependent chain but its inputs are not: load CH steps' rewards / values / dones first (CH
+  // independent L2 requests in flight per thread), then run the chain from registers.  Same arithmetic as before.
+  constexpr int CH = 16;
   float lastgaelam = 0.f;
   float nextvalues = next_value[e];
-  float nextnonterminal = (dones[(long long)(T - 1) * E + e] != 0.f) ? 0.f : 1.f;
-  for (int t = T - 1; t >= 0; --t) {
-    const long long i = (long long)t * E + e;
-    if (t < T - 1) {
-      nextnonterminal = (dones[i] != 0.f) ? 0.f : 1.f;
-      nextvalues = values[i + E];
+  for (int t1 = T; t1 > 0; t1 -= CH) {
+    float r[CH], v[CH], d[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int t = t1 - 1 - k;
+      if (t >= 0) {
+        const long long i = (long long)t * E + e;
+        r[k] = rewards[i];
+        v[k] = values[i];
+        d[k] = dones[i];
+      }
     }
-    const float delta = rewards[i] + nextvalues * nextnonterminal * gamma - values[i];
-    lastgaelam = delta + nextnonterminal * lastgaelam * gamma * lmbda;
-    advantages[i] = lastgaelam;
-    returns[i] = lastgaelam + values[i];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int t = t1 - 1 - k;
+      if (t >= 0) {
+        const long long i = (long long)t * E + e;
+        const float nextnonterminal = (d[k] != 0.f) ? 0.f : 1.f;     // dones[t] masks the bootstrap from step t+1
+        const float delta = r[k] + nextvalues * nextnonterminal * gamma - v[k];
+        lastgaelam = delta + nextnonterminal * lastgaelam * gamma * lmbda;
+        advantages[i] = lastgaelam;
+        returns[i] = lastgaelam + v[k];
+        nextvalues = v[k];
+      }
+    }
   }
 }
 

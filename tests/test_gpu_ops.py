@@ -195,12 +195,15 @@ def test_conv_down_up_wgrad(ops, NB, h, w, Cs, Cb):
 def test_obs_prep_and_transpose(ops):
     cu, em = ops
     g = torch.Generator().manual_seed(0)
-    obs = torch.randint(0, 256, (6, 3, 16, 16), generator=g, dtype=torch.uint8)
-    for o in (obs, obs.float()):
-        oc, og = torch.empty(6, 16, 16, 3), torch.empty(6, 16, 16, 3, device="cuda")
-        em.obs_prep(o, oc)
-        cu.obs_prep(o.cuda(), og)
-        assert torch.equal(og.cpu(), oc)
+    # (6,3,16,16) / (2,12,84,84) / (3,1,8,8) / (2,4,20,20): the 4-pixel kernel; (2,5,6,6), (3,3,5,5): the generic one
+    for shape in ((6, 3, 16, 16), (2, 12, 84, 84), (3, 1, 8, 8), (2, 4, 20, 20), (2, 5, 6, 6), (3, 3, 5, 5)):
+        obs = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8)
+        NB, C, H, W = shape
+        for o in (obs, obs.float()):
+            oc, og = torch.empty(NB, H, W, C), torch.empty(NB, H, W, C, device="cuda")
+            em.obs_prep(o, oc)
+            cu.obs_prep(o.cuda(), og)
+            assert torch.equal(og.cpu(), oc), shape
     X = rnd(7, 16, 40, seed=1)
     Yc, Yg = torch.empty(7, 40, 16), torch.empty(7, 40, 16, device="cuda")
     em.transpose_batched(X, Yc)
@@ -381,6 +384,22 @@ def test_optimizer_and_utils(ops):
     em.ema(tc, g, 0.02)
     cu.ema(tg, g.cuda(), 0.02)
     close(tg, tc, what="ema")
+    # odd length with a tail after the 128-bit body, and a misaligned view (scalar path): same results
+    for sl in (slice(0, 1003), slice(1, 1004)):
+        pc, mc, vc, oc = p[sl].clone(), m[sl].clone(), v[sl].clone(), torch.zeros(1)
+        base = [t.cuda() for t in (p, g, m, v)]
+        pg, gg, mg, vg = (t[sl] for t in base)
+        og = torch.zeros(1, device="cuda")
+        st_c, st_g = torch.tensor([2], dtype=torch.int32), torch.tensor([2], dtype=torch.int32, device="cuda")
+        em.adam_step(pc, g[sl], mc, vc, nc, 10.0, 1e-4, 0.9, 0.999, 1e-8, st_c, oc)
+        cu.adam_step(pg, gg, mg, vg, ng, 10.0, 1e-4, 0.9, 0.999, 1e-8, st_g, og)
+        close(pg, pc, rtol=0, atol=5e-7, what="adam p (tail / unaligned)")
+        close(vg, vc, rtol=2e-5, what="adam v (tail / unaligned)")
+        assert torch.equal(base[0][1004:].cpu(), p[1004:])                 # nothing written past the slice
+        tc, tg = p[sl].clone(), p.cuda()[sl]
+        em.ema(tc, g[sl], 0.02)
+        cu.ema(tg, g.cuda()[sl], 0.02)
+        close(tg, tc, what="ema (tail / unaligned)")
     e = torch.empty(1 << 20, device="cuda")
     cu.fill_exponential(e, 1234, 7)
     assert float(e.min()) > 0 and abs(float(e.mean()) - 1.0) < 0.01 and abs(float(e.var()) - 1.0) < 0.03
