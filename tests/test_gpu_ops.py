@@ -77,6 +77,30 @@ def test_gemm_tensor_core_path_is_taken_and_exact_enough(ops):
     assert float(Cw[:, :4].abs().sum()) == 0 and float(Cw[:, 4 + N:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("rows", [1024, 15360])
+def test_gemm_twohot_gradient_operands_with_padded_rows(ops, rows):
+    """the 255-bin logit gradients live in buffers with a 256-float row stride so that dX = dlogits W (K = 255) and
+    dW = dlogits^T act (M = 255, MN-major A) are tensor-core eligible (16-byte TMA row stride, ragged last box)"""
+    cu, em = ops
+    nb, D = 255, 512
+    dl_w = rnd(rows, 256, seed=1)
+    dl_w[:, 255] = 1e6                                           # the pad column must never be read as data
+    W, act = rnd(nb, D, seed=2), rnd(rows, D, seed=3)
+    dl_g, Wg, actg = dl_w.cuda(), W.cuda(), act.cuda()
+    import ctypes
+
+    assert cu.lib.b200rl_gemm_tc_supported(ctypes.c_void_p(dl_g.data_ptr()), ctypes.c_void_p(Wg.data_ptr()), rows, D, nb,
+                                           256, D, 0, 0) == 1
+    dx_w, dx_g = torch.empty(rows, D), torch.empty(rows, D, device="cuda")
+    em.gemm(dl_w[:, :nb], W, dx_w, False, False)
+    cu.gemm(dl_g[:, :nb], Wg, dx_g, False, False)
+    close(dx_g, dx_w, rtol=2e-6 * nb ** 0.5, what="dX")
+    dw_w, dw_g = torch.empty(nb, D), torch.empty(nb, D, device="cuda")
+    em.gemm(dl_w[:, :nb], act, dw_w, True, False)
+    cu.gemm(dl_g[:, :nb], actg, dw_g, True, False)
+    close(dw_g, dw_w, rtol=2e-6 * rows ** 0.5, what="dW")
+
+
 @pytest.mark.parametrize("M,N,K,tA,tB", GEMM_SHAPES)
 @pytest.mark.parametrize("mode", ["plain", "bias", "acc", "strided"])
 def test_gemm(ops, M, N, K, tA, tB, mode):
