@@ -126,7 +126,7 @@ class P2EDV3Engine(DV3Engine):
     def train_step(self, data: Dict[str, torch.Tensor], noise: Optional[Dict[str, torch.Tensor]] = None):
         """noise (parity mode): {"post", "img_state_expl", "img_action_expl", "img_state_task", "img_action_task"}"""
         ops = self.ops
-        T, B, N, H, Z = self.T, self.B, self.N, self.H, self.Z
+        N, H, Z = self.N, self.H, self.Z
         if noise is None:
             self._draw_noise(None)                                                   # post / task rollout streams 0-2
             ops.fill_exponential(self.noise_img_state_expl.view(-1), self.rng_seed, 3, self.rng_t)

@@ -411,8 +411,8 @@ class DV3Engine:
         heads_detached: the reward / continue losses do not reach the latent state (Plan2Explore feeds those heads
         `latent_states.detach()`, p2e_dv3_exploration.py:157,160)."""
         ops = self.ops
-        T, B, N, H, Z, R, L, A = self.T, self.B, self.N, self.H, self.Z, self.R, self.L, self.A
-        a, w = self.cfg.algo, self.cfg.algo.world_model
+        B, N, R, A = self.B, self.N, self.R, self.A
+        w = self.cfg.algo.world_model
         # ---- inputs (dreamer_v3.py:98-104): normalise pixels, force is_first[0]=1, shift actions
         ops.obs_prep(data[self.key].reshape(N, self.Cin, self.img, self.img), self.x0)
         data["is_first"][0].fill_(1.0)                      # same in-place mutation as the reference (:100)
