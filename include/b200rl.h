@@ -176,6 +176,9 @@ int b200rl_zero(float* x, long long n, cudaStream_t stream);
 int b200rl_copy2d(const float* src, float* dst, long long M, int C, long long lds, long long ldd, cudaStream_t stream);
 int b200rl_axpy(const float* x, float* y, long long n, float alpha, cudaStream_t stream);
 int b200rl_affine(const float* x, float* y, long long n, float alpha, float beta, cudaStream_t stream);
+/* y[M,C] = symlog(x[M,C]) = sign(x) log(1 + |x|)  (sheeprl/utils/utils.py:148): the squashing of vector observations in
+ * MLPEncoder.forward (dreamer_v3/agent.py:150) and the regression target of SymlogDistribution (utils/distribution.py:180). */
+int b200rl_symlog(const float* x, float* y, long long M, int C, long long ldx, long long ldy, cudaStream_t stream);
 int b200rl_tanh_fwd(const float* x, float* y, long long n, cudaStream_t stream);
 int b200rl_tanh_bwd(const float* y, const float* dy, float* dx, long long n, int accumulate, cudaStream_t stream);
 int b200rl_increment(int* p, cudaStream_t stream);

@@ -148,6 +148,32 @@ def categorical_entropy(logits_mix: Tensor, groups: int, classes: int) -> Tensor
 # --------------------------------------------------------------------------------------------------
 # networks
 # --------------------------------------------------------------------------------------------------
+def vec_dims(cfg) -> Dict[str, int]:
+    """{vector observation key: dimension} — the reference reads these from the observation space; the synthetic
+    configs of the tests / bench carry them under cfg.env.mlp_dims"""
+    return dict(cfg.env.get("mlp_dims", {}) or {})
+
+
+def mlp_encoder_forward(wm: Dict[str, Tensor], data: Dict[str, Tensor], keys: Sequence[str], n_hidden: int, eps: float):
+    """MLPEncoder (agent.py:100-152): symlog of the concatenated vectors -> n x [Linear nobias -> LN -> SiLU].
+    Returns (features, symlog inputs per key)."""
+    xs = [symlog(data[k].float()) for k in keys]
+    return dense_stack(wm, "encoder.mlp_encoder.model._model.", torch.cat(xs, -1), n_hidden, eps, False), xs
+
+
+def mlp_decoder_loss(wm: Dict[str, Tensor], latent: Tensor, targets: Sequence[Tensor], n_hidden: int, eps: float) -> Tensor:
+    """MLPDecoder (agent.py:229-278) + SymlogDistribution.log_prob (utils/distribution.py:177-192, dist "mse", agg "sum",
+    tol 1e-8): sum over keys of sum_d (head_k(x) - symlog(obs_k))^2, squared distances below tol zeroed."""
+    hid = dense_stack(wm, "observation_model.mlp_decoder.model._model.", latent, n_hidden, eps, False)
+    loss = 0.0
+    for i, tgt in enumerate(targets):
+        rec = F.linear(hid, wm[f"observation_model.mlp_decoder.heads.{i}.weight"], wm[f"observation_model.mlp_decoder.heads.{i}.bias"])
+        dist = (rec - tgt) ** 2
+        dist = torch.where(dist < 1e-8, torch.zeros_like(dist), dist)
+        loss = loss + dist.sum(-1)
+    return loss
+
+
 def encoder_forward(wm: Dict[str, Tensor], obs: Tensor, stages: int, eps: float) -> Tensor:
     """CNNEncoder (agent.py:42-97): stages x [Conv2d k4 s2 p1 nobias -> LN(channel) -> SiLU] -> flatten CHW.
     obs: [T,B,C,H,W] already normalised."""
@@ -326,11 +352,11 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
     ceps = a.cnn_layer_norm.kw.eps
     um = a.unimix
     stages = int(round(math.log2(cfg.env.screen_size) - 2))
-    key = a.cnn_keys.encoder[0]
+    cnn_keys, vkeys = list(a.cnn_keys.encoder), list(a.mlp_keys.encoder)
     n_hid = a.mlp_layers
 
     # ---- dreamer_v3.py:98-104
-    obs = data[key].float() / 255.0 - 0.5
+    obs = data[cnn_keys[0]].float() / 255.0 - 0.5 if cnn_keys else None
     is_first = data["is_first"].float().clone()
     is_first[0] = 1.0
     actions = torch.cat((torch.zeros_like(data["actions"][:1]), data["actions"][:-1]), 0).float()
@@ -338,7 +364,13 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
     cont_target = 1 - data["terminated"].float()
 
     # ---- encoder + RSSM scan (dreamer_v3.py:113-146; agent.py:396-435)
-    emb = encoder_forward(wm, obs, stages, ceps)
+    embs, vtargets = [], []
+    if cnn_keys:
+        embs.append(encoder_forward(wm, obs, stages, ceps))
+    if vkeys:                                  # MultiEncoder: cnn features first, then the vector features (models.py:466-475)
+        vemb, vtargets = mlp_encoder_forward(wm, data, vkeys, w.encoder.mlp_layers, w.encoder.mlp_layer_norm.kw.eps)
+        embs.append(vemb)
+    emb = torch.cat(embs, -1)
     h = torch.zeros(B, R)
     z = torch.zeros(B, Z)
     hs, zs, post_l, prior_l = [], [], [], []
@@ -359,8 +391,13 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
     latent = torch.cat((zs, hs), -1)
 
     # ---- heads + losses (dreamer_v3.py:149-190, loss.py:9-88)
-    recon = decoder_forward(wm, latent, stages, ceps, obs.shape[-3:])
-    obs_loss = ((recon - obs) ** 2).sum((-3, -2, -1))
+    obs_loss, recon = 0.0, None
+    if cnn_keys:
+        recon = decoder_forward(wm, latent, stages, ceps, obs.shape[-3:])
+        obs_loss = ((recon - obs) ** 2).sum((-3, -2, -1))
+    if vkeys:
+        obs_loss = obs_loss + mlp_decoder_loss(wm, latent, vtargets, w.observation_model.mlp_layers,
+                                               w.observation_model.mlp_layer_norm.kw.eps)
     head_in = latent.detach() if detach_heads else latent
     rew_logits = dense_stack(wm, "reward_model._model.", head_in, n_hid, eps, True)
     reward_loss = -twohot_log_prob(rew_logits, rewards)
@@ -388,7 +425,7 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
     })
     if keep:
         out.update({"emb": emb.detach(), "latent": latent.detach(), "post_logits": post_l.detach(),
-                    "prior_logits": prior_l.detach(), "recon": recon.detach(),
+                    "prior_logits": prior_l.detach(), "recon": None if recon is None else recon.detach(),
                     "reward_logits": rew_logits.detach(), "continue_logit": cont_logit.detach()})
 
     return zs, hs, cont_target
@@ -423,10 +460,7 @@ def dv3_train_step(
     H = a.horizon
     N = T * B
     eps = a.mlp_layer_norm.kw.eps
-    ceps = a.cnn_layer_norm.kw.eps
     um = a.unimix
-    stages = int(round(math.log2(cfg.env.screen_size) - 2))
-    key = a.cnn_keys.encoder[0]
     n_hid = a.mlp_layers
     out: Dict[str, Tensor] = {}
 
@@ -597,12 +631,19 @@ def init_params(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int
         if o is not None:
             lin(d, f"{prefix}{3 * n_hidden}", o, hidden, True, uni)
 
+    has_cnn, vd = len(a.cnn_keys.encoder) > 0, vec_dims(cfg)
+    vkeys = list(a.mlp_keys.encoder)
     chans = [in_channels] + [mult * 2 ** i for i in range(stages)]
-    for i in range(stages):
-        ci, co = chans[i], chans[i + 1]
-        wm[f"encoder.cnn_encoder.model.0._model.{3 * i}.weight"] = _trunc_normal((co, ci, 4, 4), 16 * ci, 16 * co, g, False)
-        ln(wm, f"encoder.cnn_encoder.model.0._model.{3 * i + 1}", co)
-    E = chans[-1] * 16
+    E = 0
+    if has_cnn:
+        for i in range(stages):
+            ci, co = chans[i], chans[i + 1]
+            wm[f"encoder.cnn_encoder.model.0._model.{3 * i}.weight"] = _trunc_normal((co, ci, 4, 4), 16 * ci, 16 * co, g, False)
+            ln(wm, f"encoder.cnn_encoder.model.0._model.{3 * i + 1}", co)
+        E = chans[-1] * 16
+    if vkeys:
+        mlp(wm, "encoder.mlp_encoder.model._model.", sum(vd[k] for k in vkeys), w.encoder.dense_units, w.encoder.mlp_layers, None, None)
+        E += w.encoder.dense_units
     wm["rssm.initial_recurrent_state"] = torch.zeros(R)
     lin(wm, "rssm.recurrent_model.mlp._model.0", w.recurrent_model.dense_units, Z + A, False)
     ln(wm, "rssm.recurrent_model.mlp._model.1", w.recurrent_model.dense_units)
@@ -610,9 +651,10 @@ def init_params(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int
     ln(wm, "rssm.recurrent_model.rnn.layer_norm", 3 * R)
     mlp(wm, "rssm.representation_model._model.", R + E, w.representation_model.hidden_size, 1, Z, 1.0)
     mlp(wm, "rssm.transition_model._model.", R, w.transition_model.hidden_size, 1, Z, 1.0)
-    lin(wm, "observation_model.cnn_decoder.model.0", E, L, True)
     dch = [chans[-1]] + [mult * 2 ** i for i in reversed(range(stages - 1))] + [in_channels]
-    for i in range(stages):
+    if has_cnn:
+        lin(wm, "observation_model.cnn_decoder.model.0", chans[-1] * 16, L, True)
+    for i in range(stages if has_cnn else 0):
         ci, co = dch[i], dch[i + 1]
         last = i == stages - 1
         name = f"observation_model.cnn_decoder.model.2._model.{3 * i}"
@@ -621,6 +663,11 @@ def init_params(cfg, actions_dim: Sequence[int], in_channels: int = 3, seed: int
             wm[name + ".bias"] = torch.zeros(co)
         else:
             ln(wm, f"observation_model.cnn_decoder.model.2._model.{3 * i + 1}", co)
+    if a.mlp_keys.decoder:
+        om = w.observation_model
+        mlp(wm, "observation_model.mlp_decoder.model._model.", L, om.dense_units, om.mlp_layers, None, None)
+        for i, k in enumerate(a.mlp_keys.decoder):
+            lin(wm, f"observation_model.mlp_decoder.heads.{i}", vd[k], om.dense_units, True, 1.0)
     mlp(wm, "reward_model._model.", L, du, nh, w.reward_model.bins, 0.0)
     mlp(wm, "continue_model._model.", L, du, nh, 1, 1.0)
     actor: Dict[str, Tensor] = {}
@@ -651,11 +698,15 @@ def make_batch(cfg, actions_dim: Sequence[int], seed: int = 1, in_channels: int 
         else:
             idx = torch.randint(0, ad, (T, B), generator=g)
             acts.append(F.one_hot(idx, ad).float())
-    return {
-        cfg.algo.cnn_keys.encoder[0]: rgb if as_uint8 else rgb.float(),
+    obs = {cfg.algo.cnn_keys.encoder[0]: rgb if as_uint8 else rgb.float()} if cfg.algo.cnn_keys.encoder else {}
+    out = {
+        **obs,
         "actions": torch.cat(acts, -1),
         "rewards": torch.randn(T, B, 1, generator=g),
         "terminated": (torch.rand(T, B, 1, generator=g) < 0.01).float(),
         "truncated": torch.zeros(T, B, 1),
         "is_first": (torch.rand(T, B, 1, generator=g) < 0.02).float(),
     }
+    for k, d in vec_dims(cfg).items():               # vector observations, heavy-tailed enough to exercise symlog
+        out[k] = torch.randn(T, B, d, generator=g) * 3.0
+    return out

@@ -383,6 +383,9 @@ class EmulOps:
     def axpy(self, x: Tensor, y: Tensor, alpha: float = 1.0):
         y.add_(x, alpha=alpha)
 
+    def symlog(self, x: Tensor, y: Tensor):
+        y.copy_(_symlog(x))
+
     def tanh_fwd(self, x: Tensor, y: Tensor):
         y.copy_(torch.tanh(x))
 

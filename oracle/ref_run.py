@@ -10,7 +10,7 @@ from typing import Dict, Sequence
 import torch
 
 from oracle import ref_harness
-from oracle.dv3_oracle import reference_noise_order, reference_normal_order
+from oracle.dv3_oracle import reference_noise_order, reference_normal_order, vec_dims
 
 
 def to_ref_cfg(cfg):
@@ -29,6 +29,7 @@ def build_reference_agent(cfg, actions_dim: Sequence[int], in_channels: int = 3,
     fab = ref_harness.FakeFabric()
     sz = cfg.env.screen_size
     obs_space = {k: ref_harness.Shape((in_channels, sz, sz)) for k in cfg.algo.cnn_keys.encoder}
+    obs_space.update({k: ref_harness.Shape((d,)) for k, d in vec_dims(cfg).items()})
     torch.manual_seed(seed)
     wm, actor, critic, target, player = build_agent(fab, tuple(actions_dim), is_continuous, rcfg, obs_space)
     return fab, rcfg, wm, actor, critic, target, player

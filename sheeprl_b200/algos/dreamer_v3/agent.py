@@ -97,18 +97,25 @@ def build_agent(
     actor_state: Optional[Dict[str, torch.Tensor]] = None,
     critic_state: Optional[Dict[str, torch.Tensor]] = None,
     target_critic_state: Optional[Dict[str, torch.Tensor]] = None,
+    ops=None,
 ) -> Tuple[WorldModel, ParamTree, ParamTree, ParamTree, PlayerDV3]:
-    key = cfg.algo.cnn_keys.encoder[0]
-    in_channels = int(math.prod(obs_space[key].shape[:-2]))
-    eng = DV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, is_continuous=is_continuous)
+    """ops (extra, optional): the kernel binding; default `sheeprl_b200.lib.CudaOps` (tests on a GPU-less host pass the
+    torch test double)."""
+    cnn_keys, mlp_keys = list(cfg.algo.cnn_keys.encoder or []), list(cfg.algo.mlp_keys.encoder or [])
+    in_channels = int(math.prod(obs_space[cnn_keys[0]].shape[:-2])) if cnn_keys else 3
+    mlp_dims = {k: int(obs_space[k].shape[0]) for k in mlp_keys}          # agent.py:1002
+    eng = DV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, ops=ops, is_continuous=is_continuous,
+                    mlp_dims=mlp_dims)
     g = torch.Generator().manual_seed(int(cfg.get("seed", 0) or 0))
     nh = cfg.algo.mlp_layers
     haf = bool(cfg.algo.hafner_initialization)
     last_dec = f"observation_model.cnn_decoder.model.2._model.{3 * (eng.stages - 1)}.weight"
     wm_scale = {"rssm.transition_model._model.3.weight": 1.0, "rssm.representation_model._model.3.weight": 1.0,
                 f"reward_model._model.{3 * nh}.weight": 0.0, f"continue_model._model.{3 * nh}.weight": 1.0} if haf else {}
-    wm_init = initial_state(eng.wm, wm_scale, g)
     if haf:
+        wm_scale.update({f"observation_model.mlp_decoder.heads.{i}.weight": 1.0 for i in range(len(mlp_keys))})   # agent.py:1177-1178
+    wm_init = initial_state(eng.wm, wm_scale, g)
+    if haf and cnn_keys:
         # `uniform_init_weights` only touches nn.Linear / nn.LayerNorm (dreamer_v3/utils.py:170-186): applied to the
         # last ConvTranspose2d (agent.py:1180) it is a no-op, so that layer keeps its truncated-normal init.
         assert last_dec in wm_init

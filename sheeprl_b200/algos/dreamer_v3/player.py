@@ -37,7 +37,8 @@ class PlayerDV3:
         cfg.algo.horizon = 1
         self.eng = DV3Engine(cfg, engine.actions_dim, in_channels=engine.Cin, device=engine.device, ops=engine.ops,
                              is_continuous=engine.is_continuous,
-                             groups=(engine.wm, actor_group or engine.actor, engine.critic, engine.target))
+                             groups=(engine.wm, actor_group or engine.actor, engine.critic, engine.target),
+                             mlp_dims=dict(zip(engine.vec_keys, engine.vec_dims)))
         e, E = self.eng, self.num_envs
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
         # persistent acting state (reference attribute names; leading dim 1 as in the reference)
@@ -85,11 +86,16 @@ class PlayerDV3:
             raise NotImplementedError("action masks (MineDojo actor) are not built")
         e, ops, E = self.eng, self.eng.ops, self.num_envs
         Z, R = e.Z, e.R
-        x = obs[e.key].reshape(E, e.Cin, e.img, e.img)
-        if x.dtype == torch.uint8:
-            ops.obs_prep(x.contiguous(), e.x0)
-        else:                                                                # already /255 - 0.5: layout change only
-            ops.transpose_batched(x.float().contiguous().view(E, e.Cin, e.img * e.img), e.x0.view(E, e.img * e.img, e.Cin))
+        if e.has_cnn:
+            x = obs[e.key].reshape(E, e.Cin, e.img, e.img)
+            if x.dtype == torch.uint8:
+                ops.obs_prep(x.contiguous(), e.x0)
+            else:                                                            # already /255 - 0.5: layout change only
+                ops.transpose_batched(x.float().contiguous().view(E, e.Cin, e.img * e.img), e.x0.view(E, e.img * e.img, e.Cin))
+        off = 0
+        for k, d in zip(e.vec_keys, e.vec_dims):                             # vector keys: symlog into the encoder input
+            ops.symlog(obs[k].reshape(E, d).float().contiguous(), e.vx[:, off:off + d])
+            off += d
         if noise is None:
             ops.increment(self._counter)
             ops.fill_exponential(self._noise_z.view(-1), self.rng_seed, 11, self._counter)
@@ -100,7 +106,7 @@ class PlayerDV3:
             nz, na = self._noise_z, self._noise_a
         else:
             nz, na = noise["z"].reshape(E, Z), noise["a"].reshape(E, e.A)
-        e._encoder_forward()                                                 # -> e.emb [E, 4096]
+        e._encoder_forward()                                                 # -> e.emb [E, 4096] / e.venc features
         # recurrent model on (z, a, h) of the previous step (agent.py:676-678)
         e._recurrent_forward(self.stochastic_state[0], self.actions[0], self.recurrent_state[0], e.x_pre, e.x_act,
                              e.g_pre, e.g_ln, self._h_next)
@@ -108,7 +114,7 @@ class PlayerDV3:
         # posterior from [h, embed] (agent.py:451-465) and its sample
         pr = "rssm.representation_model._model."
         Wr1 = e._w(pr + "0.weight")
-        ops.gemm(e.emb, Wr1[:, R:], e.rp_pre, False, True)
+        e._project_embedding(e.rp_pre)
         ops.gemm(self._h_next, Wr1[:, :R], e.rp_pre, False, True, accumulate=True)
         ops.ln_act_fwd(e.rp_pre, e._w(pr + "1.weight"), e._w(pr + "1.bias"), e.eps, ACT_SILU, e.rp_act)
         ops.gemm(e.rp_act, e._w(pr + "3.weight"), e.post_raw, False, True, bias=e._w(pr + "3.bias"))

@@ -39,14 +39,16 @@ def build_agent(
     critics_exploration_state: Optional[Dict[str, Dict[str, Any]]] = None,
     ops=None,
 ):
-    key = cfg.algo.cnn_keys.encoder[0]
-    in_channels = int(math.prod(obs_space[key].shape[:-2]))
-    eng = P2EDV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, ops=ops, is_continuous=is_continuous)
+    cnn_keys, mlp_keys = list(cfg.algo.cnn_keys.encoder or []), list(cfg.algo.mlp_keys.encoder or [])
+    in_channels = int(math.prod(obs_space[cnn_keys[0]].shape[:-2])) if cnn_keys else 3
+    eng = P2EDV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, ops=ops, is_continuous=is_continuous,
+                       mlp_dims={k: int(obs_space[k].shape[0]) for k in mlp_keys})
     seed = int(cfg.get("seed", 0) or 0)
     g = torch.Generator().manual_seed(seed)
     nh, haf = cfg.algo.mlp_layers, bool(cfg.algo.hafner_initialization)
     wm_scale = {"rssm.transition_model._model.3.weight": 1.0, "rssm.representation_model._model.3.weight": 1.0,
-                f"reward_model._model.{3 * nh}.weight": 0.0, f"continue_model._model.{3 * nh}.weight": 1.0} if haf else {}
+                f"reward_model._model.{3 * nh}.weight": 0.0, f"continue_model._model.{3 * nh}.weight": 1.0,
+                **{f"observation_model.mlp_decoder.heads.{i}.weight": 1.0 for i in range(len(mlp_keys))}} if haf else {}
     ac_scale = {f"mlp_heads.{i}.weight": 1.0 for i in range(len(actions_dim))} if haf else {}
     cr_scale = {f"_model.{3 * nh}.weight": 0.0} if haf else {}
     eng.wm.load(initial_state(eng.wm, wm_scale, g) if world_model_state is None else world_model_state)

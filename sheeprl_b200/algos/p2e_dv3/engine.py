@@ -46,16 +46,16 @@ class P2EDV3Engine(DV3Engine):
     METRIC_NAMES_P2E = ("Loss/ensemble_loss", "Loss/policy_loss_exploration")
 
     def __init__(self, cfg, actions_dim: Sequence[int], in_channels: int = 3, device="cuda", ops=None,
-                 is_continuous: bool = False):
+                 is_continuous: bool = False, mlp_dims=None):
         if is_continuous:
             raise NotImplementedError("Plan2Explore on the B200 engine: discrete actions only (continuous actions need the "
                                       "intrinsic reward's gradient through the ensembles)")
-        super().__init__(cfg, actions_dim, in_channels, device, ops, is_continuous=False)
+        super().__init__(cfg, actions_dim, in_channels, device, ops, is_continuous=False, mlp_dims=mlp_dims)
         a = cfg.algo
         N, H, L, A, Z = self.N, self.H, self.L, self.A, self.Z
         M1, M0 = (H + 1) * N, H * N
         b = self._buf
-        _, ac_s, cr_s, _ = dv3_param_shapes(cfg, self.actions_dim, in_channels, False)
+        _, ac_s, cr_s, _ = dv3_param_shapes(cfg, self.actions_dim, in_channels, False, dict(zip(self.vec_keys, self.vec_dims)))
         # ---- exploration actor and critics
         self.actor_expl = FlatGroup(ac_s, device)
         self.actor_expl_mlp = _MLP(self, self.actor_expl, "model._model.", L, self.du, self.nh, None, M1, self.eps,

@@ -9,7 +9,7 @@ configs/algo/dreamer_v3_{XS,S,M,L,XL}.yaml, configs/exp/dreamer_v3.yaml:10-26).
 from __future__ import annotations
 
 import copy
-from typing import Any, Dict, Sequence
+from typing import Any, Dict, Mapping, Sequence
 
 from sheeprl_b200.utils.utils import dotdict
 
@@ -36,6 +36,7 @@ def make_dv3_cfg(
     screen_size: int = 64,
     num_envs: int = 4,
     cnn_keys: Sequence[str] = ("rgb",),
+    mlp_keys: Mapping[str, int] | None = None,
     dense_units: int | None = None,
     mlp_layers: int | None = None,
     cnn_channels_multiplier: int | None = None,
@@ -47,7 +48,10 @@ def make_dv3_cfg(
     **overrides: Any,
 ) -> dotdict:
     """Build the resolved `cfg` tree `train()`/`build_agent()` read. Keyword overrides named like
-    `algo.world_model.kl_free_nats=0.1` may be passed through `overrides` with `__` for dots."""
+    `algo.world_model.kl_free_nats=0.1` may be passed through `overrides` with `__` for dots.
+    mlp_keys: {vector observation key: dimension}; the dimensions (which the reference reads from the observation
+    space) are kept under `env.mlp_dims` for the synthetic batches / initialisers."""
+    mlp_keys = dict(mlp_keys or {})
     du, ml, mult, rss, hs = DV3_SIZES[size]
     du = dense_units or du
     ml = mlp_layers or ml
@@ -66,7 +70,7 @@ def make_dv3_cfg(
     cfg = {
         "seed": 42,
         "dry_run": False,
-        "env": {"screen_size": screen_size, "num_envs": num_envs},
+        "env": {"screen_size": screen_size, "num_envs": num_envs, "mlp_dims": mlp_keys},
         "distribution": {"type": "auto", "validate_args": False},
         "algo": {
             "name": "dreamer_v3",
@@ -81,7 +85,7 @@ def make_dv3_cfg(
             "total_steps": 5000000,
             "run_test": True,
             "cnn_keys": {"encoder": list(cnn_keys), "decoder": list(cnn_keys)},
-            "mlp_keys": {"encoder": [], "decoder": []},
+            "mlp_keys": {"encoder": list(mlp_keys), "decoder": list(mlp_keys)},
             "cnn_layer_norm": copy.deepcopy(cnn_ln),
             "mlp_layer_norm": copy.deepcopy(mlp_ln),
             "dense_units": du,

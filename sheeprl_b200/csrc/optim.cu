@@ -189,6 +189,16 @@ __global__ void affine_kernel(const float* __restrict__ x, float* __restrict__ y
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = alpha * x[i] + beta;
 }
+// y[m, c] = symlog(x[m, c]) for a [M, C] block with row strides (vector observations squashed on the way into the
+// MLP encoder, dreamer_v3/agent.py:150; the same tensor is the MLP decoder's regression target, distribution.py:180)
+__global__ void symlog2d_kernel(const float* __restrict__ x, float* __restrict__ y, long long M, int C, long long ldx,
+                                long long ldy) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  const long long m = i / C;
+  const int c = (int)(i - m * C);
+  y[m * ldy + c] = symlogf_(x[m * ldx + c]);
+}
 __global__ void tanh_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = tanhf(x[i]);
@@ -294,6 +304,15 @@ extern "C" int b200rl_affine(const float* x, float* y, long long n, float alpha,
   RL_CHECK_ARG(x && y, "null pointer");
   if (n <= 0) return B200RL_OK;
   affine_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, y, n, alpha, beta);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_symlog(const float* x, float* y, long long M, int C, long long ldx, long long ldy, cudaStream_t st) {
+  RL_CHECK_ARG(x && y, "null pointer");
+  RL_CHECK_ARG(C > 0 && ldx >= C && ldy >= C, "bad C / ld");
+  if (M <= 0) return B200RL_OK;
+  symlog2d_kernel<<<ceil_div(M * C, 256), 256, 0, st>>>(x, y, M, C, ldx, ldy);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }

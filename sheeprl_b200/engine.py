@@ -22,7 +22,7 @@ Layouts (all fp32, row-major):
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Mapping, Optional, Sequence
 
 import torch
 
@@ -32,8 +32,11 @@ ACT_NONE, ACT_SILU = 0, 1
 TWOHOT_LOW, TWOHOT_HIGH = -20.0, 20.0
 
 
-def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int, is_continuous: bool = False):
-    """Shapes keyed by the reference's state-dict names (built in agent.py:935-1180)."""
+def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int, is_continuous: bool = False,
+                     mlp_dims: Optional[Mapping[str, int]] = None):
+    """Shapes keyed by the reference's state-dict names (built in agent.py:935-1180).
+    mlp_dims: {vector observation key: dimension} for the keys of cfg.algo.mlp_keys (MLPEncoder / MLPDecoder,
+    agent.py:100-152, 229-278); the CNN encoder / decoder exist only when cfg.algo.cnn_keys.encoder is not empty."""
     a, w = cfg.algo, cfg.algo.world_model
     S, D = w.stochastic_size, w.discrete_size
     Z, R = S * D, w.recurrent_model.recurrent_state_size
@@ -53,13 +56,19 @@ def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int, is_conti
             d[f"{prefix}{3 * n_hidden}.weight"] = (o, hidden)
             d[f"{prefix}{3 * n_hidden}.bias"] = (o,)
 
+    has_cnn = len(a.cnn_keys.encoder) > 0
+    vkeys, vdims = list(a.mlp_keys.encoder), dict(mlp_dims or {})
     chans = [in_channels] + [mult * 2 ** i for i in range(stages)]
-    for i in range(stages):
+    for i in range(stages if has_cnn else 0):
         p = f"encoder.cnn_encoder.model.0._model.{3 * i}"
         wm[p + ".weight"] = (chans[i + 1], chans[i], 4, 4)
         wm[f"encoder.cnn_encoder.model.0._model.{3 * i + 1}.weight"] = (chans[i + 1],)
         wm[f"encoder.cnn_encoder.model.0._model.{3 * i + 1}.bias"] = (chans[i + 1],)
-    E = chans[-1] * 16
+    E = chans[-1] * 16 if has_cnn else 0                     # CNN features; the vector features follow them
+    Ev = w.encoder.dense_units if vkeys else 0
+    if vkeys:
+        mlp(wm, "encoder.mlp_encoder.model._model.", sum(vdims[k] for k in vkeys), w.encoder.dense_units,
+            w.encoder.mlp_layers, None)
     dx = w.recurrent_model.dense_units
     wm["rssm.initial_recurrent_state"] = (R,)
     wm["rssm.recurrent_model.mlp._model.0.weight"] = (dx, Z + A)
@@ -68,12 +77,13 @@ def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int, is_conti
     wm["rssm.recurrent_model.rnn.linear.weight"] = (3 * R, R + dx)
     wm["rssm.recurrent_model.rnn.layer_norm.weight"] = (3 * R,)
     wm["rssm.recurrent_model.rnn.layer_norm.bias"] = (3 * R,)
-    mlp(wm, "rssm.representation_model._model.", R + E, w.representation_model.hidden_size, 1, Z)
+    mlp(wm, "rssm.representation_model._model.", R + E + Ev, w.representation_model.hidden_size, 1, Z)
     mlp(wm, "rssm.transition_model._model.", R, w.transition_model.hidden_size, 1, Z)
-    wm["observation_model.cnn_decoder.model.0.weight"] = (E, L)
-    wm["observation_model.cnn_decoder.model.0.bias"] = (E,)
+    if has_cnn:
+        wm["observation_model.cnn_decoder.model.0.weight"] = (E, L)
+        wm["observation_model.cnn_decoder.model.0.bias"] = (E,)
     dch = [chans[-1]] + [mult * 2 ** i for i in reversed(range(stages - 1))] + [in_channels]
-    for i in range(stages):
+    for i in range(stages if has_cnn else 0):
         p = f"observation_model.cnn_decoder.model.2._model.{3 * i}"
         wm[p + ".weight"] = (dch[i], dch[i + 1], 4, 4)
         if i == stages - 1:
@@ -81,6 +91,12 @@ def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int, is_conti
         else:
             wm[f"observation_model.cnn_decoder.model.2._model.{3 * i + 1}.weight"] = (dch[i + 1],)
             wm[f"observation_model.cnn_decoder.model.2._model.{3 * i + 1}.bias"] = (dch[i + 1],)
+    if a.mlp_keys.decoder:
+        om = w.observation_model
+        mlp(wm, "observation_model.mlp_decoder.model._model.", L, om.dense_units, om.mlp_layers, None)
+        for i, k in enumerate(a.mlp_keys.decoder):
+            wm[f"observation_model.mlp_decoder.heads.{i}.weight"] = (vdims[k], om.dense_units)
+            wm[f"observation_model.mlp_decoder.heads.{i}.bias"] = (vdims[k],)
     mlp(wm, "reward_model._model.", L, du, nh, w.reward_model.bins)
     mlp(wm, "continue_model._model.", L, du, nh, 1)
     mlp(actor, "model._model.", L, du, nh, None)
@@ -92,7 +108,7 @@ def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int, is_conti
             actor[f"mlp_heads.{i}.weight"] = (ad, du)
             actor[f"mlp_heads.{i}.bias"] = (ad,)
     mlp(critic, "_model.", L, du, nh, a.critic.bins)
-    return wm, actor, critic, dict(chans=chans, dch=dch, E=E, stages=stages)
+    return wm, actor, critic, dict(chans=chans, dch=dch, E=E, Ev=Ev, stages=stages)
 
 
 class _MLP:
@@ -166,21 +182,29 @@ class _MLP:
 
 class DV3Engine:
     def __init__(self, cfg, actions_dim: Sequence[int], in_channels: int = 3, device="cuda", ops=None,
-                 is_continuous: bool = False, groups=None):
+                 is_continuous: bool = False, groups=None, mlp_dims: Optional[Mapping[str, int]] = None):
         """groups: optional (wm, actor, critic, target) FlatGroups to adopt instead of allocating new ones — the acting
-        engine of PlayerDV3 shares the trainer's parameters this way (the reference ties `.data`, agent.py:1229-1235)."""
+        engine of PlayerDV3 shares the trainer's parameters this way (the reference ties `.data`, agent.py:1229-1235).
+        mlp_dims: {key: dimension} of the vector observations named in cfg.algo.mlp_keys (default: cfg.env.mlp_dims)."""
         a, w = cfg.algo, cfg.algo.world_model
         self.is_continuous = bool(is_continuous)
         if self.is_continuous and str(cfg.distribution.get("type", "auto")).lower() not in ("auto", "scaled_normal"):
             raise NotImplementedError(
                 "continuous actions: distribution.type must be auto / scaled_normal — the reference's own train() fails "
                 "with tanh_normal (entropy fallback shape, dreamer_v3.py:294-297) and normal (negative scale)")
-        if a.mlp_keys.encoder:
-            raise NotImplementedError("vector (mlp_keys) observations are not implemented in the B200 engine yet")
         if w.decoupled_rssm:
             raise NotImplementedError("decoupled_rssm is not implemented in the B200 engine yet")
-        if len(a.cnn_keys.encoder) != 1:
-            raise NotImplementedError("exactly one image key is supported")
+        if len(a.cnn_keys.encoder) > 1:
+            raise NotImplementedError("at most one image key is supported")
+        if list(a.cnn_keys.encoder) != list(a.cnn_keys.decoder) or list(a.mlp_keys.encoder) != list(a.mlp_keys.decoder):
+            raise NotImplementedError("the decoder must reconstruct exactly the encoder's keys")
+        if not a.cnn_keys.encoder and not a.mlp_keys.encoder:
+            raise ValueError("There must be at least one encoder, both cnn and mlp encoders are None")     # models.py:420-421
+        self.has_cnn = len(a.cnn_keys.encoder) == 1
+        self.vec_keys = list(a.mlp_keys.encoder)
+        vd = dict(mlp_dims if mlp_dims is not None else (cfg.env.get("mlp_dims", None) or {}))
+        self.vec_dims = [int(vd[k]) for k in self.vec_keys]
+        self.Dv = sum(self.vec_dims)
         if ops is None:
             from sheeprl_b200.lib import CudaOps  # raises loudly if the extension / a GPU is missing
 
@@ -204,9 +228,11 @@ class DV3Engine:
         self.ceps = float(a.cnn_layer_norm.kw.eps)
         self.unimix = float(a.unimix)
         self.img = cfg.env.screen_size
-        self.key = a.cnn_keys.encoder[0]
+        self.key = a.cnn_keys.encoder[0] if self.has_cnn else None
         self.bins_r, self.bins_c = w.reward_model.bins, a.critic.bins
-        wm_s, ac_s, cr_s, meta = dv3_param_shapes(cfg, self.actions_dim, in_channels, self.is_continuous)
+        wm_s, ac_s, cr_s, meta = dv3_param_shapes(cfg, self.actions_dim, in_channels, self.is_continuous,
+                                                  dict(zip(self.vec_keys, self.vec_dims)))
+        self.Ev = meta["Ev"]                                      # width of the vector-encoder features (0: none)
         self.AW = 2 * self.A if self.is_continuous else self.A          # width of the actor head output
         self.chans, self.dch, self.E, self.stages = meta["chans"], meta["dch"], meta["E"], meta["stages"]
         if groups is not None:
@@ -240,15 +266,27 @@ class DV3Engine:
         N, T, B, H, Z, R, L, A, E = self.N, self.T, self.B, self.H, self.Z, self.R, self.L, self.A, self.E
         b = self._buf
         img = self.img
-        self.x0 = b("x0", N, img, img, self.Cin)
+        n_st = self.stages if self.has_cnn else 0                # CNN encoder / decoder buffers exist only with an image key
+        self.x0 = b("x0", N, img, img, self.Cin) if self.has_cnn else None
         self.enc_y, self.enc_a = [], []
         s = img
-        for i in range(self.stages):
+        for i in range(n_st):
             s //= 2
             self.enc_y.append(b(f"enc_y{i}", N, s, s, self.chans[i + 1]))
             self.enc_a.append(b(f"enc_a{i}", N, s, s, self.chans[i + 1]))
-        self.emb = b("emb", N, E)
+        self.emb = b("emb", N, E) if self.has_cnn else None
         self.pe = b("pe", N, self.Dr)
+        if self.vec_keys:
+            # vector observations: vx = symlog(concat(obs_k)) is the MLP encoder's input AND the MLP decoder's target
+            we, wo = self.cfg.algo.world_model.encoder, self.cfg.algo.world_model.observation_model
+            self.vx = b("vx", N, self.Dv)
+            self.venc = _MLP(self, self.wm, "encoder.mlp_encoder.model._model.", self.Dv, we.dense_units, we.mlp_layers, None,
+                             N, float(we.mlp_layer_norm.kw.eps), "venc", True)
+            self.d_emb_vec = b("d_emb_vec", N, self.Ev)
+            self.vdec = _MLP(self, self.wm, "observation_model.mlp_decoder.model._model.", L, wo.dense_units, wo.mlp_layers,
+                             None, N, float(wo.mlp_layer_norm.kw.eps), "vdec", True)
+            self.vrecon, self.vec_rows = b("vrecon", N, self.Dv), b("vec_rows", N)
+            self.d_vdec_hidden = b("d_vdec_hidden", N, wo.dense_units)
         self.traj = b("traj", H + 1, N, L)
         self.latent = self.traj[0]
         # scan saves
@@ -276,23 +314,24 @@ class DV3Engine:
         self.dz_tot, self.dh_tot = b("dz_tot", B, Z), b("dh_tot", B, R)
         self.dh_in, self.dz_in = b("dh_in", B, R), b("dz_in", B, Z)
         self.d_h0 = b("d_h0", R)
-        self.d_emb = b("d_emb", N, E)
         self.kl_rows = b("kl_rows", N, 4)
-        # decoder
-        self.dec_lin = b("dec_lin", N, E)
-        C0 = self.dch[0]
-        self.dec_in = b("dec_in", N, 4, 4, C0)
-        self.dec_y, self.dec_a = [], []
-        s = 4
-        for i in range(self.stages - 1):
-            s *= 2
-            self.dec_y.append(b(f"dec_y{i}", N, s, s, self.dch[i + 1]))
-            self.dec_a.append(b(f"dec_a{i}", N, s, s, self.dch[i + 1]))
-        self.recon = b("recon", N, img, img, self.Cin)
-        self.d_dec_in = b("d_dec_in", N, 4, 4, C0)
-        self.d_dec_lin = b("d_dec_lin", N, E)
-        self.d_dec_a = [b(f"d_dec_a{i}", *self.dec_a[i].shape) for i in range(self.stages - 1)]
-        self.d_enc_a = [b(f"d_enc_a{i}", *self.enc_a[i].shape) for i in range(self.stages)]
+        self.dec_y, self.dec_a, self.d_dec_a, self.d_enc_a = [], [], [], []
+        if self.has_cnn:
+            self.d_emb = b("d_emb", N, E)
+            # decoder
+            self.dec_lin = b("dec_lin", N, E)
+            C0 = self.dch[0]
+            self.dec_in = b("dec_in", N, 4, 4, C0)
+            s = 4
+            for i in range(self.stages - 1):
+                s *= 2
+                self.dec_y.append(b(f"dec_y{i}", N, s, s, self.dch[i + 1]))
+                self.dec_a.append(b(f"dec_a{i}", N, s, s, self.dch[i + 1]))
+            self.recon = b("recon", N, img, img, self.Cin)
+            self.d_dec_in = b("d_dec_in", N, 4, 4, C0)
+            self.d_dec_lin = b("d_dec_lin", N, E)
+            self.d_dec_a = [b(f"d_dec_a{i}", *self.dec_a[i].shape) for i in range(self.stages - 1)]
+            self.d_enc_a = [b(f"d_enc_a{i}", *self.enc_a[i].shape) for i in range(self.stages)]
         # losses
         self.obs_rows, self.rew_rows, self.cont_rows = b("obs_rows", N), b("rew_rows", N), b("cont_rows", N)
         self.metrics = b("metrics", 16)
@@ -414,7 +453,12 @@ class DV3Engine:
         B, N, R, A = self.B, self.N, self.R, self.A
         w = self.cfg.algo.world_model
         # ---- inputs (dreamer_v3.py:98-104): normalise pixels, force is_first[0]=1, shift actions
-        ops.obs_prep(data[self.key].reshape(N, self.Cin, self.img, self.img), self.x0)
+        if self.has_cnn:
+            ops.obs_prep(data[self.key].reshape(N, self.Cin, self.img, self.img), self.x0)
+        off = 0
+        for k, d in zip(self.vec_keys, self.vec_dims):       # symlog squashing (MLPEncoder.forward, agent.py:150)
+            ops.symlog(data[k].reshape(N, d), self.vx[:, off:off + d])
+            off += d
         data["is_first"][0].fill_(1.0)                      # same in-place mutation as the reference (:100)
         first = data["is_first"].reshape(N)
         ops.zero(self.shift_actions[:B])
@@ -424,8 +468,7 @@ class DV3Engine:
 
         self._encoder_forward()
         # embed part of the representation model's first layer, for all T at once (no recurrence in it)
-        Wr1 = self._w("rssm.representation_model._model.0.weight")
-        ops.gemm(self.emb, Wr1[:, R:], self.pe, False, True)
+        self._project_embedding(self.pe)
         self._scan_forward(first)
         self._decoder_forward()
         rew_logits = self.reward_wm.forward(self.latent)
@@ -433,8 +476,16 @@ class DV3Engine:
 
         # ---- losses + seed gradients (loss.py:9-88); mean over T*B
         inv = 1.0 / N
-        P = self.img * self.img * self.Cin
-        ops.mse_loss_grad(self.recon.view(N, P), self.x0.view(N, P), inv, self.obs_rows, self.recon.view(N, P))
+        if self.has_cnn:
+            P = self.img * self.img * self.Cin
+            ops.mse_loss_grad(self.recon.view(N, P), self.x0.view(N, P), inv, self.obs_rows, self.recon.view(N, P))
+        if self.vec_keys:
+            # SymlogDistribution (utils/distribution.py:177-192): squared error against symlog(obs), summed over keys and
+            # dims (its `tol` = 1e-8 cut on the squared distance is not reproduced: |effect| < 1e-8 per element)
+            rows = self.vec_rows if self.has_cnn else self.obs_rows
+            ops.mse_loss_grad(self.vrecon, self.vx, inv, rows, self.vrecon)
+            if self.has_cnn:
+                ops.axpy(self.vec_rows, self.obs_rows)
         ops.twohot_loss_grad(rew_logits, rewards, None, inv, TWOHOT_LOW, TWOHOT_HIGH, self.rew_rows, self.d_rew_logits)
         ops.bce_loss_grad(cont_logit, self.true_cont, float(w.continue_scale_factor), inv, self.cont_rows,
                           self.d_cont_logit)
@@ -472,8 +523,22 @@ class DV3Engine:
         p = "observation_model.cnn_decoder.model.2._model."
         return f"{p}{3 * i}.weight", f"{p}{3 * i + 1}.weight", f"{p}{3 * i + 1}.bias"
 
+    def _project_embedding(self, out: torch.Tensor):
+        """out = embed W_r1[:, R:]^T with embed = [cnn features | vector features] (MultiEncoder, models.py:466-475); the
+        two feature blocks stay in their own buffers and meet in this product"""
+        ops, R, E = self.ops, self.R, self.E
+        Wr1 = self._w("rssm.representation_model._model.0.weight")
+        if self.has_cnn:
+            ops.gemm(self.emb, Wr1[:, R:R + E], out, False, True)
+        if self.vec_keys:
+            ops.gemm(self.venc.act[-1], Wr1[:, R + E:], out, False, True, accumulate=self.has_cnn)
+
     def _encoder_forward(self):
         ops = self.ops
+        if self.vec_keys:
+            self.venc.forward(self.vx)
+        if not self.has_cnn:
+            return
         cur = self.x0
         for i in range(self.stages):
             wn, gn, bn = self._enc_names(i)
@@ -486,8 +551,12 @@ class DV3Engine:
         ops.transpose_batched(cur.view(self.N, 16, C), self.emb.view(self.N, C, 16))
 
     def _encoder_backward(self):
-        """d_emb [N,E] (CHW order) -> conv weight / LN grads."""
+        """d_emb [N,E] (CHW order) -> conv weight / LN grads; d_emb_vec -> vector-encoder grads."""
         ops = self.ops
+        if self.vec_keys:
+            self.venc.backward(self.vx, self.d_emb_vec, None, False)
+        if not self.has_cnn:
+            return
         C = self.chans[-1]
         ops.transpose_batched(self.d_emb.view(self.N, C, 16), self.d_enc_a[-1].view(self.N, 16, C))
         for i in reversed(range(self.stages)):
@@ -501,8 +570,22 @@ class DV3Engine:
             if i > 0:
                 ops.conv_up(self.d_enc_a[i], self._w(wn), self.d_enc_a[i - 1])
 
+    def _vec_heads(self):
+        """[(head weight name, column offset, width)] of the MLP decoder's per-key output layers"""
+        out, off = [], 0
+        for i, d in enumerate(self.vec_dims):
+            out.append((f"observation_model.mlp_decoder.heads.{i}", off, d))
+            off += d
+        return out
+
     def _decoder_forward(self):
         ops = self.ops
+        if self.vec_keys:
+            hid = self.vdec.forward(self.latent)
+            for name, off, d in self._vec_heads():
+                ops.gemm(hid, self._w(name + ".weight"), self.vrecon[:, off:off + d], False, True, bias=self._w(name + ".bias"))
+        if not self.has_cnn:
+            return
         p = "observation_model.cnn_decoder.model."
         ops.gemm(self.latent, self._w(p + "0.weight"), self.dec_lin, False, True, bias=self._w(p + "0.bias"))
         C0 = self.dch[0]
@@ -519,7 +602,21 @@ class DV3Engine:
         ops.conv_up(cur, self._w(wn), self.recon, bias=self._w(wn.replace(".weight", ".bias")))
 
     def _decoder_backward(self):
-        """self.recon holds d(loss)/d(recon) (written in place by mse_loss_grad). Writes d_latent."""
+        """self.recon / self.vrecon hold d(loss)/d(reconstruction) (written in place by mse_loss_grad). Writes d_latent."""
+        ops = self.ops
+        if self.has_cnn:
+            self._cnn_decoder_backward()
+        if self.vec_keys:
+            hid = self.vdec.act[-1]
+            ops.zero(self.d_vdec_hidden)
+            for name, off, d in self._vec_heads():
+                dv = self.vrecon[:, off:off + d]
+                ops.gemm(dv, hid, self._gw(name + ".weight"), True, False)
+                ops.col_sum(dv, self._gw(name + ".bias"))
+                ops.gemm(dv, self._w(name + ".weight"), self.d_vdec_hidden, False, False, accumulate=True)
+            self.vdec.backward(self.latent, self.d_vdec_hidden, self.d_latent, self.has_cnn)
+
+    def _cnn_decoder_backward(self):
         ops = self.ops
         st = self.stages
         wn = self._dec_names(st - 1)[0]
@@ -636,7 +733,7 @@ class DV3Engine:
 
     def _scan_dims(self):
         return dict(T=self.T, B=self.B, S=self.S, D=self.D, R=self.R, A=self.A, Dx=self.Dx, Dt=self.Dt, Dr=self.Dr,
-                    ld_lat=self.L, ld_wr1=self.R + self.E)
+                    ld_lat=self.L, ld_wr1=self.R + self.E + self.Ev)
 
     def _scan_tensors(self, first: torch.Tensor):
         p = "rssm.recurrent_model."
@@ -726,8 +823,13 @@ class DV3Engine:
                        self.d_rp_act, self.d_rp_act, gW(pr + "1.weight"), gW(pr + "1.bias"))
         gWr1 = gW(pr + "0.weight")
         ops.gemm(self.d_rp_pre, h_all, gWr1[:, :R], True, False)
-        ops.gemm(self.d_rp_pre, self.emb, gWr1[:, R:], True, False)
-        ops.gemm(self.d_rp_pre, Wr1[:, R:], self.d_emb, False, False)
+        E = self.E
+        if self.has_cnn:
+            ops.gemm(self.d_rp_pre, self.emb, gWr1[:, R:R + E], True, False)
+            ops.gemm(self.d_rp_pre, Wr1[:, R:R + E], self.d_emb, False, False)
+        if self.vec_keys:
+            ops.gemm(self.d_rp_pre, self.venc.act[-1], gWr1[:, R + E:], True, False)
+            ops.gemm(self.d_rp_pre, Wr1[:, R + E:], self.d_emb_vec, False, False)
         # transition model
         ops.gemm(self.d_prior_raw, self.tr_act, gW(pt + "3.weight"), True, False)
         ops.col_sum(self.d_prior_raw, gW(pt + "3.bias"))

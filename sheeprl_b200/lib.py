@@ -384,6 +384,13 @@ class CudaOps:
         assert x.is_contiguous() and out.is_contiguous()
         self._ck(self.lib.b200rl_affine(_p(x), _p(out), c_ll(x.numel()), c_float(alpha), c_float(beta), self._st()))
 
+    def symlog(self, x, y):
+        """y[M,C] = symlog(x[M,C]); both may be column slices of wider buffers"""
+        _f32(x, y)
+        M, C = x.shape
+        assert tuple(y.shape) == (M, C)
+        self._ck(self.lib.b200rl_symlog(_p(x), _p(y), c_ll(M), c_int(C), c_ll(_ld(x)), c_ll(_ld(y)), self._st()))
+
     def tanh_fwd(self, x, y):
         _f32(x, y)
         self._ck(self.lib.b200rl_tanh_fwd(_p(x), _p(y), c_ll(x.numel()), self._st()))

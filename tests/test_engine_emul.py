@@ -24,7 +24,7 @@ def run_engine(cfg, adim, init, data, noise, steps, is_continuous=False):
     return eng, outs, grads
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo"])
 def test_engine_matches_oracle_and_reference(name):
     fx, cfg = load_fixture(name)
     adim = fx["actions_dim"]
@@ -51,3 +51,50 @@ def test_engine_matches_oracle_and_reference(name):
         assert_params_close(g.views, fx["after"][n], lrs[n], steps, tol=2e-6, label=n)
     assert float(eng.moments_state[0]) == pytest.approx(float(fx["moments"]["low"]), rel=1e-4, abs=1e-7)
     assert float(eng.moments_state[1]) == pytest.approx(float(fx["moments"]["high"]), rel=1e-4, abs=1e-7)
+
+
+@pytest.mark.parametrize("name", ["dv3_tiny_v", "dv3_tiny_vo"])
+def test_public_api_with_vector_observations(name):
+    """build_agent() takes the vector dimensions from the observation space, exposes the reference's state-dict keys
+    (encoder.mlp_encoder.*, observation_model.mlp_decoder.*; no cnn_* entries without an image key) and train() on a
+    batch dict with one tensor per observation key lands on the executed reference"""
+    from sheeprl_b200.algos.dreamer_v3.agent import build_agent
+    from sheeprl_b200.algos.dreamer_v3.dreamer_v3 import make_optimizers, train
+    from sheeprl_b200.algos.dreamer_v3.utils import Moments
+
+    fx, cfg = load_fixture(name)
+
+    class Fab:
+        device = torch.device("cpu")
+
+    class Space:
+        def __init__(self, shape):
+            self.shape = shape
+
+    space = {k: Space((3, 64, 64)) for k in cfg.algo.cnn_keys.encoder}
+    space.update({k: Space((d,)) for k, d in cfg.env.mlp_dims.items()})
+    cfg.env.pop("mlp_dims")                                      # the product must not depend on the test-only entry
+    wm0, *_ = build_agent(Fab, fx["actions_dim"], False, cfg, space, ops=EmulOps())          # default initialisation
+    assert set(wm0.state_dict()) == set(fx["init"]["wm"])
+    wm, actor, critic, target, player = build_agent(Fab, fx["actions_dim"], False, cfg, space, fx["init"]["wm"],
+                                                    fx["init"]["actor"], fx["init"]["critic"], fx["init"]["target"],
+                                                    ops=EmulOps())
+    eng = wm._b200_engine
+    opts = make_optimizers(eng, cfg)
+    mo = cfg.algo.actor.moments
+    moments = Moments(mo.decay, mo.max, mo.percentile.low, mo.percentile.high)
+
+    class Agg:
+        disabled = False
+        v = {}
+
+        def update(self, k, val):
+            self.v[k] = float(val)
+
+    for s in range(len(fx["data"])):
+        agg = Agg()
+        train(Fab, wm, actor, critic, target, *opts, {k: v.clone().float() for k, v in fx["data"][s].items()}, agg, cfg, False,
+              fx["actions_dim"], moments, noise=fx["noise"][s])
+        for k, v in fx["metrics"][s].items():
+            assert agg.v[k] == pytest.approx(v, rel=3e-5, abs=1e-6), (s, k)
+    assert_params_close(wm.state_dict(), fx["after"]["wm"], 1e-4, len(fx["data"]), tol=2e-6, label="wm")

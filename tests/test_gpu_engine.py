@@ -35,9 +35,10 @@ def check_grads(eng_grads, o_out, cfg, rtol):
             assert d <= rtol * max(gmax, 1e-12) + 1e-9, (grp, k, d, gmax)
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo"])
 def test_engine_cuda_matches_reference_fixture(name):
-    """dv3_tiny_c: continuous actions, policy gradient through the imagined rollout"""
+    """dv3_tiny_c: continuous actions, policy gradient through the imagined rollout; dv3_tiny_v / _vo: vector observations
+    (MLP encoder / decoder) next to / instead of the image"""
     fx, cfg = load_fixture(name)
     adim = fx["actions_dim"]
     steps = len(fx["data"])

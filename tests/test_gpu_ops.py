@@ -235,6 +235,21 @@ def test_obs_prep_and_transpose(ops):
     assert torch.equal(Yg.cpu(), Yc)
 
 
+def test_symlog_into_column_slices(ops):
+    """vector observations are squashed straight into their column range of the encoder-input buffer"""
+    cu, em = ops
+    x = rnd(37, 5, seed=1, scale=30.0)
+    x[0, :3] = torch.tensor([0.0, -0.0, 1e-9])
+    wide_c, wide_g = torch.full((37, 11), 7.0), torch.full((37, 11), 7.0, device="cuda")
+    em.symlog(x, wide_c[:, 4:9])
+    cu.symlog(x.cuda(), wide_g[:, 4:9])
+    close(wide_g, wide_c, rtol=1e-6, atol=1e-7, what="symlog")
+    src_w = rnd(37, 9, seed=2, scale=5.0)                       # strided source as well
+    em.symlog(src_w[:, 2:7], wide_c[:, 0:5])
+    cu.symlog(src_w.cuda()[:, 2:7], wide_g[:, 0:5])
+    close(wide_g, wide_c, rtol=1e-6, atol=1e-7, what="symlog strided")
+
+
 @pytest.mark.parametrize("M,R", [(16, 512), (1024, 24), (3, 7)])
 def test_gru_gate(ops, M, R):
     cu, em = ops

@@ -15,7 +15,7 @@ def cu():
     return CudaOps()
 
 
-@pytest.mark.parametrize("name", ["dv3_player_discrete", "dv3_player_continuous"])
+@pytest.mark.parametrize("name", ["dv3_player_discrete", "dv3_player_continuous", "dv3_player_vector", "dv3_player_vector_only"])
 @pytest.mark.parametrize("uint8_obs", [False, True])
 def test_player_matches_reference(cu, name, uint8_obs):
     fx, got, cont = run_player(name, device="cuda", ops=cu, uint8_obs=uint8_obs)

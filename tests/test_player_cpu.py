@@ -20,16 +20,16 @@ def run_player(name, device="cpu", ops=None, uint8_obs=False):
     eng = DV3Engine(cfg, tf["actions_dim"], in_channels=3, device=device, ops=ops or EmulOps(), is_continuous=cont)
     eng.wm.load(tf["init"]["wm"]), eng.actor.load(tf["init"]["actor"])
     player = PlayerDV3(eng, fx["num_envs"])
-    key = cfg.algo.cnn_keys.encoder[0]
+    key = cfg.algo.cnn_keys.encoder[0] if cfg.algo.cnn_keys.encoder else None
     player.init_states()
     got = [{"h": player.recurrent_state.clone().cpu(), "z": player.stochastic_state.clone().cpu(), "a": player.actions.clone().cpu()}]
     for s, obs in enumerate(fx["obs"]):
         if s == fx["reset_at"]:
             player.init_states(fx["reset_envs"])
-        o = obs.to(device)
-        if uint8_obs:                                           # raw pixels: the kernel normalises
-            o = torch.round((o + 0.5) * 255).to(torch.uint8)
-        acts = player.get_actions({key: o}, noise={"z": fx["noise_z"][s].to(device), "a": fx["noise_a"][s].to(device)})
+        o = {k: v.to(device) for k, v in obs.items()} if isinstance(obs, dict) else {key: obs.to(device)}
+        if uint8_obs and key is not None:                       # raw pixels: the kernel normalises
+            o[key] = torch.round((o[key] + 0.5) * 255).to(torch.uint8)
+        acts = player.get_actions(o, noise={"z": fx["noise_z"][s].to(device), "a": fx["noise_a"][s].to(device)})
         assert torch.equal(torch.cat(acts, -1), player.actions)
         got.append({"h": player.recurrent_state.clone().cpu(), "z": player.stochastic_state.clone().cpu(),
                     "a": player.actions.clone().cpu()})
@@ -46,7 +46,10 @@ def check(fx, got, cont):
             assert torch.equal(g["a"], w["a"]), f"actions differ after call {i}"
 
 
-@pytest.mark.parametrize("name", ["dv3_player_discrete", "dv3_player_continuous"])
+PLAYER_FIXTURES = ["dv3_player_discrete", "dv3_player_continuous", "dv3_player_vector", "dv3_player_vector_only"]
+
+
+@pytest.mark.parametrize("name", PLAYER_FIXTURES)
 def test_player_matches_reference(name):
     fx, got, cont = run_player(name)
     check(fx, got, cont)
