@@ -356,7 +356,9 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
     n_hid = a.mlp_layers
 
     # ---- dreamer_v3.py:98-104
-    obs = data[cnn_keys[0]].float() / 255.0 - 0.5 if cnn_keys else None
+    # several image keys are concatenated on the channel axis (CNNEncoder.forward agent.py:96); the decoder's per-key
+    # MSE terms (CNNDecoder splits its output, agent.py:226) add up to the MSE over the concatenated image
+    obs = torch.cat([data[k].float() for k in cnn_keys], -3) / 255.0 - 0.5 if cnn_keys else None
     is_first = data["is_first"].float().clone()
     is_first[0] = 1.0
     actions = torch.cat((torch.zeros_like(data["actions"][:1]), data["actions"][:-1]), 0).float()
@@ -690,7 +692,10 @@ def make_batch(cfg, actions_dim: Sequence[int], seed: int = 1, in_channels: int 
     g = torch.Generator().manual_seed(seed)
     T, B = cfg.algo.per_rank_sequence_length, cfg.algo.per_rank_batch_size
     sz = cfg.env.screen_size
-    rgb = torch.randint(0, 256, (T, B, in_channels, sz, sz), generator=g, dtype=torch.uint8)
+    cch = dict(cfg.env.get("cnn_channels", {}) or {})
+    first = cfg.algo.cnn_keys.encoder[0] if cfg.algo.cnn_keys.encoder else None
+    rgb = torch.randint(0, 256, (T, B, cch.get(first, in_channels) if len(cch) > 1 else in_channels, sz, sz), generator=g,
+                        dtype=torch.uint8)
     acts = []
     for ad in actions_dim:
         if is_continuous:
@@ -709,4 +714,7 @@ def make_batch(cfg, actions_dim: Sequence[int], seed: int = 1, in_channels: int 
     }
     for k, d in vec_dims(cfg).items():               # vector observations, heavy-tailed enough to exercise symlog
         out[k] = torch.randn(T, B, d, generator=g) * 3.0
+    for k in list(cfg.algo.cnn_keys.encoder)[1:]:    # further image keys (drawn last: older fixtures keep their streams)
+        img = torch.randint(0, 256, (T, B, cch[k], sz, sz), generator=g, dtype=torch.uint8)
+        out[k] = img if as_uint8 else img.float()
     return out

@@ -28,7 +28,9 @@ def build_reference_agent(cfg, actions_dim: Sequence[int], in_channels: int = 3,
     rcfg = to_ref_cfg(cfg)
     fab = ref_harness.FakeFabric()
     sz = cfg.env.screen_size
-    obs_space = {k: ref_harness.Shape((in_channels, sz, sz)) for k in cfg.algo.cnn_keys.encoder}
+    cch = dict(cfg.env.get("cnn_channels", {}) or {})
+    multi = len(cfg.algo.cnn_keys.encoder) > 1
+    obs_space = {k: ref_harness.Shape((cch[k] if multi else in_channels, sz, sz)) for k in cfg.algo.cnn_keys.encoder}
     obs_space.update({k: ref_harness.Shape((d,)) for k, d in vec_dims(cfg).items()})
     torch.manual_seed(seed)
     wm, actor, critic, target, player = build_agent(fab, tuple(actions_dim), is_continuous, rcfg, obs_space)

@@ -102,7 +102,7 @@ def build_agent(
     """ops (extra, optional): the kernel binding; default `sheeprl_b200.lib.CudaOps` (tests on a GPU-less host pass the
     torch test double)."""
     cnn_keys, mlp_keys = list(cfg.algo.cnn_keys.encoder or []), list(cfg.algo.mlp_keys.encoder or [])
-    in_channels = int(math.prod(obs_space[cnn_keys[0]].shape[:-2])) if cnn_keys else 3
+    in_channels = sum(int(math.prod(obs_space[k].shape[:-2])) for k in cnn_keys) if cnn_keys else 3    # agent.py:984
     mlp_dims = {k: int(obs_space[k].shape[0]) for k in mlp_keys}          # agent.py:1002
     eng = DV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, ops=ops, is_continuous=is_continuous,
                     mlp_dims=mlp_dims)

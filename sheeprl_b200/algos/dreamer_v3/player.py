@@ -87,7 +87,7 @@ class PlayerDV3:
         e, ops, E = self.eng, self.eng.ops, self.num_envs
         Z, R = e.Z, e.R
         if e.has_cnn:
-            x = obs[e.key].reshape(E, e.Cin, e.img, e.img)
+            x = e.image_batch(obs, E)
             if x.dtype == torch.uint8:
                 ops.obs_prep(x.contiguous(), e.x0)
             else:                                                            # already /255 - 0.5: layout change only

@@ -37,6 +37,7 @@ def make_dv3_cfg(
     num_envs: int = 4,
     cnn_keys: Sequence[str] = ("rgb",),
     mlp_keys: Mapping[str, int] | None = None,
+    cnn_channels: Mapping[str, int] | None = None,
     dense_units: int | None = None,
     mlp_layers: int | None = None,
     cnn_channels_multiplier: int | None = None,
@@ -52,6 +53,7 @@ def make_dv3_cfg(
     mlp_keys: {vector observation key: dimension}; the dimensions (which the reference reads from the observation
     space) are kept under `env.mlp_dims` for the synthetic batches / initialisers."""
     mlp_keys = dict(mlp_keys or {})
+    cnn_channels = {k: int((cnn_channels or {}).get(k, 3)) for k in cnn_keys}     # channels per image key (synthetic data)
     du, ml, mult, rss, hs = DV3_SIZES[size]
     du = dense_units or du
     ml = mlp_layers or ml
@@ -70,7 +72,7 @@ def make_dv3_cfg(
     cfg = {
         "seed": 42,
         "dry_run": False,
-        "env": {"screen_size": screen_size, "num_envs": num_envs, "mlp_dims": mlp_keys},
+        "env": {"screen_size": screen_size, "num_envs": num_envs, "mlp_dims": mlp_keys, "cnn_channels": cnn_channels},
         "distribution": {"type": "auto", "validate_args": False},
         "algo": {
             "name": "dreamer_v3",

@@ -194,13 +194,12 @@ class DV3Engine:
                 "with tanh_normal (entropy fallback shape, dreamer_v3.py:294-297) and normal (negative scale)")
         if w.decoupled_rssm:
             raise NotImplementedError("decoupled_rssm is not implemented in the B200 engine yet")
-        if len(a.cnn_keys.encoder) > 1:
-            raise NotImplementedError("at most one image key is supported")
         if list(a.cnn_keys.encoder) != list(a.cnn_keys.decoder) or list(a.mlp_keys.encoder) != list(a.mlp_keys.decoder):
             raise NotImplementedError("the decoder must reconstruct exactly the encoder's keys")
         if not a.cnn_keys.encoder and not a.mlp_keys.encoder:
             raise ValueError("There must be at least one encoder, both cnn and mlp encoders are None")     # models.py:420-421
-        self.has_cnn = len(a.cnn_keys.encoder) == 1
+        self.cnn_keys = list(a.cnn_keys.encoder)          # several image keys: concatenated on the channel axis (agent.py:96)
+        self.has_cnn = len(self.cnn_keys) > 0
         self.vec_keys = list(a.mlp_keys.encoder)
         vd = dict(mlp_dims if mlp_dims is not None else (cfg.env.get("mlp_dims", None) or {}))
         self.vec_dims = [int(vd[k]) for k in self.vec_keys]
@@ -454,7 +453,7 @@ class DV3Engine:
         w = self.cfg.algo.world_model
         # ---- inputs (dreamer_v3.py:98-104): normalise pixels, force is_first[0]=1, shift actions
         if self.has_cnn:
-            ops.obs_prep(data[self.key].reshape(N, self.Cin, self.img, self.img), self.x0)
+            ops.obs_prep(self.image_batch(data, N), self.x0)
         off = 0
         for k, d in zip(self.vec_keys, self.vec_dims):       # symlog squashing (MLPEncoder.forward, agent.py:150)
             ops.symlog(data[k].reshape(N, d), self.vx[:, off:off + d])
@@ -522,6 +521,18 @@ class DV3Engine:
     def _dec_names(self, i):
         p = "observation_model.cnn_decoder.model.2._model."
         return f"{p}{3 * i}.weight", f"{p}{3 * i + 1}.weight", f"{p}{3 * i + 1}.bias"
+
+    def image_batch(self, obs: Dict[str, torch.Tensor], rows: int) -> torch.Tensor:
+        """[rows, Cin, H, W] pixels (uint8 or float) of the image key(s); more than one key is concatenated on the channel
+        axis, as CNNEncoder.forward does on every call (agent.py:96) — a device copy, no arithmetic"""
+        imgs = [obs[k].reshape(rows, -1, self.img, self.img) for k in self.cnn_keys]
+        if len(imgs) == 1:
+            return imgs[0]
+        if any(t.dtype != imgs[0].dtype for t in imgs):
+            imgs = [t.float() for t in imgs]
+        out = torch.cat(imgs, 1)
+        assert out.shape[1] == self.Cin, f"image keys carry {out.shape[1]} channels, the encoder was built for {self.Cin}"
+        return out
 
     def _project_embedding(self, out: torch.Tensor):
         """out = embed W_r1[:, R:]^T with embed = [cnn features | vector features] (MultiEncoder, models.py:466-475); the

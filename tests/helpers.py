@@ -52,3 +52,9 @@ def assert_params_close(got, want, lr, steps, tol=1e-6, frac=2e-3, label=""):
         worst_frac = max(worst_frac, f)
         assert f <= frac or int(bad.sum()) <= 3, (label, k, f, int(bad.sum()))
     return worst_frac
+
+
+def image_channels(cfg) -> int:
+    """total channels of the image keys of a fixture config (3 for the single-key fixtures)"""
+    cch = dict(cfg.env.get("cnn_channels", {}) or {})
+    return sum(cch.values()) if len(cch) > 1 else 3

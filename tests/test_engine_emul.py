@@ -6,11 +6,11 @@ import torch
 
 from oracle.ops_emul import EmulOps
 from sheeprl_b200.engine import DV3Engine
-from tests.helpers import assert_params_close, load_fixture, oracle_run
+from tests.helpers import assert_params_close, image_channels, load_fixture, oracle_run
 
 
 def run_engine(cfg, adim, init, data, noise, steps, is_continuous=False):
-    eng = DV3Engine(cfg, adim, in_channels=3, device="cpu", ops=EmulOps(), is_continuous=is_continuous)
+    eng = DV3Engine(cfg, adim, in_channels=image_channels(cfg), device="cpu", ops=EmulOps(), is_continuous=is_continuous)
     eng.wm.load(init["wm"]), eng.actor.load(init["actor"]), eng.critic.load(init["critic"])
     eng.target.load(init["target"])
     outs, grads = [], []
@@ -24,7 +24,7 @@ def run_engine(cfg, adim, init, data, noise, steps, is_continuous=False):
     return eng, outs, grads
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk"])
 def test_engine_matches_oracle_and_reference(name):
     fx, cfg = load_fixture(name)
     adim = fx["actions_dim"]
@@ -53,7 +53,7 @@ def test_engine_matches_oracle_and_reference(name):
     assert float(eng.moments_state[1]) == pytest.approx(float(fx["moments"]["high"]), rel=1e-4, abs=1e-7)
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_v", "dv3_tiny_vo"])
+@pytest.mark.parametrize("name", ["dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk"])
 def test_public_api_with_vector_observations(name):
     """build_agent() takes the vector dimensions from the observation space, exposes the reference's state-dict keys
     (encoder.mlp_encoder.*, observation_model.mlp_decoder.*; no cnn_* entries without an image key) and train() on a
@@ -71,9 +71,9 @@ def test_public_api_with_vector_observations(name):
         def __init__(self, shape):
             self.shape = shape
 
-    space = {k: Space((3, 64, 64)) for k in cfg.algo.cnn_keys.encoder}
+    space = {k: Space((cfg.env.cnn_channels[k], 64, 64)) for k in cfg.algo.cnn_keys.encoder}
     space.update({k: Space((d,)) for k, d in cfg.env.mlp_dims.items()})
-    cfg.env.pop("mlp_dims")                                      # the product must not depend on the test-only entry
+    cfg.env.pop("mlp_dims"), cfg.env.pop("cnn_channels")        # the product must not depend on the test-only entries
     wm0, *_ = build_agent(Fab, fx["actions_dim"], False, cfg, space, ops=EmulOps())          # default initialisation
     assert set(wm0.state_dict()) == set(fx["init"]["wm"])
     wm, actor, critic, target, player = build_agent(Fab, fx["actions_dim"], False, cfg, space, fx["init"]["wm"],

@@ -17,7 +17,9 @@ def to_cuda(d):
 def make_engine(cfg, adim, init, is_continuous=False):
     from sheeprl_b200.engine import DV3Engine
 
-    eng = DV3Engine(cfg, adim, in_channels=3, device="cuda", is_continuous=is_continuous)
+    from tests.helpers import image_channels
+
+    eng = DV3Engine(cfg, adim, in_channels=image_channels(cfg), device="cuda", is_continuous=is_continuous)
     eng.wm.load(init["wm"]), eng.actor.load(init["actor"]), eng.critic.load(init["critic"])
     eng.target.load(init["target"])
     return eng
@@ -35,7 +37,7 @@ def check_grads(eng_grads, o_out, cfg, rtol):
             assert d <= rtol * max(gmax, 1e-12) + 1e-9, (grp, k, d, gmax)
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk"])
 def test_engine_cuda_matches_reference_fixture(name):
     """dv3_tiny_c: continuous actions, policy gradient through the imagined rollout; dv3_tiny_v / _vo: vector observations
     (MLP encoder / decoder) next to / instead of the image"""

@@ -136,3 +136,27 @@ def check_public_api(device="cpu", ops=None):
 
 def test_public_api_matches_reference():
     check_public_api()
+
+
+def test_finetuning_update_is_the_task_behaviour_step():
+    """p2e_dv3_finetuning.train is dreamer_v3.train on the task actor / critic of the exploration agent: on a P2E engine
+    it reproduces what a plain Dreamer-V3 engine with the same task weights does"""
+    from oracle.ops_emul import EmulOps
+    from sheeprl_b200.algos.p2e_dv3.p2e_dv3_finetuning import train
+    from sheeprl_b200.algos.dreamer_v3.agent import ParamTree
+    from sheeprl_b200.engine import DV3Engine
+
+    fx, cfg = load()
+    p2e = make_engine(fx, cfg)
+    plain = DV3Engine(cfg, fx["actions_dim"], in_channels=3, device="cpu", ops=EmulOps())
+    for g, n in ((plain.wm, "wm"), (plain.actor, "actor_task"), (plain.critic, "critic_task"), (plain.target, "target_task")):
+        g.load(fx["init"][n])
+    noise = {"post": fx["noise"][0]["post"], "img_state": fx["noise"][0]["img_state_task"], "img_action": fx["noise"][0]["img_action_task"]}
+    data = lambda: {k: v.clone().float() for k, v in fx["data"][0].items()}  # noqa: E731
+    wm = ParamTree(p2e.wm.views)
+    object.__setattr__(wm, "_b200_engine", p2e)
+    DV3Engine.train_step(plain, data(), noise)
+    # the reference signature; the P2E engine must run the PLAIN step here, not the exploration one
+    train(None, wm, None, None, None, None, None, None, data(), None, cfg, False, fx["actions_dim"], None, noise=noise)
+    for a, b in ((plain.wm, p2e.wm), (plain.actor, p2e.actor), (plain.critic, p2e.critic)):
+        assert torch.equal(a.flat, b.flat)
