@@ -160,3 +160,26 @@ def test_finetuning_update_is_the_task_behaviour_step():
     train(None, wm, None, None, None, None, None, None, data(), None, cfg, False, fx["actions_dim"], None, noise=noise)
     for a, b in ((plain.wm, p2e.wm), (plain.actor, p2e.actor), (plain.critic, p2e.critic)):
         assert torch.equal(a.flat, b.flat)
+
+
+def test_player_acts_with_the_exploration_actor():
+    """`algo.player.actor_type = exploration` (p2e_dv3/agent.py:206-212): the player's policy is the exploration actor,
+    sharing its flat group (an update is visible to the next action without a copy)"""
+    from oracle.ops_emul import EmulOps
+    from sheeprl_b200.algos.dreamer_v3.player import PlayerDV3
+    from sheeprl_b200.engine import DV3Engine
+
+    fx, cfg = load()
+    eng = make_engine(fx, cfg)
+    p2e_player = PlayerDV3(eng, 2, actor_type="exploration", actor_group=eng.actor_expl)
+    assert p2e_player.eng.actor is eng.actor_expl and p2e_player.eng.wm is eng.wm
+    plain = DV3Engine(cfg, fx["actions_dim"], in_channels=3, device="cpu", ops=EmulOps())
+    plain.wm.load(fx["init"]["wm"]), plain.actor.load(fx["init"]["actor_expl"])
+    ref_player = PlayerDV3(plain, 2)
+    g = torch.Generator().manual_seed(0)
+    obs = {"rgb": torch.randint(0, 256, (1, 2, 3, 64, 64), generator=g, dtype=torch.uint8)}
+    noise = {"z": torch.empty(2, eng.Z).exponential_(1.0, generator=g), "a": torch.empty(2, eng.A).exponential_(1.0, generator=g)}
+    for p in (p2e_player, ref_player):
+        p.init_states()
+    a, b = p2e_player.get_actions(obs, noise=noise), ref_player.get_actions(obs, noise=noise)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
