@@ -18,7 +18,6 @@ from __future__ import annotations
 from typing import Dict, List, Sequence
 
 import torch
-import torch.nn.functional as F
 from torch import Tensor
 
 from oracle.dv3_oracle import (AdamState, actor_logits, categorical_normalise, clip_grad_norm, dense_stack, recurrent_step,

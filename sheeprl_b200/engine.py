@@ -22,7 +22,7 @@ Layouts (all fp32, row-major):
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Mapping, Optional, Sequence
+from typing import Dict, Mapping, Optional, Sequence
 
 import torch
 

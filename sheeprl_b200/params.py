@@ -9,7 +9,7 @@ and shapes and `nn.Parameter.data` can alias them.
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Dict, Iterable, Mapping, Tuple
+from typing import Dict, Mapping, Tuple
 
 import torch
 

@@ -10,8 +10,6 @@ import os
 import pathlib
 from typing import Any, Dict, Optional
 
-import torch
-
 from sheeprl_b200.data.buffers import EnvIndependentReplayBuffer, ReplayBuffer
 
 
