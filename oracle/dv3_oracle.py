@@ -376,7 +376,10 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
     h = torch.zeros(B, R)
     z = torch.zeros(B, Z)
     hs, zs, post_l, prior_l = [], [], [], []
-    h0 = torch.tanh(wm["rssm.initial_recurrent_state"]).expand(B, R)
+    h0_raw = wm["rssm.initial_recurrent_state"]
+    if not w.get("learnable_initial_recurrent_state", True):     # a buffer, not a parameter (agent.py:382-389)
+        h0_raw = h0_raw.detach()
+    h0 = torch.tanh(h0_raw).expand(B, R)
     for t in range(T):
         f = is_first[t]
         act = (1 - f) * actions[t]
@@ -412,6 +415,9 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
     kl_loss = dyn + rep
     rec_loss = (w.kl_regularizer * kl_loss + obs_loss + reward_loss + continue_loss).mean()
     rec_loss.backward()
+    for v in wm.values():
+        if v.grad is None:
+            v.grad = torch.zeros_like(v)                         # buffers: no gradient, Adam leaves them untouched
     with torch.no_grad():
         wm_norm = clip_grad_norm([v.grad for v in wm.values()], w.clip_gradients)
         if keep:

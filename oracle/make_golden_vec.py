@@ -27,6 +27,9 @@ FIXTURES = {
     # two image keys (concatenated on the channel axis by the encoder, split again by the decoder) + one vector key
     "dv3_tiny_mk": dict(cfg=dict(BASE, cnn_keys=("rgb", "depth"), cnn_channels={"rgb": 3, "depth": 1}, mlp_keys={"state": 4}),
                         actions_dim=(3,), perturb=0.05, steps=2),
+    # non-default switches: the initial recurrent state is a buffer (not trained), no uniform mix
+    "dv3_tiny_h0": dict(cfg=dict(BASE, algo__world_model__learnable_initial_recurrent_state=False, algo__unimix=0.0,
+                                 algo__actor__unimix=0.0), actions_dim=(3,), perturb=0.05, steps=2),
 }
 
 

@@ -861,7 +861,10 @@ class DV3Engine:
         ops.gemm(self.d_x_pre, self.z_in, gWin[:, :Z], True, False)
         ops.gemm(self.d_x_pre, self.a_in, gWin[:, Z:], True, False)
         # learned initial recurrent state: h0 = tanh(param)
-        ops.tanh_bwd(self.h0.view(R), self.d_h0, gW("rssm.initial_recurrent_state"))
+        if self.cfg.algo.world_model.get("learnable_initial_recurrent_state", True):
+            ops.tanh_bwd(self.h0.view(R), self.d_h0, gW("rssm.initial_recurrent_state"))
+        # else: a buffer in the reference (agent.py:382-389) — its gradient stays at the zero `wm.grad` was reset to, the
+        # norm ignores it and Adam's zero moments leave the value untouched
 
     # ------------------------------------------------------------------ optimiser
     def _optimizer_step(self, name: str, g: FlatGroup, max_norm: float, ocfg, slot: int):

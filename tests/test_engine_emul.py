@@ -24,7 +24,7 @@ def run_engine(cfg, adim, init, data, noise, steps, is_continuous=False):
     return eng, outs, grads
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk", "dv3_tiny_h0"])
 def test_engine_matches_oracle_and_reference(name):
     fx, cfg = load_fixture(name)
     adim = fx["actions_dim"]

@@ -37,7 +37,7 @@ def check_grads(eng_grads, o_out, cfg, rtol):
             assert d <= rtol * max(gmax, 1e-12) + 1e-9, (grp, k, d, gmax)
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk", "dv3_tiny_h0"])
 def test_engine_cuda_matches_reference_fixture(name):
     """dv3_tiny_c: continuous actions, policy gradient through the imagined rollout; dv3_tiny_v / _vo: vector observations
     (MLP encoder / decoder) next to / instead of the image"""

@@ -8,7 +8,7 @@ from tests.helpers import assert_params_close, load_fixture, oracle_run
 METRICS_RTOL = 2e-5
 
 
-@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk"])
+@pytest.mark.parametrize("name", ["dv3_tiny_a", "dv3_tiny_b", "dv3_tiny_c", "dv3_tiny_v", "dv3_tiny_vo", "dv3_tiny_mk", "dv3_tiny_h0"])
 def test_oracle_matches_reference_fixture(name):
     fx, cfg = load_fixture(name)
     steps = len(fx["data"])
