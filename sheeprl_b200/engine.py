@@ -111,6 +111,36 @@ def dv3_param_shapes(cfg, actions_dim: Sequence[int], in_channels: int, is_conti
     return wm, actor, critic, dict(chans=chans, dch=dch, E=E, Ev=Ev, stages=stages)
 
 
+def _check_supported_modules(cfg) -> None:
+    """The kernels implement the reference's default module choices (configs/algo/dreamer_v3.yaml): SiLU everywhere,
+    LayerNorm after every hidden layer / conv stage, heads as wide and deep as `algo.dense_units` / `algo.mlp_layers`.
+    Anything else must fail loudly instead of silently training a different network."""
+    a, w = cfg.algo, cfg.algo.world_model
+    blocks = {"algo": a, "encoder": w.encoder, "observation_model": w.observation_model, "reward_model": w.reward_model,
+              "discount_model": w.discount_model, "transition_model": w.transition_model,
+              "representation_model": w.representation_model, "recurrent_model": w.recurrent_model, "actor": a.actor,
+              "critic": a.critic}
+    for name, blk in blocks.items():
+        for key in ("dense_act", "cnn_act"):
+            v = blk.get(key, None)
+            if v is not None and not str(v).endswith("SiLU"):
+                raise NotImplementedError(f"{name}.{key} = {v}: only torch.nn.SiLU is built")
+        for key in ("layer_norm", "mlp_layer_norm", "cnn_layer_norm"):
+            v = blk.get(key, None)
+            if v is not None and "LayerNorm" not in str(v.get("cls", "LayerNorm")):
+                raise NotImplementedError(f"{name}.{key}.cls = {v.get('cls')}: only the LayerNorm variants are built")
+    for name in ("reward_model", "discount_model"):
+        blk = blocks[name]
+        if int(blk.get("dense_units", a.dense_units)) != int(a.dense_units) or int(blk.get("mlp_layers", a.mlp_layers)) != int(a.mlp_layers):
+            raise NotImplementedError(f"world_model.{name}: dense_units / mlp_layers must equal algo.dense_units / algo.mlp_layers")
+    if int(w.observation_model.get("cnn_channels_multiplier", w.encoder.cnn_channels_multiplier)) != int(w.encoder.cnn_channels_multiplier):
+        raise NotImplementedError("observation_model.cnn_channels_multiplier must equal encoder.cnn_channels_multiplier")
+    for name in ("actor", "critic"):
+        blk = blocks[name]
+        if int(blk.get("dense_units", a.dense_units)) != int(a.dense_units) or int(blk.get("mlp_layers", a.mlp_layers)) != int(a.mlp_layers):
+            raise NotImplementedError(f"algo.{name}: dense_units / mlp_layers must equal algo.dense_units / algo.mlp_layers")
+
+
 class _MLP:
     """n_hidden x [Linear(no bias) -> LN -> SiLU] (+ output Linear with bias): forward with saved
     pre-activations, hand-written backward.  (reference: sheeprl/models/models.py:16-119)"""
@@ -194,6 +224,7 @@ class DV3Engine:
                 "with tanh_normal (entropy fallback shape, dreamer_v3.py:294-297) and normal (negative scale)")
         if w.decoupled_rssm:
             raise NotImplementedError("decoupled_rssm is not implemented in the B200 engine yet")
+        _check_supported_modules(cfg)
         if list(a.cnn_keys.encoder) != list(a.cnn_keys.decoder) or list(a.mlp_keys.encoder) != list(a.mlp_keys.decoder):
             raise NotImplementedError("the decoder must reconstruct exactly the encoder's keys")
         if not a.cnn_keys.encoder and not a.mlp_keys.encoder:
