@@ -37,17 +37,23 @@ def _header(obj, group):
     return box[0]
 
 
-def player_send_batch(sample: Dict[str, torch.Tensor], group=None) -> None:
-    """sample: {key: [(W-1) * rows, ...]} (what `rb.sample_tensors` returned for all trainers, sac_decoupled.py:241-247).
-    Trainer r receives rows [(r-1) * rows, r * rows) of every key, as float32 (the reference sends `v.float()`)."""
+def player_send_batch(sample: Dict[str, torch.Tensor], group=None, chunk_sizes: Optional[Sequence[int]] = None) -> None:
+    """sample: {key: [n, ...]} (what `rb.sample_tensors` returned for all trainers, sac_decoupled.py:241-247).
+    Trainer r receives the r-th block of rows of every key, as float32 (the reference sends `v.float()`): equal blocks
+    by default, `chunk_sizes` (one per trainer) for PPO's near-even split (ppo_decoupled.py:293-299)."""
     world = dist.get_world_size(group)
     n = next(iter(sample.values())).shape[0]
-    if n % (world - 1):
-        raise ValueError(f"{n} sampled rows do not split evenly over {world - 1} trainers")
-    rows = n // (world - 1)
+    if chunk_sizes is None:
+        if n % (world - 1):
+            raise ValueError(f"{n} sampled rows do not split evenly over {world - 1} trainers")
+        chunk_sizes = [n // (world - 1)] * (world - 1)
+    if len(chunk_sizes) != world - 1 or sum(chunk_sizes) != n:
+        raise ValueError(f"chunk_sizes {list(chunk_sizes)} do not cover {n} rows for {world - 1} trainers")
     data = {k: (v if v.dtype == torch.float32 else v.float()).contiguous() for k, v in sample.items()}
-    _header({"rows": rows, "spec": {k: tuple(v.shape[1:]) for k, v in data.items()}}, group)
-    ops = [dist.P2POp(dist.isend, v[(r - 1) * rows: r * rows], r, group) for r in range(1, world) for v in data.values()]
+    _header({"rows": list(chunk_sizes), "spec": {k: tuple(v.shape[1:]) for k, v in data.items()}}, group)
+    starts = [sum(chunk_sizes[:i]) for i in range(world - 1)]
+    ops = [dist.P2POp(dist.isend, v[starts[r - 1]: starts[r - 1] + chunk_sizes[r - 1]], r, group)
+           for r in range(1, world) for v in data.values()]
     for req in dist.batch_isend_irecv(ops):
         req.wait()
 
@@ -61,7 +67,8 @@ def trainer_recv_batch(device, group=None) -> Optional[Dict[str, torch.Tensor]]:
     head = _header(None, group)
     if head["rows"] == STOP:
         return None
-    out = {k: torch.empty((head["rows"], *tail), dtype=torch.float32, device=device) for k, tail in head["spec"].items()}
+    rows = head["rows"][dist.get_rank(group) - 1]
+    out = {k: torch.empty((rows, *tail), dtype=torch.float32, device=device) for k, tail in head["spec"].items()}
     for req in dist.batch_isend_irecv([dist.P2POp(dist.irecv, v, 0, group) for v in out.values()]):
         req.wait()
     return out
@@ -70,6 +77,12 @@ def trainer_recv_batch(device, group=None) -> Optional[Dict[str, torch.Tensor]]:
 def broadcast_actor(engine, pair_group) -> None:
     """rank 1 -> rank 0: the actor's flat parameter group (both ends call it; other trainers must not)"""
     dist.broadcast(engine.actor.flat, src=1, group=pair_group)
+
+
+def broadcast_flat(flat: torch.Tensor, pair_group) -> None:
+    """rank 1 -> rank 0: any flat parameter group — decoupled PPO returns the WHOLE agent (ppo_decoupled.py:302-305,
+    :551-556), which `PPOEngine` keeps as one flat group"""
+    dist.broadcast(flat, src=1, group=pair_group)
 
 
 def minibatches(n_rows: int, batch_size: int) -> Sequence[Tuple[int, int]]:
