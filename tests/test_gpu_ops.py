@@ -563,3 +563,11 @@ def test_continuous_action_kernels(ops):
     m = (torch.softmax(lt, -1) * bins).sum(-1)
     (torch.sign(m) * (torch.exp(m.abs()) - 1) * dm).sum().backward()
     close(lc, lt.grad, rtol=1e-4, atol=1e-6, what="twohot mean bwd vs autograd")
+
+
+def test_twohot_kernel_reproduces_the_reference_known_answers(ops):
+    """tests/test_utils/test_two_hot_encoder.py:6-88 (2.3 -> {0.7 @ 7, 0.3 @ 8}, 21 buckets, saturation, integers,
+    corners) through b200rl_twohot_loss_grad; see tests/test_twohot_kat_cpu.py"""
+    from tests.test_twohot_kat_cpu import check, twohot_targets
+
+    check(twohot_targets(ops[0], device="cuda"))
