@@ -64,3 +64,22 @@ def test_oracle_log_prob_reproduces_the_reference_vectors():
         for i, w in want.items():
             exp[i] = w
         assert torch.allclose(tgt, exp, atol=2e-5), (v, nb, tgt.tolist())
+
+
+def test_decoder_vectors_on_the_mean_op():
+    """tests/test_utils/test_two_hot_decoder.py:6-60: {0.7 @ 7, 0.3 @ 8} -> 2.3, {0.6 @ 8, 0.4 @ 9} -> 3.4, one-hot bins ->
+    their value.  `twohot_mean` returns symexp of the expected bin (TwoHotEncodingDistribution.mean,
+    utils/distribution.py:245-247), so the expectation is symexp(KAT value); probabilities enter as log-probabilities."""
+    from oracle.dv3_oracle import twohot_mean
+    from oracle.ops_emul import EmulOps
+
+    cases = [({7: 0.7, 8: 0.3}, 2.3), ({8: 0.6, 9: 0.4}, 3.4), ({7: 1.0}, 2.0), ({10: 1.0}, 5.0), ({0: 1.0}, -5.0)]
+    logits = torch.full((len(cases), 11), -80.0)
+    for r, (probs, _) in enumerate(cases):
+        for i, p in probs.items():
+            logits[r, i] = math.log(p)
+    want = torch.tensor([symexp(v) for _, v in cases])
+    out = torch.zeros(len(cases))
+    EmulOps().twohot_mean(logits, -5.0, 5.0, out)
+    assert torch.allclose(out, want, rtol=1e-5)
+    assert torch.allclose(twohot_mean(logits, -5.0, 5.0).reshape(-1), want, rtol=1e-5)
