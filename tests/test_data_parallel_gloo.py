@@ -118,3 +118,40 @@ def test_two_rank_gloo_sac_and_ppo_average_gradients():
         pg.append(pe.group.grad.clone())
     want = 0.5 * (pg[0] + pg[1])
     assert float((a["ppo_grad"] - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+def _worker_p2e(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    from sheeprl_b200.parallel import attach_data_parallel, init_process_group_from_env
+    from tests.test_p2e_cpu import load, make_engine
+
+    init_process_group_from_env("gloo")
+    fx, cfg = load()
+    eng = make_engine(fx, cfg)
+    attach_data_parallel(eng)
+    eng.train_step({k: v.clone().float() for k, v in fx["data"][rank].items()}, fx["noise"][rank])   # a different batch per rank
+    res = {n: g.flat.clone() for n, g in eng.groups().items()}
+    res["ens_last"], res["ens_rest"] = eng.ens_last.flat.clone(), eng.ens_rest.flat.clone()
+    res["moments_intrinsic"] = eng.critics_expl["intrinsic"]["moments_state"].clone()
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_plan2explore_replicas_stay_identical():
+    """every optimiser group of the Plan2Explore engine (ensembles, exploration actor / critics, task actor / critic,
+    world model) goes through the same all-reduce hook; the exploration critics' Moments see the gathered lambda-values"""
+    mp.set_start_method("spawn", force=True)
+    out = mp.Manager().dict()
+    mp.spawn(_worker_p2e, args=(2, 30700 + (os.getpid() % 500), out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    for k in a.keys():
+        assert torch.equal(a[k], b[k]), k
+    sys.path.insert(0, ROOT)
+    from tests.test_p2e_cpu import load, make_engine
+
+    fx, cfg = load()
+    solo = make_engine(fx, cfg)
+    solo.train_step({k: v.clone().float() for k, v in fx["data"][0].items()}, fx["noise"][0])
+    assert not torch.equal(solo.actor_expl.flat, a["actor_expl"])        # the other rank's batch did contribute
