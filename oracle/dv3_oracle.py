@@ -373,8 +373,8 @@ def world_model_phase(cfg, wm: Dict[str, Tensor], opt_wm: "AdamState", data: Dic
         vemb, vtargets = mlp_encoder_forward(wm, data, vkeys, w.encoder.mlp_layers, w.encoder.mlp_layer_norm.kw.eps)
         embs.append(vemb)
     emb = torch.cat(embs, -1)
-    h = torch.zeros(B, R)
-    z = torch.zeros(B, Z)
+    h = torch.zeros(B, R, device=emb.device)
+    z = torch.zeros(B, Z, device=emb.device)
     hs, zs, post_l, prior_l = [], [], [], []
     h0_raw = wm["rssm.initial_recurrent_state"]
     if not w.get("learnable_initial_recurrent_state", True):     # a buffer, not a parameter (agent.py:382-389)
@@ -535,7 +535,7 @@ def dv3_train_step(
         hi_q = torch.quantile(lam.detach().flatten(), mo.percentile.high)
         moments_state["low"] = mo.decay * moments_state["low"] + (1 - mo.decay) * lo
         moments_state["high"] = mo.decay * moments_state["high"] + (1 - mo.decay) * hi_q
-        invscale = torch.maximum(torch.tensor(1.0 / mo.max), moments_state["high"] - moments_state["low"])
+        invscale = torch.maximum(torch.tensor(1.0 / mo.max, device=lam.device), moments_state["high"] - moments_state["low"])
         offset = moments_state["low"]
         advantage = (lam - offset) / invscale - (values[:-1] - offset) / invscale
 

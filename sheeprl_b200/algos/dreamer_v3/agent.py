@@ -106,6 +106,18 @@ def build_agent(
     mlp_dims = {k: int(obs_space[k].shape[0]) for k in mlp_keys}          # agent.py:1002
     eng = DV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, ops=ops, is_continuous=is_continuous,
                     mlp_dims=mlp_dims)
+    seed, rank = int(cfg.get("seed", 0) or 0), int(getattr(fabric, "global_rank", 0) or 0)
+    eng.rng_seed = (seed * 1000003 + rank) & 0x7FFFFFFF        # sampling noise follows cfg.seed; ranks draw different streams
+    if int(getattr(fabric, "world_size", 1) or 1) > 1:
+        # the reference wraps every model in DDP here (agent.py:1205-1214, fabric.setup_module) and reduces inside
+        # fabric.backward; the engine's equivalent is one all-reduce per flat gradient + the Moments all-gather
+        import torch.distributed as dist
+
+        from sheeprl_b200.parallel import attach_data_parallel
+
+        if not dist.is_initialized():
+            raise RuntimeError("fabric.world_size > 1 but torch.distributed is not initialised (launch through Fabric / torchrun)")
+        attach_data_parallel(eng)
     g = torch.Generator().manual_seed(int(cfg.get("seed", 0) or 0))
     nh = cfg.algo.mlp_layers
     haf = bool(cfg.algo.hafner_initialization)
@@ -132,4 +144,5 @@ def build_agent(
     for m in (world_model, actor, critic, target_critic):
         object.__setattr__(m, "_b200_engine", eng)
     player = PlayerDV3(eng, cfg.env.num_envs)
+    player.rng_seed = (eng.rng_seed ^ 0x5EED) & 0x7FFFFFFF
     return world_model, actor, critic, target_critic, player

@@ -21,22 +21,29 @@ METRIC_ORDER = (
 )
 
 
-class B200Adam:
+class B200Adam(torch.optim.Optimizer):
     """Handle standing where the reference passes a `torch.optim.Adam` (dreamer_v3.py:448-457).  The update
-    itself is the fused clip+Adam kernel inside the engine; this object only exposes the state in torch's
-    `Optimizer.state_dict()` layout so that reference checkpoints round-trip."""
+    itself is the fused clip+Adam kernel inside the engine; this object is a real `torch.optim.Optimizer` (schedulers
+    such as the reference's `PolynomialLR`, ppo.py:236-238, attach to it and the engine reads `param_groups[0]["lr"]`
+    before every fused step) whose `state_dict()` has torch's layout, so reference checkpoints round-trip."""
 
     def __init__(self, group, names: Sequence[str], lr: float, eps: float, betas=(0.9, 0.999), weight_decay=0.0):
         if weight_decay:
             raise NotImplementedError("weight_decay != 0 is not supported by the fused Adam kernel")
         self.group, self.names = group, list(names)
-        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=0, amsgrad=False)
+        super().__init__([group.views[n] for n in self.names],
+                         dict(lr=float(lr), betas=tuple(betas), eps=float(eps), weight_decay=0, amsgrad=False))
+        group.optimizer = self
+
+    @property
+    def lr(self) -> float:
+        return float(self.param_groups[0]["lr"])
 
     def zero_grad(self, set_to_none: bool = True):  # gradients live in the engine's flat buffer
         return None
 
-    def step(self):
-        raise RuntimeError("B200Adam.step() is fused into DV3Engine.train_step()")
+    def step(self, closure=None):
+        raise RuntimeError("B200Adam.step() is fused into the engine's train step")
 
     def state_dict(self) -> Dict[str, Any]:
         m, v = self.group.optimizer_views()
@@ -45,16 +52,24 @@ class B200Adam:
             for i, n in enumerate(self.names):
                 state[i] = {"step": torch.tensor(float(self.group.step)), "exp_avg": m[n].detach().clone(),
                             "exp_avg_sq": v[n].detach().clone()}
-        return {"state": state, "param_groups": [dict(self.defaults, params=list(range(len(self.names))))]}
+        pg = {k: val for k, val in self.param_groups[0].items() if k != "params"}
+        return {"state": state, "param_groups": [dict(pg, params=list(range(len(self.names))))]}
 
     def load_state_dict(self, sd: Dict[str, Any]):
         m, v = self.group.optimizer_views()
+        n_saved = len(sd["param_groups"][0]["params"]) if sd.get("param_groups") else len(self.names)
+        if n_saved != len(self.names):
+            raise ValueError(f"optimizer state holds {n_saved} parameters, this group has {len(self.names)}: states of "
+                             "a different parameter layout are not interchangeable")
         steps = set()
         with torch.no_grad():
             for i, n in enumerate(self.names):
                 st = sd["state"].get(i)
                 if st is None:
                     continue
+                if tuple(st["exp_avg"].shape) != tuple(m[n].shape):
+                    raise ValueError(f"optimizer state of parameter {i} ({n}) has shape {tuple(st['exp_avg'].shape)}, "
+                                     f"expected {tuple(m[n].shape)}")
                 m[n].copy_(st["exp_avg"])
                 v[n].copy_(st["exp_avg_sq"])
                 steps.add(int(st["step"]))
@@ -62,6 +77,10 @@ class B200Adam:
             raise ValueError("per-parameter Adam steps differ; the fused kernel keeps one step per group")
         self.group.step = steps.pop() if steps else 0
         self.group.step_t.fill_(self.group.step)
+        if sd.get("param_groups"):
+            for k in ("lr", "eps", "betas"):
+                if k in sd["param_groups"][0]:
+                    self.param_groups[0][k] = sd["param_groups"][0][k]
 
 
 def make_optimizers(engine: DV3Engine, cfg):
@@ -103,15 +122,71 @@ def train(
         raise ValueError("is_continuous differs from the value build_agent() was called with")
     if moments is not None and getattr(moments, "low", None) is not None and moments.low.data_ptr() != eng.moments_state.data_ptr():
         moments.bind(eng.moments_state)
-    eng.train_step(data, noise)
+    if noise is None and eng.use_cuda_graph():
+        # the whole update as one CUDA-graph replay (sheeprl_b200/graph.py): the batch is copied into the graph's static
+        # inputs; the reference's in-place `data["is_first"][0] = 1` (dreamer_v3.py:100) still reaches the caller's tensor
+        data["is_first"][0].fill_(1.0)
+        eng.step_graph().run(lambda d: eng.train_step(d, None), data, key=eng.graph_key())
+    else:
+        eng.train_step(data, noise)
     if aggregator and not aggregator.disabled:
         md = eng.metrics_dict()
         for k in METRIC_ORDER:
             aggregator.update(k, md[k])
 
 
+def _optimizer_factory(engines):
+    """`hydra.utils.instantiate(cfg.algo.<model>.optimizer, params=<model>.parameters())` (dreamer_v3.py:448-452) ->
+    the fused-Adam handle of the flat group those parameters are views of"""
+    from sheeprl_b200.utils.delegate import group_of
+
+    def make(config, params):
+        if not engines:
+            return None
+        eng = engines[-1]
+        groups = {"wm": eng.wm, "actor": eng.actor, "critic": eng.critic}
+        groups.update(getattr(eng, "extra_groups", lambda: {})())
+        name = group_of(params, groups)
+        if name is None:
+            return None
+        target = str(config.get("_target_", "torch.optim.Adam"))
+        if not target.endswith("Adam"):
+            raise NotImplementedError(f"optimizer {target}: the fused update kernel implements torch.optim.Adam")
+        g = groups[name]
+        return B200Adam(g, list(g.shapes), float(config["lr"]), float(config.get("eps", 1e-8)),
+                        tuple(config.get("betas", (0.9, 0.999))), float(config.get("weight_decay", 0.0) or 0.0))
+
+    return make
+
+
+def reference_substitutions(cfg, engines):
+    """Module-level names of `sheeprl/algos/dreamer_v3/dreamer_v3.py` that the B200 package replaces while the
+    reference's own `main` runs (dreamer_v3.py:437-447 build_agent, :679-694 train, :459 Moments, :573 prepare_obs,
+    :474-480 the replay buffer classes)."""
+    from sheeprl_b200.algos.dreamer_v3 import agent as A
+    from sheeprl_b200.algos.dreamer_v3 import utils as U
+
+    def build_agent(*a, **k):
+        out = A.build_agent(*a, **k)
+        engines.append(out[0]._b200_engine)
+        return out
+
+    names = {"build_agent": build_agent, "train": train, "Moments": U.Moments, "prepare_obs": U.prepare_obs}
+    if bool(cfg.buffer.get("device_rings", True)):
+        from sheeprl_b200.data import buffers as Bf
+
+        names.update(EnvIndependentReplayBuffer=Bf.EnvIndependentReplayBuffer,
+                     SequentialReplayBuffer=Bf.SequentialReplayBuffer)
+    return names
+
+
 @register_algorithm()
 def main(fabric, cfg: Dict[str, Any]):
-    raise NotImplementedError(
-        "the environment-interaction loop (sheeprl/algos/dreamer_v3/dreamer_v3.py:361-780) is outside this "
-        "round's hot path (SURVEY.md §8); call build_agent()/train() from the reference's main().")
+    """Entry point registered for `algo.name=dreamer_v3` (looked up and launched by sheeprl/cli.py:82-98, 199).  The
+    environment-interaction loop is the reference's own `main` (dreamer_v3.py:361-780), run with this package's
+    `build_agent` / `train` / optimizer handles / Moments / device-resident replay rings substituted."""
+    from sheeprl_b200.utils.delegate import run_reference_main
+
+    engines = []
+    return run_reference_main("sheeprl.algos.dreamer_v3.dreamer_v3", fabric, cfg, reference_substitutions(cfg, engines),
+                              _optimizer_factory(engines))

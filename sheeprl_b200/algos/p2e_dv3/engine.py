@@ -102,6 +102,18 @@ class P2EDV3Engine(DV3Engine):
         self.noise_img_action_expl = b("noise_img_action_expl", H + 1, N, A)
 
     # ------------------------------------------------------------------ state access used by agent.py / tests
+    def extra_groups(self):
+        """flat groups beyond wm / actor / critic (the optimizer handles of the reference's main attach to these)"""
+        d = {"actor_expl": self.actor_expl, "ens_last": self.ens_last}
+        if self.ens_rest is not None:
+            d["ens_rest"] = self.ens_rest
+        for k, c in self.critics_expl.items():
+            d[f"critic_expl_{k}"] = c["group"]
+        return d
+
+    def optimizer_groups(self):
+        return super().optimizer_groups() + list(self.extra_groups().values())
+
     def groups(self) -> "OrderedDict[str, FlatGroup]":
         out = OrderedDict(wm=self.wm, actor_task=self.actor, critic_task=self.critic, target_task=self.target,
                           actor_expl=self.actor_expl)

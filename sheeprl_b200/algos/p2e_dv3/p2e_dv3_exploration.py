@@ -63,6 +63,23 @@ def train(
 
 @register_algorithm()
 def main(fabric, cfg: Dict[str, Any]):
-    raise NotImplementedError(
-        "the environment-interaction loop (sheeprl/algos/p2e_dv3/p2e_dv3_exploration.py:523-1060) is outside the hot "
-        "path (SURVEY.md §8); call build_agent()/train() from the reference's main().")
+    """Entry point for `algo.name=p2e_dv3_exploration`: the reference's own loop (p2e_dv3_exploration.py:523-1060) with this
+    package's `build_agent` / `train` / Adam handles / Moments / replay rings substituted (see dreamer_v3.main)."""
+    from sheeprl_b200.algos.dreamer_v3 import utils as U
+    from sheeprl_b200.algos.dreamer_v3.dreamer_v3 import _optimizer_factory
+    from sheeprl_b200.algos.p2e_dv3 import agent as A
+    from sheeprl_b200.utils.delegate import run_reference_main
+
+    engines = []
+
+    def build_agent(*a, **k):
+        out = A.build_agent(*a, **k)
+        engines.append(out[0]._b200_engine)
+        return out
+
+    names = {"build_agent": build_agent, "train": train, "Moments": U.Moments, "prepare_obs": U.prepare_obs}
+    if bool(cfg.buffer.get("device_rings", True)):
+        from sheeprl_b200.data import buffers as Bf
+
+        names.update(EnvIndependentReplayBuffer=Bf.EnvIndependentReplayBuffer, SequentialReplayBuffer=Bf.SequentialReplayBuffer)
+    return run_reference_main("sheeprl.algos.p2e_dv3.p2e_dv3_exploration", fabric, cfg, names, _optimizer_factory(engines))

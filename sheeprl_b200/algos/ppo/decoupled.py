@@ -45,8 +45,10 @@ def index_batches(n_rows: int, batch_size: int, epochs: int) -> List[List[int]]:
 def trainer_update(engine, data: Dict[str, torch.Tensor], batches: Sequence[Sequence[int]], optim_group, on_minibatch=None) -> int:
     """Runs this trainer's minibatches on `engine` (whose all-reduce hook works on `optim_group`) with DDP-Join semantics
     for uneven counts.  Returns the number of optimisation steps the group took."""
-    mine = torch.tensor([len(batches)], dtype=torch.int64)
-    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(dist.get_world_size(optim_group))]
+    # bookkeeping tensors live on the engine's device: `optim_group` inherits the default backend (NCCL on GPUs), which
+    # has no CPU transport
+    mine = torch.tensor([len(batches)], dtype=torch.int64, device=engine.device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=engine.device) for _ in range(dist.get_world_size(optim_group))]
     dist.all_gather(counts, mine, group=optim_group)
     counts = [int(c) for c in counts]
     longest = max(counts)

@@ -362,7 +362,9 @@ class PPOEngine:
             o.sumsq(g.grad, self.normsq)
         o.increment(g.step_t)
         g.step += 1
-        o.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, self.normsq, float(hp["max_grad_norm"]), self.opt["lr"],
+        handle = getattr(g, "optimizer", None)              # B200Adam: the reference's PolynomialLR edits its param_groups
+        lr = handle.lr if handle is not None else self.opt["lr"]
+        o.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, self.normsq, float(hp["max_grad_norm"]), lr,
                     self.opt["betas"][0], self.opt["betas"][1], self.opt["eps"], g.step_t, self.norm_out)
 
     def train(self, data: Dict[str, torch.Tensor], index_batches: Sequence[Sequence[int]], on_minibatch=None):

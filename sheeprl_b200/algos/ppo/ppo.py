@@ -46,6 +46,10 @@ def train(fabric, agent, optimizer, data: Dict[str, torch.Tensor], aggregator, c
     if eng is None:
         raise TypeError("train() needs the agent returned by sheeprl_b200.algos.ppo.agent.build_agent")
     s = eng.spec
+    # the reference's main anneals cfg.algo.clip_coef / ent_coef between iterations (ppo.py:418-425) and reads them inside
+    # train(): take the current values on every call
+    for k in ("clip_coef", "ent_coef", "vf_coef"):
+        eng.hp[k] = float(cfg.algo[k])
     d = {k: data[k] for k in ("actions", "logprobs", "values", "returns", "advantages")}
     d = {k: (v if v.dtype == torch.float32 else v.float()).contiguous() for k, v in d.items()}
     rgb, state = gather_obs(s, data)                      # per-key tensors -> the encoders' concatenated inputs
@@ -65,8 +69,43 @@ def train(fabric, agent, optimizer, data: Dict[str, torch.Tensor], aggregator, c
     eng.train(d, it, on_minibatch)
 
 
+def _optimizer_factory(agents):
+    from sheeprl_b200.utils.delegate import group_of
+
+    def make(config, params):
+        if not agents:
+            return None
+        e = agents[-1]._b200_engine
+        if group_of(params, {"agent": e.group}) is None:
+            return None
+        target = str(config.get("_target_", "torch.optim.Adam"))
+        if not target.endswith("Adam"):
+            raise NotImplementedError(f"optimizer {target}: the fused update kernel implements torch.optim.Adam")
+        return B200Adam(e.group, list(e.group.shapes), float(config["lr"]), float(config.get("eps", 1e-8)),
+                        tuple(config.get("betas", (0.9, 0.999))), float(config.get("weight_decay", 0.0) or 0.0))
+
+    return make
+
+
+def reference_substitutions(cfg, agents):
+    """names of `sheeprl/algos/ppo/ppo.py` replaced while the reference's `main` runs: build_agent (:174-181), train
+    (:373); `ReplayBuffer` stays the reference's host buffer (the rollout is gathered through `fabric.all_gather`)."""
+    from sheeprl_b200.algos.ppo import agent as A
+
+    def build_agent(*a, **k):
+        out = A.build_agent(*a, **k)
+        agents.append(out[0])
+        return out
+
+    return {"build_agent": build_agent, "train": train}
+
+
 @register_algorithm()
 def main(fabric, cfg: Dict[str, Any]):
-    raise NotImplementedError(
-        "the environment-interaction loop (sheeprl/algos/ppo/ppo.py:105-430) is outside this round's hot path "
-        "(SURVEY.md §8); call build_agent()/train() from the reference's main().")
+    """Entry point registered for `algo.name=ppo` (sheeprl/cli.py:82-98, 199): the reference's own interaction loop
+    (ppo.py:105-430: rollout, GAE, annealing, checkpoints) with this package's `build_agent` / `train` / Adam handle."""
+    from sheeprl_b200.utils.delegate import run_reference_main
+
+    agents = []
+    return run_reference_main("sheeprl.algos.ppo.ppo", fabric, cfg, reference_substitutions(cfg, agents),
+                              _optimizer_factory(agents))

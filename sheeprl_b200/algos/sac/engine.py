@@ -62,6 +62,10 @@ class SACEngine:
         self.abias = ((high + low) / 2.0).to(device).contiguous()
         self.rng_seed = seed
         self.allreduce = None      # data-parallel hook: f(flat_grad, name) -> averaged in place (parallel.py)
+        # Philox position of the rsample noise: created ONCE — `_alloc()` runs again whenever the minibatch size changes
+        # (tail minibatch of a chunk) and must not rewind the stream
+        self.noise_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.metrics = torch.zeros(3, dtype=torch.float32, device=self.device)      # value, policy, alpha loss
         self._alloc()
 
     # ------------------------------------------------------------------ buffers
@@ -75,10 +79,8 @@ class SACEngine:
         self.dq, self.dc2, self.dc1, self.dact = f(n, B, 1), f(n, B, Hc), f(n, B, Hc), f(n, B, A)
         self.dhead, self.da2, self.da1 = f(1, B, 2 * A), f(1, B, Ha), f(1, B, Ha)
         self.eps_next, self.eps_cur = f(B, A), f(B, A)
-        self.metrics = f(3)                                                 # value, policy, alpha loss
         self.norm_out = f(1)
         self.zero_normsq = torch.zeros(1, dtype=torch.float64, device=self.device)
-        self.noise_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         # batched views of the critics' parameters: [n, out, in] with the constant inter-critic stride
         self._qv = self._critic_views(self.qf.flat)
         self._qg = self._critic_views(self.qf.grad)
@@ -122,7 +124,9 @@ class SACEngine:
             self.allreduce(group.grad, name)
         self.ops.increment(group.step_t)
         group.step += 1
-        self.ops.adam_step(group.flat, group.grad, group.exp_avg, group.exp_avg_sq, self.zero_normsq, 0.0, opt["lr"],
+        handle = getattr(group, "optimizer", None)          # B200Adam built by main / make_optimizers (schedulers edit it)
+        lr = handle.lr if handle is not None else opt["lr"]
+        self.ops.adam_step(group.flat, group.grad, group.exp_avg, group.exp_avg_sq, self.zero_normsq, 0.0, lr,
                            opt["betas"][0], opt["betas"][1], opt["eps"], group.step_t, self.norm_out)
 
     # ------------------------------------------------------------------ the update

@@ -40,8 +40,46 @@ def train(fabric, agent, actor_optimizer, qf_optimizer, alpha_optimizer, data: D
             aggregator.update(k, md[k])
 
 
+def _optimizer_factory(agents):
+    from sheeprl_b200.utils.delegate import group_of
+
+    def make(config, params):
+        if not agents:
+            return None
+        e = agents[-1]._b200_engine
+        groups = {"actor": e.actor, "qf": e.qf, "alpha": e.alpha}
+        name = group_of(params, groups)
+        if name is None:
+            return None
+        target = str(config.get("_target_", "torch.optim.Adam"))
+        if not target.endswith("Adam"):
+            raise NotImplementedError(f"optimizer {target}: the fused update kernel implements torch.optim.Adam")
+        g = groups[name]
+        return B200Adam(g, list(g.shapes), float(config["lr"]), float(config.get("eps", 1e-8)),
+                        tuple(config.get("betas", (0.9, 0.999))), float(config.get("weight_decay", 0.0) or 0.0))
+
+    return make
+
+
+def reference_substitutions(cfg, agents):
+    """names of `sheeprl/algos/sac/sac.py` replaced while the reference's `main` runs: build_agent (:146-150), train
+    (:343-356)"""
+    from sheeprl_b200.algos.sac import agent as A
+
+    def build_agent(*a, **k):
+        out = A.build_agent(*a, **k)
+        agents.append(out[0])
+        return out
+
+    return {"build_agent": build_agent, "train": train}
+
+
 @register_algorithm()
 def main(fabric, cfg: Dict[str, Any]):
-    raise NotImplementedError(
-        "the environment-interaction loop (sheeprl/algos/sac/sac.py:81-330) is outside this round's hot path "
-        "(SURVEY.md §8); call build_agent()/train() from the reference's main().")
+    """Entry point registered for `algo.name=sac` (sheeprl/cli.py:82-98, 199): the reference's own interaction loop
+    (sac.py:81-330) with this package's `build_agent` / `train` / Adam handles."""
+    from sheeprl_b200.utils.delegate import run_reference_main
+
+    agents = []
+    return run_reference_main("sheeprl.algos.sac.sac", fabric, cfg, reference_substitutions(cfg, agents),
+                              _optimizer_factory(agents))

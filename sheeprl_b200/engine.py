@@ -5,8 +5,8 @@
 the C-ABI CUDA library (`include/b200rl.h`, loaded by `sheeprl_b200.lib.CudaOps`): forward, the
 hand-derived backward (SURVEY.md Appendix E is the gradient-flow map it follows), global-norm clip,
 Adam.  PyTorch is used only to own device memory and the CUDA stream.  Because nothing on this path
-allocates, synchronises or branches on device data, the whole step is CUDA-graph capturable
-(`sheeprl_b200.graph`).
+allocates, synchronises or branches on device data, the whole step is CUDA-graph capturable:
+`sheeprl_b200.graph.StepGraph` captures it on the third call of the public `train()` and replays it afterwards.
 
 Layouts (all fp32, row-major):
   * replay rows are flattened time-major: row n = t*B + b  (matches `posteriors.reshape(1,-1,Z)` in
@@ -426,13 +426,50 @@ class DV3Engine:
         self.noise_post = b("noise_post", T, B, Z)
         self.noise_img_state = b("noise_img_state", H, N, Z)
         self.noise_img_action = b("noise_img_action", H + 1, N, A)
-        self.rng_seed = 0
+        self.rng_seed = int(self.cfg.get("seed", 0) or 0)      # build_agent folds the rank in (agent.py)
         self.rng_t = torch.zeros(1, dtype=torch.int32, device=self.device)   # device-side step counter for Philox
+        self.cuda_graph = bool(self.cfg.algo.get("cuda_graph", True))  # B200 knob: replay the update as one CUDA graph
+        self._graph = None
         # persistent fused RSSM scan (csrc/rssm_scan.cu) when the ops backend provides it and the shape qualifies
         self.fused_scan = bool(hasattr(self.ops, "rssm_scan_fwd") and self.B <= 16 and self.D <= 32 and self.S <= 64)
         self._scan_ws = None
         self.fused_scan_bwd = hasattr(self.ops, "rssm_scan_bwd")
         self._fused_fwd_done = False
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the step
+    def optimizer_groups(self):
+        return [self.wm, self.actor, self.critic]
+
+    def use_cuda_graph(self) -> bool:
+        return self.cuda_graph and self.device.type == "cuda" and type(self.ops).__name__ == "CudaOps"
+
+    def graph_key(self) -> tuple:
+        """what a captured step bakes in besides the batch shapes: the learning rates (kernel arguments by value)"""
+        return tuple(float(g.optimizer.lr) if getattr(g, "optimizer", None) is not None else -1.0
+                     for g in self.optimizer_groups())
+
+    def step_graph(self):
+        if self._graph is None:
+            from sheeprl_b200.graph import StepGraph
+
+            groups = self.optimizer_groups()
+
+            def bump():
+                for g in groups:
+                    g.step += 1
+
+            self._graph = StepGraph(self.device, warmup=2, on_replay=bump,
+                                    host_state=(lambda: [g.step for g in groups],
+                                                lambda s: [setattr(g, "step", v) for g, v in zip(groups, s)]))
+        return self._graph
+
+    def rng_state(self) -> Dict[str, torch.Tensor]:
+        """Philox position of the sampling noise (saved with the optimizer state so a resumed run continues the stream)"""
+        return {"rng_t": self.rng_t.detach().clone().cpu(), "rng_seed": torch.tensor(self.rng_seed)}
+
+    def load_rng_state(self, st) -> None:
+        self.rng_t.copy_(st["rng_t"].to(self.rng_t.device))
+        self.rng_seed = int(st["rng_seed"])
 
     def bytes_allocated(self) -> int:
         tot = sum(t.numel() * t.element_size() for t in self._bufs.values())
@@ -906,7 +943,9 @@ class DV3Engine:
         g.step += 1
         ops.increment(g.step_t)
         b1, b2 = ocfg.betas
-        ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, self.normsq[name], max_norm, float(ocfg.lr),
+        opt = getattr(g, "optimizer", None)                  # the handle build by main / make_optimizers (schedulers edit it)
+        lr = opt.lr if opt is not None else float(ocfg.lr)
+        ops.adam_step(g.flat, g.grad, g.exp_avg, g.exp_avg_sq, self.normsq[name], max_norm, lr,
                       float(b1), float(b2), float(ocfg.eps), g.step_t, self.norms[slot: slot + 1])
 
     # ------------------------------------------------------------------ behaviour learning
