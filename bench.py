@@ -25,9 +25,31 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "Dreamer-V3 train-steps/sec (S, bs16 seq64 horizon15, 64x64x3 obs)"
 UNIT = "train-steps/s"
-WORKLOAD = "dreamer_v3_S bs16 seq64 h15 64x64x3 discreteA2 (BASELINE.json configs[1])"
+
+
+def metric_name(args):
+    return f"Dreamer-V3 train-steps/sec ({args.size}, bs{args.batch} seq{args.seq} horizon{args.horizon}, 64x64x3 obs)"
+
+
+def workload_name(args):
+    which = {"S": "BASELINE.json configs[1]", "XL": "BASELINE.json configs[4]"}.get(args.size, "")
+    return f"dreamer_v3_{args.size} bs{args.batch} seq{args.seq} h{args.horizon} 64x64x3 discreteA2 ({which})"
+
+
+def workload_config(args):
+    """identical in both arms (`--impl b200` / `--impl reference`)"""
+    return {"workload": workload_name(args), "size": args.size, "per_rank_batch": args.batch, "seq_len": args.seq,
+            "horizon": args.horizon,
+            "l2": "per-step working set (activations + optimiser state, GBs) >> 126 MB L2: no flush needed between steps"}
+
+
+def make_cfg(args, **over):
+    from sheeprl_b200.configs import make_dv3_cfg
+
+    kw = dict(per_rank_batch_size=args.batch, per_rank_sequence_length=args.seq, horizon=args.horizon)
+    kw.update(over)
+    return make_dv3_cfg(args.size, **kw)
 
 
 def measured_peaks():
@@ -179,15 +201,15 @@ def run_b200(args):
     from sheeprl_b200.algos.dreamer_v3.agent import build_agent
     from sheeprl_b200.algos.dreamer_v3.dreamer_v3 import make_optimizers, train
     from sheeprl_b200.algos.dreamer_v3.utils import Moments
-    from sheeprl_b200.configs import make_dv3_cfg
-    from sheeprl_b200.parallel import attach_data_parallel, init_process_group_from_env
+    from sheeprl_b200.parallel import init_process_group_from_env
 
     rank, local, world = init_process_group_from_env("nccl")
     assert world == args.gpus, f"WORLD_SIZE={world} but --gpus {args.gpus}"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    cfg = make_dv3_cfg("S")
+    cfg = make_cfg(args)
     cfg.seed = 5
+    cfg.algo.cuda_graph = not args.no_graph
     adim = (2,)
 
     class Fab:  # the three attributes train()/build_agent() read from Fabric
@@ -196,10 +218,10 @@ def run_b200(args):
     class Space:
         shape = (3, 64, 64)
 
+    # the PUBLIC surface only: build_agent installs the data-parallel hooks when world_size > 1, train() captures the
+    # update into a CUDA graph on its third call and replays it afterwards (sheeprl_b200/graph.py)
     wm, actor, critic, target, _ = build_agent(Fab, adim, False, cfg, {"rgb": Space})
     eng = wm._b200_engine
-    attach_data_parallel(eng)
-    eng.rng_seed = 1234 + rank
     opts = make_optimizers(eng, cfg)
     mo = cfg.algo.actor.moments
     moments = Moments(mo.decay, mo.max, mo.percentile.low, mo.percentile.high)
@@ -227,70 +249,48 @@ def run_b200(args):
         eng.update_target(cfg.algo.critic.tau)                  # main() does this before each train() (:674-680)
         train(Fab, wm, actor, critic, target, *opts, data, agg, cfg, False, adim, moments)
 
-    # ---- warm-up (eager): loads modules, first-touch, W >= 3
+    # ---- warm-up: W >= 3 public calls (the first two run eagerly, the third captures the graph)
     launches0 = eng.ops.launches
     step_public(static)
     launches_per_step = eng.ops.launches - launches0
     for _ in range(max(args.warmup, 3) - 1):
         step_public(static)
     barrier()
+    graphed = eng.use_cuda_graph() and eng.step_graph().captured(static, eng.graph_key())
 
     # ---- per-op breakdown of ONE eager step (roofline evidence).  Every rank runs it: the step contains the
     # data-parallel collectives, so a rank-0-only step would leave the other ranks' NCCL queues one step short.
-    prof = ProfilingOps(eng.ops)
-    eng.ops = prof
-    for m in (eng.reward_wm, eng.cont_wm, eng.actor_mlp, eng.critic_mlp, eng.target_mlp, eng.rew_img, eng.cont_img):
-        m.eng = eng
-    step_public(static)
-    breakdown = prof.summary()
-    eng.ops = prof._inner
-    barrier()
+    breakdown = {}
+    if args.breakdown:
+        prof = ProfilingOps(eng.ops)
+        eng.ops = prof                                          # not a CudaOps instance -> train() runs eagerly
+        for m in (eng.reward_wm, eng.cont_wm, eng.actor_mlp, eng.critic_mlp, eng.target_mlp, eng.rew_img, eng.cont_img):
+            m.eng = eng
+        step_public(static)
+        breakdown = prof.summary()
+        eng.ops = prof._inner
+        barrier()
 
-    # ---- CUDA graph of the whole update; at N > 1 the NCCL all-reduces / all-gather are captured with it
-    # (B200RL_BENCH_EAGER_NCCL=1 keeps eager launches around NCCL)
-    graph = None
-    if not args.no_graph and (world == 1 or os.environ.get("B200RL_BENCH_EAGER_NCCL", "0") != "1"):
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            step_public(static)
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step_public(static)
-        for _ in range(2):
-            graph.replay()
-    barrier()
-
-    # ---- timed region 1: `value` (inputs resident in HBM)
+    # ---- timed region 1: `value` (inputs resident in HBM; train() copies them into the graph's static inputs)
     clocks = ClockSampler(local)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        if graph is not None:
-            graph.replay()
-        else:
-            step_public(static)
+        step_public(static)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    # ---- timed region 2: `e2e` through the public train() with pinned-host inputs + metric read-back
+    # ---- timed region 2: `e2e`: the same public call with the batch in pinned HOST memory (H2D inside train()) and
+    # a device->host read of the step's 13 metrics
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
     out_host = torch.empty(13, dtype=torch.float32).pin_memory()
+    step_public(host)                                           # same signature as `static`: reuses the captured graph
     barrier()
     e2.record()
     for _ in range(args.steps):
-        tgt = static if graph is not None else dev_in
-        for k, v in host.items():
-            tgt[k].copy_(v, non_blocking=True)                  # H2D of this step's replay batch (pinned source)
-        if graph is not None:
-            graph.replay()
-        else:
-            step_public(dev_in)
+        step_public(host)
         out_host[:10].copy_(eng.metrics[:10], non_blocking=True)
         out_host[10:].copy_(eng.norms, non_blocking=True)
         torch.cuda.current_stream().synchronize()               # D2H read of the step's losses
@@ -310,10 +310,10 @@ def run_b200(args):
     e2e_v = world * args.steps / (ms_e2e / 1e3)
     hbm, tf, src = measured_peaks()
     # Dominant kernel: gemm_tc_kernel (tcgen05 3xTF32; serves every large Linear / conv forward, input-gradient
-    # and weight-gradient product).  `achieved` = algorithmic FLOPs of its largest launch in the step (a 2-layer-MLP
-    # GEMM over the imagined trajectories: M=(H+1)*T*B, N=512, K=1536) / its mean launch duration, measured here
-    # with CUDA events on the launching stream; operands (134 MB) exceed the 126 MB L2.
-    tot_ms = sum(v[0] for v in breakdown.values())
+    # and weight-gradient product).  `achieved` = algorithmic FLOPs of its largest launch in the step (an MLP
+    # GEMM over the imagined trajectories: M=(H+1)*T*B, N=dense_units, K=latent) / its mean launch duration, measured
+    # here with CUDA events on the launching stream; operands exceed the 126 MB L2.
+    tot_ms = sum(v[0] for v in breakdown.values()) or 1.0
     tc_ops = ("gemm", "conv_down", "conv_up", "conv_wgrad")
     share = sum(breakdown[k][0] for k in tc_ops if k in breakdown) / tot_ms
     gm, gn, gk = (eng.H + 1) * eng.N, eng.du, eng.L
@@ -331,31 +331,39 @@ def run_b200(args):
     torch.cuda.synchronize()
     g_ms = g0.elapsed_time(g1) / 20
     g_tf = 2.0 * gm * gn * gk / (g_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_gemm_tc_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    traffic, tsrc = None, None
+    for name in ("r2_gemm_tc_traffic.json", "r1_gemm_tc_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath) and args.size == "S":
+            traffic, tsrc = json.load(open(tpath)).get("dram_bytes_per_launch"), name
+            break
+    flops_step = {"S": 0.904e12, "XL": 37.6e12}.get(args.size) if (args.batch, args.seq, args.horizon) in ((16, 64, 15), (64, 64, 15)) else None
     roof = {"kernel": "gemm_tc_kernel<128> (tcgen05.mma kind::tf32, 3xTF32 split, TMA, TMEM)", "bound": "tensor",
             "achieved": g_tf, "peak": tf, "unit": "TFLOP/s", "frac": g_tf / tf, "traffic": traffic,
-            "peak_source": f"{src} bf16 cuBLAS",
+            "traffic_source": tsrc, "peak_source": f"{src} bf16 cuBLAS",
             "shape": {"M": gm, "N": gn, "K": gk}, "us_per_launch": g_ms * 1e3,
+            "step_tflops": (flops_step * world / (ms / args.steps * 1e-3) / 1e12 / world) if flops_step else None,
+            "step_frac_of_peak": (flops_step / (ms / args.steps * 1e-3) / 1e12 / tf) if flops_step else None,
             "note": "fp32-equivalent FLOP/s: every product costs 3 TF32 MMAs and TF32 runs at half the bf16 rate, so the "
                     f"scheme's ceiling is peak/6 = {tf / 6:.0f} TFLOP/s (frac of that: {g_tf / (tf / 6):.2f}); tensor-core "
-                    f"ops (gemm+conv) take {share:.2f} of the step; ncu --set full of this launch: profiles/r1_gemm_tc_traffic.json (r1d_gemm_tc.ncu-rep)"}
-    cpu = cpu_baseline(steps=1, warmup=1) if (args.cpu_baseline and world == 1) else None
+                    f"ops (gemm+conv) take {share:.2f} of the eager step; step_tflops = SURVEY 8(d) algorithmic FLOPs per "
+                    "train() call / measured step time"}
+    cpu = cpu_baseline(args, steps=3, warmup=1) if (args.cpu_baseline and world == 1) else None
+    eager = gpu_eager_baseline(args, dev) if (args.gpu_eager and world == 1) else None
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_rank_batch": 16, "seq_len": 64, "horizon": 15,
-                   "parallelism": f"dp{world}", "cuda_graph": graph is not None,
-                   "l2": "per-step working set (~1.6 GB of activations + 0.5 GB optimiser state) >> 126 MB L2"},
+        "config": workload_config(args),
+        "arm": {"parallelism": f"dp{world}", "cuda_graph": bool(graphed), "api": "sheeprl_b200.algos.dreamer_v3: build_agent() + train()"},
         "clocks": clk,
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 13 * 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": eager,
         "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][0])[:12]},
     }
     sys.stdout.flush()
@@ -364,72 +372,174 @@ def run_b200(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port, oracle/dv3_oracle.py) on the host cores
+# Baseline arms: the reference algorithm on the host cores / in torch eager on the same GPU.
+# `kind: "reference"` = the UNMODIFIED reference train() (package installed into baseline/_ref by __graft_entry__.build(),
+# imported through the stub harness oracle/ref_harness.py); `kind: "port"` = oracle/dv3_oracle.py when no reference tree is
+# reachable.  Only these arms execute anything under oracle/.
 # ---------------------------------------------------------------------------------------------------------
-def _oracle_runner(cfg, adim):
+def reference_root():
+    for p in (os.environ.get("SHEEPRL_REFERENCE_ROOT"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if p and os.path.isdir(os.path.join(p, "sheeprl")):
+            return p
+    return None
+
+
+def _oracle_runner(cfg, adim, device="cpu"):
     import torch
 
     from oracle import dv3_oracle as O          # checker / baseline only — never on the product path
 
-    wm, actor, critic, target = O.init_params(cfg, adim, seed=0)
+    dev = torch.device(device)
+    wm, actor, critic, target = ({k: v.to(dev) for k, v in d.items()} for d in O.init_params(cfg, adim, seed=0))
     a, w = cfg.algo, cfg.algo.world_model
     opts = [O.AdamState(wm, w.optimizer.lr, w.optimizer.eps), O.AdamState(actor, a.actor.optimizer.lr, a.actor.optimizer.eps),
             O.AdamState(critic, a.critic.optimizer.lr, a.critic.optimizer.eps)]
-    ms = {"low": torch.zeros(()), "high": torch.zeros(())}
-    data = O.make_batch(cfg, adim, seed=1)
+    ms = {"low": torch.zeros((), device=dev), "high": torch.zeros((), device=dev)}
+    data = {k: v.to(dev) for k, v in O.make_batch(cfg, adim, seed=1).items()}
     state = {"s": 0}
 
     def step():
         noise = O.draw_noise(a.per_rank_sequence_length, a.per_rank_batch_size, a.horizon, w.stochastic_size,
                              w.discrete_size, adim, seed=10 + state["s"])
+        noise = {k: (v.to(dev) if torch.is_tensor(v) else [x.to(dev) for x in v]) for k, v in noise.items()}
         state["s"] += 1
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         O.dv3_train_step(cfg, wm, actor, critic, target, *opts, data, noise, ms, adim)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         return time.perf_counter() - t0
 
     return step
 
 
-def cpu_baseline(steps: int, warmup: int):
-    """Reference algorithm (oracle port) on the host cores.  torch's intra-op pool is sized by a short probe
-    on a 1/4-length workload (more threads than ~32 make the thousands of tiny RSSM ops slower, not faster;
-    the reference itself defaults to num_threads=1, sheeprl/configs/config.yaml)."""
+def _reference_runner(cfg, adim, device="cpu"):
+    """the executed reference: its own build_agent() + train() (dreamer_v3.py:48-357) with torch.optim.Adam"""
     import torch
 
-    from sheeprl_b200.configs import make_dv3_cfg
+    os.environ["SHEEPRL_REFERENCE_ROOT"] = reference_root()
+    from oracle import ref_harness, ref_run     # baseline arm only
+
+    ref_harness.install()
+    from sheeprl.algos.dreamer_v3 import dreamer_v3 as D
+    from sheeprl.algos.dreamer_v3.agent import build_agent
+    from sheeprl.algos.dreamer_v3.utils import Moments
+
+    dev = torch.device(device)
+    fab = ref_harness.FakeFabric(dev)
+    rcfg = ref_run.to_ref_cfg(cfg)
+    torch.manual_seed(0)
+    sz = cfg.env.screen_size
+    wm, actor, critic, target, _ = build_agent(fab, tuple(adim), False, rcfg, {"rgb": ref_harness.Shape((3, sz, sz))})
+    a = cfg.algo
+
+    def adam(params, o):
+        return torch.optim.Adam(params, lr=o.lr, eps=o.eps, weight_decay=o.weight_decay, betas=tuple(o.betas))
+
+    wo, ao, co = adam(wm.parameters(), a.world_model.optimizer), adam(actor.parameters(), a.actor.optimizer), adam(critic.parameters(), a.critic.optimizer)
+    mo = a.actor.moments
+    moments = Moments(mo.decay, mo.max, mo.percentile.low, mo.percentile.high).to(dev)
+    data = {k: v.to(dev).float() for k, v in synthetic_batch(cfg, adim, seed=1).items()}
+
+    class Agg:                                   # keeps tensors, never synchronises (like torchmetrics' MeanMetric.update)
+        disabled = False
+
+        def update(self, k, v):
+            self.last = v
+
+    agg = Agg()
+
+    def step():
+        batch = {k: v.clone() for k, v in data.items()}
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        D.train(fab, wm, actor, critic, target, wo, ao, co, batch, agg, rcfg, False, tuple(adim), moments)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    return step
+
+
+def _runner(cfg, adim, device):
+    if reference_root() is not None:
+        try:
+            return _reference_runner(cfg, adim, device), "reference"
+        except Exception as e:  # harness could not import the reference on this host: fall back to the port, say so
+            print(f"[bench] executed reference unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+    return _oracle_runner(cfg, adim, device), "port"
+
+
+def cpu_baseline(args, steps: int, warmup: int):
+    """Reference train() on the host cores.  torch's intra-op pool is sized by a short probe on a 1/4-length workload
+    (more threads than ~32 make the thousands of tiny RSSM ops slower, not faster; the reference itself defaults to
+    num_threads=1, sheeprl/configs/config.yaml)."""
+    import torch
 
     cores = os.cpu_count() or 1
     adim = (2,)
     best_k, best_t = None, None
-    for k in [c for c in (8, 16, 32) if c <= cores] or [cores]:
-        torch.set_num_threads(k)
-        probe = _oracle_runner(make_dv3_cfg("S", per_rank_sequence_length=16), adim)
-        probe()
-        t = probe()
-        if best_t is None or t < best_t:
-            best_k, best_t = k, t
+    if args.size == "S":
+        for k in [c for c in (8, 16, 32) if c <= cores] or [cores]:
+            torch.set_num_threads(k)
+            probe, _ = _runner(make_cfg(args, per_rank_sequence_length=max(8, args.seq // 4)), adim, "cpu")
+            probe()
+            t = probe()
+            if best_t is None or t < best_t:
+                best_k, best_t = k, t
+    else:
+        best_k = min(cores, 32)
     torch.set_num_threads(best_k)
-    run = _oracle_runner(make_dv3_cfg("S"), adim)
+    run, kind = _runner(make_cfg(args), adim, "cpu")
     times = [run() for _ in range(warmup + steps)]
     tt = times[warmup:]
-    return {"value": len(tt) / sum(tt), "unit": UNIT, "cores": best_k, "kind": "port",
+    return {"value": len(tt) / sum(tt), "unit": UNIT, "cores": best_k, "kind": kind,
             "sample": f"{len(tt)} full train() step(s) of the same workload after {warmup} warm-up, torch fp32 CPU, "
-                      f"{best_k} of {cores} host threads (best of 8/16/32 on a seq16 probe); s/step={sum(tt) / len(tt):.2f}"}
+                      f"{best_k} of {cores} host threads; s/step={sum(tt) / len(tt):.2f}; "
+                      + ("the UNMODIFIED reference (baseline/_ref) through the stub-import harness" if kind == "reference"
+                         else "oracle port of the reference (no reference tree on this host)")}
+
+
+def gpu_eager_baseline(args, dev):
+    """The same-box bar: the reference train() in torch eager on THIS GPU, with
+    float32_matmul_precision "high" (the reference's default, configs/config.yaml:18: TF32 products) and "highest"."""
+    import torch
+
+    adim = (2,)
+    out = {"unit": UNIT}
+    steps, warm = (10, 3) if args.size == "S" else (3, 2)
+    for prec in ("high", "highest"):
+        torch.set_float32_matmul_precision(prec)
+        torch.backends.cudnn.allow_tf32 = prec != "highest"
+        try:
+            run, kind = _runner(make_cfg(args), adim, str(dev))
+            times = [run() for _ in range(warm + steps)]
+            tt = times[warm:]
+            out[prec] = {"value": len(tt) / sum(tt), "ms_per_step": 1e3 * sum(tt) / len(tt), "steps": len(tt), "kind": kind}
+        except Exception as e:
+            out[prec] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        finally:
+            torch.set_float32_matmul_precision("highest")
+            torch.backends.cudnn.allow_tf32 = True
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 30))
-    warm = max(1, min(args.warmup, 3))
-    cb = cpu_baseline(steps=steps, warmup=warm)
+    steps = max(1, min(args.steps, 30 if args.size == "S" else 2))
+    warm = max(args.warmup, 3) if args.size == "S" else 1
+    cb = cpu_baseline(args, steps=steps, warmup=warm)
     out = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(args), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_rank_batch": 16, "seq_len": 64, "horizon": 15,
-                   "parallelism": "host cpu threads"},
+        "config": workload_config(args),
+        "arm": {"parallelism": "host cpu threads", "cuda_graph": False, "api": "sheeprl.algos.dreamer_v3: build_agent() + train()"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -442,10 +552,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--graph-nccl", action="store_true", help="(default now) capture the step incl. the NCCL collectives in a CUDA graph at N > 1")
+    ap.add_argument("--no-graph", action="store_true", help="keep train() eager (cfg.algo.cuda_graph=False)")
+    ap.add_argument("--size", default="S", choices=["S", "XL"], help="S = BASELINE configs[1]; XL = configs[4]")
+    ap.add_argument("--batch", type=int, default=None, help="per-rank batch (default 16 for S, 64 for XL)")
+    ap.add_argument("--seq", type=int, default=64)
+    ap.add_argument("--horizon", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-gpu-eager", dest="gpu_eager", action="store_false")
+    ap.add_argument("--no-breakdown", dest="breakdown", action="store_false")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 16 if args.size == "S" else 64
+    if args.size != "S" and "--cpu-baseline" not in sys.argv:
+        args.cpu_baseline = False          # minutes per step on the host at XL: only the explicit reference arm times it
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -154,7 +154,7 @@ class FakeFabric:
         self.is_global_zero = True
 
     def setup_module(self, m):
-        return _Wrap(m)
+        return _Wrap(m.to(self.device))        # Fabric.setup_module moves the module to its device
 
     def setup_optimizers(self, *o):
         return o if len(o) > 1 else o[0]

@@ -18,6 +18,10 @@ from sheeprl_b200.algos.dreamer_v3.player import PlayerDV3
 from sheeprl_b200.engine import DV3Engine
 from sheeprl_b200.params import FlatGroup
 
+# kernel binding used when build_agent() is called without `ops` (the reference's main never passes one): None -> the CUDA
+# library.  Tests on a GPU-less host point this at the torch test double.
+DEFAULT_OPS = None
+
 
 class ParamTree(nn.Module):
     """Nested modules mirroring dotted state-dict names; leaves are nn.Parameters aliasing `views`."""
@@ -104,8 +108,8 @@ def build_agent(
     cnn_keys, mlp_keys = list(cfg.algo.cnn_keys.encoder or []), list(cfg.algo.mlp_keys.encoder or [])
     in_channels = sum(int(math.prod(obs_space[k].shape[:-2])) for k in cnn_keys) if cnn_keys else 3    # agent.py:984
     mlp_dims = {k: int(obs_space[k].shape[0]) for k in mlp_keys}          # agent.py:1002
-    eng = DV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, ops=ops, is_continuous=is_continuous,
-                    mlp_dims=mlp_dims)
+    eng = DV3Engine(cfg, actions_dim, in_channels=in_channels, device=fabric.device, ops=ops if ops is not None else DEFAULT_OPS,
+                    is_continuous=is_continuous, mlp_dims=mlp_dims)
     seed, rank = int(cfg.get("seed", 0) or 0), int(getattr(fabric, "global_rank", 0) or 0)
     eng.rng_seed = (seed * 1000003 + rank) & 0x7FFFFFFF        # sampling noise follows cfg.seed; ranks draw different streams
     if int(getattr(fabric, "world_size", 1) or 1) > 1:

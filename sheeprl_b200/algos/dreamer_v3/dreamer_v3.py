@@ -180,6 +180,13 @@ def reference_substitutions(cfg, engines):
     return names
 
 
+def _bind_buffer_device(fabric):
+    """the reference's main builds its buffers without a device argument: the rings default to this rank's GPU"""
+    from sheeprl_b200.data import buffers as Bf
+
+    Bf.DEFAULTS["device"] = fabric.device
+
+
 @register_algorithm()
 def main(fabric, cfg: Dict[str, Any]):
     """Entry point registered for `algo.name=dreamer_v3` (looked up and launched by sheeprl/cli.py:82-98, 199).  The
@@ -188,5 +195,6 @@ def main(fabric, cfg: Dict[str, Any]):
     from sheeprl_b200.utils.delegate import run_reference_main
 
     engines = []
+    _bind_buffer_device(fabric)
     return run_reference_main("sheeprl.algos.dreamer_v3.dreamer_v3", fabric, cfg, reference_substitutions(cfg, engines),
                               _optimizer_factory(engines))

@@ -81,5 +81,6 @@ def main(fabric, cfg: Dict[str, Any]):
     if bool(cfg.buffer.get("device_rings", True)):
         from sheeprl_b200.data import buffers as Bf
 
+        Bf.DEFAULTS["device"] = fabric.device
         names.update(EnvIndependentReplayBuffer=Bf.EnvIndependentReplayBuffer, SequentialReplayBuffer=Bf.SequentialReplayBuffer)
     return run_reference_main("sheeprl.algos.p2e_dv3.p2e_dv3_exploration", fabric, cfg, names, _optimizer_factory(engines))

@@ -51,6 +51,7 @@ def main(fabric, cfg: Dict[str, Any], exploration_cfg: Dict[str, Any] | None = N
     if bool(cfg.buffer.get("device_rings", True)):
         from sheeprl_b200.data import buffers as Bf
 
+        Bf.DEFAULTS["device"] = fabric.device
         names.update(EnvIndependentReplayBuffer=Bf.EnvIndependentReplayBuffer, SequentialReplayBuffer=Bf.SequentialReplayBuffer)
     ref = "sheeprl.algos.p2e_dv3.p2e_dv3_finetuning"
     from sheeprl_b200.utils.delegate import _InstantiateProxy, import_reference, substituted

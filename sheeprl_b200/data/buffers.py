@@ -48,10 +48,18 @@ def _clone_rng(rng: np.random.Generator) -> np.random.Generator:
     return out
 
 
+# Process-wide defaults for buffers built WITHOUT a `device` / `ops` argument — which is how the reference's own `main`
+# constructs them (dreamer_v3.py:474-480: it has no such notion).  The B200 entry points set the device to `fabric.device`
+# before delegating; tests on a GPU-less host set `ops` to the torch test double.
+DEFAULTS = {"device": "cuda", "ops": None}
+
+
 def _default_ops():
+    if DEFAULTS["ops"] is not None:
+        return DEFAULTS["ops"]
     from sheeprl_b200.lib import CudaOps  # raises B200RLError when the extension / a B200 is missing
 
-    return CudaOps()
+    return CudaOps(DEFAULTS["device"]) if DEFAULTS["device"] != "cuda" else CudaOps()
 
 
 def get_tensor(array, dtype: Optional[torch.dtype] = None, clone: bool = False, device="cpu", from_numpy: bool = False):
@@ -97,7 +105,8 @@ class ReplayBuffer:
     batch_axis: int = 1
 
     def __init__(self, buffer_size: int, n_envs: int = 1, obs_keys: Sequence[str] = ("observations",),
-                 memmap: bool = False, memmap_dir=None, memmap_mode: str = "r+", device="cuda", ops=None, **kwargs):
+                 memmap: bool = False, memmap_dir=None, memmap_mode: str = "r+", device=None, ops=None, **kwargs):
+        device = DEFAULTS["device"] if device is None else device
         if buffer_size <= 0:
             raise ValueError(f"The buffer size must be greater than zero, got: {buffer_size}")
         if n_envs <= 0:
@@ -469,7 +478,8 @@ class EnvIndependentReplayBuffer:
 
     def __init__(self, buffer_size: int, n_envs: int = 1, obs_keys: Sequence[str] = ("observations",),
                  memmap: bool = False, memmap_dir=None, memmap_mode: str = "r+",
-                 buffer_cls: Type[ReplayBuffer] = ReplayBuffer, device="cuda", ops=None, **kwargs):
+                 buffer_cls: Type[ReplayBuffer] = ReplayBuffer, device=None, ops=None, **kwargs):
+        device = DEFAULTS["device"] if device is None else device
         if buffer_size <= 0:
             raise ValueError(f"The buffer size must be greater than zero, got: {buffer_size}")
         if n_envs <= 0:

@@ -155,3 +155,50 @@ def test_two_rank_gloo_plan2explore_replicas_stay_identical():
     solo = make_engine(fx, cfg)
     solo.train_step({k: v.clone().float() for k, v in fx["data"][0].items()}, fx["noise"][0])
     assert not torch.equal(solo.actor_expl.flat, a["actor_expl"])        # the other rank's batch did contribute
+
+
+def _worker_public(rank, world, port, out):
+    """only the public surface: build_agent(fabric with world_size 2) + train(); no explicit attach call"""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    from oracle.ops_emul import EmulOps
+    from sheeprl_b200.algos.dreamer_v3.agent import build_agent
+    from sheeprl_b200.algos.dreamer_v3.dreamer_v3 import make_optimizers, train
+    from sheeprl_b200.algos.dreamer_v3.utils import Moments
+    from sheeprl_b200.parallel import init_process_group_from_env
+    from tests.helpers import load_fixture
+
+    init_process_group_from_env("gloo")            # what fabric.launch does before calling the entry point
+
+    class Fab:
+        device, world_size, global_rank = torch.device("cpu"), world, rank
+
+    class Space:
+        shape = (3, 64, 64)
+
+    fx, cfg = load_fixture("dv3_tiny_a")
+    wm, actor, critic, target, _ = build_agent(Fab, fx["actions_dim"], False, cfg, {"rgb": Space}, fx["init"]["wm"],
+                                               fx["init"]["actor"], fx["init"]["critic"], fx["init"]["target"], ops=EmulOps())
+    eng = wm._b200_engine
+    assert eng.world_size == world and eng.allreduce is not None and eng.allgather is not None
+    opts = make_optimizers(eng, cfg)
+    mo = cfg.algo.actor.moments
+    moments = Moments(mo.decay, mo.max, mo.percentile.low, mo.percentile.high)
+    data = {k: v.clone().float() for k, v in fx["data"][rank].items()}
+    train(Fab, wm, actor, critic, target, *opts, data, None, cfg, False, fx["actions_dim"], moments, noise=fx["noise"][rank])
+    out[rank] = {"wm": eng.wm.flat.clone(), "actor": eng.actor.flat.clone(), "critic": eng.critic.flat.clone(),
+                 "moments": torch.stack([moments.low.clone(), moments.high.clone()]), "seed": eng.rng_seed}
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_through_build_agent_only():
+    """the reference gets data parallelism from `fabric.setup_module` inside build_agent (agent.py:1205-1214); here
+    `build_agent` installs the all-reduce / all-gather hooks itself when fabric.world_size > 1"""
+    mp.set_start_method("spawn", force=True)
+    out = mp.Manager().dict()
+    mp.spawn(_worker_public, args=(2, 31300 + (os.getpid() % 500), out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    for k in ("wm", "actor", "critic", "moments"):
+        assert torch.equal(a[k], b[k]), k
+    assert a["seed"] != b["seed"]                   # ranks draw different sampling-noise streams
