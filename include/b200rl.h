@@ -105,11 +105,14 @@ int b200rl_kl_loss_grad(const float* post_mix, const float* prior_mix, float* d_
                         long long M, int groups, int classes, long long ldp, long long ldq, long long lddp,
                         long long lddq, float kl_dyn, float kl_rep, float free_nats, float regularizer, float scale,
                         cudaStream_t stream);
-/* Persistent fused scan: all T steps of RSSM.dynamic (dreamer_v3.py:131-145 -> agent.py:396-435) in ONE
- * cooperative kernel; weight slices resident in shared memory, state rows staged in shared memory, grid
- * barriers between the 4 dependent stages of a step (rssm_scan.cu).  Writes the same saved activations as the
- * per-step ops above so either backward can consume them.  Requires B <= 16, classes <= 32 and the per-CTA
- * weight slices to fit in 227 KB (returns non-zero otherwise; the caller then uses the per-step ops). */
+/* Persistent fused scan: all T steps of the POSTERIOR recurrence of RSSM.dynamic (dreamer_v3.py:131-145 ->
+ * agent.py:396-435: recurrent model, representation model, unimix, straight-through sample) in ONE cooperative
+ * kernel; weight slices resident in shared memory, cross-SM hand-offs as flag-carrying data exchanges instead of grid
+ * barriers (rssm_scan.cu).  The prior (transition model on the finished h sequence, agent.py:433) is NOT computed here:
+ * it is off the recurrence and runs as batched products over all T*B rows (tr_pre / tr_act / prior_raw / prior_mix
+ * below are unused by the kernels; the fields stay so that the per-step path and this one fill the same set of saved
+ * activations).  Requires B <= 16, classes <= 32, even layer widths and the per-CTA weight slices to fit in 227 KB
+ * (returns non-zero otherwise; the caller then uses the per-step ops). */
 typedef struct b200rl_rssm_scan_args {
   int T, B, S, D, R, A, Dx, Dt, Dr, ld_lat, ld_wr1;
   float eps, unimix;
@@ -120,23 +123,34 @@ typedef struct b200rl_rssm_scan_args {
   float* latent;                              /* [T*B, ld_lat]: z (S*D) | h (R) */
   float *z_in, *h_in, *a_in, *x_pre, *x_act, *g_pre, *g_ln, *tr_pre, *tr_act, *rp_pre, *rp_act;
   float *post_raw, *prior_raw, *post_mix, *prior_mix;
+  const float* W_in_t;                        /* [S*D + A, Dx]: W_in transposed (one-hot z -> row gather) */
   void* workspace;
   long long workspace_bytes;
 } b200rl_rssm_scan_args;
 /* Gradient buffers of the persistent BPTT kernel (same meaning as the per-step path's buffers):
- * inputs d_latent [T*B, ld_lat] (grad wrt z|h from decoder + heads), d_post_mix / d_prior_mix (KL seed grads);
- * outputs: per-step pre-activation gradients consumed by the deferred weight-gradient GEMMs, and d_h0 [R]. */
+ * inputs d_latent [T*B, ld_lat] (grad wrt z|h from decoder + heads + the batched prior backward), d_post_mix (KL seed
+ * grads); outputs: d_post_raw and the per-step ACTIVATION gradients d_rp_act / d_g_ln / d_x_act (the batched
+ * LayerNorm-backward kernels turn them into d_rp_pre / d_g_pre / d_x_pre afterwards), and d_h0 [R].
+ * d_prior_mix / d_prior_raw / d_tr_act / d_tr_pre / d_*_pre are unused by the kernel. */
 typedef struct b200rl_rssm_scan_grads {
   const float *d_latent, *d_post_mix, *d_prior_mix;
   float *d_post_raw, *d_prior_raw, *d_rp_act, *d_rp_pre, *d_tr_act, *d_tr_pre, *d_g_ln, *d_g_pre, *d_x_act, *d_x_pre;
   float* d_h0;
+  /* pre-activation x weight products over all T*B rows (batched, before the kernel; they let the consumer of a
+   * LayerNorm gradient apply the LayerNorm-backward correction by linearity, rssm_scan.cu):
+   * q_r = rp_pre W_r1[:, :R] [T*B, R];  q_g = g_pre W_g [T*B, R+Dx];  q_x = x_pre W_in[:, :S*D] [T*B, S*D] */
+  const float *q_r, *q_g, *q_x;
 } b200rl_rssm_scan_grads;
-long long b200rl_rssm_scan_workspace_bytes(int T, int B, int S, int D);
+long long b200rl_rssm_scan_workspace_bytes(int T, int B, int S, int D, int Dx, int R, int Dr);
 int b200rl_rssm_scan_fwd(const b200rl_rssm_scan_args* args, cudaStream_t stream);
 /* BPTT over the same scan (autograd replay inside fabric.backward, dreamer_v3.py:191); must follow
- * b200rl_rssm_scan_fwd on the same workspace (uses its saved LayerNorm statistics). */
+ * b200rl_rssm_scan_fwd on the same workspace (uses its saved LayerNorm statistics and class indices). */
 int b200rl_rssm_scan_bwd(const b200rl_rssm_scan_args* args, const b200rl_rssm_scan_grads* grads, cudaStream_t stream);
+/* envelope check of the backward kernel for `args` (non-zero + last_error if it cannot run); launches nothing */
+int b200rl_rssm_scan_bwd_check(const b200rl_rssm_scan_args* args);
 int b200rl_rssm_scan_error(const void* workspace, cudaStream_t stream);
+/* cycle counters (2 x 32 int64: CTA 0 = a row owner, CTA 1) accumulated per phase by the last launch on `workspace` */
+int b200rl_rssm_scan_profile(const void* workspace, long long* out64, cudaStream_t stream);
 
 /* ---- losses (value + seed gradient) -----------------------------------------------------------------
  * distribution.py:212-276 (MSE, two-hot on symlog), Bernoulli continue head loss.py:77, lambda returns

@@ -22,6 +22,7 @@ Layouts (all fp32, row-major):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Mapping, Optional, Sequence
 
 import torch
@@ -433,7 +434,9 @@ class DV3Engine:
         # persistent fused RSSM scan (csrc/rssm_scan.cu) when the ops backend provides it and the shape qualifies
         self.fused_scan = bool(hasattr(self.ops, "rssm_scan_fwd") and self.B <= 16 and self.D <= 32 and self.S <= 64)
         self._scan_ws = None
-        self.fused_scan_bwd = hasattr(self.ops, "rssm_scan_bwd")
+        self._scan_q = None
+        self._scan_bwd_checked = False
+        self.fused_scan_bwd = hasattr(self.ops, "rssm_scan_bwd") and os.environ.get("B200RL_SCAN_BWD", "1") != "0"
         self._fused_fwd_done = False
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step
@@ -789,15 +792,23 @@ class DV3Engine:
             ops.cat_sample(self.post_raw[s], self.noise_post[t], self.unimix, self.S, self.D, self.latent[s, :Z],
                            self.post_mix[s])
 
+    def _prior_forward(self):
+        """The prior of every step (transition model on h_t, agent.py:433) is off the recurrence: with the h sequence
+        finished it is two batched tensor-core products over all T*B rows instead of 2 x T skinny ones in the scan."""
+        Z = self.Z
+        self._transition_forward(self.latent[:, Z:], self.tr_pre, self.tr_act, self.prior_raw)
+        # only the prior's unimix log-probs are needed (the prior sample is discarded, dreamer_v3.py:135)
+        self.ops.cat_sample(self.prior_raw, None, self.unimix, self.S, self.D, None, self.prior_mix)
+
     def _scan_forward_fused(self, first: torch.Tensor) -> bool:
-        """The whole scan as ONE persistent cooperative kernel (csrc/rssm_scan.cu).  Produces exactly the saved
-        activations of the per-step path above.  Returns False (and disables itself) if the model does not fit
-        the kernel's shared-memory budget."""
-        p = "rssm.recurrent_model."
-        pt, pr = "rssm.transition_model._model.", "rssm.representation_model._model."
-        w = self._w
+        """The posterior recurrence of the scan as ONE persistent cooperative kernel (csrc/rssm_scan.cu), the prior
+        batched behind it.  Produces exactly the saved activations of the per-step path above.  Returns False (and
+        disables itself) if the model does not fit the kernel's shared-memory budget."""
         if self._scan_ws is None:
-            self._scan_ws = self.ops.rssm_scan_workspace(self.T, self.B, self.S, self.D)
+            self._scan_ws = self.ops.rssm_scan_workspace(self.T, self.B, self.S, self.D, self.Dx, self.R, self.Dr)
+            Win = self._w("rssm.recurrent_model.mlp._model.0.weight")
+            self._win_t_scan = torch.empty(Win.shape[1], Win.shape[0], dtype=torch.float32, device=self.device)
+        self.ops.transpose2d(self._w("rssm.recurrent_model.mlp._model.0.weight"), self._win_t_scan)
         tensors = self._scan_tensors(first)
         dims = self._scan_dims()
         try:
@@ -807,6 +818,7 @@ class DV3Engine:
                 self.fused_scan = False
                 return False
             raise
+        self._prior_forward()
         self._fused_fwd_done = True
         return True
 
@@ -827,23 +839,51 @@ class DV3Engine:
             actions=self.shift_actions, first=first, noise=self.noise_post, latent=self.latent, z_in=self.z_in,
             h_in=self.h_in, a_in=self.a_in, x_pre=self.x_pre, x_act=self.x_act, g_pre=self.g_pre, g_ln=self.g_ln,
             tr_pre=self.tr_pre, tr_act=self.tr_act, rp_pre=self.rp_pre, rp_act=self.rp_act, post_raw=self.post_raw,
-            prior_raw=self.prior_raw, post_mix=self.post_mix, prior_mix=self.prior_mix)
+            prior_raw=self.prior_raw, post_mix=self.post_mix, prior_mix=self.prior_mix, W_in_t=self._win_t_scan)
+
+    def _prior_backward(self):
+        """Backward of the batched prior: its gradient comes from the KL term only (d_prior_mix), so it does not depend on
+        the BPTT either; its contribution to dh is added to d_latent before the backward scan starts.  Also writes the
+        transition model's LayerNorm parameter gradients."""
+        ops, Z = self.ops, self.Z
+        pt = "rssm.transition_model._model."
+        ops.cat_sample_bwd(self.prior_raw, None, self.d_prior_mix, self.unimix, self.S, self.D, self.d_prior_raw)
+        ops.gemm(self.d_prior_raw, self._w(pt + "3.weight"), self.d_tr_act, False, False)
+        ops.ln_act_bwd(self.tr_pre, self._w(pt + "1.weight"), self._w(pt + "1.bias"), self.eps, ACT_SILU,
+                       self.d_tr_act, self.d_tr_pre, self._gw(pt + "1.weight"), self._gw(pt + "1.bias"))
+        ops.gemm(self.d_tr_pre, self._w(pt + "0.weight"), self.d_latent[:, Z:], False, False, accumulate=True)
 
     def _scan_backward_fused(self, first: torch.Tensor) -> bool:
-        """BPTT of the scan as ONE persistent cooperative kernel; fills the same per-step gradient buffers the
-        deferred weight-gradient GEMMs read."""
+        """BPTT of the posterior recurrence as ONE persistent cooperative kernel.  Before it: the batched prior backward
+        and the three `pre-activation x weight` products that let the kernel apply every LayerNorm-backward correction on
+        the consumer side (csrc/rssm_scan.cu).  It fills d_post_raw and the activation gradients d_rp_act / d_g_ln /
+        d_x_act; the deferred section turns those into the pre-activation gradients for all T*B rows at once."""
+        ops, Z, R = self.ops, self.Z, self.R
+        if self._scan_q is None:
+            new = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.device)  # noqa: E731
+            self._scan_q = (new(self.N, R), new(self.N, R + self.Dx), new(self.N, Z))
+        q_r, q_g, q_x = self._scan_q
         grads = dict(d_latent=self.d_latent, d_post_mix=self.d_post_mix, d_prior_mix=self.d_prior_mix,
                      d_post_raw=self.d_post_raw, d_prior_raw=self.d_prior_raw, d_rp_act=self.d_rp_act,
                      d_rp_pre=self.d_rp_pre, d_tr_act=self.d_tr_act, d_tr_pre=self.d_tr_pre, d_g_ln=self.d_g_ln,
-                     d_g_pre=self.d_g_pre, d_x_act=self.d_x_act, d_x_pre=self.d_x_pre, d_h0=self.d_h0)
-        try:
-            self.ops.rssm_scan_bwd(self._scan_dims(), self.eps, self.unimix, self._scan_tensors(first), grads,
-                                   self._scan_ws)
-        except Exception as e:
-            if "shared memory" in str(e) or "supports" in str(e):
-                self.fused_scan_bwd = False
-                return False
-            raise
+                     d_g_pre=self.d_g_pre, d_x_act=self.d_x_act, d_x_pre=self.d_x_pre, d_h0=self.d_h0,
+                     q_r=q_r, q_g=q_g, q_x=q_x)
+        tensors, dims = self._scan_tensors(first), self._scan_dims()
+        if not self._scan_bwd_checked:          # envelope check before anything is launched (first call only)
+            try:
+                ops.rssm_scan_bwd_check(dims, self.eps, self.unimix, tensors, grads, self._scan_ws)
+            except Exception as e:
+                if "shared memory" in str(e) or "supports" in str(e):
+                    self.fused_scan_bwd = False
+                    return False
+                raise
+            self._scan_bwd_checked = True
+        self._prior_backward()
+        p, pr = "rssm.recurrent_model.", "rssm.representation_model._model."
+        ops.gemm(self.rp_pre, self._w(pr + "0.weight")[:, :R], q_r, False, False)
+        ops.gemm(self.g_pre, self._w(p + "rnn.linear.weight"), q_g, False, False)
+        ops.gemm(self.x_pre, self._w(p + "mlp._model.0.weight")[:, :Z], q_x, False, False)
+        ops.rssm_scan_bwd(dims, self.eps, self.unimix, tensors, grads, self._scan_ws)
         return True
 
     def _scan_backward(self, first: torch.Tensor):
@@ -898,8 +938,10 @@ class DV3Engine:
         # representation model
         ops.gemm(self.d_post_raw, self.rp_act, gW(pr + "3.weight"), True, False)
         ops.col_sum(self.d_post_raw, gW(pr + "3.bias"))
+        # LayerNorm parameter gradients over all rows; the same pass (re)writes the pre-activation gradients the weight
+        # products below consume (the fused backward kernel saves only the activation gradients)
         ops.ln_act_bwd(self.rp_pre, self._w(pr + "1.weight"), self._w(pr + "1.bias"), self.eps, ACT_SILU,
-                       self.d_rp_act, self.d_rp_act, gW(pr + "1.weight"), gW(pr + "1.bias"))
+                       self.d_rp_act, self.d_rp_pre, gW(pr + "1.weight"), gW(pr + "1.bias"))
         gWr1 = gW(pr + "0.weight")
         ops.gemm(self.d_rp_pre, h_all, gWr1[:, :R], True, False)
         E = self.E
@@ -912,18 +954,19 @@ class DV3Engine:
         # transition model
         ops.gemm(self.d_prior_raw, self.tr_act, gW(pt + "3.weight"), True, False)
         ops.col_sum(self.d_prior_raw, gW(pt + "3.bias"))
-        ops.ln_act_bwd(self.tr_pre, self._w(pt + "1.weight"), self._w(pt + "1.bias"), self.eps, ACT_SILU,
-                       self.d_tr_act, self.d_tr_act, gW(pt + "1.weight"), gW(pt + "1.bias"))
+        if not fused:                              # (the fused path's batched prior backward already did this one)
+            ops.ln_act_bwd(self.tr_pre, self._w(pt + "1.weight"), self._w(pt + "1.bias"), self.eps, ACT_SILU,
+                           self.d_tr_act, self.d_tr_pre, gW(pt + "1.weight"), gW(pt + "1.bias"))
         ops.gemm(self.d_tr_pre, h_all, gW(pt + "0.weight"), True, False)
         # recurrent model
         ops.ln_act_bwd(self.g_pre, self._w(p + "rnn.layer_norm.weight"), self._w(p + "rnn.layer_norm.bias"),
-                       self.eps, ACT_NONE, self.d_g_ln, self.d_g_ln, gW(p + "rnn.layer_norm.weight"),
+                       self.eps, ACT_NONE, self.d_g_ln, self.d_g_pre, gW(p + "rnn.layer_norm.weight"),
                        gW(p + "rnn.layer_norm.bias"))
         gWg = gW(p + "rnn.linear.weight")
         ops.gemm(self.d_g_pre, self.h_in, gWg[:, :R], True, False)
         ops.gemm(self.d_g_pre, self.x_act, gWg[:, R:], True, False)
         ops.ln_act_bwd(self.x_pre, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"), self.eps,
-                       ACT_SILU, self.d_x_act, self.d_x_act, gW(p + "mlp._model.1.weight"),
+                       ACT_SILU, self.d_x_act, self.d_x_pre, gW(p + "mlp._model.1.weight"),
                        gW(p + "mlp._model.1.bias"))
         gWin = gW(p + "mlp._model.0.weight")
         ops.gemm(self.d_x_pre, self.z_in, gWin[:, :Z], True, False)

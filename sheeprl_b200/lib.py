@@ -73,7 +73,7 @@ class RssmScanArgs(ctypes.Structure):
     POINTERS = ("W_in", "lnx_g", "lnx_b", "W_g", "lng_g", "lng_b", "W_t1", "lnt_g", "lnt_b", "W_t2", "b_t2",
                 "W_r1", "lnr_g", "lnr_b", "W_r2", "b_r2", "h0", "z0", "pe", "actions", "first", "noise", "latent",
                 "z_in", "h_in", "a_in", "x_pre", "x_act", "g_pre", "g_ln", "tr_pre", "tr_act", "rp_pre", "rp_act",
-                "post_raw", "prior_raw", "post_mix", "prior_mix")
+                "post_raw", "prior_raw", "post_mix", "prior_mix", "W_in_t")
     _fields_ = ([(n, c_int) for n in ("T", "B", "S", "D", "R", "A", "Dx", "Dt", "Dr", "ld_lat", "ld_wr1")]
                 + [("eps", c_float), ("unimix", c_float)]
                 + [(n, c_void_p) for n in POINTERS]
@@ -83,7 +83,7 @@ class RssmScanArgs(ctypes.Structure):
 class RssmScanGrads(ctypes.Structure):
     """Mirror of `b200rl_rssm_scan_grads`."""
     POINTERS = ("d_latent", "d_post_mix", "d_prior_mix", "d_post_raw", "d_prior_raw", "d_rp_act", "d_rp_pre",
-                "d_tr_act", "d_tr_pre", "d_g_ln", "d_g_pre", "d_x_act", "d_x_pre", "d_h0")
+                "d_tr_act", "d_tr_pre", "d_g_ln", "d_g_pre", "d_x_act", "d_x_pre", "d_h0", "q_r", "q_g", "q_x")
     _fields_ = [(n, c_void_p) for n in POINTERS]
 
 
@@ -400,9 +400,10 @@ class CudaOps:
         self._ck(self.lib.b200rl_tanh_bwd(_p(y), _p(dy), _p(dx), c_ll(y.numel()), c_int(int(accumulate)), self._st()))
 
     # ------------------------------------------------------------------ persistent RSSM scan
-    def rssm_scan_workspace(self, T: int, B: int, S: int, D: int) -> torch.Tensor:
+    def rssm_scan_workspace(self, T: int, B: int, S: int, D: int, Dx: int, R: int, Dr: int) -> torch.Tensor:
         self.lib.b200rl_rssm_scan_workspace_bytes.restype = c_ll
-        n = int(self.lib.b200rl_rssm_scan_workspace_bytes(c_int(T), c_int(B), c_int(S), c_int(D)))
+        n = int(self.lib.b200rl_rssm_scan_workspace_bytes(c_int(T), c_int(B), c_int(S), c_int(D), c_int(Dx), c_int(R),
+                                                          c_int(Dr)))
         return torch.zeros((n + 3) // 4, dtype=torch.int32, device=self.device)
 
     def _scan_args(self, dims: dict, eps: float, unimix: float, tensors: dict, workspace: torch.Tensor):
@@ -424,6 +425,14 @@ class CudaOps:
         a = self._scan_args(dims, eps, unimix, tensors, workspace)
         self._ck(self.lib.b200rl_rssm_scan_fwd(ctypes.byref(a), self._st()))
 
+    def rssm_scan_bwd_check(self, dims: dict, eps: float, unimix: float, tensors: dict, grads: dict,
+                            workspace: torch.Tensor):
+        """raises if the model is outside the backward kernel's envelope; launches nothing"""
+        a = self._scan_args(dims, eps, unimix, tensors, workspace)
+        rc = self.lib.b200rl_rssm_scan_bwd_check(ctypes.byref(a))
+        if rc != 0:
+            raise B200RLError(self.lib.b200rl_last_error().decode())
+
     def rssm_scan_bwd(self, dims: dict, eps: float, unimix: float, tensors: dict, grads: dict,
                       workspace: torch.Tensor):
         a = self._scan_args(dims, eps, unimix, tensors, workspace)
@@ -436,6 +445,14 @@ class CudaOps:
 
     def rssm_scan_error(self, workspace: torch.Tensor) -> int:
         return int(self.lib.b200rl_rssm_scan_error(_p(workspace), self._st()))
+
+    def rssm_scan_profile(self, workspace: torch.Tensor):
+        """per-phase cycle counters of CTA 0 (a row owner) and CTA 1 of the last scan launch: [2][32] int64"""
+        out = (ctypes.c_longlong * 64)()
+        rc = self.lib.b200rl_rssm_scan_profile(_p(workspace), out, self._st())
+        if rc != 0:
+            raise B200RLError(self.lib.b200rl_last_error().decode())
+        return [list(out[:32]), list(out[32:])]
 
     # ------------------------------------------------------------------ replay / PPO
     def replay_gather(self, storage, idx, out, n_samples: int, batch: int, seq_len: int):
