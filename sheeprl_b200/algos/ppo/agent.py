@@ -211,7 +211,21 @@ def build_agent(fabric, actions_dim: Sequence[int], is_continuous: bool, cfg: Di
     g = torch.Generator().manual_seed(int(cfg.get("seed", 0) or 0))
     ortho = "feature_extractor." if cfg.algo.encoder.ortho_init else None
     eng.load_reference_state(default_init(eng.reference_shapes(), g, ortho))
+    _attach_if_distributed(fabric, eng)
     agent = PPOAgent(eng)
     if agent_state:
         agent.load_state_dict(agent_state)
     return agent, PPOPlayer(eng)
+
+
+def _attach_if_distributed(fabric, eng) -> None:
+    """the reference gets DDP from `fabric.setup_module(agent)` (ppo/agent.py:352-356); the engine's equivalent is the
+    all-reduce hook on its flat gradient"""
+    if int(getattr(fabric, "world_size", 1) or 1) > 1:
+        import torch.distributed as dist
+
+        from sheeprl_b200.parallel import attach_data_parallel
+
+        if not dist.is_initialized():
+            raise RuntimeError("fabric.world_size > 1 but torch.distributed is not initialised (launch through Fabric / torchrun)")
+        attach_data_parallel(eng)

@@ -138,6 +138,15 @@ def build_agent(fabric, cfg: Dict[str, Any], obs_space, action_space, agent_stat
     eng.actor.load(_default_linear_init(eng.actor.shapes, g))
     eng.qf.load(_default_linear_init(eng.qf.shapes, g))
     eng.qf_target.load(eng.qf.state_dict())
+    if int(getattr(fabric, "world_size", 1) or 1) > 1:
+        # the reference wraps actor / critics in DDP here (sac/agent.py:351-360, fabric.setup_module)
+        import torch.distributed as dist
+
+        from sheeprl_b200.parallel import attach_data_parallel
+
+        if not dist.is_initialized():
+            raise RuntimeError("fabric.world_size > 1 but torch.distributed is not initialised (launch through Fabric / torchrun)")
+        attach_data_parallel(eng)
     agent = SACAgent(eng)
     if agent_state:
         agent.load_state_dict(agent_state)

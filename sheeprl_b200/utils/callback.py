@@ -14,52 +14,59 @@ from sheeprl_b200.data.buffers import EnvIndependentReplayBuffer, ReplayBuffer
 
 
 class CheckpointCallback:
+    """Hooks `fabric.call("on_checkpoint_*", ...)` reaches (same names and keyword arguments as the reference's callback).
+    All three funnel into `_write`: mark the newest step of every ring as truncated, put the buffer(s) into the state,
+    save, undo the mark, prune old files."""
+
     def __init__(self, keep_last: Optional[int] = None) -> None:
         self.keep_last = keep_last
 
-    # ------------------------------------------------------------------ reference entry points
-    def on_checkpoint_coupled(self, fabric, ckpt_path: str, state: Dict[str, Any], replay_buffer=None):
-        if replay_buffer is not None:
-            rb_state = self._ckpt_rb(replay_buffer)
-            state["rb"] = replay_buffer
-            if fabric.world_size > 1:
-                # every rank's buffer goes into rank 0's file; host objects travel over gloo (callback.py:42-54)
-                import torch.distributed as dist
+    # ------------------------------------------------------------------ one writer behind the three hooks
+    def _write(self, fabric, path: str, state: Dict[str, Any], rb, gather: bool) -> None:
+        rings = self._rings(rb) if rb is not None else []
+        marks = self._mark_truncated(rings)
+        try:
+            if rb is not None:
+                state["rb"] = self._all_ranks(fabric, rb) if gather else rb
+            fabric.save(path, state)
+        finally:
+            for ring, old in zip(rings, marks):               # the run goes on with the episode it was in
+                if old is not None:
+                    ring["truncated"][(ring._pos - 1) % ring.buffer_size] = old
+        if self.keep_last and fabric.is_global_zero:
+            files = sorted(pathlib.Path(path).parent.glob("*.ckpt"), key=os.path.getmtime)
+            for stale in files[: max(0, len(files) - self.keep_last)]:
+                stale.unlink()
 
-                group = dist.new_group(backend="gloo")
-                gathered = [None for _ in range(fabric.world_size)] if fabric.global_rank == 0 else None
-                dist.gather_object(replay_buffer, gathered, dst=0, group=group)
-                if fabric.global_rank == 0:
-                    state["rb"] = gathered
-                dist.destroy_process_group(group)
-        fabric.save(ckpt_path, state)
-        if replay_buffer is not None:
-            self._experiment_consistent_rb(replay_buffer, rb_state)
-        if fabric.is_global_zero and self.keep_last:
-            self._delete_old_checkpoints(pathlib.Path(ckpt_path).parent)
+    @staticmethod
+    def _all_ranks(fabric, rb):
+        """world_size > 1: rank 0's file holds the list of every rank's buffer (host objects travel over a gloo group)"""
+        import torch.distributed as dist
+
+        group = dist.new_group(backend="gloo")
+        box = [None] * fabric.world_size if fabric.global_rank == 0 else None
+        dist.gather_object(rb, box, dst=0, group=group)
+        dist.destroy_process_group(group)
+        return box if fabric.global_rank == 0 else rb
+
+    def on_checkpoint_coupled(self, fabric, ckpt_path: str, state: Dict[str, Any], replay_buffer=None):
+        self._write(fabric, ckpt_path, state, replay_buffer, gather=fabric.world_size > 1)
 
     def on_checkpoint_player(self, fabric, player_trainer_collective, ckpt_path: str, replay_buffer=None,
                              ratio_state_dict: Optional[Dict[str, Any]] = None):
-        state = [None]
-        player_trainer_collective.broadcast_object_list(state, src=1)
-        state = state[0]
-        if replay_buffer is not None:
-            rb_state = self._ckpt_rb(replay_buffer)
-            state["rb"] = replay_buffer
+        box = [None]
+        player_trainer_collective.broadcast_object_list(box, src=1)       # the model state lives on the first trainer
+        state = box[0]
         if ratio_state_dict is not None:
             state["ratio"] = ratio_state_dict
-        fabric.save(ckpt_path, state)
-        if replay_buffer is not None:
-            self._experiment_consistent_rb(replay_buffer, rb_state)
-        if fabric.is_global_zero and self.keep_last:
-            self._delete_old_checkpoints(pathlib.Path(ckpt_path).parent)
+        self._write(fabric, ckpt_path, state, replay_buffer, gather=False)
 
     def on_checkpoint_trainer(self, fabric, player_trainer_collective, state: Dict[str, Any], ckpt_path: str):
         if fabric.global_rank == 1:
             player_trainer_collective.broadcast_object_list([state], src=1)
         fabric.save(ckpt_path, state)
 
-    # ------------------------------------------------------------------ truncated fix-up
+    # ------------------------------------------------------------------ truncated mark
     @staticmethod
     def _rings(rb):
         if isinstance(rb, EnvIndependentReplayBuffer):
@@ -68,27 +75,19 @@ class CheckpointCallback:
             return [rb]
         raise TypeError(f"unsupported replay buffer type {type(rb)} (EpisodeBuffer is not part of the B200 data path)")
 
-    def _ckpt_rb(self, rb):
-        saved = []
-        for b in self._rings(rb):
-            if b.empty or "truncated" not in b.buffer:
-                saved.append(None)
+    @staticmethod
+    def _mark_truncated(rings):
+        """The environments' state is not checkpointed: a resumed run starts new episodes, so the newest stored step of
+        every ring must read as the end of one.  Returns the overwritten values."""
+        old = []
+        for ring in rings:
+            if ring.empty or "truncated" not in ring.buffer:
+                old.append(None)
                 continue
-            row = (b._pos - 1) % b.buffer_size
-            saved.append(b["truncated"][row].clone())
-            b["truncated"][row] = 1
-        return saved
-
-    def _experiment_consistent_rb(self, rb, saved) -> None:
-        for b, old in zip(self._rings(rb), saved):
-            if old is not None:
-                b["truncated"][(b._pos - 1) % b.buffer_size] = old
-
-    def _delete_old_checkpoints(self, ckpt_folder: pathlib.Path) -> None:
-        ckpts = sorted(ckpt_folder.glob("*.ckpt"), key=os.path.getmtime)
-        if len(ckpts) > self.keep_last:
-            for f in ckpts[:-self.keep_last]:
-                f.unlink()
+            row = (ring._pos - 1) % ring.buffer_size
+            old.append(ring["truncated"][row].clone())
+            ring["truncated"][row] = 1
+        return old
 
 
 def load_replay_buffer(obj, device="cuda", ops=None):

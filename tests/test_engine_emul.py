@@ -40,9 +40,14 @@ def test_engine_matches_oracle_and_reference(name):
         norm = float(o_outs[0]["Grads/" + {"wm": "world_model"}.get(grp, grp)])
         coef = min(1.0, max_norm / (norm + 1e-6))
         gmax = max(float(v.abs().max()) for v in og.values()) / coef
+        gnorm = float(torch.sqrt(sum((v.double() ** 2).sum() for v in og.values())))
         for k, v in og.items():
-            d = float((e_grads[0][grp][k] * coef - v).abs().max())
+            diff = e_grads[0][grp][k] * coef - v
+            d = float(diff.abs().max())
             assert d <= 2e-5 * max(gmax * coef, 1e-12) + 1e-9, (grp, k, d, gmax)
+            # every tensor on its own scale (l2), floor 1e-6 of the group norm
+            rel = float(diff.double().norm()) / (float(v.double().norm()) + 1e-6 * gnorm + 1e-30)
+            assert rel <= 1e-4, (grp, k, "per-tensor relative gradient error", rel)
     for s in range(steps):
         for k, v in fx["metrics"][s].items():
             assert e_outs[s][k] == pytest.approx(v, rel=3e-5, abs=1e-6), (s, k)
