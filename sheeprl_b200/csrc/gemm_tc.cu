@@ -187,6 +187,7 @@ struct Smem {
   float b_lo[STAGES][BN * BK];
   uint64_t full[STAGES], split[STAGES], empty[STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
+  int last_split;                // split-K: this CTA is the last of its output tile to arrive (it reduces the partials)
 };
 
 // Two-level accumulation.  The tensor core adds each k-step into the fp32 TMEM accumulator with truncation
@@ -204,7 +205,10 @@ struct TileGeo {
   int tiles_x, tiles_y;    // tiles per image
   int chunks;              // input channels / 32
   int Cout;                // output channels
-  int ksplits;             // GEMM mode: number of K splits (gridDim.z); > 1 => atomic accumulation into C
+  int ksplits;             // GEMM mode: number of K splits (gridDim.z); > 1 => partial tiles go through `part`
+  float* part;             // split-K workspace: [ksplits][mpad][ldw] partial sums (fixed-order reduction, no atomics)
+  int* cnt;                // split-K: arrival counter per output tile (self-resetting)
+  int mpad, ldw;           // split-K workspace geometry (rows per split, row stride)
   int a_mn, b_mn;          // GEMM mode: operand stored [K][M] / [K][N] (MN-major) instead of [M][K] / [N][K]
   int mtiles;              // number of M tiles; a CTA walks tiles blockIdx.y, blockIdx.y + gridDim.y, ... (persistent)
   int wg;                  // GEMM mode, conv weight gradient: A rows = (tap, big channel), K = small-grid pixels gathered
@@ -220,7 +224,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int mtiles = geo.mtiles, tstride = gridDim.y;
-  // split-K (GEMM mode): blockIdx.z owns k-blocks [kb_base, kb_base + nkb); partial sums are atomically added
+  // split-K (GEMM mode): blockIdx.z owns k-blocks [kb_base, kb_base + nkb); its partial tile goes to the workspace and
+  // the LAST split to arrive for an output tile sums all partials in split order (bit-reproducible, no atomics on C)
   int kb_base = 0, nkb = (K + BK - 1) / BK;
   if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
     const int per = (nkb + geo.ksplits - 1) / geo.ksplits;
@@ -437,22 +442,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (geo.mode == MODE_DOWN) row_off = (((size_t)n * geo.h + y) * geo.w + x) * (size_t)ldc;
       else row_off = (((size_t)n * (2 * geo.h) + (2 * y + py)) * (2 * geo.w) + (2 * x + px)) * (size_t)ldc;
     }
-    if (row_ok) {
+    bool store = true;
+    if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
+      // ---- deterministic split-K: publish this split's partial tile, count the arrival
+      float* prow = geo.part + ((size_t)blockIdx.z * geo.mpad + (size_t)(m0 + q * 32 + lane)) * geo.ldw + n0 + half * ACC_COLS;
+#pragma unroll
+      for (int j = 0; j < ACC_COLS; j += 4)
+        *reinterpret_cast<float4*>(prow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(NACC_WARPS * 32) : "memory");
+      if (threadIdx.x == ACC_WARP0 * 32) {
+        int* c = geo.cnt + (size_t)tile * gridDim.x + blockIdx.x;
+        const int old = atomicAdd(c, 1);
+        const int last = (old == geo.ksplits - 1);
+        if (last) *c = 0;                        // every split of this tile has arrived: leave the counter clean
+        __threadfence();
+        s.last_split = last;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NACC_WARPS * 32) : "memory");
+      store = s.last_split != 0;
+      if (store) {
+#pragma unroll
+        for (int j = 0; j < ACC_COLS; ++j) acc[j] = 0.f;
+        for (int z = 0; z < geo.ksplits; ++z) {  // fixed order 0 .. ksplits-1, whoever arrived last
+          const float* pz = geo.part + ((size_t)z * geo.mpad + (size_t)(m0 + q * 32 + lane)) * geo.ldw + n0 + half * ACC_COLS;
+#pragma unroll
+          for (int j = 0; j < ACC_COLS; j += 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(pz + j));
+            acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NACC_WARPS * 32) : "memory");   // `last_split` is rewritten by the next tile
+    }
+    if (row_ok && store) {
       const int cb = n0 + half * ACC_COLS;
       float* crow = C + row_off + cb;
       const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (cb + ACC_COLS <= N);
-      if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
-        // C was initialised by init_c_kernel (bias / zero / kept); 16-byte vector reductions when the row allows
-        if (vec) {
-#pragma unroll
-          for (int j = 0; j < ACC_COLS; j += 4)
-            atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < ACC_COLS; ++j)
-            if (cb + j < N) atomicAdd(crow + j, acc[j]);
-        }
-      } else if (vec) {
+      if (vec) {
 #pragma unroll
         for (int j = 0; j < ACC_COLS; j += 4) {
           float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -631,18 +658,50 @@ __global__ void conv_pack_up_kernel(const float* __restrict__ W, float* __restri
   P[idx] = W[((long long)cs * Cb + cb) * 16 + ky * 4 + kx];
 }
 
-__global__ void init_c_kernel(float* __restrict__ C, const float* __restrict__ bias, int M, int N, int ldc, int keep) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)M * N) return;
-  const int m = (int)(idx / N), n = (int)(idx % N);
-  float v = keep ? C[(size_t)m * ldc + n] : 0.f;
-  if (bias) v += bias[n];
-  C[(size_t)m * ldc + n] = v;
+// Split-K workspace: partial tiles + per-tile arrival counters, one per device, grown on demand OUTSIDE stream capture
+// (launches on one stream serialise, so consecutive products share it; a capture replays the size it was captured with).
+struct SplitWs {
+  float* part = nullptr;
+  size_t floats = 0;
+  int* cnt = nullptr;
+};
+constexpr int SPLIT_MAX_TILES = 4096;
+SplitWs g_split[16];
+std::mutex g_split_mu;
+
+int split_workspace(size_t need_floats, int tiles, cudaStream_t st, float** part, int** cnt) {
+  int dev = 0;
+  RL_CUDA(cudaGetDevice(&dev));
+  RL_CHECK_ARG(dev < 16 && tiles <= SPLIT_MAX_TILES, "split-K workspace: device index / tile count out of range");
+  std::lock_guard<std::mutex> lk(g_split_mu);
+  SplitWs& w = g_split[dev];
+  if (need_floats > w.floats || !w.cnt) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    RL_CUDA(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone) {
+      b200rl_set_error("split-K workspace must grow during stream capture: run the step once eagerly first");
+      return B200RL_ERR_CUDA;
+    }
+    RL_CUDA(cudaDeviceSynchronize());
+    if (need_floats > w.floats) {
+      if (w.part) RL_CUDA(cudaFree(w.part));
+      const size_t n = need_floats + need_floats / 2 > (size_t)16 << 20 ? need_floats + need_floats / 2 : (size_t)16 << 20;
+      RL_CUDA(cudaMalloc(&w.part, n * sizeof(float)));
+      w.floats = n;
+    }
+    if (!w.cnt) {
+      RL_CUDA(cudaMalloc(&w.cnt, SPLIT_MAX_TILES * sizeof(int)));
+      RL_CUDA(cudaMemset(w.cnt, 0, SPLIT_MAX_TILES * sizeof(int)));
+    }
+  }
+  *part = w.part;
+  *cnt = w.cnt;
+  return B200RL_OK;
 }
 
 int launch_conv(int mode, const float* img, const float* Wp, float* out, const float* bias, int NB, int h, int w, int Cin,
                 int Cout, cudaStream_t st) {
-  TileGeo g;
+  TileGeo g = {};
   g.mode = mode; g.h = h; g.w = w; g.NB = NB; g.chunks = Cin / BK; g.Cout = Cout; g.ksplits = 1;
   RL_CHECK_ARG(conv_tile(h, w, NB, &g.bw, &g.bh, &g.bn), "image grid not tileable by 128 pixels");
   g.tiles_x = w / g.bw; g.tiles_y = h / g.bh;
@@ -749,11 +808,9 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
   }
   if (g.ksplits > 1) {
     grid.z = g.ksplits;
-    if (!accumulate && !bias && ldc == N) {
-      RL_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));      // contiguous C: a memset node is enough
-    } else if (!accumulate || bias) {
-      init_c_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(C, bias, M, N, ldc, accumulate);
-    }
+    g.mpad = (int)grid.y * BM;
+    g.ldw = (int)grid.x * BN;
+    if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, tiles, st, &g.part, &g.cnt)) return rc;
   }
   g.mtiles = (int)grid.y;
   grid.y = persistent_grid_y(g.mtiles, grid.x, grid.z);
@@ -804,7 +861,11 @@ extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float
   g.ksplits = (nkb + per - 1) / per;
   grid.z = g.ksplits;
   g.mtiles = (int)grid.y;
-  if (g.ksplits > 1) RL_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)M * N, st));
+  if (g.ksplits > 1) {
+    g.mpad = (int)grid.y * BM;
+    g.ldw = (int)grid.x * BN;
+    if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, tiles, st, &g.part, &g.cnt)) return rc;
+  }
   if (BN == 64) {
     const size_t smem = sizeof(Smem<64>) + 1024;
     RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

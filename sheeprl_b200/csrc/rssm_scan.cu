@@ -164,30 +164,41 @@ __device__ __forceinline__ float ll_wait(const u64* p, unsigned tag, Spin& sp) {
 }
 
 // Receives rows x n values (n even; LL rows of stride ss elements, 16-byte aligned) into shared memory rows of stride ds.
-// LL_UNROLL 16-byte loads are in flight per thread before the first tag is checked.
+// A thread owns column pairs k = 2*tid (+ 2*SCAN_NT ...) and walks the rows, LL_UNROLL 16-byte loads in flight before the
+// first tag is checked; no integer division on this path.
 __device__ __forceinline__ void ll_recv(float* dst, int ds, const u64* src, int ss, int rows, int n, unsigned tag, int tid, Spin& sp) {
-  const int half = n >> 1, total = rows * half;
-  for (int e0 = tid; e0 < total; e0 += SCAN_NT * LL_UNROLL) {
-    u64 a[LL_UNROLL], b[LL_UNROLL];
+  for (int k = 2 * tid; k < n; k += 2 * SCAN_NT) {
+    for (int r0 = 0; r0 < rows; r0 += LL_UNROLL) {
+      u64 a[LL_UNROLL], b[LL_UNROLL];
 #pragma unroll
-    for (int u = 0; u < LL_UNROLL; ++u) {
-      const int e = e0 + u * SCAN_NT;
-      if (e < total) ll_load2(src + (size_t)(e / half) * ss + 2 * (size_t)(e % half), a[u], b[u]);
-    }
+      for (int u = 0; u < LL_UNROLL; ++u)
+        if (r0 + u < rows) ll_load2(src + (size_t)(r0 + u) * ss + k, a[u], b[u]);
 #pragma unroll
-    for (int u = 0; u < LL_UNROLL; ++u) {
-      const int e = e0 + u * SCAN_NT;
-      if (e < total) {
-        const int row = e / half, k = (e - row * half) * 2;
-        while ((unsigned)(a[u] >> 32) != tag || (unsigned)(b[u] >> 32) != tag) {
-          if (sp.fail()) break;
-          ll_load2(src + (size_t)row * ss + k, a[u], b[u]);
+      for (int u = 0; u < LL_UNROLL; ++u)
+        if (r0 + u < rows) {
+          while ((unsigned)(a[u] >> 32) != tag || (unsigned)(b[u] >> 32) != tag) {
+            if (sp.fail()) break;
+            ll_load2(src + (size_t)(r0 + u) * ss + k, a[u], b[u]);
+          }
+          *reinterpret_cast<float2*>(dst + (r0 + u) * ds + k) =
+              make_float2(__uint_as_float((unsigned)a[u]), __uint_as_float((unsigned)b[u]));
         }
-        *reinterpret_cast<float2*>(dst + row * ds + k) =
-            make_float2(__uint_as_float((unsigned)a[u]), __uint_as_float((unsigned)b[u]));
-      }
     }
   }
+}
+
+// (row, owned-column) element a thread is responsible for during the whole scan: e = b * per_row + cj
+struct Slot {
+  int b, cj, col;
+  bool ok;
+};
+__device__ __forceinline__ Slot make_slot(int e, int per_row, int B, int cta, int width) {
+  Slot s;
+  s.b = per_row > 0 ? e / per_row : 0;
+  s.cj = e - s.b * per_row;
+  s.col = (cta + (s.cj >> 2) * SCAN_G) * 4 + (s.cj & 3);
+  s.ok = per_row > 0 && s.b < B && s.col < width;
+  return s;
 }
 
 // fast transcendental form for SiLU; rel. error ~1e-6
@@ -310,7 +321,7 @@ struct GeoF {
   int unit_g, unit_r0, unit_nr; // this CTA's unit: group (-1: none), first row, row count
   int owner_row;                // batch row whose x this CTA builds (-1: none)
   int ldp;                      // row length of the product partial buffers
-  int oWg, oWr1, oW2, oXh, oXx, oPart, oAcc, oX0, oMisc, oInt, total;
+  int oWg, oWr1, oW2, oXh, oXx, oPart, oAcc, oX0, oPar, oMisc, oInt, total;
 };
 
 __host__ __device__ inline GeoF make_geo_f(const b200rl_rssm_scan_args& a, int cta) {
@@ -341,6 +352,7 @@ __host__ __device__ inline GeoF make_geo_f(const b200rl_rssm_scan_args& a, int c
   g.oPart = o; o += imax(SCAN_NW * MAXB * g.ldp, SCAN_NW * MAXRPU * 32);
   g.oAcc = o;  o += MAXB * g.ldp;
   g.oX0 = o;   o += g.sDx;
+  g.oPar = o;  o += g.sR + 2 * g.sDx + 2 * g.sDr;   // h0 | lnx gamma, beta | lnr gamma, beta (read every step)
   g.oMisc = o; o += 8 * MAXB + 64;
   g.oInt = o;  o += r4(64 + 64 + SCAN_G);      // z0 class indices, z_{t-1} indices of the owned row, column counts
   g.total = o;
@@ -362,8 +374,13 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
   float* Xh = sm + g.oXh;       // [MAXB][sR]  h rows (carried from one step to the next)
   float* Xx = sm + g.oXx;       // [MAXB][sDx] x rows; reused for the unit's rp rows
   float* PART = sm + g.oPart;
-  float* ACC = sm + g.oAcc;     // [MAXB][ldp] h-part of the GRU product, then the finished g_pre columns
+  float* ACC = sm + g.oAcc;     // [MAXB][ldp] finished g_pre columns (for the row statistics)
   float* X0 = sm + g.oX0;       // [Dx] x_pre contribution of the learned initial posterior z0
+  float* H0 = sm + g.oPar;      // [R] tanh(initial_recurrent_state)
+  float* LNXG = H0 + g.sR;      // [Dx] x LayerNorm gamma, beta
+  float* LNXB = LNXG + g.sDx;
+  float* LNRG = LNXB + g.sDx;   // [Dr] representation LayerNorm gamma, beta
+  float* LNRB = LNRG + g.sDr;
   float* misc = sm + g.oMisc;   // [0,16) first flags; [16,32) mean; [32,48) rstd; [48,80) reduction scratch
   int* z0idx = (int*)(sm + g.oInt);
   int* zrow = z0idx + 64;
@@ -376,7 +393,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
   Spin sp;
   sp.init(ws.error);
 
-  // ---------------- prologue: weight slices -> shared memory (read from HBM once per scan)
+  // ---------------- prologue: weight slices and per-step parameters -> shared memory (read from HBM once per scan)
   for (int e = tid; e < g.total; e += SCAN_NT) sm[e] = 0.f;
   __syncthreads();
   for (int gi = 0; gi < g.ngh; ++gi)
@@ -393,6 +410,9 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       const int d = e / Dr, k = e - d * Dr;
       W2[d * g.w2st + k] = a.W_r2[((size_t)g.unit_g * D + d) * Dr + k];
     }
+  for (int k = tid; k < R; k += SCAN_NT) H0[k] = a.h0[k];
+  for (int k = tid; k < Dx; k += SCAN_NT) { LNXG[k] = a.lnx_g[k]; LNXB[k] = a.lnx_b[k]; }
+  for (int k = tid; k < Dr; k += SCAN_NT) { LNRG[k] = a.lnr_g[k]; LNRB[k] = a.lnr_b[k]; }
   for (int c = tid; c < SCAN_G; c += SCAN_NT) nctab[c] = owned_cols(R, c);
   if (wid == 0) {  // class index of the learned initial posterior (one-hot `z0`)
     for (int gq = 0; gq < S; ++gq) {
@@ -417,6 +437,20 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       const int b = g.unit_r0 + e / D, d = e % D;
       a.z_in[(size_t)b * Z + g.unit_g * D + d] = a.first[b] * ((z0idx[g.unit_g] == d) ? 1.f : 0.f);
     }
+  // fixed element assignments (no index arithmetic inside the time loop)
+  const int nh4 = g.ngh * 4, nh12 = g.ngh * 12, nr4 = g.ngr * 4;
+  const Slot sH = make_slot(tid, nh4, B, cta, R);           // gate / h element
+  const Slot sR_ = make_slot(tid, nr4, B, cta, Dr);         // rp element
+  // g_pre element: c = (group, part, j) inside the row of 12*ngh products
+  const int pb = nh12 > 0 ? tid / nh12 : 0, pc = tid - pb * nh12;
+  const int pcol = (cta + (pc / 12) * SCAN_G) * 4 + (pc & 3), ppart = (pc % 12) >> 2;
+  const bool pok = nh12 > 0 && pb < B && pcol < R;
+  float lg_g[3] = {0.f, 0.f, 0.f}, lg_b[3] = {0.f, 0.f, 0.f};
+  if (sH.ok)
+#pragma unroll
+    for (int part = 0; part < 3; ++part) { lg_g[part] = a.lng_g[part * R + sH.col]; lg_b[part] = a.lng_b[part * R + sH.col]; }
+  const int ncol3 = 3 * owned_cols(R, cta);                // values per row in this CTA's share of the GRU LayerNorm
+  const float bias2 = (sampler && lane < D) ? a.b_r2[g.unit_g * D + lane] : 0.f;
   __syncthreads();
   prof_mark(prof, 0, tlast, prof_on);
 
@@ -426,24 +460,28 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     const unsigned tag = (unsigned)t + 1u;
     if (tid < MAXB) misc[tid] = (tid < B) ? a.first[row0 + tid] : 0.f;
     // prefetches that do not depend on the chain
-    float pe_pref[4] = {0.f, 0.f, 0.f, 0.f};      // pe[t][b][own rp columns]: ngr*4*B values over 256 threads
-    {
-      const int nv = B * g.ngr * 4;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = tid + u * SCAN_NT;
-        if (e < nv) {
-          const int b = e / (g.ngr * 4), cj = e - b * (g.ngr * 4);
-          const int col = (cta + (cj >> 2) * SCAN_G) * 4 + (cj & 3);
-          if (col < Dr) pe_pref[u] = a.pe[(row0 + b) * Dr + col];
-        }
-      }
+    const float pe_pref = sR_.ok ? a.pe[(row0 + sR_.b) * Dr + sR_.col] : 0.f;
+    float noise_pref = 1.f, fnext = 0.f;
+    if (sampler && wid < g.unit_nr) {
+      if (lane < D) noise_pref = a.noise[(row0 + g.unit_r0 + wid) * Z + (size_t)g.unit_g * D + lane];
+      if (t + 1 < T) fnext = a.first[row0 + B + g.unit_r0 + wid];
     }
-    float noise_pref = 1.f;
-    if (sampler && wid < g.unit_nr && lane < D)
-      noise_pref = a.noise[(row0 + g.unit_r0 + wid) * Z + (size_t)g.unit_g * D + lane];
+    float act_pref[2] = {0.f, 0.f};                         // (owner) action part of x_pre for the thread's column pair
     __syncthreads();
     const float* fl = misc;
+
+    // ============ B1: h_in = (1-f) h_{t-1} + f h0 (agent.py:428), rows with f != 0 only; h-part of the GRU product
+    for (int b = 0; b < B; ++b) {
+      const float f = fl[b];
+      if (f != 0.f || t == 0)
+        for (int k = tid; k < R; k += SCAN_NT) Xh[b * g.sR + k] = (1.f - f) * ((t > 0) ? Xh[b * g.sR + k] : 0.f) + f * H0[k];
+    }
+    __syncthreads();
+    const int ksh = product(Xh, g.sR, Wg, g.wgst, g.ngh * 3, R, PART, ldp, 0, tid);
+    __syncthreads();
+    const float acch = pok ? part_sum(PART, ldp, ksh, pb, pc) : 0.f;
+    const float hin = sH.ok ? Xh[sH.b * g.sR + sH.col] : 0.f;
+    prof_mark(prof, 1, tlast, prof_on);
 
     // ============ A (row owner): x = SiLU(LN(W_in [z_in, a_in])) for the owned row; z_in one-hot -> row gather
     if (owner) {
@@ -452,67 +490,67 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       if (t > 0 && tid < S) zrow[tid] = (int)__float_as_uint(ll_wait(ws.ll + L.z + ((size_t)(par ^ 1) * MAXB + b) * S + tid, (unsigned)t, sp));
       __syncthreads();
       prof_mark(prof, 2, tlast, prof_on);
-      float xv[4];
+      float2 xv[2];
       float s = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = tid + u * SCAN_NT;
-        xv[u] = 0.f;
+      for (int u = 0; u < 2; ++u) {
+        const int c = 2 * tid + 2 * SCAN_NT * u;
+        xv[u] = make_float2(0.f, 0.f);
         if (c < Dx) {
-          float acc = 0.f;
+          float2 acc = make_float2(0.f, 0.f);
           if (t > 0 && f != 1.f)
-            for (int gq = 0; gq < S; ++gq) acc += a.W_in_t[(size_t)(gq * D + zrow[gq]) * Dx + c];
-          float aa = 0.f;
-          for (int qq = 0; qq < A; ++qq) aa = fmaf(a.actions[(row0 + b) * A + qq], a.W_in_t[(size_t)(Z + qq) * Dx + c], aa);
-          xv[u] = (1.f - f) * (acc + aa) + f * X0[c];
-          a.x_pre[(row0 + b) * Dx + c] = xv[u];
-          s += xv[u];
+            for (int g0 = 0; g0 < S; g0 += 8) {            // 8 row gathers in flight, summed in group order
+              float2 v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (g0 + i < S) v[i] = __ldg(reinterpret_cast<const float2*>(a.W_in_t + (size_t)((g0 + i) * D + zrow[g0 + i]) * Dx + c));
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (g0 + i < S) { acc.x += v[i].x; acc.y += v[i].y; }
+            }
+          float2 aa = make_float2(0.f, 0.f);
+          for (int qq = 0; qq < A; ++qq) {
+            const float av = a.actions[(row0 + b) * A + qq];
+            const float2 w = __ldg(reinterpret_cast<const float2*>(a.W_in_t + (size_t)(Z + qq) * Dx + c));
+            aa.x = fmaf(av, w.x, aa.x); aa.y = fmaf(av, w.y, aa.y);
+          }
+          xv[u].x = (1.f - f) * (acc.x + aa.x) + f * X0[c];
+          xv[u].y = (1.f - f) * (acc.y + aa.y) + f * X0[c + 1];
+          s += xv[u].x + xv[u].y;
         }
       }
       const float mu = block_sum(s, misc + 48) / (float)Dx;
       float v = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = tid + u * SCAN_NT;
-        if (c < Dx) { const float d = xv[u] - mu; v = fmaf(d, d, v); }
+      for (int u = 0; u < 2; ++u) {
+        const int c = 2 * tid + 2 * SCAN_NT * u;
+        if (c < Dx) { const float d0 = xv[u].x - mu, d1 = xv[u].y - mu; v = fmaf(d0, d0, v); v = fmaf(d1, d1, v); }
       }
       const float rstd = rsqrtf(block_sum(v, misc + 48) / (float)Dx + a.eps);
       u64* dst = ws.ll + L.x + ((size_t)par * MAXB + b) * Dx;
+      float2 ov[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = tid + u * SCAN_NT;
+      for (int u = 0; u < 2; ++u) {
+        const int c = 2 * tid + 2 * SCAN_NT * u;
         if (c < Dx) {
-          const float o = fsilu((xv[u] - mu) * rstd * a.lnx_g[c] + a.lnx_b[c]);
-          ll_store(dst + c, o, tag);
-          a.x_act[(row0 + b) * Dx + c] = o;
+          ov[u].x = fsilu((xv[u].x - mu) * rstd * LNXG[c] + LNXB[c]);
+          ov[u].y = fsilu((xv[u].y - mu) * rstd * LNXG[c + 1] + LNXB[c + 1]);
+          ll_store2(dst + c, ov[u].x, ov[u].y, tag);            // hand-off first ...
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {                             // ... saves for the backward after it
+        const int c = 2 * tid + 2 * SCAN_NT * u;
+        if (c < Dx) {
+          *reinterpret_cast<float2*>(a.x_pre + (row0 + b) * Dx + c) = xv[u];
+          *reinterpret_cast<float2*>(a.x_act + (row0 + b) * Dx + c) = ov[u];
         }
       }
       if (tid == 0) { ws.ln_stats[((size_t)0 * NB + row0 + b) * 2] = mu; ws.ln_stats[((size_t)0 * NB + row0 + b) * 2 + 1] = rstd; }
       for (int e = tid; e < A; e += SCAN_NT) a.a_in[(row0 + b) * A + e] = (1.f - f) * a.actions[(row0 + b) * A + e];
       prof_mark(prof, 3, tlast, prof_on);
     }
-
-    // ============ B1: h_in = (1-f) h_{t-1} + f h0 (agent.py:428) in place; h-part of the GRU product
-    for (int e = tid; e < B * R; e += SCAN_NT) {
-      const int b = e / R, k = e - b * R;
-      const float f = fl[b];
-      const float hp = (t > 0) ? Xh[b * g.sR + k] : 0.f;
-      Xh[b * g.sR + k] = (1.f - f) * hp + f * a.h0[k];
-    }
-    __syncthreads();
-    for (int e = tid; e < B * g.ngh * 4; e += SCAN_NT) {     // save h_in for the owned columns
-      const int b = e / (g.ngh * 4), cj = e - b * (g.ngh * 4);
-      const int col = (cta + (cj >> 2) * SCAN_G) * 4 + (cj & 3);
-      if (col < R) a.h_in[(row0 + b) * R + col] = Xh[b * g.sR + col];
-    }
-    const int ksh = product(Xh, g.sR, Wg, g.wgst, g.ngh * 3, R, PART, ldp, 0, tid);
-    __syncthreads();
-    for (int e = tid; e < B * g.ngh * 12; e += SCAN_NT) {
-      const int b = e / (g.ngh * 12), c = e - b * (g.ngh * 12);
-      ACC[b * ldp + c] = part_sum(PART, ldp, ksh, b, c);
-    }
-    __syncthreads();
-    prof_mark(prof, 1, tlast, prof_on);
+    (void)act_pref;
 
     // ============ B2: x-part of the GRU product; g_pre columns; partial LayerNorm statistics
     ll_recv(Xx, xxs, ws.ll + L.x + (size_t)par * MAXB * Dx, Dx, B, Dx, tag, tid, sp);
@@ -520,127 +558,106 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     prof_mark(prof, 4, tlast, prof_on);
     const int ksx = product(Xx, xxs, Wg + g.sR, g.wgst, g.ngh * 3, Dx, PART, ldp, 0, tid);
     __syncthreads();
-    for (int e = tid; e < B * g.ngh * 12; e += SCAN_NT) {
-      const int b = e / (g.ngh * 12), c = e - b * (g.ngh * 12);
-      const float v = ACC[b * ldp + c] + part_sum(PART, ldp, ksx, b, c);
-      ACC[b * ldp + c] = v;
-      const int gi = c / 12, part = (c % 12) / 4, j = c & 3;
-      const int col = (cta + gi * SCAN_G) * 4 + j;
-      if (col < R) a.g_pre[(row0 + b) * 3 * R + part * R + col] = v;
+    float gpre = 0.f;
+    if (pok) {
+      gpre = acch + part_sum(PART, ldp, ksx, pb, pc);
+      ACC[pb * ldp + pc] = gpre;
     }
     __syncthreads();
     for (int b = wid; b < B; b += SCAN_NW) {   // per-row partial statistics (mean, M2) over the owned valid columns
       float s = 0.f;
-      int cnt = 0;
-      for (int c = lane; c < g.ngh * 12; c += 32) {
-        const int col = (cta + (c / 12) * SCAN_G) * 4 + (c & 3);
-        if (col < R) { s += ACC[b * ldp + c]; ++cnt; }
-      }
+      for (int c = lane; c < nh12; c += 32)
+        if ((cta + (c / 12) * SCAN_G) * 4 + (c & 3) < R) s += ACC[b * ldp + c];
       s = warp_sum(s);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      const float mean = cnt > 0 ? s / (float)cnt : 0.f;
+      const float mean = ncol3 > 0 ? s / (float)ncol3 : 0.f;
       float m2 = 0.f;
-      for (int c = lane; c < g.ngh * 12; c += 32) {
-        const int col = (cta + (c / 12) * SCAN_G) * 4 + (c & 3);
-        if (col < R) { const float d = ACC[b * ldp + c] - mean; m2 = fmaf(d, d, m2); }
-      }
+      for (int c = lane; c < nh12; c += 32)
+        if ((cta + (c / 12) * SCAN_G) * 4 + (c & 3) < R) { const float d = ACC[b * ldp + c] - mean; m2 = fmaf(d, d, m2); }
       m2 = warp_sum(m2);
       if (lane == 0) ll_store2(ws.ll + L.s + (((size_t)par * MAXB + b) * SCAN_G + cta) * 2, mean, m2, tag);
     }
+    if (pok) a.g_pre[(row0 + pb) * 3 * R + ppart * R + pcol] = gpre;      // save after the hand-off
     prof_mark(prof, 5, tlast, prof_on);
 
     // ============ C: merge statistics (Chan), LayerNorm, GRU gate -> h_t for the owned columns
-    for (int b = wid; b < B; b += SCAN_NW) {
-      float pm[SCAN_G / 32], pq[SCAN_G / 32];
+    for (int b0 = wid; b0 < B; b0 += 2 * SCAN_NW) {          // a warp merges up to two rows, all their loads in flight
+      u64 x[2][SCAN_G / 32], y[2][SCAN_G / 32];
 #pragma unroll
-      for (int i = 0; i < SCAN_G / 32; ++i) {
-        const u64* p = ws.ll + L.s + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2;
-        u64 x, y;
-        ll_load2(p, x, y);
-        while ((unsigned)(x >> 32) != tag || (unsigned)(y >> 32) != tag) {
-          if (sp.fail()) break;
-          ll_load2(p, x, y);
+      for (int rr = 0; rr < 2; ++rr) {
+        const int b = b0 + rr * SCAN_NW;
+        if (b < B)
+#pragma unroll
+          for (int i = 0; i < SCAN_G / 32; ++i)
+            ll_load2(ws.ll + L.s + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2, x[rr][i], y[rr][i]);
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int b = b0 + rr * SCAN_NW;
+        if (b >= B) continue;
+        float pm[SCAN_G / 32], pq[SCAN_G / 32];
+#pragma unroll
+        for (int i = 0; i < SCAN_G / 32; ++i) {
+          const u64* p = ws.ll + L.s + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2;
+          while ((unsigned)(x[rr][i] >> 32) != tag || (unsigned)(y[rr][i] >> 32) != tag) {
+            if (sp.fail()) break;
+            ll_load2(p, x[rr][i], y[rr][i]);
+          }
+          pm[i] = __uint_as_float((unsigned)x[rr][i]);
+          pq[i] = __uint_as_float((unsigned)y[rr][i]);
         }
-        pm[i] = __uint_as_float((unsigned)x);
-        pq[i] = __uint_as_float((unsigned)y);
-      }
-      float sm_ = 0.f;
+        float sm_ = 0.f;
 #pragma unroll
-      for (int i = 0; i < SCAN_G / 32; ++i) sm_ += (float)(3 * nctab[lane + 32 * i]) * pm[i];
-      const float mean = warp_sum(sm_) / (float)(3 * R);
-      float m2 = 0.f;
+        for (int i = 0; i < SCAN_G / 32; ++i) sm_ += (float)(3 * nctab[lane + 32 * i]) * pm[i];
+        const float mean = warp_sum(sm_) / (float)(3 * R);
+        float m2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < SCAN_G / 32; ++i) {
-        const float d = pm[i] - mean;
-        m2 += pq[i] + (float)(3 * nctab[lane + 32 * i]) * d * d;
-      }
-      m2 = warp_sum(m2);
-      if (lane == 0) {
-        const float rstd = rsqrtf(m2 / (float)(3 * R) + a.eps);
-        misc[16 + b] = mean;
-        misc[32 + b] = rstd;
-        if (cta == ((t + 2) % SCAN_G)) {
-          ws.ln_stats[((size_t)1 * NB + row0 + b) * 2] = mean;
-          ws.ln_stats[((size_t)1 * NB + row0 + b) * 2 + 1] = rstd;
+        for (int i = 0; i < SCAN_G / 32; ++i) {
+          const float d = pm[i] - mean;
+          m2 += pq[i] + (float)(3 * nctab[lane + 32 * i]) * d * d;
+        }
+        m2 = warp_sum(m2);
+        if (lane == 0) {
+          const float rstd = rsqrtf(m2 / (float)(3 * R) + a.eps);
+          misc[16 + b] = mean;
+          misc[32 + b] = rstd;
+          if (cta == ((t + 2) % SCAN_G)) {
+            ws.ln_stats[((size_t)1 * NB + row0 + b) * 2] = mean;
+            ws.ln_stats[((size_t)1 * NB + row0 + b) * 2 + 1] = rstd;
+          }
         }
       }
     }
     __syncthreads();
     prof_mark(prof, 6, tlast, prof_on);
-    for (int e = tid; e < B * g.ngh * 4; e += SCAN_NT) {
-      const int b = e / (g.ngh * 4), cj = e - b * (g.ngh * 4);
-      const int gi = cj >> 2, j = cj & 3;
-      const int col = (cta + gi * SCAN_G) * 4 + j;
-      if (col >= R) continue;
+    if (sH.ok) {
+      const int b = sH.b, gi = sH.cj >> 2, j = sH.cj & 3;
       const float mu = misc[16 + b], rstd = misc[32 + b];
       float gl[3];
 #pragma unroll
-      for (int part = 0; part < 3; ++part) {
-        const float v = ACC[b * ldp + gi * 12 + part * 4 + j];
-        gl[part] = (v - mu) * rstd * a.lng_g[part * R + col] + a.lng_b[part * R + col];
-        a.g_ln[(row0 + b) * 3 * R + part * R + col] = gl[part];
-      }
+      for (int part = 0; part < 3; ++part)
+        gl[part] = (ACC[b * ldp + gi * 12 + part * 4 + j] - mu) * rstd * lg_g[part] + lg_b[part];
       const float r = sigmoidf_(gl[0]);
       const float c = tanhf(r * gl[1]);
       const float u = sigmoidf_(gl[2] - 1.f);
-      const float h = u * c + (1.f - u) * Xh[b * g.sR + col];
-      ll_store(ws.ll + L.h + ((size_t)par * MAXB + b) * R + col, h, tag);
-      a.latent[(row0 + b) * a.ld_lat + Z + col] = h;
+      const float h = u * c + (1.f - u) * hin;
+      ll_store(ws.ll + L.h + ((size_t)par * MAXB + b) * R + sH.col, h, tag);      // hand-off first, saves after
+      a.latent[(row0 + b) * a.ld_lat + Z + sH.col] = h;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) a.g_ln[(row0 + b) * 3 * R + part * R + sH.col] = gl[part];
+      a.h_in[(row0 + b) * R + sH.col] = hin;
     }
     prof_mark(prof, 7, tlast, prof_on);
 
     // ============ D: rp_pre = h W_r1[:, :R]^T + pe for the owned columns (h rows stay in Xh for the next step)
-    __syncthreads();                         // every thread is done reading the old Xh
-    ll_recv(Xh, g.sR, ws.ll + L.h + (size_t)par * MAXB * R, R, B, R, tag, tid, sp);
+    ll_recv(Xh, g.sR, ws.ll + L.h + (size_t)par * MAXB * R, R, B, R, tag, tid, sp);   // (own h_in was read above, into `hin`)
     __syncthreads();
     prof_mark(prof, 8, tlast, prof_on);
     const int ksr = product(Xh, g.sR, Wr1, g.sR, g.ngr, R, PART, ldp, 0, tid);
     __syncthreads();
-    {
-      const int nv = B * g.ngr * 4;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = tid + u * SCAN_NT;
-        if (e < nv) {
-          const int b = e / (g.ngr * 4), cj = e - b * (g.ngr * 4);
-          const int col = (cta + (cj >> 2) * SCAN_G) * 4 + (cj & 3);
-          if (col < Dr) {
-            const float v = part_sum(PART, ldp, ksr, b, cj) + pe_pref[u];
-            ll_store(ws.ll + L.r + ((size_t)par * MAXB + b) * Dr + col, v, tag);
-            a.rp_pre[(row0 + b) * Dr + col] = v;
-          }
-        }
-      }
-      for (int e = tid + 4 * SCAN_NT; e < nv; e += SCAN_NT) {   // (only when a CTA owns more than 16 columns)
-        const int b = e / (g.ngr * 4), cj = e - b * (g.ngr * 4);
-        const int col = (cta + (cj >> 2) * SCAN_G) * 4 + (cj & 3);
-        if (col < Dr) {
-          const float v = part_sum(PART, ldp, ksr, b, cj) + a.pe[(row0 + b) * Dr + col];
-          ll_store(ws.ll + L.r + ((size_t)par * MAXB + b) * Dr + col, v, tag);
-          a.rp_pre[(row0 + b) * Dr + col] = v;
-        }
-      }
+    if (sR_.ok) {
+      const float v = part_sum(PART, ldp, ksr, sR_.b, sR_.cj) + pe_pref;
+      ll_store(ws.ll + L.r + ((size_t)par * MAXB + sR_.b) * Dr + sR_.col, v, tag);
+      a.rp_pre[(row0 + sR_.b) * Dr + sR_.col] = v;
     }
     prof_mark(prof, 9, tlast, prof_on);
 
@@ -651,22 +668,39 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       ll_recv(Xx, xxs, ws.ll + L.r + ((size_t)par * MAXB + rb) * Dr, Dr, nr, Dr, tag, tid, sp);
       __syncthreads();
       prof_mark(prof, 10, tlast, prof_on);
-      for (int bb = wid; bb < nr; bb += SCAN_NW) {
+      {
+        // LayerNorm + SiLU with all warps: wpr warps share a row (nrp = rows rounded up to a power of two)
+        const int nrp = nr <= 1 ? 1 : (nr <= 2 ? 2 : (nr <= 4 ? 4 : 8));
+        const int wpr = SCAN_NW / nrp, bb = wid / wpr, wi = wid - bb * wpr;
         float* xr = Xx + bb * xxs;
         float s = 0.f;
-        for (int k = lane; k < Dr; k += 32) s += xr[k];
-        const float mu = warp_sum(s) / (float)Dr;
+        if (bb < nr)
+          for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) s += xr[k];
+        s = warp_sum(s);
+        if (lane == 0) misc[48 + wid] = s;
+        __syncthreads();
+        float mu = 0.f;
+        for (int i = 0; i < wpr; ++i) mu += misc[48 + bb * wpr + i];
+        mu /= (float)Dr;
         float v = 0.f;
-        for (int k = lane; k < Dr; k += 32) { const float d = xr[k] - mu; v = fmaf(d, d, v); }
-        const float rstd = rsqrtf(warp_sum(v) / (float)Dr + a.eps);
-        for (int k = lane; k < Dr; k += 32) {
-          const float o = fsilu((xr[k] - mu) * rstd * a.lnr_g[k] + a.lnr_b[k]);
-          xr[k] = o;
-          if (gq == 0) a.rp_act[(row0 + rb + bb) * Dr + k] = o;
-        }
-        if (gq == 0 && lane == 0) {
-          ws.ln_stats[((size_t)2 * NB + row0 + rb + bb) * 2] = mu;
-          ws.ln_stats[((size_t)2 * NB + row0 + rb + bb) * 2 + 1] = rstd;
+        if (bb < nr)
+          for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) { const float d = xr[k] - mu; v = fmaf(d, d, v); }
+        v = warp_sum(v);
+        if (lane == 0) misc[56 + wid] = v;
+        __syncthreads();
+        float var = 0.f;
+        for (int i = 0; i < wpr; ++i) var += misc[56 + bb * wpr + i];
+        const float rstd = rsqrtf(var / (float)Dr + a.eps);
+        if (bb < nr) {
+          for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) {
+            const float o = fsilu((xr[k] - mu) * rstd * LNRG[k] + LNRB[k]);
+            xr[k] = o;
+            if (gq == 0) a.rp_act[(row0 + rb + bb) * Dr + k] = o;
+          }
+          if (gq == 0 && wi == 0 && lane == 0) {
+            ws.ln_stats[((size_t)2 * NB + row0 + rb + bb) * 2] = mu;
+            ws.ln_stats[((size_t)2 * NB + row0 + rb + bb) * 2 + 1] = rstd;
+          }
         }
       }
       __syncthreads();
@@ -693,33 +727,23 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       }
       __syncthreads();
       // one warp per row: the D classes of the group live on the lanes (D <= 32)
-      for (int bb = wid; bb < nr; bb += SCAN_NW) {
-        const int b = rb + bb;
+      if (wid < nr) {
+        const int bb = wid, b = rb + bb;
         const bool on = lane < D;
         float lg = 0.f;
         for (int s2 = 0; s2 < SCAN_NW; ++s2) lg += PART[((size_t)s2 * MAXRPU + bb) * 32 + lane];
-        const float raw = on ? lg + a.b_r2[gq * D + lane] : -INFINITY;
-        const size_t o = (row0 + b) * Z + (size_t)gq * D + lane;
+        const float raw = on ? lg + bias2 : -INFINITY;
         const float mx = warp_max(raw);
         const float ex = on ? expf(raw - mx) : 0.f;
         const float se = warp_sum(ex);
-        float l = raw;
-        if (a.unimix > 0.f && on) {
-          const float pmx = (1.f - a.unimix) * (ex / se) + a.unimix / (float)D;
-          l = logf(fminf(fmaxf(pmx, kFp32Eps), 1.f - kFp32Eps));
+        // unimix (agent.py:437-449); Categorical(logits=l).probs is proportional to the clamped mixture pmc, so the draw
+        // argmax(probs / q) (torch.multinomial) equals argmax(pmc / q): the normaliser is common to all classes
+        float pmc = ex / se, l = raw;
+        if (a.unimix > 0.f) {
+          pmc = fminf(fmaxf((1.f - a.unimix) * pmc + a.unimix / (float)D, kFp32Eps), 1.f - kFp32Eps);
+          l = logf(pmc);
         }
-        if (on) {
-          a.post_raw[o] = raw;
-          a.post_mix[o] = l;
-        }
-        // torch Categorical: lg = l - logsumexp(l); probs = softmax(lg); sample = argmax(probs / q)
-        const float lmx = warp_max(on ? l : -INFINITY);
-        const float lse = lmx + logf(warp_sum(on ? expf(l - lmx) : 0.f));
-        const float lgmax = warp_max(on ? l - lse : -INFINITY);
-        const float pe_ = on ? expf(l - lse - lgmax) : 0.f;
-        const float psum = warp_sum(pe_);
-        const float q = (bb == wid) ? noise_pref : (on ? a.noise[o] : 1.f);
-        float best = on ? (pe_ / psum) / q : -INFINITY;
+        float best = on ? pmc / noise_pref : -INFINITY;
         int besti = on ? lane : 0x7fffffff;
 #pragma unroll
         for (int s2 = 16; s2 > 0; s2 >>= 1) {
@@ -727,17 +751,17 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
           const int oi = __shfl_xor_sync(0xffffffffu, besti, s2);
           if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
         }
-        if (lane == 0) {
-          ll_store(ws.ll + L.z + ((size_t)par * MAXB + b) * S + gq, __uint_as_float((unsigned)besti), tag);
-          ws.zidx[(row0 + b) * S + gq] = besti;
-        }
+        if (lane == 0) ll_store(ws.ll + L.z + ((size_t)par * MAXB + b) * S + gq, __uint_as_float((unsigned)besti), tag);
+        // saves after the hand-off
+        const size_t o = (row0 + b) * Z + (size_t)gq * D + lane;
+        if (lane == 0) ws.zidx[(row0 + b) * S + gq] = besti;
         if (on) {
-          a.latent[(row0 + b) * a.ld_lat + (size_t)gq * D + lane] = (lane == besti) ? 1.f : 0.f;
-          if (t + 1 < T) {   // z_in of the next step: (1-f) z_t + f z0 (agent.py:430), both one-hot
-            const float fn = a.first[row0 + B + b];
-            a.z_in[(row0 + B + b) * Z + (size_t)gq * D + lane] =
-                (1.f - fn) * ((lane == besti) ? 1.f : 0.f) + fn * ((z0idx[gq] == lane) ? 1.f : 0.f);
-          }
+          a.post_raw[o] = raw;
+          a.post_mix[o] = l;
+          const float zt = (lane == besti) ? 1.f : 0.f;
+          a.latent[(row0 + b) * a.ld_lat + (size_t)gq * D + lane] = zt;
+          if (t + 1 < T)     // z_in of the next step: (1-f) z_t + f z0 (agent.py:430), both one-hot
+            a.z_in[(row0 + B + b) * Z + (size_t)gq * D + lane] = (1.f - fnext) * zt + fnext * ((z0idx[gq] == lane) ? 1.f : 0.f);
         }
       }
       prof_mark(prof, 11, tlast, prof_on);
@@ -768,27 +792,8 @@ struct GeoB {
   int wgst, winst;              // smem row strides of the W_g^T slice (3 parts of sR) and the unit's W_in slice
   int nsplit, rpu, unit_g, unit_r0, unit_nr;
   int ldp;
-  int oW2, oW1, oWg, oWin, oX, oPart, oAcc, oDhin, oDhc, oDh0, oWs, oPre, oMisc, total;
+  int oW2, oW1, oWg, oWin, oX, oPart, oAcc, oSt, oDhc, oDh0, oWs, oMisc, total;
 };
-
-// per-step prefetch area (floats): small chain-independent inputs of the owned columns
-struct PreB {
-  int rp, gl, gp, hin, xp, dlh, qr, qg, n;
-};
-__host__ __device__ inline PreB make_pre(int mh, int mx, int mr) {
-  PreB p;
-  int o = 0;
-  p.rp = o;  o += MAXB * mr * 4;        // rp_pre
-  p.gl = o;  o += MAXB * mh * 12;       // g_ln
-  p.gp = o;  o += MAXB * mh * 12;       // g_pre
-  p.hin = o; o += MAXB * mh * 4;        // h_in
-  p.xp = o;  o += MAXB * mx * 4;        // x_pre
-  p.dlh = o; o += MAXB * mh * 4;        // d_latent (h part)
-  p.qr = o;  o += MAXB * mh * 4;        // q_r
-  p.qg = o;  o += MAXB * (mh + mx) * 4; // q_g
-  p.n = o;
-  return p;
-}
 
 __host__ __device__ inline GeoB make_geo_b(const b200rl_rssm_scan_args& a, int cta) {
   GeoB g;
@@ -797,7 +802,7 @@ __host__ __device__ inline GeoB make_geo_b(const b200rl_rssm_scan_args& a, int c
   g.ngx = owned_groups(a.Dx, cta);
   g.ngr = owned_groups(a.Dr, cta);
   g.sZ = r4(Z); g.sR = r4(a.R); g.sDx = r4(a.Dx); g.sDr = r4(a.Dr);
-  g.xw = imax(imax(g.sZ, g.sR), imax(g.sDx, g.sDr));
+  g.xw = imax(imax(g.sZ, 2 * g.sR), imax(g.sDx, g.sDr));
   g.wgst = 3 * g.sR;
   g.winst = g.sDx + 4;
   g.nsplit = imax(1, imin(a.B, SCAN_G / a.S));
@@ -819,39 +824,60 @@ __host__ __device__ inline GeoB make_geo_b(const b200rl_rssm_scan_args& a, int c
   g.oX = o;    o += MAXB * g.xw;
   g.oPart = o; o += imax(SCAN_NW * MAXB * g.ldp, SCAN_NW * MAXRPU * 32);
   g.oAcc = o;  o += MAXB * g.ldp;
-  g.oDhin = o; o += MAXB * mh * 4;
-  g.oDhc = o;  o += MAXB * mh * 4;
-  g.oDh0 = o;  o += mh * 4;
+  g.oSt = o;   o += 2 * MAXB * imax(imax(mh * 12, mx * 4), imax(mr * 4, 4));   // (dxh, dxh*xh) staging for the row sums
+  g.oDhc = o;  o += MAXB * imax(mh * 4, 4);
+  g.oDh0 = o;  o += imax(mh * 4, 4);
   g.oWs = o;   o += mh * 4 + (mh + mx) * 4 + 32;   // column sums of the weight slices
-  g.oPre = o;  o += make_pre(mh, mx, mr).n;
   g.oMisc = o; o += 16 * MAXB + 64;
   g.total = o;
   return g;
 }
 
-// (sum dxh, sum dxh*xh) / n of the rows [r0, r0+nr) from the per-CTA partials; one warp per row, fixed summation order
+// (sum dxh, sum dxh*xh) / n of the rows [r0, r0+nr) from the per-CTA partials; one warp per row (two rows in flight per
+// warp), fixed summation order
 __device__ __forceinline__ void recv_row_sums(const u64* base, int par, int r0, int nr, unsigned tag, float inv, float* out1,
                                               float* out2, int tid, Spin& sp) {
   const int lane = tid & 31, wid = tid >> 5;
-  for (int bb = wid; bb < nr; bb += SCAN_NW) {
-    const int b = r0 + bb;
-    float v0 = 0.f, v1 = 0.f;
-    u64 x[SCAN_G / 32], y[SCAN_G / 32];
+  for (int bb0 = wid; bb0 < nr; bb0 += 2 * SCAN_NW) {
+    u64 x[2][SCAN_G / 32], y[2][SCAN_G / 32];
 #pragma unroll
-    for (int i = 0; i < SCAN_G / 32; ++i)
-      ll_load2(base + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2, x[i], y[i]);
+    for (int rr = 0; rr < 2; ++rr) {
+      const int bb = bb0 + rr * SCAN_NW;
+      if (bb < nr)
 #pragma unroll
-    for (int i = 0; i < SCAN_G / 32; ++i) {
-      const u64* p = base + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2;
-      while ((unsigned)(x[i] >> 32) != tag || (unsigned)(y[i] >> 32) != tag) {
-        if (sp.fail()) break;
-        ll_load2(p, x[i], y[i]);
-      }
-      v0 += __uint_as_float((unsigned)x[i]);
-      v1 += __uint_as_float((unsigned)y[i]);
+        for (int i = 0; i < SCAN_G / 32; ++i)
+          ll_load2(base + (((size_t)par * MAXB + r0 + bb) * SCAN_G + lane + 32 * i) * 2, x[rr][i], y[rr][i]);
     }
-    v0 = warp_sum(v0); v1 = warp_sum(v1);
-    if (lane == 0) { out1[b] = v0 * inv; out2[b] = v1 * inv; }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int bb = bb0 + rr * SCAN_NW;
+      if (bb >= nr) continue;
+      const int b = r0 + bb;
+      float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < SCAN_G / 32; ++i) {
+        const u64* p = base + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2;
+        while ((unsigned)(x[rr][i] >> 32) != tag || (unsigned)(y[rr][i] >> 32) != tag) {
+          if (sp.fail()) break;
+          ll_load2(p, x[rr][i], y[rr][i]);
+        }
+        v0 += __uint_as_float((unsigned)x[rr][i]);
+        v1 += __uint_as_float((unsigned)y[rr][i]);
+      }
+      v0 = warp_sum(v0); v1 = warp_sum(v1);
+      if (lane == 0) { out1[b] = v0 * inv; out2[b] = v1 * inv; }
+    }
+  }
+}
+
+// per-row sums of the staged (dxh, dxh*xh) pairs of this CTA's columns -> LL partial for every row
+__device__ __forceinline__ void send_row_sums(const float* ST, int ncols, int B, u64* base, int par, int cta, unsigned tag, int tid) {
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int b = wid; b < B; b += SCAN_NW) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < ncols; c += 32) { s1 += ST[(b * ncols + c) * 2]; s2 += ST[(b * ncols + c) * 2 + 1]; }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) ll_store2(base + (((size_t)par * MAXB + b) * SCAN_G + cta) * 2, s1, s2, tag);
   }
 }
 
@@ -865,8 +891,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
   const GeoB g = make_geo_b(a, cta);
   const Workspace ws = carve(a.workspace, T, B, S, D, Dx, R, Dr);
   const LLGeo L = make_ll(S, Dx, R, Dr, Z);
-  const int mh = owned_groups(R, 0), mx = owned_groups(Dx, 0), mr = owned_groups(Dr, 0);
-  const PreB P = make_pre(mh, mx, mr);
+  const int mh = owned_groups(R, 0), mx = owned_groups(Dx, 0);
   float* W2T = sm + g.oW2;      // [ngr*4][sZ]
   float* W1T = sm + g.oW1;      // [ngh*4][sDr]
   float* WgT = sm + g.oWg;      // [(ngh+ngx)*4][3*sR]
@@ -874,13 +899,12 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
   float* X = sm + g.oX;         // [MAXB][xw]
   float* PART = sm + g.oPart;
   float* ACC = sm + g.oAcc;     // [MAXB][ldp]
-  float* DHIN = sm + g.oDhin;   // [MAXB][nh4] dh wrt h_in through the gate
+  float* ST = sm + g.oSt;       // [(b, col)][2] staged (dxh, dxh*xh)
   float* DHC = sm + g.oDhc;     // [MAXB][nh4] dh carried to step t-1
   float* DH0 = sm + g.oDh0;     // [nh4] accumulated grad of tanh(initial_recurrent_state)
   float* WS1 = sm + g.oWs;      // [nh4] column sums of the W_r1 slice
   float* WSG = WS1 + mh * 4;    // [(ngh+ngx)*4] column sums of the W_g slice
   float* WSI = WSG + (mh + mx) * 4;   // [D] column sums of the unit's W_in slice
-  float* PRE = sm + g.oPre;
   float* misc = sm + g.oMisc;   // [0,16) first(t); [16,32) first(t+1); [32,48) S1; [48,64) S2; [64,..) per-row (mu, rstd) x3
   float* S1 = misc + 32;
   float* S2 = misc + 48;
@@ -936,6 +960,19 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
       if (lane == 0) WSI[d] = s;
     }
   __syncthreads();
+  // fixed element assignments and per-element parameters (no index arithmetic / parameter loads inside the time loop)
+  const Slot sR_ = make_slot(tid, nr4, B, cta, Dr);          // d_rp_act element
+  const Slot sH = make_slot(tid, nh4, B, cta, R);            // dh element
+  const Slot sX = make_slot(tid, nx4, B, cta, Dx);           // d_x_act element
+  const float gam_r = sR_.ok ? a.lnr_g[sR_.col] : 0.f, bet_r = sR_.ok ? a.lnr_b[sR_.col] : 0.f;
+  const float gam_x = sX.ok ? a.lnx_g[sX.col] : 0.f, bet_x = sX.ok ? a.lnx_b[sX.col] : 0.f;
+  float gam_g[3] = {0.f, 0.f, 0.f};
+  if (sH.ok)
+#pragma unroll
+    for (int part = 0; part < 3; ++part) gam_g[part] = a.lng_g[part * R + sH.col];
+  const float ws1 = sH.ok ? WS1[sH.cj] : 0.f, wsgh = sH.ok ? WSG[sH.cj] : 0.f, wsgx = sX.ok ? WSG[nh4 + sX.cj] : 0.f;
+  const float wsi = (unit && lane < D) ? WSI[lane] : 0.f;
+  float dh0_acc = 0.f;                                        // (threads tid < nh4) accumulated over rows in fixed order
   prof_mark(prof, 16, tlast, prof_on);
 
   for (int t = T - 1; t >= 0; --t) {
@@ -944,7 +981,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     const unsigned tag = (unsigned)bt + 1u;
     const bool last = (t == T - 1);
 
-    // ---------------- step-start prefetch of chain-independent inputs (owned columns only)
+    // ---------------- step-start prefetch of chain-independent inputs (registers of the element's thread)
     if (tid < MAXB) {
       misc[tid] = (tid < B) ? a.first[row0 + tid] : 0.f;
       misc[16 + tid] = (tid < B && !last) ? a.first[row0 + B + tid] : 0.f;
@@ -955,30 +992,29 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     }
     if (!last)
       for (int e = tid; e < B * 2; e += SCAN_NT) LNX1[e] = ws.ln_stats[((size_t)0 * NB + row0 + B) * 2 + e];
-    for (int e = tid; e < B * nr4; e += SCAN_NT) {
-      const int b = e / nr4, cj = e - b * nr4;
-      const int col = (cta + (cj >> 2) * SCAN_G) * 4 + (cj & 3);
-      PRE[P.rp + e] = (col < Dr) ? a.rp_pre[(row0 + b) * Dr + col] : 0.f;
-    }
-    for (int e = tid; e < B * nh4; e += SCAN_NT) {
-      const int b = e / nh4, cj = e - b * nh4;
-      const int col = (cta + (cj >> 2) * SCAN_G) * 4 + (cj & 3);
-      const bool ok = col < R;
-      PRE[P.hin + e] = ok ? a.h_in[(row0 + b) * R + col] : 0.f;
-      PRE[P.dlh + e] = ok ? q.d_latent[(row0 + b) * a.ld_lat + Z + col] : 0.f;
-      PRE[P.qr + e] = ok ? q.q_r[(row0 + b) * R + col] : 0.f;
-      PRE[P.qg + b * (nh4 + nx4) + cj] = ok ? q.q_g[(row0 + b) * KG + col] : 0.f;
+    const float p_rp = sR_.ok ? a.rp_pre[(row0 + sR_.b) * Dr + sR_.col] : 0.f;
+    float p_hin = 0.f, p_dlh = 0.f, p_qr = 0.f, p_qgh = 0.f, p_gl[3] = {0.f, 0.f, 0.f}, p_gp[3] = {0.f, 0.f, 0.f};
+    if (sH.ok) {
+      p_hin = a.h_in[(row0 + sH.b) * R + sH.col];
+      p_dlh = q.d_latent[(row0 + sH.b) * a.ld_lat + Z + sH.col];
+      p_qr = q.q_r[(row0 + sH.b) * R + sH.col];
+      p_qgh = q.q_g[(row0 + sH.b) * KG + sH.col];
 #pragma unroll
       for (int part = 0; part < 3; ++part) {
-        PRE[P.gl + (b * 3 + part) * nh4 + cj] = ok ? a.g_ln[(row0 + b) * 3 * R + part * R + col] : 0.f;
-        PRE[P.gp + (b * 3 + part) * nh4 + cj] = ok ? a.g_pre[(row0 + b) * 3 * R + part * R + col] : 0.f;
+        p_gl[part] = a.g_ln[(row0 + sH.b) * 3 * R + part * R + sH.col];
+        p_gp[part] = a.g_pre[(row0 + sH.b) * 3 * R + part * R + sH.col];
       }
     }
-    for (int e = tid; e < B * nx4; e += SCAN_NT) {
-      const int b = e / nx4, cj = e - b * nx4;
-      const int col = (cta + (cj >> 2) * SCAN_G) * 4 + (cj & 3);
-      PRE[P.xp + e] = (col < Dx) ? a.x_pre[(row0 + b) * Dx + col] : 0.f;
-      PRE[P.qg + b * (nh4 + nx4) + nh4 + cj] = (col < Dx) ? q.q_g[(row0 + b) * KG + R + col] : 0.f;
+    const float p_xp = sX.ok ? a.x_pre[(row0 + sX.b) * Dx + sX.col] : 0.f;
+    const float p_qgx = sX.ok ? q.q_g[(row0 + sX.b) * KG + R + sX.col] : 0.f;
+    // (unit) per-row inputs of the group: one warp per row
+    float u_dl = 0.f, u_dmix = 0.f, u_raw = -INFINITY, u_qx = 0.f;
+    if (unit && wid < g.unit_nr && lane < D) {
+      const size_t o = (row0 + g.unit_r0 + wid) * Z + (size_t)g.unit_g * D + lane;
+      u_dl = q.d_latent[(row0 + g.unit_r0 + wid) * a.ld_lat + (size_t)g.unit_g * D + lane];
+      u_dmix = q.d_post_mix[o];
+      u_raw = a.post_raw[o];
+      if (!last) u_qx = q.q_x[(row0 + B + g.unit_r0 + wid) * Z + (size_t)g.unit_g * D + lane];
     }
     __syncthreads();
     const float* fl = misc;
@@ -1011,49 +1047,40 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
           if (i < nr) PART[((size_t)wid * MAXRPU + i) * 32 + lane] = acc[i];
         __syncthreads();
       }
-      for (int bb = wid; bb < nr; bb += SCAN_NW) {
-        const int b = rb + bb;
+      if (wid < nr) {
+        const int bb = wid, b = rb + bb;
         const bool on = lane < D;
-        const size_t o = (row0 + b) * Z + (size_t)gq * D + lane;
-        float dz = on ? q.d_latent[(row0 + b) * a.ld_lat + (size_t)gq * D + lane] : 0.f;
+        float dz = u_dl;
         if (!last) {
           float p1 = 0.f;
           for (int s2 = 0; s2 < SCAN_NW; ++s2) p1 += PART[((size_t)s2 * MAXRPU + bb) * 32 + lane];
           if (on) {
             const float mu = LNX1[b * 2], rstd = LNX1[b * 2 + 1];
-            const float wsum = WSI[lane];
-            const float p2 = rstd * (q.q_x[(row0 + B + b) * Z + (size_t)gq * D + lane] - mu * wsum);
-            const float dzin = rstd * (p1 - S1[b] * wsum - S2[b] * p2);
-            dz += (1.f - fl[16 + b]) * dzin;
+            const float p2 = rstd * (u_qx - mu * wsi);
+            dz += (1.f - fl[16 + b]) * rstd * (p1 - S1[b] * wsi - S2[b] * p2);
           }
         }
-        const float raw = on ? a.post_raw[o] : -INFINITY;
-        const float mx_ = warp_max(raw);
-        const float ex = on ? expf(raw - mx_) : 0.f;
-        const float se = warp_sum(ex);
-        const float sft = ex / se;
-        float pmx = 0.f, l = raw;
-        if (a.unimix > 0.f && on) {
-          pmx = (1.f - a.unimix) * sft + a.unimix / (float)D;
-          l = logf(fminf(fmaxf(pmx, kFp32Eps), 1.f - kFp32Eps));
-        }
-        float gg = on ? q.d_post_mix[o] : 0.f;
-        {
-          const float lmx = warp_max(on ? l : -INFINITY);
-          const float lse = lmx + logf(warp_sum(on ? expf(l - lmx) : 0.f));
-          const float p = on ? expf(l - lse) : 0.f;
-          const float pdz = warp_sum(p * dz);
-          gg += p * (dz - pdz);
-        }
+        const float mx_ = warp_max(u_raw);
+        const float ex = on ? expf(u_raw - mx_) : 0.f;
+        const float sft = ex / warp_sum(ex);
+        float gg = u_dmix;
         if (a.unimix > 0.f) {
+          const float pmx = (1.f - a.unimix) * sft + a.unimix / (float)D;
+          const float pmc = on ? fminf(fmaxf(pmx, kFp32Eps), 1.f - kFp32Eps) : 0.f;
+          const float p = pmc / warp_sum(pmc);          // Categorical(logits = log pmc).probs
+          const float pdz = warp_sum(p * dz);
+          gg += p * (dz - pdz);                          // straight-through sample: d/dlogits of probs . dz
           const bool inside = on && pmx >= kFp32Eps && pmx <= 1.f - kFp32Eps;
           const float ds = inside ? gg * (1.f - a.unimix) / pmx : 0.f;
           const float sds = warp_sum(sft * ds);
           gg = sft * (ds - sds);
+        } else {
+          const float pdz = warp_sum(sft * dz);
+          gg += sft * (dz - pdz);
         }
         if (on) {
-          q.d_post_raw[o] = gg;
           ll_store(ws.ll + L.a + ((size_t)par * MAXB + b) * Z + (size_t)gq * D + lane, gg, tag);
+          q.d_post_raw[(row0 + b) * Z + (size_t)gq * D + lane] = gg;
         }
       }
       prof_mark(prof, 18, tlast, prof_on);
@@ -1066,26 +1093,22 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     prof_mark(prof, 19, tlast, prof_on);
     const int ks2 = product(X, xw, W2T, g.sZ, g.ngr, Z, PART, ldp, 0, tid);
     __syncthreads();
-    for (int b = wid; b < B; b += SCAN_NW) {
-      float s1 = 0.f, s2 = 0.f;
-      for (int c = lane; c < nr4; c += 32) {
-        const int col = (cta + (c >> 2) * SCAN_G) * 4 + (c & 3);
-        if (col < Dr) {
-          const float dact = part_sum(PART, ldp, ks2, b, c);
-          q.d_rp_act[(row0 + b) * Dr + col] = dact;
-          const float xh = (PRE[P.rp + b * nr4 + c] - LNS[(2 * MAXB + b) * 2]) * LNS[(2 * MAXB + b) * 2 + 1];
-          const float gam = a.lnr_g[col];
-          const float ln = xh * gam + a.lnr_b[col];
-          const float sg = sigmoidf_(ln);
-          const float dxh = dact * sg * (1.f + ln * (1.f - sg)) * gam;
-          ll_store(ws.ll + L.b + ((size_t)par * MAXB + b) * Dr + col, dxh, tag);
-          s1 += dxh;
-          s2 = fmaf(dxh, xh, s2);
-        }
-      }
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) ll_store2(ws.ll + L.sb + (((size_t)par * MAXB + b) * SCAN_G + cta) * 2, s1, s2, tag);
+    float dact_r = 0.f;
+    if (sR_.ok) {
+      dact_r = part_sum(PART, ldp, ks2, sR_.b, sR_.cj);
+      const float xh = (p_rp - LNS[(2 * MAXB + sR_.b) * 2]) * LNS[(2 * MAXB + sR_.b) * 2 + 1];
+      const float ln = xh * gam_r + bet_r;
+      const float sg = sigmoidf_(ln);
+      const float dxh = dact_r * sg * (1.f + ln * (1.f - sg)) * gam_r;
+      ll_store(ws.ll + L.b + ((size_t)par * MAXB + sR_.b) * Dr + sR_.col, dxh, tag);
+      ST[(sR_.b * nr4 + sR_.cj) * 2] = dxh;
+      ST[(sR_.b * nr4 + sR_.cj) * 2 + 1] = dxh * xh;
+    } else if (tid < B * nr4) {
+      ST[tid * 2] = 0.f; ST[tid * 2 + 1] = 0.f;
     }
+    __syncthreads();
+    send_row_sums(ST, nr4, B, ws.ll + L.sb, par, cta, tag, tid);
+    if (sR_.ok) q.d_rp_act[(row0 + sR_.b) * Dr + sR_.col] = dact_r;
     prof_mark(prof, 20, tlast, prof_on);
 
     // ============ R: dh = d_latent_h + carry + d_rp_pre W_r1h ; GRU gate backward ; dxh of the GRU LayerNorm
@@ -1096,112 +1119,107 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     prof_mark(prof, 21, tlast, prof_on);
     const int ks1 = product(X, xw, W1T, g.sDr, g.ngh, Dr, PART, ldp, 0, tid);
     __syncthreads();
-    for (int b = wid; b < B; b += SCAN_NW) {
-      float s1 = 0.f, s2 = 0.f;
+    float dhin_gate = 0.f, dgl[3] = {0.f, 0.f, 0.f};
+    if (sH.ok) {
+      const int b = sH.b;
       const float mur = LNS[(2 * MAXB + b) * 2], rstdr = LNS[(2 * MAXB + b) * 2 + 1];
       const float mug = LNS[(1 * MAXB + b) * 2], rstdg = LNS[(1 * MAXB + b) * 2 + 1];
-      for (int c = lane; c < nh4; c += 32) {
-        const int col = (cta + (c >> 2) * SCAN_G) * 4 + (c & 3);
-        float dhin = 0.f;
-        if (col < R) {
-          const float p1 = part_sum(PART, ldp, ks1, b, c);
-          const float wsum = WS1[c];
-          const float p2 = rstdr * (PRE[P.qr + b * nh4 + c] - mur * wsum);
-          float dh = PRE[P.dlh + b * nh4 + c] + rstdr * (p1 - S1[b] * wsum - S2[b] * p2);
-          if (!last) dh += DHC[b * nh4 + c];
-          const float gr = PRE[P.gl + (b * 3 + 0) * nh4 + c], gc = PRE[P.gl + (b * 3 + 1) * nh4 + c],
-                      gu = PRE[P.gl + (b * 3 + 2) * nh4 + c];
-          const float r = sigmoidf_(gr), cnd = tanhf(r * gc), u = sigmoidf_(gu - 1.f);
-          const float hin = PRE[P.hin + b * nh4 + c];
-          const float du = dh * (cnd - hin);
-          const float drc = dh * u * (1.f - cnd * cnd);
-          float dgl[3];
-          dgl[0] = drc * gc * r * (1.f - r);
-          dgl[1] = drc * r;
-          dgl[2] = du * u * (1.f - u);
-          dhin = dh * (1.f - u);
+      const float p1 = part_sum(PART, ldp, ks1, b, sH.cj);
+      const float p2 = rstdr * (p_qr - mur * ws1);
+      float dh = p_dlh + rstdr * (p1 - S1[b] * ws1 - S2[b] * p2);
+      if (!last) dh += DHC[b * nh4 + sH.cj];
+      const float r = sigmoidf_(p_gl[0]), cnd = tanhf(r * p_gl[1]), u = sigmoidf_(p_gl[2] - 1.f);
+      const float du = dh * (cnd - p_hin);
+      const float drc = dh * u * (1.f - cnd * cnd);
+      dgl[0] = drc * p_gl[1] * r * (1.f - r);
+      dgl[1] = drc * r;
+      dgl[2] = du * u * (1.f - u);
+      dhin_gate = dh * (1.f - u);
 #pragma unroll
-          for (int part = 0; part < 3; ++part) {
-            q.d_g_ln[(row0 + b) * 3 * R + part * R + col] = dgl[part];
-            const float xh = (PRE[P.gp + (b * 3 + part) * nh4 + c] - mug) * rstdg;
-            const float dxh = dgl[part] * a.lng_g[part * R + col];
-            ll_store(ws.ll + L.c + ((size_t)par * MAXB + b) * 3 * R + (size_t)part * R + col, dxh, tag);
-            s1 += dxh;
-            s2 = fmaf(dxh, xh, s2);
-          }
-        }
-        DHIN[b * nh4 + c] = dhin;
+      for (int part = 0; part < 3; ++part) {
+        const float xh = (p_gp[part] - mug) * rstdg;
+        const float dxh = dgl[part] * gam_g[part];
+        ll_store(ws.ll + L.c + ((size_t)par * MAXB + b) * 3 * R + (size_t)part * R + sH.col, dxh, tag);
+        ST[(b * (3 * nh4) + part * nh4 + sH.cj) * 2] = dxh;
+        ST[(b * (3 * nh4) + part * nh4 + sH.cj) * 2 + 1] = dxh * xh;
       }
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) ll_store2(ws.ll + L.sc + (((size_t)par * MAXB + b) * SCAN_G + cta) * 2, s1, s2, tag);
+    } else if (tid < B * nh4) {
+      const int b = tid / imax(nh4, 1), cj = tid - b * nh4;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        ST[(b * (3 * nh4) + part * nh4 + cj) * 2] = 0.f;
+        ST[(b * (3 * nh4) + part * nh4 + cj) * 2 + 1] = 0.f;
+      }
     }
+    __syncthreads();
+    send_row_sums(ST, 3 * nh4, B, ws.ll + L.sc, par, cta, tag, tid);
+    if (sH.ok)
+#pragma unroll
+      for (int part = 0; part < 3; ++part) q.d_g_ln[(row0 + sH.b) * 3 * R + part * R + sH.col] = dgl[part];
     prof_mark(prof, 22, tlast, prof_on);
 
-    // ============ S: [dh_in, d_x_act] = d_g_pre W_g for the owned columns (K = 3R in three parts); x-LN dxh
-    for (int e = tid; e < MAXB * ldp; e += SCAN_NT) ACC[e] = 0.f;
-    for (int part = 0; part < 3; ++part) {
-      __syncthreads();
-      ll_recv(X, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)part * R, 3 * R, B, R, tag, tid, sp);
-      __syncthreads();
-      const int ksg = product(X, xw, WgT + part * g.sR, g.wgst, g.ngh + g.ngx, R, PART, ldp, 0, tid);
-      __syncthreads();
-      for (int e = tid; e < B * (nh4 + nx4); e += SCAN_NT) {
-        const int b = e / (nh4 + nx4), c = e - b * (nh4 + nx4);
-        ACC[b * ldp + c] += part_sum(PART, ldp, ksg, b, c);
-      }
-    }
+    // ============ S: [dh_in, d_x_act] = d_g_pre W_g for the owned columns (K = 3R: parts r,c together, then u)
+    __syncthreads();
+    for (int part = 0; part < 2; ++part)
+      ll_recv(X + part * g.sR, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)part * R, 3 * R, B, R, tag, tid, sp);
+    __syncthreads();
+    const int ksa = product(X, xw, WgT, g.wgst, g.ngh + g.ngx, 2 * g.sR, PART, ldp, 0, tid);
+    __syncthreads();
+    float acc_h = sH.ok ? part_sum(PART, ldp, ksa, sH.b, sH.cj) : 0.f;
+    float acc_x = sX.ok ? part_sum(PART, ldp, ksa, sX.b, nh4 + sX.cj) : 0.f;
+    __syncthreads();
+    ll_recv(X, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)2 * R, 3 * R, B, R, tag, tid, sp);
     recv_row_sums(ws.ll + L.sc, par, 0, B, tag, 1.f / (float)(3 * R), S1, S2, tid, sp);
     __syncthreads();
+    const int ksb = product(X, xw, WgT + 2 * g.sR, g.wgst, g.ngh + g.ngx, R, PART, ldp, 0, tid);
+    __syncthreads();
     prof_mark(prof, 23, tlast, prof_on);
-    for (int b = wid; b < B; b += SCAN_NW) {
-      const float f = fl[b];
+    float dact_x = 0.f;
+    if (sX.ok) {
+      const int b = sX.b;
+      acc_x += part_sum(PART, ldp, ksb, b, nh4 + sX.cj);
       const float mug = LNS[(1 * MAXB + b) * 2], rstdg = LNS[(1 * MAXB + b) * 2 + 1];
       const float mux = LNS[(0 * MAXB + b) * 2], rstdx = LNS[(0 * MAXB + b) * 2 + 1];
-      for (int c = lane; c < nh4; c += 32) {
-        const int col = (cta + (c >> 2) * SCAN_G) * 4 + (c & 3);
-        if (col < R) {
-          const float wsum = WSG[c];
-          const float p2 = rstdg * (PRE[P.qg + b * (nh4 + nx4) + c] - mug * wsum);
-          const float dhin = DHIN[b * nh4 + c] + rstdg * (ACC[b * ldp + c] - S1[b] * wsum - S2[b] * p2);
-          DHC[b * nh4 + c] = (1.f - f) * dhin;          // carried to step t-1 (agent.py:428 mask)
-          DHIN[b * nh4 + c] = f * dhin;                 // grad of tanh(initial_recurrent_state), summed below
-        }
-      }
-      float s1 = 0.f, s2 = 0.f;
-      for (int c = lane; c < nx4; c += 32) {
-        const int col = (cta + (c >> 2) * SCAN_G) * 4 + (c & 3);
-        if (col < Dx) {
-          const float wsum = WSG[nh4 + c];
-          const float p2 = rstdg * (PRE[P.qg + b * (nh4 + nx4) + nh4 + c] - mug * wsum);
-          const float dact = rstdg * (ACC[b * ldp + nh4 + c] - S1[b] * wsum - S2[b] * p2);
-          q.d_x_act[(row0 + b) * Dx + col] = dact;
-          const float xh = (PRE[P.xp + b * nx4 + c] - mux) * rstdx;
-          const float gam = a.lnx_g[col];
-          const float ln = xh * gam + a.lnx_b[col];
-          const float sg = sigmoidf_(ln);
-          const float dxh = dact * sg * (1.f + ln * (1.f - sg)) * gam;
-          ll_store(ws.ll + L.d + ((size_t)par * MAXB + b) * Dx + col, dxh, tag);
-          s1 += dxh;
-          s2 = fmaf(dxh, xh, s2);
-        }
-      }
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) ll_store2(ws.ll + L.sd + (((size_t)par * MAXB + b) * SCAN_G + cta) * 2, s1, s2, tag);
+      const float p2 = rstdg * (p_qgx - mug * wsgx);
+      dact_x = rstdg * (acc_x - S1[b] * wsgx - S2[b] * p2);
+      const float xh = (p_xp - mux) * rstdx;
+      const float ln = xh * gam_x + bet_x;
+      const float sg = sigmoidf_(ln);
+      const float dxh = dact_x * sg * (1.f + ln * (1.f - sg)) * gam_x;
+      ll_store(ws.ll + L.d + ((size_t)par * MAXB + b) * Dx + sX.col, dxh, tag);
+      ST[(b * nx4 + sX.cj) * 2] = dxh;
+      ST[(b * nx4 + sX.cj) * 2 + 1] = dxh * xh;
+    } else if (tid < B * nx4) {
+      ST[tid * 2] = 0.f; ST[tid * 2 + 1] = 0.f;
+    }
+    float dhin_f = 0.f;
+    if (sH.ok) {
+      const int b = sH.b;
+      acc_h += part_sum(PART, ldp, ksb, b, sH.cj);
+      const float mug = LNS[(1 * MAXB + b) * 2], rstdg = LNS[(1 * MAXB + b) * 2 + 1];
+      const float p2 = rstdg * (p_qgh - mug * wsgh);
+      const float dhin = dhin_gate + rstdg * (acc_h - S1[b] * wsgh - S2[b] * p2);
+      DHC[b * nh4 + sH.cj] = (1.f - fl[b]) * dhin;          // carried to step t-1 (agent.py:428 mask)
+      dhin_f = fl[b] * dhin;                                // grad of tanh(initial_recurrent_state)
     }
     __syncthreads();
-    for (int c = tid; c < nh4; c += SCAN_NT) {          // fixed row order: bit-reproducible
-      float s = DH0[c];
-      for (int b = 0; b < B; ++b) s += DHIN[b * nh4 + c];
-      DH0[c] = s;
-    }
+    send_row_sums(ST, nx4, B, ws.ll + L.sd, par, cta, tag, tid);
+    if (sX.ok) q.d_x_act[(row0 + sX.b) * Dx + sX.col] = dact_x;
+    // d_h0: sum over the rows with is_first set, fixed row order (bit-reproducible): stage through ACC
+    if (sH.ok) ACC[sH.b * ldp + sH.cj] = dhin_f;
+    __syncthreads();
+    if (tid < nh4)
+      for (int b = 0; b < B; ++b)
+        if (fl[b] != 0.f) dh0_acc += ACC[b * ldp + tid];
     prof_mark(prof, 24, tlast, prof_on);
     __syncthreads();
     if (sp.dead) break;    // a hand-off timed out somewhere: bail out, never hang
   }
-  for (int c = tid; c < nh4; c += SCAN_NT) {
-    const int col = (cta + (c >> 2) * SCAN_G) * 4 + (c & 3);
-    if (col < R) q.d_h0[col] = DH0[c];
+  if (tid < nh4) {
+    const int col = (cta + (tid >> 2) * SCAN_G) * 4 + (tid & 3);
+    if (col < R) q.d_h0[col] = dh0_acc;
   }
+  (void)DH0;
 }
 
 int scan_check(const b200rl_rssm_scan_args& a) {
@@ -1210,6 +1228,10 @@ int scan_check(const b200rl_rssm_scan_args& a) {
   RL_CHECK_ARG(a.T >= 1 && a.S >= 1 && a.S <= 64, "bad T / S (S <= 64)");
   RL_CHECK_ARG(a.Dx % 2 == 0 && a.R % 2 == 0 && a.Dr % 2 == 0 && (a.S * a.D) % 2 == 0, "persistent scan supports even layer widths");
   RL_CHECK_ARG(a.Dx <= 4 * SCAN_NT, "persistent scan supports recurrent dense_units <= 1024");
+  // one element of every per-step epilogue per thread (fixed assignments, rssm_scan.cu `Slot`)
+  RL_CHECK_ARG(MAXB * owned_groups(a.R, 0) * 12 <= SCAN_NT && MAXB * owned_groups(a.Dr, 0) * 4 <= SCAN_NT &&
+                   MAXB * owned_groups(a.Dx, 0) * 4 <= SCAN_NT,
+               "persistent scan supports recurrent_state_size <= 512 and hidden / dense sizes <= 2048");
   RL_CHECK_ARG(a.W_in_t, "W_in_t (transposed recurrent-model input weight) is required");
   RL_CHECK_ARG(a.workspace && a.workspace_bytes >= (long long)ws_bytes(a.T, a.B, a.S, a.D, a.Dx, a.R, a.Dr), "workspace too small");
   return B200RL_OK;
