@@ -36,6 +36,12 @@ int b200rl_gemm_f32(const float* A, const float* B, float* C, const float* bias,
 /* Tensor-core path used by b200rl_gemm_f32 for large NT products (transA = 0, transB = 1, 16-byte aligned
  * operands): 3xTF32 split-precision on tcgen05.mma with TMA-fed 128B-swizzled tiles and TMEM accumulators
  * (gemm_tc.cu).  Same contract as b200rl_gemm_f32; `_supported` tells whether a shape is eligible. */
+/* Precision of every tensor-core product (GEMM, conv forward / input gradient / weight gradient), process-wide like
+ * torch.set_float32_matmul_precision (the reference sets it from configs/config.yaml:18, default "high"):
+ * 3 = three TF32 products per k-step on x = hi + lo (fp32-accurate, default; the 1e-4 parity tests run this),
+ * 1 = one TF32 product ("high": the numerics of the reference's own GPU runs, ~3x the throughput). */
+int b200rl_set_matmul_precision(int tf32_passes);
+int b200rl_get_matmul_precision(void);
 int b200rl_gemm_tc_supported(const float* A, const float* B, int M, int N, int K, int lda, int ldb, int transA,
                              int transB);
 int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,

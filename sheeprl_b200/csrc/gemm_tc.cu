@@ -209,6 +209,8 @@ struct TileGeo {
   float* part;             // split-K workspace: [ksplits][mpad][ldw] partial sums (fixed-order reduction, no atomics)
   int* cnt;                // split-K: arrival counter per output tile (self-resetting)
   int mpad, ldw;           // split-K workspace geometry (rows per split, row stride)
+  int passes;              // 3: x = hi + lo split, three TF32 products per k-step (fp32-accurate); 1: one TF32 product
+                           // (torch's float32_matmul_precision "high", the reference's default on GPUs)
   int a_mn, b_mn;          // GEMM mode: operand stored [K][M] / [K][N] (MN-major) instead of [M][K] / [N][K]
   int mtiles;              // number of M tiles; a CTA walks tiles blockIdx.y, blockIdx.y + gridDim.y, ... (persistent)
   int wg;                  // GEMM mode, conv weight gradient: A rows = (tap, big channel), K = small-grid pixels gathered
@@ -334,10 +336,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int k4 = 0; k4 < BK / 8; ++k4) {
           const uint64_t ob = (uint64_t)k4 * b_step;
-          // small cross terms first, then the leading term
-          umma_tf32_ts(acc, ta_hi + 8u * k4, dbl0 + ob, idesc, !(chunk_start && k4 == 0));
-          umma_tf32_ts(acc, ta_lo + 8u * k4, dbh0 + ob, idesc, 1);
-          umma_tf32_ts(acc, ta_hi + 8u * k4, dbh0 + ob, idesc, 1);
+          if (geo.passes == 3) {
+            // small cross terms first, then the leading term
+            umma_tf32_ts(acc, ta_hi + 8u * k4, dbl0 + ob, idesc, !(chunk_start && k4 == 0));
+            umma_tf32_ts(acc, ta_lo + 8u * k4, dbh0 + ob, idesc, 1);
+            umma_tf32_ts(acc, ta_hi + 8u * k4, dbh0 + ob, idesc, 1);
+          } else {
+            umma_tf32_ts(acc, ta_hi + 8u * k4, dbh0 + ob, idesc, !(chunk_start && k4 == 0));
+          }
         }
         umma_commit(&s.empty[st]);   // stage reusable once these MMAs have read it
         if ((kb % CH) == CH - 1 || kb == nkb - 1) umma_commit(&s.tfull[buf]);   // chunk complete
@@ -377,17 +383,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int k = 0; k < 32; ++k)
             hi[k] = *reinterpret_cast<const uint32_t*>(blk + k * 128 + ((ch ^ (k & 3)) << 5));
         }
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float x = __uint_as_float(hi[k]);
-          lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
-        }
         const uint32_t ta = tmem + (((uint32_t)(t & ~31)) << 16) + A_TMEM0 + 64u * (uint32_t)st;
         tmem_st32(ta, hi);
-        tmem_st32(ta + 32u, lo);      // completion is awaited after the B tile has been split (overlaps the two)
+        if (geo.passes == 3) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = __uint_as_float(hi[k]);
+            lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
+          }
+          tmem_st32(ta + 32u, lo);    // completion is awaited after the B tile has been split (overlaps the two)
+        }
       }
       float4* bh = reinterpret_cast<float4*>(s.b_hi[st]);
       float4* bl = reinterpret_cast<float4*>(s.b_lo[st]);
+      if (geo.passes == 3)
 #pragma unroll
       for (int i = 0; i < BN * BK / 4 / NSPLIT_THREADS; ++i) {
         const int idx = t + i * NSPLIT_THREADS;
@@ -658,6 +667,10 @@ __global__ void conv_pack_up_kernel(const float* __restrict__ W, float* __restri
   P[idx] = W[((long long)cs * Cb + cb) * 16 + ky * 4 + kx];
 }
 
+// Matmul precision of every tensor-core product of the library (process-wide, like torch.set_float32_matmul_precision):
+// 3 = fp32-accurate 3xTF32 (default; what the 1e-4 parity tests run), 1 = single TF32 pass.
+int g_passes = 3;
+
 // Split-K workspace: partial tiles + per-tile arrival counters, one per device, grown on demand OUTSIDE stream capture
 // (launches on one stream serialise, so consecutive products share it; a capture replays the size it was captured with).
 struct SplitWs {
@@ -703,6 +716,7 @@ int launch_conv(int mode, const float* img, const float* Wp, float* out, const f
                 int Cout, cudaStream_t st) {
   TileGeo g = {};
   g.mode = mode; g.h = h; g.w = w; g.NB = NB; g.chunks = Cin / BK; g.Cout = Cout; g.ksplits = 1;
+  g.passes = g_passes;
   RL_CHECK_ARG(conv_tile(h, w, NB, &g.bw, &g.bh, &g.bn), "image grid not tileable by 128 pixels");
   g.tiles_x = w / g.bw; g.tiles_y = h / g.bh;
   const int taps = mode == MODE_DOWN ? 16 : 4;
@@ -732,6 +746,13 @@ int launch_conv(int mode, const float* img, const float* Wp, float* out, const f
 }
 
 }  // namespace
+
+extern "C" int b200rl_set_matmul_precision(int tf32_passes) {
+  RL_CHECK_ARG(tf32_passes == 1 || tf32_passes == 3, "tf32_passes must be 3 (fp32-accurate 3xTF32) or 1 (single TF32 pass)");
+  g_passes = tf32_passes;
+  return B200RL_OK;
+}
+extern "C" int b200rl_get_matmul_precision(void) { return g_passes; }
 
 // ---- convolution entry points (tensor-core implicit GEMM).  Wpacked: 16*Cs*Cb floats of caller workspace.
 extern "C" int b200rl_conv_tc_supported(int mode_up, int NB, int h, int w, int Cs, int Cb) {
@@ -790,6 +811,7 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
   g.a_mn = transA ? 1 : 0;
   g.b_mn = transB ? 0 : 1;
   g.ksplits = 1;
+  g.passes = g_passes;
   const int tiles = grid.x * grid.y, nkb = (K + BK - 1) / BK;
   if (tiles < 2 * kNumSMs && nkb >= 8) {
     // split-K for launches that cannot fill the SMs (the M = T*B = 1024 products of the imagination rollout, weight
@@ -845,7 +867,7 @@ extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float
   RL_CHECK_ARG(b200rl_conv_wgrad_mn_supported(NB, h, w, Cs, Cb), "shape not eligible for the in-place wgrad path");
   const int P = NB * h * w, M = 16 * Cb, N = Cs;
   TileGeo g = {};
-  g.mode = MODE_GEMM; g.a_mn = 1; g.b_mn = 1; g.wg = 1;
+  g.mode = MODE_GEMM; g.a_mn = 1; g.b_mn = 1; g.wg = 1; g.passes = g_passes;
   g.h = h; g.w = w; g.NB = NB; g.Cout = Cb;
   g.bw = w < 32 ? w : 32; g.bh = (32 / g.bw) < h ? (32 / g.bw) : h; g.bn = 32 / (g.bw * g.bh);
   CUtensorMap ma, mb;

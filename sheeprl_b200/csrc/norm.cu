@@ -312,7 +312,13 @@ int vec_grid(long long M, int rows_per_warp) {
 }
 bool vec_ok(int C, long long ld0, long long ld1, long long ld2, const void* p0, const void* p1, const void* p2, const void* g,
             const void* b) {
-  if (C != 32 && C != 64 && C != 128 && C != 256 && C != 512 && C != 1024 && C != 1536) return false;
+  // widths with a register-resident instantiation: powers of two 32..1024, 1536 (S GRU: 3*512) and the 3 * 2^k family
+  // of the M / L / XL conv stacks and dense layers (48, 96, 192, 384, 768; cnn multipliers 48 / 96, dense 768), 640 (M)
+  switch (C) {
+    case 32: case 64: case 128: case 256: case 512: case 1024: case 1536:
+    case 48: case 96: case 192: case 384: case 768: case 640: break;
+    default: return false;
+  }
   if ((ld0 | ld1 | ld2) & 3) return false;
   return ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) |
            reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
@@ -344,6 +350,12 @@ extern "C" int b200rl_ln_act_fwd(const float* X, const float* gamma, const float
       case 256: LN_FWD_VEC(32, 2); break;
       case 512: LN_FWD_VEC(32, 4); break;
       case 1024: LN_FWD_VEC(32, 8); break;
+      case 48: LN_FWD_VEC(4, 3); break;
+      case 96: LN_FWD_VEC(8, 3); break;
+      case 192: LN_FWD_VEC(16, 3); break;
+      case 384: LN_FWD_VEC(32, 3); break;
+      case 640: LN_FWD_VEC(32, 5); break;
+      case 768: LN_FWD_VEC(32, 6); break;
       default: LN_FWD_VEC(32, 12); break;
     }
 #undef LN_FWD_VEC
@@ -381,6 +393,12 @@ extern "C" int b200rl_ln_act_bwd(const float* X, const float* gamma, const float
       case 256: LN_BWD_VEC(32, 2); break;
       case 512: LN_BWD_VEC(32, 4); break;
       case 1024: LN_BWD_VEC(32, 8); break;
+      case 48: LN_BWD_VEC(4, 3); break;
+      case 96: LN_BWD_VEC(8, 3); break;
+      case 192: LN_BWD_VEC(16, 3); break;
+      case 384: LN_BWD_VEC(32, 3); break;
+      case 640: LN_BWD_VEC(32, 5); break;
+      case 768: LN_BWD_VEC(32, 6); break;
       default: LN_BWD_VEC(32, 12); break;
     }
 #undef LN_BWD_VEC

@@ -430,6 +430,12 @@ class DV3Engine:
         self.rng_seed = int(self.cfg.get("seed", 0) or 0)      # build_agent folds the rank in (agent.py)
         self.rng_t = torch.zeros(1, dtype=torch.int32, device=self.device)   # device-side step counter for Philox
         self.cuda_graph = bool(self.cfg.algo.get("cuda_graph", True))  # B200 knob: replay the update as one CUDA graph
+        # the reference applies cfg.float32_matmul_precision with torch.set_float32_matmul_precision (cli.py:186;
+        # configs/config.yaml:18 defaults to "high" = TF32 products).  Here the key is honoured when PRESENT; without it the
+        # products stay fp32-accurate (3xTF32), which is what the 1e-4 parity contract is stated for.
+        prec = self.cfg.get("float32_matmul_precision", None)
+        if prec is not None and hasattr(self.ops, "set_matmul_precision"):
+            self.ops.set_matmul_precision(str(prec))
         self._graph = None
         # persistent fused RSSM scan (csrc/rssm_scan.cu) when the ops backend provides it and the shape qualifies
         self.fused_scan = bool(hasattr(self.ops, "rssm_scan_fwd") and self.B <= 16 and self.D <= 32 and self.S <= 64)
@@ -448,8 +454,9 @@ class DV3Engine:
 
     def graph_key(self) -> tuple:
         """what a captured step bakes in besides the batch shapes: the learning rates (kernel arguments by value)"""
+        prec = self.ops.matmul_precision() if hasattr(self.ops, "matmul_precision") else "highest"
         return tuple(float(g.optimizer.lr) if getattr(g, "optimizer", None) is not None else -1.0
-                     for g in self.optimizer_groups())
+                     for g in self.optimizer_groups()) + (prec,)
 
     def step_graph(self):
         if self._graph is None:

@@ -114,6 +114,18 @@ class CudaOps:
             raise B200RLError(self.lib.b200rl_last_error().decode())
 
     # ------------------------------------------------------------------ GEMM family
+    def set_matmul_precision(self, precision: str) -> None:
+        """"highest": fp32-accurate 3xTF32 products (default); "high" / "medium": one TF32 product per k-step — what
+        torch.set_float32_matmul_precision("high") gives the reference on a GPU (sheeprl/configs/config.yaml:18)."""
+        p = str(precision).lower()
+        if p not in ("highest", "high", "medium"):
+            raise ValueError(f"float32_matmul_precision must be highest / high / medium, got {precision}")
+        self._ck(self.lib.b200rl_set_matmul_precision(c_int(3 if p == "highest" else 1)))
+        self.launches -= 1
+
+    def matmul_precision(self) -> str:
+        return "highest" if int(self.lib.b200rl_get_matmul_precision()) == 3 else "high"
+
     def gemm(self, A, B, C, transA: bool, transB: bool, bias=None, accumulate: bool = False):
         _f32(A, B, C, bias)
         M, N = C.shape

@@ -77,6 +77,48 @@ def test_gemm_tensor_core_path_is_taken_and_exact_enough(ops):
     assert float(Cw[:, :4].abs().sum()) == 0 and float(Cw[:, 4 + N:].abs().sum()) == 0
 
 
+def test_matmul_precision_knob_single_tf32_pass(ops):
+    """`float32_matmul_precision: high` (the reference's GPU default, configs/config.yaml:18): one TF32 product per k-step —
+    TF32-level error (~1e-3 of the largest entry), clearly distinct from the fp32-accurate default, and switching back
+    restores it.  Also covers the split-K path (M = 1024) in both modes."""
+    cu, em = ops
+    for M, N, K in ((2048, 512, 1536), (1024, 1536, 1024)):
+        A, B = rnd(M, K, seed=21), rnd(N, K, seed=22)
+        Ag, Bg, Cg = A.cuda(), B.cuda(), torch.empty(M, N, device="cuda")
+        ref = A.double() @ B.double().t()
+        try:
+            cu.set_matmul_precision("high")
+            assert cu.matmul_precision() == "high"
+            cu.gemm(Ag, Bg, Cg, False, True)
+            err_hi = float((Cg.cpu().double() - ref).abs().max() / ref.abs().max())
+        finally:
+            cu.set_matmul_precision("highest")
+        cu.gemm(Ag, Bg, Cg, False, True)
+        err = float((Cg.cpu().double() - ref).abs().max() / ref.abs().max())
+        assert err < 3e-6 and 2e-5 < err_hi < 5e-3, (M, N, K, err, err_hi)
+
+
+def test_split_k_products_are_bit_reproducible(ops):
+    """split-K partial tiles are summed in split order by the last CTA to arrive (no atomics on C): same bits every launch"""
+    cu, em = ops
+    M, N, K = 1024, 512, 4096
+    A, B = rnd(M, K, seed=31).cuda(), rnd(N, K, seed=32).cuda()
+    outs = []
+    for _ in range(4):
+        C = torch.empty(M, N, device="cuda")
+        cu.gemm(A, B, C, False, True)
+        outs.append(C.clone())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    # accumulate + bias through the split-K path
+    bias = rnd(1, N, seed=33).cuda().reshape(N)
+    C0 = rnd(M, N, seed=34).cuda()
+    C1 = C0.clone()
+    cu.gemm(A, B, C1, False, True, bias=bias, accumulate=True)
+    ref = C0.cpu().double() + A.cpu().double() @ B.cpu().double().t() + bias.cpu().double()
+    assert float((C1.cpu().double() - ref).abs().max() / ref.abs().max()) < 3e-6
+
+
 @pytest.mark.parametrize("rows", [1024, 15360])
 def test_gemm_twohot_gradient_operands_with_padded_rows(ops, rows):
     """the 255-bin logit gradients live in buffers with a 256-float row stride so that dX = dlogits W (K = 255) and
