@@ -277,6 +277,8 @@ class DV3Engine:
         self.world_size = 1
         self.allreduce = None          # set by the data-parallel wrapper: fn(flat_grad_tensor)
         self.allgather = None          # fn(tensor) -> gathered tensor (Moments)
+        self.allreduce_async = None    # fn(slice of a flat gradient): reduce on a side stream (parallel.py)
+        self.allreduce_join = None
         self._bufs: Dict[str, torch.Tensor] = {}
         self._alloc()
 
@@ -587,9 +589,21 @@ class DV3Engine:
         self._decoder_backward()                                       # writes d_latent
         self.reward_wm.backward(self.latent, self.d_rew_logits, None if heads_detached else self.d_latent, True)
         self.cont_wm.backward(self.latent, self.d_cont_logit, None if heads_detached else self.d_latent, True)
+        # data parallel: the flat gradient is laid out encoder | rssm | decoder, reward, continue, and the backward
+        # finishes those three ranges in REVERSE order, so each is all-reduced on a side stream as soon as it is final
+        # (the reference's DDP buckets, fabric.backward dreamer_v3.py:191, overlap the same way)
+        b_enc, b_tail = self._wm_buckets()
+        overlap = self.allreduce_async is not None
+        if overlap:
+            self.allreduce_async(self.wm.grad[b_tail:])
         self._scan_backward(first)
+        if overlap:
+            self.allreduce_async(self.wm.grad[b_enc:b_tail])
         self._encoder_backward()
-        self._optimizer_step("wm", self.wm, float(w.clip_gradients or 0.0), w.optimizer, 0)
+        if overlap:
+            self.allreduce_async(self.wm.grad[:b_enc])
+            self.allreduce_join()
+        self._optimizer_step("wm", self.wm, float(w.clip_gradients or 0.0), w.optimizer, 0, reduced=overlap)
 
     # ------------------------------------------------------------------ encoder / decoder
     def _enc_names(self, i):
@@ -985,9 +999,16 @@ class DV3Engine:
         # norm ignores it and Adam's zero moments leave the value untouched
 
     # ------------------------------------------------------------------ optimiser
-    def _optimizer_step(self, name: str, g: FlatGroup, max_norm: float, ocfg, slot: int):
+    def _wm_buckets(self):
+        """(first float of the rssm range, first float of the decoder / heads range) of the world model's flat buffer"""
+        off = self.wm.offsets
+        b_enc = off["rssm.initial_recurrent_state"]
+        tail = [v for k, v in off.items() if not (k.startswith("encoder.") or k.startswith("rssm."))]
+        return b_enc, min(tail)
+
+    def _optimizer_step(self, name: str, g: FlatGroup, max_norm: float, ocfg, slot: int, reduced: bool = False):
         ops = self.ops
-        if self.allreduce is not None:
+        if self.allreduce is not None and not reduced:
             self.allreduce(g.grad, name)
         ops.sumsq(g.grad, self.normsq[name])
         g.step += 1

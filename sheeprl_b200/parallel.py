@@ -40,6 +40,8 @@ def attach_data_parallel(engine, group=None) -> None:
     if world == 1:
         engine.allreduce = None
         engine.allgather = None
+        engine.allreduce_async = None
+        engine.allreduce_join = None
         return
     use_avg = dist.get_backend(group) == "nccl"
     # Dreamer-V3 gathers its lambda-values for Moments (dreamer_v3/utils.py:58); SAC / PPO engines have no gather
@@ -57,5 +59,24 @@ def attach_data_parallel(engine, group=None) -> None:
         dist.all_gather_into_tensor(gather_buf, x.reshape(-1).contiguous(), group=group)
         return gather_buf
 
+    # Bucketed, overlapped reduction of the world-model gradient (the 62.7 MB buffer at size S): a slice of the flat
+    # gradient whose producers have finished is reduced on a side stream while the backward continues; `join` makes the
+    # optimizer wait for all of them.  Works inside CUDA-graph capture (fork / join through stream dependencies).
+    side = torch.cuda.Stream(device=engine.device) if torch.device(engine.device).type == "cuda" else None
+
+    def allreduce_async(flat_slice: torch.Tensor):
+        if side is None:
+            allreduce(flat_slice, "bucket")
+            return
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            allreduce(flat_slice, "bucket")
+
+    def allreduce_join():
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+
     engine.allreduce = allreduce
     engine.allgather = allgather
+    engine.allreduce_async = allreduce_async
+    engine.allreduce_join = allreduce_join
