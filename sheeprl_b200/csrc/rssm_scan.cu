@@ -477,11 +477,13 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
         for (int k = tid; k < R; k += SCAN_NT) Xh[b * g.sR + k] = (1.f - f) * ((t > 0) ? Xh[b * g.sR + k] : 0.f) + f * H0[k];
     }
     __syncthreads();
+    prof_mark(prof, 12, tlast, prof_on);
     const int ksh = product(Xh, g.sR, Wg, g.wgst, g.ngh * 3, R, PART, ldp, 0, tid);
+    prof_mark(prof, 1, tlast, prof_on);
     __syncthreads();
     const float acch = pok ? part_sum(PART, ldp, ksh, pb, pc) : 0.f;
     const float hin = sH.ok ? Xh[sH.b * g.sR + sH.col] : 0.f;
-    prof_mark(prof, 1, tlast, prof_on);
+    prof_mark(prof, 13, tlast, prof_on);
 
     // ============ A (row owner): x = SiLU(LN(W_in [z_in, a_in])) for the owned row; z_in one-hot -> row gather
     if (owner) {
@@ -704,6 +706,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
         }
       }
       __syncthreads();
+      prof_mark(prof, 14, tlast, prof_on);
       // logits: lane = class, warp = K slice, all rows of the unit
       {
         const int kc = ((g.sDr + SCAN_NW - 1) / SCAN_NW + 3) / 4 * 4;
@@ -726,6 +729,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
           if (i < nr) PART[((size_t)wid * MAXRPU + i) * 32 + lane] = acc[i];
       }
       __syncthreads();
+      prof_mark(prof, 15, tlast, prof_on);
       // one warp per row: the D classes of the group live on the lanes (D <= 32)
       if (wid < nr) {
         const int bb = wid, b = rb + bb;
