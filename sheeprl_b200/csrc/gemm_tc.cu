@@ -187,7 +187,6 @@ struct Smem {
   float b_lo[STAGES][BN * BK];
   uint64_t full[STAGES], split[STAGES], empty[STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
-  int last_split;                // split-K: this CTA is the last of its output tile to arrive (it reduces the partials)
 };
 
 // Two-level accumulation.  The tensor core adds each k-step into the fp32 TMEM accumulator with truncation
@@ -207,7 +206,6 @@ struct TileGeo {
   int Cout;                // output channels
   int ksplits;             // GEMM mode: number of K splits (gridDim.z); > 1 => partial tiles go through `part`
   float* part;             // split-K workspace: [ksplits][mpad][ldw] partial sums (fixed-order reduction, no atomics)
-  int* cnt;                // split-K: arrival counter per output tile (self-resetting)
   int mpad, ldw;           // split-K workspace geometry (rows per split, row stride)
   int passes;              // 3: x = hi + lo split, three TF32 products per k-step (fp32-accurate); 1: one TF32 product
                            // (torch's float32_matmul_precision "high", the reference's default on GPUs)
@@ -453,36 +451,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     bool store = true;
     if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
-      // ---- deterministic split-K: publish this split's partial tile, count the arrival
+      // ---- deterministic split-K: this split's partial tile goes to the workspace; splitk_reduce_kernel (launched right
+      // behind this kernel) sums the partials of every output element in split order — no atomics, bit-reproducible
       float* prow = geo.part + ((size_t)blockIdx.z * geo.mpad + (size_t)(m0 + q * 32 + lane)) * geo.ldw + n0 + half * ACC_COLS;
 #pragma unroll
       for (int j = 0; j < ACC_COLS; j += 4)
         *reinterpret_cast<float4*>(prow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(NACC_WARPS * 32) : "memory");
-      if (threadIdx.x == ACC_WARP0 * 32) {
-        int* c = geo.cnt + (size_t)tile * gridDim.x + blockIdx.x;
-        const int old = atomicAdd(c, 1);
-        const int last = (old == geo.ksplits - 1);
-        if (last) *c = 0;                        // every split of this tile has arrived: leave the counter clean
-        __threadfence();
-        s.last_split = last;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NACC_WARPS * 32) : "memory");
-      store = s.last_split != 0;
-      if (store) {
-#pragma unroll
-        for (int j = 0; j < ACC_COLS; ++j) acc[j] = 0.f;
-        for (int z = 0; z < geo.ksplits; ++z) {  // fixed order 0 .. ksplits-1, whoever arrived last
-          const float* pz = geo.part + ((size_t)z * geo.mpad + (size_t)(m0 + q * 32 + lane)) * geo.ldw + n0 + half * ACC_COLS;
-#pragma unroll
-          for (int j = 0; j < ACC_COLS; j += 4) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(pz + j));
-            acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
-          }
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NACC_WARPS * 32) : "memory");   // `last_split` is rewritten by the next tile
+      store = false;
     }
     if (row_ok && store) {
       const int cb = n0 + half * ACC_COLS;
@@ -671,24 +646,22 @@ __global__ void conv_pack_up_kernel(const float* __restrict__ W, float* __restri
 // 3 = fp32-accurate 3xTF32 (default; what the 1e-4 parity tests run), 1 = single TF32 pass.
 int g_passes = 3;
 
-// Split-K workspace: partial tiles + per-tile arrival counters, one per device, grown on demand OUTSIDE stream capture
-// (launches on one stream serialise, so consecutive products share it; a capture replays the size it was captured with).
+// Split-K workspace (partial tiles), one per device, grown on demand OUTSIDE stream capture (launches on one stream
+// serialise, so consecutive products share it; a capture replays the size it was captured with).
 struct SplitWs {
   float* part = nullptr;
   size_t floats = 0;
-  int* cnt = nullptr;
 };
-constexpr int SPLIT_MAX_TILES = 4096;
 SplitWs g_split[16];
 std::mutex g_split_mu;
 
-int split_workspace(size_t need_floats, int tiles, cudaStream_t st, float** part, int** cnt) {
+int split_workspace(size_t need_floats, cudaStream_t st, float** part) {
   int dev = 0;
   RL_CUDA(cudaGetDevice(&dev));
-  RL_CHECK_ARG(dev < 16 && tiles <= SPLIT_MAX_TILES, "split-K workspace: device index / tile count out of range");
+  RL_CHECK_ARG(dev < 16, "split-K workspace: device index out of range");
   std::lock_guard<std::mutex> lk(g_split_mu);
   SplitWs& w = g_split[dev];
-  if (need_floats > w.floats || !w.cnt) {
+  if (need_floats > w.floats) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     RL_CUDA(cudaStreamIsCapturing(st, &cs));
     if (cs != cudaStreamCaptureStatusNone) {
@@ -696,20 +669,44 @@ int split_workspace(size_t need_floats, int tiles, cudaStream_t st, float** part
       return B200RL_ERR_CUDA;
     }
     RL_CUDA(cudaDeviceSynchronize());
-    if (need_floats > w.floats) {
-      if (w.part) RL_CUDA(cudaFree(w.part));
-      const size_t n = need_floats + need_floats / 2 > (size_t)16 << 20 ? need_floats + need_floats / 2 : (size_t)16 << 20;
-      RL_CUDA(cudaMalloc(&w.part, n * sizeof(float)));
-      w.floats = n;
-    }
-    if (!w.cnt) {
-      RL_CUDA(cudaMalloc(&w.cnt, SPLIT_MAX_TILES * sizeof(int)));
-      RL_CUDA(cudaMemset(w.cnt, 0, SPLIT_MAX_TILES * sizeof(int)));
-    }
+    if (w.part) RL_CUDA(cudaFree(w.part));
+    const size_t n = need_floats + need_floats / 2 > (size_t)16 << 20 ? need_floats + need_floats / 2 : (size_t)16 << 20;
+    RL_CUDA(cudaMalloc(&w.part, n * sizeof(float)));
+    w.floats = n;
   }
   *part = w.part;
-  *cnt = w.cnt;
   return B200RL_OK;
+}
+
+// C[m][n] (+)= bias[n] + sum_z part[z][m][n], z ascending: the fixed-order tail of a split-K product
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, const float* __restrict__ bias, int M, int N,
+                     int ldc, int ks, int mpad, int ldw, int accumulate) {
+  const int n4 = (N + 3) >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * n4) return;
+  const int m = (int)(idx / n4), n = (int)(idx - (long long)m * n4) * 4;
+  const float* p = part + (size_t)m * ldw + n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < ks; ++z) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (size_t)z * mpad * ldw));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float* c = C + (size_t)m * ldc + n;
+  const float o[4] = {acc.x, acc.y, acc.z, acc.w};
+  if (n + 4 <= N && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+    float4 r = acc;
+    if (bias) { r.x += bias[n]; r.y += bias[n + 1]; r.z += bias[n + 2]; r.w += bias[n + 3]; }
+    if (accumulate) { const float4 q = *reinterpret_cast<const float4*>(c); r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w; }
+    *reinterpret_cast<float4*>(c) = r;
+  } else {
+    for (int j = 0; j < 4 && n + j < N; ++j) {
+      float r = o[j];
+      if (bias) r += bias[n + j];
+      if (accumulate) r += c[j];
+      c[j] = r;
+    }
+  }
 }
 
 int launch_conv(int mode, const float* img, const float* Wp, float* out, const float* bias, int NB, int h, int w, int Cin,
@@ -816,14 +813,15 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
   if (tiles < 2 * kNumSMs && nkb >= 8) {
     // split-K for launches that cannot fill the SMs (the M = T*B = 1024 products of the imagination rollout, weight
     // gradients): pick the split count that minimises  waves x (k-blocks per CTA x t_kb + fixed cost)  with
-    // t_kb ~ 0.8 us per 128x128x32 k-block, ~4 us of pipeline fill + epilogue per CTA, ~2 us for the vector reductions
+    // t_kb ~ 0.8 us per 128x128x32 k-block, ~4 us of pipeline fill + epilogue per CTA, and for the fixed-order reduce
+    // kernel behind a split product ~3 us + 0.3 us per split
     int best = 1;
     float best_t = 1e30f;
     const int max_sp = nkb / 4 < 32 ? nkb / 4 : 32;
     for (int sp = 1; sp <= (max_sp < 1 ? 1 : max_sp); ++sp) {
       const int per = (nkb + sp - 1) / sp, real = (nkb + per - 1) / per;
       const int waves = (tiles * real + kNumSMs - 1) / kNumSMs;
-      const float t = waves * (per * 0.8f + 4.0f + (real > 1 ? 2.0f : 0.0f));
+      const float t = waves * (per * 0.8f + 4.0f) + (real > 1 ? 3.0f + 0.3f * real : 0.0f);
       if (t < best_t - 1e-3f) { best_t = t; best = real; }
     }
     g.ksplits = best;
@@ -832,7 +830,7 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
     grid.z = g.ksplits;
     g.mpad = (int)grid.y * BM;
     g.ldw = (int)grid.x * BN;
-    if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, tiles, st, &g.part, &g.cnt)) return rc;
+    if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, st, &g.part)) return rc;
   }
   g.mtiles = (int)grid.y;
   grid.y = persistent_grid_y(g.mtiles, grid.x, grid.z);
@@ -846,6 +844,11 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
     gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate, g);
   }
   RL_CHECK_LAUNCH();
+  if (g.ksplits > 1) {
+    splitk_reduce_kernel<<<ceil_div((long long)M * ((N + 3) / 4), 256), 256, 0, st>>>(g.part, C, bias, M, N, ldc, g.ksplits, g.mpad,
+                                                                                      g.ldw, accumulate);
+    RL_CHECK_LAUNCH();
+  }
   return B200RL_OK;
 }
 
@@ -886,7 +889,7 @@ extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float
   if (g.ksplits > 1) {
     g.mpad = (int)grid.y * BM;
     g.ldw = (int)grid.x * BN;
-    if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, tiles, st, &g.part, &g.cnt)) return rc;
+    if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, st, &g.part)) return rc;
   }
   if (BN == 64) {
     const size_t smem = sizeof(Smem<64>) + 1024;
@@ -898,5 +901,10 @@ extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float
     gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, G, nullptr, M, N, P, N, 0, g);
   }
   RL_CHECK_LAUNCH();
+  if (g.ksplits > 1) {
+    splitk_reduce_kernel<<<ceil_div((long long)M * ((N + 3) / 4), 256), 256, 0, st>>>(g.part, G, nullptr, M, N, N, g.ksplits, g.mpad,
+                                                                                      g.ldw, 0);
+    RL_CHECK_LAUNCH();
+  }
   return B200RL_OK;
 }
