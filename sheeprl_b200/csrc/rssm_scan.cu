@@ -37,12 +37,17 @@
 namespace {
 
 constexpr int SCAN_G = 128;    // CTAs (one per SM; 148 SMs available)
-constexpr int SCAN_NT = 256;   // threads per CTA
+constexpr int SCAN_NT = 512;   // threads per CTA: the scan is latency-bound (ncu: 11 stall cycles per issued instruction at
+                               // 8 warps / SM), so every phase is spread over 32 warps with short per-warp instruction streams
 constexpr int SCAN_NW = SCAN_NT / 32;
 constexpr int MAXB = 16;
 constexpr int OWN_STRIDE = SCAN_G / MAXB;   // batch row b is owned by CTA b * OWN_STRIDE
 constexpr int MAXRPU = 8;      // rows of one sampling unit (S <= 64 groups over 128 CTAs -> >= 2 row splits)
-constexpr int LL_UNROLL = 8;   // 16-byte loads in flight per thread while receiving rows
+constexpr int LL_UNROLL = 4;   // 16-byte loads in flight per thread while receiving rows
+constexpr int NRB = 4;         // rows of one product item (4 rows x 4 columns of packed accumulators per lane)
+constexpr int KS_MAX = 8;      // K slices of a product (rows of the partial buffer)
+constexpr int CLS_SLICES = 8;  // K slices of the class-per-lane products (logits / dz)
+constexpr int GPARTS = SCAN_NT / 256;   // thread groups of the owner's row gather (each sums a contiguous range of groups)
 
 typedef unsigned long long u64;
 
@@ -164,23 +169,26 @@ __device__ __forceinline__ float ll_wait(const u64* p, unsigned tag, Spin& sp) {
 }
 
 // Receives rows x n values (n even; LL rows of stride ss elements, 16-byte aligned) into shared memory rows of stride ds.
-// A thread owns column pairs k = 2*tid (+ 2*SCAN_NT ...) and walks the rows, LL_UNROLL 16-byte loads in flight before the
-// first tag is checked; no integer division on this path.
+// Thread (row group, column pair): LL_UNROLL 16-byte loads in flight before the first tag is checked.
 __device__ __forceinline__ void ll_recv(float* dst, int ds, const u64* src, int ss, int rows, int n, unsigned tag, int tid, Spin& sp) {
-  for (int k = 2 * tid; k < n; k += 2 * SCAN_NT) {
-    for (int r0 = 0; r0 < rows; r0 += LL_UNROLL) {
+  const int half = n >> 1;
+  int rg = 0, kp = tid, nrg = 1, kstep = SCAN_NT;
+  if (half < SCAN_NT) { rg = tid / half; kp = tid - rg * half; nrg = SCAN_NT / half; kstep = half; if (rg >= nrg) return; }
+  for (int k = 2 * kp; k < n; k += 2 * kstep) {
+    for (int r0 = rg; r0 < rows; r0 += nrg * LL_UNROLL) {
       u64 a[LL_UNROLL], b[LL_UNROLL];
 #pragma unroll
       for (int u = 0; u < LL_UNROLL; ++u)
-        if (r0 + u < rows) ll_load2(src + (size_t)(r0 + u) * ss + k, a[u], b[u]);
+        if (r0 + u * nrg < rows) ll_load2(src + (size_t)(r0 + u * nrg) * ss + k, a[u], b[u]);
 #pragma unroll
       for (int u = 0; u < LL_UNROLL; ++u)
-        if (r0 + u < rows) {
+        if (r0 + u * nrg < rows) {
+          const int r = r0 + u * nrg;
           while ((unsigned)(a[u] >> 32) != tag || (unsigned)(b[u] >> 32) != tag) {
             if (sp.fail()) break;
-            ll_load2(src + (size_t)(r0 + u) * ss + k, a[u], b[u]);
+            ll_load2(src + (size_t)r * ss + k, a[u], b[u]);
           }
-          *reinterpret_cast<float2*>(dst + (r0 + u) * ds + k) =
+          *reinterpret_cast<float2*>(dst + r * ds + k) =
               make_float2(__uint_as_float((unsigned)a[u]), __uint_as_float((unsigned)b[u]));
         }
     }
@@ -204,12 +212,19 @@ __device__ __forceinline__ Slot make_slot(int e, int per_row, int B, int cta, in
 // fast transcendental form for SiLU; rel. error ~1e-6
 __device__ __forceinline__ float fsilu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
-// v[N] = acc[N/4 rows][4 cols] per lane; sum across the 32 lanes; lane ends up owning N/32 consecutive values
-// starting at the returned base: N - N/32 shuffles instead of 5N.
-template <int N>
-__device__ __forceinline__ int reduce_scatter(float (&v)[N], int lane) {
+// Packed fp32 FMA (Blackwell FFMA2): two independent fp32 fused multiply-adds per instruction on 64-bit register pairs.
+__device__ __forceinline__ void fma2(u64& acc, u64 x, u64 w) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(x), "l"(w));
+}
+__device__ __forceinline__ float pair_sum(u64 v) {
+  return __uint_as_float((unsigned)v) + __uint_as_float((unsigned)(v >> 32));
+}
+
+// 16 values per lane, summed across the 32 lanes: 16 shuffles; the total of value `idx` (returned) ends up in both lanes
+// of a pair (lane, lane ^ 1) as v[0].
+__device__ __forceinline__ int reduce16(float (&v)[16], int lane) {
 #pragma unroll
-  for (int off = 16, n = N; off >= 1; off >>= 1, n >>= 1) {
+  for (int off = 16, n = 16; off >= 2; off >>= 1, n >>= 1) {
     const bool upper = (lane & off) != 0;
 #pragma unroll
     for (int i = 0; i < n / 2; ++i) {
@@ -219,63 +234,58 @@ __device__ __forceinline__ int reduce_scatter(float (&v)[N], int lane) {
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
-  return ((lane >> 4) & 1) * (N / 2) + ((lane >> 3) & 1) * (N / 4) + ((lane >> 2) & 1) * (N / 8) +
-         ((lane >> 1) & 1) * (N / 16) + (lane & 1) * (N / 32);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
-// part[b][c0 + j] = sum_{k in [k0,k1)} X[b][k] * W_j[k] for NR rows and the 4 columns (weight rows w + j*wst).
-// X: smem [NR][xs] (xs % 4 == 0, zero padded); weight rows in smem (stride wst % 4 == 0, zero padded);
-// k0, k1 multiples of 4.  One warp; a lane handles 4 consecutive k per 128-wide sweep (LDS.128).
-template <int NR>
+// part[r0 + b][c0 + j] = sum_{k in [k0,k1)} X[r0 + b][k] * W_j[k] for NRB rows and the 4 columns (weight rows w + j*wst).
+// X: smem rows of stride xs (xs % 4 == 0, zero padded); weight rows in smem (stride wst % 4 == 0, zero padded);
+// k0, k1 multiples of 4.  One warp; a lane handles 4 consecutive k per 128-wide sweep (LDS.128); every accumulator is a
+// packed pair (even-k partial, odd-k partial) fed by FFMA2.
 __device__ __forceinline__ void warp_item(const float* __restrict__ X, int xs, const float* __restrict__ w, int wst,
-                                          int k0, int k1, float* part, int ldp, int c0, int lane) {
-  float acc[NR * 4];
+                                          int k0, int k1, float* part, int ldp, int r0, int c0, int lane) {
+  u64 acc[NRB * 4];
 #pragma unroll
-  for (int i = 0; i < NR * 4; ++i) acc[i] = 0.f;
+  for (int i = 0; i < NRB * 4; ++i) acc[i] = 0ull;
   for (int k = k0 + 4 * lane; k < k1; k += 128) {
-    const float4 a0 = *reinterpret_cast<const float4*>(w + k);
-    const float4 a1 = *reinterpret_cast<const float4*>(w + wst + k);
-    const float4 a2 = *reinterpret_cast<const float4*>(w + 2 * wst + k);
-    const float4 a3 = *reinterpret_cast<const float4*>(w + 3 * wst + k);
+    ulonglong2 a[4];
 #pragma unroll
-    for (int b = 0; b < NR; ++b) {
-      const float4 x = *reinterpret_cast<const float4*>(X + b * xs + k);
-      acc[b * 4 + 0] = fmaf(x.w, a0.w, fmaf(x.z, a0.z, fmaf(x.y, a0.y, fmaf(x.x, a0.x, acc[b * 4 + 0]))));
-      acc[b * 4 + 1] = fmaf(x.w, a1.w, fmaf(x.z, a1.z, fmaf(x.y, a1.y, fmaf(x.x, a1.x, acc[b * 4 + 1]))));
-      acc[b * 4 + 2] = fmaf(x.w, a2.w, fmaf(x.z, a2.z, fmaf(x.y, a2.y, fmaf(x.x, a2.x, acc[b * 4 + 2]))));
-      acc[b * 4 + 3] = fmaf(x.w, a3.w, fmaf(x.z, a3.z, fmaf(x.y, a3.y, fmaf(x.x, a3.x, acc[b * 4 + 3]))));
+    for (int j = 0; j < 4; ++j) a[j] = *reinterpret_cast<const ulonglong2*>(w + j * wst + k);
+#pragma unroll
+    for (int b = 0; b < NRB; ++b) {
+      const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(X + (r0 + b) * xs + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        fma2(acc[b * 4 + j], x.x, a[j].x);
+        fma2(acc[b * 4 + j], x.y, a[j].y);
+      }
     }
   }
-  const int base = reduce_scatter<NR * 4>(acc, lane);
+  float v[NRB * 4];
 #pragma unroll
-  for (int i = 0; i < NR / 8; ++i) {
-    const int idx = base + i, b = idx >> 2, j = idx & 3;
-    part[b * ldp + c0 + j] = acc[i];
-  }
+  for (int i = 0; i < NRB * 4; ++i) v[i] = pair_sum(acc[i]);
+  const int idx = reduce16(v, lane);
+  if ((lane & 1) == 0) part[(r0 + (idx >> 2)) * ldp + c0 + (idx & 3)] = v[0];
 }
 
-// number of K slices a product of `ngroups` column groups over K is cut into (all SCAN_NW warps busy when possible)
-__device__ __forceinline__ int k_slices(int ngroups, int K, int& kchunk) {
-  const int Kp = r4(K);
-  int ks = imax(1, SCAN_NW / imax(ngroups, 1));
-  kchunk = ((Kp + ks - 1) / ks + 127) / 128 * 128;
-  return (Kp + kchunk - 1) / kchunk;
-}
-
-// Runs all (column group, K slice) items of one product over the CTA's warps.  Slice s writes its partial sums to
-// PART[s][b][cbase + 4*group + j] (every element written by exactly one lane); the caller sums the slices in order.
-// `wbase`: first weight row of group 0; group g starts at wbase + g*4*wst.  Returns the number of slices.
-// No barrier inside: the caller synchronises before (X complete) and after (PART complete).
-__device__ __forceinline__ int product(const float* X, int xs, const float* wbase, int wst, int ngroups, int K,
+// Runs all (column group, row block, K slice) items of one product over the CTA's warps.  Slice s writes its partial sums
+// to PART[s][b][cbase + 4*group + j] (every element written by exactly one lane); the caller sums the slices in order
+// (bit-reproducible).  `wbase`: first weight row of group 0; group g starts at wbase + g*4*wst.  Returns the number of
+// slices.  No barrier inside: the caller synchronises before (X complete) and after (PART complete).
+__device__ __forceinline__ int product(const float* X, int xs, const float* wbase, int wst, int ngroups, int K, int B,
                                        float* PART, int ldp, int cbase, int tid) {
   if (ngroups <= 0) return 0;
   const int lane = tid & 31, wid = tid >> 5;
-  int kchunk;
-  const int ks = k_slices(ngroups, K, kchunk), Kp = r4(K);
-  for (int item = wid; item < ngroups * ks; item += SCAN_NW) {
-    const int cg = item % ngroups, sl = item / ngroups;
+  const int nrb = (B + NRB - 1) / NRB, Kp = r4(K);
+  int ks = imin(KS_MAX, imax(1, SCAN_NW / (ngroups * nrb)));
+  const int kchunk = ((Kp + ks - 1) / ks + 127) / 128 * 128;
+  ks = (Kp + kchunk - 1) / kchunk;
+  const int per = ngroups * nrb;
+  for (int item = wid; item < per * ks; item += SCAN_NW) {
+    const int sl = item / per, rem = item - sl * per;
+    const int rb = rem / ngroups, cg = rem - rb * ngroups;
     const int k0 = sl * kchunk, k1 = imin(Kp, k0 + kchunk);
-    warp_item<MAXB>(X, xs, wbase + (size_t)cg * 4 * wst, wst, k0, k1, PART + (size_t)sl * MAXB * ldp, ldp, cbase + cg * 4, lane);
+    warp_item(X, xs, wbase + (size_t)cg * 4 * wst, wst, k0, k1, PART + (size_t)sl * MAXB * ldp, ldp, rb * NRB, cbase + cg * 4, lane);
   }
   return ks;
 }
@@ -284,6 +294,28 @@ __device__ __forceinline__ float part_sum(const float* PART, int ldp, int ks, in
   float v = 0.f;
   for (int s = 0; s < ks; ++s) v += PART[((size_t)s * MAXB + b) * ldp + c];
   return v;
+}
+
+// Class-per-lane product (forward logits, backward dz): out[row][lane] = sum_k X[row][k] * W[lane][k] for nr <= MAXRPU rows.
+// Warp (K slice s = wid % CLS_SLICES, row phase wid / CLS_SLICES); partials go to PART[s][row][lane] (fixed-order sum by
+// the caller).  W rows have stride wst = K + 4 (the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups).
+__device__ __forceinline__ void class_product(const float* X, int xs, const float* W, int wst, int D, int Kp, int nr, float* PART,
+                                              int tid) {
+  const int lane = tid & 31, wid = tid >> 5;
+  const int sl = wid % CLS_SLICES, rph = wid / CLS_SLICES, nph = SCAN_NW / CLS_SLICES;
+  const int kc = ((Kp + CLS_SLICES - 1) / CLS_SLICES + 3) / 4 * 4;
+  const int k0 = sl * kc, k1 = imin(Kp, k0 + kc);
+  const float* wrow = W + (size_t)imin(lane, D - 1) * wst;
+  for (int r = rph; r < nr; r += nph) {
+    u64 acc = 0ull;
+    for (int k = k0; k < k1; k += 4) {
+      const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wrow + k);
+      const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(X + r * xs + k);
+      fma2(acc, x.x, w4.x);
+      fma2(acc, x.y, w4.y);
+    }
+    PART[((size_t)sl * MAXRPU + r) * 32 + lane] = pair_sum(acc);
+  }
 }
 
 // Copies 4 rows (row0..row0+3) of a row-major [rows][ld] weight, columns [c0, c0+K), into smem rows of stride `wst` at
@@ -349,11 +381,11 @@ __host__ __device__ inline GeoF make_geo_f(const b200rl_rssm_scan_args& a, int c
   g.oW2 = o;   o += a.D * g.w2st;
   g.oXh = o;   o += MAXB * g.sR;
   g.oXx = o;   o += MAXB * imax(g.sDx, g.sDr);
-  g.oPart = o; o += imax(SCAN_NW * MAXB * g.ldp, SCAN_NW * MAXRPU * 32);
+  g.oPart = o; o += imax(imax(KS_MAX * MAXB * g.ldp, CLS_SLICES * MAXRPU * 32), GPARTS * g.sDx);
   g.oAcc = o;  o += MAXB * g.ldp;
   g.oX0 = o;   o += g.sDx;
   g.oPar = o;  o += g.sR + 2 * g.sDx + 2 * g.sDr;   // h0 | lnx gamma, beta | lnr gamma, beta (read every step)
-  g.oMisc = o; o += 8 * MAXB + 64;
+  g.oMisc = o; o += 8 * MAXB + 64;           // [0,48) flags / statistics; [48,80) and [80,112) per-warp reduction scratch
   g.oInt = o;  o += r4(64 + 64 + SCAN_G);      // z0 class indices, z_{t-1} indices of the owned row, column counts
   g.total = o;
   return g;
@@ -478,7 +510,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     }
     __syncthreads();
     prof_mark(prof, 12, tlast, prof_on);
-    const int ksh = product(Xh, g.sR, Wg, g.wgst, g.ngh * 3, R, PART, ldp, 0, tid);
+    const int ksh = product(Xh, g.sR, Wg, g.wgst, g.ngh * 3, R, B, PART, ldp, 0, tid);
     prof_mark(prof, 1, tlast, prof_on);
     __syncthreads();
     const float acch = pok ? part_sum(PART, ldp, ksh, pb, pc) : 0.f;
@@ -492,6 +524,28 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       if (t > 0 && tid < S) zrow[tid] = (int)__float_as_uint(ll_wait(ws.ll + L.z + ((size_t)(par ^ 1) * MAXB + b) * S + tid, (unsigned)t, sp));
       __syncthreads();
       prof_mark(prof, 2, tlast, prof_on);
+      // gather: thread (column pair cp, part p): part p sums the groups [p*S/4, (p+1)*S/4) in order, all its row loads in
+      // flight at once; the four partials are then added in part order (fixed summation order)
+      const int npairs = Dx >> 1, gper = (S + GPARTS - 1) / GPARTS;
+      float* XG = PART;                          // [GPARTS][sDx] partial rows
+      {
+        const int part = tid >> 8, g_lo = part * gper, g_hi = imin(S, g_lo + gper);
+        for (int cp = tid & 255; cp < npairs; cp += 256) {
+          float2 acc = make_float2(0.f, 0.f);
+          if (t > 0 && f != 1.f)
+            for (int g0 = g_lo; g0 < g_hi; g0 += 8) {
+              float2 v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (g0 + i < g_hi) v[i] = __ldg(reinterpret_cast<const float2*>(a.W_in_t + (size_t)((g0 + i) * D + zrow[g0 + i]) * Dx) + cp);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (g0 + i < g_hi) { acc.x += v[i].x; acc.y += v[i].y; }
+            }
+          *reinterpret_cast<float2*>(XG + part * g.sDx + 2 * cp) = acc;
+        }
+      }
+      __syncthreads();
       float2 xv[2];
       float s = 0.f;
 #pragma unroll
@@ -500,16 +554,8 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
         xv[u] = make_float2(0.f, 0.f);
         if (c < Dx) {
           float2 acc = make_float2(0.f, 0.f);
-          if (t > 0 && f != 1.f)
-            for (int g0 = 0; g0 < S; g0 += 8) {            // 8 row gathers in flight, summed in group order
-              float2 v[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (g0 + i < S) v[i] = __ldg(reinterpret_cast<const float2*>(a.W_in_t + (size_t)((g0 + i) * D + zrow[g0 + i]) * Dx + c));
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (g0 + i < S) { acc.x += v[i].x; acc.y += v[i].y; }
-            }
+          for (int part = 0; part < GPARTS; ++part) { acc.x += XG[part * g.sDx + c]; acc.y += XG[part * g.sDx + c + 1]; }
           float2 aa = make_float2(0.f, 0.f);
           for (int qq = 0; qq < A; ++qq) {
             const float av = a.actions[(row0 + b) * A + qq];
@@ -558,7 +604,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     ll_recv(Xx, xxs, ws.ll + L.x + (size_t)par * MAXB * Dx, Dx, B, Dx, tag, tid, sp);
     __syncthreads();
     prof_mark(prof, 4, tlast, prof_on);
-    const int ksx = product(Xx, xxs, Wg + g.sR, g.wgst, g.ngh * 3, Dx, PART, ldp, 0, tid);
+    const int ksx = product(Xx, xxs, Wg + g.sR, g.wgst, g.ngh * 3, Dx, B, PART, ldp, 0, tid);
     __syncthreads();
     float gpre = 0.f;
     if (pok) {
@@ -654,7 +700,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     ll_recv(Xh, g.sR, ws.ll + L.h + (size_t)par * MAXB * R, R, B, R, tag, tid, sp);   // (own h_in was read above, into `hin`)
     __syncthreads();
     prof_mark(prof, 8, tlast, prof_on);
-    const int ksr = product(Xh, g.sR, Wr1, g.sR, g.ngr, R, PART, ldp, 0, tid);
+    const int ksr = product(Xh, g.sR, Wr1, g.sR, g.ngr, R, B, PART, ldp, 0, tid);
     __syncthreads();
     if (sR_.ok) {
       const float v = part_sum(PART, ldp, ksr, sR_.b, sR_.cj) + pe_pref;
@@ -688,10 +734,10 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
         if (bb < nr)
           for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) { const float d = xr[k] - mu; v = fmaf(d, d, v); }
         v = warp_sum(v);
-        if (lane == 0) misc[56 + wid] = v;
+        if (lane == 0) misc[80 + wid] = v;
         __syncthreads();
         float var = 0.f;
-        for (int i = 0; i < wpr; ++i) var += misc[56 + bb * wpr + i];
+        for (int i = 0; i < wpr; ++i) var += misc[80 + bb * wpr + i];
         const float rstd = rsqrtf(var / (float)Dr + a.eps);
         if (bb < nr) {
           for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) {
@@ -707,27 +753,8 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       }
       __syncthreads();
       prof_mark(prof, 14, tlast, prof_on);
-      // logits: lane = class, warp = K slice, all rows of the unit
-      {
-        const int kc = ((g.sDr + SCAN_NW - 1) / SCAN_NW + 3) / 4 * 4;
-        const int k0 = wid * kc, k1 = imin(g.sDr, k0 + kc);
-        float acc[MAXRPU];
-#pragma unroll
-        for (int i = 0; i < MAXRPU; ++i) acc[i] = 0.f;
-        const float* wrow = W2 + (size_t)imin(lane, D - 1) * g.w2st;
-        for (int k = k0; k < k1; k += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
-#pragma unroll
-          for (int i = 0; i < MAXRPU; ++i)
-            if (i < nr) {
-              const float4 x = *reinterpret_cast<const float4*>(Xx + i * xxs + k);
-              acc[i] = fmaf(x.w, w4.w, fmaf(x.z, w4.z, fmaf(x.y, w4.y, fmaf(x.x, w4.x, acc[i]))));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < MAXRPU; ++i)
-          if (i < nr) PART[((size_t)wid * MAXRPU + i) * 32 + lane] = acc[i];
-      }
+      // logits: lane = class, warp = (K slice, row phase)
+      class_product(Xx, xxs, W2, g.w2st, D, g.sDr, nr, PART, tid);
       __syncthreads();
       prof_mark(prof, 15, tlast, prof_on);
       // one warp per row: the D classes of the group live on the lanes (D <= 32)
@@ -735,7 +762,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
         const int bb = wid, b = rb + bb;
         const bool on = lane < D;
         float lg = 0.f;
-        for (int s2 = 0; s2 < SCAN_NW; ++s2) lg += PART[((size_t)s2 * MAXRPU + bb) * 32 + lane];
+        for (int s2 = 0; s2 < CLS_SLICES; ++s2) lg += PART[((size_t)s2 * MAXRPU + bb) * 32 + lane];
         const float raw = on ? lg + bias2 : -INFINITY;
         const float mx = warp_max(raw);
         const float ex = on ? expf(raw - mx) : 0.f;
@@ -826,7 +853,7 @@ __host__ __device__ inline GeoB make_geo_b(const b200rl_rssm_scan_args& a, int c
   g.oWg = o;   o += (mh + mx) * 4 * g.wgst;    // W_g[:, j] (h part) then W_g[:, R + c] (x part), 3 parts of sR each
   g.oWin = o;  o += a.D * g.winst;             // W_in[:, gq*D + d] of the unit's group
   g.oX = o;    o += MAXB * g.xw;
-  g.oPart = o; o += imax(SCAN_NW * MAXB * g.ldp, SCAN_NW * MAXRPU * 32);
+  g.oPart = o; o += imax(KS_MAX * MAXB * g.ldp, CLS_SLICES * MAXRPU * 32);
   g.oAcc = o;  o += MAXB * g.ldp;
   g.oSt = o;   o += 2 * MAXB * imax(imax(mh * 12, mx * 4), imax(mr * 4, 4));   // (dxh, dxh*xh) staging for the row sums
   g.oDhc = o;  o += MAXB * imax(mh * 4, 4);
@@ -1031,24 +1058,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
         recv_row_sums(ws.ll + L.sd, par ^ 1, rb, nr, (unsigned)bt, 1.f / (float)Dx, S1, S2, tid, sp);
         __syncthreads();
         prof_mark(prof, 17, tlast, prof_on);
-        const int kc = ((g.sDx + SCAN_NW - 1) / SCAN_NW + 3) / 4 * 4;
-        const int k0 = wid * kc, k1 = imin(g.sDx, k0 + kc);
-        float acc[MAXRPU];
-#pragma unroll
-        for (int i = 0; i < MAXRPU; ++i) acc[i] = 0.f;
-        const float* wrow = WinU + (size_t)imin(lane, D - 1) * g.winst;
-        for (int k = k0; k < k1; k += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
-#pragma unroll
-          for (int i = 0; i < MAXRPU; ++i)
-            if (i < nr) {
-              const float4 x = *reinterpret_cast<const float4*>(X + i * xw + k);
-              acc[i] = fmaf(x.w, w4.w, fmaf(x.z, w4.z, fmaf(x.y, w4.y, fmaf(x.x, w4.x, acc[i]))));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < MAXRPU; ++i)
-          if (i < nr) PART[((size_t)wid * MAXRPU + i) * 32 + lane] = acc[i];
+        class_product(X, xw, WinU, g.winst, D, g.sDx, nr, PART, tid);
         __syncthreads();
       }
       if (wid < nr) {
@@ -1057,7 +1067,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
         float dz = u_dl;
         if (!last) {
           float p1 = 0.f;
-          for (int s2 = 0; s2 < SCAN_NW; ++s2) p1 += PART[((size_t)s2 * MAXRPU + bb) * 32 + lane];
+          for (int s2 = 0; s2 < CLS_SLICES; ++s2) p1 += PART[((size_t)s2 * MAXRPU + bb) * 32 + lane];
           if (on) {
             const float mu = LNX1[b * 2], rstd = LNX1[b * 2 + 1];
             const float p2 = rstd * (u_qx - mu * wsi);
@@ -1095,7 +1105,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     ll_recv(X, xw, ws.ll + L.a + (size_t)par * MAXB * Z, Z, B, Z, tag, tid, sp);
     __syncthreads();
     prof_mark(prof, 19, tlast, prof_on);
-    const int ks2 = product(X, xw, W2T, g.sZ, g.ngr, Z, PART, ldp, 0, tid);
+    const int ks2 = product(X, xw, W2T, g.sZ, g.ngr, Z, B, PART, ldp, 0, tid);
     __syncthreads();
     float dact_r = 0.f;
     if (sR_.ok) {
@@ -1121,7 +1131,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     recv_row_sums(ws.ll + L.sb, par, 0, B, tag, 1.f / (float)Dr, S1, S2, tid, sp);
     __syncthreads();
     prof_mark(prof, 21, tlast, prof_on);
-    const int ks1 = product(X, xw, W1T, g.sDr, g.ngh, Dr, PART, ldp, 0, tid);
+    const int ks1 = product(X, xw, W1T, g.sDr, g.ngh, Dr, B, PART, ldp, 0, tid);
     __syncthreads();
     float dhin_gate = 0.f, dgl[3] = {0.f, 0.f, 0.f};
     if (sH.ok) {
@@ -1167,7 +1177,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     for (int part = 0; part < 2; ++part)
       ll_recv(X + part * g.sR, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)part * R, 3 * R, B, R, tag, tid, sp);
     __syncthreads();
-    const int ksa = product(X, xw, WgT, g.wgst, g.ngh + g.ngx, 2 * g.sR, PART, ldp, 0, tid);
+    const int ksa = product(X, xw, WgT, g.wgst, g.ngh + g.ngx, 2 * g.sR, B, PART, ldp, 0, tid);
     __syncthreads();
     float acc_h = sH.ok ? part_sum(PART, ldp, ksa, sH.b, sH.cj) : 0.f;
     float acc_x = sX.ok ? part_sum(PART, ldp, ksa, sX.b, nh4 + sX.cj) : 0.f;
@@ -1175,7 +1185,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     ll_recv(X, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)2 * R, 3 * R, B, R, tag, tid, sp);
     recv_row_sums(ws.ll + L.sc, par, 0, B, tag, 1.f / (float)(3 * R), S1, S2, tid, sp);
     __syncthreads();
-    const int ksb = product(X, xw, WgT + 2 * g.sR, g.wgst, g.ngh + g.ngx, R, PART, ldp, 0, tid);
+    const int ksb = product(X, xw, WgT + 2 * g.sR, g.wgst, g.ngh + g.ngx, R, B, PART, ldp, 0, tid);
     __syncthreads();
     prof_mark(prof, 23, tlast, prof_on);
     float dact_x = 0.f;
