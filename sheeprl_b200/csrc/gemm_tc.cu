@@ -215,7 +215,7 @@ struct TileGeo {
                            // from the channel-last big image by 4-D TMA boxes of 32 pixels (Cout = big channels)
 };
 
-template <int BN>
+template <int BN, int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float* __restrict__ C,
                const float* __restrict__ bias, int M, int N, int K, int ldc, int accumulate, const TileGeo geo) {
@@ -334,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int k4 = 0; k4 < BK / 8; ++k4) {
           const uint64_t ob = (uint64_t)k4 * b_step;
-          if (geo.passes == 3) {
+          if (PASSES == 3) {
             // small cross terms first, then the leading term
             umma_tf32_ts(acc, ta_hi + 8u * k4, dbl0 + ob, idesc, !(chunk_start && k4 == 0));
             umma_tf32_ts(acc, ta_lo + 8u * k4, dbh0 + ob, idesc, 1);
@@ -383,7 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         const uint32_t ta = tmem + (((uint32_t)(t & ~31)) << 16) + A_TMEM0 + 64u * (uint32_t)st;
         tmem_st32(ta, hi);
-        if (geo.passes == 3) {
+        if (PASSES == 3) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const float x = __uint_as_float(hi[k]);
@@ -394,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       float4* bh = reinterpret_cast<float4*>(s.b_hi[st]);
       float4* bl = reinterpret_cast<float4*>(s.b_lo[st]);
-      if (geo.passes == 3)
+      if (PASSES == 3)
 #pragma unroll
       for (int i = 0; i < BN * BK / 4 / NSPLIT_THREADS; ++i) {
         const int idx = t + i * NSPLIT_THREADS;
@@ -709,6 +709,24 @@ splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, cons
   }
 }
 
+// one launch site for the four instantiations (tile width x TF32 passes)
+#define LAUNCH_GEMM_TC(BN_, PASSES_, grid_, st_, ...)                                                                \
+  do {                                                                                                               \
+    const size_t smem__ = sizeof(Smem<BN_>) + 1024;                                                                  \
+    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, PASSES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem__)); \
+    gemm_tc_kernel<BN_, PASSES_><<<grid_, NTHREADS, smem__, st_>>>(__VA_ARGS__);                                      \
+  } while (0)
+#define DISPATCH_GEMM_TC(BN_val, passes_val, grid_, st_, ...)                                  \
+  do {                                                                                          \
+    if ((BN_val) == 64) {                                                                       \
+      if ((passes_val) == 3) LAUNCH_GEMM_TC(64, 3, grid_, st_, __VA_ARGS__);                    \
+      else LAUNCH_GEMM_TC(64, 1, grid_, st_, __VA_ARGS__);                                      \
+    } else {                                                                                    \
+      if ((passes_val) == 3) LAUNCH_GEMM_TC(128, 3, grid_, st_, __VA_ARGS__);                   \
+      else LAUNCH_GEMM_TC(128, 1, grid_, st_, __VA_ARGS__);                                     \
+    }                                                                                           \
+  } while (0)
+
 int launch_conv(int mode, const float* img, const float* Wp, float* out, const float* bias, int NB, int h, int w, int Cin,
                 int Cout, cudaStream_t st) {
   TileGeo g = {};
@@ -729,15 +747,7 @@ int launch_conv(int mode, const float* img, const float* Wp, float* out, const f
   dim3 grid((Cout + BN - 1) / BN, 1, mode == MODE_UP ? 4 : 1);
   grid.y = persistent_grid_y(mtiles, grid.x, grid.z);
   const int M = NB * h * w;  // unused by conv addressing; row validity comes from geo
-  if (BN == 64) {
-    const size_t smem = sizeof(Smem<64>) + 1024;
-    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma, mb, out, bias, M, Cout, K, Cout, 0, g);
-  } else {
-    const size_t smem = sizeof(Smem<128>) + 1024;
-    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, out, bias, M, Cout, K, Cout, 0, g);
-  }
+  DISPATCH_GEMM_TC(BN, g.passes, grid, st, ma, mb, out, bias, M, Cout, K, Cout, 0, g);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }
@@ -834,15 +844,7 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
   }
   g.mtiles = (int)grid.y;
   grid.y = persistent_grid_y(g.mtiles, grid.x, grid.z);
-  if (BN == 64) {
-    const size_t smem = sizeof(Smem<64>) + 1024;
-    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate, g);
-  } else {
-    const size_t smem = sizeof(Smem<128>) + 1024;
-    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, accumulate, g);
-  }
+  DISPATCH_GEMM_TC(BN, g.passes, grid, st, ma, mb, C, bias, M, N, K, ldc, accumulate, g);
   RL_CHECK_LAUNCH();
   if (g.ksplits > 1) {
     splitk_reduce_kernel<<<ceil_div((long long)M * ((N + 3) / 4), 256), 256, 0, st>>>(g.part, C, bias, M, N, ldc, g.ksplits, g.mpad,
@@ -891,15 +893,7 @@ extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float
     g.ldw = (int)grid.x * BN;
     if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, st, &g.part)) return rc;
   }
-  if (BN == 64) {
-    const size_t smem = sizeof(Smem<64>) + 1024;
-    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(ma, mb, G, nullptr, M, N, P, N, 0, g);
-  } else {
-    const size_t smem = sizeof(Smem<128>) + 1024;
-    RL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(ma, mb, G, nullptr, M, N, P, N, 0, g);
-  }
+  DISPATCH_GEMM_TC(BN, g.passes, grid, st, ma, mb, G, nullptr, M, N, P, N, 0, g);
   RL_CHECK_LAUNCH();
   if (g.ksplits > 1) {
     splitk_reduce_kernel<<<ceil_div((long long)M * ((N + 3) / 4), 256), 256, 0, st>>>(g.part, G, nullptr, M, N, N, g.ksplits, g.mpad,
