@@ -16,6 +16,22 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def build_xl_layernorm(cu, dev="cuda"):
+    """the LayerNorm launches of the XL model (BASELINE configs[4]: conv channels 96..768 on 4096 images, dense 1024 on the
+    65 536 imagined rows, the GRU's joint LayerNorm over 3 x 4096)"""
+    f = lambda *s: torch.randn(*s, device=dev)  # noqa: E731
+    z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
+    out = []
+    for M, C in ((4096 * 32 * 32, 96), (4096 * 16 * 16, 192), (4096 * 8 * 8, 384), (4096 * 4 * 4, 768), (65536, 1024),
+                 (4096, 12288), (64, 12288), (64, 1024)):
+        X, Y, dY, dX = f(M, C), z(M, C), f(M, C), z(M, C)
+        gam, bet, dg, db = f(C) + 1, f(C), z(C), z(C)
+        out.append((f"ln_act_fwd [{M},{C}]", 8 * M * C, lambda X=X, Y=Y, gam=gam, bet=bet: cu.ln_act_fwd(X, gam, bet, 1e-3, 1, Y)))
+        out.append((f"ln_act_bwd [{M},{C}]", 12 * M * C,
+                    lambda X=X, dY=dY, dX=dX, gam=gam, bet=bet, dg=dg, db=db: cu.ln_act_bwd(X, gam, bet, 1e-3, 1, dY, dX, dg, db)))
+    return out
+
+
 def build(cu, dev="cuda"):
     """[(name, algorithmic_bytes, thunk)]"""
     f = lambda *s: torch.randn(*s, device=dev)  # noqa: E731
@@ -77,7 +93,7 @@ def main():
     from sheeprl_b200.lib import CudaOps
 
     cu = CudaOps()
-    kernels = build(cu)
+    kernels = build_xl_layernorm(cu) if "--xl-layernorm" in sys.argv else build(cu)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     for _, _, fn in kernels:                                                   # warm-up (module load, scratch)
         fn()
