@@ -335,6 +335,9 @@ __device__ __forceinline__ void load_cols4(float* dst, int wst, const float* W, 
   }
 }
 
+// per-phase cycle counters: accumulated in SHARED memory by thread 0 of CTA 0 / 1 (a global read-modify-write per mark
+// would stall that warp for an L2 round trip ~16 times per step and make the instrumented CTAs the stragglers of every
+// hand-off), flushed to the workspace when the kernel ends
 __device__ __forceinline__ void prof_mark(long long* prof, int slot, long long& last, bool on) {
   if (on) {
     const long long now = clock64();
@@ -356,7 +359,9 @@ struct GeoF {
   int oWg, oWr1, oW2, oXh, oXx, oPart, oAcc, oX0, oPar, oMisc, oInt, total;
 };
 
-__host__ __device__ inline GeoF make_geo_f(const b200rl_rssm_scan_args& a, int cta) {
+struct Dims { int B, S, D, R, Dx, Dr; };
+
+__host__ __device__ inline GeoF make_geo_f(const Dims& a, int cta) {
   GeoF g;
   g.ngh = owned_groups(a.R, cta);
   g.ngr = owned_groups(a.Dr, cta);
@@ -391,13 +396,17 @@ __host__ __device__ inline GeoF make_geo_f(const b200rl_rssm_scan_args& a, int c
   return g;
 }
 
+// FIX: the model widths are compile-time constants (the BASELINE S model: stochastic 32x32, recurrent / dense / hidden
+// 512) — index arithmetic and loop bounds fold; the generic instantiation reads them from the arguments.
+template <bool FIX>
 __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_rssm_scan_args a) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int cta = blockIdx.x;
-  const int T = a.T, B = a.B, S = a.S, D = a.D, Z = S * D, R = a.R, A = a.A, Dx = a.Dx, Dr = a.Dr;
+  const int T = a.T, B = a.B, A = a.A;
+  const int S = FIX ? 32 : a.S, D = FIX ? 32 : a.D, Z = S * D, R = FIX ? 512 : a.R, Dx = FIX ? 512 : a.Dx, Dr = FIX ? 512 : a.Dr;
   const int NB = T * B;
-  const GeoF g = make_geo_f(a, cta);
+  const GeoF g = make_geo_f(Dims{B, S, D, R, Dx, Dr}, cta);
   const Workspace ws = carve(a.workspace, T, B, S, D, Dx, R, Dr);
   const LLGeo L = make_ll(S, Dx, R, Dr, Z);
   float* Wg = sm + g.oWg;       // [ngh*12][wgst]  rows: (group, part r/c/u, col-in-group); cols [h (sR) | x (sDx)]
@@ -419,8 +428,10 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
   int* nctab = zrow + 64;
   const int ldp = g.ldp, xxs = imax(g.sDx, g.sDr);
   const bool owner = g.owner_row >= 0, sampler = g.unit_g >= 0;
+  __shared__ long long sprof[32];
   const bool prof_on = (cta < 2) && tid == 0;
-  long long* prof = ws.prof + cta * 32;
+  long long* prof = sprof;
+  if (tid < 32) sprof[tid] = 0;
   long long tlast = prof_on ? clock64() : 0;
   Spin sp;
   sp.init(ws.error);
@@ -798,8 +809,10 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       prof_mark(prof, 11, tlast, prof_on);
     }
     __syncthreads();
-    if (sp.dead) return;   // a hand-off timed out somewhere: bail out, never hang
+    if (sp.dead) break;    // a hand-off timed out somewhere: bail out, never hang
   }
+  if (prof_on)
+    for (int i = 0; i < 32; ++i) ws.prof[cta * 32 + i] = sprof[i];
 }
 
 // =====================================================================================================
@@ -826,7 +839,7 @@ struct GeoB {
   int oW2, oW1, oWg, oWin, oX, oPart, oAcc, oSt, oDhc, oDh0, oWs, oMisc, total;
 };
 
-__host__ __device__ inline GeoB make_geo_b(const b200rl_rssm_scan_args& a, int cta) {
+__host__ __device__ inline GeoB make_geo_b(const Dims& a, int cta) {
   GeoB g;
   const int Z = a.S * a.D;
   g.ngh = owned_groups(a.R, cta);
@@ -912,14 +925,16 @@ __device__ __forceinline__ void send_row_sums(const float* ST, int ncols, int B,
   }
 }
 
+template <bool FIX>
 __global__ void __launch_bounds__(SCAN_NT, 1)
 rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads q) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int cta = blockIdx.x;
-  const int T = a.T, B = a.B, S = a.S, D = a.D, Z = S * D, R = a.R, Dx = a.Dx, Dr = a.Dr;
+  const int T = a.T, B = a.B;
+  const int S = FIX ? 32 : a.S, D = FIX ? 32 : a.D, Z = S * D, R = FIX ? 512 : a.R, Dx = FIX ? 512 : a.Dx, Dr = FIX ? 512 : a.Dr;
   const int KG = R + Dx, KIN = Z + a.A, NB = T * B;
-  const GeoB g = make_geo_b(a, cta);
+  const GeoB g = make_geo_b(Dims{B, S, D, R, Dx, Dr}, cta);
   const Workspace ws = carve(a.workspace, T, B, S, D, Dx, R, Dr);
   const LLGeo L = make_ll(S, Dx, R, Dr, Z);
   const int mh = owned_groups(R, 0), mx = owned_groups(Dx, 0);
@@ -944,8 +959,10 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
   const int xw = g.xw, ldp = g.ldp;
   const int nh4 = g.ngh * 4, nx4 = g.ngx * 4, nr4 = g.ngr * 4;
   const bool unit = g.unit_g >= 0;
+  __shared__ long long sprof[32];
   const bool prof_on = (cta < 2) && tid == 0;
-  long long* prof = ws.prof + cta * 32;
+  long long* prof = sprof;
+  if (tid < 32) sprof[tid] = 0;
   long long tlast = prof_on ? clock64() : 0;
   Spin sp;
   sp.init(ws.error);
@@ -1234,7 +1251,12 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     if (col < R) q.d_h0[col] = dh0_acc;
   }
   (void)DH0;
+  if (prof_on)
+    for (int i = 0; i < 32; ++i) ws.prof[cta * 32 + i] = sprof[i];
 }
+
+// the BASELINE S model runs the instantiation with compile-time widths
+bool fixed_dims(const b200rl_rssm_scan_args& a) { return a.S == 32 && a.D == 32 && a.R == 512 && a.Dx == 512 && a.Dr == 512; }
 
 int scan_check(const b200rl_rssm_scan_args& a) {
   RL_CHECK_ARG(a.B >= 1 && a.B <= MAXB, "persistent scan supports batch <= 16 rows per rank");
@@ -1261,20 +1283,22 @@ extern "C" int b200rl_rssm_scan_fwd(const b200rl_rssm_scan_args* args, cudaStrea
   RL_CHECK_ARG(args, "null args");
   const b200rl_rssm_scan_args& a = *args;
   if (int rc = scan_check(a)) return rc;
-  const GeoF g = make_geo_f(a, 0);
+  const GeoF g = make_geo_f(Dims{a.B, a.S, a.D, a.R, a.Dx, a.Dr}, 0);
   const size_t smem = sizeof(float) * (size_t)g.total;
   RL_CHECK_ARG(smem <= 227 * 1024, "weight slices do not fit in shared memory for this model size");
-  RL_CUDA(cudaFuncSetAttribute(rssm_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool fix = fixed_dims(a);
+  void* fn = fix ? (void*)rssm_scan_fwd_kernel<true> : (void*)rssm_scan_fwd_kernel<false>;
+  RL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RL_CUDA(cudaMemsetAsync(a.workspace, 0, WS_HEADER + WS_PROF + ws_ll_bytes(a.S, a.D, a.Dx, a.R, a.Dr), st));
   void* kargs[] = {(void*)args};
-  RL_CUDA(cudaLaunchCooperativeKernel((void*)rssm_scan_fwd_kernel, dim3(SCAN_G), dim3(SCAN_NT), kargs, smem, st));
+  RL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(SCAN_G), dim3(SCAN_NT), kargs, smem, st));
   return B200RL_OK;
 }
 
 extern "C" int b200rl_rssm_scan_bwd_check(const b200rl_rssm_scan_args* args) {
   RL_CHECK_ARG(args, "null args");
   if (int rc = scan_check(*args)) return rc;
-  const GeoB g = make_geo_b(*args, 0);
+  const GeoB g = make_geo_b(Dims{args->B, args->S, args->D, args->R, args->Dx, args->Dr}, 0);
   RL_CHECK_ARG(sizeof(float) * (size_t)g.total <= 227 * 1024, "weight slices do not fit in shared memory for this model size");
   return B200RL_OK;
 }
@@ -1285,14 +1309,16 @@ extern "C" int b200rl_rssm_scan_bwd(const b200rl_rssm_scan_args* args, const b20
   const b200rl_rssm_scan_args& a = *args;
   if (int rc = scan_check(a)) return rc;
   RL_CHECK_ARG(grads->q_r && grads->q_g && grads->q_x, "q_r / q_g / q_x (pre-activation x weight products) are required");
-  const GeoB g = make_geo_b(a, 0);
+  const GeoB g = make_geo_b(Dims{a.B, a.S, a.D, a.R, a.Dx, a.Dr}, 0);
   const size_t smem = sizeof(float) * (size_t)g.total;
   RL_CHECK_ARG(smem <= 227 * 1024, "weight slices do not fit in shared memory for this model size");
-  RL_CUDA(cudaFuncSetAttribute(rssm_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool fix = fixed_dims(a);
+  void* fn = fix ? (void*)rssm_scan_bwd_kernel<true> : (void*)rssm_scan_bwd_kernel<false>;
+  RL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // header + LL region are reset; the forward's saves (class indices, LayerNorm statistics) behind them stay
   RL_CUDA(cudaMemsetAsync(a.workspace, 0, WS_HEADER + WS_PROF + ws_ll_bytes(a.S, a.D, a.Dx, a.R, a.Dr), st));
   void* kargs[] = {(void*)args, (void*)grads};
-  RL_CUDA(cudaLaunchCooperativeKernel((void*)rssm_scan_bwd_kernel, dim3(SCAN_G), dim3(SCAN_NT), kargs, smem, st));
+  RL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(SCAN_G), dim3(SCAN_NT), kargs, smem, st));
   return B200RL_OK;
 }
 
