@@ -135,6 +135,155 @@ ln_act_bwd_kernel(const float* __restrict__ X, const float* __restrict__ gamma, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Wide rows (C > 1536, e.g. the XL GRU's joint LayerNorm over 3 x 4096 channels): one CTA of 512 threads per row at a
+// time, the row held in registers (up to WNV float4 per thread), block-wide statistics.  The warp-per-row kernels above
+// need many rows to fill the machine; the XL per-step scan has 64 rows of 12 288 floats (268 us -> HBM/latency bound).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int WIDE_NT = 512, WNV = 8;   // C <= 4 * WIDE_NT * WNV = 16384
+
+__device__ __forceinline__ float block_sum512(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = (lane < WIDE_NT / 32) ? red[lane] : 0.f;
+  return warp_sum(r);
+}
+
+__global__ void __launch_bounds__(WIDE_NT)
+ln_act_fwd_wide_kernel(const float* __restrict__ X, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float* __restrict__ Y, long long M, int C, long long ldx, long long ldy, float eps, int act) {
+  __shared__ float red[32];
+  const int n4 = C >> 2;
+  const float invC = 1.f / (float)C;
+  for (long long r = blockIdx.x; r < M; r += gridDim.x) {
+    const float4* x4 = reinterpret_cast<const float4*>(X + r * ldx);
+    float4 v[WNV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < WNV; ++i) {
+      const int c = threadIdx.x + i * WIDE_NT;
+      v[i] = (c < n4) ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = block_sum512(s, red) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < WNV; ++i) {
+      const int c = threadIdx.x + i * WIDE_NT;
+      if (c < n4) {
+        const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(block_sum512(q, red) * invC + eps);
+    float4* y4 = reinterpret_cast<float4*>(Y + r * ldy);
+#pragma unroll
+    for (int i = 0; i < WNV; ++i) {
+      const int c = threadIdx.x + i * WIDE_NT;
+      if (c < n4) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[c], b = reinterpret_cast<const float4*>(beta)[c];
+        float4 o;
+        o.x = act_fwd(act, (v[i].x - mu) * rstd * g.x + b.x);
+        o.y = act_fwd(act, (v[i].y - mu) * rstd * g.y + b.y);
+        o.z = act_fwd(act, (v[i].z - mu) * rstd * g.z + b.z);
+        o.w = act_fwd(act, (v[i].w - mu) * rstd * g.w + b.w);
+        y4[c] = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WIDE_NT)
+ln_act_bwd_wide_kernel(const float* __restrict__ X, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const float* dY, float* dX, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C,
+                       long long ldx, long long lddy, long long lddx, float eps, int act) {
+  __shared__ float red[32];
+  const int n4 = C >> 2;
+  const float invC = 1.f / (float)C;
+  const bool want_param = dgamma != nullptr;
+  float4 ag[WNV], ab[WNV];
+#pragma unroll
+  for (int i = 0; i < WNV; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  for (long long r = blockIdx.x; r < M; r += gridDim.x) {
+    const float4* x4 = reinterpret_cast<const float4*>(X + r * ldx);
+    const float4* d4 = reinterpret_cast<const float4*>(dY + r * lddy);
+    float4 v[WNV], d[WNV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < WNV; ++i) {
+      const int c = threadIdx.x + i * WIDE_NT;
+      v[i] = (c < n4) ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[i] = (c < n4) ? d4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mu = block_sum512(s, red) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < WNV; ++i) {
+      const int c = threadIdx.x + i * WIDE_NT;
+      if (c < n4) {
+        const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(block_sum512(q, red) * invC + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < WNV; ++i) {
+      const int c = threadIdx.x + i * WIDE_NT;
+      if (c < n4) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[c], b = reinterpret_cast<const float4*>(beta)[c];
+        float4 xh, dl;
+        xh.x = (v[i].x - mu) * rstd; xh.y = (v[i].y - mu) * rstd; xh.z = (v[i].z - mu) * rstd; xh.w = (v[i].w - mu) * rstd;
+        dl.x = act_bwd(act, xh.x * g.x + b.x, d[i].x); dl.y = act_bwd(act, xh.y * g.y + b.y, d[i].y);
+        dl.z = act_bwd(act, xh.z * g.z + b.z, d[i].z); dl.w = act_bwd(act, xh.w * g.w + b.w, d[i].w);
+        ag[i].x += dl.x * xh.x; ag[i].y += dl.y * xh.y; ag[i].z += dl.z * xh.z; ag[i].w += dl.w * xh.w;
+        ab[i].x += dl.x; ab[i].y += dl.y; ab[i].z += dl.z; ab[i].w += dl.w;
+        d[i].x = dl.x * g.x; d[i].y = dl.y * g.y; d[i].z = dl.z * g.z; d[i].w = dl.w * g.w;
+        v[i] = xh;
+        s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+        s2 += (d[i].x * xh.x + d[i].y * xh.y) + (d[i].z * xh.z + d[i].w * xh.w);
+      }
+    }
+    s1 = block_sum512(s1, red) * invC;
+    s2 = block_sum512(s2, red) * invC;
+    float4* o4 = reinterpret_cast<float4*>(dX + r * lddx);
+#pragma unroll
+    for (int i = 0; i < WNV; ++i) {
+      const int c = threadIdx.x + i * WIDE_NT;
+      if (c < n4) {
+        float4 o;
+        o.x = rstd * (d[i].x - s1 - v[i].x * s2); o.y = rstd * (d[i].y - s1 - v[i].y * s2);
+        o.z = rstd * (d[i].z - s1 - v[i].z * s2); o.w = rstd * (d[i].w - s1 - v[i].w * s2);
+        o4[c] = o;
+      }
+    }
+  }
+  if (want_param) {
+#pragma unroll
+    for (int i = 0; i < WNV; ++i) {
+      const int c = threadIdx.x + i * WIDE_NT;
+      if (c < n4) {
+        atomicAdd(&dgamma[4 * c + 0], ag[i].x); atomicAdd(&dgamma[4 * c + 1], ag[i].y);
+        atomicAdd(&dgamma[4 * c + 2], ag[i].z); atomicAdd(&dgamma[4 * c + 3], ag[i].w);
+        atomicAdd(&dbeta[4 * c + 0], ab[i].x); atomicAdd(&dbeta[4 * c + 1], ab[i].y);
+        atomicAdd(&dbeta[4 * c + 2], ab[i].z); atomicAdd(&dbeta[4 * c + 3], ab[i].w);
+      }
+    }
+  }
+}
+
+bool wide_ok(int C, long long ld0, long long ld1, long long ld2, const void* p0, const void* p1, const void* p2, const void* g,
+             const void* b) {
+  if (C <= 1536 || (C & 3) || C > 4 * WIDE_NT * WNV) return false;
+  if ((ld0 | ld1 | ld2) & 3) return false;
+  return ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) |
+           reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
 // out[c] (+)= sum_m X[m,c]; blockDim = (32, 8); out pre-zeroed by the host wrapper unless accumulating.
 __global__ void col_sum_kernel(const float* __restrict__ X, float* __restrict__ out, long long M, int C,
                                long long ldx, long long rows_per_block) {
@@ -362,6 +511,12 @@ extern "C" int b200rl_ln_act_fwd(const float* X, const float* gamma, const float
     RL_CHECK_LAUNCH();
     return B200RL_OK;
   }
+  if (wide_ok(C, ldx, ldy, 0, X, Y, nullptr, gamma, beta)) {
+    const int grid = (int)(M < 4LL * kNumSMs ? M : 4LL * kNumSMs);
+    ln_act_fwd_wide_kernel<<<grid, WIDE_NT, 0, st>>>(X, gamma, beta, Y, M, C, ldx, ldy, eps, act);
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
   ln_act_fwd_kernel<<<grid_for_rows(M), 256, 0, st>>>(X, gamma, beta, Y, M, C, ldx, ldy, eps, act);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
@@ -402,6 +557,12 @@ extern "C" int b200rl_ln_act_bwd(const float* X, const float* gamma, const float
       default: LN_BWD_VEC(32, 12); break;
     }
 #undef LN_BWD_VEC
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
+  if (wide_ok(C, ldx, lddy, lddx, X, dY, dX, gamma, beta)) {
+    const int wgrid = (int)(M < 2LL * kNumSMs ? M : 2LL * kNumSMs);
+    ln_act_bwd_wide_kernel<<<wgrid, WIDE_NT, 0, st>>>(X, gamma, beta, dY, dX, dgamma, dbeta, M, C, ldx, lddy, lddx, eps, act);
     RL_CHECK_LAUNCH();
     return B200RL_OK;
   }

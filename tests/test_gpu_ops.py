@@ -171,7 +171,11 @@ def test_gemm(ops, M, N, K, tA, tB, mode):
     close(Cg, Cc, rtol=2e-6 * max(K, 8) ** 0.5, what="gemm")
 
 
-@pytest.mark.parametrize("M,C", [(1024, 512), (1000, 32), (16, 1536), (37, 72), (5, 4), (4096, 255), (64, 3)])
+@pytest.mark.parametrize("M,C", [(1024, 512), (1000, 32), (16, 1536), (37, 72), (5, 4), (4096, 255), (64, 3),
+                                 # widths of the M / L / XL models (register-resident rows) and the XL GRU's 3 x 4096
+                                 # joint LayerNorm (one CTA per row)
+                                 (1000, 96), (500, 192), (300, 384), (100, 768), (64, 640), (128, 48), (64, 12288),
+                                 (300, 3072), (3, 16384)])
 @pytest.mark.parametrize("act", [0, 1])
 def test_ln_act(ops, M, C, act):
     cu, em = ops
