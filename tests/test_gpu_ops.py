@@ -52,6 +52,8 @@ GEMM_SHAPES = [
     (255, 512, 15360, True, False), (4096, 1536, 1024, True, False), (1024, 4608, 512, False, False),
     # MN-major operands with ragged tiles in every dimension (TMA zero fill on both box axes)
     (257, 129, 100, True, False), (300, 200, 68, False, False), (129, 52, 36, True, True), (1024, 1024, 1026, True, False),
+    # fewer rows than one 128-row tile (the 64-row products of the per-step scan at the XL width): forward, dX, dW
+    (64, 3072, 1280, False, True), (64, 1280, 3072, False, False), (3072, 1280, 64, True, False), (40, 512, 512, False, True),
 ]
 
 
