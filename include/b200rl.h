@@ -129,7 +129,6 @@ typedef struct b200rl_rssm_scan_args {
   float* latent;                              /* [T*B, ld_lat]: z (S*D) | h (R) */
   float *z_in, *h_in, *a_in, *x_pre, *x_act, *g_pre, *g_ln, *tr_pre, *tr_act, *rp_pre, *rp_act;
   float *post_raw, *prior_raw, *post_mix, *prior_mix;
-  const float* W_in_t;                        /* [S*D + A, Dx]: W_in transposed (one-hot z -> row gather) */
   void* workspace;
   long long workspace_bytes;
 } b200rl_rssm_scan_args;
@@ -155,7 +154,7 @@ int b200rl_rssm_scan_bwd(const b200rl_rssm_scan_args* args, const b200rl_rssm_sc
 /* envelope check of the backward kernel for `args` (non-zero + last_error if it cannot run); launches nothing */
 int b200rl_rssm_scan_bwd_check(const b200rl_rssm_scan_args* args);
 int b200rl_rssm_scan_error(const void* workspace, cudaStream_t stream);
-/* cycle counters (2 x 32 int64: CTA 0 = a row owner, CTA 1) accumulated per phase by the last launch on `workspace` */
+/* cycle counters (2 x 32 int64: CTA 0, CTA 1) accumulated per phase by the last launch on `workspace` */
 int b200rl_rssm_scan_profile(const void* workspace, long long* out64, cudaStream_t stream);
 
 /* ---- losses (value + seed gradient) -----------------------------------------------------------------

@@ -26,8 +26,8 @@
 //     LayerNorm partial statistics, h rows, rp rows), four per backward step.
 //   * Work that does not depend on the newest hand-off is issued before waiting for it (the h-part of the GRU product
 //     runs while the x rows are still being built; input prefetches at step start).
-//   * z_{t-1} is one-hot per group, so z W_in^T is a gather of S rows of W_in^T (read from L2 by the CTA that owns
-//     the batch row: it then normalises the full row once, instead of every CTA normalising every row).
+//   * z_{t-1} is one-hot per group, so z W_in^T is a gather of S weights per output from the CTA's W_in slice; the x
+//     LayerNorm runs on partial statistics exchanged with the values (like the GRU's), no CTA is a serial row owner.
 //   * Products: a warp takes a (4-column group) x (K slice) item: 16 rows x 4 columns of accumulators per lane,
 //     128-bit shared loads along K, a 62-shuffle reduce-scatter; K-slice partials are summed in a fixed order
 //     (bit-reproducible).  The 32 classes of a categorical sit on the 32 lanes of a warp.
@@ -41,13 +41,11 @@ constexpr int SCAN_NT = 512;   // threads per CTA: the scan is latency-bound (nc
                                // 8 warps / SM), so every phase is spread over 32 warps with short per-warp instruction streams
 constexpr int SCAN_NW = SCAN_NT / 32;
 constexpr int MAXB = 16;
-constexpr int OWN_STRIDE = SCAN_G / MAXB;   // batch row b is owned by CTA b * OWN_STRIDE
 constexpr int MAXRPU = 8;      // rows of one sampling unit (S <= 64 groups over 128 CTAs -> >= 2 row splits)
-constexpr int LL_UNROLL = 4;   // 16-byte loads in flight per thread while receiving rows
+constexpr int LL_UNROLL = 8;   // 16-byte loads in flight per thread while receiving rows (one L2 round trip per batch)
 constexpr int NRB = 4;         // rows of one product item (4 rows x 4 columns of packed accumulators per lane)
 constexpr int KS_MAX = 8;      // K slices of a product (rows of the partial buffer)
 constexpr int CLS_SLICES = 8;  // K slices of the class-per-lane products (logits / dz)
-constexpr int GPARTS = SCAN_NT / 256;   // thread groups of the owner's row gather (each sums a contiguous range of groups)
 
 typedef unsigned long long u64;
 
@@ -71,22 +69,23 @@ __host__ __device__ inline int owned_cols(int width, int cta) {
 // ---------------------------------------------------------------------------------------------------------------
 struct Workspace {
   int* error;
-  long long* prof;       // [2][32] cycle counters of CTA 0 (a row owner) and CTA 1 (profiling aid)
+  long long* prof;       // [2][32] cycle counters of CTA 0 and CTA 1 (profiling aid)
   u64* ll;               // LL region base
   int* zidx;             // [T][B][S] sampled class per group
   float* ln_stats;       // [3][T*B][2] (mean, rstd) of the x / g / representation LayerNorms
 };
 
 struct LLGeo {           // offsets (in u64 elements) inside the LL region; every buffer is double-buffered by step parity
-  size_t z, x, s, h, r, a, b, c, d, sb, sc, sd, total;
+  size_t z, x, sx, s, h, r, a, b, c, d, sb, sc, sd, total;
 };
 
 __host__ __device__ inline LLGeo make_ll(int S, int Dx, int R, int Dr, int Z) {
   LLGeo g;
   size_t o = 0;
   g.z = o; o += 2 * (size_t)MAXB * S;            // forward: sampled class indices
-  g.x = o; o += 2 * (size_t)MAXB * Dx;           //          x_act rows
-  g.s = o; o += 2 * (size_t)MAXB * SCAN_G * 2;   //          LayerNorm partial statistics (also backward row sums)
+  g.x = o; o += 2 * (size_t)MAXB * Dx;           //          x_pre rows
+  g.sx = o; o += 2 * (size_t)MAXB * SCAN_G * 2;  //          partial statistics of the x LayerNorm
+  g.s = o; o += 2 * (size_t)MAXB * SCAN_G * 2;   //          partial statistics of the GRU LayerNorm
   g.h = o; o += 2 * (size_t)MAXB * R;            //          h rows
   g.r = o; o += 2 * (size_t)MAXB * Dr;           //          rp_pre rows
   g.a = o; o += 2 * (size_t)MAXB * Z;            // backward: d_post_raw rows
@@ -350,21 +349,23 @@ __device__ __forceinline__ void prof_mark(long long* prof, int slot, long long& 
 // forward
 // =====================================================================================================
 struct GeoF {
-  int ngh, ngr;                 // owned 4-column groups of R (GRU output columns) and Dr (representation layer 1)
+  int ngh, ngr, ngx;            // owned 4-column groups of R (GRU output columns), Dr (representation layer 1), Dx (x_pre)
   int sR, sDx, sDr, wgst, w2st; // padded widths; smem row strides of the W_g / W_r2 slices
   int nsplit, rpu;              // sampling units: S groups x nsplit row blocks of rpu rows
   int unit_g, unit_r0, unit_nr; // this CTA's unit: group (-1: none), first row, row count
-  int owner_row;                // batch row whose x this CTA builds (-1: none)
   int ldp;                      // row length of the product partial buffers
-  int oWg, oWr1, oW2, oXh, oXx, oPart, oAcc, oX0, oPar, oMisc, oInt, total;
+  int kin;                      // row length of the W_in slice: S*D + A, padded
+  int oWg, oWr1, oW2, oWin, oXh, oXx, oPart, oAcc, oX0, oPar, oMisc, oInt, total;
 };
 
-struct Dims { int B, S, D, R, Dx, Dr; };
+struct Dims { int B, S, D, R, Dx, Dr, A; };
 
 __host__ __device__ inline GeoF make_geo_f(const Dims& a, int cta) {
   GeoF g;
   g.ngh = owned_groups(a.R, cta);
   g.ngr = owned_groups(a.Dr, cta);
+  g.ngx = owned_groups(a.Dx, cta);
+  g.kin = r4(a.S * a.D + a.A);
   g.sR = r4(a.R); g.sDx = r4(a.Dx); g.sDr = r4(a.Dr);
   g.wgst = g.sR + g.sDx;
   g.w2st = g.sDr + 4;           // +4: the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups
@@ -377,21 +378,21 @@ __host__ __device__ inline GeoF make_geo_f(const Dims& a, int cta) {
     g.unit_nr = imin(g.rpu, a.B - g.unit_r0);
     if (g.unit_nr > 0) g.unit_g = cta % a.S; else g.unit_nr = 0;
   }
-  g.owner_row = (cta % OWN_STRIDE == 0 && cta / OWN_STRIDE < a.B) ? cta / OWN_STRIDE : -1;
-  const int mh = owned_groups(a.R, 0), mr = owned_groups(a.Dr, 0);
+  const int mh = owned_groups(a.R, 0), mr = owned_groups(a.Dr, 0), mx = owned_groups(a.Dx, 0);
   g.ldp = imax(imax(mh * 12, mr * 4), 4);
   int o = 0;
   g.oWg = o;   o += mh * 12 * g.wgst;
   g.oWr1 = o;  o += mr * 4 * g.sR;
   g.oW2 = o;   o += a.D * g.w2st;
+  g.oWin = o;  o += mx * 4 * g.kin;            // W_in rows of the owned x_pre columns
   g.oXh = o;   o += MAXB * g.sR;
   g.oXx = o;   o += MAXB * imax(g.sDx, g.sDr);
-  g.oPart = o; o += imax(imax(KS_MAX * MAXB * g.ldp, CLS_SLICES * MAXRPU * 32), GPARTS * g.sDx);
+  g.oPart = o; o += imax(KS_MAX * MAXB * g.ldp, CLS_SLICES * MAXRPU * 32);
   g.oAcc = o;  o += MAXB * g.ldp;
-  g.oX0 = o;   o += g.sDx;
+  g.oX0 = o;   o += imax(mx * 4, 4);           // x_pre of the learned initial posterior z0, owned columns
   g.oPar = o;  o += g.sR + 2 * g.sDx + 2 * g.sDr;   // h0 | lnx gamma, beta | lnr gamma, beta (read every step)
   g.oMisc = o; o += 8 * MAXB + 64;           // [0,48) flags / statistics; [48,80) and [80,112) per-warp reduction scratch
-  g.oInt = o;  o += r4(64 + 64 + SCAN_G);      // z0 class indices, z_{t-1} indices of the owned row, column counts
+  g.oInt = o;  o += r4(64 + MAXB * 64 + 2 * SCAN_G);   // z0 class indices, z_{t-1} indices of every row, column counts (R, Dx)
   g.total = o;
   return g;
 }
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
   const int T = a.T, B = a.B, A = a.A;
   const int S = FIX ? 32 : a.S, D = FIX ? 32 : a.D, Z = S * D, R = FIX ? 512 : a.R, Dx = FIX ? 512 : a.Dx, Dr = FIX ? 512 : a.Dr;
   const int NB = T * B;
-  const GeoF g = make_geo_f(Dims{B, S, D, R, Dx, Dr}, cta);
+  const GeoF g = make_geo_f(Dims{B, S, D, R, Dx, Dr, a.A}, cta);
   const Workspace ws = carve(a.workspace, T, B, S, D, Dx, R, Dr);
   const LLGeo L = make_ll(S, Dx, R, Dr, Z);
   float* Wg = sm + g.oWg;       // [ngh*12][wgst]  rows: (group, part r/c/u, col-in-group); cols [h (sR) | x (sDx)]
@@ -416,7 +417,8 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
   float* Xx = sm + g.oXx;       // [MAXB][sDx] x rows; reused for the unit's rp rows
   float* PART = sm + g.oPart;
   float* ACC = sm + g.oAcc;     // [MAXB][ldp] finished g_pre columns (for the row statistics)
-  float* X0 = sm + g.oX0;       // [Dx] x_pre contribution of the learned initial posterior z0
+  float* Win = sm + g.oWin;     // [ngx*4][kin] rows of W_in of the owned x_pre columns
+  float* X0 = sm + g.oX0;       // [ngx*4] x_pre contribution of the learned initial posterior z0 (owned columns)
   float* H0 = sm + g.oPar;      // [R] tanh(initial_recurrent_state)
   float* LNXG = H0 + g.sR;      // [Dx] x LayerNorm gamma, beta
   float* LNXB = LNXG + g.sDx;
@@ -424,10 +426,11 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
   float* LNRB = LNRG + g.sDr;
   float* misc = sm + g.oMisc;   // [0,16) first flags; [16,32) mean; [32,48) rstd; [48,80) reduction scratch
   int* z0idx = (int*)(sm + g.oInt);
-  int* zrow = z0idx + 64;
-  int* nctab = zrow + 64;
+  int* zall = z0idx + 64;       // [MAXB][64] class indices of z_{t-1}, every row
+  int* nctab = zall + MAXB * 64;   // valid GRU columns per CTA
+  int* nxtab = nctab + SCAN_G;     // valid x_pre columns per CTA
   const int ldp = g.ldp, xxs = imax(g.sDx, g.sDr);
-  const bool owner = g.owner_row >= 0, sampler = g.unit_g >= 0;
+  const bool sampler = g.unit_g >= 0;
   __shared__ long long sprof[32];
   const bool prof_on = (cta < 2) && tid == 0;
   long long* prof = sprof;
@@ -456,7 +459,9 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
   for (int k = tid; k < R; k += SCAN_NT) H0[k] = a.h0[k];
   for (int k = tid; k < Dx; k += SCAN_NT) { LNXG[k] = a.lnx_g[k]; LNXB[k] = a.lnx_b[k]; }
   for (int k = tid; k < Dr; k += SCAN_NT) { LNRG[k] = a.lnr_g[k]; LNRB[k] = a.lnr_b[k]; }
-  for (int c = tid; c < SCAN_G; c += SCAN_NT) nctab[c] = owned_cols(R, c);
+  for (int c = tid; c < SCAN_G; c += SCAN_NT) { nctab[c] = owned_cols(R, c); nxtab[c] = owned_cols(Dx, c); }
+  for (int gi = 0; gi < g.ngx; ++gi)
+    load_rows4(Win + (size_t)gi * 4 * g.kin, g.kin, 0, a.W_in, Z + A, (cta + gi * SCAN_G) * 4, Dx, 0, Z + A, g.kin, tid);
   if (wid == 0) {  // class index of the learned initial posterior (one-hot `z0`)
     for (int gq = 0; gq < S; ++gq) {
       int best = 0;
@@ -468,12 +473,11 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     }
   }
   __syncthreads();
-  if (owner)       // x_pre row of z0 (used wherever is_first is set): sum of the gathered rows of W_in^T
-    for (int c = tid; c < Dx; c += SCAN_NT) {
-      float acc = 0.f;
-      for (int gq = 0; gq < S; ++gq) acc += a.W_in_t[(size_t)(gq * D + z0idx[gq]) * Dx + c];
-      X0[c] = acc;
-    }
+  for (int cj = tid; cj < g.ngx * 4; cj += SCAN_NT) {   // x_pre of z0 (used wherever is_first is set), owned columns
+    float acc = 0.f;
+    for (int gq = 0; gq < S; ++gq) acc += Win[(size_t)cj * g.kin + gq * D + z0idx[gq]];
+    X0[cj] = acc;
+  }
   // z_in of step 0 (z_{-1} = 0): f * z0, written by the sampling units for their (rows, group) block
   if (sampler)
     for (int e = tid; e < g.unit_nr * D; e += SCAN_NT) {
@@ -481,8 +485,10 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       a.z_in[(size_t)b * Z + g.unit_g * D + d] = a.first[b] * ((z0idx[g.unit_g] == d) ? 1.f : 0.f);
     }
   // fixed element assignments (no index arithmetic inside the time loop)
-  const int nh4 = g.ngh * 4, nh12 = g.ngh * 12, nr4 = g.ngr * 4;
+  const int nh4 = g.ngh * 4, nh12 = g.ngh * 12, nr4 = g.ngr * 4, nx4 = g.ngx * 4;
   const Slot sH = make_slot(tid, nh4, B, cta, R);           // gate / h element
+  const Slot sX = make_slot(tid, nx4, B, cta, Dx);          // x element (save of x_act)
+  const int nxcol = owned_cols(Dx, cta);                    // values per row in this CTA's share of the x LayerNorm
   const Slot sR_ = make_slot(tid, nr4, B, cta, Dr);         // rp element
   // g_pre element: c = (group, part, j) inside the row of 12*ngh products
   const int pb = nh12 > 0 ? tid / nh12 : 0, pc = tid - pb * nh12;
@@ -494,6 +500,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     for (int part = 0; part < 3; ++part) { lg_g[part] = a.lng_g[part * R + sH.col]; lg_b[part] = a.lng_b[part * R + sH.col]; }
   const int ncol3 = 3 * owned_cols(R, cta);                // values per row in this CTA's share of the GRU LayerNorm
   const float bias2 = (sampler && lane < D) ? a.b_r2[g.unit_g * D + lane] : 0.f;
+  float first_next = (tid < B) ? a.first[tid] : 0.f;        // is_first flags of the step about to run (threads < MAXB)
   __syncthreads();
   prof_mark(prof, 0, tlast, prof_on);
 
@@ -501,7 +508,8 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     const size_t row0 = (size_t)t * B;
     const int par = t & 1;
     const unsigned tag = (unsigned)t + 1u;
-    if (tid < MAXB) misc[tid] = (tid < B) ? a.first[row0 + tid] : 0.f;
+    if (tid < MAXB) misc[tid] = first_next;                 // loaded during the previous step
+    if (tid < MAXB) first_next = (tid < B && t + 1 < T) ? a.first[row0 + B + tid] : 0.f;
     // prefetches that do not depend on the chain
     const float pe_pref = sR_.ok ? a.pe[(row0 + sR_.b) * Dr + sR_.col] : 0.f;
     float noise_pref = 1.f, fnext = 0.f;
@@ -509,7 +517,6 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
       if (lane < D) noise_pref = a.noise[(row0 + g.unit_r0 + wid) * Z + (size_t)g.unit_g * D + lane];
       if (t + 1 < T) fnext = a.first[row0 + B + g.unit_r0 + wid];
     }
-    float act_pref[2] = {0.f, 0.f};                         // (owner) action part of x_pre for the thread's column pair
     __syncthreads();
     const float* fl = misc;
 
@@ -528,92 +535,103 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     const float hin = sH.ok ? Xh[sH.b * g.sR + sH.col] : 0.f;
     prof_mark(prof, 13, tlast, prof_on);
 
-    // ============ A (row owner): x = SiLU(LN(W_in [z_in, a_in])) for the owned row; z_in one-hot -> row gather
-    if (owner) {
-      const int b = g.owner_row;
+    // ============ A: x_pre = W_in [z_in, a_in] for the owned columns, every row; z_in one-hot -> gather from the slice.
+    // Warp b builds row b: lane = (column cj = lane / 8, part = lane % 8): 8 lanes sum S/8 gathered weights each, then a
+    // fixed 3-level shuffle tree; the row's partial LayerNorm statistics go out with the values.
+    if (t > 0)
+      for (int e = tid; e < B * S; e += SCAN_NT) {
+        const int b = e / S, gq = e - b * S;
+        zall[b * 64 + gq] = (int)__float_as_uint(ll_wait(ws.ll + L.z + ((size_t)(par ^ 1) * MAXB + b) * S + gq, (unsigned)t, sp));
+      }
+    __syncthreads();
+    prof_mark(prof, 2, tlast, prof_on);
+    for (int b = wid; b < B; b += SCAN_NW) {
       const float f = fl[b];
-      if (t > 0 && tid < S) zrow[tid] = (int)__float_as_uint(ll_wait(ws.ll + L.z + ((size_t)(par ^ 1) * MAXB + b) * S + tid, (unsigned)t, sp));
-      __syncthreads();
-      prof_mark(prof, 2, tlast, prof_on);
-      // gather: thread (column pair cp, part p): part p sums the groups [p*S/4, (p+1)*S/4) in order, all its row loads in
-      // flight at once; the four partials are then added in part order (fixed summation order)
-      const int npairs = Dx >> 1, gper = (S + GPARTS - 1) / GPARTS;
-      float* XG = PART;                          // [GPARTS][sDx] partial rows
-      {
-        const int part = tid >> 8, g_lo = part * gper, g_hi = imin(S, g_lo + gper);
-        for (int cp = tid & 255; cp < npairs; cp += 256) {
-          float2 acc = make_float2(0.f, 0.f);
-          if (t > 0 && f != 1.f)
-            for (int g0 = g_lo; g0 < g_hi; g0 += 8) {
-              float2 v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (g0 + i < g_hi) v[i] = __ldg(reinterpret_cast<const float2*>(a.W_in_t + (size_t)((g0 + i) * D + zrow[g0 + i]) * Dx) + cp);
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (g0 + i < g_hi) { acc.x += v[i].x; acc.y += v[i].y; }
-            }
-          *reinterpret_cast<float2*>(XG + part * g.sDx + 2 * cp) = acc;
+      float rowv[4] = {0.f, 0.f, 0.f, 0.f};           // (lanes with part == 0) the row's x_pre of the <= 4 column groups
+      float rs = 0.f;
+      int rcnt = 0;
+      for (int c0 = 0; c0 < nx4; c0 += 4) {            // 4 columns x 8 parts per pass
+        const int cj = c0 + (lane >> 3), part = lane & 7;
+        const int col = (cta + (cj >> 2) * SCAN_G) * 4 + (cj & 3);
+        const bool okc = cj < nx4 && col < Dx;
+        float acc = 0.f;
+        if (okc && t > 0 && f != 1.f) {
+          const float* wrow = Win + (size_t)cj * g.kin;
+          const int gper = (S + 7) >> 3, g_lo = part * gper, g_hi = imin(S, g_lo + gper);
+          for (int gq = g_lo; gq < g_hi; ++gq) acc += wrow[gq * D + zall[b * 64 + gq]];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (okc && part == 0) {
+          float aa = 0.f;
+          for (int qq = 0; qq < A; ++qq) aa = fmaf(a.actions[(row0 + b) * A + qq], Win[(size_t)cj * g.kin + Z + qq], aa);
+          const float xv = (1.f - f) * (acc + aa) + f * X0[cj];
+          ll_store(ws.ll + L.x + ((size_t)par * MAXB + b) * Dx + col, xv, tag);
+          a.x_pre[(row0 + b) * Dx + col] = xv;
+          rowv[c0 >> 2] = xv;
+          rs += xv;
+          ++rcnt;
         }
       }
-      __syncthreads();
-      float2 xv[2];
-      float s = 0.f;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = 2 * tid + 2 * SCAN_NT * u;
-        xv[u] = make_float2(0.f, 0.f);
-        if (c < Dx) {
-          float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int part = 0; part < GPARTS; ++part) { acc.x += XG[part * g.sDx + c]; acc.y += XG[part * g.sDx + c + 1]; }
-          float2 aa = make_float2(0.f, 0.f);
-          for (int qq = 0; qq < A; ++qq) {
-            const float av = a.actions[(row0 + b) * A + qq];
-            const float2 w = __ldg(reinterpret_cast<const float2*>(a.W_in_t + (size_t)(Z + qq) * Dx + c));
-            aa.x = fmaf(av, w.x, aa.x); aa.y = fmaf(av, w.y, aa.y);
-          }
-          xv[u].x = (1.f - f) * (acc.x + aa.x) + f * X0[c];
-          xv[u].y = (1.f - f) * (acc.y + aa.y) + f * X0[c + 1];
-          s += xv[u].x + xv[u].y;
-        }
-      }
-      const float mu = block_sum(s, misc + 48) / (float)Dx;
-      float v = 0.f;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = 2 * tid + 2 * SCAN_NT * u;
-        if (c < Dx) { const float d0 = xv[u].x - mu, d1 = xv[u].y - mu; v = fmaf(d0, d0, v); v = fmaf(d1, d1, v); }
-      }
-      const float rstd = rsqrtf(block_sum(v, misc + 48) / (float)Dx + a.eps);
-      u64* dst = ws.ll + L.x + ((size_t)par * MAXB + b) * Dx;
-      float2 ov[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = 2 * tid + 2 * SCAN_NT * u;
-        if (c < Dx) {
-          ov[u].x = fsilu((xv[u].x - mu) * rstd * LNXG[c] + LNXB[c]);
-          ov[u].y = fsilu((xv[u].y - mu) * rstd * LNXG[c + 1] + LNXB[c + 1]);
-          ll_store2(dst + c, ov[u].x, ov[u].y, tag);            // hand-off first ...
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {                             // ... saves for the backward after it
-        const int c = 2 * tid + 2 * SCAN_NT * u;
-        if (c < Dx) {
-          *reinterpret_cast<float2*>(a.x_pre + (row0 + b) * Dx + c) = xv[u];
-          *reinterpret_cast<float2*>(a.x_act + (row0 + b) * Dx + c) = ov[u];
-        }
-      }
-      if (tid == 0) { ws.ln_stats[((size_t)0 * NB + row0 + b) * 2] = mu; ws.ln_stats[((size_t)0 * NB + row0 + b) * 2 + 1] = rstd; }
-      for (int e = tid; e < A; e += SCAN_NT) a.a_in[(row0 + b) * A + e] = (1.f - f) * a.actions[(row0 + b) * A + e];
-      prof_mark(prof, 3, tlast, prof_on);
+      // partial statistics over the owned valid columns of this row (values sit in lanes 0, 8, 16, 24)
+      rs = warp_sum(rs);
+      const float mean = nxcol > 0 ? rs / (float)nxcol : 0.f;
+      float m2 = 0.f;
+      for (int i = 0; i < 4; ++i)
+        if (i < rcnt) { const float d = rowv[i] - mean; m2 = fmaf(d, d, m2); }
+      m2 = warp_sum(m2);
+      if (lane == 0) ll_store2(ws.ll + L.sx + (((size_t)par * MAXB + b) * SCAN_G + cta) * 2, mean, m2, tag);
     }
-    (void)act_pref;
+    if (cta == (t % SCAN_G))
+      for (int e = tid; e < B * A; e += SCAN_NT) a.a_in[row0 * A + e] = (1.f - fl[e / A]) * a.actions[row0 * A + e];
+    prof_mark(prof, 3, tlast, prof_on);
 
     // ============ B2: x-part of the GRU product; g_pre columns; partial LayerNorm statistics
     ll_recv(Xx, xxs, ws.ll + L.x + (size_t)par * MAXB * Dx, Dx, B, Dx, tag, tid, sp);
+    for (int b = wid; b < B; b += SCAN_NW) {               // merge the x LayerNorm statistics of row b (Chan)
+      float pm[SCAN_G / 32], pq[SCAN_G / 32];
+#pragma unroll
+      for (int i = 0; i < SCAN_G / 32; ++i) {
+        const u64* p = ws.ll + L.sx + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2;
+        u64 x, y;
+        ll_load2(p, x, y);
+        while ((unsigned)(x >> 32) != tag || (unsigned)(y >> 32) != tag) {
+          if (sp.fail()) break;
+          ll_load2(p, x, y);
+        }
+        pm[i] = __uint_as_float((unsigned)x);
+        pq[i] = __uint_as_float((unsigned)y);
+      }
+      float sm_ = 0.f;
+#pragma unroll
+      for (int i = 0; i < SCAN_G / 32; ++i) sm_ += (float)nxtab[lane + 32 * i] * pm[i];
+      const float mean = warp_sum(sm_) / (float)Dx;
+      float m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < SCAN_G / 32; ++i) {
+        const float d = pm[i] - mean;
+        m2 += pq[i] + (float)nxtab[lane + 32 * i] * d * d;
+      }
+      m2 = warp_sum(m2);
+      if (lane == 0) {
+        const float rstd = rsqrtf(m2 / (float)Dx + a.eps);
+        misc[16 + b] = mean;
+        misc[32 + b] = rstd;
+        if (cta == ((t + 1) % SCAN_G)) {
+          ws.ln_stats[((size_t)0 * NB + row0 + b) * 2] = mean;
+          ws.ln_stats[((size_t)0 * NB + row0 + b) * 2 + 1] = rstd;
+        }
+      }
+    }
     __syncthreads();
+    for (int k = tid; k < Dx; k += SCAN_NT) {              // x = SiLU(LN(x_pre)) in place, every row (column k per thread)
+      const float gk = LNXG[k], bk = LNXB[k];
+      for (int b = 0; b < B; ++b)
+        Xx[b * xxs + k] = fsilu((Xx[b * xxs + k] - misc[16 + b]) * misc[32 + b] * gk + bk);
+    }
+    __syncthreads();
+    if (sX.ok) a.x_act[(row0 + sX.b) * Dx + sX.col] = Xx[sX.b * xxs + sX.col];
     prof_mark(prof, 4, tlast, prof_on);
     const int ksx = product(Xx, xxs, Wg + g.sR, g.wgst, g.ngh * 3, Dx, B, PART, ldp, 0, tid);
     __syncthreads();
@@ -934,7 +952,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
   const int T = a.T, B = a.B;
   const int S = FIX ? 32 : a.S, D = FIX ? 32 : a.D, Z = S * D, R = FIX ? 512 : a.R, Dx = FIX ? 512 : a.Dx, Dr = FIX ? 512 : a.Dr;
   const int KG = R + Dx, KIN = Z + a.A, NB = T * B;
-  const GeoB g = make_geo_b(Dims{B, S, D, R, Dx, Dr}, cta);
+  const GeoB g = make_geo_b(Dims{B, S, D, R, Dx, Dr, a.A}, cta);
   const Workspace ws = carve(a.workspace, T, B, S, D, Dx, R, Dr);
   const LLGeo L = make_ll(S, Dx, R, Dr, Z);
   const int mh = owned_groups(R, 0), mx = owned_groups(Dx, 0);
@@ -1266,9 +1284,8 @@ int scan_check(const b200rl_rssm_scan_args& a) {
   RL_CHECK_ARG(a.Dx <= 4 * SCAN_NT, "persistent scan supports recurrent dense_units <= 1024");
   // one element of every per-step epilogue per thread (fixed assignments, rssm_scan.cu `Slot`)
   RL_CHECK_ARG(MAXB * owned_groups(a.R, 0) * 12 <= SCAN_NT && MAXB * owned_groups(a.Dr, 0) * 4 <= SCAN_NT &&
-                   MAXB * owned_groups(a.Dx, 0) * 4 <= SCAN_NT,
+                   owned_groups(a.Dx, 0) <= 4,
                "persistent scan supports recurrent_state_size <= 512 and hidden / dense sizes <= 2048");
-  RL_CHECK_ARG(a.W_in_t, "W_in_t (transposed recurrent-model input weight) is required");
   RL_CHECK_ARG(a.workspace && a.workspace_bytes >= (long long)ws_bytes(a.T, a.B, a.S, a.D, a.Dx, a.R, a.Dr), "workspace too small");
   return B200RL_OK;
 }
@@ -1283,7 +1300,7 @@ extern "C" int b200rl_rssm_scan_fwd(const b200rl_rssm_scan_args* args, cudaStrea
   RL_CHECK_ARG(args, "null args");
   const b200rl_rssm_scan_args& a = *args;
   if (int rc = scan_check(a)) return rc;
-  const GeoF g = make_geo_f(Dims{a.B, a.S, a.D, a.R, a.Dx, a.Dr}, 0);
+  const GeoF g = make_geo_f(Dims{a.B, a.S, a.D, a.R, a.Dx, a.Dr, a.A}, 0);
   const size_t smem = sizeof(float) * (size_t)g.total;
   RL_CHECK_ARG(smem <= 227 * 1024, "weight slices do not fit in shared memory for this model size");
   const bool fix = fixed_dims(a);
@@ -1298,7 +1315,7 @@ extern "C" int b200rl_rssm_scan_fwd(const b200rl_rssm_scan_args* args, cudaStrea
 extern "C" int b200rl_rssm_scan_bwd_check(const b200rl_rssm_scan_args* args) {
   RL_CHECK_ARG(args, "null args");
   if (int rc = scan_check(*args)) return rc;
-  const GeoB g = make_geo_b(Dims{args->B, args->S, args->D, args->R, args->Dx, args->Dr}, 0);
+  const GeoB g = make_geo_b(Dims{args->B, args->S, args->D, args->R, args->Dx, args->Dr, args->A}, 0);
   RL_CHECK_ARG(sizeof(float) * (size_t)g.total <= 227 * 1024, "weight slices do not fit in shared memory for this model size");
   return B200RL_OK;
 }
@@ -1309,7 +1326,7 @@ extern "C" int b200rl_rssm_scan_bwd(const b200rl_rssm_scan_args* args, const b20
   const b200rl_rssm_scan_args& a = *args;
   if (int rc = scan_check(a)) return rc;
   RL_CHECK_ARG(grads->q_r && grads->q_g && grads->q_x, "q_r / q_g / q_x (pre-activation x weight products) are required");
-  const GeoB g = make_geo_b(Dims{a.B, a.S, a.D, a.R, a.Dx, a.Dr}, 0);
+  const GeoB g = make_geo_b(Dims{a.B, a.S, a.D, a.R, a.Dx, a.Dr, a.A}, 0);
   const size_t smem = sizeof(float) * (size_t)g.total;
   RL_CHECK_ARG(smem <= 227 * 1024, "weight slices do not fit in shared memory for this model size");
   const bool fix = fixed_dims(a);

@@ -827,9 +827,6 @@ class DV3Engine:
         disables itself) if the model does not fit the kernel's shared-memory budget."""
         if self._scan_ws is None:
             self._scan_ws = self.ops.rssm_scan_workspace(self.T, self.B, self.S, self.D, self.Dx, self.R, self.Dr)
-            Win = self._w("rssm.recurrent_model.mlp._model.0.weight")
-            self._win_t_scan = torch.empty(Win.shape[1], Win.shape[0], dtype=torch.float32, device=self.device)
-        self.ops.transpose2d(self._w("rssm.recurrent_model.mlp._model.0.weight"), self._win_t_scan)
         tensors = self._scan_tensors(first)
         dims = self._scan_dims()
         try:
@@ -860,7 +857,7 @@ class DV3Engine:
             actions=self.shift_actions, first=first, noise=self.noise_post, latent=self.latent, z_in=self.z_in,
             h_in=self.h_in, a_in=self.a_in, x_pre=self.x_pre, x_act=self.x_act, g_pre=self.g_pre, g_ln=self.g_ln,
             tr_pre=self.tr_pre, tr_act=self.tr_act, rp_pre=self.rp_pre, rp_act=self.rp_act, post_raw=self.post_raw,
-            prior_raw=self.prior_raw, post_mix=self.post_mix, prior_mix=self.prior_mix, W_in_t=self._win_t_scan)
+            prior_raw=self.prior_raw, post_mix=self.post_mix, prior_mix=self.prior_mix)
 
     def _prior_backward(self):
         """Backward of the batched prior: its gradient comes from the KL term only (d_prior_mix), so it does not depend on

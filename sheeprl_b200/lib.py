@@ -73,7 +73,7 @@ class RssmScanArgs(ctypes.Structure):
     POINTERS = ("W_in", "lnx_g", "lnx_b", "W_g", "lng_g", "lng_b", "W_t1", "lnt_g", "lnt_b", "W_t2", "b_t2",
                 "W_r1", "lnr_g", "lnr_b", "W_r2", "b_r2", "h0", "z0", "pe", "actions", "first", "noise", "latent",
                 "z_in", "h_in", "a_in", "x_pre", "x_act", "g_pre", "g_ln", "tr_pre", "tr_act", "rp_pre", "rp_act",
-                "post_raw", "prior_raw", "post_mix", "prior_mix", "W_in_t")
+                "post_raw", "prior_raw", "post_mix", "prior_mix")
     _fields_ = ([(n, c_int) for n in ("T", "B", "S", "D", "R", "A", "Dx", "Dt", "Dr", "ld_lat", "ld_wr1")]
                 + [("eps", c_float), ("unimix", c_float)]
                 + [(n, c_void_p) for n in POINTERS]
@@ -459,7 +459,7 @@ class CudaOps:
         return int(self.lib.b200rl_rssm_scan_error(_p(workspace), self._st()))
 
     def rssm_scan_profile(self, workspace: torch.Tensor):
-        """per-phase cycle counters of CTA 0 (a row owner) and CTA 1 of the last scan launch: [2][32] int64"""
+        """per-phase cycle counters of CTA 0 and CTA 1 of the last scan launch: [2][32] int64"""
         out = (ctypes.c_longlong * 64)()
         rc = self.lib.b200rl_rssm_scan_profile(_p(workspace), out, self._st())
         if rc != 0:

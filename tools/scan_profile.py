@@ -13,7 +13,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 FWD = {0: "prologue", 12: "B1 step start + mask-mix + sync", 13: "B1 sync + slice sums", 14: "E LayerNorm", 15: "E logits product",
-       1: "B1 h-part product (thread 0's warp)", 2: "A wait z", 3: "A gather+LN+send x", 4: "B2 wait x rows", 5: "B2 product+stats send",
+       1: "B1 h-part product (thread 0's warp)", 2: "A wait z (all rows)", 3: "A gather + send x_pre, stats", 4: "B2 wait x rows + stats, normalise", 5: "B2 product+stats send",
        6: "C wait stats+merge", 7: "C gates+send h", 8: "D wait h rows", 9: "D product+send rp", 10: "E wait rp rows",
        11: "E sample + saves"}
 BWD = {16: "prologue", 17: "P wait dxh_x rows", 18: "P product+softmax bwd+send", 19: "Q wait d_post_raw rows", 20: "Q product+send",
