@@ -42,7 +42,6 @@ constexpr int SCAN_NT = 512;   // threads per CTA: the scan is latency-bound (nc
 constexpr int SCAN_NW = SCAN_NT / 32;
 constexpr int MAXB = 16;
 constexpr int MAXRPU = 8;      // rows of one sampling unit (S <= 64 groups over 128 CTAs -> >= 2 row splits)
-constexpr int LL_UNROLL = 8;   // 16-byte loads in flight per thread while receiving rows (one L2 round trip per batch)
 constexpr int NRB = 4;         // rows of one product item (4 rows x 4 columns of packed accumulators per lane)
 constexpr int KS_MAX = 8;      // K slices of a product (rows of the partial buffer)
 constexpr int CLS_SLICES = 8;  // K slices of the class-per-lane products (logits / dz)
@@ -168,7 +167,9 @@ __device__ __forceinline__ float ll_wait(const u64* p, unsigned tag, Spin& sp) {
 }
 
 // Receives rows x n values (n even; LL rows of stride ss elements, 16-byte aligned) into shared memory rows of stride ds.
-// Thread (row group, column pair): LL_UNROLL 16-byte loads in flight before the first tag is checked.
+// Thread (row group, column pair): LL_UNROLL 16-byte loads in flight before the first tag is checked (one L2 round trip
+// per batch; 8 in the forward kernel, 4 in the register-tighter backward kernel where 8 spilled and measured slower).
+template <int LL_UNROLL>
 __device__ __forceinline__ void ll_recv(float* dst, int ds, const u64* src, int ss, int rows, int n, unsigned tag, int tid, Spin& sp) {
   const int half = n >> 1;
   int rg = 0, kp = tid, nrg = 1, kstep = SCAN_NT;
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     prof_mark(prof, 3, tlast, prof_on);
 
     // ============ B2: x-part of the GRU product; g_pre columns; partial LayerNorm statistics
-    ll_recv(Xx, xxs, ws.ll + L.x + (size_t)par * MAXB * Dx, Dx, B, Dx, tag, tid, sp);
+    ll_recv<8>(Xx, xxs, ws.ll + L.x + (size_t)par * MAXB * Dx, Dx, B, Dx, tag, tid, sp);
     for (int b = wid; b < B; b += SCAN_NW) {               // merge the x LayerNorm statistics of row b (Chan)
       float pm[SCAN_G / 32], pq[SCAN_G / 32];
 #pragma unroll
@@ -726,7 +727,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     prof_mark(prof, 7, tlast, prof_on);
 
     // ============ D: rp_pre = h W_r1[:, :R]^T + pe for the owned columns (h rows stay in Xh for the next step)
-    ll_recv(Xh, g.sR, ws.ll + L.h + (size_t)par * MAXB * R, R, B, R, tag, tid, sp);   // (own h_in was read above, into `hin`)
+    ll_recv<8>(Xh, g.sR, ws.ll + L.h + (size_t)par * MAXB * R, R, B, R, tag, tid, sp);   // (own h_in was read above, into `hin`)
     __syncthreads();
     prof_mark(prof, 8, tlast, prof_on);
     const int ksr = product(Xh, g.sR, Wr1, g.sR, g.ngr, R, B, PART, ldp, 0, tid);
@@ -742,7 +743,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     if (sampler) {
       const int gq = g.unit_g, nr = g.unit_nr, rb = g.unit_r0;
       __syncthreads();                       // PART / Xx free
-      ll_recv(Xx, xxs, ws.ll + L.r + ((size_t)par * MAXB + rb) * Dr, Dr, nr, Dr, tag, tid, sp);
+      ll_recv<8>(Xx, xxs, ws.ll + L.r + ((size_t)par * MAXB + rb) * Dr, Dr, nr, Dr, tag, tid, sp);
       __syncthreads();
       prof_mark(prof, 10, tlast, prof_on);
       {
@@ -1089,7 +1090,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     if (unit) {
       const int gq = g.unit_g, nr = g.unit_nr, rb = g.unit_r0;
       if (!last) {
-        ll_recv(X, xw, ws.ll + L.d + ((size_t)(par ^ 1) * MAXB + rb) * Dx, Dx, nr, Dx, (unsigned)bt, tid, sp);
+        ll_recv<4>(X, xw, ws.ll + L.d + ((size_t)(par ^ 1) * MAXB + rb) * Dx, Dx, nr, Dx, (unsigned)bt, tid, sp);
         recv_row_sums(ws.ll + L.sd, par ^ 1, rb, nr, (unsigned)bt, 1.f / (float)Dx, S1, S2, tid, sp);
         __syncthreads();
         prof_mark(prof, 17, tlast, prof_on);
@@ -1137,7 +1138,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
 
     // ============ Q: d_rp_act = d_post_raw W_r2 for the owned columns; dxh of the representation LayerNorm
     __syncthreads();
-    ll_recv(X, xw, ws.ll + L.a + (size_t)par * MAXB * Z, Z, B, Z, tag, tid, sp);
+    ll_recv<4>(X, xw, ws.ll + L.a + (size_t)par * MAXB * Z, Z, B, Z, tag, tid, sp);
     __syncthreads();
     prof_mark(prof, 19, tlast, prof_on);
     const int ks2 = product(X, xw, W2T, g.sZ, g.ngr, Z, B, PART, ldp, 0, tid);
@@ -1162,7 +1163,7 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
 
     // ============ R: dh = d_latent_h + carry + d_rp_pre W_r1h ; GRU gate backward ; dxh of the GRU LayerNorm
     __syncthreads();
-    ll_recv(X, xw, ws.ll + L.b + (size_t)par * MAXB * Dr, Dr, B, Dr, tag, tid, sp);
+    ll_recv<4>(X, xw, ws.ll + L.b + (size_t)par * MAXB * Dr, Dr, B, Dr, tag, tid, sp);
     recv_row_sums(ws.ll + L.sb, par, 0, B, tag, 1.f / (float)Dr, S1, S2, tid, sp);
     __syncthreads();
     prof_mark(prof, 21, tlast, prof_on);
@@ -1210,14 +1211,14 @@ rssm_scan_bwd_kernel(const b200rl_rssm_scan_args a, const b200rl_rssm_scan_grads
     // ============ S: [dh_in, d_x_act] = d_g_pre W_g for the owned columns (K = 3R: parts r,c together, then u)
     __syncthreads();
     for (int part = 0; part < 2; ++part)
-      ll_recv(X + part * g.sR, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)part * R, 3 * R, B, R, tag, tid, sp);
+      ll_recv<4>(X + part * g.sR, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)part * R, 3 * R, B, R, tag, tid, sp);
     __syncthreads();
     const int ksa = product(X, xw, WgT, g.wgst, g.ngh + g.ngx, 2 * g.sR, B, PART, ldp, 0, tid);
     __syncthreads();
     float acc_h = sH.ok ? part_sum(PART, ldp, ksa, sH.b, sH.cj) : 0.f;
     float acc_x = sX.ok ? part_sum(PART, ldp, ksa, sX.b, nh4 + sX.cj) : 0.f;
     __syncthreads();
-    ll_recv(X, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)2 * R, 3 * R, B, R, tag, tid, sp);
+    ll_recv<4>(X, xw, ws.ll + L.c + (size_t)par * MAXB * 3 * R + (size_t)2 * R, 3 * R, B, R, tag, tid, sp);
     recv_row_sums(ws.ll + L.sc, par, 0, B, tag, 1.f / (float)(3 * R), S1, S2, tid, sp);
     __syncthreads();
     const int ksb = product(X, xw, WgT + 2 * g.sR, g.wgst, g.ngh + g.ngx, R, B, PART, ldp, 0, tid);
