@@ -53,7 +53,11 @@ class B200Adam(torch.optim.Optimizer):
                 state[i] = {"step": torch.tensor(float(self.group.step)), "exp_avg": m[n].detach().clone(),
                             "exp_avg_sq": v[n].detach().clone()}
         pg = {k: val for k, val in self.param_groups[0].items() if k != "params"}
-        return {"state": state, "param_groups": [dict(pg, params=list(range(len(self.names))))]}
+        out = {"state": state, "param_groups": [dict(pg, params=list(range(len(self.names))))]}
+        eng = getattr(self, "rng_engine", None)
+        if eng is not None:          # Philox position of the sampling noise travels with the world-model optimizer state, so
+            out["b200_rng"] = eng.rng_state()      # a resumed run continues the stream (torch's Adam ignores the extra key)
+        return out
 
     def load_state_dict(self, sd: Dict[str, Any]):
         m, v = self.group.optimizer_views()
@@ -81,13 +85,17 @@ class B200Adam(torch.optim.Optimizer):
             for k in ("lr", "eps", "betas"):
                 if k in sd["param_groups"][0]:
                     self.param_groups[0][k] = sd["param_groups"][0][k]
+        eng = getattr(self, "rng_engine", None)
+        if eng is not None and "b200_rng" in sd:
+            eng.load_rng_state(sd["b200_rng"])
 
 
 def make_optimizers(engine: DV3Engine, cfg):
     a = cfg.algo
     mk = lambda g, o: B200Adam(g, list(g.shapes), float(o.lr), float(o.eps), tuple(o.betas), float(o.weight_decay))  # noqa
-    return (mk(engine.wm, a.world_model.optimizer), mk(engine.actor, a.actor.optimizer),
-            mk(engine.critic, a.critic.optimizer))
+    opts = (mk(engine.wm, a.world_model.optimizer), mk(engine.actor, a.actor.optimizer), mk(engine.critic, a.critic.optimizer))
+    opts[0].rng_engine = engine
+    return opts
 
 
 def _engine_of(module) -> DV3Engine:
@@ -153,8 +161,11 @@ def _optimizer_factory(engines):
         if not target.endswith("Adam"):
             raise NotImplementedError(f"optimizer {target}: the fused update kernel implements torch.optim.Adam")
         g = groups[name]
-        return B200Adam(g, list(g.shapes), float(config["lr"]), float(config.get("eps", 1e-8)),
-                        tuple(config.get("betas", (0.9, 0.999))), float(config.get("weight_decay", 0.0) or 0.0))
+        opt = B200Adam(g, list(g.shapes), float(config["lr"]), float(config.get("eps", 1e-8)),
+                       tuple(config.get("betas", (0.9, 0.999))), float(config.get("weight_decay", 0.0) or 0.0))
+        if name == "wm":
+            opt.rng_engine = eng
+        return opt
 
     return make
 
