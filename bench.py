@@ -210,6 +210,7 @@ def run_b200(args):
     cfg = make_cfg(args)
     cfg.seed = 5
     cfg.algo.cuda_graph = not args.no_graph
+    cfg.algo.overlap_allreduce = not args.no_overlap_allreduce
     adim = (2,)
 
     class Fab:  # the three attributes train()/build_agent() read from Fabric
@@ -373,7 +374,8 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "arm": {"parallelism": f"dp{world}", "cuda_graph": bool(graphed), "api": "sheeprl_b200.algos.dreamer_v3: build_agent() + train()"},
+        "arm": {"parallelism": f"dp{world}", "cuda_graph": bool(graphed), "api": "sheeprl_b200.algos.dreamer_v3: build_agent() + train()",
+                "overlap_allreduce": bool(world > 1 and not args.no_overlap_allreduce)},
         "clocks": clk,
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 13 * 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -581,6 +583,8 @@ def main():
     ap.add_argument("--no-gpu-eager", dest="gpu_eager", action="store_false")
     ap.add_argument("--no-breakdown", dest="breakdown", action="store_false")
     ap.add_argument("--no-tf32", dest="tf32_also", action="store_false", help="skip the secondary single-pass-TF32 measurement")
+    ap.add_argument("--no-overlap-allreduce", action="store_true", help="one all-reduce of the whole world-model gradient "
+                    "before the optimizer instead of three overlapped buckets")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = 16 if args.size == "S" else 64
@@ -592,8 +596,16 @@ def main():
         try:
             run_b200(args)
         finally:
+            import gc
+
             import torch.distributed as dist
 
+            from sheeprl_b200.graph import release_all
+
+            # captured graphs hold NCCL kernels: they must be gone before the communicator is torn down, or
+            # destroy_process_group() blocks (the engine sits in a reference cycle, so drop the graphs explicitly)
+            release_all()
+            gc.collect()
             if dist.is_available() and dist.is_initialized():
                 dist.destroy_process_group()
 

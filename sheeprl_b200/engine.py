@@ -593,7 +593,7 @@ class DV3Engine:
         # finishes those three ranges in REVERSE order, so each is all-reduced on a side stream as soon as it is final
         # (the reference's DDP buckets, fabric.backward dreamer_v3.py:191, overlap the same way)
         b_enc, b_tail = self._wm_buckets()
-        overlap = self.allreduce_async is not None
+        overlap = self.allreduce_async is not None and bool(self.cfg.algo.get("overlap_allreduce", True))
         if overlap:
             self.allreduce_async(self.wm.grad[b_tail:])
         self._scan_backward(first)

@@ -11,9 +11,30 @@ lives in pinned host memory), so the reference's calling convention — a fresh 
 """
 from __future__ import annotations
 
+import atexit
+import weakref
 from typing import Callable, Dict, Optional, Tuple
 
 import torch
+
+_LIVE = weakref.WeakSet()
+
+
+def release_all() -> None:
+    """Drops every captured graph of the process.  A graph that contains NCCL kernels keeps the communicator busy:
+    `torch.distributed.destroy_process_group()` (and NCCL's teardown at interpreter exit) blocks until the graph is gone,
+    so graphs must die first — at exit (registered below, runs before torch's own handlers) or explicitly before
+    destroying the process group."""
+    for g in list(_LIVE):
+        g.reset()
+    if torch.cuda.is_available():
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+
+
+atexit.register(release_all)
 
 
 class _Entry:
@@ -35,6 +56,7 @@ class StepGraph:
         self.on_replay = on_replay
         self.host_state = host_state
         self._entries: Dict[tuple, _Entry] = {}
+        _LIVE.add(self)
 
     @staticmethod
     def signature(data: Dict[str, torch.Tensor]) -> tuple:
