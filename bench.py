@@ -210,7 +210,8 @@ def run_b200(args):
     cfg = make_cfg(args)
     cfg.seed = 5
     cfg.algo.cuda_graph = not args.no_graph
-    cfg.algo.overlap_allreduce = not args.no_overlap_allreduce
+    if args.no_overlap_allreduce or args.overlap_allreduce:
+        cfg.algo.overlap_allreduce = bool(args.overlap_allreduce)
     adim = (2,)
 
     class Fab:  # the three attributes train()/build_agent() read from Fabric
@@ -375,7 +376,7 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "arm": {"parallelism": f"dp{world}", "cuda_graph": bool(graphed), "api": "sheeprl_b200.algos.dreamer_v3: build_agent() + train()",
-                "overlap_allreduce": bool(world > 1 and not args.no_overlap_allreduce)},
+                "overlap_allreduce": bool(world > 1 and cfg.algo.get("overlap_allreduce", not eng.fused_scan))},
         "clocks": clk,
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 13 * 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -584,7 +585,8 @@ def main():
     ap.add_argument("--no-breakdown", dest="breakdown", action="store_false")
     ap.add_argument("--no-tf32", dest="tf32_also", action="store_false", help="skip the secondary single-pass-TF32 measurement")
     ap.add_argument("--no-overlap-allreduce", action="store_true", help="one all-reduce of the whole world-model gradient "
-                    "before the optimizer instead of three overlapped buckets")
+                    "before the optimizer instead of three overlapped buckets (the default when the persistent scan runs)")
+    ap.add_argument("--overlap-allreduce", action="store_true", help="force the three overlapped bucket reductions")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = 16 if args.size == "S" else 64

@@ -180,17 +180,24 @@ __device__ __forceinline__ void ll_recv(float* dst, int ds, const u64* src, int 
 #pragma unroll
       for (int u = 0; u < LL_UNROLL; ++u)
         if (r0 + u * nrg < rows) ll_load2(src + (size_t)(r0 + u * nrg) * ss + k, a[u], b[u]);
+      // elements that came back with an old tag are re-polled TOGETHER (one L2 round trip per retry of the whole batch,
+      // not one per element)
+      for (;;) {
+        bool stale = false;
+#pragma unroll
+        for (int u = 0; u < LL_UNROLL; ++u)
+          if (r0 + u * nrg < rows && ((unsigned)(a[u] >> 32) != tag || (unsigned)(b[u] >> 32) != tag)) stale = true;
+        if (!stale || sp.fail()) break;
+#pragma unroll
+        for (int u = 0; u < LL_UNROLL; ++u)
+          if (r0 + u * nrg < rows && ((unsigned)(a[u] >> 32) != tag || (unsigned)(b[u] >> 32) != tag))
+            ll_load2(src + (size_t)(r0 + u * nrg) * ss + k, a[u], b[u]);
+      }
 #pragma unroll
       for (int u = 0; u < LL_UNROLL; ++u)
-        if (r0 + u * nrg < rows) {
-          const int r = r0 + u * nrg;
-          while ((unsigned)(a[u] >> 32) != tag || (unsigned)(b[u] >> 32) != tag) {
-            if (sp.fail()) break;
-            ll_load2(src + (size_t)r * ss + k, a[u], b[u]);
-          }
-          *reinterpret_cast<float2*>(dst + r * ds + k) =
+        if (r0 + u * nrg < rows)
+          *reinterpret_cast<float2*>(dst + (r0 + u * nrg) * ds + k) =
               make_float2(__uint_as_float((unsigned)a[u]), __uint_as_float((unsigned)b[u]));
-        }
     }
   }
 }
@@ -592,17 +599,25 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     ll_recv<8>(Xx, xxs, ws.ll + L.x + (size_t)par * MAXB * Dx, Dx, B, Dx, tag, tid, sp);
     for (int b = wid; b < B; b += SCAN_NW) {               // merge the x LayerNorm statistics of row b (Chan)
       float pm[SCAN_G / 32], pq[SCAN_G / 32];
+      u64 x[SCAN_G / 32], y[SCAN_G / 32];
+#pragma unroll
+      for (int i = 0; i < SCAN_G / 32; ++i)
+        ll_load2(ws.ll + L.sx + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2, x[i], y[i]);
+      for (;;) {                                   // stale partials are re-polled together
+        bool stale = false;
+#pragma unroll
+        for (int i = 0; i < SCAN_G / 32; ++i)
+          if ((unsigned)(x[i] >> 32) != tag || (unsigned)(y[i] >> 32) != tag) stale = true;
+        if (!stale || sp.fail()) break;
+#pragma unroll
+        for (int i = 0; i < SCAN_G / 32; ++i)
+          if ((unsigned)(x[i] >> 32) != tag || (unsigned)(y[i] >> 32) != tag)
+            ll_load2(ws.ll + L.sx + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2, x[i], y[i]);
+      }
 #pragma unroll
       for (int i = 0; i < SCAN_G / 32; ++i) {
-        const u64* p = ws.ll + L.sx + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2;
-        u64 x, y;
-        ll_load2(p, x, y);
-        while ((unsigned)(x >> 32) != tag || (unsigned)(y >> 32) != tag) {
-          if (sp.fail()) break;
-          ll_load2(p, x, y);
-        }
-        pm[i] = __uint_as_float((unsigned)x);
-        pq[i] = __uint_as_float((unsigned)y);
+        pm[i] = __uint_as_float((unsigned)x[i]);
+        pq[i] = __uint_as_float((unsigned)y[i]);
       }
       float sm_ = 0.f;
 #pragma unroll
@@ -673,13 +688,19 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
         const int b = b0 + rr * SCAN_NW;
         if (b >= B) continue;
         float pm[SCAN_G / 32], pq[SCAN_G / 32];
+        for (;;) {                                 // stale partials are re-polled together
+          bool stale = false;
+#pragma unroll
+          for (int i = 0; i < SCAN_G / 32; ++i)
+            if ((unsigned)(x[rr][i] >> 32) != tag || (unsigned)(y[rr][i] >> 32) != tag) stale = true;
+          if (!stale || sp.fail()) break;
+#pragma unroll
+          for (int i = 0; i < SCAN_G / 32; ++i)
+            if ((unsigned)(x[rr][i] >> 32) != tag || (unsigned)(y[rr][i] >> 32) != tag)
+              ll_load2(ws.ll + L.s + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2, x[rr][i], y[rr][i]);
+        }
 #pragma unroll
         for (int i = 0; i < SCAN_G / 32; ++i) {
-          const u64* p = ws.ll + L.s + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2;
-          while ((unsigned)(x[rr][i] >> 32) != tag || (unsigned)(y[rr][i] >> 32) != tag) {
-            if (sp.fail()) break;
-            ll_load2(p, x[rr][i], y[rr][i]);
-          }
           pm[i] = __uint_as_float((unsigned)x[rr][i]);
           pq[i] = __uint_as_float((unsigned)y[rr][i]);
         }
@@ -917,13 +938,19 @@ __device__ __forceinline__ void recv_row_sums(const u64* base, int par, int r0, 
       if (bb >= nr) continue;
       const int b = r0 + bb;
       float v0 = 0.f, v1 = 0.f;
+      for (;;) {                                   // stale partials are re-polled together
+        bool stale = false;
+#pragma unroll
+        for (int i = 0; i < SCAN_G / 32; ++i)
+          if ((unsigned)(x[rr][i] >> 32) != tag || (unsigned)(y[rr][i] >> 32) != tag) stale = true;
+        if (!stale || sp.fail()) break;
+#pragma unroll
+        for (int i = 0; i < SCAN_G / 32; ++i)
+          if ((unsigned)(x[rr][i] >> 32) != tag || (unsigned)(y[rr][i] >> 32) != tag)
+            ll_load2(base + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2, x[rr][i], y[rr][i]);
+      }
 #pragma unroll
       for (int i = 0; i < SCAN_G / 32; ++i) {
-        const u64* p = base + (((size_t)par * MAXB + b) * SCAN_G + lane + 32 * i) * 2;
-        while ((unsigned)(x[rr][i] >> 32) != tag || (unsigned)(y[rr][i] >> 32) != tag) {
-          if (sp.fail()) break;
-          ll_load2(p, x[rr][i], y[rr][i]);
-        }
         v0 += __uint_as_float((unsigned)x[rr][i]);
         v1 += __uint_as_float((unsigned)y[rr][i]);
       }
