@@ -169,8 +169,10 @@ __device__ __forceinline__ float ll_wait(const u64* p, unsigned tag, Spin& sp) {
 // Receives rows x n values (n even; LL rows of stride ss elements, 16-byte aligned) into shared memory rows of stride ds.
 // Thread (row group, column pair): LL_UNROLL 16-byte loads in flight before the first tag is checked (one L2 round trip
 // per batch; 8 in the forward kernel, 4 in the register-tighter backward kernel where 8 spilled and measured slower).
+// (not inlined, like the product routines below: their hot loops then own the register file instead of sharing it with
+// every value the step loop keeps live — inlined, ptxas spilled inside the FFMA2 loops and the products ran 5x slower)
 template <int LL_UNROLL>
-__device__ __forceinline__ void ll_recv(float* dst, int ds, const u64* src, int ss, int rows, int n, unsigned tag, int tid, Spin& sp) {
+__device__ __noinline__ void ll_recv(float* dst, int ds, const u64* src, int ss, int rows, int n, unsigned tag, int tid, Spin& sp) {
   const int half = n >> 1;
   int rg = 0, kp = tid, nrg = 1, kstep = SCAN_NT;
   if (half < SCAN_NT) { rg = tid / half; kp = tid - rg * half; nrg = SCAN_NT / half; kstep = half; if (rg >= nrg) return; }
@@ -279,7 +281,7 @@ __device__ __forceinline__ void warp_item(const float* __restrict__ X, int xs, c
 // to PART[s][b][cbase + 4*group + j] (every element written by exactly one lane); the caller sums the slices in order
 // (bit-reproducible).  `wbase`: first weight row of group 0; group g starts at wbase + g*4*wst.  Returns the number of
 // slices.  No barrier inside: the caller synchronises before (X complete) and after (PART complete).
-__device__ __forceinline__ int product(const float* X, int xs, const float* wbase, int wst, int ngroups, int K, int B,
+__device__ __noinline__ int product(const float* X, int xs, const float* wbase, int wst, int ngroups, int K, int B,
                                        float* PART, int ldp, int cbase, int tid) {
   if (ngroups <= 0) return 0;
   const int lane = tid & 31, wid = tid >> 5;
@@ -306,7 +308,7 @@ __device__ __forceinline__ float part_sum(const float* PART, int ldp, int ks, in
 // Class-per-lane product (forward logits, backward dz): out[row][lane] = sum_k X[row][k] * W[lane][k] for nr <= MAXRPU rows.
 // Warp (K slice s = wid % CLS_SLICES, row phase wid / CLS_SLICES); partials go to PART[s][row][lane] (fixed-order sum by
 // the caller).  W rows have stride wst = K + 4 (the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups).
-__device__ __forceinline__ void class_product(const float* X, int xs, const float* W, int wst, int D, int Kp, int nr, float* PART,
+__device__ __noinline__ void class_product(const float* X, int xs, const float* W, int wst, int D, int Kp, int nr, float* PART,
                                               int tid) {
   const int lane = tid & 31, wid = tid >> 5;
   const int sl = wid % CLS_SLICES, rph = wid / CLS_SLICES, nph = SCAN_NW / CLS_SLICES;
@@ -919,7 +921,7 @@ __host__ __device__ inline GeoB make_geo_b(const Dims& a, int cta) {
 
 // (sum dxh, sum dxh*xh) / n of the rows [r0, r0+nr) from the per-CTA partials; one warp per row (two rows in flight per
 // warp), fixed summation order
-__device__ __forceinline__ void recv_row_sums(const u64* base, int par, int r0, int nr, unsigned tag, float inv, float* out1,
+__device__ __noinline__ void recv_row_sums(const u64* base, int par, int r0, int nr, unsigned tag, float inv, float* out1,
                                               float* out2, int tid, Spin& sp) {
   const int lane = tid & 31, wid = tid >> 5;
   for (int bb0 = wid; bb0 < nr; bb0 += 2 * SCAN_NW) {
@@ -961,7 +963,7 @@ __device__ __forceinline__ void recv_row_sums(const u64* base, int par, int r0, 
 }
 
 // per-row sums of the staged (dxh, dxh*xh) pairs of this CTA's columns -> LL partial for every row
-__device__ __forceinline__ void send_row_sums(const float* ST, int ncols, int B, u64* base, int par, int cta, unsigned tag, int tid) {
+__device__ __noinline__ void send_row_sums(const float* ST, int ncols, int B, u64* base, int par, int cta, unsigned tag, int tid) {
   const int lane = tid & 31, wid = tid >> 5;
   for (int b = wid; b < B; b += SCAN_NW) {
     float s1 = 0.f, s2 = 0.f;
