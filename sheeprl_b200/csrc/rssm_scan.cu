@@ -530,22 +530,7 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     __syncthreads();
     const float* fl = misc;
 
-    // ============ B1: h_in = (1-f) h_{t-1} + f h0 (agent.py:428), rows with f != 0 only; h-part of the GRU product
-    for (int b = 0; b < B; ++b) {
-      const float f = fl[b];
-      if (f != 0.f || t == 0)
-        for (int k = tid; k < R; k += SCAN_NT) Xh[b * g.sR + k] = (1.f - f) * ((t > 0) ? Xh[b * g.sR + k] : 0.f) + f * H0[k];
-    }
-    __syncthreads();
-    prof_mark(prof, 12, tlast, prof_on);
-    const int ksh = product(Xh, g.sR, Wg, g.wgst, g.ngh * 3, R, B, PART, ldp, 0, tid);
-    prof_mark(prof, 1, tlast, prof_on);
-    __syncthreads();
-    const float acch = pok ? part_sum(PART, ldp, ksh, pb, pc) : 0.f;
-    const float hin = sH.ok ? Xh[sH.b * g.sR + sH.col] : 0.f;
-    prof_mark(prof, 13, tlast, prof_on);
-
-    // ============ A: x_pre = W_in [z_in, a_in] for the owned columns, every row; z_in one-hot -> gather from the slice.
+    // ============ A (first: its hand-off is in flight while B1 runs): x_pre = W_in [z_in, a_in] for the owned columns, every row; z_in one-hot -> gather from the slice.
     // Warp b builds row b: lane = (column cj = lane / 8, part = lane % 8): 8 lanes sum S/8 gathered weights each, then a
     // fixed 3-level shuffle tree; the row's partial LayerNorm statistics go out with the values.
     if (t > 0)
@@ -596,6 +581,21 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
     if (cta == (t % SCAN_G))
       for (int e = tid; e < B * A; e += SCAN_NT) a.a_in[row0 * A + e] = (1.f - fl[e / A]) * a.actions[row0 * A + e];
     prof_mark(prof, 3, tlast, prof_on);
+
+    // ============ B1: h_in = (1-f) h_{t-1} + f h0 (agent.py:428), rows with f != 0 only; h-part of the GRU product
+    for (int b = 0; b < B; ++b) {
+      const float f = fl[b];
+      if (f != 0.f || t == 0)
+        for (int k = tid; k < R; k += SCAN_NT) Xh[b * g.sR + k] = (1.f - f) * ((t > 0) ? Xh[b * g.sR + k] : 0.f) + f * H0[k];
+    }
+    __syncthreads();
+    prof_mark(prof, 12, tlast, prof_on);
+    const int ksh = product(Xh, g.sR, Wg, g.wgst, g.ngh * 3, R, B, PART, ldp, 0, tid);
+    prof_mark(prof, 1, tlast, prof_on);
+    __syncthreads();
+    const float acch = pok ? part_sum(PART, ldp, ksh, pb, pc) : 0.f;
+    const float hin = sH.ok ? Xh[sH.b * g.sR + sH.col] : 0.f;
+    prof_mark(prof, 13, tlast, prof_on);
 
     // ============ B2: x-part of the GRU product; g_pre columns; partial LayerNorm statistics
     ll_recv<8>(Xx, xxs, ws.ll + L.x + (size_t)par * MAXB * Dx, Dx, B, Dx, tag, tid, sp);
@@ -774,24 +774,20 @@ __global__ void __launch_bounds__(SCAN_NT, 1) rssm_scan_fwd_kernel(const b200rl_
         const int nrp = nr <= 1 ? 1 : (nr <= 2 ? 2 : (nr <= 4 ? 4 : 8));
         const int wpr = SCAN_NW / nrp, bb = wid / wpr, wi = wid - bb * wpr;
         float* xr = Xx + bb * xxs;
-        float s = 0.f;
+        // one pass, one barrier: sum and sum of squares together (rp_pre is O(1): the E[x^2] - mean^2 form costs ~1e-7
+        // relative here, far inside the tolerance; the two-barrier centred form cost 1 k cycles of the critical path)
+        float s = 0.f, q2 = 0.f;
         if (bb < nr)
-          for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) s += xr[k];
+          for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) { const float xv = xr[k]; s += xv; q2 = fmaf(xv, xv, q2); }
         s = warp_sum(s);
-        if (lane == 0) misc[48 + wid] = s;
+        q2 = warp_sum(q2);
+        if (lane == 0) { misc[48 + wid] = s; misc[80 + wid] = q2; }
         __syncthreads();
-        float mu = 0.f;
-        for (int i = 0; i < wpr; ++i) mu += misc[48 + bb * wpr + i];
+        float mu = 0.f, var = 0.f;
+        for (int i = 0; i < wpr; ++i) { mu += misc[48 + bb * wpr + i]; var += misc[80 + bb * wpr + i]; }
         mu /= (float)Dr;
-        float v = 0.f;
-        if (bb < nr)
-          for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) { const float d = xr[k] - mu; v = fmaf(d, d, v); }
-        v = warp_sum(v);
-        if (lane == 0) misc[80 + wid] = v;
-        __syncthreads();
-        float var = 0.f;
-        for (int i = 0; i < wpr; ++i) var += misc[80 + bb * wpr + i];
-        const float rstd = rsqrtf(var / (float)Dr + a.eps);
+        var = fmaxf(var / (float)Dr - mu * mu, 0.f);
+        const float rstd = rsqrtf(var + a.eps);
         if (bb < nr) {
           for (int k = wi * 32 + lane; k < Dr; k += wpr * 32) {
             const float o = fsilu((xr[k] - mu) * rstd * LNRG[k] + LNRB[k]);
