@@ -46,6 +46,18 @@ int b200rl_gemm_tc_supported(const float* A, const float* B, int M, int N, int K
                              int transB);
 int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
                    int ldc, int transA, int transB, int accumulate, cudaStream_t stream);
+/* Dense block Linear(bias=False) -> LayerNorm(eps) -> activation in two launches (sheeprl/utils/model.py:34-88 miniblock,
+ * as built by MLP at sheeprl/models/models.py:23-119): the tcgen05 product leaves split-K partial tiles, one kernel sums
+ * them in split order, normalises the row in registers and applies the activation.  `pre` (optional) keeps W.x for the
+ * backward.  mode 1 (N = 3R): the tail is LayerNormGRUCell's gate instead (sheeprl/models/models.py:396-403): h_out (and
+ * h_out2, optional second copy, e.g. the next step's [h | x] input) = u * tanh(r * c) + (1 - u) * h_prev; `out` (optional)
+ * keeps LN(W.x).  A [M, K] (lda), W [N, K] (ldw): y = A W^T.  `_supported`: 16-byte aligned NT operands, N % 4 == 0,
+ * N <= 1536 (mode 1: N % 384 == 0). */
+int b200rl_gemm_ln_supported(const float* A, const float* W, int M, int N, int K, int lda, int ldw, int mode);
+int b200rl_gemm_ln(const float* A, const float* W, int M, int N, int K, int lda, int ldw, const float* gamma,
+                   const float* beta, float eps, int act, float* pre, long long ldpre, float* out, long long ldout,
+                   int mode, const float* h_prev, long long ldh, float* h_out, long long ldho, float* h_out2,
+                   long long ldho2, cudaStream_t stream);
 /* nn.LayerNorm(eps) (+ nn.SiLU): miniblock sheeprl/utils/model.py:34-88; LayerNormChannelLast
  * sheeprl/models/models.py:507-518 (channel-last is native here).  act: 0 none, 1 SiLU, 2 tanh, 3 ReLU (the last two:
  * PPO MLPs with layer_norm=True, sheeprl/algos/ppo/agent.py:58-66,152-176). */
@@ -104,6 +116,12 @@ int b200rl_mask_bwd(const float* dIn, const float* first, float* dPrev, float* d
 int b200rl_cat_sample(const float* raw, const float* noise, float* onehot, float* mix_out, long long M, int groups,
                       int classes, long long ldr, long long ldn, long long ldo, long long ldm, float unimix,
                       cudaStream_t stream);
+/* Policy head + straight-through sample in one launch (Actor.mlp_heads[i] + OneHotCategoricalStraightThrough.rsample,
+ * sheeprl/algos/dreamer_v3/agent.py:793-818): raw [M, A] = X W^T + bias, onehot = sample(unimix(raw), noise) with
+ * b200rl_cat_sample's rule.  A <= 32, Kin <= 1024, Kin % 4 == 0, 16-byte aligned rows. */
+int b200rl_head_sample(const float* X, const float* W, const float* bias, const float* noise, float* raw, float* onehot,
+                       long long M, int Kin, int A, long long ldx, long long ldw, long long ldr, long long ldn,
+                       long long ldo, float unimix, cudaStream_t stream);
 int b200rl_cat_sample_bwd(const float* raw, const float* dz, const float* dmix, float* draw, long long M, int groups,
                           int classes, long long ldr, long long lddz, long long lddm, long long lddr, float unimix,
                           cudaStream_t stream);
@@ -271,6 +289,11 @@ int b200rl_ppo_loss(const float* head, const float* actions, const float* old_lo
  * rollout.  z: [M, S*K] (row stride ldz), act: [M, A], out: [M, N]. */
 int b200rl_onehot_linear(const float* z, const float* act, const float* WT, float* out, long long M, int S, int K, int A,
                          int N, long long ldz, long long lda, long long ldo, cudaStream_t stream);
+/* The same gather followed, in the same launch, by the miniblock's LayerNorm(eps) + SiLU (N <= 1024): out = SiLU(LN(Linear
+ * ([z, a]))); `pre` (optional) keeps the Linear output. */
+int b200rl_onehot_linear_ln(const float* z, const float* act, const float* WT, const float* gamma, const float* beta,
+                            float eps, float* pre, long long ldpre, float* out, long long M, int S, int K, int A, int N,
+                            long long ldz, long long lda, long long ldo, cudaStream_t stream);
 
 /* ---- Dreamer-V3 continuous actions (policy gradient through the imagined rollout) -------------------------
  * Actor.forward `scaled_normal` branch agent.py:803-825: head = [mean | std_raw] (M x 2A), eps ~ N(0,1);

@@ -207,6 +207,7 @@ struct TileGeo {
   int ksplits;             // GEMM mode: number of K splits (gridDim.z); > 1 => partial tiles go through `part`
   float* part;             // split-K workspace: [ksplits][mpad][ldw] partial sums (fixed-order reduction, no atomics)
   int mpad, ldw;           // split-K workspace geometry (rows per split, row stride)
+  int force_part;          // write the partial tile to the workspace even with a single split (fused reduce + LayerNorm tail)
   int passes;              // 3: x = hi + lo split, three TF32 products per k-step (fp32-accurate); 1: one TF32 product
                            // (torch's float32_matmul_precision "high", the reference's default on GPUs)
   int a_mn, b_mn;          // GEMM mode: operand stored [K][M] / [K][N] (MN-major) instead of [M][K] / [N][K]
@@ -450,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       else row_off = (((size_t)n * (2 * geo.h) + (2 * y + py)) * (2 * geo.w) + (2 * x + px)) * (size_t)ldc;
     }
     bool store = true;
-    if (geo.mode == MODE_GEMM && geo.ksplits > 1) {
+    if (geo.mode == MODE_GEMM && (geo.ksplits > 1 || geo.force_part)) {
       // ---- deterministic split-K: this split's partial tile goes to the workspace; splitk_reduce_kernel (launched right
       // behind this kernel) sums the partials of every output element in split order — no atomics, bit-reproducible
       float* prow = geo.part + ((size_t)blockIdx.z * geo.mpad + (size_t)(m0 + q * 32 + lane)) * geo.ldw + n0 + half * ACC_COLS;
@@ -804,9 +805,15 @@ extern "C" int b200rl_gemm_tc_supported(const float* A, const float* B, int M, i
   return 1;
 }
 
-extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
-                              int ldb, int ldc, int transA, int transB, int accumulate, cudaStream_t st) {
-  RL_CHECK_ARG(A && B && C, "null pointer");
+namespace {
+// `fused`: when non-null the product always leaves its result as split-K partial tiles (one split is allowed) and the
+// caller launches the reduction itself, fused with what follows (LayerNorm, activation, GRU gate): *fused receives the
+// workspace geometry.
+struct FusedTail { float* part; int ks, mpad, ldw; };
+
+int gemm_tc_impl(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                 int ldb, int ldc, int transA, int transB, int accumulate, cudaStream_t st, FusedTail* fused) {
+  RL_CHECK_ARG(A && B && (C || fused), "null pointer");
   RL_CHECK_ARG(b200rl_gemm_tc_supported(A, B, M, N, K, lda, ldb, transA, transB), "shape not eligible for the tensor-core path");
   const int BN = (N <= 64) ? 64 : 128;
   CUtensorMap ma, mb;
@@ -839,21 +846,147 @@ extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const fl
     }
     g.ksplits = best;
   }
-  if (g.ksplits > 1) {
+  if (g.ksplits > 1 || fused) {
     grid.z = g.ksplits;
     g.mpad = (int)grid.y * BM;
     g.ldw = (int)grid.x * BN;
     if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, st, &g.part)) return rc;
+    if (fused) { g.force_part = 1; *fused = FusedTail{g.part, g.ksplits, g.mpad, g.ldw}; }
   }
   g.mtiles = (int)grid.y;
   grid.y = persistent_grid_y(g.mtiles, grid.x, grid.z);
   DISPATCH_GEMM_TC(BN, g.passes, grid, st, ma, mb, C, bias, M, N, K, ldc, accumulate, g);
   RL_CHECK_LAUNCH();
-  if (g.ksplits > 1) {
+  if (g.ksplits > 1 && !fused) {
     splitk_reduce_kernel<<<ceil_div((long long)M * ((N + 3) / 4), 256), 256, 0, st>>>(g.part, C, bias, M, N, ldc, g.ksplits, g.mpad,
                                                                                       g.ldw, accumulate);
     RL_CHECK_LAUNCH();
   }
+  return B200RL_OK;
+}
+
+// Fixed-order sum of the split-K partial tiles of a row, fused with LayerNorm (+ activation) or LayerNorm + GRU gate.
+// One warp per row, the row in registers (NV float4 per lane, N = 128 * NV or less).
+//   mode 0: out = act(LN(pre));  mode 1 (N = 3R, R % 128 == 0): LayerNormGRUCell gate (models.py:396-403) on the
+//   normalised (reset | cand | update) thirds with h_prev -> h_out (and h_out2).  `pre` / `ln_out` are optional saves.
+template <int NV>
+__global__ void __launch_bounds__(256)
+splitk_ln_kernel(const float* __restrict__ part, int ks, int mpad, int ldw, int M, int N, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, int act, float* __restrict__ pre, long long ldpre,
+                 float* __restrict__ ln_out, long long ldln, int mode, const float* __restrict__ h_prev, long long ldh,
+                 float* __restrict__ h_out, long long ldho, float* __restrict__ h_out2, long long ldho2) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  const int n4 = N >> 2;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < ks; ++z) {
+    const float4* p = reinterpret_cast<const float4*>(part + ((size_t)z * mpad + row) * ldw);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < n4) { const float4 t = __ldcg(p + c); v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w; }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < n4) {
+      if (pre) reinterpret_cast<float4*>(pre + row * ldpre)[c] = v[i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mu = warp_sum(s) / (float)N;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < n4) {
+      const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)N + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < n4) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[c], b = reinterpret_cast<const float4*>(beta)[c];
+      v[i].x = (v[i].x - mu) * rstd * g.x + b.x; v[i].y = (v[i].y - mu) * rstd * g.y + b.y;
+      v[i].z = (v[i].z - mu) * rstd * g.z + b.z; v[i].w = (v[i].w - mu) * rstd * g.w + b.w;
+      if (mode == 0 && act == 1) {   // SiLU
+        v[i].x = v[i].x / (1.f + expf(-v[i].x)); v[i].y = v[i].y / (1.f + expf(-v[i].y));
+        v[i].z = v[i].z / (1.f + expf(-v[i].z)); v[i].w = v[i].w / (1.f + expf(-v[i].w));
+      }
+      if (ln_out) reinterpret_cast<float4*>(ln_out + row * ldln)[c] = v[i];
+    }
+  }
+  if (mode == 1) {
+    constexpr int NR = NV / 3;      // float4 per lane of one third (R = 128 * NR)
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int c = lane + 32 * i;
+      const float4 hp = reinterpret_cast<const float4*>(h_prev + row * ldh)[c];
+      const float4 gr = v[i], gc = v[i + NR], gu = v[i + 2 * NR];
+      float4 h;
+      auto gate = [](float r_, float c_, float u_, float hprev) {
+        const float r = 1.f / (1.f + expf(-r_));
+        const float cand = tanhf(r * c_);
+        const float u = 1.f / (1.f + expf(-(u_ - 1.f)));
+        return u * cand + (1.f - u) * hprev;
+      };
+      h.x = gate(gr.x, gc.x, gu.x, hp.x); h.y = gate(gr.y, gc.y, gu.y, hp.y);
+      h.z = gate(gr.z, gc.z, gu.z, hp.z); h.w = gate(gr.w, gc.w, gu.w, hp.w);
+      reinterpret_cast<float4*>(h_out + row * ldho)[c] = h;
+      if (h_out2) reinterpret_cast<float4*>(h_out2 + row * ldho2)[c] = h;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int b200rl_gemm_tc(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                              int ldb, int ldc, int transA, int transB, int accumulate, cudaStream_t st) {
+  return gemm_tc_impl(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, accumulate, st, nullptr);
+}
+
+extern "C" int b200rl_gemm_ln_supported(const float* A, const float* B, int M, int N, int K, int lda, int ldb, int mode) {
+  if (!b200rl_gemm_tc_supported(A, B, M, N, K, lda, ldb, 0, 1)) return 0;
+  if (N % 4 || N > 1536) return 0;
+  if (mode == 1 && (N % 384 != 0)) return 0;      // three thirds of R = 128 * k columns each
+  return 1;
+}
+
+extern "C" int b200rl_gemm_ln(const float* A, const float* W, int M, int N, int K, int lda, int ldw_, const float* gamma,
+                              const float* beta, float eps, int act, float* pre, long long ldpre, float* out, long long ldout,
+                              int mode, const float* h_prev, long long ldh, float* h_out, long long ldho, float* h_out2,
+                              long long ldho2, cudaStream_t st) {
+  RL_CHECK_ARG(A && W && gamma && beta, "null pointer");
+  RL_CHECK_ARG(b200rl_gemm_ln_supported(A, W, M, N, K, lda, ldw_, mode), "shape not eligible for the fused product + LayerNorm");
+  RL_CHECK_ARG(mode == 0 ? out != nullptr : (h_prev && h_out), "missing output");
+  RL_CHECK_ARG(((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(pre) |
+                 reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(h_prev) | reinterpret_cast<uintptr_t>(h_out) |
+                 reinterpret_cast<uintptr_t>(h_out2)) & 15) == 0 &&
+                   ((ldpre | ldout | ldh | ldho | ldho2) & 3) == 0,
+               "fused product + LayerNorm needs 16-byte aligned rows");
+  FusedTail ft;
+  if (int rc = gemm_tc_impl(A, W, nullptr, nullptr, M, N, K, lda, ldw_, N, 0, 1, 0, st, &ft)) return rc;
+  const int blocks = ceil_div((long long)M * 32, 256);
+#define LAUNCH_SPLITK_LN(NV_)                                                                                              \
+  splitk_ln_kernel<NV_><<<blocks, 256, 0, st>>>(ft.part, ft.ks, ft.mpad, ft.ldw, M, N, gamma, beta, eps, act, pre, ldpre, out, \
+                                                ldout, mode, h_prev, ldh, h_out, ldho, h_out2, ldho2)
+  if (mode == 1) {
+    if (N == 384) LAUNCH_SPLITK_LN(3); else if (N == 768) LAUNCH_SPLITK_LN(6); else if (N == 1152) LAUNCH_SPLITK_LN(9);
+    else LAUNCH_SPLITK_LN(12);
+  } else if (N <= 128) LAUNCH_SPLITK_LN(1);
+  else if (N <= 256) LAUNCH_SPLITK_LN(2);
+  else if (N <= 512) LAUNCH_SPLITK_LN(4);
+  else if (N <= 1024) LAUNCH_SPLITK_LN(8);
+  else LAUNCH_SPLITK_LN(12);
+#undef LAUNCH_SPLITK_LN
+  RL_CHECK_LAUNCH();
   return B200RL_OK;
 }
 

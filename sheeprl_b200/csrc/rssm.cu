@@ -168,6 +168,38 @@ cat_sample_kernel(const float* __restrict__ raw, const float* __restrict__ noise
 
 // K <= 32: one class per lane, every quantity computed once and kept in a register.  Same expressions and the same
 // butterfly reductions as cat_sample_kernel, so samples and log-probs are bit-identical to the general path.
+__device__ __forceinline__ void cat_sample_lane(float xv, bool on, int K, int lane, float unimix,
+                                                const float* __restrict__ noise_row, float* __restrict__ onehot_row,
+                                                float* __restrict__ mix_row) {
+  const float mx = warp_max(xv);
+  const float sm = warp_sum(on ? expf(xv - mx) : 0.f);
+  const float invK = 1.f / (float)K;
+  float l = xv;
+  if (unimix > 0.f && on) { float pm; l = unimix_logprob(expf(xv - mx) / sm, unimix, invK, pm); }
+  const float lmx = warp_max(on ? l : -INFINITY);
+  const float ls = warp_sum(on ? expf(l - lmx) : 0.f);
+  const float lse = lmx + logf(ls);
+  if (mix_row && on) mix_row[lane] = l;
+  const float lgmax = warp_max(on ? l - lse : -INFINITY);
+  const float e = on ? expf(l - lse - lgmax) : 0.f;
+  const float psum = warp_sum(e);
+  if (!onehot_row) return;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  if (on) {
+    float p = e / psum;
+    if (noise_row) p = p / noise_row[lane];
+    if (p > best) { best = p; besti = lane; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (on) onehot_row[lane] = (lane == besti) ? 1.f : 0.f;
+}
+
 __global__ void __launch_bounds__(256)
 cat_sample_small_kernel(const float* __restrict__ raw, const float* __restrict__ noise, float* __restrict__ onehot,
                         float* __restrict__ mix_out, long long M, int groups, int K, long long ldr, long long ldn,
@@ -179,33 +211,45 @@ cat_sample_small_kernel(const float* __restrict__ raw, const float* __restrict__
   const int g = (int)(warp - m * groups);
   const bool on = lane < K;
   const float xv = on ? raw[m * ldr + (long long)g * K + lane] : -INFINITY;
-  const float mx = warp_max(xv);
-  const float sm = warp_sum(on ? expf(xv - mx) : 0.f);
-  const float invK = 1.f / (float)K;
-  float l = xv;
-  if (unimix > 0.f && on) { float pm; l = unimix_logprob(expf(xv - mx) / sm, unimix, invK, pm); }
-  const float lmx = warp_max(on ? l : -INFINITY);
-  const float ls = warp_sum(on ? expf(l - lmx) : 0.f);
-  const float lse = lmx + logf(ls);
-  if (mix_out && on) mix_out[m * ldm + (long long)g * K + lane] = l;
-  const float lgmax = warp_max(on ? l - lse : -INFINITY);
-  const float e = on ? expf(l - lse - lgmax) : 0.f;
-  const float psum = warp_sum(e);
-  if (!onehot) return;
-  float best = -INFINITY;
-  int besti = 0x7fffffff;
-  if (on) {
-    float p = e / psum;
-    if (noise) p = p / noise[m * ldn + (long long)g * K + lane];
-    if (p > best) { best = p; besti = lane; }
-  }
+  cat_sample_lane(xv, on, K, lane, unimix, noise ? noise + m * ldn + (long long)g * K : nullptr,
+                  onehot ? onehot + m * ldo + (long long)g * K : nullptr, mix_out ? mix_out + m * ldm + (long long)g * K : nullptr);
+}
+
+// Policy head + sample in one launch (Actor.mlp_heads[i] then OneHotCategoricalStraightThrough.rsample, agent.py:793-818):
+// one warp per row computes the A <= 32 logits of a [A, Kin] Linear (+ bias) on its row (Kin % 4 == 0, Kin <= 1024: the
+// row stays in registers), writes them (`raw`, kept for the policy gradient) and draws the sample like cat_sample.
+__global__ void __launch_bounds__(256)
+head_sample_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+                   const float* __restrict__ noise, float* __restrict__ raw, float* __restrict__ onehot, long long M, int Kin,
+                   int A, long long ldx, long long ldw, long long ldr, long long ldn, long long ldo, float unimix) {
+  const int lane = threadIdx.x & 31;
+  const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const int k4 = Kin >> 2;
+  float4 x[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    x[i] = c < k4 ? reinterpret_cast<const float4*>(X + m * ldx)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (on) onehot[m * ldo + (long long)g * K + lane] = (lane == besti) ? 1.f : 0.f;
+  float mine = -INFINITY;
+  for (int a = 0; a < A; ++a) {
+    const float4* w = reinterpret_cast<const float4*>(W + (long long)a * ldw);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < k4) {
+        const float4 t = __ldg(w + c);
+        acc = fmaf(x[i].x, t.x, acc); acc = fmaf(x[i].y, t.y, acc); acc = fmaf(x[i].z, t.z, acc); acc = fmaf(x[i].w, t.w, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == a) mine = acc + (bias ? bias[a] : 0.f);
+  }
+  const bool on = lane < A;
+  if (on) raw[m * ldr + lane] = mine;
+  cat_sample_lane(mine, on, A, lane, unimix, noise ? noise + m * ldn : nullptr, onehot + m * ldo, nullptr);
 }
 
 __global__ void __launch_bounds__(256)
@@ -331,11 +375,16 @@ kl_loss_grad_kernel(const float* __restrict__ post, const float* __restrict__ pr
 // z is a concatenation of S one-hot groups (a straight-through categorical sample), so Linear([z, a]) is a gather-sum
 // of S+A rows of the transposed weight instead of a K = S*K + A product (agent.py:328-341 RecurrentModel.mlp input).
 // One CTA per row; WT [S*K + A, N] row-major (transposed copy of the Linear weight, L2 resident).
+// With `gamma`: the row continues through LayerNorm(eps) + SiLU (RecurrentModel.mlp's miniblock) before it is written
+// (N <= 1024: the row lives in 4 registers per thread); `pre` optionally keeps the Linear output for a backward.
 __global__ void __launch_bounds__(256)
 onehot_linear_kernel(const float* __restrict__ z, const float* __restrict__ act, const float* __restrict__ WT,
-                     float* __restrict__ out, int S, int K, int A, int N, long long ldz, long long lda, long long ldo) {
+                     float* __restrict__ out, int S, int K, int A, int N, long long ldz, long long lda, long long ldo,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ pre,
+                     long long ldpre) {
   __shared__ int idx[64];
   __shared__ float av[32];
+  __shared__ float red[8];
   const long long m = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int g = warp; g < S; g += 8) {                       // hot index of each group by ballot
@@ -349,12 +398,56 @@ onehot_linear_kernel(const float* __restrict__ z, const float* __restrict__ act,
   }
   if (threadIdx.x < A) av[threadIdx.x] = act[m * lda + threadIdx.x];
   __syncthreads();
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float acc = 0.f;
+  if (gamma == nullptr) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      float acc = 0.f;
 #pragma unroll 8
-    for (int g = 0; g < S; ++g) acc += __ldg(WT + ((long long)g * K + idx[g]) * N + n);   // independent L2 loads in flight
-    for (int a = 0; a < A; ++a) acc = fmaf(av[a], __ldg(WT + ((long long)S * K + a) * N + n), acc);
-    out[m * ldo + n] = acc;
+      for (int g = 0; g < S; ++g) acc += __ldg(WT + ((long long)g * K + idx[g]) * N + n);   // independent L2 loads in flight
+      for (int a = 0; a < A; ++a) acc = fmaf(av[a], __ldg(WT + ((long long)S * K + a) * N + n), acc);
+      out[m * ldo + n] = acc;
+    }
+    return;
+  }
+  float v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = threadIdx.x + 256 * i;
+    float acc = 0.f;
+    if (n < N) {
+#pragma unroll 8
+      for (int g = 0; g < S; ++g) acc += __ldg(WT + ((long long)g * K + idx[g]) * N + n);
+      for (int a = 0; a < A; ++a) acc = fmaf(av[a], __ldg(WT + ((long long)S * K + a) * N + n), acc);
+      if (pre) pre[m * ldpre + n] = acc;
+    }
+    v[i] = acc;
+    s += acc;
+  }
+  auto block_sum = [&](float x) {
+    x = warp_sum(x);
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
+  };
+  const float mu = block_sum(s) / (float)N;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float d = v[i] - mu;
+    if (threadIdx.x + 256 * i < N) q += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(q) / (float)N + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = threadIdx.x + 256 * i;
+    if (n < N) {
+      const float y = (v[i] - mu) * rstd * gamma[n] + beta[n];
+      out[m * ldo + n] = y / (1.f + expf(-y));
+    }
   }
 }
 
@@ -414,6 +507,20 @@ extern "C" int b200rl_cat_sample(const float* raw, const float* noise, float* on
   return B200RL_OK;
 }
 
+extern "C" int b200rl_head_sample(const float* X, const float* W, const float* bias, const float* noise, float* raw,
+                                  float* onehot, long long M, int Kin, int A, long long ldx, long long ldw, long long ldr,
+                                  long long ldn, long long ldo, float unimix, cudaStream_t st) {
+  RL_CHECK_ARG(X && W && raw && onehot, "null pointer");
+  RL_CHECK_ARG(A > 0 && A <= 32 && Kin > 0 && Kin <= 1024 && Kin % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) == 0,
+               "head_sample: A <= 32, Kin <= 1024, 16-byte aligned rows");
+  if (M <= 0) return B200RL_OK;
+  head_sample_kernel<<<ceil_div(M * 32, 256), 256, 0, st>>>(X, W, bias, noise, raw, onehot, M, Kin, A, ldx, ldw, ldr, ldn, ldo,
+                                                            unimix);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
 extern "C" int b200rl_cat_sample_bwd(const float* raw, const float* dz, const float* dmix, float* draw, long long M,
                                      int groups, int K, long long ldr, long long lddz, long long lddm,
                                      long long lddr, float unimix, cudaStream_t st) {
@@ -444,7 +551,20 @@ extern "C" int b200rl_onehot_linear(const float* z, const float* act, const floa
   RL_CHECK_ARG(z && act && WT && out, "null pointer");
   RL_CHECK_ARG(S > 0 && S <= 64 && K > 0 && A >= 0 && A <= 32 && N > 0, "bad dims (S <= 64 groups, A <= 32)");
   if (M <= 0) return B200RL_OK;
-  onehot_linear_kernel<<<(unsigned)M, 256, 0, st>>>(z, act, WT, out, S, K, A, N, ldz, lda, ldo);
+  onehot_linear_kernel<<<(unsigned)M, 256, 0, st>>>(z, act, WT, out, S, K, A, N, ldz, lda, ldo, nullptr, nullptr, 0.f, nullptr, 0);
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_onehot_linear_ln(const float* z, const float* act, const float* WT, const float* gamma,
+                                       const float* beta, float eps, float* pre, long long ldpre, float* out, long long M,
+                                       int S, int K, int A, int N, long long ldz, long long lda, long long ldo,
+                                       cudaStream_t st) {
+  RL_CHECK_ARG(z && act && WT && out && gamma && beta, "null pointer");
+  RL_CHECK_ARG(S > 0 && S <= 64 && K > 0 && A >= 0 && A <= 32 && N > 0 && N <= 1024,
+               "bad dims (S <= 64 groups, A <= 32, N <= 1024)");
+  if (M <= 0) return B200RL_OK;
+  onehot_linear_kernel<<<(unsigned)M, 256, 0, st>>>(z, act, WT, out, S, K, A, N, ldz, lda, ldo, gamma, beta, eps, pre, ldpre);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }

@@ -142,6 +142,21 @@ def _check_supported_modules(cfg) -> None:
             raise NotImplementedError(f"algo.{name}: dense_units / mlp_layers must equal algo.dense_units / algo.mlp_layers")
 
 
+FUSED_DENSE_MAX_ROWS = 4096
+
+
+def dense_ln_act(ops, x, W, gamma, beta, eps, act, out, pre=None, scratch=None):
+    """out = act(LayerNorm(x W^T)) (the miniblock of sheeprl/utils/model.py:34-88, bias-free Linear).  Small row counts
+    (imagination steps, heads on one batch) take the two-launch fused path of csrc/gemm_tc.cu; `pre` keeps x W^T for a
+    backward and may be None there.  The unfused path needs somewhere to put x W^T: `pre`, else `scratch`."""
+    if (x.shape[0] <= FUSED_DENSE_MAX_ROWS and hasattr(ops, "gemm_ln_act") and ops.gemm_ln_supported(x, W)):
+        ops.gemm_ln_act(x, W, gamma, beta, eps, act, out, pre)
+        return
+    tmp = pre if pre is not None else scratch
+    ops.gemm(x, W, tmp, False, True)
+    ops.ln_act_fwd(tmp, gamma, beta, eps, act, out)
+
+
 class _MLP:
     """n_hidden x [Linear(no bias) -> LN -> SiLU] (+ output Linear with bias): forward with saved
     pre-activations, hand-written backward.  (reference: sheeprl/models/models.py:16-119)"""
@@ -169,9 +184,8 @@ class _MLP:
         M = x.shape[0] if M is None else M
         cur = x
         for i in range(self.n_hidden):
-            ops.gemm(cur, g.views[f"{self.prefix}{3 * i}.weight"], self.pre[i][:M], False, True)
-            ops.ln_act_fwd(self.pre[i][:M], g.views[f"{self.prefix}{3 * i + 1}.weight"],
-                           g.views[f"{self.prefix}{3 * i + 1}.bias"], self.eps, ACT_SILU, self.act[i][:M])
+            dense_ln_act(ops, cur, g.views[f"{self.prefix}{3 * i}.weight"], g.views[f"{self.prefix}{3 * i + 1}.weight"],
+                         g.views[f"{self.prefix}{3 * i + 1}.bias"], self.eps, ACT_SILU, self.act[i][:M], self.pre[i][:M])
             cur = self.act[i][:M]
         if self.out_dim is None:
             return cur
@@ -749,20 +763,35 @@ class DV3Engine:
         ops.gemm(self.d_dec_lin, self._w(p + "0.weight"), self.d_latent, False, False)
 
     # ------------------------------------------------------------------ RSSM pieces
-    def _recurrent_forward(self, z, act, h_prev, x_pre, x_act, g_pre, g_ln, h_out, win_t=None, hx=None):
+    def _recurrent_forward(self, z, act, h_prev, x_pre, x_act, g_pre, g_ln, h_out, win_t=None, hx=None, h_next=None,
+                           keep: bool = True):
         """RecurrentModel + LayerNormGRUCell on M rows (agent.py:328-341, models.py:396-403).  `win_t`: transposed
-        first-layer weight; given only when z is an exact one-hot sample (imagination), the product becomes a gather."""
+        first-layer weight; given only when z is an exact one-hot sample (imagination), the product becomes a gather.
+        `keep`: pre-activations are needed by a backward (x_pre / g_pre / g_ln are written); `h_next`: optional second
+        destination of the new h.  Returns True when `h_next` was written."""
         ops, Z, R = self.ops, self.Z, self.R
         p = "rssm.recurrent_model."
         Win = self._w(p + "mlp._model.0.weight")
-        if win_t is not None:
+        fused_x = win_t is not None and hasattr(ops, "onehot_linear_ln") and win_t.shape[1] <= 1024
+        if fused_x:
+            ops.onehot_linear_ln(z, act, win_t, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"),
+                                 self.eps, x_act, self.S, self.D, pre=x_pre if keep else None)
+        elif win_t is not None:
             ops.onehot_linear(z, act, win_t, x_pre, self.S, self.D)
         else:
             ops.gemm(z, Win[:, :Z], x_pre, False, True)
             ops.gemm(act, Win[:, Z:], x_pre, False, True, accumulate=True)
-        ops.ln_act_fwd(x_pre, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"), self.eps,
-                       ACT_SILU, x_act)
+        if not fused_x:
+            ops.ln_act_fwd(x_pre, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"), self.eps,
+                           ACT_SILU, x_act)
         Wg = self._w(p + "rnn.linear.weight")
+        if (hx is not None and hx.shape[0] <= FUSED_DENSE_MAX_ROWS and hasattr(ops, "gemm_ln_gru")
+                and ops.gemm_ln_supported(hx, Wg, 1)):
+            # product + split-K sum + LayerNorm + gate in two launches; the new h also lands in `h_next` (the next
+            # step's [h | x] input)
+            ops.gemm_ln_gru(hx, Wg, self._w(p + "rnn.layer_norm.weight"), self._w(p + "rnn.layer_norm.bias"), self.eps,
+                            h_prev, h_out, h_next, g_pre if keep else None, g_ln if keep else None)
+            return True
         if hx is not None:                                   # [h | x] contiguous (x_act is its right half)
             ops.gemm(hx, Wg, g_pre, False, True)
         else:
@@ -771,12 +800,13 @@ class DV3Engine:
         ops.ln_act_fwd(g_pre, self._w(p + "rnn.layer_norm.weight"), self._w(p + "rnn.layer_norm.bias"), self.eps,
                        ACT_NONE, g_ln)
         ops.gru_gate_fwd(g_ln, h_prev, h_out)
+        return False
 
-    def _transition_forward(self, h, tr_pre, tr_act, raw):
+    def _transition_forward(self, h, tr_pre, tr_act, raw, keep: bool = True):
         ops = self.ops
         p = "rssm.transition_model._model."
-        ops.gemm(h, self._w(p + "0.weight"), tr_pre, False, True)
-        ops.ln_act_fwd(tr_pre, self._w(p + "1.weight"), self._w(p + "1.bias"), self.eps, ACT_SILU, tr_act)
+        dense_ln_act(ops, h, self._w(p + "0.weight"), self._w(p + "1.weight"), self._w(p + "1.bias"), self.eps, ACT_SILU,
+                     tr_act, tr_pre if keep else None, scratch=tr_pre)
         ops.gemm(tr_act, self._w(p + "3.weight"), raw, False, True, bias=self._w(p + "3.bias"))
 
     def _scan_forward(self, first: torch.Tensor):
@@ -1047,6 +1077,7 @@ class DV3Engine:
             if getattr(self, "_win_t", None) is None:
                 self._win_t = torch.empty(Win.shape[1], Win.shape[0], dtype=torch.float32, device=self.device)
             ops.transpose2d(Win, self._win_t)
+        h_staged = False
         for i in range(H + 1):
             rows = slice(i * N, (i + 1) * N)
             if i > 0:
@@ -1058,20 +1089,38 @@ class DV3Engine:
                 else:
                     x_pre, hx, g_pre, g_ln = self.i_x_pre, self.i_hx, self.i_g_pre, self.i_g_ln
                     tr_pre, tr_act, raw = self.i_tr_pre, self.i_tr_act, self.i_raw
-                ops.copy(prev[:, Z:], hx[:, :R])
-                self._recurrent_forward(prev[:, :Z], self.actions[i - 1], prev[:, Z:], x_pre, hx[:, R:], g_pre, g_ln,
-                                        cur[:, Z:], win_t=self._win_t if gather else None, hx=hx)
-                self._transition_forward(cur[:, Z:], tr_pre, tr_act, raw)
+                if not h_staged:
+                    ops.copy(prev[:, Z:], hx[:, :R])
+                keep = self.is_continuous
+                h_next = None
+                if i < H:
+                    h_next = (self.c_hx[i] if self.is_continuous else hx)[:, :R]
+                h_staged = self._recurrent_forward(prev[:, :Z], self.actions[i - 1], prev[:, Z:], x_pre, hx[:, R:], g_pre,
+                                                   g_ln, cur[:, Z:], win_t=self._win_t if gather else None, hx=hx,
+                                                   h_next=h_next, keep=keep) and h_next is not None
+                self._transition_forward(cur[:, Z:], tr_pre, tr_act, raw, keep=keep)
                 ops.cat_sample(raw, self.noise_img_state[i - 1], self.unimix, self.S, self.D, cur[:, :Z])
             # actor on traj[i]; activations are kept for the policy-gradient backward (the reference's second
             # actor evaluation at dreamer_v3.py:273 recomputes exactly these numbers)
             x = self.traj[i]
             cur_in = x
             for l in range(am.n_hidden):
-                ops.gemm(cur_in, am.W(l), am.pre[l][rows], False, True)
-                ops.ln_act_fwd(am.pre[l][rows], actor.views[f"model._model.{3 * l + 1}.weight"],
-                               actor.views[f"model._model.{3 * l + 1}.bias"], self.eps, ACT_SILU, am.act[l][rows])
+                dense_ln_act(ops, cur_in, am.W(l), actor.views[f"model._model.{3 * l + 1}.weight"],
+                             actor.views[f"model._model.{3 * l + 1}.bias"], self.eps, ACT_SILU, am.act[l][rows],
+                             am.pre[l][rows])
                 cur_in = am.act[l][rows]
+            if not self.is_continuous and hasattr(ops, "head_sample"):
+                off, done = 0, True
+                for k, ad in enumerate(self.actions_dim):
+                    Wh = actor.views[f"mlp_heads.{k}.weight"]
+                    done = done and ops.head_sample_supported(cur_in, Wh)
+                if done:
+                    for k, ad in enumerate(self.actions_dim):
+                        ops.head_sample(cur_in, actor.views[f"mlp_heads.{k}.weight"], actor.views[f"mlp_heads.{k}.bias"],
+                                        self.noise_img_action[i, :, off:off + ad], self.unimix,
+                                        self.actor_raw[rows, off:off + ad], self.actions[i, :, off:off + ad])
+                        off += ad
+                    continue
             self._actor_heads(cur_in, self.actor_raw[rows], actor)
             if self.is_continuous:
                 ac = self.cfg.algo.actor

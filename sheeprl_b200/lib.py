@@ -138,6 +138,37 @@ class CudaOps:
                                           c_int(_ld(B)), c_int(_ld(C)), c_int(int(transA)), c_int(int(transB)),
                                           c_int(int(accumulate)), self._st()))
 
+    def gemm_ln_supported(self, A, W, mode: int = 0) -> bool:
+        M, K = A.shape
+        return self.use_tc and bool(self.lib.b200rl_gemm_ln_supported(_p(A), _p(W), c_int(M), c_int(W.shape[0]), c_int(K),
+                                                                     c_int(_ld(A)), c_int(_ld(W)), c_int(mode)))
+
+    def gemm_ln_act(self, A, W, gamma, beta, eps: float, act: int, out, pre=None):
+        """out = act(LayerNorm(A W^T)); `pre` (optional) receives A W^T.  Two launches (product, fused reduce + LN)."""
+        _f32(A, W, gamma, beta, out, pre)
+        M, K = A.shape
+        N = W.shape[0]
+        assert W.shape[1] == K and out.shape == (M, N)
+        self._ck(self.lib.b200rl_gemm_ln(_p(A), _p(W), c_int(M), c_int(N), c_int(K), c_int(_ld(A)), c_int(_ld(W)), _p(gamma),
+                                         _p(beta), c_float(eps), c_int(act), _p(pre), c_ll(_ld(pre) if pre is not None else 0),
+                                         _p(out), c_ll(_ld(out)), c_int(0), _p(None), c_ll(0), _p(None), c_ll(0), _p(None), c_ll(0),
+                                         self._st()))
+        self.launches += 1
+
+    def gemm_ln_gru(self, A, W, gamma, beta, eps: float, h_prev, h_out, h_out2=None, g_pre=None, g_ln=None):
+        """LayerNormGRUCell on [h | x] rows `A`: h_out = gate(LayerNorm(A W^T), h_prev) (models.py:396-403)."""
+        _f32(A, W, gamma, beta, h_prev, h_out, h_out2, g_pre, g_ln)
+        M, K = A.shape
+        N = W.shape[0]
+        assert W.shape[1] == K and h_prev.shape == (M, N // 3) and h_out.shape == (M, N // 3)
+        self._ck(self.lib.b200rl_gemm_ln(_p(A), _p(W), c_int(M), c_int(N), c_int(K), c_int(_ld(A)), c_int(_ld(W)), _p(gamma),
+                                         _p(beta), c_float(eps), c_int(0), _p(g_pre),
+                                         c_ll(_ld(g_pre) if g_pre is not None else 0), _p(g_ln),
+                                         c_ll(_ld(g_ln) if g_ln is not None else 0), c_int(1), _p(h_prev), c_ll(_ld(h_prev)),
+                                         _p(h_out), c_ll(_ld(h_out)), _p(h_out2),
+                                         c_ll(_ld(h_out2) if h_out2 is not None else 0), self._st()))
+        self.launches += 1
+
     def _scratch(self, slot: str, numel: int) -> torch.Tensor:
         buf = self._scratch_bufs.get(slot)
         if buf is None or buf.numel() < numel:
@@ -267,6 +298,21 @@ class CudaOps:
             _p(raw), _p(noise), _p(onehot), _p(mix_out), c_ll(M), c_int(groups), c_int(classes), c_ll(_ld(raw)),
             c_ll(_ld(noise) if noise is not None else 0), c_ll(_ld(onehot) if onehot is not None else 0),
             c_ll(_ld(mix_out) if mix_out is not None else 0), c_float(unimix), self._st()))
+
+    def head_sample_supported(self, X, W) -> bool:
+        return (W.shape[0] <= 32 and X.shape[1] <= 1024 and X.shape[1] % 4 == 0 and _ld(X) % 4 == 0 and _ld(W) % 4 == 0
+                and X.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0)
+
+    def head_sample(self, X, W, bias, noise, unimix: float, raw, onehot):
+        """raw = X W^T + bias; onehot = straight-through categorical sample of unimix(raw) — one launch."""
+        _f32(X, W, bias, noise, raw, onehot)
+        M, Kin = X.shape
+        A = W.shape[0]
+        assert raw.shape == (M, A) and onehot.shape == (M, A) and W.shape[1] == Kin
+        self._ck(self.lib.b200rl_head_sample(_p(X), _p(W), _p(bias), _p(noise), _p(raw), _p(onehot), c_ll(M), c_int(Kin),
+                                             c_int(A), c_ll(_ld(X)), c_ll(_ld(W)), c_ll(_ld(raw)),
+                                             c_ll(_ld(noise) if noise is not None else 0), c_ll(_ld(onehot)),
+                                             c_float(unimix), self._st()))
 
     def cat_sample_bwd(self, raw, dz, dmix, unimix: float, groups: int, classes: int, draw):
         _f32(raw, dz, dmix, draw)
@@ -601,6 +647,16 @@ class CudaOps:
         assert WT.is_contiguous() and WT.shape[0] == groups * classes + A and out.shape == (M, N)
         self._ck(self.lib.b200rl_onehot_linear(_p(z), _p(act), _p(WT), _p(out), c_ll(M), c_int(groups), c_int(classes),
                                                c_int(A), c_int(N), c_ll(_ld(z)), c_ll(_ld(act)), c_ll(_ld(out)), self._st()))
+
+    def onehot_linear_ln(self, z, act, WT, gamma, beta, eps: float, out, groups: int, classes: int, pre=None):
+        """out = SiLU(LayerNorm(Linear([one-hot z, act]))) in one launch; `pre` (optional) keeps the Linear output."""
+        _f32(z, act, WT, gamma, beta, out, pre)
+        M, A, N = z.shape[0], act.shape[1], WT.shape[1]
+        assert WT.is_contiguous() and WT.shape[0] == groups * classes + A and out.shape == (M, N) and N <= 1024
+        self._ck(self.lib.b200rl_onehot_linear_ln(_p(z), _p(act), _p(WT), _p(gamma), _p(beta), c_float(eps), _p(pre),
+                                                  c_ll(_ld(pre) if pre is not None else 0), _p(out), c_ll(M), c_int(groups),
+                                                  c_int(classes), c_int(A), c_int(N), c_ll(_ld(z)), c_ll(_ld(act)),
+                                                  c_ll(_ld(out)), self._st()))
 
     # ------------------------------------------------------------------ Dreamer-V3 continuous actions (csrc/dv3_cont.cu)
     def cont_action_fwd(self, head, eps, action, ent, min_std: float, max_std: float, init_std: float, clip: float):

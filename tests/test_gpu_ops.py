@@ -619,3 +619,99 @@ def test_twohot_kernel_reproduces_the_reference_known_answers(ops):
     from tests.test_twohot_kat_cpu import check, twohot_targets
 
     check(twohot_targets(ops[0], device="cuda"))
+
+
+# ---- fused imagination ops: each must equal the composition of the ops it replaces (oracle/ops_emul.py) ---------------------
+@pytest.mark.parametrize("M,N,K,act,keep", [(1024, 512, 512, 1, True), (1024, 512, 1536, 1, False), (1024, 1024, 1024, 1, True),
+                                            (64, 512, 512, 0, True), (200, 100, 68, 1, True), (4096, 1536, 512, 0, False)])
+def test_gemm_ln_act_equals_gemm_then_layernorm(ops, M, N, K, act, keep):
+    cu, em = ops
+    X, W = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    gamma, beta = 1 + 0.1 * rnd(N, seed=3), 0.1 * rnd(N, seed=4)
+    pre_c, out_c = torch.empty(M, N), torch.empty(M, N)
+    em.gemm(X, W, pre_c, False, True)
+    em.ln_act_fwd(pre_c, gamma, beta, 1e-3, act, out_c)
+    Xg, Wg = X.cuda(), W.cuda()
+    assert cu.gemm_ln_supported(Xg, Wg)
+    wide = torch.zeros(M, N + 8, device="cuda")                # outputs inside wider rows
+    out_g, pre_g = wide[:, :N], (torch.empty(M, N, device="cuda") if keep else None)
+    cu.gemm_ln_act(Xg, Wg, gamma.cuda(), beta.cuda(), 1e-3, act, out_g, pre_g)
+    close(out_g, out_c, rtol=2e-5, atol=2e-6, what="gemm_ln_act")
+    if keep:
+        close(pre_g, pre_c, rtol=2e-5, what="gemm_ln_act pre")
+    assert float(wide[:, N:].abs().max()) == 0.0
+    # bit-reproducible: fixed-order partial sums
+    out2 = torch.empty(M, N, device="cuda")
+    cu.gemm_ln_act(Xg, Wg, gamma.cuda(), beta.cuda(), 1e-3, act, out2, None)
+    assert torch.equal(out2, out_g)
+
+
+@pytest.mark.parametrize("M,R,Kx", [(1024, 512, 512), (1024, 128, 64), (64, 1024, 1024), (4096, 384, 384)])
+def test_gemm_ln_gru_equals_unfused_cell(ops, M, R, Kx):
+    cu, em = ops
+    hx = rnd(M, R + Kx, seed=1)
+    W = rnd(3 * R, R + Kx, seed=2, scale=(R + Kx) ** -0.5)
+    gamma, beta = 1 + 0.1 * rnd(3 * R, seed=3), 0.1 * rnd(3 * R, seed=4)
+    h_prev = hx[:, :R].clone()
+    g_pre, g_ln, h_c = torch.empty(M, 3 * R), torch.empty(M, 3 * R), torch.empty(M, R)
+    em.gemm(hx, W, g_pre, False, True)
+    em.ln_act_fwd(g_pre, gamma, beta, 1e-3, 0, g_ln)
+    em.gru_gate_fwd(g_ln, h_prev, h_c)
+    hxg, Wg = hx.cuda(), W.cuda()
+    assert cu.gemm_ln_supported(hxg, Wg, 1)
+    traj = torch.zeros(M, 40 + R, device="cuda")
+    nxt = torch.zeros(M, R + Kx, device="cuda")
+    pre_g, ln_g = torch.empty(M, 3 * R, device="cuda"), torch.empty(M, 3 * R, device="cuda")
+    cu.gemm_ln_gru(hxg, Wg, gamma.cuda(), beta.cuda(), 1e-3, h_prev.cuda(), traj[:, 40:], nxt[:, :R], pre_g, ln_g)
+    close(traj[:, 40:], h_c, rtol=2e-5, atol=2e-6, what="fused GRU h")
+    assert torch.equal(nxt[:, :R], traj[:, 40:]) and float(nxt[:, R:].abs().max()) == 0.0
+    close(pre_g, g_pre, rtol=2e-5, what="fused GRU pre"), close(ln_g, g_ln, rtol=2e-5, atol=2e-5, what="fused GRU ln")
+    # in place on the [h | x] buffer it just read (the discrete-action rollout), without the optional saves
+    h2 = torch.empty(M, R, device="cuda")
+    cu.gemm_ln_gru(hxg, Wg, gamma.cuda(), beta.cuda(), 1e-3, h_prev.cuda(), h2, hxg[:, :R])
+    assert torch.equal(h2, traj[:, 40:]) and torch.equal(hxg[:, :R], h2)
+
+
+@pytest.mark.parametrize("M,S,D,A,N,keep", [(1024, 32, 32, 2, 512, False), (64, 6, 5, 3, 100, True), (256, 32, 32, 18, 1024, True)])
+def test_onehot_linear_ln_equals_gather_then_layernorm(ops, M, S, D, A, N, keep):
+    cu, em = ops
+    g = torch.Generator().manual_seed(3)
+    z = torch.nn.functional.one_hot(torch.randint(0, D, (M, S), generator=g), D).float().reshape(M, S * D)
+    act, W = rnd(M, A, seed=1), rnd(N, S * D + A, seed=2, scale=0.1)
+    gamma, beta = 1 + 0.1 * rnd(N, seed=5), 0.1 * rnd(N, seed=6)
+    WT = W.t().contiguous()
+    pre_c, out_c = torch.empty(M, N), torch.empty(M, N)
+    em.onehot_linear(z, act, WT, pre_c, S, D)
+    em.ln_act_fwd(pre_c, gamma, beta, 1e-3, 1, out_c)
+    hx = torch.zeros(M, 16 + N, device="cuda")
+    pre_g = torch.empty(M, N, device="cuda") if keep else None
+    cu.onehot_linear_ln(z.cuda(), act.cuda(), WT.cuda(), gamma.cuda(), beta.cuda(), 1e-3, hx[:, 16:], S, D, pre=pre_g)
+    close(hx[:, 16:], out_c, rtol=1e-5, atol=2e-6, what="onehot_linear_ln")
+    if keep:
+        close(pre_g, pre_c, rtol=1e-5, what="onehot_linear_ln pre")
+    assert float(hx[:, :16].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,Kin,A,unimix", [(1024, 512, 2, 0.01), (1024, 1024, 18, 0.01), (100, 64, 6, 0.0), (300, 400, 32, 0.01)])
+def test_head_sample_equals_linear_then_cat_sample(ops, M, Kin, A, unimix):
+    cu, em = ops
+    X, W, b = rnd(M, Kin, seed=1), rnd(A, Kin, seed=2, scale=Kin ** -0.5), 0.1 * rnd(A, seed=3)
+    q = torch.empty(M, A + 5).exponential_(1.0, generator=torch.Generator().manual_seed(4))[:, 2:2 + A]
+    raw_c, hot_c = torch.empty(M, A), torch.empty(M, A)
+    em.gemm(X, W, raw_c, False, True, bias=b)
+    em.cat_sample(raw_c, q, unimix, 1, A, hot_c)
+    Xg, Wg = X.cuda(), W.cuda()
+    assert cu.head_sample_supported(Xg, Wg)
+    raw_all, act_all = torch.zeros(M, A + 3, device="cuda"), torch.zeros(M, A + 3, device="cuda")
+    qg = torch.zeros(M, A + 5, device="cuda")
+    qg[:, 2:2 + A] = q.cuda()
+    cu.head_sample(Xg, Wg, b.cuda(), qg[:, 2:2 + A], unimix, raw_all[:, 3:], act_all[:, 3:])
+    close(raw_all[:, 3:], raw_c, rtol=1e-5, atol=1e-6, what="head logits")
+    assert float((act_all[:, 3:].sum(-1) - 1).abs().max()) == 0.0
+    mism = (act_all[:, 3:].cpu() != hot_c).any(-1).float().mean()
+    assert float(mism) <= 2e-3, float(mism)                   # only near-ties of p/q may differ
+    # identical to the two-launch CUDA path on the logits it wrote
+    hot2 = torch.empty(M, A, device="cuda")
+    cu.cat_sample(raw_all[:, 3:], qg[:, 2:2 + A], unimix, 1, A, hot2)
+    assert torch.equal(hot2, act_all[:, 3:])
+    assert float(raw_all[:, :3].abs().max()) == 0.0 and float(act_all[:, :3].abs().max()) == 0.0
