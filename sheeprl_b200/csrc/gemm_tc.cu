@@ -78,6 +78,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 2000000000LL) asm volatile("trap;");
   }
 }
+// one lane of a converged warp (warp-uniform choice: the same lane every time)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -269,8 +281,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tmem = s.tmem_base;
 
   if (warp == 0) {
-    // ===== TMA producer
-    if (lane == 0) {
+    // ===== TMA producer (warp-uniform loop, the elected lane issues: see the MMA issuer)
+    {
+      const bool leader = elect_one();
       int it = 0;                                  // k-blocks issued so far, across tiles: stage / phase bookkeeping
       for (int tile = blockIdx.y; tile < mtiles; tile += tstride) {
       const int m0 = tile * BM;
@@ -279,6 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int st = it % STAGES;
         if (it >= STAGES) mbar_wait(&s.empty[st], ((it / STAGES) - 1) & 1);
+        if (leader) {
         mbar_expect_tx(&s.full[st], (uint32_t)((BM + BN) * BK * sizeof(float)));
         if (geo.mode == MODE_GEMM) {
           const int k0 = (kb_base + kb) * BK;
@@ -304,34 +318,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tma_load_4d(s.a_hi[st], &mapA, &s.full[st], ch, x, y, tn0);
           tma_load_2d(s.b_hi[st], &mapB, &s.full[st], kb * BK, n0 + (geo.mode == MODE_UP ? (int)blockIdx.z * geo.Cout : 0));
         }
+        }
+        __syncwarp();
       }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single elected lane)
-    if (lane == 0) {
-      const bool b_mn = geo.b_mn != 0;
-      // A comes from tensor memory (always [row][k]): only B's major bit depends on the operand layout
-      const uint32_t idesc = IDESC | ((uint32_t)b_mn << 16);
-      const uint64_t b_step = (b_mn ? 1024 : 32) >> 4;
-      int it = 0, gc0 = 0;                         // k-blocks / TMEM chunks issued so far, across tiles
-      for (int tile = blockIdx.y; tile < mtiles; tile += tstride, gc0 += nchunks)
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int st = it % STAGES;
-        const int c = gc0 + kb / CH, buf = c & 1;
-        const bool chunk_start = (kb % CH) == 0;
-        if (chunk_start && c >= 2) {           // the accumulator warps must have drained this TMEM buffer
-          mbar_wait(&s.tempty[buf], ((c >> 1) - 1) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        mbar_wait(&s.split[st], (it / STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem + (uint32_t)(buf * BN);
-        const uint32_t bh = smem_u32(s.b_hi[st]), bl = smem_u32(s.b_lo[st]);
-        // B descriptors of the stage once; a k-step only advances the 14-bit start-address field (16-byte units):
-        // K-major by 32 B inside the 128-byte swizzle row, MN-major by 1024 B (two 4-row k atoms).  A: 8 TMEM columns.
-        const uint64_t dbh0 = b_mn ? make_desc_mn(bh) : make_desc(bh), dbl0 = b_mn ? make_desc_mn(bl) : make_desc(bl);
-        const uint32_t ta_hi = tmem + A_TMEM0 + 64u * (uint32_t)st, ta_lo = ta_hi + 32u;
+    // ===== MMA issuer.  The WHOLE warp walks the loop with warp-uniform control flow, so stage / descriptor arithmetic
+    // stays on the uniform datapath; only the tcgen05 instructions sit behind the elected lane.  (With the loop inside
+    // `if (lane == 0)` ptxas cannot prove uniformity and rebuilds every uniform operand with ELECT + R2UR.BROADCAST: 225
+    // dependent SASS instructions per k-block made this single thread the limiter of the kernel, ncu r2_gemm_tc.)
+    const bool leader = elect_one();
+    const bool b_mn = geo.b_mn != 0;
+    // A comes from tensor memory (always [row][k]): only B's major bit depends on the operand layout
+    const uint32_t idesc = IDESC | ((uint32_t)b_mn << 16);
+    const uint64_t b_step = (b_mn ? 1024 : 32) >> 4;
+    // B descriptors of stage 0; a stage advances the 14-bit start-address field (16-byte units) by the buffer size, a
+    // k-step by 32 B inside the 128-byte swizzle row (K-major) or by 1024 B = two 4-row k atoms (MN-major)
+    const uint64_t dbh_base = b_mn ? make_desc_mn(smem_u32(s.b_hi[0])) : make_desc(smem_u32(s.b_hi[0]));
+    const uint64_t dbl_base = b_mn ? make_desc_mn(smem_u32(s.b_lo[0])) : make_desc(smem_u32(s.b_lo[0]));
+    constexpr uint64_t STAGE_STEP = (uint64_t)(BN * BK * sizeof(float)) >> 4;
+    int it = 0, gc0 = 0;                         // k-blocks / TMEM chunks issued so far, across tiles
+    for (int tile = blockIdx.y; tile < mtiles; tile += tstride, gc0 += nchunks)
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const int st = it % STAGES;
+      const int c = gc0 + kb / CH, buf = c & 1;
+      const bool chunk_start = (kb % CH) == 0;
+      if (chunk_start && c >= 2)             // the accumulator warps must have drained this TMEM buffer
+        mbar_wait(&s.tempty[buf], ((c >> 1) - 1) & 1);
+      mbar_wait(&s.split[st], (it / STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem + (uint32_t)(buf * BN);
+      const uint64_t dbh0 = dbh_base + (uint64_t)st * STAGE_STEP, dbl0 = dbl_base + (uint64_t)st * STAGE_STEP;
+      const uint32_t ta_hi = tmem + A_TMEM0 + 64u * (uint32_t)st, ta_lo = ta_hi + 32u;
+      if (leader) {
 #pragma unroll
         for (int k4 = 0; k4 < BK / 8; ++k4) {
           const uint64_t ob = (uint64_t)k4 * b_step;
@@ -347,6 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         umma_commit(&s.empty[st]);   // stage reusable once these MMAs have read it
         if ((kb % CH) == CH - 1 || kb == nkb - 1) umma_commit(&s.tfull[buf]);   // chunk complete
       }
+      __syncwarp();
     }
   } else if (warp >= SPLIT_WARP0 && warp < ACC_WARP0) {
     // ===== splitters: hi/lo decomposition of each landed stage (layout-agnostic, in place)

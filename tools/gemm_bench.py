@@ -1,0 +1,53 @@
+"""Times gemm_tc_kernel alone on the step's main product shapes (CUDA events, L2-sized operands rotate through 4 buffers).
+
+    python tools/gemm_bench.py [--json out.json]
+"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sheeprl_b200.lib import CudaOps
+
+SHAPES = [  # M, N, K, transA, transB  (C[M,N] = op(A) op(B))
+    (16384, 512, 1536, False, True), (16384, 512, 512, False, True), (1024, 1536, 1024, False, True),
+    (1024, 512, 512, False, True), (15360, 1536, 512, False, False), (512, 1536, 15360, True, False),
+    (4096, 12288, 5120, False, True), (65536, 1024, 5120, False, True), (65536, 1024, 1024, False, True),
+    (64, 12288, 4096, False, True),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--reps", type=int, default=20)
+    a = ap.parse_args()
+    cu = CudaOps("cuda")
+    out = []
+    for prec in ("highest", "high"):
+        cu.set_matmul_precision(prec)
+        for M, N, K, tA, tB in SHAPES:
+            nbuf = 4
+            As = [torch.randn((K, M) if tA else (M, K), device="cuda") for _ in range(nbuf)]
+            Bs = [torch.randn((N, K) if tB else (K, N), device="cuda") for _ in range(nbuf)]
+            C = torch.empty(M, N, device="cuda")
+            for i in range(3):
+                cu.gemm(As[i % nbuf], Bs[i % nbuf], C, tA, tB)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(a.reps):
+                cu.gemm(As[i % nbuf], Bs[i % nbuf], C, tA, tB)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / a.reps
+            tf = 2.0 * M * N * K / us / 1e6
+            out.append({"precision": prec, "M": M, "N": N, "K": K, "transA": tA, "transB": tB, "us": round(us, 2),
+                        "tflops_fp32_equiv": round(tf, 1)})
+            print(f"{prec:8s} M{M} N{N} K{K} {'T' if tA else 'N'}{'T' if tB else 'N'}: {us:9.1f} us  {tf:7.1f} TF/s", flush=True)
+            del As, Bs, C
+    cu.set_matmul_precision("highest")
+    if a.json:
+        json.dump(out, open(a.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
