@@ -209,6 +209,7 @@ struct Smem {
 constexpr int CH = 4;
 
 constexpr int MODE_GEMM = 0, MODE_DOWN = 1, MODE_UP = 2;
+constexpr int GROUP_M = 16;
 struct TileGeo {
   int mode;
   int h, w, NB;            // small-image grid (conv modes)
@@ -223,7 +224,10 @@ struct TileGeo {
   int passes;              // 3: x = hi + lo split, three TF32 products per k-step (fp32-accurate); 1: one TF32 product
                            // (torch's float32_matmul_precision "high", the reference's default on GPUs)
   int a_mn, b_mn;          // GEMM mode: operand stored [K][M] / [K][N] (MN-major) instead of [M][K] / [N][K]
-  int mtiles;              // number of M tiles; a CTA walks tiles blockIdx.y, blockIdx.y + gridDim.y, ... (persistent)
+  int mtiles;              // number of M tiles
+  int ntiles;              // number of N tiles.  A CTA walks the flattened (m, n) tile list blockIdx.y, blockIdx.y +
+                           // gridDim.y, ... (persistent); consecutive ids cover GROUP_M m-tiles x all n-tiles column by
+                           // column, so the ~148 tiles in flight share few operand panels in L2
   int wg;                  // GEMM mode, conv weight gradient: A rows = (tap, big channel), K = small-grid pixels gathered
                            // from the channel-last big image by 4-D TMA boxes of 32 pixels (Cout = big channels)
 };
@@ -235,8 +239,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Smem<BN>& s = *reinterpret_cast<Smem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int mtiles = geo.mtiles, tstride = gridDim.y;
+  const int mtiles = geo.mtiles * geo.ntiles, tstride = gridDim.y;   // flattened tile count
+  auto tile_mn = [&](int id, int& tm, int& tn) {
+    if (geo.ntiles == 1) { tm = id; tn = 0; return; }
+    const int per = GROUP_M * geo.ntiles, grp = id / per, first = grp * GROUP_M;
+    const int gsz = min(GROUP_M, geo.mtiles - first), r = id - grp * per;
+    tn = r / gsz;
+    tm = first + (r - tn * gsz);
+  };
   // split-K (GEMM mode): blockIdx.z owns k-blocks [kb_base, kb_base + nkb); its partial tile goes to the workspace and
   // the LAST split to arrive for an output tile sums all partials in split order (bit-reproducible, no atomics on C)
   int kb_base = 0, nkb = (K + BK - 1) / BK;
@@ -286,9 +296,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const bool leader = elect_one();
       int it = 0;                                  // k-blocks issued so far, across tiles: stage / phase bookkeeping
       for (int tile = blockIdx.y; tile < mtiles; tile += tstride) {
-      const int m0 = tile * BM;
+      int tm, tn;
+      tile_mn(tile, tm, tn);
+      const int m0 = tm * BM, n0 = tn * BN;
       int tx0 = 0, ty0 = 0, tn0 = 0;
-      if (geo.mode != MODE_GEMM) tile_origin(tile, tx0, ty0, tn0);
+      if (geo.mode != MODE_GEMM) tile_origin(tm, tx0, ty0, tn0);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int st = it % STAGES;
         if (it >= STAGES) mbar_wait(&s.empty[st], ((it / STAGES) - 1) & 1);
@@ -439,9 +451,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int q = warp & 3, half = (warp - ACC_WARP0) >> 2;
     int gc0 = 0;
     for (int tile = blockIdx.y; tile < mtiles; tile += tstride, gc0 += nchunks) {
-    const int m0 = tile * BM;
+    int tm, tn;
+    tile_mn(tile, tm, tn);
+    const int m0 = tm * BM, n0 = tn * BN;
     int tx0 = 0, ty0 = 0, tn0 = 0;
-    if (geo.mode != MODE_GEMM) tile_origin(tile, tx0, ty0, tn0);
+    if (geo.mode != MODE_GEMM) tile_origin(tm, tx0, ty0, tn0);
     float acc[ACC_COLS];
 #pragma unroll
     for (int j = 0; j < ACC_COLS; ++j) acc[j] = 0.f;
@@ -634,12 +648,12 @@ bool conv_tile(int h, int w, int NB, int* bw, int* bh, int* bn) {
 // TMEM allocation, barrier setup, pipeline fill and an un-overlapped epilogue per tile.  When there are more than two
 // waves of tiles, launch about one CTA per SM and let each walk its M tiles (the epilogue of a tile overlaps the main
 // loop of the next through the double-buffered TMEM accumulator).
-static unsigned persistent_grid_y(int mtiles, unsigned gx, unsigned gz) {
-  const long long total = (long long)mtiles * gx * gz;
-  if (total <= 2LL * kNumSMs) return (unsigned)mtiles;
-  unsigned gy = kNumSMs / (gx * gz);
+static unsigned persistent_grid_y(int tiles, unsigned gz) {
+  const long long total = (long long)tiles * gz;
+  if (total <= 2LL * kNumSMs) return (unsigned)tiles;
+  unsigned gy = kNumSMs / gz;
   if (gy < 1) gy = 1;
-  return gy < (unsigned)mtiles ? gy : (unsigned)mtiles;
+  return gy < (unsigned)tiles ? gy : (unsigned)tiles;
 }
 
 __global__ void conv_pack_down_kernel(const float* __restrict__ W, float* __restrict__ P, int Cs, int Cb) {
@@ -766,8 +780,9 @@ int launch_conv(int mode, const float* img, const float* Wp, float* out, const f
   if (int rc = get_map(Wp, brows, K, K, BN, &mb)) return rc;
   const int mtiles = g.tiles_x * g.tiles_y * (NB / g.bn);
   g.mtiles = mtiles;
-  dim3 grid((Cout + BN - 1) / BN, 1, mode == MODE_UP ? 4 : 1);
-  grid.y = persistent_grid_y(mtiles, grid.x, grid.z);
+  g.ntiles = (Cout + BN - 1) / BN;
+  dim3 grid(1, 1, mode == MODE_UP ? 4 : 1);
+  grid.y = persistent_grid_y(mtiles * g.ntiles, grid.z);
   const int M = NB * h * w;  // unused by conv addressing; row validity comes from geo
   DISPATCH_GEMM_TC(BN, g.passes, grid, st, ma, mb, out, bias, M, Cout, K, Cout, 0, g);
   RL_CHECK_LAUNCH();
@@ -875,7 +890,9 @@ int gemm_tc_impl(const float* A, const float* B, float* C, const float* bias, in
     if (fused) { g.force_part = 1; *fused = FusedTail{g.part, g.ksplits, g.mpad, g.ldw}; }
   }
   g.mtiles = (int)grid.y;
-  grid.y = persistent_grid_y(g.mtiles, grid.x, grid.z);
+  g.ntiles = (int)grid.x;
+  grid.x = 1;
+  grid.y = persistent_grid_y(g.mtiles * g.ntiles, grid.z);
   DISPATCH_GEMM_TC(BN, g.passes, grid, st, ma, mb, C, bias, M, N, K, ldc, accumulate, g);
   RL_CHECK_LAUNCH();
   if (g.ksplits > 1 && !fused) {
@@ -1045,11 +1062,14 @@ extern "C" int b200rl_conv_wgrad_mn(const float* small_, const float* big, float
   g.ksplits = (nkb + per - 1) / per;
   grid.z = g.ksplits;
   g.mtiles = (int)grid.y;
+  g.ntiles = (int)grid.x;
   if (g.ksplits > 1) {
     g.mpad = (int)grid.y * BM;
     g.ldw = (int)grid.x * BN;
     if (int rc = split_workspace((size_t)g.ksplits * g.mpad * g.ldw, st, &g.part)) return rc;
   }
+  grid.x = 1;
+  grid.y = (unsigned)(g.mtiles * g.ntiles);
   DISPATCH_GEMM_TC(BN, g.passes, grid, st, ma, mb, G, nullptr, M, N, P, N, 0, g);
   RL_CHECK_LAUNCH();
   if (g.ksplits > 1) {
