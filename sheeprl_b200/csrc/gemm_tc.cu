@@ -41,9 +41,14 @@
 namespace {
 
 constexpr int BM = 128, BK = 32, STAGES = 4;   // 4 x 48 KB operand stages; TMEM: 2 accumulators + 4 x (A hi | lo) = 512 columns
-constexpr int NTHREADS = 512;                       // 16 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 split, 8-15 accumulate
+// 18 warps: 0 TMA, 1 MMA, 4-7 split A (-> TMEM), 8-15 accumulate, {2, 3, 16, 17} split B (-> shared memory; warp 2 also
+// owns the TMEM allocation).  A and B of a stage are split concurrently by different warps: the hi/lo split is a chain
+// of dependent latencies (barrier -> LDS -> ALU -> tcgen05.st / STS -> fence), the longest stage of the pipeline for the
+// convolutions' narrow N tiles.
+constexpr int NTHREADS = 576;
 constexpr int SPLIT_WARP0 = 4, NSPLIT_THREADS = 128;
 constexpr int ACC_WARP0 = 8, NACC_WARPS = 8;
+constexpr int BSPLIT_WARP_HI = 16;                  // B splitters: warps 2, 3, 16, 17
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -164,6 +169,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major operand tile [rows][32 fp32] with 128B swizzle: 8-row groups are 1024 B apart (SBO), one atom along K.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -275,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&s.full[i], 1);
-      mbar_init(&s.split[i], NSPLIT_THREADS / 32);
+      mbar_init(&s.split[i], (PASSES == 3 ? 2 : 1) * (NSPLIT_THREADS / 32));
       mbar_init(&s.empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -382,7 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       __syncwarp();
     }
   } else if (warp >= SPLIT_WARP0 && warp < ACC_WARP0) {
-    // ===== splitters: hi/lo decomposition of each landed stage (layout-agnostic, in place)
+    // ===== A splitters: hi/lo decomposition of each landed A tile into tensor memory
     const int t = threadIdx.x - SPLIT_WARP0 * 32;
     const bool a_mn_tile = geo.a_mn != 0;          // GEMM with transposed A, or the conv weight gradient
     int ntl = 0;
@@ -391,58 +407,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int kb = 0; kb < total_kb; ++kb) {
       const int st = kb % STAGES;
       mbar_wait(&s.full[st], (kb / STAGES) & 1);
-      {
-        // A: thread t owns tile row t = TMEM lane t (splitter warp w reads/writes lanes [32w, 32w+32)).  It gathers the
-        // row's 32 k values from the swizzled tile, stores them (the raw bits are the hi operand: the datapath truncates)
-        // and lo = x - trunc(x) into this stage's TMEM columns.
-        const char* base = reinterpret_cast<const char*>(s.a_hi[st]);
-        uint32_t hi[32], lo[32];
-        if (!a_mn_tile) {
-          // K-major tile: row t = 128 B, 16-byte chunk c stored at position c ^ (t & 7)
-          const char* row = base + t * 128;
+      // thread t owns tile row t = TMEM lane t (splitter warp w reads/writes lanes [32w, 32w+32)).  It gathers the
+      // row's 32 k values from the swizzled tile, stores them (the raw bits are the hi operand: the datapath truncates)
+      // and lo = x - trunc(x) into this stage's TMEM columns.
+      const char* base = reinterpret_cast<const char*>(s.a_hi[st]);
+      uint32_t hi[32], lo[32];
+      if (!a_mn_tile) {
+        // K-major tile: row t = 128 B, 16-byte chunk c stored at position c ^ (t & 7)
+        const char* row = base + t * 128;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ (t & 7)) << 4));
-            hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
-            hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
-          }
-        } else {
-          // MN-major tile: block t/32 (4 KB), k-row k = 128 B, element t%32 inside it with the 32-byte chunk index
-          // XOR-ed by k % 4 (SWIZZLE_128B_BASE32B)
-          const char* blk = base + (t >> 5) * 4096 + ((t & 7) << 2);
-          const int ch = (t & 31) >> 3;
-#pragma unroll
-          for (int k = 0; k < 32; ++k)
-            hi[k] = *reinterpret_cast<const uint32_t*>(blk + k * 128 + ((ch ^ (k & 3)) << 5));
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ (t & 7)) << 4));
+          hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+          hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
         }
-        const uint32_t ta = tmem + (((uint32_t)(t & ~31)) << 16) + A_TMEM0 + 64u * (uint32_t)st;
-        tmem_st32(ta, hi);
-        if (PASSES == 3) {
+      } else {
+        // MN-major tile: block t/32 (4 KB), k-row k = 128 B, element t%32 inside it with the 32-byte chunk index
+        // XOR-ed by k % 4 (SWIZZLE_128B_BASE32B)
+        const char* blk = base + (t >> 5) * 4096 + ((t & 7) << 2);
+        const int ch = (t & 31) >> 3;
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const float x = __uint_as_float(hi[k]);
-            lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
-          }
-          tmem_st32(ta + 32u, lo);    // completion is awaited after the B tile has been split (overlaps the two)
-        }
+        for (int k = 0; k < 32; ++k)
+          hi[k] = *reinterpret_cast<const uint32_t*>(blk + k * 128 + ((ch ^ (k & 3)) << 5));
       }
-      float4* bh = reinterpret_cast<float4*>(s.b_hi[st]);
+      const uint32_t ta = tmem + (((uint32_t)(t & ~31)) << 16) + A_TMEM0 + 64u * (uint32_t)st;
+      tmem_st32(ta, hi);
+      if (PASSES == 3) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float x = __uint_as_float(hi[k]);
+          lo[k] = __float_as_uint(x - __uint_as_float(hi[k] & 0xffffe000u));
+        }
+        tmem_st32(ta + 32u, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // the A halves have landed in TMEM
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM stores ordered before the arrival
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.split[st]);
+    }
+  } else if (PASSES == 3 && (warp == 2 || warp == 3 || warp >= BSPLIT_WARP_HI)) {
+    // ===== B splitters: lo = x - trunc(x) of each landed B tile to the twin buffer (same swizzled offsets, so the split
+    // is layout-agnostic); the raw tile itself is the hi operand
+    const int t = (warp >= BSPLIT_WARP_HI ? warp - BSPLIT_WARP_HI + 2 : warp - 2) * 32 + lane;
+    int ntl = 0;
+    for (int tile = blockIdx.y; tile < mtiles; tile += tstride) ++ntl;
+    const int total_kb = ntl * nkb;
+    for (int kb = 0; kb < total_kb; ++kb) {
+      const int st = kb % STAGES;
+      mbar_wait(&s.full[st], (kb / STAGES) & 1);
+      const float4* bh = reinterpret_cast<const float4*>(s.b_hi[st]);
       float4* bl = reinterpret_cast<float4*>(s.b_lo[st]);
-      if (PASSES == 3)
 #pragma unroll
       for (int i = 0; i < BN * BK / 4 / NSPLIT_THREADS; ++i) {
         const int idx = t + i * NSPLIT_THREADS;
         const float4 v = bh[idx];
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
         bl[idx] = l;
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // the A halves have landed in TMEM
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM stores ordered before the arrival
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.split[st]);
     }
@@ -464,11 +490,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&s.tfull[buf], (c >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int c0 = 0; c0 < ACC_COLS; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * ACC_COLS + c0), r);
+      for (int c0 = 0; c0 < ACC_COLS; c0 += 16) {   // 16 columns at a time: 96 registers per thread (576 threads)
+        uint32_t r[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * ACC_COLS + c0), r);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
