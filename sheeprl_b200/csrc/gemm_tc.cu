@@ -472,7 +472,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.split[st]);
     }
-  } else if (warp >= ACC_WARP0) {
+  } else if (warp >= ACC_WARP0 && warp < ACC_WARP0 + NACC_WARPS) {
     // ===== accumulators + epilogue.  Warp (q, half): TMEM lanes [32q, 32q+32), columns [half*BN/2, +BN/2).
     const int q = warp & 3, half = (warp - ACC_WARP0) >> 2;
     int gc0 = 0;
