@@ -545,6 +545,8 @@ extern "C" int b200rl_transpose2d(const float* X, float* Y, int rows, int cols, 
 // thin-channel specialisations (conv_thin.cu)
 bool b200rl_thin_up_supported(int Cs, int Cb);
 bool b200rl_thin_wgrad_supported(int Cs, int Cb);
+bool b200rl_thin_down_supported(int w, int Cs, int Cb);
+int b200rl_conv_down_thin(const float* big, const float* W, float* small, int NB, int h, int w, int Cs, int Cb, cudaStream_t st);
 int b200rl_conv_up_thin(const float* small, const float* W, float* big, const float* bias, int NB, int h, int w, int Cs,
                         int Cb, cudaStream_t st);
 int b200rl_conv_wgrad_thin(const float* small, const float* big, float* dW, int NB, int h, int w, int Cs, int Cb,
@@ -554,6 +556,7 @@ extern "C" int b200rl_conv_down(const float* big, const float* W, float* small, 
                                 cudaStream_t st) {
   RL_CHECK_ARG(big && W && small, "null pointer");
   RL_CHECK_ARG(NB > 0 && h > 0 && w > 0 && Cs > 0 && Cb > 0, "bad dims");
+  if (b200rl_thin_down_supported(w, Cs, Cb)) return b200rl_conv_down_thin(big, W, small, NB, h, w, Cs, Cb, st);
   const long long Mtot = (long long)NB * h * w;
   const int gm = ceil_div(Mtot, 128);
   if (Cs <= 32)

@@ -213,14 +213,246 @@ conv_wgrad_thin_kernel(const float* __restrict__ small, const float* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed-FMA (FFMA2, fma.rn.f32x2) versions for 32-wide small grids (the 64x64 images of Dreamer-V3): one warp per pair of
+// small-grid rows, lane = column.  The generic kernels above issue ~4 instructions per FMA (ncu r2_thin_convs: IPC 3.2 of
+// 4 with the FMA pipe 43 % busy — issue bound); here every weight LDS.128 (warp-uniform, one wavefront) feeds 4-8 packed
+// FMAs and the image rows are staged once per warp in shared memory in a conflict-free layout.
+// ---------------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ void fma2(u64& acc, u64 x, u64 w) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(x), "l"(w)); }
+__device__ __forceinline__ u64 dup2(float x) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "r"(__float_as_uint(x)));
+  return r;
+}
+__device__ __forceinline__ float lo32(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+// down_thin: Conv2d(3 -> CS, k4 s2 p1) on [NB][2h][64][3] -> [NB][h][32][CS]  (CNNEncoder first layer, agent.py:78-91; also
+// the input-gradient pass of the decoder's last ConvTranspose2d).  Lane x of a warp owns output pixels (y, x) and (y+1, x):
+// per patch element k = (ky, kx, cb) two staged inputs and 8 weight LDS.128 feed 32 packed FMAs (32 channels x 2 pixels).
+// Staged rows: [6 rows][3 ch][column parity][33] so that lane x reads column 2x-1+kx at slot x + (kx >> 1) of plane kx & 1.
+constexpr int DT_PLANE = 33, DT_ROWF = 3 * 2 * DT_PLANE, DT_STAGE = 6 * DT_ROWF;
+template <int CS>
+__global__ void __launch_bounds__(128)
+conv_down_thin_kernel(const float* __restrict__ big, const float* __restrict__ W, float* __restrict__ small_, int NB, int h) {
+  extern __shared__ __align__(16) float sm[];
+  float* Wk = sm;                                  // [48][CS], k = (ky*4+kx)*3 + cb
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* stg = sm + 48 * CS + warp * DT_STAGE;
+  for (int e = threadIdx.x; e < CS * 48; e += blockDim.x) {
+    const int cs = e / 48, rem = e - cs * 48, cb = rem >> 4, tap = rem & 15;    // W[cs][cb][ky][kx]
+    Wk[(tap * 3 + cb) * CS + cs] = W[e];
+  }
+  __syncthreads();
+  const int Hb = 2 * h, pairs = (h + 1) >> 1;
+  const long long units = (long long)NB * pairs;
+  for (long long u = (long long)blockIdx.x * 4 + warp; u < units; u += (long long)gridDim.x * 4) {
+    const long long n = u / pairs;
+    const int y0 = (int)(u - n * pairs) * 2;
+    __syncwarp();
+    // stage big rows 2*y0-1 .. 2*y0+4 (zero outside the image), 48 float4 per row
+    for (int idx = lane; idx < 6 * 48; idx += 32) {
+      const int r = idx / 48, f4 = idx - r * 48, iy = 2 * y0 - 1 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < Hb) v = __ldg(reinterpret_cast<const float4*>(big + ((n * Hb + iy) * 64) * 3) + f4);
+      const float vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = f4 * 4 + j, col = e / 3, ch = e - col * 3, pc = col + 1;
+        stg[r * DT_ROWF + (ch * 2 + (pc & 1)) * DT_PLANE + (pc >> 1)] = vs[j];
+      }
+    }
+    if (lane < 18) {                                 // the two padding columns (-1 and 64) of every (row, channel)
+      const int r = lane / 3, ch = lane - r * 3;
+      stg[r * DT_ROWF + (ch * 2 + 0) * DT_PLANE + 0] = 0.f;
+      stg[r * DT_ROWF + (ch * 2 + 1) * DT_PLANE + 32] = 0.f;
+    }
+    __syncwarp();
+    const bool two = y0 + 1 < h;
+#pragma unroll 1
+    for (int c0 = 0; c0 < CS; c0 += 32) {
+      u64 acc0[16], acc1[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { acc0[q] = 0ull; acc1[q] = 0ull; }
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            const int off = (cb * 2 + (kx & 1)) * DT_PLANE + lane + (kx >> 1);
+            const u64 x0 = dup2(stg[ky * DT_ROWF + off]), x1 = dup2(stg[(ky + 2) * DT_ROWF + off]);
+            const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(Wk + ((ky * 4 + kx) * 3 + cb) * CS + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const ulonglong2 wv = wp[q];
+              fma2(acc0[2 * q], x0, wv.x); fma2(acc0[2 * q + 1], x0, wv.y);
+              fma2(acc1[2 * q], x1, wv.x); fma2(acc1[2 * q + 1], x1, wv.y);
+            }
+          }
+      float4* o0 = reinterpret_cast<float4*>(small_ + ((n * h + y0) * 32 + lane) * (long long)CS + c0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o0[q] = make_float4(lo32(acc0[2 * q]), hi32(acc0[2 * q]), lo32(acc0[2 * q + 1]), hi32(acc0[2 * q + 1]));
+      if (two) {
+        float4* o1 = reinterpret_cast<float4*>(small_ + ((n * h + y0 + 1) * 32 + lane) * (long long)CS + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o1[q] = make_float4(lo32(acc1[2 * q]), hi32(acc1[2 * q]), lo32(acc1[2 * q + 1]), hi32(acc1[2 * q + 1]));
+      }
+    }
+  }
+}
+
+// up_thin2: ConvTranspose2d(CS -> 3, k4 s2 p1) on [NB][h][32][CS] -> [NB][2h][64][3] (CNNDecoder last layer, agent.py:199-222).
+// Lane j owns small-grid positions (i, j) and (i+1, j), i.e. 2 x (2x2x3) outputs.  Packed FMAs pair EVEN/ODD input channels
+// (both operands are natural 64-bit pairs of the channel-last layouts, no duplication moves); the two partial sums of an
+// output are added at the end.  Per neighbour column dx the four staged rows are loaded once (4 LDS.128) and every weight
+// LDS.128 (4 channels of one (dy, dx, a, b, c) combination, warp-uniform) feeds 4 packed FMAs.
+// Output (2i+a) takes small rows i+dy with kernel row ky = a - 2dy + 1 (dy=-1: a=0, ky=3; dy=0: ky=a+1; dy=+1: a=1, ky=0).
+// A CTA (4 warps) owns 8 consecutive small rows and stages the 10 rows they touch once: [10][34 positions][32 ch + 4 pad].
+constexpr int UT_POS = 34, UT_CH = 36, UT_ROWS = 10, UT_STAGE = UT_ROWS * UT_POS * UT_CH;
+template <int CS>
+__global__ void __launch_bounds__(128)
+conv_up_thin2_kernel(const float* __restrict__ small_, const float* __restrict__ W, const float* __restrict__ bias,
+                     float* __restrict__ big, int NB, int h) {
+  extern __shared__ __align__(16) float sm[];
+  float* Wn = sm;                                  // [3 dy][3 dx][2 a][2 b][3 c][CS] (unused (a, b) slots stay zero)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* stg = sm + 108 * CS;
+  for (int e = threadIdx.x; e < 108 * CS; e += blockDim.x) Wn[e] = 0.f;
+  __syncthreads();
+  for (int e = threadIdx.x; e < CS * 48; e += blockDim.x) {
+    const int cs = e / 48, rem = e - cs * 48, c = rem >> 4, ky = (rem >> 2) & 3, kx = rem & 3;   // W[cs][c][ky][kx]
+    const int dy = (ky == 3) ? -1 : ((ky == 0) ? 1 : 0), a = (ky == 2 || ky == 0) ? 1 : 0;
+    const int dx = (kx == 3) ? -1 : ((kx == 0) ? 1 : 0), b = (kx == 2 || kx == 0) ? 1 : 0;
+    Wn[(((((dy + 1) * 3 + (dx + 1)) * 2 + a) * 2 + b) * 3 + c) * CS + cs] = W[e];
+  }
+  __syncthreads();
+  const int octs = (h + 7) >> 3, Hb = 2 * h;
+  const long long units = (long long)NB * octs;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const long long n = u / octs;
+    const int ib = (int)(u - n * octs) * 8, i0 = ib + 2 * warp;
+    u64 acc[2][2][2][3];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[p][a][b][c] = 0ull;
+#pragma unroll 1
+    for (int c0 = 0; c0 < CS; c0 += 32) {
+      __syncthreads();
+      // stage small rows ib-1 .. ib+8, 32 channels [c0, c0+32): 8 float4 per position
+      for (int idx = threadIdx.x; idx < UT_ROWS * 32 * 8; idx += blockDim.x) {
+        const int r = idx >> 8, pos = (idx >> 3) & 31, f4 = idx & 7, iy = ib - 1 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < h) v = __ldg(reinterpret_cast<const float4*>(small_ + ((n * h + iy) * 32 + pos) * (long long)CS + c0) + f4);
+        *reinterpret_cast<float4*>(stg + (r * UT_POS + pos + 1) * UT_CH + f4 * 4) = v;
+      }
+      for (int idx = threadIdx.x; idx < UT_ROWS * 2 * 8; idx += blockDim.x) {      // zero the border positions -1 and 32
+        const int r = idx >> 4, side = (idx >> 3) & 1, f4 = idx & 7;
+        *reinterpret_cast<float4*>(stg + (r * UT_POS + side * 33) * UT_CH + f4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
+      const float* wst = stg + 2 * warp * UT_POS * UT_CH;     // this warp's rows i0-1 .. i0+2
+#pragma unroll 1
+      for (int cq = 0; cq < 8; ++cq) {                   // 4 channels per step
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          ulonglong2 x[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            x[r] = *reinterpret_cast<const ulonglong2*>(wst + (r * UT_POS + lane + 1 + dx) * UT_CH + cq * 4);
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int a = (dy == 1 ? 1 : 0); a <= (dy == -1 ? 0 : 1); ++a)
+#pragma unroll
+              for (int b = (dx == 1 ? 1 : 0); b <= (dx == -1 ? 0 : 1); ++b)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(
+                      Wn + (((((dy + 1) * 3 + (dx + 1)) * 2 + a) * 2 + b) * 3 + c) * CS + c0 + cq * 4);
+                  fma2(acc[0][a][b][c], x[dy + 1].x, wv.x); fma2(acc[0][a][b][c], x[dy + 1].y, wv.y);
+                  fma2(acc[1][a][b][c], x[dy + 2].x, wv.x); fma2(acc[1][a][b][c], x[dy + 2].y, wv.y);
+                }
+        }
+      }
+    }
+    float bv[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bv[c] = bias ? bias[c] : 0.f;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (i0 + p >= h) break;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        float2* dst = reinterpret_cast<float2*>(big + ((n * Hb + 2 * (i0 + p) + a) * 64 + 2 * lane) * 3LL);   // 6 floats
+        float o[6];
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) o[b * 3 + c] = lo32(acc[p][a][b][c]) + hi32(acc[p][a][b][c]) + bv[c];
+        dst[0] = make_float2(o[0], o[1]); dst[1] = make_float2(o[2], o[3]); dst[2] = make_float2(o[4], o[5]);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // internal entry points used by conv.cu's dispatchers
 bool b200rl_thin_up_supported(int Cs, int Cb) { return Cb == 3 && (Cs == 32 || Cs == 48 || Cs == 64 || Cs == 96); }
 bool b200rl_thin_wgrad_supported(int Cs, int Cb) { return Cb >= 1 && Cb <= 4 && Cs % 32 == 0 && Cs <= 128; }
 
+bool b200rl_thin_down_supported(int w, int Cs, int Cb) { return Cb == 3 && w == 32 && (Cs == 32 || Cs == 64 || Cs == 96); }
+
+int b200rl_conv_down_thin(const float* big, const float* W, float* small, int NB, int h, int w, int Cs, int Cb, cudaStream_t st) {
+  (void)w; (void)Cb;
+  const long long units = (long long)NB * ((h + 1) / 2);
+  long long blocks = (units + 3) / 4;
+  if (blocks > 4LL * kNumSMs) blocks = 4LL * kNumSMs;
+  const size_t smem = sizeof(float) * (48 * Cs + 4 * DT_STAGE);
+#define DOWN_THIN(CS_)                                                                                               \
+  do {                                                                                                               \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      RL_CUDA(cudaFuncSetAttribute(conv_down_thin_kernel<CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    conv_down_thin_kernel<CS_><<<(unsigned)blocks, 128, smem, st>>>(big, W, small, NB, h);                         \
+  } while (0)
+  if (Cs == 32) DOWN_THIN(32); else if (Cs == 64) DOWN_THIN(64); else DOWN_THIN(96);
+#undef DOWN_THIN
+  RL_CHECK_LAUNCH();
+  return B200RL_OK;
+}
+
 int b200rl_conv_up_thin(const float* small, const float* W, float* big, const float* bias, int NB, int h, int w, int Cs,
                         int Cb, cudaStream_t st) {
+  if (w == 32 && (Cs == 32 || Cs == 64 || Cs == 96)) {
+    const long long units = (long long)NB * ((h + 7) / 8);
+    long long blocks = units < 3LL * kNumSMs ? units : 3LL * kNumSMs;
+    const size_t smem = sizeof(float) * (108 * Cs + UT_STAGE);
+#define UP_THIN2(CS_)                                                                                                \
+  do {                                                                                                               \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      RL_CUDA(cudaFuncSetAttribute(conv_up_thin2_kernel<CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    conv_up_thin2_kernel<CS_><<<(unsigned)blocks, 128, smem, st>>>(small, W, bias, big, NB, h);                    \
+  } while (0)
+    if (Cs == 32) UP_THIN2(32); else if (Cs == 64) UP_THIN2(64); else UP_THIN2(96);
+#undef UP_THIN2
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
   const long long total = (long long)NB * h * w;
   long long blocks = (total + 127) / 128;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;

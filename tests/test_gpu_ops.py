@@ -238,6 +238,8 @@ CONV_SHAPES = [(3, 8, 8, 16, 8), (2, 4, 4, 32, 16), (5, 16, 16, 4, 3), (2, 32, 3
                (2, 4, 4, 130, 72), (1, 8, 8, 8, 2),
                # thin big-image side (conv_thin.cu): partial / multiple 32-pixel row tiles, every channel-group count
                (3, 16, 16, 64, 3), (2, 40, 40, 96, 3), (1, 32, 32, 48, 3), (2, 8, 8, 32, 1), (2, 8, 8, 64, 4),
+               # 32-wide small grids take the packed-FMA kernels: odd / non-multiple-of-8 heights, every channel count
+               (3, 32, 32, 64, 3), (2, 32, 32, 96, 3), (2, 5, 32, 32, 3), (1, 12, 32, 64, 3), (5, 1, 32, 96, 3),
                # tensor-core implicit-GEMM eligible (gathered image has a multiple of 32 channels, grid tiles by 128 px)
                (8, 4, 4, 64, 32), (2, 32, 32, 32, 64), (4, 16, 16, 128, 64), (16, 8, 8, 256, 128), (24, 4, 4, 96, 32),
                # weight gradient with operands read in place (MN-major tcgen05): k-block = part of a row / rows / images
