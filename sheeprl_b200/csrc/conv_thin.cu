@@ -404,6 +404,71 @@ conv_up_thin2_kernel(const float* __restrict__ small_, const float* __restrict__
   }
 }
 
+
+// wgrad_thin2: dW[cs][cb][ky][kx] += sum over small pixels of small[p][cs] * big[patch(p)][ky][kx][cb] for 3-channel big images
+// and 32-wide small grids (weight gradient of the encoder's first Conv2d / the decoder's last ConvTranspose2d).  One warp per
+// small row, lane = small channel (blockIdx.y = 32-channel group): the 32 pixels' patches are materialised in shared memory
+// as [pixel][48] (k = (ky*4+kx)*3 + cb, 16-byte aligned), so per pixel 12 warp-uniform LDS.128 + 1 LDS feed 24 packed FMAs
+// on 48 register accumulators (the kernel above needs 24 LDS.64 + 48 FFMA).  One shared-memory + global atomic flush per CTA.
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+conv_wgrad_thin2_kernel(const float* __restrict__ small_, const float* __restrict__ big, float* __restrict__ dW, int NB, int h,
+                        int Cs) {
+  __shared__ __align__(16) float P[NWARPS][32 * 48];
+  __shared__ __align__(16) float S[NWARPS][32 * 32];
+  __shared__ float Red[48 * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = blockIdx.y;
+  const int Hb = 2 * h;
+  for (int e = threadIdx.x; e < 48 * 32; e += blockDim.x) Red[e] = 0.f;
+  __syncthreads();
+  u64 acc[24];
+#pragma unroll
+  for (int q = 0; q < 24; ++q) acc[q] = 0ull;
+  const long long rows = (long long)NB * h;
+  for (long long u = (long long)blockIdx.x * NWARPS + warp; u < rows; u += (long long)gridDim.x * NWARPS) {
+    const long long n = u / h;
+    const int y = (int)(u - n * h);
+    __syncwarp();
+    // patches: element e = pixel * 48 + ky * 12 + (kx * 3 + cb); the 12 floats of a patch row are contiguous in the image
+#pragma unroll 4
+    for (int i = 0; i < 48; ++i) {
+      const int e = lane + 32 * i, px = e / 48, k = e - px * 48, ky = k / 12, f = k - ky * 12;
+      const int iy = 2 * y - 1 + ky, col3 = (2 * px - 1) * 3 + f;           // float offset inside the 192-float image row
+      float v = 0.f;
+      if (iy >= 0 && iy < Hb && col3 >= 0 && col3 < 192) v = __ldg(big + (n * Hb + iy) * 192 + col3);
+      P[warp][e] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                    // small row: 32 pixels x 32 channels of group g
+      const int idx = lane + 32 * i, px = idx >> 3, f4 = idx & 7;
+      *reinterpret_cast<float4*>(&S[warp][px * 32 + f4 * 4]) =
+          __ldg(reinterpret_cast<const float4*>(small_ + ((n * h + y) * 32 + px) * (long long)Cs + g * 32) + f4);
+    }
+    __syncwarp();
+#pragma unroll 2
+    for (int px = 0; px < 32; ++px) {
+      const u64 ss = dup2(S[warp][px * 32 + lane]);
+      const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(&P[warp][px * 48]);
+#pragma unroll
+      for (int q = 0; q < 12; ++q) {
+        const ulonglong2 bv = pp[q];
+        fma2(acc[2 * q], ss, bv.x);
+        fma2(acc[2 * q + 1], ss, bv.y);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 24; ++q) {
+    atomicAdd(&Red[(2 * q) * 32 + lane], lo32(acc[q]));
+    atomicAdd(&Red[(2 * q + 1) * 32 + lane], hi32(acc[q]));
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 48 * 32; e += blockDim.x) {
+    const int cs = g * 32 + (e & 31), k = e >> 5, tap = k / 3, cb = k - tap * 3;      // k = tap * 3 + cb
+    atomicAdd(&dW[((long long)cs * 3 + cb) * 16 + tap], Red[e]);
+  }
+}
+
 }  // namespace
 
 // internal entry points used by conv.cu's dispatchers
@@ -468,6 +533,16 @@ int b200rl_conv_up_thin(const float* small, const float* W, float* big, const fl
 
 int b200rl_conv_wgrad_thin(const float* small, const float* big, float* dW, int NB, int h, int w, int Cs, int Cb,
                            cudaStream_t st) {
+  if (Cb == 3 && w == 32 && Cs % 32 == 0) {
+    constexpr int NW = 4;
+    const long long rows = (long long)NB * h;
+    long long bx = (rows + NW - 1) / NW;
+    const long long cap = (4LL * kNumSMs) / (Cs / 32) > 0 ? (4LL * kNumSMs) / (Cs / 32) : 1;
+    if (bx > cap) bx = cap;
+    conv_wgrad_thin2_kernel<NW><<<dim3((unsigned)bx, Cs / 32), NW * 32, 0, st>>>(small, big, dW, NB, h, Cs);
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
   const int tiles_per_row = (w + 31) / 32;
   const long long ntiles = (long long)NB * h * tiles_per_row;
   // ~13 KB of smem and 80 registers per thread: 6 CTAs per SM hide the stage -> compute latency of a 32-pixel tile
