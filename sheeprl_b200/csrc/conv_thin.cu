@@ -407,19 +407,22 @@ conv_up_thin2_kernel(const float* __restrict__ small_, const float* __restrict__
 
 // wgrad_thin2: dW[cs][cb][ky][kx] += sum over small pixels of small[p][cs] * big[patch(p)][ky][kx][cb] for 3-channel big images
 // and 32-wide small grids (weight gradient of the encoder's first Conv2d / the decoder's last ConvTranspose2d).  One warp per
-// small row, lane = small channel (blockIdx.y = 32-channel group): the 32 pixels' patches are materialised in shared memory
-// as [pixel][48] (k = (ky*4+kx)*3 + cb, 16-byte aligned), so per pixel 12 warp-uniform LDS.128 + 1 LDS feed 24 packed FMAs
-// on 48 register accumulators (the kernel above needs 24 LDS.64 + 48 FFMA).  One shared-memory + global atomic flush per CTA.
+// small row, lane = small channel (blockIdx.y = 32-channel group).  The 4 image rows a small row touches are staged twice,
+// left-padded by 3 and by 5 floats: pixel x's 12-float patch row starts at float 6x (even x, first copy) or 6x+2 (odd x, second
+// copy), both 16-byte aligned, so per pixel 12 warp-uniform LDS.128 + 1 LDS feed 24 packed FMAs on 48 register accumulators
+// (the kernel above needs 24 LDS.64 + 48 FFMA).  One shared-memory + global atomic flush per CTA.
+constexpr int WT_ROW = 200;
 template <int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
 conv_wgrad_thin2_kernel(const float* __restrict__ small_, const float* __restrict__ big, float* __restrict__ dW, int NB, int h,
                         int Cs) {
-  __shared__ __align__(16) float P[NWARPS][32 * 48];
+  __shared__ __align__(16) float R[NWARPS][2][4][WT_ROW];
   __shared__ __align__(16) float S[NWARPS][32 * 32];
   __shared__ float Red[48 * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = blockIdx.y;
   const int Hb = 2 * h;
   for (int e = threadIdx.x; e < 48 * 32; e += blockDim.x) Red[e] = 0.f;
+  for (int e = threadIdx.x; e < NWARPS * 2 * 4 * WT_ROW; e += blockDim.x) (&R[0][0][0][0])[e] = 0.f;   // the pads stay zero
   __syncthreads();
   u64 acc[24];
 #pragma unroll
@@ -429,14 +432,15 @@ conv_wgrad_thin2_kernel(const float* __restrict__ small_, const float* __restric
     const long long n = u / h;
     const int y = (int)(u - n * h);
     __syncwarp();
-    // patches: element e = pixel * 48 + ky * 12 + (kx * 3 + cb); the 12 floats of a patch row are contiguous in the image
-#pragma unroll 4
-    for (int i = 0; i < 48; ++i) {
-      const int e = lane + 32 * i, px = e / 48, k = e - px * 48, ky = k / 12, f = k - ky * 12;
-      const int iy = 2 * y - 1 + ky, col3 = (2 * px - 1) * 3 + f;           // float offset inside the 192-float image row
-      float v = 0.f;
-      if (iy >= 0 && iy < Hb && col3 >= 0 && col3 < 192) v = __ldg(big + (n * Hb + iy) * 192 + col3);
-      P[warp][e] = v;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {                    // image rows 2y-1 .. 2y+2: 4 x 48 float4
+      const int idx = lane + 32 * i, ky = idx / 48, f4 = idx - ky * 48, iy = 2 * y - 1 + ky;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < Hb) v = __ldg(reinterpret_cast<const float4*>(big + (n * Hb + iy) * 192) + f4);
+      float* ra = &R[warp][0][ky][4 * f4 + 3];
+      float* rb = &R[warp][1][ky][4 * f4 + 5];
+      ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; ra[3] = v.w;
+      rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {                    // small row: 32 pixels x 32 channels of group g
@@ -445,15 +449,21 @@ conv_wgrad_thin2_kernel(const float* __restrict__ small_, const float* __restric
           __ldg(reinterpret_cast<const float4*>(small_ + ((n * h + y) * 32 + px) * (long long)Cs + g * 32) + f4);
     }
     __syncwarp();
-#pragma unroll 2
-    for (int px = 0; px < 32; ++px) {
-      const u64 ss = dup2(S[warp][px * 32 + lane]);
-      const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(&P[warp][px * 48]);
+#pragma unroll 1
+    for (int px = 0; px < 32; px += 2) {
 #pragma unroll
-      for (int q = 0; q < 12; ++q) {
-        const ulonglong2 bv = pp[q];
-        fma2(acc[2 * q], ss, bv.x);
-        fma2(acc[2 * q + 1], ss, bv.y);
+      for (int o = 0; o < 2; ++o) {
+        const u64 ss = dup2(S[warp][(px + o) * 32 + lane]);
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(&R[warp][o][ky][6 * (px + o) + 2 * o]);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const ulonglong2 bv = pp[q];
+            fma2(acc[6 * ky + 2 * q], ss, bv.x);
+            fma2(acc[6 * ky + 2 * q + 1], ss, bv.y);
+          }
+        }
       }
     }
   }
