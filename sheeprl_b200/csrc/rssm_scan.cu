@@ -277,24 +277,85 @@ __device__ __forceinline__ void warp_item(const float* __restrict__ X, int xs, c
   if ((lane & 1) == 0) part[(r0 + (idx >> 2)) * ldp + c0 + (idx & 3)] = v[0];
 }
 
-// Runs all (column group, row block, K slice) items of one product over the CTA's warps.  Slice s writes its partial sums
-// to PART[s][b][cbase + 4*group + j] (every element written by exactly one lane); the caller sums the slices in order
-// (bit-reproducible).  `wbase`: first weight row of group 0; group g starts at wbase + g*4*wst.  Returns the number of
-// slices.  No barrier inside: the caller synchronises before (X complete) and after (PART complete).
+// ---- products on the warp-level tensor-core path -------------------------------------------------------------------
+// The batch is exactly one MMA tile high (B <= 16 rows), so a product is a row of m16n8k8 TF32 MMAs per 8 output columns.
+// fp32 accuracy comes from the same 3xTF32 split as the large GEMMs (x = hi + lo, hi = x with the 13 low mantissa bits
+// cleared; hi*lo + lo*hi + hi*hi, fp32 accumulate), the K reduction happens inside the MMA (the FFMA2 version spent most of
+// a product item in its 62-shuffle cross-lane reduction and was bound by the 128 B/clk shared-memory return path: every
+// loaded word fed only two FMAs), and a K slice's partial tile goes to PART like before (fixed-order sum by the caller).
+// k permutation: within a 16-wide k step lane (g, t) owns k = 4t..4t+3 of BOTH operands (one LDS.128 each); the first MMA
+// of the step consumes words 0, 1 as fragment columns (t, t+4), the second words 2, 3 — any pairing is valid as long as A
+// and B agree, the MMA sums over k.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+__device__ __forceinline__ unsigned tf32_lo(float x) { return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u)); }
+
+// One (8-column tile, K slice) item.  X rows [0, 16) of stride xs (rows >= B are never read: their fragments are zero), weight
+// rows w + n * wst for n < nvalid (missing rows read as zero).  k0, k1 multiples of 4; the tail of a slice is zero padded
+// (both operands are zero padded to r4(K) by their producers, reads stay below k1).
+__device__ __forceinline__ void mma_item(const float* __restrict__ X, int xs, int B, const float* __restrict__ w, int wst,
+                                         int nvalid, int k0, int k1, float* part, int ldp, int c0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool r_lo = g < B, r_hi = g + 8 < B, n_ok = g < nvalid;
+  const float* xa = X + (size_t)g * xs;
+  const float* xb = X + (size_t)(g + 8) * xs;
+  const float* wr = w + (size_t)g * wst;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = k0 + 4 * t; k < k1; k += 16) {
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va, vw = va;
+    if (r_lo) va = *reinterpret_cast<const float4*>(xa + k);
+    if (r_hi) vb = *reinterpret_cast<const float4*>(xb + k);
+    if (n_ok) vw = *reinterpret_cast<const float4*>(wr + k);
+    {
+      const unsigned ah[4] = {tf32_hi(va.x), tf32_hi(vb.x), tf32_hi(va.y), tf32_hi(vb.y)};
+      const unsigned al[4] = {tf32_lo(va.x), tf32_lo(vb.x), tf32_lo(va.y), tf32_lo(vb.y)};
+      const unsigned bh0 = tf32_hi(vw.x), bh1 = tf32_hi(vw.y), bl0 = tf32_lo(vw.x), bl1 = tf32_lo(vw.y);
+      mma_tf32(d, ah, bl0, bl1);
+      mma_tf32(d, al, bh0, bh1);
+      mma_tf32(d, ah, bh0, bh1);
+    }
+    {
+      const unsigned ah[4] = {tf32_hi(va.z), tf32_hi(vb.z), tf32_hi(va.w), tf32_hi(vb.w)};
+      const unsigned al[4] = {tf32_lo(va.z), tf32_lo(vb.z), tf32_lo(va.w), tf32_lo(vb.w)};
+      const unsigned bh0 = tf32_hi(vw.z), bh1 = tf32_hi(vw.w), bl0 = tf32_lo(vw.z), bl1 = tf32_lo(vw.w);
+      mma_tf32(d, ah, bl0, bl1);
+      mma_tf32(d, al, bh0, bh1);
+      mma_tf32(d, ah, bh0, bh1);
+    }
+  }
+  // accumulator fragment: d0 (row g, col 2t), d1 (g, 2t+1), d2 (g+8, 2t), d3 (g+8, 2t+1)
+  const int c = 2 * t;
+  if (c < nvalid) {
+    part[(size_t)g * ldp + c0 + c] = d[0];
+    part[(size_t)(g + 8) * ldp + c0 + c] = d[2];
+  }
+  if (c + 1 < nvalid) {
+    part[(size_t)g * ldp + c0 + c + 1] = d[1];
+    part[(size_t)(g + 8) * ldp + c0 + c + 1] = d[3];
+  }
+}
+
+// Runs all (8-column tile, K slice) items of one product over the CTA's warps.  Slice s writes its partial sums to
+// PART[s][b][cbase + column] for all MAXB rows (every element written by exactly one lane); the caller sums the slices in
+// order (bit-reproducible).  `wbase`: first weight row; column n is row wbase + n*wst (groups of 4 columns are contiguous
+// rows).  Returns the number of slices.  No barrier inside: the caller synchronises before (X complete) and after.
 __device__ __noinline__ int product(const float* X, int xs, const float* wbase, int wst, int ngroups, int K, int B,
                                        float* PART, int ldp, int cbase, int tid) {
   if (ngroups <= 0) return 0;
   const int lane = tid & 31, wid = tid >> 5;
-  const int nrb = (B + NRB - 1) / NRB, Kp = r4(K);
-  int ks = imin(KS_MAX, imax(1, SCAN_NW / (ngroups * nrb)));
-  const int kchunk = ((Kp + ks - 1) / ks + 127) / 128 * 128;
+  const int ncols = ngroups * 4, ntiles = (ncols + 7) >> 3, Kp = r4(K);
+  int ks = imin(KS_MAX, imax(1, SCAN_NW / ntiles));
+  const int kchunk = ((Kp + ks - 1) / ks + 15) / 16 * 16;
   ks = (Kp + kchunk - 1) / kchunk;
-  const int per = ngroups * nrb;
-  for (int item = wid; item < per * ks; item += SCAN_NW) {
-    const int sl = item / per, rem = item - sl * per;
-    const int rb = rem / ngroups, cg = rem - rb * ngroups;
+  for (int item = wid; item < ntiles * ks; item += SCAN_NW) {
+    const int sl = item / ntiles, tile = item - sl * ntiles;
     const int k0 = sl * kchunk, k1 = imin(Kp, k0 + kchunk);
-    warp_item(X, xs, wbase + (size_t)cg * 4 * wst, wst, k0, k1, PART + (size_t)sl * MAXB * ldp, ldp, rb * NRB, cbase + cg * 4, lane);
+    mma_item(X, xs, B, wbase + (size_t)tile * 8 * wst, wst, imin(8, ncols - tile * 8), k0, k1,
+             PART + (size_t)sl * MAXB * ldp, ldp, cbase + tile * 8, lane);
   }
   return ks;
 }
