@@ -305,11 +305,13 @@ __device__ __forceinline__ void mma_item(const float* __restrict__ X, int xs, in
   const float* xb = X + (size_t)(g + 8) * xs;
   const float* wr = w + (size_t)g * wst;
   float d[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k = k0 + 4 * t; k < k1; k += 16) {
+  for (int kb = k0; kb < k1; kb += 16) {             // warp-uniform trip count (mma.sync needs the whole warp)
+    const int k = kb + 4 * t;
+    const bool k_ok = k < k1;
     float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va, vw = va;
-    if (r_lo) va = *reinterpret_cast<const float4*>(xa + k);
-    if (r_hi) vb = *reinterpret_cast<const float4*>(xb + k);
-    if (n_ok) vw = *reinterpret_cast<const float4*>(wr + k);
+    if (r_lo && k_ok) va = *reinterpret_cast<const float4*>(xa + k);
+    if (r_hi && k_ok) vb = *reinterpret_cast<const float4*>(xb + k);
+    if (n_ok && k_ok) vw = *reinterpret_cast<const float4*>(wr + k);
     {
       const unsigned ah[4] = {tf32_hi(va.x), tf32_hi(vb.x), tf32_hi(va.y), tf32_hi(vb.y)};
       const unsigned al[4] = {tf32_lo(va.x), tf32_lo(vb.x), tf32_lo(va.y), tf32_lo(vb.y)};
