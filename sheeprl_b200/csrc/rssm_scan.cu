@@ -368,25 +368,49 @@ __device__ __forceinline__ float part_sum(const float* PART, int ldp, int ks, in
   return v;
 }
 
-// Class-per-lane product (forward logits, backward dz): out[row][lane] = sum_k X[row][k] * W[lane][k] for nr <= MAXRPU rows.
-// Warp (K slice s = wid % CLS_SLICES, row phase wid / CLS_SLICES); partials go to PART[s][row][lane] (fixed-order sum by
-// the caller).  W rows have stride wst = K + 4 (the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups).
+// Class-per-column product (forward logits, backward dz): out[row][class] = sum_k X[row][k] * W[class][k] for nr <= MAXRPU
+// rows and D <= 32 classes, on the same m16n8k8 3xTF32 MMAs as `product` (rows 8..15 of the tile are unused).  Warp
+// (K slice s = wid % CLS_SLICES, class half wid / CLS_SLICES: two 8-class tiles sharing the A fragments); partials go to
+// PART[s][row][class] (fixed-order sum by the caller).
 __device__ __noinline__ void class_product(const float* X, int xs, const float* W, int wst, int D, int Kp, int nr, float* PART,
                                               int tid) {
-  const int lane = tid & 31, wid = tid >> 5;
-  const int sl = wid % CLS_SLICES, rph = wid / CLS_SLICES, nph = SCAN_NW / CLS_SLICES;
-  const int kc = ((Kp + CLS_SLICES - 1) / CLS_SLICES + 3) / 4 * 4;
+  const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int sl = wid % CLS_SLICES, half = wid / CLS_SLICES;           // SCAN_NW == 2 * CLS_SLICES
+  const int kc = ((Kp + CLS_SLICES - 1) / CLS_SLICES + 15) / 16 * 16;
   const int k0 = sl * kc, k1 = imin(Kp, k0 + kc);
-  const float* wrow = W + (size_t)imin(lane, D - 1) * wst;
-  for (int r = rph; r < nr; r += nph) {
-    u64 acc = 0ull;
-    for (int k = k0; k < k1; k += 4) {
-      const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wrow + k);
-      const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(X + r * xs + k);
-      fma2(acc, x.x, w4.x);
-      fma2(acc, x.y, w4.y);
+  const int n0 = half * 16;                                           // classes [n0, n0 + 16)
+  if (n0 >= D) return;
+  const bool r_ok = g < nr, n_ok0 = n0 + g < D, n_ok1 = n0 + 8 + g < D;
+  const float* xa = X + (size_t)g * xs;
+  const float* w0 = W + (size_t)(n0 + g) * wst;
+  const float* w1 = W + (size_t)(n0 + 8 + g) * wst;
+  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kb = k0; kb < k1; kb += 16) {
+    const int k = kb + 4 * t;
+    const bool k_ok = k < k1;
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), v0 = va, v1 = va;
+    if (r_ok && k_ok) va = *reinterpret_cast<const float4*>(xa + k);
+    if (n_ok0 && k_ok) v0 = *reinterpret_cast<const float4*>(w0 + k);
+    if (n_ok1 && k_ok) v1 = *reinterpret_cast<const float4*>(w1 + k);
+    {
+      const unsigned ah[4] = {tf32_hi(va.x), 0u, tf32_hi(va.y), 0u}, al[4] = {tf32_lo(va.x), 0u, tf32_lo(va.y), 0u};
+      mma_tf32(d0, ah, tf32_lo(v0.x), tf32_lo(v0.y)); mma_tf32(d0, al, tf32_hi(v0.x), tf32_hi(v0.y));
+      mma_tf32(d0, ah, tf32_hi(v0.x), tf32_hi(v0.y));
+      mma_tf32(d1, ah, tf32_lo(v1.x), tf32_lo(v1.y)); mma_tf32(d1, al, tf32_hi(v1.x), tf32_hi(v1.y));
+      mma_tf32(d1, ah, tf32_hi(v1.x), tf32_hi(v1.y));
     }
-    PART[((size_t)sl * MAXRPU + r) * 32 + lane] = pair_sum(acc);
+    {
+      const unsigned ah[4] = {tf32_hi(va.z), 0u, tf32_hi(va.w), 0u}, al[4] = {tf32_lo(va.z), 0u, tf32_lo(va.w), 0u};
+      mma_tf32(d0, ah, tf32_lo(v0.z), tf32_lo(v0.w)); mma_tf32(d0, al, tf32_hi(v0.z), tf32_hi(v0.w));
+      mma_tf32(d0, ah, tf32_hi(v0.z), tf32_hi(v0.w));
+      mma_tf32(d1, ah, tf32_lo(v1.z), tf32_lo(v1.w)); mma_tf32(d1, al, tf32_hi(v1.z), tf32_hi(v1.w));
+      mma_tf32(d1, ah, tf32_hi(v1.z), tf32_hi(v1.w));
+    }
+  }
+  if (g < nr) {                                        // accumulator rows g (d[0], d[1]); rows g + 8 are padding
+    float* out = PART + ((size_t)sl * MAXRPU + g) * 32 + n0 + 2 * t;
+    out[0] = d0[0]; out[1] = d0[1];
+    out[8] = d1[0]; out[9] = d1[1];
   }
 }
 
