@@ -304,7 +304,8 @@ __device__ __forceinline__ void mma_item(const float* __restrict__ X, int xs, in
   const float* xa = X + (size_t)g * xs;
   const float* xb = X + (size_t)(g + 8) * xs;
   const float* wr = w + (size_t)g * wst;
-  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  // three independent accumulators (hi*lo, lo*hi, hi*hi): a step's 6 MMAs form chains of 2 instead of 6 dependent MMAs
+  float d[4] = {0.f, 0.f, 0.f, 0.f}, dx[4] = {0.f, 0.f, 0.f, 0.f}, dy[4] = {0.f, 0.f, 0.f, 0.f};
   for (int kb = k0; kb < k1; kb += 16) {             // warp-uniform trip count (mma.sync needs the whole warp)
     const int k = kb + 4 * t;
     const bool k_ok = k < k1;
@@ -316,19 +317,21 @@ __device__ __forceinline__ void mma_item(const float* __restrict__ X, int xs, in
       const unsigned ah[4] = {tf32_hi(va.x), tf32_hi(vb.x), tf32_hi(va.y), tf32_hi(vb.y)};
       const unsigned al[4] = {tf32_lo(va.x), tf32_lo(vb.x), tf32_lo(va.y), tf32_lo(vb.y)};
       const unsigned bh0 = tf32_hi(vw.x), bh1 = tf32_hi(vw.y), bl0 = tf32_lo(vw.x), bl1 = tf32_lo(vw.y);
-      mma_tf32(d, ah, bl0, bl1);
-      mma_tf32(d, al, bh0, bh1);
+      mma_tf32(dx, ah, bl0, bl1);
+      mma_tf32(dy, al, bh0, bh1);
       mma_tf32(d, ah, bh0, bh1);
     }
     {
       const unsigned ah[4] = {tf32_hi(va.z), tf32_hi(vb.z), tf32_hi(va.w), tf32_hi(vb.w)};
       const unsigned al[4] = {tf32_lo(va.z), tf32_lo(vb.z), tf32_lo(va.w), tf32_lo(vb.w)};
       const unsigned bh0 = tf32_hi(vw.z), bh1 = tf32_hi(vw.w), bl0 = tf32_lo(vw.z), bl1 = tf32_lo(vw.w);
-      mma_tf32(d, ah, bl0, bl1);
-      mma_tf32(d, al, bh0, bh1);
+      mma_tf32(dx, ah, bl0, bl1);
+      mma_tf32(dy, al, bh0, bh1);
       mma_tf32(d, ah, bh0, bh1);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i] += dx[i] + dy[i];
   // accumulator fragment: d0 (row g, col 2t), d1 (g, 2t+1), d2 (g+8, 2t), d3 (g+8, 2t+1)
   const int c = 2 * t;
   if (c < nvalid) {
@@ -385,6 +388,7 @@ __device__ __noinline__ void class_product(const float* X, int xs, const float* 
   const float* w0 = W + (size_t)(n0 + g) * wst;
   const float* w1 = W + (size_t)(n0 + 8 + g) * wst;
   float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+  float e0[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f};     // cross terms (hi*lo + lo*hi), separate chains
   for (int kb = k0; kb < k1; kb += 16) {
     const int k = kb + 4 * t;
     const bool k_ok = k < k1;
@@ -394,23 +398,21 @@ __device__ __noinline__ void class_product(const float* X, int xs, const float* 
     if (n_ok1 && k_ok) v1 = *reinterpret_cast<const float4*>(w1 + k);
     {
       const unsigned ah[4] = {tf32_hi(va.x), 0u, tf32_hi(va.y), 0u}, al[4] = {tf32_lo(va.x), 0u, tf32_lo(va.y), 0u};
-      mma_tf32(d0, ah, tf32_lo(v0.x), tf32_lo(v0.y)); mma_tf32(d0, al, tf32_hi(v0.x), tf32_hi(v0.y));
-      mma_tf32(d0, ah, tf32_hi(v0.x), tf32_hi(v0.y));
-      mma_tf32(d1, ah, tf32_lo(v1.x), tf32_lo(v1.y)); mma_tf32(d1, al, tf32_hi(v1.x), tf32_hi(v1.y));
-      mma_tf32(d1, ah, tf32_hi(v1.x), tf32_hi(v1.y));
+      mma_tf32(e0, ah, tf32_lo(v0.x), tf32_lo(v0.y)); mma_tf32(e1, ah, tf32_lo(v1.x), tf32_lo(v1.y));
+      mma_tf32(d0, ah, tf32_hi(v0.x), tf32_hi(v0.y)); mma_tf32(d1, ah, tf32_hi(v1.x), tf32_hi(v1.y));
+      mma_tf32(e0, al, tf32_hi(v0.x), tf32_hi(v0.y)); mma_tf32(e1, al, tf32_hi(v1.x), tf32_hi(v1.y));
     }
     {
       const unsigned ah[4] = {tf32_hi(va.z), 0u, tf32_hi(va.w), 0u}, al[4] = {tf32_lo(va.z), 0u, tf32_lo(va.w), 0u};
-      mma_tf32(d0, ah, tf32_lo(v0.z), tf32_lo(v0.w)); mma_tf32(d0, al, tf32_hi(v0.z), tf32_hi(v0.w));
-      mma_tf32(d0, ah, tf32_hi(v0.z), tf32_hi(v0.w));
-      mma_tf32(d1, ah, tf32_lo(v1.z), tf32_lo(v1.w)); mma_tf32(d1, al, tf32_hi(v1.z), tf32_hi(v1.w));
-      mma_tf32(d1, ah, tf32_hi(v1.z), tf32_hi(v1.w));
+      mma_tf32(e0, ah, tf32_lo(v0.z), tf32_lo(v0.w)); mma_tf32(e1, ah, tf32_lo(v1.z), tf32_lo(v1.w));
+      mma_tf32(d0, ah, tf32_hi(v0.z), tf32_hi(v0.w)); mma_tf32(d1, ah, tf32_hi(v1.z), tf32_hi(v1.w));
+      mma_tf32(e0, al, tf32_hi(v0.z), tf32_hi(v0.w)); mma_tf32(e1, al, tf32_hi(v1.z), tf32_hi(v1.w));
     }
   }
   if (g < nr) {                                        // accumulator rows g (d[0], d[1]); rows g + 8 are padding
     float* out = PART + ((size_t)sl * MAXRPU + g) * 32 + n0 + 2 * t;
-    out[0] = d0[0]; out[1] = d0[1];
-    out[8] = d1[0]; out[9] = d1[1];
+    out[0] = d0[0] + e0[0]; out[1] = d0[1] + e0[1];
+    out[8] = d1[0] + e1[0]; out[9] = d1[1] + e1[1];
   }
 }
 
