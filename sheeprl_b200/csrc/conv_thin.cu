@@ -407,10 +407,9 @@ conv_up_thin2_kernel(const float* __restrict__ small_, const float* __restrict__
 
 // wgrad_thin2: dW[cs][cb][ky][kx] += sum over small pixels of small[p][cs] * big[patch(p)][ky][kx][cb] for 3-channel big images
 // and 32-wide small grids (weight gradient of the encoder's first Conv2d / the decoder's last ConvTranspose2d).  One warp per
-// small row, lane = small channel (blockIdx.y = 32-channel group).  The 4 image rows a small row touches are staged twice,
-// left-padded by 3 and by 5 floats: pixel x's 12-float patch row starts at float 6x (even x, first copy) or 6x+2 (odd x, second
-// copy), both 16-byte aligned, so per pixel 12 warp-uniform LDS.128 + 1 LDS feed 24 packed FMAs on 48 register accumulators
-// (the kernel above needs 24 LDS.64 + 48 FFMA).  One shared-memory + global atomic flush per CTA.
+// small row (blockIdx.y = 32-channel group).  The 4 image rows a small row touches are staged twice, left-padded by 3 and by
+// 5 floats: pixel x's 12-float patch row starts at float 6x (even x, first copy) or 6x+2 (odd x, second copy), both 16-byte
+// aligned LDS.128.  One shared-memory + global atomic flush per CTA.
 constexpr int WT_ROW = 200;
 template <int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
@@ -424,9 +423,16 @@ conv_wgrad_thin2_kernel(const float* __restrict__ small_, const float* __restric
   for (int e = threadIdx.x; e < 48 * 32; e += blockDim.x) Red[e] = 0.f;
   for (int e = threadIdx.x; e < NWARPS * 2 * 4 * WT_ROW; e += blockDim.x) (&R[0][0][0][0])[e] = 0.f;   // the pads stay zero
   __syncthreads();
-  u64 acc[24];
+  // lane = (patch row ky = lane >> 3, channel quad csg = lane & 7): 12 patch floats x 4 channels of accumulators, packed
+  // over patch-float pairs.  Per pixel a lane loads its 12 patch floats (3 LDS.128, shared by the 8 lanes of a ky) and its
+  // 4 channel values (1 LDS.128, shared by the 4 lanes of a quad): 16 words for 48 FMAs — the warp-per-channel mapping
+  // loaded 49 words for 48 FMAs and sat on the 128 B/clk shared-memory return path.
+  const int kg = lane >> 3, csg = lane & 7;
+  u64 acc[6][4];
 #pragma unroll
-  for (int q = 0; q < 24; ++q) acc[q] = 0ull;
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[q][c] = 0ull;
   const long long rows = (long long)NB * h;
   for (long long u = (long long)blockIdx.x * NWARPS + warp; u < rows; u += (long long)gridDim.x * NWARPS) {
     const long long n = u / h;
@@ -449,29 +455,31 @@ conv_wgrad_thin2_kernel(const float* __restrict__ small_, const float* __restric
           __ldg(reinterpret_cast<const float4*>(small_ + ((n * h + y) * 32 + px) * (long long)Cs + g * 32) + f4);
     }
     __syncwarp();
-#pragma unroll 1
+#pragma unroll 2
     for (int px = 0; px < 32; px += 2) {
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
-        const u64 ss = dup2(S[warp][(px + o) * 32 + lane]);
+        const float4 sv = *reinterpret_cast<const float4*>(&S[warp][(px + o) * 32 + csg * 4]);
+        const u64 s0 = dup2(sv.x), s1 = dup2(sv.y), s2 = dup2(sv.z), s3 = dup2(sv.w);
+        const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(&R[warp][o][kg][6 * (px + o) + 2 * o]);
 #pragma unroll
-        for (int ky = 0; ky < 4; ++ky) {
-          const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(&R[warp][o][ky][6 * (px + o) + 2 * o]);
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const ulonglong2 bv = pp[q];
-            fma2(acc[6 * ky + 2 * q], ss, bv.x);
-            fma2(acc[6 * ky + 2 * q + 1], ss, bv.y);
-          }
+        for (int q = 0; q < 3; ++q) {
+          const ulonglong2 bv = pp[q];
+          fma2(acc[2 * q][0], s0, bv.x); fma2(acc[2 * q][1], s1, bv.x); fma2(acc[2 * q][2], s2, bv.x); fma2(acc[2 * q][3], s3, bv.x);
+          fma2(acc[2 * q + 1][0], s0, bv.y); fma2(acc[2 * q + 1][1], s1, bv.y);
+          fma2(acc[2 * q + 1][2], s2, bv.y); fma2(acc[2 * q + 1][3], s3, bv.y);
         }
       }
     }
   }
+  // acc[q][c]: patch floats f = 2q, 2q+1 of row kg (k = kg*12 + f), channel csg*4 + c
 #pragma unroll
-  for (int q = 0; q < 24; ++q) {
-    atomicAdd(&Red[(2 * q) * 32 + lane], lo32(acc[q]));
-    atomicAdd(&Red[(2 * q + 1) * 32 + lane], hi32(acc[q]));
-  }
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      atomicAdd(&Red[(kg * 12 + 2 * q) * 32 + csg * 4 + c], lo32(acc[q][c]));
+      atomicAdd(&Red[(kg * 12 + 2 * q + 1) * 32 + csg * 4 + c], hi32(acc[q][c]));
+    }
   __syncthreads();
   for (int e = threadIdx.x; e < 48 * 32; e += blockDim.x) {
     const int cs = g * 32 + (e & 31), k = e >> 5, tap = k / 3, cb = k - tap * 3;      // k = tap * 3 + cb

@@ -304,6 +304,34 @@ __global__ void col_sum_kernel(const float* __restrict__ X, float* __restrict__ 
   }
 }
 
+// Narrow contiguous matrices (C <= 32, ldx == C: the 3-channel image gradient behind the decoder's output bias): the
+// matrix is read as one flat float4 stream.  The total thread count is a multiple of C, so the column of each of a
+// thread's 4 vector slots never changes across its grid-stride iterations: 4 register accumulators, no per-element modulo.
+__global__ void __launch_bounds__(256)
+col_sum_narrow_kernel(const float* __restrict__ X, float* __restrict__ out, long long total, int C) {
+  __shared__ float bins[32];
+  if (threadIdx.x < 32) bins[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  const long long n4 = total >> 2;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (long long j = tid; j < n4; j += nt) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(X) + j);
+    a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+  }
+  const int c0 = (int)((4 * tid) % C);
+  if (tid < n4) {
+    atomicAdd(&bins[c0], a0);
+    atomicAdd(&bins[(c0 + 1) % C], a1);
+    atomicAdd(&bins[(c0 + 2) % C], a2);
+    atomicAdd(&bins[(c0 + 3) % C], a3);
+  }
+  if (tid == 0)
+    for (long long i = n4 << 2; i < total; ++i) atomicAdd(&bins[(int)(i % C)], X[i]);
+  __syncthreads();
+  if (threadIdx.x < C && bins[threadIdx.x] != 0.f) atomicAdd(&out[threadIdx.x], bins[threadIdx.x]);
+}
+
 
 // ---------------------------------------------------------------------------------------------------------
 // Vectorised row kernels: a row of C = 4*LPR*NV floats is held in registers by LPR lanes (NV float4 each), so X
@@ -595,6 +623,13 @@ extern "C" int b200rl_col_sum(const float* X, float* out, long long M, int C, lo
   RL_CHECK_ARG(C > 0 && ldx >= C, "bad C / ld");
   if (!accumulate) RL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
   if (M <= 0) return B200RL_OK;
+  if (C <= 32 && ldx == C && M * C >= (1 << 16) && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    int blocks = 4 * kNumSMs;
+    blocks = (blocks + C - 1) / C * C;             // thread count divisible by C: fixed column per vector slot
+    col_sum_narrow_kernel<<<blocks, 256, 0, st>>>(X, out, M * C, C);
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
   const int cb = ceil_div(C, 32);
   long long rb = (2LL * kNumSMs + cb - 1) / cb;
   long long rows_per_block = (M + rb - 1) / rb;

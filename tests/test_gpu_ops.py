@@ -224,7 +224,9 @@ def test_ln_act_tanh_relu(ops, M, C, act):
     close(dbg, dbc, rtol=2e-5 * max(M, 16) ** 0.5 / 4, what="ln dbeta")
 
 
-@pytest.mark.parametrize("M,C", [(1024, 255), (1048576 // 64, 3), (17, 4096), (3, 1)])
+@pytest.mark.parametrize("M,C", [(1024, 255), (1048576 // 64, 3), (17, 4096), (3, 1),
+                                 # narrow contiguous matrices take the flat float4 kernel (tail of 2 elements in the second)
+                                 (262144, 3), (21846, 3), (100000, 7), (70000, 32), (65536, 1)])
 def test_col_sum(ops, M, C):
     cu, em = ops
     X = rnd(M, C, seed=1)
