@@ -215,109 +215,6 @@ cat_sample_small_kernel(const float* __restrict__ raw, const float* __restrict__
                   onehot ? onehot + m * ldo + (long long)g * K : nullptr, mix_out ? mix_out + m * ldm + (long long)g * K : nullptr);
 }
 
-// Thread-per-categorical version for many small groups (the 1024 x 32 categoricals of an imagination step): the K <= 32
-// classes sit in one thread's registers, so no shuffle is needed (the lane-per-class kernel spends its time in ~55 dependent
-// SHFLs per categorical).  Sums and maxima are reduced in the butterfly's pairing order (i, i+16), (i, i+8), ... so every
-// quantity — and therefore every sample — is bit-identical to cat_sample_small_kernel.
-__device__ __forceinline__ float tree_sum32(const float (&v)[32]) {
-  float a[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = v[i] + v[i + 16];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = a[i] + a[i + 8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) a[i] = a[i] + a[i + 4];
-  return ((a[0] + a[2]) + (a[1] + a[3]));
-}
-__device__ __forceinline__ float tree_max32(const float (&v)[32]) {
-  float m = v[0];
-#pragma unroll
-  for (int i = 1; i < 32; ++i) m = fmaxf(m, v[i]);
-  return m;
-}
-
-__global__ void __launch_bounds__(128)
-cat_sample_thread_kernel(const float* __restrict__ raw, const float* __restrict__ noise, float* __restrict__ onehot,
-                         float* __restrict__ mix_out, long long M, int groups, int K, long long ldr, long long ldn,
-                         long long ldo, long long ldm, float unimix) {
-  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= M * groups) return;
-  const long long m = id / groups;
-  const int g = (int)(id - m * groups);
-  const float* x = raw + m * ldr + (long long)g * K;
-  const bool vec = (K == 32) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  float v[32];
-  if (vec) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 t = reinterpret_cast<const float4*>(x)[q];
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = c < K ? x[c] : -INFINITY;
-  }
-  const float mx = tree_max32(v);
-  float e[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) e[c] = c < K ? expf(v[c] - mx) : 0.f;
-  const float sm = tree_sum32(e);
-  const float invK = 1.f / (float)K;
-  // l = unimix log-probs (or the raw logits)
-  if (unimix > 0.f) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < K) { float pm; v[c] = unimix_logprob(e[c] / sm, unimix, invK, pm); }
-  }
-  float lmx = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) if (c < K) lmx = fmaxf(lmx, v[c]);
-#pragma unroll
-  for (int c = 0; c < 32; ++c) e[c] = c < K ? expf(v[c] - lmx) : 0.f;
-  const float lse = lmx + logf(tree_sum32(e));
-  if (mix_out) {
-    float* mo = mix_out + m * ldm + (long long)g * K;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) if (c < K) mo[c] = v[c];
-  }
-  if (!onehot) return;
-  float lgmax = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) if (c < K) lgmax = fmaxf(lgmax, v[c] - lse);
-#pragma unroll
-  for (int c = 0; c < 32; ++c) e[c] = c < K ? expf(v[c] - lse - lgmax) : 0.f;
-  const float psum = tree_sum32(e);
-  float best = -INFINITY;
-  int besti = 0;
-  const float* nz = noise ? noise + m * ldn + (long long)g * K : nullptr;
-  const bool nvec = nz && (K == 32) && ((reinterpret_cast<uintptr_t>(nz) & 15) == 0);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float4 t = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (nvec) t = reinterpret_cast<const float4*>(nz)[q];
-    const float ns[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = 4 * q + j;
-      if (c < K) {
-        float p = e[c] / psum;
-        if (nz) p = p / (nvec ? ns[j] : nz[c]);
-        if (p > best) { best = p; besti = c; }     // strict >: the first maximum, like the butterfly's lowest-lane tie break
-      }
-    }
-  }
-  float* oh = onehot + m * ldo + (long long)g * K;
-  if (K == 32 && (reinterpret_cast<uintptr_t>(oh) & 15) == 0) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      reinterpret_cast<float4*>(oh)[q] = make_float4(besti == 4 * q ? 1.f : 0.f, besti == 4 * q + 1 ? 1.f : 0.f,
-                                                     besti == 4 * q + 2 ? 1.f : 0.f, besti == 4 * q + 3 ? 1.f : 0.f);
-  } else {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) if (c < K) oh[c] = (c == besti) ? 1.f : 0.f;
-  }
-}
-
 // Policy head + sample in one launch (Actor.mlp_heads[i] then OneHotCategoricalStraightThrough.rsample, agent.py:793-818):
 // one warp per row computes the A <= 32 logits of a [A, Kin] Linear (+ bias) on its row (Kin % 4 == 0, Kin <= 1024: the
 // row stays in registers), writes them (`raw`, kept for the policy gradient) and draws the sample like cat_sample.
@@ -600,10 +497,7 @@ extern "C" int b200rl_cat_sample(const float* raw, const float* noise, float* on
   RL_CHECK_ARG(groups > 0 && K > 0, "bad groups / classes");
   if (M <= 0) return B200RL_OK;
   const long long warps = M * groups;
-  if (K <= 32 && warps >= 8192)      // many small categoricals: one thread each, classes in registers
-    cat_sample_thread_kernel<<<ceil_div(warps, 128), 128, 0, st>>>(raw, noise, onehot, mix_out, M, groups, K, ldr, ldn, ldo,
-                                                                   ldm, unimix);
-  else if (K <= 32)
+  if (K <= 32)
     cat_sample_small_kernel<<<ceil_div(warps, 8), 256, 0, st>>>(raw, noise, onehot, mix_out, M, groups, K, ldr, ldn, ldo,
                                                                 ldm, unimix);
   else

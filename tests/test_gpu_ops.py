@@ -719,21 +719,3 @@ def test_head_sample_equals_linear_then_cat_sample(ops, M, Kin, A, unimix):
     cu.cat_sample(raw_all[:, 3:], qg[:, 2:2 + A], unimix, 1, A, hot2)
     assert torch.equal(hot2, act_all[:, 3:])
     assert float(raw_all[:, :3].abs().max()) == 0.0 and float(act_all[:, :3].abs().max()) == 0.0
-
-
-@pytest.mark.parametrize("S,D,unimix", [(32, 32, 0.01), (32, 32, 0.0), (40, 7, 0.01), (64, 20, 0.01)])
-def test_cat_sample_thread_per_group_kernel_is_bit_identical_to_the_lane_kernel(ops, S, D, unimix):
-    """>= 8192 categoricals take the thread-per-categorical kernel (classes in registers, tree reductions in the butterfly's
-    pairing order); fewer take the lane-per-class kernel.  Same rows through both: identical samples and log-probs."""
-    cu, _ = ops
-    M = (8192 + S - 1) // S + 3
-    few = 8191 // S
-    raw = (rnd(M, S * D + 4, seed=1, scale=2.5)[:, 4:]).cuda()            # rows not 16-byte aligned when D * 4 % 16 != 0
-    q = torch.empty(M, S * D).exponential_(1.0, generator=torch.Generator().manual_seed(2)).cuda()
-    for noise in (q, None):
-        h_all, m_all = torch.empty(M, S * D, device="cuda"), torch.empty(M, S * D, device="cuda")
-        h_few, m_few = torch.empty(few, S * D, device="cuda"), torch.empty(few, S * D, device="cuda")
-        cu.cat_sample(raw, noise, unimix, S, D, h_all, m_all)
-        cu.cat_sample(raw[:few], None if noise is None else noise[:few], unimix, S, D, h_few, m_few)
-        assert torch.equal(h_all[:few], h_few) and torch.equal(m_all[:few], m_few)
-        assert float((h_all.view(M, S, D).sum(-1) - 1).abs().max()) == 0.0
