@@ -289,8 +289,9 @@ int b200rl_ppo_loss(const float* head, const float* actions, const float* old_lo
  * rollout.  z: [M, S*K] (row stride ldz), act: [M, A], out: [M, N]. */
 int b200rl_onehot_linear(const float* z, const float* act, const float* WT, float* out, long long M, int S, int K, int A,
                          int N, long long ldz, long long lda, long long ldo, cudaStream_t stream);
-/* The same gather followed, in the same launch, by the miniblock's LayerNorm(eps) + SiLU (N <= 1024): out = SiLU(LN(Linear
- * ([z, a]))); `pre` (optional) keeps the Linear output. */
+/* The same gather followed, in the same launch, by the miniblock's LayerNorm(eps) + SiLU: out = SiLU(LN(Linear([z, a])));
+ * `pre` (optional) keeps the Linear output.  N a multiple of 128 up to 1024 (one float4 of the row per thread), 16-byte
+ * aligned WT / gamma / beta / out / pre rows. */
 int b200rl_onehot_linear_ln(const float* z, const float* act, const float* WT, const float* gamma, const float* beta,
                             float eps, float* pre, long long ldpre, float* out, long long M, int S, int K, int A, int N,
                             long long ldz, long long lda, long long ldo, cudaStream_t stream);

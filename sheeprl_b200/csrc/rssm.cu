@@ -376,7 +376,7 @@ kl_loss_grad_kernel(const float* __restrict__ post, const float* __restrict__ pr
 // of S+A rows of the transposed weight instead of a K = S*K + A product (agent.py:328-341 RecurrentModel.mlp input).
 // One CTA per row; WT [S*K + A, N] row-major (transposed copy of the Linear weight, L2 resident).
 // With `gamma`: the row continues through LayerNorm(eps) + SiLU (RecurrentModel.mlp's miniblock) before it is written
-// (N <= 1024: the row lives in 4 registers per thread); `pre` optionally keeps the Linear output for a backward.
+// (launched with N / 4 threads, one float4 of the row each); `pre` optionally keeps the Linear output for a backward.
 __global__ void __launch_bounds__(256)
 onehot_linear_kernel(const float* __restrict__ z, const float* __restrict__ act, const float* __restrict__ WT,
                      float* __restrict__ out, int S, int K, int A, int N, long long ldz, long long lda, long long ldo,
@@ -387,7 +387,7 @@ onehot_linear_kernel(const float* __restrict__ z, const float* __restrict__ act,
   __shared__ float red[8];
   const long long m = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int g = warp; g < S; g += 8) {                       // hot index of each group by ballot
+  for (int g = warp; g < S; g += (int)(blockDim.x >> 5)) {  // hot index of each group by ballot
     int found = 0;
     for (int c0 = 0; c0 < K; c0 += 32) {
       const int c = c0 + lane;
@@ -408,47 +408,38 @@ onehot_linear_kernel(const float* __restrict__ z, const float* __restrict__ act,
     }
     return;
   }
-  float v[4];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = threadIdx.x + 256 * i;
-    float acc = 0.f;
-    if (n < N) {
+  // LayerNorm path: one float4 of the row per thread (blockDim.x == N / 4): 128-bit gathers, the row never leaves registers
+  const int t = threadIdx.x, nw = (blockDim.x + 31) >> 5;
+  const float4* W4 = reinterpret_cast<const float4*>(WT);
+  const int n4 = N >> 2;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-      for (int g = 0; g < S; ++g) acc += __ldg(WT + ((long long)g * K + idx[g]) * N + n);
-      for (int a = 0; a < A; ++a) acc = fmaf(av[a], __ldg(WT + ((long long)S * K + a) * N + n), acc);
-      if (pre) pre[m * ldpre + n] = acc;
-    }
-    v[i] = acc;
-    s += acc;
+  for (int g = 0; g < S; ++g) {
+    const float4 w = __ldg(W4 + ((long long)g * K + idx[g]) * n4 + t);
+    acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
   }
+  for (int a = 0; a < A; ++a) {
+    const float4 w = __ldg(W4 + ((long long)S * K + a) * n4 + t);
+    acc.x = fmaf(av[a], w.x, acc.x); acc.y = fmaf(av[a], w.y, acc.y); acc.z = fmaf(av[a], w.z, acc.z); acc.w = fmaf(av[a], w.w, acc.w);
+  }
+  if (pre) *reinterpret_cast<float4*>(pre + m * ldpre + 4 * t) = acc;
   auto block_sum = [&](float x) {
     x = warp_sum(x);
     __syncthreads();
     if (lane == 0) red[warp] = x;
     __syncthreads();
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w];
-    return t;
+    float r = 0.f;
+    for (int w = 0; w < nw; ++w) r += red[w];
+    return r;
   };
-  const float mu = block_sum(s) / (float)N;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float d = v[i] - mu;
-    if (threadIdx.x + 256 * i < N) q += d * d;
-  }
-  const float rstd = rsqrtf(block_sum(q) / (float)N + eps);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = threadIdx.x + 256 * i;
-    if (n < N) {
-      const float y = (v[i] - mu) * rstd * gamma[n] + beta[n];
-      out[m * ldo + n] = y / (1.f + expf(-y));
-    }
-  }
+  const float mu = block_sum((acc.x + acc.y) + (acc.z + acc.w)) / (float)N;
+  const float dx = acc.x - mu, dy = acc.y - mu, dz = acc.z - mu, dw = acc.w - mu;
+  const float rstd = rsqrtf(block_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) / (float)N + eps);
+  const float4 gm = reinterpret_cast<const float4*>(gamma)[t], bt = reinterpret_cast<const float4*>(beta)[t];
+  float4 y;
+  y.x = dx * rstd * gm.x + bt.x; y.y = dy * rstd * gm.y + bt.y; y.z = dz * rstd * gm.z + bt.z; y.w = dw * rstd * gm.w + bt.w;
+  y.x = y.x / (1.f + expf(-y.x)); y.y = y.y / (1.f + expf(-y.y)); y.z = y.z / (1.f + expf(-y.z)); y.w = y.w / (1.f + expf(-y.w));
+  *reinterpret_cast<float4*>(out + m * ldo + 4 * t) = y;
 }
 
 }  // namespace
@@ -561,10 +552,13 @@ extern "C" int b200rl_onehot_linear_ln(const float* z, const float* act, const f
                                        int S, int K, int A, int N, long long ldz, long long lda, long long ldo,
                                        cudaStream_t st) {
   RL_CHECK_ARG(z && act && WT && out && gamma && beta, "null pointer");
-  RL_CHECK_ARG(S > 0 && S <= 64 && K > 0 && A >= 0 && A <= 32 && N > 0 && N <= 1024,
-               "bad dims (S <= 64 groups, A <= 32, N <= 1024)");
+  RL_CHECK_ARG(S > 0 && S <= 64 && K > 0 && A >= 0 && A <= 32 && N >= 128 && N <= 1024 && N % 128 == 0,
+               "bad dims (S <= 64 groups, A <= 32, N a multiple of 128 up to 1024)");
+  RL_CHECK_ARG(((reinterpret_cast<uintptr_t>(WT) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                 reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(pre)) & 15) == 0 && ldo % 4 == 0 && ldpre % 4 == 0,
+               "onehot_linear_ln needs 16-byte aligned rows");
   if (M <= 0) return B200RL_OK;
-  onehot_linear_kernel<<<(unsigned)M, 256, 0, st>>>(z, act, WT, out, S, K, A, N, ldz, lda, ldo, gamma, beta, eps, pre, ldpre);
+  onehot_linear_kernel<<<(unsigned)M, N / 4, 0, st>>>(z, act, WT, out, S, K, A, N, ldz, lda, ldo, gamma, beta, eps, pre, ldpre);
   RL_CHECK_LAUNCH();
   return B200RL_OK;
 }

@@ -772,7 +772,8 @@ class DV3Engine:
         ops, Z, R = self.ops, self.Z, self.R
         p = "rssm.recurrent_model."
         Win = self._w(p + "mlp._model.0.weight")
-        fused_x = win_t is not None and hasattr(ops, "onehot_linear_ln") and win_t.shape[1] <= 1024
+        fused_x = (win_t is not None and hasattr(ops, "onehot_linear_ln")
+                   and ops.onehot_linear_ln_supported(win_t, x_act, x_pre if keep else None))
         if fused_x:
             ops.onehot_linear_ln(z, act, win_t, self._w(p + "mlp._model.1.weight"), self._w(p + "mlp._model.1.bias"),
                                  self.eps, x_act, self.S, self.D, pre=x_pre if keep else None)

@@ -648,6 +648,11 @@ class CudaOps:
         self._ck(self.lib.b200rl_onehot_linear(_p(z), _p(act), _p(WT), _p(out), c_ll(M), c_int(groups), c_int(classes),
                                                c_int(A), c_int(N), c_ll(_ld(z)), c_ll(_ld(act)), c_ll(_ld(out)), self._st()))
 
+    def onehot_linear_ln_supported(self, WT, out, pre=None) -> bool:
+        N = WT.shape[1]
+        ok = 128 <= N <= 1024 and N % 128 == 0 and out.data_ptr() % 16 == 0 and _ld(out) % 4 == 0 and WT.data_ptr() % 16 == 0
+        return ok and (pre is None or (pre.data_ptr() % 16 == 0 and _ld(pre) % 4 == 0))
+
     def onehot_linear_ln(self, z, act, WT, gamma, beta, eps: float, out, groups: int, classes: int, pre=None):
         """out = SiLU(LayerNorm(Linear([one-hot z, act]))) in one launch; `pre` (optional) keeps the Linear output."""
         _f32(z, act, WT, gamma, beta, out, pre)
