@@ -676,7 +676,7 @@ def test_gemm_ln_gru_equals_unfused_cell(ops, M, R, Kx):
     assert torch.equal(h2, traj[:, 40:]) and torch.equal(hxg[:, :R], h2)
 
 
-@pytest.mark.parametrize("M,S,D,A,N,keep", [(1024, 32, 32, 2, 512, False), (64, 6, 5, 3, 128, True), (256, 32, 32, 18, 1024, True), (33, 64, 3, 0, 384, True)])
+@pytest.mark.parametrize("M,S,D,A,N,keep", [(1024, 32, 32, 2, 512, False), (64, 6, 5, 3, 128, True), (256, 32, 32, 18, 1024, True), (33, 64, 3, 1, 384, True)])
 def test_onehot_linear_ln_equals_gather_then_layernorm(ops, M, S, D, A, N, keep):
     cu, em = ops
     g = torch.Generator().manual_seed(3)
