@@ -94,6 +94,9 @@ long long b200rl_conv_wgrad_tc_workspace(int NB, int h, int w, int Cs, int Cb);
 int b200rl_conv_wgrad_tc(const float* small_, const float* big, float* dW, float* workspace, int NB, int h, int w,
                          int Cs, int Cb, int accumulate, cudaStream_t stream);
 int b200rl_conv_tc_supported(int mode_up, int NB, int h, int w, int Cs, int Cb);
+/* floats of workspace b200rl_conv_pack writes (16*Cs*Cb; 36*Cs*Cb for ConvTranspose2d layers with 32 output channels, whose
+ * four output-parity classes are computed as one 128-column tile over the 9 shifted input windows) */
+long long b200rl_conv_pack_floats(int mode_up, int Cs, int Cb);
 int b200rl_conv_pack(const float* W, float* Wpacked, int mode_up, int Cs, int Cb, cudaStream_t stream);
 int b200rl_conv_down_tc(const float* big, const float* Wpacked, float* small_, int NB, int h, int w, int Cs, int Cb,
                         cudaStream_t stream);

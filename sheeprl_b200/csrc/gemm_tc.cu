@@ -225,6 +225,12 @@ struct Smem {
 constexpr int CH = 4;
 
 constexpr int MODE_GEMM = 0, MODE_DOWN = 1, MODE_UP = 2;
+// MODE_UP4: ConvTranspose2d forward with all four output parity classes in ONE 128-column tile (Cout == 32): the K loop walks
+// the 9 shifted input windows (dy, dx in {-1, 0, 1}) instead of 4 parities x 4 taps, so every input tile is fetched from L2
+// 9 times instead of 16 (the per-parity launch ran at the L2 -> SM bandwidth: 1.07 GB per call at 1024 x 16x16x64 inputs),
+// the B tile is the parity-major weight [4 * Cout][9 * Cin] with zeros where a (parity, shift) pair does not exist, and the
+// epilogue scatters column group p to output pixel (2y + py, 2x + px).
+constexpr int MODE_UP4 = 3;
 constexpr int GROUP_M = 16;
 struct TileGeo {
   int mode;
@@ -341,8 +347,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else {
           const int tap = kb / geo.chunks, ch = (kb - tap * geo.chunks) * BK;
           int x, y;
-          if (geo.mode == MODE_DOWN) { x = 2 * tx0 - 1 + (tap & 3); y = 2 * ty0 - 1 + (tap >> 2); }
-          else                       { x = tx0 + px - (tap & 1);    y = ty0 + py - (tap >> 1); }
+          if (geo.mode == MODE_DOWN)     { x = 2 * tx0 - 1 + (tap & 3); y = 2 * ty0 - 1 + (tap >> 2); }
+          else if (geo.mode == MODE_UP4) { x = tx0 + (tap % 3) - 1;     y = ty0 + (tap / 3) - 1; }      // tap = shift index
+          else                           { x = tx0 + px - (tap & 1);    y = ty0 + py - (tap >> 1); }
           tma_load_4d(s.a_hi[st], &mapA, &s.full[st], ch, x, y, tn0);
           tma_load_2d(s.b_hi[st], &mapB, &s.full[st], kb * BK, n0 + (geo.mode == MODE_UP ? (int)blockIdx.z * geo.Cout : 0));
         }
@@ -512,6 +519,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       else row_off = (((size_t)n * (2 * geo.h) + (2 * y + py)) * (2 * geo.w) + (2 * x + px)) * (size_t)ldc;
     }
     bool store = true;
+    if (geo.mode == MODE_UP4) {
+      // columns [32p, 32p + 32) of the tile = the Cout = 32 channels of output pixel (2y + (p >> 1), 2x + (p & 1))
+      if (row_ok) {
+        const int r = q * 32 + lane;
+        const int wi = r % geo.bw, hi = (r / geo.bw) % geo.bh, ni = r / (geo.bw * geo.bh);
+        const size_t n = (size_t)(tn0 + ni);
+        const int y = ty0 + hi, x = tx0 + wi;
+#pragma unroll
+        for (int jp = 0; jp < ACC_COLS / 32; ++jp) {
+          const int p = (half * ACC_COLS) / 32 + jp;
+          float* dst = C + ((n * (2 * geo.h) + (2 * y + (p >> 1))) * (2 * geo.w) + (2 * x + (p & 1))) * (size_t)32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(acc[32 * jp + j], acc[32 * jp + j + 1], acc[32 * jp + j + 2], acc[32 * jp + j + 3]);
+            if (bias) { o.x += bias[j]; o.y += bias[j + 1]; o.z += bias[j + 2]; o.w += bias[j + 3]; }
+            *reinterpret_cast<float4*>(dst + j) = o;
+          }
+        }
+      }
+      store = false;
+    }
     if (geo.mode == MODE_GEMM && (geo.ksplits > 1 || geo.force_part)) {
       // ---- deterministic split-K: this split's partial tile goes to the workspace; splitk_reduce_kernel (launched right
       // behind this kernel) sums the partials of every output element in split order — no atomics, bit-reproducible
@@ -704,6 +732,23 @@ __global__ void conv_pack_up_kernel(const float* __restrict__ W, float* __restri
   P[idx] = W[((long long)cs * Cb + cb) * 16 + ky * 4 + kx];
 }
 
+__global__ void conv_pack_up4_kernel(const float* __restrict__ W, float* __restrict__ P, int Cs, int Cb) {
+  // P[parity * Cb + cb][shift * Cs + cs] = W[cs][cb][ky][kx] when output parity (py, px) reads shift (dy, dx) (j = py - dy,
+  // i = px - dx in {0, 1}; ky = (1 - py) + 2j, kx = (1 - px) + 2i), else 0.  shift = (dy + 1) * 3 + (dx + 1).
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 36LL * Cs * Cb) return;
+  const int cs = (int)(idx % Cs);
+  const int shift = (int)((idx / Cs) % 9);
+  const int cb = (int)((idx / (9LL * Cs)) % Cb);
+  const int par = (int)(idx / (9LL * Cs * Cb));
+  const int py = par >> 1, px = par & 1, dy = shift / 3 - 1, dx = shift % 3 - 1;
+  const int j = py - dy, i = px - dx;
+  float v = 0.f;
+  if (j >= 0 && j <= 1 && i >= 0 && i <= 1) v = W[((long long)cs * Cb + cb) * 16 + ((1 - py) + 2 * j) * 4 + (1 - px) + 2 * i];
+  P[idx] = v;
+}
+static bool conv_up_merged(int Cb) { return Cb == 32; }
+
 // Matmul precision of every tensor-core product of the library (process-wide, like torch.set_float32_matmul_precision):
 // 3 = fp32-accurate 3xTF32 (default; what the 1e-4 parity tests run), 1 = single TF32 pass.
 int g_passes = 3;
@@ -796,17 +841,18 @@ int launch_conv(int mode, const float* img, const float* Wp, float* out, const f
   g.passes = g_passes;
   RL_CHECK_ARG(conv_tile(h, w, NB, &g.bw, &g.bh, &g.bn), "image grid not tileable by 128 pixels");
   g.tiles_x = w / g.bw; g.tiles_y = h / g.bh;
-  const int taps = mode == MODE_DOWN ? 16 : 4;
+  if (mode == MODE_UP && conv_up_merged(Cout)) mode = g.mode = MODE_UP4;
+  const int taps = mode == MODE_DOWN ? 16 : (mode == MODE_UP4 ? 9 : 4);
   const int K = taps * Cin;
   CUtensorMap ma, mb;
   if (mode == MODE_DOWN) { if (int rc = get_map4(img, Cin, 2 * w, 2 * h, NB, g.bw, g.bh, g.bn, 2, &ma)) return rc; }
   else                   { if (int rc = get_map4(img, Cin, w, h, NB, g.bw, g.bh, g.bn, 1, &ma)) return rc; }
-  const int BN = (Cout <= 64) ? 64 : 128;
-  const int brows = mode == MODE_UP ? 4 * Cout : Cout;
+  const int BN = (mode == MODE_UP4) ? 128 : ((Cout <= 64) ? 64 : 128);
+  const int brows = (mode == MODE_UP || mode == MODE_UP4) ? 4 * Cout : Cout;
   if (int rc = get_map(Wp, brows, K, K, BN, &mb)) return rc;
   const int mtiles = g.tiles_x * g.tiles_y * (NB / g.bn);
   g.mtiles = mtiles;
-  g.ntiles = (Cout + BN - 1) / BN;
+  g.ntiles = (mode == MODE_UP4) ? 1 : (Cout + BN - 1) / BN;
   dim3 grid(1, 1, mode == MODE_UP ? 4 : 1);
   grid.y = persistent_grid_y(mtiles * g.ntiles, grid.z);
   const int M = NB * h * w;  // unused by conv addressing; row validity comes from geo
@@ -824,7 +870,11 @@ extern "C" int b200rl_set_matmul_precision(int tf32_passes) {
 }
 extern "C" int b200rl_get_matmul_precision(void) { return g_passes; }
 
-// ---- convolution entry points (tensor-core implicit GEMM).  Wpacked: 16*Cs*Cb floats of caller workspace.
+// ---- convolution entry points (tensor-core implicit GEMM).  Wpacked: caller workspace of b200rl_conv_pack_floats() floats
+// (16*Cs*Cb; 36*Cs*Cb for the merged-parity ConvTranspose2d layout used when Cb == 32).
+extern "C" long long b200rl_conv_pack_floats(int mode_up, int Cs, int Cb) {
+  return (mode_up && conv_up_merged(Cb) ? 36LL : 16LL) * Cs * Cb;
+}
 extern "C" int b200rl_conv_tc_supported(int mode_up, int NB, int h, int w, int Cs, int Cb) {
   int bw, bh, bn;
   if (!conv_tile(h, w, NB, &bw, &bh, &bn)) return 0;
@@ -835,7 +885,8 @@ extern "C" int b200rl_conv_tc_supported(int mode_up, int NB, int h, int w, int C
 extern "C" int b200rl_conv_pack(const float* W, float* Wpacked, int mode_up, int Cs, int Cb, cudaStream_t st) {
   RL_CHECK_ARG(W && Wpacked, "null pointer");
   const long long n = (long long)Cs * Cb * 16;
-  if (mode_up) conv_pack_up_kernel<<<ceil_div(n, 256), 256, 0, st>>>(W, Wpacked, Cs, Cb);
+  if (mode_up && conv_up_merged(Cb)) conv_pack_up4_kernel<<<ceil_div(36LL * Cs * Cb, 256), 256, 0, st>>>(W, Wpacked, Cs, Cb);
+  else if (mode_up) conv_pack_up_kernel<<<ceil_div(n, 256), 256, 0, st>>>(W, Wpacked, Cs, Cb);
   else conv_pack_down_kernel<<<ceil_div(n, 256), 256, 0, st>>>(W, Wpacked, Cs, Cb);
   RL_CHECK_LAUNCH();
   return B200RL_OK;

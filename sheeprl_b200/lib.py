@@ -225,8 +225,10 @@ class CudaOps:
         use because the optimiser rewrites W each step; 16*Cs*Cb floats, a few microseconds)."""
         key = (W.data_ptr(), mode_up)
         buf = self._pack_bufs.get(key)
-        if buf is None or buf.numel() != W.numel():
-            buf = torch.empty(W.numel(), dtype=torch.float32, device=W.device)
+        self.lib.b200rl_conv_pack_floats.restype = c_ll
+        need = int(self.lib.b200rl_conv_pack_floats(c_int(mode_up), c_int(Cs), c_int(Cb)))
+        if buf is None or buf.numel() != need:
+            buf = torch.empty(need, dtype=torch.float32, device=W.device)
             self._pack_bufs[key] = buf
         self._ck(self.lib.b200rl_conv_pack(_p(W), _p(buf), c_int(mode_up), c_int(Cs), c_int(Cb), self._st()))
         return buf
