@@ -386,36 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t acc = tmem + (uint32_t)(buf * BN);
       const uint64_t dbh0 = dbh_base + (uint64_t)st * STAGE_STEP, dbl0 = dbl_base + (uint64_t)st * STAGE_STEP;
       const uint32_t ta_hi = tmem + A_TMEM0 + 64u * (uint32_t)st, ta_lo = ta_hi + 32u;
-      if (leader && geo.mode == MODE_UP4 && !chunk_start) {
-        // merged-parity ConvTranspose2d: shift (dy, dx) only feeds the parities p = py*2+px with py - dy, px - dx in {0, 1};
-        // their 32-column groups form one or two contiguous segments (the zero rows of the packed weight are skipped).  The
-        // k-block that opens a TMEM chunk runs at full width below: its first MMA must overwrite all 128 columns.
-        const int shift = kb / geo.chunks, sy = shift / 3, sx = shift % 3;
-        // rows (dy): -1 -> py = 0, 0 -> both, +1 -> py = 1; same for columns
-        const int py0 = (sy == 2) ? 1 : 0, npy = (sy == 1) ? 2 : 1, px0 = (sx == 2) ? 1 : 0, npx = (sx == 1) ? 2 : 1;
-        // segments in units of 32 columns: npx == 2 -> (py*2, 2 groups) per py, merged when npy == 2; npx == 1 -> one group per py
-        int seg_col[2], seg_n[2], nseg;
-        if (npx == 2) { nseg = 1; seg_col[0] = py0 * 2; seg_n[0] = 2 * npy; }
-        else { nseg = npy; seg_col[0] = py0 * 2 + px0; seg_n[0] = 1; seg_col[1] = (py0 + 1) * 2 + px0; seg_n[1] = 1; }
-        for (int sg = 0; sg < nseg; ++sg) {
-          const uint32_t ncols = 32u * (uint32_t)seg_n[sg], c0 = 32u * (uint32_t)seg_col[sg];
-          const uint32_t idn = (idesc & ~(0x3fu << 17)) | ((ncols >> 3) << 17);
-          const uint64_t rb = (uint64_t)(c0 * BK * sizeof(float)) >> 4;      // B rows c0.. : 128 B per row, whole swizzle atoms
-#pragma unroll
-          for (int k4 = 0; k4 < BK / 8; ++k4) {
-            const uint64_t ob = (uint64_t)k4 * b_step + rb;
-            if (PASSES == 3) {
-              umma_tf32_ts(acc + c0, ta_hi + 8u * k4, dbl0 + ob, idn, 1);
-              umma_tf32_ts(acc + c0, ta_lo + 8u * k4, dbh0 + ob, idn, 1);
-              umma_tf32_ts(acc + c0, ta_hi + 8u * k4, dbh0 + ob, idn, 1);
-            } else {
-              umma_tf32_ts(acc + c0, ta_hi + 8u * k4, dbh0 + ob, idn, 1);
-            }
-          }
-        }
-        umma_commit(&s.empty[st]);
-        if ((kb % CH) == CH - 1 || kb == nkb - 1) umma_commit(&s.tfull[buf]);
-      } else if (leader) {
+      if (leader) {
 #pragma unroll
         for (int k4 = 0; k4 < BK / 8; ++k4) {
           const uint64_t ob = (uint64_t)k4 * b_step;
