@@ -333,7 +333,7 @@ def run_b200(args):
     # GEMM over the imagined trajectories: M=(H+1)*T*B, N=dense_units, K=latent) / its mean launch duration, measured
     # here with CUDA events on the launching stream; operands exceed the 126 MB L2.
     tot_ms = sum(v[0] for v in breakdown.values()) or 1.0
-    tc_ops = ("gemm", "conv_down", "conv_up", "conv_wgrad")
+    tc_ops = ("gemm", "gemm_ln_act", "gemm_ln_gru", "conv_down", "conv_up", "conv_wgrad")
     share = sum(breakdown[k][0] for k in tc_ops if k in breakdown) / tot_ms
     gm, gn, gk = (eng.H + 1) * eng.N, eng.du, eng.L
     ga = torch.randn(gm, gk, device=dev)
