@@ -795,6 +795,7 @@ splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, cons
   const int m = (int)(idx / n4), n = (int)(idx - (long long)m * n4) * 4;
   const float* p = part + (size_t)m * ldw + n;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4                                    // the splits' loads in flight together; the adds keep split order
   for (int z = 0; z < ks; ++z) {
     const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (size_t)z * mpad * ldw));
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -997,6 +998,7 @@ splitk_ln_kernel(const float* __restrict__ part, int ks, int mpad, int ldw, int 
   float4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4                                    // the splits' loads in flight together; the adds keep split order
   for (int z = 0; z < ks; ++z) {
     const float4* p = reinterpret_cast<const float4*>(part + ((size_t)z * mpad + row) * ldw);
 #pragma unroll
