@@ -28,9 +28,8 @@
 //     runs while the x rows are still being built; input prefetches at step start).
 //   * z_{t-1} is one-hot per group, so z W_in^T is a gather of S weights per output from the CTA's W_in slice; the x
 //     LayerNorm runs on partial statistics exchanged with the values (like the GRU's), no CTA is a serial row owner.
-//   * Products: a warp takes a (4-column group) x (K slice) item: 16 rows x 4 columns of accumulators per lane,
-//     128-bit shared loads along K, a 62-shuffle reduce-scatter; K-slice partials are summed in a fixed order
-//     (bit-reproducible).  The 32 classes of a categorical sit on the 32 lanes of a warp.
+//   * Products: the batch is one MMA tile high, so a warp takes an (8-column tile) x (K slice) item of m16n8k8 TF32 MMAs
+//     with the 3xTF32 split (fp32-accurate); K-slice partials are summed in a fixed order (bit-reproducible).
 #include "b200rl.h"
 #include "common.cuh"
 
@@ -42,7 +41,6 @@ constexpr int SCAN_NT = 512;   // threads per CTA: the scan is latency-bound (nc
 constexpr int SCAN_NW = SCAN_NT / 32;
 constexpr int MAXB = 16;
 constexpr int MAXRPU = 8;      // rows of one sampling unit (S <= 64 groups over 128 CTAs -> >= 2 row splits)
-constexpr int NRB = 4;         // rows of one product item (4 rows x 4 columns of packed accumulators per lane)
 constexpr int KS_MAX = 8;      // K slices of a product (rows of the partial buffer)
 constexpr int CLS_SLICES = 8;  // K slices of the class-per-lane products (logits / dz)
 
@@ -220,62 +218,6 @@ __device__ __forceinline__ Slot make_slot(int e, int per_row, int B, int cta, in
 
 // fast transcendental form for SiLU; rel. error ~1e-6
 __device__ __forceinline__ float fsilu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
-
-// Packed fp32 FMA (Blackwell FFMA2): two independent fp32 fused multiply-adds per instruction on 64-bit register pairs.
-__device__ __forceinline__ void fma2(u64& acc, u64 x, u64 w) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(x), "l"(w));
-}
-__device__ __forceinline__ float pair_sum(u64 v) {
-  return __uint_as_float((unsigned)v) + __uint_as_float((unsigned)(v >> 32));
-}
-
-// 16 values per lane, summed across the 32 lanes: 16 shuffles; the total of value `idx` (returned) ends up in both lanes
-// of a pair (lane, lane ^ 1) as v[0].
-__device__ __forceinline__ int reduce16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int off = 16, n = 16; off >= 2; off >>= 1, n >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float lo = v[i], hi = v[i + n / 2];
-      const float send = upper ? lo : hi;
-      const float keep = upper ? hi : lo;
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
-
-// part[r0 + b][c0 + j] = sum_{k in [k0,k1)} X[r0 + b][k] * W_j[k] for NRB rows and the 4 columns (weight rows w + j*wst).
-// X: smem rows of stride xs (xs % 4 == 0, zero padded); weight rows in smem (stride wst % 4 == 0, zero padded);
-// k0, k1 multiples of 4.  One warp; a lane handles 4 consecutive k per 128-wide sweep (LDS.128); every accumulator is a
-// packed pair (even-k partial, odd-k partial) fed by FFMA2.
-__device__ __forceinline__ void warp_item(const float* __restrict__ X, int xs, const float* __restrict__ w, int wst,
-                                          int k0, int k1, float* part, int ldp, int r0, int c0, int lane) {
-  u64 acc[NRB * 4];
-#pragma unroll
-  for (int i = 0; i < NRB * 4; ++i) acc[i] = 0ull;
-  for (int k = k0 + 4 * lane; k < k1; k += 128) {
-    ulonglong2 a[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = *reinterpret_cast<const ulonglong2*>(w + j * wst + k);
-#pragma unroll
-    for (int b = 0; b < NRB; ++b) {
-      const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(X + (r0 + b) * xs + k);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        fma2(acc[b * 4 + j], x.x, a[j].x);
-        fma2(acc[b * 4 + j], x.y, a[j].y);
-      }
-    }
-  }
-  float v[NRB * 4];
-#pragma unroll
-  for (int i = 0; i < NRB * 4; ++i) v[i] = pair_sum(acc[i]);
-  const int idx = reduce16(v, lane);
-  if ((lane & 1) == 0) part[(r0 + (idx >> 2)) * ldp + c0 + (idx & 3)] = v[0];
-}
 
 // ---- products on the warp-level tensor-core path -------------------------------------------------------------------
 // The batch is exactly one MMA tile high (B <= 16 rows), so a product is a row of m16n8k8 TF32 MMAs per 8 output columns.
