@@ -231,12 +231,12 @@ __device__ __forceinline__ float lo32(u64 v) { return __uint_as_float((unsigned)
 __device__ __forceinline__ float hi32(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
 
 // down_thin: Conv2d(3 -> CS, k4 s2 p1) on [NB][2h][64][3] -> [NB][h][32][CS]  (CNNEncoder first layer, agent.py:78-91; also
-// the input-gradient pass of the decoder's last ConvTranspose2d).  Lane x of a warp owns output pixels (y, x) and (y+1, x):
-// per patch element k = (ky, kx, cb) two staged inputs and 8 weight LDS.128 feed 32 packed FMAs (32 channels x 2 pixels).
-// Staged rows: [6 rows][3 ch][column parity][33] so that lane x reads column 2x-1+kx at slot x + (kx >> 1) of plane kx & 1.
+// the input-gradient pass of the decoder's last ConvTranspose2d).  A warp owns two output rows (64 pixels) x 32 channels.
+// Staged rows: [6 rows][3 ch][column parity][33] so that output column x reads input column 2x-1+kx at slot x + (kx >> 1) of
+// plane kx & 1 (conflict-free, no index arithmetic per element).
 constexpr int DT_PLANE = 33, DT_ROWF = 3 * 2 * DT_PLANE, DT_STAGE = 6 * DT_ROWF;
 template <int CS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 conv_down_thin_kernel(const float* __restrict__ big, const float* __restrict__ W, float* __restrict__ small_, int NB, int h) {
   extern __shared__ __align__(16) float sm[];
   float* Wk = sm;                                  // [48][CS], k = (ky*4+kx)*3 + cb
@@ -272,34 +272,42 @@ conv_down_thin_kernel(const float* __restrict__ big, const float* __restrict__ W
     }
     __syncwarp();
     const bool two = y0 + 1 < h;
+    // lane = (pixel group pg = lane >> 2: columns 4pg .. 4pg+3 of both rows, channel octet cg = lane & 3): 8 pixels x 8
+    // channels of packed accumulators.  Per patch element a lane loads 8 inputs (LDS.32, shared by the 4 lanes of a pixel
+    // group) and 8 weights (2 LDS.128, shared by the 8 lanes of an octet): 16 words for 64 FMAs (the lane-per-pixel mapping
+    // loaded 34 for 64 and sat on the shared-memory return path).
+    const int pg = lane >> 2, cg = lane & 3;
 #pragma unroll 1
     for (int c0 = 0; c0 < CS; c0 += 32) {
-      u64 acc0[16], acc1[16];
+      u64 acc[8][4];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) { acc0[q] = 0ull; acc1[q] = 0ull; }
+      for (int p = 0; p < 8; ++p)
 #pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = 0ull;
+#pragma unroll 1
       for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 4; ++kx)
 #pragma unroll
           for (int cb = 0; cb < 3; ++cb) {
-            const int off = (cb * 2 + (kx & 1)) * DT_PLANE + lane + (kx >> 1);
-            const u64 x0 = dup2(stg[ky * DT_ROWF + off]), x1 = dup2(stg[(ky + 2) * DT_ROWF + off]);
-            const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(Wk + ((ky * 4 + kx) * 3 + cb) * CS + c0);
+            const int off = (cb * 2 + (kx & 1)) * DT_PLANE + 4 * pg + (kx >> 1);
+            const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(Wk + ((ky * 4 + kx) * 3 + cb) * CS + c0 + cg * 8);
+            const ulonglong2 w0 = wp[0], w1 = wp[1];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const ulonglong2 wv = wp[q];
-              fma2(acc0[2 * q], x0, wv.x); fma2(acc0[2 * q + 1], x0, wv.y);
-              fma2(acc1[2 * q], x1, wv.x); fma2(acc1[2 * q + 1], x1, wv.y);
+            for (int j = 0; j < 4; ++j) {
+              const u64 x0 = dup2(stg[ky * DT_ROWF + off + j]), x1 = dup2(stg[(ky + 2) * DT_ROWF + off + j]);
+              fma2(acc[j][0], x0, w0.x); fma2(acc[j][1], x0, w0.y); fma2(acc[j][2], x0, w1.x); fma2(acc[j][3], x0, w1.y);
+              fma2(acc[4 + j][0], x1, w0.x); fma2(acc[4 + j][1], x1, w0.y); fma2(acc[4 + j][2], x1, w1.x); fma2(acc[4 + j][3], x1, w1.y);
             }
           }
-      float4* o0 = reinterpret_cast<float4*>(small_ + ((n * h + y0) * 32 + lane) * (long long)CS + c0);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) o0[q] = make_float4(lo32(acc0[2 * q]), hi32(acc0[2 * q]), lo32(acc0[2 * q + 1]), hi32(acc0[2 * q + 1]));
-      if (two) {
-        float4* o1 = reinterpret_cast<float4*>(small_ + ((n * h + y0 + 1) * 32 + lane) * (long long)CS + c0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) o1[q] = make_float4(lo32(acc1[2 * q]), hi32(acc1[2 * q]), lo32(acc1[2 * q + 1]), hi32(acc1[2 * q + 1]));
+      for (int p = 0; p < 8; ++p) {
+        const int row = y0 + (p >> 2), x = 4 * pg + (p & 3);
+        if (row < h && (two || p < 4)) {
+          float4* o = reinterpret_cast<float4*>(small_ + ((n * h + row) * 32 + x) * (long long)CS + c0 + cg * 8);
+          o[0] = make_float4(lo32(acc[p][0]), hi32(acc[p][0]), lo32(acc[p][1]), hi32(acc[p][1]));
+          o[1] = make_float4(lo32(acc[p][2]), hi32(acc[p][2]), lo32(acc[p][3]), hi32(acc[p][3]));
+        }
       }
     }
   }
