@@ -511,11 +511,7 @@ int b200rl_conv_down_thin(const float* big, const float* W, float* small, int NB
   const size_t smem = sizeof(float) * (48 * Cs + 4 * DT_STAGE);
 #define DOWN_THIN(CS_)                                                                                               \
   do {                                                                                                               \
-    static bool attr_set = false;                                                                                    \
-    if (!attr_set) {                                                                                                 \
-      RL_CUDA(cudaFuncSetAttribute(conv_down_thin_kernel<CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_set = true;                                                                                               \
-    }                                                                                                                \
+    RL_CUDA(cudaFuncSetAttribute(conv_down_thin_kernel<CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     conv_down_thin_kernel<CS_><<<(unsigned)blocks, 128, smem, st>>>(big, W, small, NB, h);                         \
   } while (0)
   if (Cs == 32) DOWN_THIN(32); else if (Cs == 64) DOWN_THIN(64); else DOWN_THIN(96);
@@ -532,11 +528,7 @@ int b200rl_conv_up_thin(const float* small, const float* W, float* big, const fl
     const size_t smem = sizeof(float) * (108 * Cs + UT_STAGE);
 #define UP_THIN2(CS_)                                                                                                \
   do {                                                                                                               \
-    static bool attr_set = false;                                                                                    \
-    if (!attr_set) {                                                                                                 \
-      RL_CUDA(cudaFuncSetAttribute(conv_up_thin2_kernel<CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_set = true;                                                                                               \
-    }                                                                                                                \
+    RL_CUDA(cudaFuncSetAttribute(conv_up_thin2_kernel<CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     conv_up_thin2_kernel<CS_><<<(unsigned)blocks, 128, smem, st>>>(small, W, bias, big, NB, h);                    \
   } while (0)
     if (Cs == 32) UP_THIN2(32); else if (Cs == 64) UP_THIN2(64); else UP_THIN2(96);

@@ -188,6 +188,31 @@ static bool tc_enabled() {
   return v == 1;
 }
 
+// Rank-K update for tiny K (input gradient of a policy head with a handful of actions: [rows, A] x [A, hidden]):
+// C[m, n..n+3] (+)= bias + sum_k A[m, k] * B[k, n..n+3], one float4 of C per thread, B rows through the read-only cache.
+// The tiled kernels below spend a whole 16-deep k-step on K = 2.
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+rank_k_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, const float* __restrict__ bias,
+                 int M, int N, int K, int lda, int ldb, int ldc, int accumulate) {
+  const int n4 = N >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * n4) return;
+  const int m = (int)(idx / n4), c = (int)(idx - (long long)m * n4);
+  float4 acc = bias ? reinterpret_cast<const float4*>(bias)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K) {
+      const float a = __ldg(A + (size_t)m * lda + k);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(B + (size_t)k * ldb) + c);
+      acc.x = fmaf(a, b.x, acc.x); acc.y = fmaf(a, b.y, acc.y); acc.z = fmaf(a, b.z, acc.z); acc.w = fmaf(a, b.w, acc.w);
+    }
+  }
+  float4* out = reinterpret_cast<float4*>(C + (size_t)m * ldc) + c;
+  if (accumulate) { const float4 o = *out; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+  *out = acc;
+}
+
 // include/b200rl.h: b200rl_gemm_f32.  Large NT products go to the tcgen05 3xTF32 kernel (gemm_tc.cu); everything
 // else (skinny, transposed, unaligned) runs on the exact-fp32 FFMA kernels below.
 extern "C" int b200rl_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K,
@@ -206,6 +231,12 @@ extern "C" int b200rl_gemm_f32(const float* A, const float* B, float* C, const f
   }
   if (tc_enabled() && b200rl_gemm_tc_supported(A, B, M, N, K, lda, ldb, transA, transB))
     return b200rl_gemm_tc(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, accumulate, st);
+  if (!transA && !transB && K <= 8 && M >= 1024 && (N & 3) == 0 && (ldb & 3) == 0 && (ldc & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0) {
+    rank_k_nn_kernel<8><<<ceil_div((long long)M * (N >> 2), 256), 256, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, accumulate);
+    RL_CHECK_LAUNCH();
+    return B200RL_OK;
+  }
   if (M <= 32) return launch_cfg<16, 64, 32, 1, 8>(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, accumulate, st);
   if (N <= 32) return launch_cfg<128, 32, 16, 8, 2>(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, accumulate, st);
   if (M <= 64 || N <= 64)

@@ -54,6 +54,8 @@ GEMM_SHAPES = [
     (257, 129, 100, True, False), (300, 200, 68, False, False), (129, 52, 36, True, True), (1024, 1024, 1026, True, False),
     # fewer rows than one 128-row tile (the 64-row products of the per-step scan at the XL width): forward, dX, dW
     (64, 3072, 1280, False, True), (64, 1280, 3072, False, False), (3072, 1280, 64, True, False), (40, 512, 512, False, True),
+    # tiny K, many rows, NN (input gradient of a policy head): rank-K kernel
+    (15360, 512, 2, False, False), (2048, 64, 7, False, False), (1024, 128, 8, False, False),
 ]
 
 
