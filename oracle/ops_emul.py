@@ -525,6 +525,58 @@ class EmulOps:
         Z = groups * classes
         out.copy_(z @ WT[:Z] + act @ WT[Z:])
 
+    # ---- fused imagination ops: exact compositions of the ops above (b200rl_gemm_ln, b200rl_onehot_linear_ln,
+    # b200rl_head_sample); having them here lets the CPU engine tests walk the same fused schedule as the GPU
+    def gemm_ln_supported(self, A: Tensor, W: Tensor, mode: int = 0) -> bool:
+        N = W.shape[0]
+        return A.shape[0] >= 32 and N % 4 == 0 and N <= 1536 and (mode == 0 or N % 384 == 0)
+
+    def gemm_ln_act(self, A: Tensor, W: Tensor, gamma: Tensor, beta: Tensor, eps: float, act: int, out: Tensor,
+                    pre: Optional[Tensor] = None):
+        tmp = torch.empty(A.shape[0], W.shape[0])
+        self.gemm(A, W, tmp, False, True)
+        if pre is not None:
+            pre.copy_(tmp)
+        self.ln_act_fwd(tmp, gamma, beta, eps, act, out)
+
+    def gemm_ln_gru(self, A: Tensor, W: Tensor, gamma: Tensor, beta: Tensor, eps: float, h_prev: Tensor, h_out: Tensor,
+                    h_out2: Optional[Tensor] = None, g_pre: Optional[Tensor] = None, g_ln: Optional[Tensor] = None):
+        """h_out2 may alias the left half of A (the next step's [h | x] buffer): everything is computed before it is written."""
+        tmp = torch.empty(A.shape[0], W.shape[0])
+        self.gemm(A, W, tmp, False, True)
+        ln = torch.empty_like(tmp)
+        self.ln_act_fwd(tmp, gamma, beta, eps, ACT_NONE, ln)
+        h = torch.empty(A.shape[0], W.shape[0] // 3)
+        self.gru_gate_fwd(ln, h_prev, h)
+        if g_pre is not None:
+            g_pre.copy_(tmp)
+        if g_ln is not None:
+            g_ln.copy_(ln)
+        h_out.copy_(h)
+        if h_out2 is not None:
+            h_out2.copy_(h)
+
+    def onehot_linear_ln_supported(self, WT: Tensor, out: Tensor, pre: Optional[Tensor] = None) -> bool:
+        return 128 <= WT.shape[1] <= 1024 and WT.shape[1] % 128 == 0
+
+    def onehot_linear_ln(self, z: Tensor, act: Tensor, WT: Tensor, gamma: Tensor, beta: Tensor, eps: float, out: Tensor,
+                         groups: int, classes: int, pre: Optional[Tensor] = None):
+        tmp = torch.empty(z.shape[0], WT.shape[1])
+        self.onehot_linear(z, act, WT, tmp, groups, classes)
+        if pre is not None:
+            pre.copy_(tmp)
+        self.ln_act_fwd(tmp, gamma, beta, eps, ACT_SILU, out)
+
+    def head_sample_supported(self, X: Tensor, W: Tensor) -> bool:
+        return W.shape[0] <= 32 and X.shape[1] <= 1024 and X.shape[1] % 4 == 0
+
+    def head_sample(self, X: Tensor, W: Tensor, bias: Optional[Tensor], noise: Optional[Tensor], unimix: float, raw: Tensor,
+                    onehot: Tensor):
+        tmp = torch.empty(X.shape[0], W.shape[0])
+        self.gemm(X, W, tmp, False, True, bias=bias)
+        raw.copy_(tmp)
+        self.cat_sample(tmp, noise, unimix, 1, W.shape[0], onehot)
+
     # ---- Dreamer-V3 continuous actions (csrc/dv3_cont.cu)
     def cont_action_fwd(self, head, eps, action, ent, min_std, max_std, init_std, clip):
         A = eps.shape[1]
